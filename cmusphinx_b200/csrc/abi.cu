@@ -1,0 +1,728 @@
+// abi.cu -- the extern "C" surface of libb200sphinx.so (device side).
+//
+// Owns the device-resident models, scratch and streams; every scoring entry
+// point ends in sm_100a kernel launches (gmm_exact.cu, mahal_tc.cu,
+// hmm_kernels.cu).  There is no host fallback: without a CUDA device the
+// constructors fail and say so.
+#include "gmm_dev.cuh"
+#include "hmm_dev.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+namespace b200 {
+std::atomic<long long> g_launches{0};
+}
+using namespace b200;
+
+namespace {
+
+template <typename T>
+int dev_alloc_copy(T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) return B200_OK;
+    B200_CUDA_OK(cudaMalloc((void **)dst, n * sizeof(T)));
+    if (src) B200_CUDA_OK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+constexpr size_t kListScratchBytes = (size_t)256 << 20;
+constexpr int kHostChunkFrames = 8192;
+
+}  // namespace
+
+struct b200_mgau {
+    int kind = 0;  // 0 ms, 1 ptm, 2 s2_semi
+    b200_mgau_cfg_t cfg{};
+    GmmDev g{};
+    int device = 0;
+    bool cont = false;  // ms with identity senone->codebook map
+    int path = 0;
+    TcPlan *tc = nullptr;
+    float *d_mean = nullptr, *d_var = nullptr, *d_det = nullptr;
+    uint8_t *d_mixw = nullptr, *d_sen2cb = nullptr;
+    uint32_t *d_sen2mgau = nullptr;
+    size_t n_param = 0, n_det = 0;
+    // scratch
+    int2 *d_lists = nullptr; size_t lists_cap = 0;  // bytes
+    float *d_feat[2] = {nullptr, nullptr}; int16_t *d_out[2] = {nullptr, nullptr};
+    size_t feat_cap[2] = {0, 0}, out_cap[2] = {0, 0};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    // per-frame / utterance cache
+    float *d_ufeat = nullptr; size_t ufeat_cap = 0;
+    int16_t *d_uraw = nullptr; size_t uraw_cap = 0;
+    int2 *d_ulists = nullptr; size_t ulists_cap = 0;
+    int utt_T = 0;
+    uint8_t *d_active = nullptr; size_t active_cap = 0;
+    int16_t *d_row = nullptr;
+    int16_t *h_row = nullptr;   // pinned
+    float *h_frame = nullptr;   // pinned, one frame of features
+};
+
+namespace {
+
+int ensure(void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes) return B200_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    B200_CUDA_OK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return B200_OK;
+}
+
+size_t list_bytes_per_frame(const b200_mgau *m) {
+    return (size_t)m->g.n_mgau * m->g.n_feat * m->g.topn * sizeof(int2);
+}
+
+int frames_per_list_chunk(const b200_mgau *m) {
+    size_t per = list_bytes_per_frame(m);
+    size_t n = kListScratchBytes / (per ? per : 1);
+    if (n < 128) n = 128;
+    if (n > 32768) n = 32768;
+    return (int)n;
+}
+
+b200_mgau *mgau_common(int kind, const b200_mgau_cfg_t *cfg, const float *mean, const float *var,
+                       const float *det) {
+    if (!cfg || !mean || !var || !det) { set_error("null argument"); return nullptr; }
+    if (cfg->n_feat < 1 || cfg->n_feat > B200_MAX_STREAMS) { set_error("n_feat %d unsupported (1..%d)", cfg->n_feat, B200_MAX_STREAMS); return nullptr; }
+    if (cfg->topn < 1 || cfg->topn > B200_MAX_TOPN) { set_error("topn %d unsupported (1..%d)", cfg->topn, B200_MAX_TOPN); return nullptr; }
+    if (cfg->topn > cfg->n_density) { set_error("topn %d > n_density %d", cfg->topn, cfg->n_density); return nullptr; }
+    if (cfg->ds_ratio > 1) { set_error("-ds %d: frame down-sampling is not supported on the device path", cfg->ds_ratio); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libb200sphinx has no CPU fallback");
+        return nullptr;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("bad device %d", cfg->device); return nullptr; }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    b200_mgau *m = new (std::nothrow) b200_mgau();
+    if (!m) return nullptr;
+    m->kind = kind; m->cfg = *cfg; m->device = cfg->device;
+    GmmDev &g = m->g;
+    g.n_mgau = cfg->n_mgau; g.n_feat = cfg->n_feat; g.n_density = cfg->n_density; g.n_sen = cfg->n_sen;
+    g.topn = cfg->topn; g.aw = cfg->aw > 0 ? cfg->aw : 1;
+    g.veclen = 0; g.maxlen = 0;
+    for (int f = 0; f < cfg->n_feat; ++f) {
+        g.featlen[f] = cfg->featlen[f]; g.featoff[f] = g.veclen;
+        g.veclen += cfg->featlen[f]; g.maxlen = std::max(g.maxlen, cfg->featlen[f]);
+    }
+    m->n_param = (size_t)g.n_mgau * g.n_density * g.veclen;
+    m->n_det = (size_t)g.n_mgau * g.n_feat * g.n_density;
+    uint32_t tab[256];
+    LogMath lm(cfg->logbase, kShift, true);
+    if (lm.width != 1) { set_error("log base %f too small for an 8-bit add table", cfg->logbase); delete m; return nullptr; }
+    for (int i = 0; i < 256; ++i) g.logadd[i] = (uint8_t)(i < (int)lm.table.size() ? lm.table[i] : 0);
+    (void)tab;
+    if (dev_alloc_copy(&m->d_mean, mean, m->n_param) || dev_alloc_copy(&m->d_var, var, m->n_param) ||
+        dev_alloc_copy(&m->d_det, det, m->n_det)) { b200_mgau_free(m); return nullptr; }
+    g.mean = m->d_mean; g.var = m->d_var; g.det = m->d_det;
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithFlags(&m->st[i], cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); b200_mgau_free(m); return nullptr; }
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreate(&m->ev[i]) != cudaSuccess) { set_error("event create failed"); b200_mgau_free(m); return nullptr; }
+    if (cudaMalloc((void **)&m->d_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
+        cudaMallocHost((void **)&m->h_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
+        cudaMallocHost((void **)&m->h_frame, (size_t)g.veclen * 4 + 16) != cudaSuccess) {
+        set_error("row buffers alloc failed"); b200_mgau_free(m); return nullptr;
+    }
+    return m;
+}
+
+// Dense un-normalised (ms, normalize=false) or final scores for frames [0,T)
+// of d_feat.  Events: ev0 start, ev1 after operand prep (tensor-core path
+// only), ev2 after the scoring kernels, ev3 after normalisation.
+int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cudaStream_t st,
+                    bool normalize, bool timed) {
+    const GmmDev &g = m->g;
+    if (T <= 0) return B200_OK;
+    int rc;
+    if (timed) cudaEventRecord(m->ev[0], st);
+    if (m->kind == 0 && m->path == 1 && m->tc) {
+        if ((rc = tc_score(m->tc, g, d_feat, T, d_out, st, timed ? &m->ev[1] : nullptr))) return rc;
+    } else {
+        if (timed) cudaEventRecord(m->ev[1], st);
+        if (m->kind == 0 && m->cont) {
+            for (int t0 = 0; t0 < T; t0 += 65535 * 128) {   // grid.y limit
+                int tn = std::min(T - t0, 65535 * 128);
+                if ((rc = gmm_launch_topn(g, 0, d_feat, T, t0, tn, nullptr, d_out, 1, st))) return rc;
+            }
+        } else {
+            const int chunk = frames_per_list_chunk(m);
+            if ((rc = ensure((void **)&m->d_lists, &m->lists_cap, (size_t)chunk * list_bytes_per_frame(m)))) return rc;
+            for (int t0 = 0; t0 < T; t0 += chunk) {
+                int tn = std::min(T - t0, chunk);
+                if ((rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st))) return rc;
+                if (m->kind == 0) rc = gmm_launch_ms_senone(g, m->d_lists, T, t0, tn, d_out, st);
+                else rc = gmm_launch_tied_senone(g, m->d_lists, T, t0, tn, m->kind == 2, nullptr, 0, d_out, st);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (timed) cudaEventRecord(m->ev[2], st);
+    if (m->kind == 0 && normalize && (rc = gmm_launch_normalize(d_out, T, g.n_sen, st))) return rc;
+    if (timed) cudaEventRecord(m->ev[3], st);
+    return B200_OK;
+}
+
+void fetch_times(b200_mgau *m) {
+    // ev0 start, ev1 after prep (or start), ev2 after main, ev3 end
+    float a = 0, b = 0, c = 0, tot = 0;
+    cudaEventElapsedTime(&tot, m->ev[0], m->ev[3]);
+    cudaEventElapsedTime(&a, m->ev[0], m->ev[1]);
+    cudaEventElapsedTime(&b, m->ev[1], m->ev[2]);
+    cudaEventElapsedTime(&c, m->ev[2], m->ev[3]);
+    m->last_ms[0] = tot; m->last_ms[1] = a; m->last_ms[2] = b; m->last_ms[3] = c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+long long b200_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------- create
+b200_mgau_t *b200_ms_create(const b200_mgau_cfg_t *cfg, const float *mean, const float *var,
+                            const float *det, const uint8_t *mixw, const uint32_t *sen2mgau) {
+    if (!mixw || !sen2mgau) { set_error("null argument"); return nullptr; }
+    b200_mgau *m = mgau_common(0, cfg, mean, var, det);
+    if (!m) return nullptr;
+    GmmDev &g = m->g;
+    // transpose mixw [sen][feat][cw] -> [feat][cw][sen]
+    std::vector<uint8_t> t((size_t)g.n_sen * g.n_feat * g.n_density);
+    for (int s = 0; s < g.n_sen; ++s)
+        for (int f = 0; f < g.n_feat; ++f)
+            for (int c = 0; c < g.n_density; ++c)
+                t[((size_t)f * g.n_density + c) * g.n_sen + s] = mixw[((size_t)s * g.n_feat + f) * g.n_density + c];
+    m->cont = (g.n_mgau == g.n_sen);
+    for (int s = 0; s < g.n_sen; ++s) {
+        if ((int)sen2mgau[s] >= g.n_mgau) { set_error("sen2mgau[%d]=%u out of range", s, sen2mgau[s]); b200_mgau_free(m); return nullptr; }
+        if ((int)sen2mgau[s] != s) m->cont = false;
+    }
+    if (dev_alloc_copy(&m->d_mixw, t.data(), t.size()) || dev_alloc_copy(&m->d_sen2mgau, sen2mgau, (size_t)g.n_sen)) {
+        b200_mgau_free(m); return nullptr;
+    }
+    g.mixw_t = m->d_mixw; g.sen2mgau = m->d_sen2mgau; g.sen2cb = nullptr; g.n_clust = 0; g.row_bytes = g.n_sen;
+    m->path = 0;
+    if (m->cont && tc_shape_supported(g)) {
+        m->tc = tc_plan_create(g, mean, var, det, mixw, m->device);
+        if (m->tc) m->path = 1;
+    }
+    return m;
+}
+
+static b200_mgau_t *tied_create(int kind, const b200_mgau_cfg_t *cfg, const float *mean, const float *var,
+                                const float *det, const uint8_t *mixw, int n_clust, const uint8_t *mixw_cb,
+                                const uint8_t *sen2cb) {
+    if (!mixw) { set_error("null argument"); return nullptr; }
+    if (n_clust && !mixw_cb) { set_error("cluster codebook missing"); return nullptr; }
+    if (kind == 2 && cfg && cfg->n_mgau != 1) { set_error("s2_semi needs exactly one codebook"); return nullptr; }
+    if (kind == 1 && cfg && cfg->n_mgau > 256) { set_error("number of codebooks exceeds 256: %d", cfg->n_mgau); return nullptr; }
+    b200_mgau *m = mgau_common(kind, cfg, mean, var, det);
+    if (!m) return nullptr;
+    GmmDev &g = m->g;
+    g.n_clust = n_clust ? 16 : 0;
+    g.row_bytes = n_clust ? (g.n_sen + 1) / 2 : g.n_sen;
+    memset(g.mixw_cb, 0, 16);
+    if (n_clust) memcpy(g.mixw_cb, mixw_cb, 16);
+    std::vector<uint8_t> s2c((size_t)g.n_sen, 0);
+    if (kind == 1) {
+        if (!sen2cb) { set_error("ptm needs sen2cb"); b200_mgau_free(m); return nullptr; }
+        for (int s = 0; s < g.n_sen; ++s) {
+            if (sen2cb[s] >= g.n_mgau) { set_error("sen2cb[%d]=%d out of range", s, sen2cb[s]); b200_mgau_free(m); return nullptr; }
+            s2c[s] = sen2cb[s];
+        }
+    }
+    if (dev_alloc_copy(&m->d_mixw, mixw, (size_t)g.n_feat * g.n_density * g.row_bytes) ||
+        dev_alloc_copy(&m->d_sen2cb, s2c.data(), s2c.size())) { b200_mgau_free(m); return nullptr; }
+    g.mixw_t = m->d_mixw; g.sen2cb = m->d_sen2cb; g.sen2mgau = nullptr;
+    if (gmm_tied_smem(g, g.n_sen + g.n_sen / 255 + 1) > 200 * 1024) {
+        set_error("model too large for the tied senone kernel's shared memory"); b200_mgau_free(m); return nullptr;
+    }
+    return m;
+}
+
+b200_mgau_t *b200_ptm_create(const b200_mgau_cfg_t *cfg, const float *mean, const float *var, const float *det,
+                             const uint8_t *mixw, int n_clust, const uint8_t *mixw_cb, const uint8_t *sen2cb) {
+    return tied_create(1, cfg, mean, var, det, mixw, n_clust, mixw_cb, sen2cb);
+}
+
+b200_mgau_t *b200_semi_create(const b200_mgau_cfg_t *cfg, const float *mean, const float *var, const float *det,
+                              const uint8_t *mixw, int n_clust, const uint8_t *mixw_cb) {
+    return tied_create(2, cfg, mean, var, det, mixw, n_clust, mixw_cb, nullptr);
+}
+
+b200_mgau_t *b200_ms_load(const char *meanfile, const char *varfile, const char *mixwfile, const char *senmgau,
+                          const uint8_t *sen2cb, double varfloor, double mixwfloor, int topn, int aw,
+                          double logbase, int device) {
+    int32_t dm[4], dv[4], dw[4], vl[64], vl2[64];
+    if (b200_s3_read_gauden(meanfile, dm, vl, nullptr) || b200_s3_read_gauden(varfile, dv, vl2, nullptr)) return nullptr;
+    if (dm[0] != dv[0] || dm[1] != dv[1] || dm[2] != dv[2]) { set_error("mixture-gaussians dimensions for means and variances differ"); return nullptr; }
+    if (dm[1] > B200_MAX_STREAMS) { set_error("n_feat %d unsupported", dm[1]); return nullptr; }
+    for (int f = 0; f < dm[1]; ++f) if (vl[f] != vl2[f]) { set_error("feature lengths for means and variances differ"); return nullptr; }
+    std::vector<float> mean((size_t)dm[3]), var((size_t)dm[3]);
+    if (b200_s3_read_gauden(meanfile, dm, vl, mean.data()) || b200_s3_read_gauden(varfile, dv, vl2, var.data())) return nullptr;
+    if (b200_s3_read_mixw(mixwfile, dw, nullptr)) return nullptr;
+    std::vector<float> mixw((size_t)dw[3]);
+    if (b200_s3_read_mixw(mixwfile, dw, mixw.data())) return nullptr;
+    if (dw[1] != dm[1]) { set_error("#feature mismatch: gauden=%d senone=%d", dm[1], dw[1]); return nullptr; }
+    if (dw[2] != dm[2]) { set_error("#densities mismatch: gauden=%d senone=%d", dm[2], dw[2]); return nullptr; }
+    const int n_sen = dw[0], n_feat = dm[1], n_density = dm[2], n_mgau = dm[0];
+    // precompute per stream block (layout [mgau][feat][density][len f])
+    std::vector<float> det((size_t)n_mgau * n_feat * n_density);
+    int veclen = 0;
+    for (int f = 0; f < n_feat; ++f) veclen += vl[f];
+    for (int mg = 0; mg < n_mgau; ++mg) {
+        int off = 0;
+        for (int f = 0; f < n_feat; ++f) {
+            float *vp = var.data() + (size_t)mg * n_density * veclen + (size_t)n_density * off;
+            float *dp = det.data() + ((size_t)mg * n_feat + f) * n_density;
+            if (b200_gauden_precompute(vp, dp, n_density, vl[f], (float)varfloor, logbase)) return nullptr;
+            off += vl[f];
+        }
+    }
+    std::vector<uint8_t> q((size_t)dw[3]);
+    if (b200_mixw_quantize_ms(mixw.data(), q.data(), n_sen, n_feat, n_density, (float)mixwfloor, logbase)) return nullptr;
+    std::vector<uint32_t> map((size_t)n_sen, 0u);
+    std::string sm = senmgau ? senmgau : "";
+    if (sm.empty()) sm = (n_mgau == 1) ? ".semi." : ".cont.";
+    if (sm == ".semi.") { /* all zero */ }
+    else if (sm == ".ptm.") {
+        if (!sen2cb) { set_error(".ptm. mapping needs sen2cb"); return nullptr; }
+        for (int s = 0; s < n_sen; ++s) map[s] = sen2cb[s];
+    } else if (sm == ".cont." || sm == ".s3cont.") {
+        if (n_sen <= 1) { set_error("#senone=%d; must be >1", n_sen); return nullptr; }
+        for (int s = 0; s < n_sen; ++s) map[s] = s;
+    } else { set_error("senone-codebook map files are not supported (%s)", sm.c_str()); return nullptr; }
+    b200_mgau_cfg_t cfg{};
+    cfg.n_mgau = n_mgau; cfg.n_feat = n_feat; cfg.n_density = n_density; cfg.n_sen = n_sen;
+    for (int f = 0; f < n_feat; ++f) cfg.featlen[f] = vl[f];
+    cfg.topn = (topn == 0 || topn > n_density) ? n_density : topn;   // ms_mgau.c:121-127
+    cfg.aw = aw; cfg.ds_ratio = 1; cfg.logbase = logbase; cfg.device = device;
+    return b200_ms_create(&cfg, mean.data(), var.data(), det.data(), q.data(), map.data());
+}
+
+void b200_mgau_free(b200_mgau_t *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->tc) tc_plan_free(m->tc);
+    cudaFree(m->d_mean); cudaFree(m->d_var); cudaFree(m->d_det); cudaFree(m->d_mixw);
+    cudaFree(m->d_sen2cb); cudaFree(m->d_sen2mgau); cudaFree(m->d_lists);
+    for (int i = 0; i < 2; ++i) { cudaFree(m->d_feat[i]); cudaFree(m->d_out[i]); if (m->st[i]) cudaStreamDestroy(m->st[i]); }
+    for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_active); cudaFree(m->d_row);
+    if (m->h_row) cudaFreeHost(m->h_row);
+    if (m->h_frame) cudaFreeHost(m->h_frame);
+    delete m;
+}
+
+const char *b200_mgau_name(const b200_mgau_t *m) {
+    if (!m) return "";
+    return m->kind == 0 ? "b200_ms" : (m->kind == 1 ? "b200_ptm" : "b200_semi");
+}
+int b200_mgau_n_sen(const b200_mgau_t *m) { return m ? m->g.n_sen : 0; }
+int b200_mgau_featdim(const b200_mgau_t *m) { return m ? m->g.veclen : 0; }
+
+int b200_mgau_update_params(b200_mgau_t *m, const float *mean, const float *var, const float *det) {
+    if (!m || !mean || !var || !det) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    B200_CUDA_OK(cudaMemcpy(m->d_mean, mean, m->n_param * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(m->d_var, var, m->n_param * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(m->d_det, det, m->n_det * 4, cudaMemcpyHostToDevice));
+    if (m->tc) {
+        // the tensor-core operand is derived from (mean, var, det): rebuild it
+        std::vector<uint8_t> mixw_sfc((size_t)m->g.n_sen * m->g.n_feat * m->g.n_density);
+        std::vector<uint8_t> t(mixw_sfc.size());
+        B200_CUDA_OK(cudaMemcpy(t.data(), m->d_mixw, t.size(), cudaMemcpyDeviceToHost));
+        const GmmDev &g = m->g;
+        for (int s = 0; s < g.n_sen; ++s)
+            for (int f = 0; f < g.n_feat; ++f)
+                for (int c = 0; c < g.n_density; ++c)
+                    mixw_sfc[((size_t)s * g.n_feat + f) * g.n_density + c] = t[((size_t)f * g.n_density + c) * g.n_sen + s];
+        tc_plan_free(m->tc);
+        m->tc = tc_plan_create(m->g, mean, var, det, mixw_sfc.data(), m->device);
+        if (!m->tc) m->path = 0;
+    }
+    return B200_OK;
+}
+
+int b200_mgau_set_path(b200_mgau_t *m, int path) {
+    if (!m) return B200_ERR_ARG;
+    if (path == 0) { m->path = 0; return B200_OK; }
+    if (path == 1) {
+        if (!m->tc) { set_error("tensor-core path unavailable for this model shape"); return B200_ERR_UNSUP; }
+        m->path = 1; return B200_OK;
+    }
+    set_error("unknown path %d", path);
+    return B200_ERR_ARG;
+}
+int b200_mgau_get_path(const b200_mgau_t *m) { return m ? m->path : -1; }
+
+// ------------------------------------------------------------ dense scoring
+int b200_mgau_score_dev(b200_mgau_t *m, const float *d_feat, int T, int16_t *d_out, void *stream) {
+    if (!m || (T > 0 && (!d_feat || !d_out))) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->st[0];
+    int rc = score_dense_dev(m, d_feat, T, d_out, st, true, true);
+    if (rc) return rc;
+    if (!stream) {
+        B200_CUDA_OK(cudaStreamSynchronize(st));
+        fetch_times(m);
+    }
+    return B200_OK;
+}
+
+int b200_mgau_score_host(b200_mgau_t *m, const float *feat, int T, int16_t *out) {
+    if (!m || (T > 0 && (!feat || !out))) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    const GmmDev &g = m->g;
+    const int chunk = std::min(T, kHostChunkFrames);
+    if (chunk <= 0) return B200_OK;
+    const size_t fb = (size_t)chunk * g.veclen * 4, ob = (size_t)chunk * g.n_sen * 2;
+    for (int i = 0; i < 2; ++i) {
+        int rc = ensure((void **)&m->d_feat[i], &m->feat_cap[i], fb); if (rc) return rc;
+        rc = ensure((void **)&m->d_out[i], &m->out_cap[i], ob); if (rc) return rc;
+    }
+    // two streams ping-pong: H2D(k+1) and D2H(k-1) overlap compute(k).  The list
+    // scratch is shared, so compute itself is serialised through events.
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; ++i) B200_CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    int k = 0, rc = B200_OK;
+    for (int t0 = 0; t0 < T; t0 += chunk, ++k) {
+        const int b = k & 1, tn = std::min(chunk, T - t0);
+        cudaStream_t st = m->st[b];
+        cudaMemcpyAsync(m->d_feat[b], feat + (size_t)t0 * g.veclen, (size_t)tn * g.veclen * 4, cudaMemcpyHostToDevice, st);
+        if (k > 0) cudaStreamWaitEvent(st, done[b ^ 1], 0);
+        rc = score_dense_dev(m, m->d_feat[b], tn, m->d_out[b], st, true, false);
+        if (rc) break;
+        cudaEventRecord(done[b], st);
+        cudaMemcpyAsync(out + (size_t)t0 * g.n_sen, m->d_out[b], (size_t)tn * g.n_sen * 2, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(m->st[0]), e1 = cudaStreamSynchronize(m->st[1]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+    if (rc) return rc;
+    B200_CUDA_OK(e0);
+    B200_CUDA_OK(e1);
+    return B200_OK;
+}
+
+float b200_mgau_last_ms(const b200_mgau_t *m, int which) {
+    if (!m || which < 0 || which > 3) return -1.f;
+    return m->last_ms[which];
+}
+
+// ------------------------------------------------- utterance / frame serving
+int b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T) {
+    if (!m || T < 0 || (T > 0 && !feat)) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    const GmmDev &g = m->g;
+    m->utt_T = 0;
+    if (T == 0) return B200_OK;
+    cudaStream_t st = m->st[0];
+    int rc = ensure((void **)&m->d_ufeat, &m->ufeat_cap, (size_t)T * g.veclen * 4);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaMemcpyAsync(m->d_ufeat, feat, (size_t)T * g.veclen * 4, cudaMemcpyHostToDevice, st));
+    if (m->kind == 0) {
+        if ((rc = ensure((void **)&m->d_uraw, &m->uraw_cap, (size_t)T * g.n_sen * 2))) return rc;
+        if ((rc = score_dense_dev(m, m->d_ufeat, T, m->d_uraw, st, false, false))) return rc;
+    } else {
+        if ((rc = ensure((void **)&m->d_ulists, &m->ulists_cap, (size_t)T * list_bytes_per_frame(m)))) return rc;
+        for (int t0 = 0; t0 < T; t0 += 65535 * 128) {
+            int tn = std::min(T - t0, 65535 * 128);
+            // lists for frame t land at index (t - 0): pass t0 = 0 base by offsetting the pointer
+            if ((rc = gmm_launch_topn(g, m->kind, m->d_ufeat, T, t0, tn,
+                                      m->d_ulists + (size_t)t0 * g.n_mgau * g.n_feat * g.topn, nullptr, 0, st))) return rc;
+        }
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    m->utt_T = T;
+    return B200_OK;
+}
+
+static int serve_frame(b200_mgau_t *m, int frame, int16_t *senscr, const uint8_t *senone_active,
+                       int32_t n_active, int32_t compallsen) {
+    const GmmDev &g = m->g;
+    cudaStream_t st = m->st[0];
+    const bool use_active = !compallsen;
+    if (use_active) {
+        if (n_active < 0 || (n_active > 0 && !senone_active)) { set_error("bad active list"); return B200_ERR_ARG; }
+        int rc = ensure((void **)&m->d_active, &m->active_cap, (size_t)std::max(n_active, 1));
+        if (rc) return rc;
+        if (n_active > 0)
+            B200_CUDA_OK(cudaMemcpyAsync(m->d_active, senone_active, (size_t)n_active, cudaMemcpyHostToDevice, st));
+    }
+    int rc;
+    if (m->kind == 0) {
+        const int16_t *raw = m->d_uraw + (size_t)frame * g.n_sen;
+        if (use_active) {
+            if (n_active == 0) return B200_OK;
+            B200_CUDA_OK(cudaMemcpyAsync(m->d_row, raw, (size_t)g.n_sen * 2, cudaMemcpyDeviceToDevice, st));
+            if ((rc = gmm_launch_ms_active_normalize(raw, m->d_active, n_active, m->d_row, st))) return rc;
+        } else {
+            B200_CUDA_OK(cudaMemcpyAsync(m->d_row, raw, (size_t)g.n_sen * 2, cudaMemcpyDeviceToDevice, st));
+            if ((rc = gmm_launch_normalize(m->d_row, 1, g.n_sen, st))) return rc;
+        }
+    } else {
+        const int2 *l = m->d_ulists + (size_t)frame * g.n_mgau * g.n_feat * g.topn;
+        // out row index is t - t0 with T=1,t0=0 -> write straight into d_row
+        if ((rc = gmm_launch_tied_senone(g, l, 1, 0, 1, m->kind == 2, use_active ? m->d_active : nullptr,
+                                         use_active ? n_active : 0, m->d_row, st))) return rc;
+    }
+    B200_CUDA_OK(cudaMemcpyAsync(m->h_row, m->d_row, (size_t)g.n_sen * 2, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    if (m->kind == 0 && use_active) {
+        // the reference writes only the active entries of the caller's array
+        int s = 0;
+        for (int i = 0; i < n_active; ++i) { s += senone_active[i]; senscr[s] = m->h_row[s]; }
+    } else {
+        memcpy(senscr, m->h_row, (size_t)g.n_sen * 2);
+    }
+    return B200_OK;
+}
+
+int b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr, const uint8_t *senone_active, int32_t n_senone_active,
+                        int32_t frame, int32_t compallsen) {
+    if (!m || !senscr) { set_error("null argument"); return B200_ERR_ARG; }
+    if (frame < 0 || frame >= m->utt_T) { set_error("frame %d outside the scored utterance (0..%d)", frame, m->utt_T); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    return serve_frame(m, frame, senscr, senone_active, n_senone_active, compallsen);
+}
+
+int b200_mgau_frame_eval(b200_mgau_t *m, int16_t *senscr, const uint8_t *senone_active, int32_t n_senone_active,
+                         const float *const *feat, int32_t frame, int32_t compallsen) {
+    if (!m || !senscr || !feat) { set_error("null argument"); return B200_ERR_ARG; }
+    (void)frame;
+    const GmmDev &g = m->g;
+    for (int f = 0; f < g.n_feat; ++f) {
+        if (!feat[f]) { set_error("null stream pointer"); return B200_ERR_ARG; }
+        memcpy(m->h_frame + g.featoff[f], feat[f], (size_t)g.featlen[f] * 4);
+    }
+    int rc = b200_mgau_utt_begin(m, m->h_frame, 1);
+    if (rc) return rc;
+    return serve_frame(m, 0, senscr, senone_active, n_senone_active, compallsen);
+}
+
+// ---------------------------------------------------------------------- HMM
+}  // extern "C"
+
+struct b200_hmmctx {
+    HmmDev c{};
+    int device = 0;
+    uint8_t *d_tp = nullptr; uint16_t *d_sseq = nullptr;
+    HmmPop p{};
+    size_t pop_cap = 0;  // in HMMs
+    HmmFrame *d_fr = nullptr;
+    uint8_t *d_keep = nullptr; int32_t *d_block_count = nullptr, *d_keep_idx = nullptr;
+    uint32_t *d_mask = nullptr;
+    int16_t *d_senscr = nullptr; size_t senscr_cap = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    float last_ms = 0;
+};
+
+namespace {
+
+void pop_free(b200_hmmctx *c) {
+    cudaFree(c->p.score); cudaFree(c->p.history); cudaFree(c->p.out_score); cudaFree(c->p.out_history);
+    cudaFree(c->p.bestscore); cudaFree(c->p.senid); cudaFree(c->p.tmatid); cudaFree(c->p.mpx);
+    cudaFree(c->d_keep); cudaFree(c->d_block_count); cudaFree(c->d_keep_idx);
+    c->p = HmmPop{}; c->d_keep = nullptr; c->d_block_count = nullptr; c->d_keep_idx = nullptr; c->pop_cap = 0;
+}
+
+int pop_reserve(b200_hmmctx *c, int n) {
+    if ((size_t)n <= c->pop_cap) { c->p.n_hmm = n; return B200_OK; }
+    pop_free(c);
+    const int ne = c->c.n_emit;
+    const size_t N = (size_t)n;
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.score, N * ne * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.history, N * ne * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.out_score, N * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.out_history, N * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.bestscore, N * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.senid, N * ne * 2));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.tmatid, N * 2));
+    B200_CUDA_OK(cudaMalloc((void **)&c->p.mpx, N));
+    B200_CUDA_OK(cudaMalloc((void **)&c->d_keep, N));
+    B200_CUDA_OK(cudaMalloc((void **)&c->d_block_count, ((N + 255) / 256 + 1) * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->d_keep_idx, N * 4));
+    c->pop_cap = N; c->p.n_hmm = n;
+    return B200_OK;
+}
+
+int check_soa(const b200_hmmctx *c, const b200_hmm_soa_t *h) {
+    if (!c || !h) { set_error("null argument"); return B200_ERR_ARG; }
+    if (h->n_hmm < 0) { set_error("negative n_hmm"); return B200_ERR_ARG; }
+    if (h->n_hmm > 0 && (!h->score || !h->history || !h->out_score || !h->out_history || !h->senid ||
+                         !h->tmatid || !h->mpx || !h->bestscore)) { set_error("null SoA field"); return B200_ERR_ARG; }
+    for (int i = 0; i < h->n_hmm; ++i)
+        if (h->tmatid[i] < 0 || h->tmatid[i] >= c->c.n_tmat) { set_error("tmatid[%d]=%d out of range", i, h->tmatid[i]); return B200_ERR_ARG; }
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat, const uint16_t *sseq, int n_sseq,
+                                   int n_sen, int device) {
+    if (n_emit != 3 && n_emit != 5) { set_error("n_emit_state %d unsupported (3 or 5; hmm_vit_eval_anytopo is host-only)", n_emit); return nullptr; }
+    if (!tp || n_tmat <= 0 || n_sen <= 0 || n_sen > 65535 || (n_sseq > 0 && !sseq)) { set_error("bad hmm context arguments"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libb200sphinx has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { set_error("bad device %d", device); return nullptr; }
+    b200_hmmctx *c = new (std::nothrow) b200_hmmctx();
+    if (!c) return nullptr;
+    c->device = device;
+    c->c.n_emit = n_emit; c->c.n_tmat = n_tmat; c->c.n_sseq = n_sseq; c->c.n_sen = n_sen;
+    const int n_words = (n_sen + 31) / 32;
+    if (dev_alloc_copy(&c->d_tp, tp, (size_t)n_tmat * n_emit * (n_emit + 1)) ||
+        dev_alloc_copy(&c->d_sseq, sseq, (size_t)std::max(n_sseq, 1) * n_emit * (n_sseq > 0 ? 1 : 0)) ||
+        cudaMalloc((void **)&c->d_fr, sizeof(HmmFrame)) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_mask, (size_t)n_words * 4) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess) {
+        set_error("hmm context allocation failed"); b200_hmm_ctx_free(c); return nullptr;
+    }
+    c->c.tp = c->d_tp; c->c.sseq = c->d_sseq;
+    return c;
+}
+
+void b200_hmm_ctx_free(b200_hmmctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    pop_free(c);
+    cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr);
+    if (c->st) cudaStreamDestroy(c->st);
+    for (int i = 0; i < 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+}
+
+int b200_hmm_pop_upload(b200_hmmctx_t *c, const b200_hmm_soa_t *h) {
+    int rc = check_soa(c, h);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    if ((rc = pop_reserve(c, h->n_hmm))) return rc;
+    const size_t N = (size_t)h->n_hmm;
+    const int ne = c->c.n_emit;
+    if (N == 0) return B200_OK;
+    B200_CUDA_OK(cudaMemcpy(c->p.score, h->score, N * ne * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.history, h->history, N * ne * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.out_score, h->out_score, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.out_history, h->out_history, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.bestscore, h->bestscore, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.senid, h->senid, N * ne * 2, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.tmatid, h->tmatid, N * 2, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->p.mpx, h->mpx, N, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+int b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h) {
+    if (!c || !h) { set_error("null argument"); return B200_ERR_ARG; }
+    if (h->n_hmm != c->p.n_hmm) { set_error("population size mismatch: %d vs %d", h->n_hmm, c->p.n_hmm); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    const size_t N = (size_t)h->n_hmm;
+    const int ne = c->c.n_emit;
+    if (N == 0) return B200_OK;
+    B200_CUDA_OK(cudaStreamSynchronize(c->st));
+    B200_CUDA_OK(cudaMemcpy(h->score, c->p.score, N * ne * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(h->history, c->p.history, N * ne * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(h->out_score, c->p.out_score, N * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(h->out_history, c->p.out_history, N * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(h->bestscore, c->p.bestscore, N * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(h->senid, c->p.senid, N * ne * 2, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam, void *stream) {
+    if (!c || !d_senscr) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->st;
+    cudaEventRecord(c->ev[0], st);
+    int rc = hmm_launch_step(c->c, c->p, d_senscr, beam, c->d_fr, c->d_keep, c->d_block_count, c->d_keep_idx,
+                             c->d_mask, 1, st);
+    cudaEventRecord(c->ev[1], st);
+    return rc;
+}
+
+int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int32_t *keep_idx, uint32_t *sen_mask) {
+    if (!c) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    B200_CUDA_OK(cudaStreamSynchronize(c->st));
+    HmmFrame fr;
+    B200_CUDA_OK(cudaMemcpy(&fr, c->d_fr, sizeof fr, cudaMemcpyDeviceToHost));
+    if (best) *best = fr.best;
+    if (n_keep) *n_keep = fr.n_keep;
+    if (keep_idx && fr.n_keep > 0) B200_CUDA_OK(cudaMemcpy(keep_idx, c->d_keep_idx, (size_t)fr.n_keep * 4, cudaMemcpyDeviceToHost));
+    if (sen_mask) B200_CUDA_OK(cudaMemcpy(sen_mask, c->d_mask, (size_t)((c->c.n_sen + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+    cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[1]);
+    return B200_OK;
+}
+
+int b200_hmm_step_host(b200_hmmctx_t *c, const int16_t *senscr, int32_t beam) {
+    if (!c || !senscr) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    int rc = ensure((void **)&c->d_senscr, &c->senscr_cap, (size_t)c->c.n_sen * 2);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, (size_t)c->c.n_sen * 2, cudaMemcpyHostToDevice, c->st));
+    return b200_hmm_step_dev(c, c->d_senscr, beam, nullptr);
+}
+
+int b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h, const int16_t *senscr, int n_frames, int32_t *best_out) {
+    if (!senscr || n_frames < 0) { set_error("bad arguments"); return B200_ERR_ARG; }
+    int rc = b200_hmm_pop_upload(c, h);
+    if (rc) return rc;
+    if (h->n_hmm == 0) { for (int f = 0; f < n_frames; ++f) if (best_out) best_out[f] = B200_WORST_SCORE; return B200_OK; }
+    if ((rc = ensure((void **)&c->d_senscr, &c->senscr_cap, (size_t)c->c.n_sen * 2 * std::max(n_frames, 1)))) return rc;
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, (size_t)c->c.n_sen * 2 * n_frames, cudaMemcpyHostToDevice, c->st));
+    for (int f = 0; f < n_frames; ++f) {
+        rc = hmm_launch_step(c->c, c->p, c->d_senscr + (size_t)f * c->c.n_sen, 0, c->d_fr, c->d_keep,
+                             c->d_block_count, c->d_keep_idx, c->d_mask, 0, c->st);
+        if (rc) return rc;
+        if (best_out) B200_CUDA_OK(cudaMemcpyAsync(&best_out[f], (const int32_t *)c->d_fr, 4, cudaMemcpyDeviceToHost, c->st));
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(c->st));
+    return b200_hmm_pop_download(c, h);
+}
+
+float b200_hmm_last_ms(const b200_hmmctx_t *c) { return c ? c->last_ms : -1.f; }
+
+// ------------------------------------------------------------ memory helpers
+void *b200_dev_alloc(size_t bytes, int device) {
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void b200_dev_free(void *p) { if (p) cudaFree(p); }
+int b200_dev_upload(void *dst, const void *src, size_t bytes) {
+    B200_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+int b200_dev_download(void *dst, const void *src, size_t bytes) {
+    B200_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+void *b200_host_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b200_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+int b200_dev_sync(int device) {
+    B200_CUDA_OK(cudaSetDevice(device));
+    B200_CUDA_OK(cudaDeviceSynchronize());
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// hmm_kernels.cu -- batched HMM Viterbi step, beam test + order-preserving
+// compaction, active-senone gather (sm_100a).
+//
+// Reference: pocketsphinx/src/libpocketsphinx/hmm.c
+//   hmm_vit_eval_5st_lr      :224-352      hmm_vit_eval_5st_lr_mpx :357-527
+//   hmm_vit_eval_3st_lr      :531-609      hmm_vit_eval_3st_lr_mpx :611-709
+// and the beam test of ngram_search_fwdtree.c:714-869, acmod_activate_hmm
+// (acmod.c:1178-1217).  All arithmetic is int32 max-plus and is reproduced
+// literally, including the quirks listed in SURVEY.md section 8(a):
+// the stale exit score when s1 is dead (3st) / s3 dead (5st), the t2 leak from
+// the exit step into state 2 when tp(0,2) is "zero", the nested tie-breaking
+// order, and the BAD_SSID / "!= WORST_SCORE" guards of the mpx variants.
+//
+// Layout: structure of arrays, state-major ([state][hmm]) so that a warp's
+// loads and stores of one field are contiguous 128-byte lines.  The frame's
+// senone scores (int16, <= 64 K entries) and the transition table are staged
+// in shared memory; the mpx senone-sequence table is read through L1/L2.
+#include "hmm_dev.cuh"
+
+namespace b200 {
+
+#define BT(a, b) ((a) > (b))   // BETTER_THAN (hmm.h:85)
+#define WT(a, b) ((a) < (b))   // WORSE_THAN
+
+struct HmmRegs {
+    int32_t sc[5], hi[5], out_sc, out_hi, best;
+    uint16_t sid[5];
+};
+
+// tp row-major [from][to] with n+1 columns, stored negated (uint8).
+template <int NE>
+__device__ __forceinline__ int32_t tpv(const uint8_t *tp, int i, int j) { return -(int32_t)tp[i * (NE + 1) + j]; }
+
+__device__ __forceinline__ void eval3(HmmRegs &h, const uint8_t *tp, const int16_t *sen) {
+    int32_t s3, s2, s1, s0, t2, t1, t0, best;
+    s2 = h.sc[2] - sen[h.sid[2]];
+    s1 = h.sc[1] - sen[h.sid[1]];
+    s0 = h.sc[0] - sen[h.sid[0]];
+    best = kWorstScore;
+    t2 = (int32_t)0x80000000;
+    if (BT(s1, kWorstScore)) {
+        t1 = s2 + tpv<3>(tp, 2, 3);
+        if (BT(tpv<3>(tp, 1, 3), B200_TMAT_WORST)) t2 = s1 + tpv<3>(tp, 1, 3);
+        if (BT(t1, t2)) { s3 = t1; h.out_hi = h.hi[2]; }
+        else { s3 = t2; h.out_hi = h.hi[1]; }
+        if (WT(s3, kWorstScore)) s3 = kWorstScore;
+        h.out_sc = s3;
+        best = s3;
+    }
+    t0 = s2 + tpv<3>(tp, 2, 2);
+    t1 = s1 + tpv<3>(tp, 1, 2);
+    if (BT(tpv<3>(tp, 0, 2), B200_TMAT_WORST)) t2 = s0 + tpv<3>(tp, 0, 2);
+    if (BT(t0, t1)) {
+        if (BT(t2, t0)) { s2 = t2; h.hi[2] = h.hi[0]; } else s2 = t0;
+    } else {
+        if (BT(t2, t1)) { s2 = t2; h.hi[2] = h.hi[0]; } else { s2 = t1; h.hi[2] = h.hi[1]; }
+    }
+    if (WT(s2, kWorstScore)) s2 = kWorstScore;
+    if (BT(s2, best)) best = s2;
+    h.sc[2] = s2;
+    t0 = s1 + tpv<3>(tp, 1, 1);
+    t1 = s0 + tpv<3>(tp, 0, 1);
+    if (BT(t0, t1)) s1 = t0; else { s1 = t1; h.hi[1] = h.hi[0]; }
+    if (WT(s1, kWorstScore)) s1 = kWorstScore;
+    if (BT(s1, best)) best = s1;
+    h.sc[1] = s1;
+    s0 = s0 + tpv<3>(tp, 0, 0);
+    if (WT(s0, kWorstScore)) s0 = kWorstScore;
+    if (BT(s0, best)) best = s0;
+    h.sc[0] = s0;
+    h.best = best;
+}
+
+#define MPX_SEN(st) sen[sseq[(size_t)h.sid[st] * NE + (st)]]
+
+__device__ __forceinline__ void eval3_mpx(HmmRegs &h, const uint8_t *tp, const int16_t *sen,
+                                          const uint16_t *__restrict__ sseq) {
+    constexpr int NE = 3;
+    int32_t s3, s2, s1, s0, t2, t1, t0, best;
+    t2 = (int32_t)0x80000000;
+    if (h.sid[2] == B200_BAD_SSID) s2 = t1 = kWorstScore;
+    else { s2 = h.sc[2] - MPX_SEN(2); t1 = s2 + tpv<3>(tp, 2, 3); }
+    if (h.sid[1] == B200_BAD_SSID) s1 = t2 = kWorstScore;
+    else {
+        s1 = h.sc[1] - MPX_SEN(1);
+        if (BT(tpv<3>(tp, 1, 3), B200_TMAT_WORST)) t2 = s1 + tpv<3>(tp, 1, 3);
+    }
+    if (BT(t1, t2)) { s3 = t1; h.out_hi = h.hi[2]; }
+    else { s3 = t2; h.out_hi = h.hi[1]; }
+    if (WT(s3, kWorstScore)) s3 = kWorstScore;
+    h.out_sc = s3;
+    best = s3;
+    s0 = h.sc[0] - MPX_SEN(0);
+    t0 = t1 = kWorstScore;
+    if (s2 != kWorstScore) t0 = s2 + tpv<3>(tp, 2, 2);
+    if (s1 != kWorstScore) t1 = s1 + tpv<3>(tp, 1, 2);
+    if (BT(tpv<3>(tp, 0, 2), B200_TMAT_WORST)) t2 = s0 + tpv<3>(tp, 0, 2);
+    if (BT(t0, t1)) {
+        if (BT(t2, t0)) { s2 = t2; h.hi[2] = h.hi[0]; h.sid[2] = h.sid[0]; } else s2 = t0;
+    } else {
+        if (BT(t2, t1)) { s2 = t2; h.hi[2] = h.hi[0]; h.sid[2] = h.sid[0]; }
+        else { s2 = t1; h.hi[2] = h.hi[1]; h.sid[2] = h.sid[1]; }
+    }
+    if (WT(s2, kWorstScore)) s2 = kWorstScore;
+    if (BT(s2, best)) best = s2;
+    h.sc[2] = s2;
+    t0 = kWorstScore;
+    if (s1 != kWorstScore) t0 = s1 + tpv<3>(tp, 1, 1);
+    t1 = s0 + tpv<3>(tp, 0, 1);
+    if (BT(t0, t1)) s1 = t0; else { s1 = t1; h.hi[1] = h.hi[0]; h.sid[1] = h.sid[0]; }
+    if (WT(s1, kWorstScore)) s1 = kWorstScore;
+    if (BT(s1, best)) best = s1;
+    h.sc[1] = s1;
+    s0 += tpv<3>(tp, 0, 0);
+    if (WT(s0, kWorstScore)) s0 = kWorstScore;
+    if (BT(s0, best)) best = s0;
+    h.sc[0] = s0;
+    h.best = best;
+}
+
+// One "all transitions into state `to`" block of the 5-state non-mpx eval.
+#define INTO3(S_TO, S_A, S_B, S_C, TO, A, B, C)                                      \
+    t0 = S_A + tpv<5>(tp, A, TO); t1 = S_B + tpv<5>(tp, B, TO); t2 = S_C + tpv<5>(tp, C, TO); \
+    if (BT(t0, t1)) { if (BT(t2, t0)) { S_TO = t2; h.hi[TO] = h.hi[C]; } else S_TO = t0; } \
+    else { if (BT(t2, t1)) { S_TO = t2; h.hi[TO] = h.hi[C]; } else { S_TO = t1; h.hi[TO] = h.hi[B]; } } \
+    if (WT(S_TO, kWorstScore)) S_TO = kWorstScore;                                   \
+    if (BT(S_TO, best)) best = S_TO;                                                 \
+    h.sc[TO] = S_TO;
+
+__device__ __forceinline__ void eval5(HmmRegs &h, const uint8_t *tp, const int16_t *sen) {
+    int32_t s5, s4, s3, s2, s1, s0, t2, t1, t0, best;
+    best = kWorstScore;
+    s4 = h.sc[4] - sen[h.sid[4]];
+    s3 = h.sc[3] - sen[h.sid[3]];
+    if (BT(s3, kWorstScore)) {
+        t1 = s4 + tpv<5>(tp, 4, 5);
+        t2 = s3 + tpv<5>(tp, 3, 5);
+        if (BT(t1, t2)) { s5 = t1; h.out_hi = h.hi[4]; }
+        else { s5 = t2; h.out_hi = h.hi[3]; }
+        if (WT(s5, kWorstScore)) s5 = kWorstScore;
+        h.out_sc = s5;
+        best = s5;
+    }
+    s2 = h.sc[2] - sen[h.sid[2]];
+    if (BT(s2, kWorstScore)) { INTO3(s4, s4, s3, s2, 4, 4, 3, 2) }
+    s1 = h.sc[1] - sen[h.sid[1]];
+    if (BT(s1, kWorstScore)) { INTO3(s3, s3, s2, s1, 3, 3, 2, 1) }
+    s0 = h.sc[0] - sen[h.sid[0]];
+    { INTO3(s2, s2, s1, s0, 2, 2, 1, 0) }
+    t0 = s1 + tpv<5>(tp, 1, 1);
+    t1 = s0 + tpv<5>(tp, 0, 1);
+    if (BT(t0, t1)) s1 = t0; else { s1 = t1; h.hi[1] = h.hi[0]; }
+    if (WT(s1, kWorstScore)) s1 = kWorstScore;
+    if (BT(s1, best)) best = s1;
+    h.sc[1] = s1;
+    s0 = s0 + tpv<5>(tp, 0, 0);
+    if (WT(s0, kWorstScore)) s0 = kWorstScore;
+    if (BT(s0, best)) best = s0;
+    h.sc[0] = s0;
+    h.best = best;
+}
+
+// mpx flavour of the same block: guarded self/prev terms, ssid propagation.
+#define INTO3_MPX(S_TO, S_A, S_B, TO, A, B, C)                                        \
+    t0 = t1 = kWorstScore;                                                            \
+    if (S_A != kWorstScore) t0 = S_A + tpv<5>(tp, A, TO);                             \
+    if (S_B != kWorstScore) t1 = S_B + tpv<5>(tp, B, TO);                             \
+    if (BT(t0, t1)) {                                                                 \
+        if (BT(t2, t0)) { S_TO = t2; h.hi[TO] = h.hi[C]; h.sid[TO] = h.sid[C]; } else S_TO = t0; \
+    } else {                                                                          \
+        if (BT(t2, t1)) { S_TO = t2; h.hi[TO] = h.hi[C]; h.sid[TO] = h.sid[C]; }      \
+        else { S_TO = t1; h.hi[TO] = h.hi[B]; h.sid[TO] = h.sid[B]; }                 \
+    }                                                                                 \
+    if (WT(S_TO, kWorstScore)) S_TO = kWorstScore;                                    \
+    if (BT(S_TO, best)) best = S_TO;                                                  \
+    h.sc[TO] = S_TO;
+
+__device__ __forceinline__ void eval5_mpx(HmmRegs &h, const uint8_t *tp, const int16_t *sen,
+                                          const uint16_t *__restrict__ sseq) {
+    constexpr int NE = 5;
+    int32_t s5, s4, s3, s2, s1, s0, t2, t1, t0, best;
+    if (h.sid[4] == B200_BAD_SSID) s4 = t1 = kWorstScore;
+    else { s4 = h.sc[4] - MPX_SEN(4); t1 = s4 + tpv<5>(tp, 4, 5); }
+    if (h.sid[3] == B200_BAD_SSID) s3 = t2 = kWorstScore;
+    else { s3 = h.sc[3] - MPX_SEN(3); t2 = s3 + tpv<5>(tp, 3, 5); }
+    if (BT(t1, t2)) { s5 = t1; h.out_hi = h.hi[4]; }
+    else { s5 = t2; h.out_hi = h.hi[3]; }
+    if (WT(s5, kWorstScore)) s5 = kWorstScore;
+    h.out_sc = s5;
+    best = s5;
+    if (h.sid[2] == B200_BAD_SSID) s2 = t2 = kWorstScore;
+    else { s2 = h.sc[2] - MPX_SEN(2); t2 = s2 + tpv<5>(tp, 2, 4); }
+    { INTO3_MPX(s4, s4, s3, 4, 4, 3, 2) }
+    if (h.sid[1] == B200_BAD_SSID) s1 = t2 = kWorstScore;
+    else { s1 = h.sc[1] - MPX_SEN(1); t2 = s1 + tpv<5>(tp, 1, 3); }
+    { INTO3_MPX(s3, s3, s2, 3, 3, 2, 1) }
+    s0 = h.sc[0] - MPX_SEN(0);
+    t2 = s0 + tpv<5>(tp, 0, 2);
+    {
+        // state 2: same shape, but t2 is computed before the guards
+        int32_t t2keep = t2;
+        t0 = t1 = kWorstScore;
+        if (s2 != kWorstScore) t0 = s2 + tpv<5>(tp, 2, 2);
+        if (s1 != kWorstScore) t1 = s1 + tpv<5>(tp, 1, 2);
+        t2 = t2keep;
+        if (BT(t0, t1)) {
+            if (BT(t2, t0)) { s2 = t2; h.hi[2] = h.hi[0]; h.sid[2] = h.sid[0]; } else s2 = t0;
+        } else {
+            if (BT(t2, t1)) { s2 = t2; h.hi[2] = h.hi[0]; h.sid[2] = h.sid[0]; }
+            else { s2 = t1; h.hi[2] = h.hi[1]; h.sid[2] = h.sid[1]; }
+        }
+        if (WT(s2, kWorstScore)) s2 = kWorstScore;
+        if (BT(s2, best)) best = s2;
+        h.sc[2] = s2;
+    }
+    t0 = kWorstScore;
+    if (s1 != kWorstScore) t0 = s1 + tpv<5>(tp, 1, 1);
+    t1 = s0 + tpv<5>(tp, 0, 1);
+    if (BT(t0, t1)) s1 = t0; else { s1 = t1; h.hi[1] = h.hi[0]; h.sid[1] = h.sid[0]; }
+    if (WT(s1, kWorstScore)) s1 = kWorstScore;
+    if (BT(s1, best)) best = s1;
+    h.sc[1] = s1;
+    s0 += tpv<5>(tp, 0, 0);
+    if (WT(s0, kWorstScore)) s0 = kWorstScore;
+    if (BT(s0, best)) best = s0;
+    h.sc[0] = s0;
+    h.best = best;
+}
+
+// ---------------------------------------------------------------- kernels
+constexpr int kHmmBlock = 256;
+
+template <int NE>
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr, HmmFrame *fr) {
+    extern __shared__ uint8_t sm_raw[];
+    int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
+    uint8_t *s_tp = sm_raw + (((size_t)c.n_sen * 2 + 15) & ~(size_t)15);
+    const int tid = threadIdx.x;
+    // stage the frame's senone scores (vectorised) and the transition table
+    {
+        const int n16 = ((reinterpret_cast<size_t>(senscr) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
+        const int4 *src = reinterpret_cast<const int4 *>(senscr);
+        int4 *dst = reinterpret_cast<int4 *>(s_sen);
+        for (int i = tid; i < n16; i += kHmmBlock) dst[i] = src[i];
+        for (int i = n16 * 8 + tid; i < c.n_sen; i += kHmmBlock) s_sen[i] = senscr[i];
+        const int ntp = c.n_tmat * NE * (NE + 1);
+        for (int i = tid; i < ntp; i += kHmmBlock) s_tp[i] = c.tp[i];
+    }
+    __syncthreads();
+    int32_t blockbest = kWorstScore;
+    const int n = p.n_hmm;
+    for (int i = blockIdx.x * kHmmBlock + tid; i < n; i += gridDim.x * kHmmBlock) {
+        HmmRegs h;
+#pragma unroll
+        for (int s = 0; s < NE; ++s) {
+            h.sc[s] = p.score[(size_t)s * n + i];
+            h.hi[s] = p.history[(size_t)s * n + i];
+            h.sid[s] = p.senid[(size_t)s * n + i];
+        }
+        h.out_sc = p.out_score[i];
+        h.out_hi = p.out_history[i];
+        const uint8_t *tp = s_tp + (int)p.tmatid[i] * NE * (NE + 1);
+        const bool mpx = p.mpx[i] != 0;
+        if (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
+        else { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
+#pragma unroll
+        for (int s = 0; s < NE; ++s) {
+            p.score[(size_t)s * n + i] = h.sc[s];
+            p.history[(size_t)s * n + i] = h.hi[s];
+        }
+        if (mpx) {
+#pragma unroll
+            for (int s = 1; s < NE; ++s) p.senid[(size_t)s * n + i] = h.sid[s];
+        }
+        p.out_score[i] = h.out_sc;
+        p.out_history[i] = h.out_hi;
+        p.bestscore[i] = h.best;
+        blockbest = max(blockbest, h.best);
+    }
+    for (int o = 16; o > 0; o >>= 1) blockbest = max(blockbest, __shfl_xor_sync(0xffffffffu, blockbest, o));
+    __shared__ int32_t s_best[kHmmBlock / 32];
+    if ((tid & 31) == 0) s_best[tid >> 5] = blockbest;
+    __syncthreads();
+    if (tid == 0) {
+        int32_t b = s_best[0];
+        for (int w = 1; w < kHmmBlock / 32; ++w) b = max(b, s_best[w]);
+        atomicMax(&fr->best, b);
+    }
+}
+
+__global__ void hmm_frame_init_kernel(HmmFrame *fr, uint32_t *mask, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) mask[i] = 0u;
+    if (threadIdx.x == 0) { fr->best = kWorstScore; fr->n_keep = 0; }
+}
+
+// Pass 1 of the order-preserving compaction: keep flag + per-block count.
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_beam_flag_kernel(HmmPop p, const HmmFrame *fr, int32_t beam, uint8_t *keep, int32_t *block_count) {
+    const int i = blockIdx.x * kHmmBlock + threadIdx.x;
+    const int32_t thresh = fr->best + beam;
+    bool k = false;
+    if (i < p.n_hmm) {
+        k = BT(p.bestscore[i], thresh);
+        keep[i] = k ? 1 : 0;
+    }
+    const int cnt = __syncthreads_count(k);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = cnt;
+}
+
+// Pass 2: exclusive scan of the block counts by one block.
+__global__ void __launch_bounds__(1024)
+hmm_scan_kernel(int32_t *block_count, int n_blocks, HmmFrame *fr) {
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + tid;
+        int32_t v = i < n_blocks ? block_count[i] : 0;
+        int32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int32_t ws = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
+            s_warp[lane] = ws;
+        }
+        __syncthreads();
+        const int32_t incl = x + (w ? s_warp[w - 1] : 0) + s_carry;
+        if (i < n_blocks) block_count[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (tid == 0) fr->n_keep = s_carry;
+}
+
+// Pass 3: scatter survivors (index order preserved) and OR their senones into
+// the active mask (acmod_activate_hmm).
+template <int NE>
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block_off,
+                   int32_t *keep_idx, uint32_t *mask) {
+    extern __shared__ uint32_t s_mask[];
+    __shared__ int32_t s_wsum[kHmmBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n_words = (c.n_sen + 31) / 32;
+    for (int k = tid; k < n_words; k += kHmmBlock) s_mask[k] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * kHmmBlock + tid;
+    const bool k = (i < p.n_hmm) && keep[i];
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) s_wsum[w] = __popc(bal);
+    if (k) {
+        const int n = p.n_hmm;
+        const bool mpx = p.mpx[i] != 0;
+#pragma unroll
+        for (int s = 0; s < NE; ++s) {
+            uint32_t id = p.senid[(size_t)s * n + i];
+            if (mpx) {
+                if (id == B200_BAD_SSID) continue;
+                id = c.sseq[(size_t)id * NE + s];
+            }
+            atomicOr(&s_mask[id >> 5], 1u << (id & 31));
+        }
+    }
+    __syncthreads();
+    if (k) {
+        int off = block_off[blockIdx.x];
+        for (int ww = 0; ww < w; ++ww) off += s_wsum[ww];
+        off += __popc(bal & ((1u << lane) - 1u));
+        keep_idx[off] = i;
+    }
+    for (int kk = tid; kk < n_words; kk += kHmmBlock)
+        if (s_mask[kk]) atomicOr(&mask[kk], s_mask[kk]);
+}
+
+// ------------------------------------------------------------ host launchers
+static size_t step_smem(const HmmDev &c) {
+    return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * c.n_emit * (c.n_emit + 1) + 16;
+}
+
+int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, int32_t beam,
+                    HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
+                    uint32_t *mask, int do_beam, cudaStream_t st) {
+    const int n_words = (c.n_sen + 31) / 32;
+    const int n_blocks = (p.n_hmm + kHmmBlock - 1) / kHmmBlock;
+    if (p.n_hmm <= 0) return B200_OK;
+    hmm_frame_init_kernel<<<1, 256, 0, st>>>(fr, mask, n_words);
+    B200_LAUNCH_CHECK();
+    const size_t sh = step_smem(c);
+    if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    // persistent-style grid: at most a few CTAs per SM, each strides the population
+    const int grid = std::min(n_blocks, 148 * 4);
+    if (c.n_emit == 3) hmm_step_kernel<3><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
+    else hmm_step_kernel<5><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
+    B200_LAUNCH_CHECK();
+    if (!do_beam) return B200_OK;
+    hmm_beam_flag_kernel<<<n_blocks, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
+    B200_LAUNCH_CHECK();
+    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, n_blocks, fr);
+    B200_LAUNCH_CHECK();
+    const size_t msh = (size_t)n_words * 4;
+    if (c.n_emit == 3) hmm_scatter_kernel<3><<<n_blocks, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    else hmm_scatter_kernel<5><<<n_blocks, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200

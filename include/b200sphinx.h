@@ -1,0 +1,274 @@
+/* b200sphinx.h -- C ABI of the B200-native acoustic-scoring / HMM-evaluation
+ * engine (libb200sphinx.so).
+ *
+ * Plain pointers and sizes only; no torch, no C++ types.  Every entry point
+ * names the reference interface it stands in for (paths relative to the
+ * cjac/cmusphinx tree; PS = pocketsphinx/src/libpocketsphinx,
+ * SB = sphinxbase/src/libsphinxbase, S3 = sphinx3/src/libs3decoder).
+ *
+ * Conventions
+ *   - return 0 on success, <0 on error (b200_last_error() gives the text);
+ *     constructors return NULL on error (the reference's *_init convention,
+ *     PS/acmod.c:110-127).
+ *   - "host" pointers are ordinary (pinned or pageable) CPU memory; "dev"
+ *     pointers are CUDA device memory on the context's device.
+ *   - There is NO CPU fallback: every scoring entry point launches sm_100a
+ *     kernels and fails with B200_ERR_CUDA if no device is present.
+ *   - Senone scores are the reference's negated, shifted (>>10) int16 log
+ *     scores, 0 = best (PS/hmm.h:63, PS/acmod.c:1075-1131).
+ */
+#ifndef B200SPHINX_H
+#define B200SPHINX_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK            0
+#define B200_ERR_ARG      -1
+#define B200_ERR_CUDA     -2
+#define B200_ERR_IO       -3
+#define B200_ERR_UNSUP    -4
+
+#define B200_SENSCR_SHIFT 10                      /* PS/hmm.h:63 */
+#define B200_WORST_SCORE  ((int32_t)0xE0000000)   /* PS/hmm.h:74 */
+#define B200_TMAT_WORST   (-255)                  /* PS/hmm.h:80 */
+#define B200_BAD_SSID     0xffff                  /* PS/bin_mdef.h:96 */
+#define B200_MAX_TOPN     8
+#define B200_MAX_STREAMS  4
+
+/* ------------------------------------------------------------------ misc */
+const char *b200_last_error(void);
+/* Library/ABI version and the number of CUDA devices visible (0 if none). */
+int  b200_abi_version(void);
+int  b200_device_count(void);
+/* Number of kernels this library has launched since load (bench.py's
+ * gpu_launches claim is read from here). */
+long long b200_launch_count(void);
+
+/* ------------------------------------------------------------- logmath */
+/* SB/util/logmath.c:61-161  logmath_init(base, shift, use_table=1): writes the
+ * log-add table (widened to uint32) and returns its size, or <0. */
+int  b200_logadd_table(double base, int shift, uint32_t *out, int max_out);
+/* SB/util/logmath.c:446-452 logmath_log(), :391-436 logmath_add() */
+int32_t b200_logmath_log(double base, int shift, double p);
+int32_t b200_logmath_add(double base, int shift, int32_t x, int32_t y);
+
+/* -------------------------------------------------- load-time precompute */
+/* PS/ms_gauden.c:314-359 gauden_dist_precompute: floors raw variances at
+ * varfloor, writes det[n_vec] and overwrites var[n_vec*len] with the
+ * integer-valued scaled 1/(2 var).  Host arrays. */
+int  b200_gauden_precompute(float *var, float *det, long n_vec, int len,
+                            float varfloor, double logbase);
+/* PS/ms_senone.c:236-258: normalise/floor/renormalise float mixture weights
+ * [n_sen][n_feat][n_cw] (modified in place) and quantise to uint8 with the
+ * +511 rounding bias, same logical order. */
+int  b200_mixw_quantize_ms(float *mixw, uint8_t *out, int n_sen, int n_feat,
+                           int n_cw, float mixwfloor, double logbase);
+/* PS/ptm_mgau.c:720-742, PS/s2_semi_mgau.c:1155-1177: same normalisation but
+ * quantised as -logmath_log(lmath_8b) clamped to [0,159]; output TRANSPOSED
+ * to [n_feat][n_cw][n_sen]. */
+int  b200_mixw_quantize_tied(float *mixw, uint8_t *out, int n_sen, int n_feat,
+                             int n_cw, float mixwfloor, double logbase);
+/* PS/tmat.c:275-296: float [n_tmat][n_src][n_src+1] -> uint8 negated
+ * log>>10 (255 = "zero"). */
+int  b200_tmat_quantize(float *tp, uint8_t *out, int n_tmat, int n_src,
+                        double tmatfloor, double logbase);
+
+/* ------------------------------------------------------ S3 binary files */
+/* SB/util/bio.c:137-262 + PS/ms_gauden.c:160-298 gauden_param_read.  First
+ * call with data=NULL to get dims = {n_mgau, n_feat, n_density, total_floats}
+ * and veclen[n_feat]; second call fills data[total_floats]. */
+int  b200_s3_read_gauden(const char *path, int32_t dims[4], int32_t *veclen,
+                         float *data);
+/* PS/ms_senone.c:149-282 header part: dims = {n_sen, n_feat, n_cw, total}. */
+int  b200_s3_read_mixw(const char *path, int32_t dims[4], float *data);
+/* PS/tmat.c:191-274: dims = {n_tmat, n_src, n_dst, total}. */
+int  b200_s3_read_tmat(const char *path, int32_t dims[4], float *data);
+/* PS/s2_semi_mgau.c:888-1089 read_sendump.  On input dims[0..2] hold the
+ * model's {n_feat, n_density, n_sen} (defaults when the file does not name
+ * them); on output dims = {n_feat, n_density, n_sen, n_clust (0 if none),
+ * row_bytes}.  mixw (NULL = query only) receives [n_feat][n_density][row_bytes]
+ * raw rows (4-bit packed, even senone in the low nibble, when cluster_bits is
+ * 4), cb the 16 cluster values when n_clust != 0. */
+int  b200_s3_read_sendump(const char *path, int32_t dims[5], uint8_t *mixw,
+                          uint8_t cb[16]);
+
+/* ============================================================ GMM scoring
+ * One handle type for the three pocketsphinx back-ends.  The handle owns a
+ * device-resident copy of the (precomputed) parameters.
+ */
+typedef struct b200_mgau b200_mgau_t;
+
+typedef struct {
+    int32_t n_mgau, n_feat, n_density, n_sen;
+    int32_t featlen[B200_MAX_STREAMS];
+    int32_t topn;       /* -topn  (PS cmdln_macro.h:351) */
+    int32_t aw;         /* -aw    (:331), ms only */
+    int32_t ds_ratio;   /* -ds    (:347); only 1 is supported on device */
+    double  logbase;    /* -logbase (:371) */
+    int32_t device;     /* CUDA device ordinal */
+} b200_mgau_cfg_t;
+
+/* ms back-end: PS/ms_mgau.c:79-141 ms_mgau_init.  mean/var/det are the
+ * PRECOMPUTED arrays [mgau][feat][density][featlen f] / [mgau][feat][density]
+ * (b200_gauden_precompute), mixw the ms-quantised uint8 [sen][feat][cw],
+ * sen2mgau[n_sen] the senone->codebook map (PS/ms_senone.c:297-340). */
+b200_mgau_t *b200_ms_create(const b200_mgau_cfg_t *cfg, const float *mean,
+                            const float *var, const float *det,
+                            const uint8_t *mixw, const uint32_t *sen2mgau);
+/* Convenience mirroring ms_mgau_init(config): reads S3 files, precomputes on
+ * the host exactly as the reference does, uploads.  senmgau is ".cont.",
+ * ".semi." or ".ptm." (then sen2cb must be given), as PS/ms_senone.c:297-340. */
+b200_mgau_t *b200_ms_load(const char *meanfile, const char *varfile,
+                          const char *mixwfile, const char *senmgau,
+                          const uint8_t *sen2cb, double varfloor,
+                          double mixwfloor, int topn, int aw, double logbase,
+                          int device);
+
+/* ptm / s2_semi back-ends: PS/ptm_mgau.c:775-872 ptm_mgau_init,
+ * PS/s2_semi_mgau.c:1240-1330 s2_semi_mgau_init.  mixw is
+ * [n_feat][n_density][row_bytes]: 8-bit rows of n_sen bytes, or (n_clust!=0)
+ * 4-bit packed rows of (n_sen+1)/2 bytes with the 16-entry cluster codebook
+ * mixw_cb.  sen2cb[n_sen] (ptm only; NULL for s2_semi = one codebook). */
+b200_mgau_t *b200_ptm_create(const b200_mgau_cfg_t *cfg, const float *mean,
+                             const float *var, const float *det,
+                             const uint8_t *mixw, int n_clust,
+                             const uint8_t *mixw_cb, const uint8_t *sen2cb);
+b200_mgau_t *b200_semi_create(const b200_mgau_cfg_t *cfg, const float *mean,
+                              const float *var, const float *det,
+                              const uint8_t *mixw, int n_clust,
+                              const uint8_t *mixw_cb);
+
+/* ps_mgaufuncs_t.free (PS/acmod.h:111) */
+void b200_mgau_free(b200_mgau_t *m);
+/* ps_mgaufuncs_t.name: "b200_ms" | "b200_ptm" | "b200_semi" */
+const char *b200_mgau_name(const b200_mgau_t *m);
+int  b200_mgau_n_sen(const b200_mgau_t *m);
+int  b200_mgau_featdim(const b200_mgau_t *m);   /* sum of stream lengths */
+
+/* ps_mgaufuncs_t.transform (PS/acmod.h:108; gauden_mllr_transform
+ * PS/ms_gauden.c:551-605): replace the device parameters by freshly
+ * transformed + precomputed host arrays. */
+int  b200_mgau_update_params(b200_mgau_t *m, const float *mean,
+                             const float *var, const float *det);
+
+/* Which kernel family scores dense batches for the ms back-end:
+ *   0 = exact CUDA-core path (sequential f32, bit-exact vs the reference),
+ *   1 = tcgen05 tensor-core Mahalanobis GEMM (TF32x3 split, fused top-N /
+ *       log-add epilogue; .cont. single-stream models only).
+ * Default: 1 when the model shape allows it, else 0. */
+int  b200_mgau_set_path(b200_mgau_t *m, int path);
+int  b200_mgau_get_path(const b200_mgau_t *m);
+
+/* Batched dense scoring == ps_mgau_frame_eval(..., compallsen=1) for frames
+ * 0..T-1 (PS/ms_mgau.c:162-205, PS/ptm_mgau.c:405-450,
+ * PS/s2_semi_mgau.c:840-886): feat [T][featdim] float32 (streams
+ * concatenated as in acmod's feat_buf, SB/feat/feat.c:519-549),
+ * out [T][n_sen] int16.  Host version copies in/out (pinned staging inside). */
+int  b200_mgau_score_host(b200_mgau_t *m, const float *feat, int T, int16_t *out);
+/* Same with device-resident input/output on `stream` (a cudaStream_t cast to
+ * void*, NULL = default stream); asynchronous. */
+int  b200_mgau_score_dev(b200_mgau_t *m, const float *d_feat, int T,
+                         int16_t *d_out, void *stream);
+
+/* Drop-in for one ps_mgaufuncs_t.frame_eval call (PS/acmod.h:99-105): feat is
+ * the reference's mfcc_t** (one pointer per stream), senone_active the uint8
+ * delta list of PS/acmod.c:1219-1271.  With compallsen==0 only active entries
+ * of senscr are meaningful (ms) / others are zero-minus-best (ptm) / zero
+ * (s2_semi), as in the reference. */
+int  b200_mgau_frame_eval(b200_mgau_t *m, int16_t *senscr,
+                          const uint8_t *senone_active, int32_t n_senone_active,
+                          const float *const *feat, int32_t frame,
+                          int32_t compallsen);
+
+/* Utterance-batched variant used by the plug-in: score all T frames of an
+ * utterance once (dense, un-normalised pieces kept on the host), then serve
+ * frame_eval calls from the cache applying the active-set-dependent
+ * normalisation (ms: PS/ms_mgau.c:226-248; ptm: PS/ptm_mgau.c:267-288,390-397)
+ * on the host with the caller's active list. */
+int  b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T);
+int  b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr,
+                         const uint8_t *senone_active, int32_t n_senone_active,
+                         int32_t frame, int32_t compallsen);
+
+/* Timing of the last score_* call's dominant kernel(s) in milliseconds
+ * (CUDA events on the launching stream). which: 0 = total device time,
+ * 1 = operand-prep kernel, 2 = main scoring kernel, 3 = normalise kernel. */
+float b200_mgau_last_ms(const b200_mgau_t *m, int which);
+
+/* ======================================================= HMM evaluation
+ * Batched hmm_vit_eval (PS/hmm.c:224-807) over a structure-of-arrays
+ * population, plus the active-senone gather (PS/acmod.c:1178-1271,
+ * PS/ngram_search_fwdtree.c:518-555) and the beam/compaction step
+ * (PS/ngram_search_fwdtree.c:714-869 beam test only).
+ */
+typedef struct b200_hmmctx b200_hmmctx_t;
+
+/* hmm_context_init (PS/hmm.c:55-77): tp [n_tmat][n_emit][n_emit+1] uint8,
+ * sseq [n_sseq][n_emit] uint16.  n_emit must be 3 or 5. */
+b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat,
+                                   const uint16_t *sseq, int n_sseq, int n_sen,
+                                   int device);
+void b200_hmm_ctx_free(b200_hmmctx_t *c);
+
+/* The SoA population (all arrays length n_hmm unless noted; state-major:
+ * score[st*n_hmm + i]).  Same fields as hmm_t (PS/hmm.h:156-173). */
+typedef struct {
+    int32_t  n_hmm;
+    int32_t *score;        /* [n_emit][n_hmm] */
+    int32_t *history;      /* [n_emit][n_hmm] */
+    int32_t *out_score;    /* [n_hmm] */
+    int32_t *out_history;  /* [n_hmm] */
+    uint16_t *senid;       /* [n_emit][n_hmm]: senone ids, or ssids if mpx */
+    int16_t *tmatid;       /* [n_hmm] */
+    uint8_t *mpx;          /* [n_hmm] */
+    int32_t *bestscore;    /* [n_hmm] out */
+} b200_hmm_soa_t;
+
+/* Host round trip: upload SoA, run n_frames steps with senscr[f] =
+ * senscr + f*n_sen (hmm_context_set_senscore per frame), download.
+ * best_out[n_frames] gets max bestscore per frame. */
+int  b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h,
+                        const int16_t *senscr, int n_frames, int32_t *best_out);
+
+/* Device-resident population for benchmarking / resident search state. */
+int  b200_hmm_pop_upload(b200_hmmctx_t *c, const b200_hmm_soa_t *h);
+int  b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h);
+/* One frame on the resident population: hmm_vit_eval for every HMM, frame
+ * best (max), then beam test bestscore > best + beam
+ * (PS/ngram_search_fwdtree.c:741,800) -> keep[n_hmm] uint8 flags and an
+ * ORDER-PRESERVING compacted index list; then active-senone bitmask of the
+ * survivors (acmod_activate_hmm) -> mask[(n_sen+31)/32].
+ * d_senscr: device int16[n_sen].  Results stay on the device; fetch with
+ * b200_hmm_step_results. */
+int  b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam,
+                       void *stream);
+int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep,
+                           int32_t *keep_idx /* [n_hmm] or NULL */,
+                           uint32_t *sen_mask /* [(n_sen+31)/32] or NULL */);
+/* Host-input convenience for tests: senscr on the host. */
+int  b200_hmm_step_host(b200_hmmctx_t *c, const int16_t *senscr, int32_t beam);
+float b200_hmm_last_ms(const b200_hmmctx_t *c);
+
+/* acmod_flags2list (PS/acmod.c:1219-1271): bitmask -> uint8 delta list with
+ * the reference's lossy >255 bridging.  Host utility; returns n written. */
+int  b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_out);
+
+/* -------------------------------------------------- device memory helpers
+ * (so a non-torch host can keep buffers resident) */
+void *b200_dev_alloc(size_t bytes, int device);
+void  b200_dev_free(void *p);
+int   b200_dev_upload(void *dst, const void *src, size_t bytes);
+int   b200_dev_download(void *dst, const void *src, size_t bytes);
+void *b200_host_alloc_pinned(size_t bytes);
+void  b200_host_free_pinned(void *p);
+int   b200_dev_sync(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPHINX_H */

@@ -1,0 +1,101 @@
+/* oracle/sphinx_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("port") of the pocketsphinx / sphinx3 hot path used as the
+ * parity checker for the CUDA engine.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library;
+ * the product (cmusphinx_b200/) never does.
+ *
+ * Pinned against the reference itself (oracle/_ref, built from
+ * /root/reference by oracle/Makefile) in tests/test_oracle_vs_ref.py and
+ * against committed golden vectors in tests/golden/.
+ */
+#ifndef SPHINX_ORACLE_H
+#define SPHINX_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_SENSCR_SHIFT 10
+#define ORC_WORST_SCORE ((int32_t)0xE0000000)
+#define ORC_TMAT_WORST (-255)
+#define ORC_BAD_SSID 0xffff
+#define ORC_WORST_DIST ((int32_t)0x80000000)
+
+/* ---- logmath (sphinxbase/src/libsphinxbase/util/logmath.c) ---- */
+typedef struct {
+    double base, inv_log_of_base;
+    int shift;
+    int32_t zero;
+    uint32_t table_size;
+    uint32_t *table; /* widened to 32 bit whatever the reference width */
+} orc_logmath_t;
+
+orc_logmath_t *orc_logmath_init(double base, int shift, int use_table);
+void orc_logmath_free(orc_logmath_t *lm);
+int orc_logmath_table(const orc_logmath_t *lm, int32_t *out, int max_out);
+int32_t orc_logmath_log(const orc_logmath_t *lm, double p);
+int32_t orc_logmath_ln_to_log(const orc_logmath_t *lm, double ln_p);
+int32_t orc_logmath_add(const orc_logmath_t *lm, int32_t x, int32_t y);
+
+/* ---- load-time precompute ---- */
+/* ms_gauden.c:314-359. var: in = raw variances, out = scaled 1/(2 var);
+ * det: out.  n_vec = number of (mgau,feat,density) vectors of length len. */
+int orc_gauden_precompute(float *var, float *det, long n_vec, int len,
+                          float varfloor, double logbase);
+/* ms_senone.c:236-258. in: [n_sen][n_feat][n_cw] float32 (rows normalised in
+ * place), out: same logical order uint8. */
+int orc_mixw_quantize(float *mixw, uint8_t *out, int n_sen, int n_feat,
+                      int n_cw, float mixwfloor, double logbase);
+/* tmat.c:275-296.  in: [n_tmat][n_src][n_src+1] float32, out: uint8. */
+int orc_tmat_quantize(float *tp, uint8_t *out, int n_tmat, int n_src,
+                      double tpfloor, double logbase);
+
+/* ---- multi-stream GMM scoring (ms_mgau.c / ms_gauden.c / ms_senone.c) ---- */
+typedef struct {
+    int n_mgau, n_feat, n_density, n_sen, topn, aw;
+    int featlen[8];
+    int featoff[8];          /* offset of stream f inside a frame vector */
+    int veclen;              /* sum of featlen */
+    const float *mean;       /* [mgau][feat][density][featlen[f]] */
+    const float *var;        /* precomputed, same layout */
+    const float *det;        /* [mgau][feat][density] */
+    const uint8_t *mixw;     /* [sen][feat][cw] */
+    const uint32_t *sen2mgau;/* [sen] */
+    orc_logmath_t *lmath10;  /* base, shift 10, table */
+} orc_ms_model_t;
+
+orc_ms_model_t *orc_ms_model_new(int n_mgau, int n_feat, const int *featlen,
+                                 int n_density, int n_sen, int topn, int aw,
+                                 const float *mean, const float *var,
+                                 const float *det, const uint8_t *mixw,
+                                 const uint32_t *sen2mgau, double logbase);
+void orc_ms_model_free(orc_ms_model_t *m);
+
+/* Top-N of one codebook/stream, ms_gauden.c:417-523.  ids/dists: [topn]. */
+void orc_ms_compute_dist(const orc_ms_model_t *m, int mgau, int feat,
+                         const float *obs, int32_t *ids, float *dists);
+/* One frame, ms_mgau.c:162-252.  feat: [veclen]; senscr: [n_sen]. */
+int orc_ms_frame_eval(const orc_ms_model_t *m, const float *feat,
+                      const uint8_t *senone_active, int n_senone_active,
+                      int compallsen, int16_t *senscr);
+/* T frames with compallsen=1.  feat [T][veclen], out [T][n_sen]. */
+int orc_ms_eval_all(const orc_ms_model_t *m, const float *feat, int T,
+                    int16_t *out);
+
+/* ---- HMM Viterbi step (hmm.c:224-807), SoA batch ---- */
+int32_t orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat,
+                           const uint16_t *sseq, int n_sseq,
+                           const int16_t *senscr, int32_t *score,
+                           int32_t *history, int32_t *out_score,
+                           int32_t *out_history, uint16_t *senid,
+                           const uint16_t *ssid, const int16_t *tmatid,
+                           const uint8_t *mpx, int32_t *bestscore,
+                           int n_frames_repeat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
