@@ -49,7 +49,12 @@ struct b200_mgau {
     float *d_feat[2] = {nullptr, nullptr}; int16_t *d_out[2] = {nullptr, nullptr};
     size_t feat_cap[2] = {0, 0}, out_cap[2] = {0, 0};
     cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ring of event quadruples: one per timed scoring call, so a caller can run
+    // K asynchronous steps and read every step's kernel times afterwards
+    static constexpr int kRing = 64;
+    cudaEvent_t ring[kRing][4] = {};
+    cudaEvent_t *ev = ring[0];
+    long long n_timed = 0;
     float last_ms[4] = {0, 0, 0, 0};
     // per-frame / utterance cache
     float *d_ufeat = nullptr; size_t ufeat_cap = 0;
@@ -122,8 +127,9 @@ b200_mgau *mgau_common(int kind, const b200_mgau_cfg_t *cfg, const float *mean, 
     g.mean = m->d_mean; g.var = m->d_var; g.det = m->d_det;
     for (int i = 0; i < 2; ++i)
         if (cudaStreamCreateWithFlags(&m->st[i], cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); b200_mgau_free(m); return nullptr; }
-    for (int i = 0; i < 4; ++i)
-        if (cudaEventCreate(&m->ev[i]) != cudaSuccess) { set_error("event create failed"); b200_mgau_free(m); return nullptr; }
+    for (int r = 0; r < b200_mgau::kRing; ++r)
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreate(&m->ring[r][i]) != cudaSuccess) { set_error("event create failed"); b200_mgau_free(m); return nullptr; }
     if (cudaMalloc((void **)&m->d_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
         cudaMallocHost((void **)&m->h_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
         cudaMallocHost((void **)&m->h_frame, (size_t)g.veclen * 4 + 16) != cudaSuccess) {
@@ -140,7 +146,11 @@ int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cu
     const GmmDev &g = m->g;
     if (T <= 0) return B200_OK;
     int rc;
-    if (timed) cudaEventRecord(m->ev[0], st);
+    if (timed) {
+        m->ev = m->ring[m->n_timed % b200_mgau::kRing];
+        ++m->n_timed;
+        cudaEventRecord(m->ev[0], st);
+    }
     if (m->kind == 0 && m->path == 1 && m->tc) {
         if ((rc = tc_score(m->tc, g, d_feat, T, d_out, st, timed ? &m->ev[1] : nullptr))) return rc;
     } else {
@@ -318,7 +328,8 @@ void b200_mgau_free(b200_mgau_t *m) {
     cudaFree(m->d_mean); cudaFree(m->d_var); cudaFree(m->d_det); cudaFree(m->d_mixw);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2mgau); cudaFree(m->d_lists);
     for (int i = 0; i < 2; ++i) { cudaFree(m->d_feat[i]); cudaFree(m->d_out[i]); if (m->st[i]) cudaStreamDestroy(m->st[i]); }
-    for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    for (int r = 0; r < b200_mgau::kRing; ++r)
+        for (int i = 0; i < 4; ++i) if (m->ring[r][i]) cudaEventDestroy(m->ring[r][i]);
     cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_active); cudaFree(m->d_row);
     if (m->h_row) cudaFreeHost(m->h_row);
     if (m->h_frame) cudaFreeHost(m->h_frame);
@@ -418,6 +429,24 @@ int b200_mgau_score_host(b200_mgau_t *m, const float *feat, int T, int16_t *out)
 float b200_mgau_last_ms(const b200_mgau_t *m, int which) {
     if (!m || which < 0 || which > 3) return -1.f;
     return m->last_ms[which];
+}
+
+float b200_mgau_timing_avg(b200_mgau_t *m, int n_calls, int which) {
+    if (!m || which < 0 || which > 3 || n_calls < 1) return -1.f;
+    if (n_calls > b200_mgau::kRing) n_calls = b200_mgau::kRing;
+    if ((long long)n_calls > m->n_timed) n_calls = (int)m->n_timed;
+    if (n_calls < 1) return -1.f;
+    if (cudaSetDevice(m->device) != cudaSuccess) return -1.f;
+    double sum = 0;
+    for (int k = 0; k < n_calls; ++k) {
+        cudaEvent_t *e = m->ring[(m->n_timed - 1 - k) % b200_mgau::kRing];
+        float ms = 0;
+        cudaError_t rc = which == 0 ? cudaEventElapsedTime(&ms, e[0], e[3])
+                                    : cudaEventElapsedTime(&ms, e[which - 1], e[which]);
+        if (rc != cudaSuccess) { set_error("timing not available: %s", cudaGetErrorString(rc)); cudaGetLastError(); return -1.f; }
+        sum += ms;
+    }
+    return (float)(sum / n_calls);
 }
 
 // ------------------------------------------------- utterance / frame serving

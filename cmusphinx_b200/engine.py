@@ -1,0 +1,429 @@
+"""Host-side mirror of the reference's back-end interface over the C ABI.
+
+Names follow the reference: an ``Mgau`` is a ``ps_mgau_t`` (PS/acmod.h:95-124)
+with ``frame_eval`` / ``transform`` / ``free``; ``HmmContext`` is
+``hmm_context_t`` (PS/hmm.h:136-151) and ``HmmPopulation`` a structure-of-arrays
+batch of ``hmm_t`` (PS/hmm.h:156-173).  All arithmetic happens inside
+libb200sphinx.so on the GPU; numpy is used only to hold buffers.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, B200Error, MgauCfg, HmmSoa
+
+# -logbase is read with cmd_ln_float32_r (PS/pocketsphinx.c:223), so the
+# reference's effective base is (double)(float)1.0001.
+LOGBASE = float(np.float32(1.0001))
+WORST_SCORE = np.int32(-0x20000000)   # (int)0xE0000000, PS/hmm.h:74
+BAD_SSID = 0xFFFF
+
+
+def _p(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def device_count() -> int:
+    return lib.b200_device_count()
+
+
+def launch_count() -> int:
+    return lib.b200_launch_count()
+
+
+# ------------------------------------------------------------ host utilities
+def logadd_table(base: float = 1.0001, shift: int = 10) -> np.ndarray:
+    n = lib.b200_logadd_table(base, shift, None, 0)
+    check(n, "logadd_table")
+    out = np.zeros(n, np.uint32)
+    lib.b200_logadd_table(base, shift, _p(out, C.c_uint32), n)
+    return out
+
+
+def gauden_precompute(var: np.ndarray, length: int, varfloor: float = 1e-4, logbase: float = LOGBASE):
+    """var: float32 [..., length] raw variances -> (scaled 1/(2var), det[...])."""
+    v = _c(var, np.float32).copy().reshape(-1, length)
+    det = np.zeros(v.shape[0], np.float32)
+    check(lib.b200_gauden_precompute(_p(v, C.c_float), _p(det, C.c_float), v.shape[0], length,
+                                     varfloor, logbase), "gauden_precompute")
+    return v.reshape(var.shape), det.reshape(var.shape[:-1])
+
+
+def mixw_quantize_ms(mixw: np.ndarray, mixwfloor: float = 1e-7, logbase: float = LOGBASE) -> np.ndarray:
+    m = _c(mixw, np.float32).copy()
+    n_sen, n_feat, n_cw = m.shape
+    out = np.zeros(m.shape, np.uint8)
+    check(lib.b200_mixw_quantize_ms(_p(m, C.c_float), _p(out, C.c_uint8), n_sen, n_feat, n_cw,
+                                    mixwfloor, logbase), "mixw_quantize_ms")
+    return out
+
+
+def mixw_quantize_tied(mixw: np.ndarray, mixwfloor: float = 1e-7, logbase: float = LOGBASE) -> np.ndarray:
+    m = _c(mixw, np.float32).copy()
+    n_sen, n_feat, n_cw = m.shape
+    out = np.zeros((n_feat, n_cw, n_sen), np.uint8)
+    check(lib.b200_mixw_quantize_tied(_p(m, C.c_float), _p(out, C.c_uint8), n_sen, n_feat, n_cw,
+                                      mixwfloor, logbase), "mixw_quantize_tied")
+    return out
+
+
+def tmat_quantize(tp: np.ndarray, tmatfloor: float = 1e-4, logbase: float = LOGBASE) -> np.ndarray:
+    t = _c(tp, np.float32).copy()
+    n_tmat, n_src, n_dst = t.shape
+    assert n_dst == n_src + 1
+    out = np.zeros(t.shape, np.uint8)
+    check(lib.b200_tmat_quantize(_p(t, C.c_float), _p(out, C.c_uint8), n_tmat, n_src, tmatfloor, logbase),
+          "tmat_quantize")
+    return out
+
+
+def flags2list(mask: np.ndarray, n_sen: int) -> np.ndarray:
+    m = _c(mask, np.uint32)
+    out = np.zeros(n_sen * 2 + 8, np.uint8)
+    n = check(lib.b200_flags2list(_p(m, C.c_uint32), n_sen, _p(out, C.c_uint8), out.size), "flags2list")
+    return out[:n].copy()
+
+
+def read_gauden(path: str):
+    dims = (C.c_int32 * 4)()
+    vl = (C.c_int32 * 64)()
+    check(lib.b200_s3_read_gauden(path.encode(), dims, vl, None), "read_gauden")
+    data = np.zeros(dims[3], np.float32)
+    check(lib.b200_s3_read_gauden(path.encode(), dims, vl, _p(data, C.c_float)), "read_gauden")
+    return dict(n_mgau=dims[0], n_feat=dims[1], n_density=dims[2], veclen=[vl[i] for i in range(dims[1])],
+                data=data)
+
+
+def _read4(fn, path):
+    dims = (C.c_int32 * 4)()
+    check(fn(path.encode(), dims, None), path)
+    data = np.zeros(dims[3], np.float32)
+    check(fn(path.encode(), dims, _p(data, C.c_float)), path)
+    return data.reshape(dims[0], dims[1], dims[2])
+
+
+def read_mixw(path: str) -> np.ndarray:
+    return _read4(lib.b200_s3_read_mixw, path)
+
+
+def read_tmat(path: str) -> np.ndarray:
+    return _read4(lib.b200_s3_read_tmat, path)
+
+
+def read_sendump(path: str, n_feat: int, n_density: int, n_sen: int):
+    dims = (C.c_int32 * 5)(n_feat, n_density, n_sen, 0, 0)
+    check(lib.b200_s3_read_sendump(path.encode(), dims, None, None), "read_sendump")
+    mixw = np.zeros((dims[0], dims[1], dims[4]), np.uint8)
+    cb = np.zeros(16, np.uint8)
+    dims2 = (C.c_int32 * 5)(n_feat, n_density, n_sen, 0, 0)
+    check(lib.b200_s3_read_sendump(path.encode(), dims2, _p(mixw, C.c_uint8), _p(cb, C.c_uint8)), "read_sendump")
+    return dict(n_feat=dims[0], n_density=dims[1], n_sen=dims[2], n_clust=dims[3], row_bytes=dims[4],
+                mixw=mixw, mixw_cb=cb)
+
+
+# --------------------------------------------------------------------- GMM
+@dataclass
+class MgauConfig:
+    n_mgau: int
+    n_feat: int
+    n_density: int
+    n_sen: int
+    featlen: Sequence[int]
+    topn: int = 4
+    aw: int = 1
+    ds_ratio: int = 1
+    logbase: float = LOGBASE
+    device: int = 0
+
+    def to_c(self) -> MgauCfg:
+        c = MgauCfg()
+        c.n_mgau, c.n_feat, c.n_density, c.n_sen = self.n_mgau, self.n_feat, self.n_density, self.n_sen
+        for i, l in enumerate(self.featlen):
+            c.featlen[i] = int(l)
+        c.topn, c.aw, c.ds_ratio, c.logbase, c.device = self.topn, self.aw, self.ds_ratio, self.logbase, self.device
+        return c
+
+
+class Mgau:
+    """A ``ps_mgau_t`` living on the GPU (ms / ptm / s2_semi flavour)."""
+
+    def __init__(self, handle, cfg: Optional[MgauConfig] = None):
+        if not handle:
+            raise B200Error(f"mgau init failed: {_lib.last_error()}")
+        self._h = C.c_void_p(handle)
+        self.cfg = cfg
+        self.n_sen = lib.b200_mgau_n_sen(self._h)
+        self.featdim = lib.b200_mgau_featdim(self._h)
+        self.frame_idx = 0   # ps_mgau_t.frame_idx (PS/acmod.h:115)
+
+    # vt->name
+    @property
+    def name(self) -> str:
+        return lib.b200_mgau_name(self._h).decode()
+
+    @property
+    def path(self) -> int:
+        return lib.b200_mgau_get_path(self._h)
+
+    def set_path(self, path: int):
+        check(lib.b200_mgau_set_path(self._h, path), "set_path")
+
+    # vt->free
+    def free(self):
+        if self._h:
+            lib.b200_mgau_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # vt->transform: the caller supplies already transformed + precomputed arrays
+    def transform(self, mean, var, det):
+        mean, var, det = _c(mean, np.float32), _c(var, np.float32), _c(det, np.float32)
+        check(lib.b200_mgau_update_params(self._h, _p(mean, C.c_float), _p(var, C.c_float), _p(det, C.c_float)),
+              "transform")
+
+    # vt->frame_eval (PS/acmod.h:99-105)
+    def frame_eval(self, senscr: np.ndarray, senone_active: Optional[np.ndarray], n_senone_active: int,
+                   feat: Sequence[np.ndarray], frame: int, compallsen: bool) -> int:
+        assert senscr.dtype == np.int16 and senscr.flags.c_contiguous and senscr.size >= self.n_sen
+        streams = [_c(f, np.float32) for f in feat]
+        ptrs = (C.POINTER(C.c_float) * len(streams))(*[_p(s, C.c_float) for s in streams])
+        act = None
+        if senone_active is not None:
+            senone_active = _c(senone_active, np.uint8)
+            act = _p(senone_active, C.c_uint8)
+        check(lib.b200_mgau_frame_eval(self._h, _p(senscr, C.c_int16), act, int(n_senone_active), ptrs,
+                                       int(frame), 1 if compallsen else 0), "frame_eval")
+        return 0
+
+    # batched compallsen scoring, host buffers (the e2e path)
+    def score(self, feat: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        feat = _c(feat, np.float32)
+        T = feat.shape[0] if feat.ndim == 2 else feat.size // max(self.featdim, 1)
+        if out is None:
+            out = np.empty((T, self.n_sen), np.int16)
+        assert out.dtype == np.int16 and out.flags.c_contiguous and out.size >= T * self.n_sen
+        check(lib.b200_mgau_score_host(self._h, feat.ctypes.data, T, out.ctypes.data), "score_host")
+        return out
+
+    def score_ptr(self, feat_ptr: int, T: int, out_ptr: int):
+        """Host pointers (e.g. pinned torch tensors)."""
+        check(lib.b200_mgau_score_host(self._h, feat_ptr, T, out_ptr), "score_host")
+
+    def score_dev(self, d_feat: int, T: int, d_out: int, stream: int = 0):
+        """Device pointers; synchronous and timed when stream == 0."""
+        check(lib.b200_mgau_score_dev(self._h, d_feat, T, d_out, stream or None), "score_dev")
+
+    def last_ms(self, which: int = 0) -> float:
+        return lib.b200_mgau_last_ms(self._h, which)
+
+    def timing_avg(self, n_calls: int, which: int = 2) -> float:
+        """Mean device time (ms) of section `which` (0 total, 1 operand prep, 2
+        scoring kernels, 3 normalise) over the last n_calls score_dev calls."""
+        return lib.b200_mgau_timing_avg(self._h, n_calls, which)
+
+    # utterance-batched serving (what the plug-in does)
+    def utt_begin(self, feat: np.ndarray):
+        feat = _c(feat, np.float32)
+        T = feat.shape[0]
+        check(lib.b200_mgau_utt_begin(self._h, feat.ctypes.data, T), "utt_begin")
+
+    def utt_frame(self, senscr: np.ndarray, senone_active: Optional[np.ndarray], n_senone_active: int,
+                  frame: int, compallsen: bool):
+        act = None
+        if senone_active is not None:
+            senone_active = _c(senone_active, np.uint8)
+            act = _p(senone_active, C.c_uint8)
+        check(lib.b200_mgau_utt_frame(self._h, _p(senscr, C.c_int16), act, int(n_senone_active), int(frame),
+                                      1 if compallsen else 0), "utt_frame")
+
+
+def ms_from_arrays(cfg: MgauConfig, mean, var_pre, det, mixw_q, sen2mgau) -> Mgau:
+    """ms_mgau_init from already precomputed arrays (see b200_ms_create)."""
+    mean, var_pre, det = _c(mean, np.float32), _c(var_pre, np.float32), _c(det, np.float32)
+    mixw_q, sen2mgau = _c(mixw_q, np.uint8), _c(sen2mgau, np.uint32)
+    c = cfg.to_c()
+    h = lib.b200_ms_create(C.byref(c), _p(mean, C.c_float), _p(var_pre, C.c_float), _p(det, C.c_float),
+                           _p(mixw_q, C.c_uint8), _p(sen2mgau, C.c_uint32))
+    return Mgau(h, cfg)
+
+
+def ms_from_files(mean: str, var: str, mixw: str, senmgau: str = ".cont.", sen2cb=None, varfloor=1e-4,
+                  mixwfloor=1e-7, topn=4, aw=1, logbase=LOGBASE, device=0) -> Mgau:
+    """ms_mgau_init(config) (PS/ms_mgau.c:79-141) on S3 parameter files."""
+    s2c = None
+    if sen2cb is not None:
+        sen2cb = _c(sen2cb, np.uint8)
+        s2c = _p(sen2cb, C.c_uint8)
+    h = lib.b200_ms_load(mean.encode(), var.encode(), mixw.encode(), senmgau.encode(), s2c, varfloor,
+                         mixwfloor, topn, aw, logbase, device)
+    return Mgau(h, None)
+
+
+def _tied(kind, cfg, mean, var_pre, det, mixw_rows, n_clust, mixw_cb, sen2cb):
+    mean, var_pre, det = _c(mean, np.float32), _c(var_pre, np.float32), _c(det, np.float32)
+    mixw_rows = _c(mixw_rows, np.uint8)
+    cbp = None
+    if n_clust:
+        mixw_cb = _c(mixw_cb, np.uint8)
+        cbp = _p(mixw_cb, C.c_uint8)
+    c = cfg.to_c()
+    if kind == 1:
+        sen2cb = _c(sen2cb, np.uint8)
+        h = lib.b200_ptm_create(C.byref(c), _p(mean, C.c_float), _p(var_pre, C.c_float), _p(det, C.c_float),
+                                _p(mixw_rows, C.c_uint8), int(n_clust), cbp, _p(sen2cb, C.c_uint8))
+    else:
+        h = lib.b200_semi_create(C.byref(c), _p(mean, C.c_float), _p(var_pre, C.c_float), _p(det, C.c_float),
+                                 _p(mixw_rows, C.c_uint8), int(n_clust), cbp)
+    return Mgau(h, cfg)
+
+
+def ptm_from_arrays(cfg, mean, var_pre, det, mixw_rows, sen2cb, n_clust=0, mixw_cb=None) -> Mgau:
+    """ptm_mgau_init (PS/ptm_mgau.c:775-872) from precomputed arrays."""
+    return _tied(1, cfg, mean, var_pre, det, mixw_rows, n_clust, mixw_cb, sen2cb)
+
+
+def semi_from_arrays(cfg, mean, var_pre, det, mixw_rows, n_clust=0, mixw_cb=None) -> Mgau:
+    """s2_semi_mgau_init (PS/s2_semi_mgau.c:1240-1330) from precomputed arrays."""
+    return _tied(2, cfg, mean, var_pre, det, mixw_rows, n_clust, mixw_cb, None)
+
+
+def tied_from_model_dir(hmmdir: str, n_sen: int, sen2cb=None, topn=4, varfloor=1e-4, mixwfloor=1e-7,
+                        logbase=LOGBASE, device=0) -> Mgau:
+    """Back-end selection of acmod_init_am (PS/acmod.c:110-127) for a model
+    directory holding means / variances / sendump|mixture_weights: one codebook
+    -> s2_semi, otherwise ptm (sen2cb = bin_mdef sen2cimap must be given)."""
+    import os
+    g = read_gauden(os.path.join(hmmdir, "means"))
+    v = read_gauden(os.path.join(hmmdir, "variances"))
+    n_mgau, n_feat, n_density, veclen = g["n_mgau"], g["n_feat"], g["n_density"], g["veclen"]
+    tot = sum(veclen)
+    mean = g["data"].reshape(n_mgau, -1)
+    var = v["data"].reshape(n_mgau, -1).copy()
+    det = np.zeros((n_mgau, n_feat, n_density), np.float32)
+    for mg in range(n_mgau):
+        off = 0
+        for f, l in enumerate(veclen):
+            blk = var[mg, n_density * off:n_density * (off + l)].reshape(n_density, l)
+            pv, pd = gauden_precompute(blk, l, varfloor, logbase)
+            var[mg, n_density * off:n_density * (off + l)] = pv.reshape(-1)
+            det[mg, f] = pd
+            off += l
+    assert mean.shape[1] == n_density * tot
+    sd = os.path.join(hmmdir, "sendump")
+    if os.path.exists(sd):
+        d = read_sendump(sd, n_feat, n_density, n_sen)
+        rows, n_clust, cb = d["mixw"], d["n_clust"], d["mixw_cb"]
+    else:
+        mw = read_mixw(os.path.join(hmmdir, "mixture_weights"))
+        rows, n_clust, cb = mixw_quantize_tied(mw, mixwfloor, logbase), 0, None
+    cfg = MgauConfig(n_mgau, n_feat, n_density, n_sen, veclen, topn=topn, logbase=logbase, device=device)
+    if n_mgau == 1:
+        return semi_from_arrays(cfg, mean, var, det, rows, n_clust, cb)
+    return ptm_from_arrays(cfg, mean, var, det, rows, sen2cb, n_clust, cb)
+
+
+# --------------------------------------------------------------------- HMM
+class HmmPopulation:
+    """Structure-of-arrays batch of hmm_t, state-major ([state][hmm])."""
+
+    def __init__(self, n_hmm: int, n_emit: int):
+        self.n_hmm, self.n_emit = n_hmm, n_emit
+        self.score = np.full((n_emit, n_hmm), WORST_SCORE, np.int32)
+        self.history = np.full((n_emit, n_hmm), -1, np.int32)
+        self.out_score = np.full(n_hmm, WORST_SCORE, np.int32)
+        self.out_history = np.full(n_hmm, -1, np.int32)
+        self.senid = np.zeros((n_emit, n_hmm), np.uint16)
+        self.tmatid = np.zeros(n_hmm, np.int16)
+        self.mpx = np.zeros(n_hmm, np.uint8)
+        self.bestscore = np.full(n_hmm, WORST_SCORE, np.int32)
+
+    def to_c(self) -> HmmSoa:
+        for k in ("score", "history", "out_score", "out_history", "senid", "tmatid", "mpx", "bestscore"):
+            a = getattr(self, k)
+            assert a.flags.c_contiguous
+        s = HmmSoa()
+        s.n_hmm = self.n_hmm
+        s.score, s.history = _p(self.score, C.c_int32), _p(self.history, C.c_int32)
+        s.out_score, s.out_history = _p(self.out_score, C.c_int32), _p(self.out_history, C.c_int32)
+        s.senid, s.tmatid = _p(self.senid, C.c_uint16), _p(self.tmatid, C.c_int16)
+        s.mpx, s.bestscore = _p(self.mpx, C.c_uint8), _p(self.bestscore, C.c_int32)
+        return s
+
+
+class HmmContext:
+    """hmm_context_t on the GPU: hmm_context_init(n_emit, tp, senscore, sseq)."""
+
+    def __init__(self, n_emit: int, tp: np.ndarray, sseq: Optional[np.ndarray], n_sen: int, device: int = 0):
+        tp = _c(tp, np.uint8)
+        assert tp.ndim == 3 and tp.shape[1] == n_emit and tp.shape[2] == n_emit + 1
+        n_sseq = 0 if sseq is None else sseq.shape[0]
+        ss = None if sseq is None else _c(sseq, np.uint16)
+        h = lib.b200_hmm_ctx_create(n_emit, _p(tp, C.c_uint8), tp.shape[0],
+                                    None if ss is None else _p(ss, C.c_uint16), n_sseq, n_sen, device)
+        if not h:
+            raise B200Error(f"hmm_context_init failed: {_lib.last_error()}")
+        self._h = C.c_void_p(h)
+        self.n_emit, self.n_sen = n_emit, n_sen
+
+    def free(self):
+        if self._h:
+            lib.b200_hmm_ctx_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def vit_eval(self, pop: HmmPopulation, senscr: np.ndarray) -> np.ndarray:
+        """hmm_vit_eval for every HMM, once per row of senscr ([n_frames][n_sen]
+        int16); pop is updated in place.  Returns the per-frame best score."""
+        senscr = _c(senscr, np.int16).reshape(-1, self.n_sen)
+        best = np.zeros(senscr.shape[0], np.int32)
+        soa = pop.to_c()
+        check(lib.b200_hmm_eval_host(self._h, C.byref(soa), _p(senscr, C.c_int16), senscr.shape[0],
+                                     _p(best, C.c_int32)), "hmm_eval_host")
+        return best
+
+    def upload(self, pop: HmmPopulation):
+        soa = pop.to_c()
+        check(lib.b200_hmm_pop_upload(self._h, C.byref(soa)), "pop_upload")
+
+    def download(self, pop: HmmPopulation):
+        soa = pop.to_c()
+        check(lib.b200_hmm_pop_download(self._h, C.byref(soa)), "pop_download")
+
+    def step(self, senscr, beam: int, n_hmm: int, want_idx=True):
+        """One search frame on the resident population: eval + beam + compaction +
+        active-senone gather.  senscr: host int16[n_sen] or a device pointer."""
+        if isinstance(senscr, np.ndarray):
+            s = _c(senscr, np.int16)
+            check(lib.b200_hmm_step_host(self._h, _p(s, C.c_int16), int(beam)), "hmm_step_host")
+        else:
+            check(lib.b200_hmm_step_dev(self._h, senscr, int(beam), None), "hmm_step_dev")
+        best, nk = C.c_int32(), C.c_int32()
+        idx = np.zeros(n_hmm, np.int32) if want_idx else None
+        mask = np.zeros((self.n_sen + 31) // 32, np.uint32)
+        check(lib.b200_hmm_step_results(self._h, C.byref(best), C.byref(nk),
+                                        _p(idx, C.c_int32) if want_idx else None, _p(mask, C.c_uint32)),
+              "hmm_step_results")
+        return best.value, (idx[:nk.value] if want_idx else nk.value), mask
+
+    def step_dev_async(self, d_senscr: int, beam: int):
+        check(lib.b200_hmm_step_dev(self._h, d_senscr, int(beam), None), "hmm_step_dev")
+
+    def last_ms(self) -> float:
+        return lib.b200_hmm_last_ms(self._h)

@@ -199,6 +199,10 @@ int  b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr,
  * (CUDA events on the launching stream). which: 0 = total device time,
  * 1 = operand-prep kernel, 2 = main scoring kernel, 3 = normalise kernel. */
 float b200_mgau_last_ms(const b200_mgau_t *m, int which);
+/* Average of the same quantity over the last n_calls (<= 64) score_dev calls,
+ * including asynchronous ones on a caller's stream; the caller must have
+ * synchronised that stream.  <0 on error. */
+float b200_mgau_timing_avg(b200_mgau_t *m, int n_calls, int which);
 
 /* ======================================================= HMM evaluation
  * Batched hmm_vit_eval (PS/hmm.c:224-807) over a structure-of-arrays

@@ -345,6 +345,39 @@ ref_acmod_score_feats(void *vh, const float *feat, int T, int16 *out)
     return 0;
 }
 
+/* One ps_mgau_frame_eval call with an explicit active list (uint8 deltas) or
+ * compallsen; the caller steps frames in order.  mgau->frame_idx is set to
+ * `frame` before the call and frame+1 after, like acmod_score/acmod_advance. */
+int
+ref_acmod_frame_eval(void *vh, const float *feat, const uint8 *deltas, int n_active,
+                     int frame, int compallsen, int16 *out)
+{
+    ref_acmod_t *h = vh;
+    acmod_t *a = h->acmod;
+    int nf = feat_dimension1(a->fcb), f, off = 0;
+    mfcc_t **fp = ckd_calloc(nf, sizeof(*fp));
+    for (f = 0; f < nf; ++f) {
+        fp[f] = (mfcc_t *)(feat + off);
+        off += feat_dimension2(a->fcb, f);
+    }
+    a->mgau->frame_idx = frame;
+    ps_mgau_frame_eval(a->mgau, out, (uint8 *)deltas, n_active, fp, frame, compallsen);
+    a->mgau->frame_idx = frame + 1;
+    ckd_free(fp);
+    return 0;
+}
+
+/* bin_mdef_sen2cimap for every senone (the ptm senone->codebook map,
+ * ptm_mgau.c:834-836). */
+void
+ref_acmod_sen2cimap(void *vh, uint8 *out)
+{
+    ref_acmod_t *h = vh;
+    int i, n = bin_mdef_n_sen(h->acmod->mdef);
+    for (i = 0; i < n; ++i)
+        out[i] = (uint8)bin_mdef_sen2cimap(h->acmod->mdef, i);
+}
+
 /* Feature extraction only: 13-dim cepstra [n_cep_frames][ceplen] -> dynamic
  * features [T][featdim] using the model's own feat_t in whole-utterance mode
  * (feat_s2mfc2feat_live with beginutt=endutt=TRUE, acmod.c:513-540).

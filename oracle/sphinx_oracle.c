@@ -1,0 +1,858 @@
+/* oracle/sphinx_oracle.c -- TEST INFRASTRUCTURE ONLY (see sphinx_oracle.h).
+ *
+ * Plain-C restatement of the pocketsphinx hot path, written from the
+ * reference's behaviour (file:line cited per function), never linked into the
+ * product.  Pinned against the reference's own compiled code (oracle/_ref,
+ * tests/test_oracle_vs_ref.py) and the golden vectors in tests/golden/.
+ */
+#include "sphinx_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SHIFT ORC_SENSCR_SHIFT
+
+/* ------------------------------------------------------------------ logmath
+ * sphinxbase/src/libsphinxbase/util/logmath.c:61-161 (init), :391-436 (add),
+ * :446-465 (log, ln_to_log). */
+orc_logmath_t *
+orc_logmath_init(double base, int shift, int use_table)
+{
+    orc_logmath_t *lm;
+    uint32_t i, n;
+    double byx;
+
+    if (base <= 1.0)
+        return NULL;
+    lm = calloc(1, sizeof(*lm));
+    lm->base = base;
+    lm->inv_log_of_base = 1.0 / log(base);
+    lm->shift = shift;
+    lm->zero = INT_MIN >> (shift + 2);
+    if (!use_table)
+        return lm;
+    for (i = 0, byx = 1.0;; ++i, byx /= base) {
+        int32_t k = (int32_t)(log(1.0 + byx) * lm->inv_log_of_base + 0.5 * (1 << shift)) >> shift;
+        if (k <= 0)
+            break;
+    }
+    n = i >> shift;
+    if (n < 255)
+        n = 255;
+    lm->table_size = n + 1;
+    lm->table = calloc(lm->table_size, sizeof(uint32_t));
+    {
+        uint32_t maxyx = (uint32_t)(log(2.0) / log(base) + 0.5) >> shift;
+        uint32_t mask = maxyx < 256 ? 0xffu : (maxyx < 65536 ? 0xffffu : 0xffffffffu);
+        for (i = 0, byx = 1.0;; ++i, byx /= base) {
+            int32_t k = (int32_t)(log(1.0 + byx) * lm->inv_log_of_base + 0.5 * (1 << shift)) >> shift;
+            if (lm->table[i >> shift] == 0)
+                lm->table[i >> shift] = (uint32_t)k & mask;
+            if (k <= 0)
+                break;
+        }
+    }
+    return lm;
+}
+
+void
+orc_logmath_free(orc_logmath_t *lm)
+{
+    if (lm) {
+        free(lm->table);
+        free(lm);
+    }
+}
+
+int
+orc_logmath_table(const orc_logmath_t *lm, int32_t *out, int max_out)
+{
+    uint32_t i;
+    for (i = 0; i < lm->table_size && (int)i < max_out; ++i)
+        out[i] = (int32_t)lm->table[i];
+    return (int)lm->table_size;
+}
+
+int32_t
+orc_logmath_log(const orc_logmath_t *lm, double p)
+{
+    if (p <= 0)
+        return lm->zero;
+    return (int32_t)(log(p) * lm->inv_log_of_base) >> lm->shift;
+}
+
+int32_t
+orc_logmath_ln_to_log(const orc_logmath_t *lm, double ln_p)
+{
+    return (int32_t)(ln_p * lm->inv_log_of_base) >> lm->shift;
+}
+
+int32_t
+orc_logmath_add(const orc_logmath_t *lm, int32_t x, int32_t y)
+{
+    int32_t d, r;
+    if (x <= lm->zero)
+        return y;
+    if (y <= lm->zero)
+        return x;
+    if (x > y) { d = x - y; r = x; }
+    else { d = y - x; r = y; }
+    if (d < 0 || (uint32_t)d >= lm->table_size)
+        return r;
+    return r + (int32_t)lm->table[d];
+}
+
+/* tied_mgau_common.h:104-121 */
+static int
+fast_add(const orc_logmath_t *lm, int mlx, int mly)
+{
+    int d, r;
+    if (mlx > mly) { d = mlx - mly; r = mly; }
+    else { d = mly - mlx; r = mlx; }
+    return r - (int)lm->table[d];
+}
+
+/* ------------------------------------------------------ load-time precompute */
+/* pocketsphinx/src/libpocketsphinx/vector.c:90-128 */
+static double
+sum_norm(float *v, int n)
+{
+    double s = 0.0;
+    int i;
+    for (i = 0; i < n; ++i)
+        s += v[i];
+    if (s != 0.0) {
+        double f = 1.0 / s;
+        for (i = 0; i < n; ++i)
+            v[i] *= f;
+    }
+    return s;
+}
+
+/* ms_gauden.c:314-359 */
+int
+orc_gauden_precompute(float *var, float *det, long n_vec, int len, float varfloor, double logbase)
+{
+    orc_logmath_t *lm = orc_logmath_init(logbase, 0, 0);
+    long v;
+    int i;
+    for (v = 0; v < n_vec; ++v) {
+        float *vp = var + v * len;
+        det[v] = 0;
+        for (i = 0; i < len; ++i) {
+            if (vp[i] < varfloor)
+                vp[i] = varfloor;
+            det[v] += (float)orc_logmath_log(lm, 1.0 / sqrt(vp[i] * 2.0 * M_PI));
+            vp[i] = (float)orc_logmath_ln_to_log(lm, 1.0 / (vp[i] * 2.0));
+        }
+    }
+    orc_logmath_free(lm);
+    return 0;
+}
+
+/* ms_senone.c:236-258 */
+int
+orc_mixw_quantize(float *mixw, uint8_t *out, int n_sen, int n_feat, int n_cw, float mixwfloor, double logbase)
+{
+    orc_logmath_t *lm = orc_logmath_init(logbase, 0, 0);
+    long r, nr = (long)n_sen * n_feat;
+    int c;
+    for (r = 0; r < nr; ++r) {
+        float *pdf = mixw + r * n_cw;
+        sum_norm(pdf, n_cw);
+        for (c = 0; c < n_cw; ++c)
+            if (pdf[c] < mixwfloor)
+                pdf[c] = mixwfloor;
+        sum_norm(pdf, n_cw);
+        for (c = 0; c < n_cw; ++c) {
+            int32_t p = -orc_logmath_log(lm, pdf[c]) + (1 << (SHIFT - 1)) - 1;
+            out[r * n_cw + c] = (p < (255 << SHIFT)) ? (uint8_t)(p >> SHIFT) : 255;
+        }
+    }
+    orc_logmath_free(lm);
+    return 0;
+}
+
+/* ptm_mgau.c:720-742 / s2_semi_mgau.c:1155-1177 */
+int
+orc_mixw_quantize_tied(float *mixw, uint8_t *out, int n_sen, int n_feat, int n_cw, float mixwfloor, double logbase)
+{
+    orc_logmath_t *lm8 = orc_logmath_init(logbase, SHIFT, 0);
+    int s, f, c;
+    for (s = 0; s < n_sen; ++s)
+        for (f = 0; f < n_feat; ++f) {
+            float *pdf = mixw + ((long)s * n_feat + f) * n_cw;
+            sum_norm(pdf, n_cw);
+            for (c = 0; c < n_cw; ++c)
+                if (pdf[c] < mixwfloor)
+                    pdf[c] = mixwfloor;
+            sum_norm(pdf, n_cw);
+            for (c = 0; c < n_cw; ++c) {
+                int32_t q = -orc_logmath_log(lm8, pdf[c]);
+                if (q > 159 || q < 0)
+                    q = 159;
+                out[((long)f * n_cw + c) * n_sen + s] = (uint8_t)q;
+            }
+        }
+    orc_logmath_free(lm8);
+    return 0;
+}
+
+/* tmat.c:275-296 */
+int
+orc_tmat_quantize(float *tp, uint8_t *out, int n_tmat, int n_src, double tpfloor, double logbase)
+{
+    orc_logmath_t *lm = orc_logmath_init(logbase, 0, 0);
+    int t, j, k, n_dst = n_src + 1;
+    for (t = 0; t < n_tmat; ++t)
+        for (j = 0; j < n_src; ++j) {
+            float *row = tp + ((long)t * n_src + j) * n_dst;
+            sum_norm(row, n_dst);
+            for (k = 0; k < n_dst; ++k)
+                if (row[k] != 0.0 && row[k] < tpfloor)
+                    row[k] = (float)tpfloor;
+            sum_norm(row, n_dst);
+            for (k = 0; k < n_dst; ++k) {
+                int ltp = -orc_logmath_log(lm, row[k]) >> SHIFT;
+                if (ltp > 255)
+                    ltp = 255;
+                out[((long)t * n_src + j) * n_dst + k] = (uint8_t)ltp;
+            }
+        }
+    orc_logmath_free(lm);
+    return 0;
+}
+
+/* acmod.c:1219-1271 */
+int
+orc_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas)
+{
+    int s, n = 0, l = 0;
+    for (s = 0; s < n_sen; ++s) {
+        int delta;
+        if (!(mask[s / 32] & (1u << (s % 32))))
+            continue;
+        delta = s - l;
+        while (delta > 255) {
+            deltas[n++] = 255;
+            delta -= 255;
+        }
+        deltas[n++] = (uint8_t)delta;
+        l = s;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------ ms back-end */
+orc_ms_model_t *
+orc_ms_model_new(int n_mgau, int n_feat, const int *featlen, int n_density, int n_sen, int topn, int aw,
+                 const float *mean, const float *var, const float *det, const uint8_t *mixw,
+                 const uint32_t *sen2mgau, double logbase)
+{
+    orc_ms_model_t *m = calloc(1, sizeof(*m));
+    int f;
+    m->n_mgau = n_mgau; m->n_feat = n_feat; m->n_density = n_density; m->n_sen = n_sen;
+    m->topn = (topn == 0 || topn > n_density) ? n_density : topn;   /* ms_mgau.c:121-127 */
+    m->aw = aw > 0 ? aw : 1;
+    for (f = 0; f < n_feat; ++f) {
+        m->featlen[f] = featlen[f];
+        m->featoff[f] = m->veclen;
+        m->veclen += featlen[f];
+    }
+    m->mean = mean; m->var = var; m->det = det; m->mixw = mixw; m->sen2mgau = sen2mgau;
+    m->lmath10 = orc_logmath_init(logbase, SHIFT, 1);
+    return m;
+}
+
+void
+orc_ms_model_free(orc_ms_model_t *m)
+{
+    if (m) {
+        orc_logmath_free(m->lmath10);
+        free(m);
+    }
+}
+
+/* ms_gauden.c:417-523: one codebook, one stream. */
+void
+orc_ms_compute_dist(const orc_ms_model_t *m, int mgau, int feat, const float *obs, int32_t *ids, float *dists)
+{
+    int len = m->featlen[feat], nd = m->n_density, n = m->topn, d, i, j;
+    const float *mp = m->mean + (long)mgau * nd * m->veclen + (long)nd * m->featoff[feat];
+    const float *vp = m->var + (long)mgau * nd * m->veclen + (long)nd * m->featoff[feat];
+    const float *dp = m->det + ((long)mgau * m->n_feat + feat) * nd;
+
+    if (n >= nd) {   /* compute_dist_all: everything, index order */
+        for (d = 0; d < nd; ++d) {
+            float dval = dp[d];
+            for (i = 0; i < len; ++i) {
+                float diff = obs[i] - mp[d * len + i];
+                dval -= diff * diff * vp[d * len + i];
+            }
+            dists[d] = dval;
+            ids[d] = d;
+        }
+        return;
+    }
+    for (i = 0; i < n; ++i) {
+        dists[i] = (float)ORC_WORST_DIST;
+        ids[i] = 0;
+    }
+    for (d = 0; d < nd; ++d) {
+        float dval = dp[d];
+        for (i = 0; i < len && dval >= dists[n - 1]; ++i) {
+            float diff = obs[i] - mp[d * len + i];
+            dval -= diff * diff * vp[d * len + i];
+        }
+        if (i < len || dval < dists[n - 1])
+            continue;
+        for (i = 0; i < n && dval < dists[i]; ++i)
+            ;
+        for (j = n - 1; j > i; --j) {
+            dists[j] = dists[j - 1];
+            ids[j] = ids[j - 1];
+        }
+        dists[i] = dval;
+        ids[i] = d;
+    }
+}
+
+/* ms_senone.c:372-421 */
+static int32_t
+ms_senone_eval(const orc_ms_model_t *m, int s, const int32_t *ids, const float *dists)
+{
+    int n = m->topn, f, t;
+    int32_t scr = 0;
+    for (f = 0; f < m->n_feat; ++f) {
+        const int32_t *fi = ids + f * n;
+        const float *fd = dists + f * n;
+        const uint8_t *pdf = m->mixw + ((long)s * m->n_feat + f) * m->n_density;
+        int32_t fden = ((int32_t)fd[0] + ((1 << SHIFT) - 1)) >> SHIFT;
+        int32_t fscr = fden - pdf[fi[0]];
+        for (t = 1; t < n; ++t) {
+            fden = ((int32_t)fd[t] + ((1 << SHIFT) - 1)) >> SHIFT;
+            fscr = orc_logmath_add(m->lmath10, fscr, fden - pdf[fi[t]]);
+        }
+        scr -= fscr;
+    }
+    scr /= m->aw;
+    if (scr > 32767) scr = 32767;
+    if (scr < -32768) scr = -32768;
+    return scr;
+}
+
+/* ms_mgau.c:162-252 */
+int
+orc_ms_frame_eval(const orc_ms_model_t *m, const float *feat, const uint8_t *senone_active,
+                  int n_senone_active, int compallsen, int16_t *senscr)
+{
+    int n = m->topn, nf = m->n_feat, g, f, s, i, l;
+    int32_t *ids = malloc(sizeof(int32_t) * (size_t)m->n_mgau * nf * n);
+    float *dists = malloc(sizeof(float) * (size_t)m->n_mgau * nf * n);
+    char *act = calloc(m->n_mgau, 1);
+    int32_t best = 0x7fffffff;
+
+    if (compallsen)
+        memset(act, 1, m->n_mgau);
+    else
+        for (i = 0, l = 0; i < n_senone_active; ++i) {
+            l += senone_active[i];
+            act[m->sen2mgau[l]] = 1;
+        }
+    for (g = 0; g < m->n_mgau; ++g)
+        if (act[g])
+            for (f = 0; f < nf; ++f)
+                orc_ms_compute_dist(m, g, f, feat + m->featoff[f], ids + ((long)g * nf + f) * n,
+                                    dists + ((long)g * nf + f) * n);
+    if (compallsen) {
+        for (s = 0; s < m->n_sen; ++s) {
+            long o = (long)m->sen2mgau[s] * nf * n;
+            senscr[s] = (int16_t)ms_senone_eval(m, s, ids + o, dists + o);
+            if (best > senscr[s]) best = senscr[s];
+        }
+        for (s = 0; s < m->n_sen; ++s) {
+            int32_t bs = senscr[s] - best;
+            senscr[s] = (int16_t)(bs > 32767 ? 32767 : (bs < -32768 ? -32768 : bs));
+        }
+    }
+    else {
+        for (i = 0, s = 0; i < n_senone_active; ++i) {
+            long o;
+            s += senone_active[i];
+            o = (long)m->sen2mgau[s] * nf * n;
+            senscr[s] = (int16_t)ms_senone_eval(m, s, ids + o, dists + o);
+            if (best > senscr[s]) best = senscr[s];
+        }
+        for (i = 0, s = 0; i < n_senone_active; ++i) {
+            int32_t bs;
+            s += senone_active[i];
+            bs = senscr[s] - best;
+            senscr[s] = (int16_t)(bs > 32767 ? 32767 : (bs < -32768 ? -32768 : bs));
+        }
+    }
+    free(ids); free(dists); free(act);
+    return 0;
+}
+
+int
+orc_ms_eval_all(const orc_ms_model_t *m, const float *feat, int T, int16_t *out)
+{
+    int t;
+    for (t = 0; t < T; ++t)
+        orc_ms_frame_eval(m, feat + (long)t * m->veclen, NULL, 0, 1, out + (long)t * m->n_sen);
+    return 0;
+}
+
+/* ------------------------------------------------------- ptm / s2_semi */
+typedef struct { int32_t cw, score; } topn_t;
+
+struct orc_tied_model {
+    int kind, n_mgau, n_feat, n_density, n_sen, topn, veclen;
+    int featlen[8], featoff[8];
+    const float *mean, *var, *det;
+    const uint8_t *mixw, *mixw_cb, *sen2cb;
+    int row_bytes, n_clust;
+    orc_logmath_t *lm8;
+    topn_t *hist[2];          /* [n_mgau][n_feat][topn] x 2 slots */
+    topn_t *f;                /* current slot */
+    char *cb_active;
+    int frame_idx;
+};
+
+orc_tied_model_t *
+orc_tied_new(int kind, int n_mgau, int n_feat, const int *featlen, int n_density, int n_sen, int topn,
+             const float *mean, const float *var, const float *det, const uint8_t *mixw, int row_bytes,
+             int n_clust, const uint8_t *mixw_cb, const uint8_t *sen2cb, double logbase)
+{
+    orc_tied_model_t *m = calloc(1, sizeof(*m));
+    int f;
+    m->kind = kind; m->n_mgau = n_mgau; m->n_feat = n_feat; m->n_density = n_density;
+    m->n_sen = n_sen; m->topn = topn;
+    for (f = 0; f < n_feat; ++f) {
+        m->featlen[f] = featlen[f];
+        m->featoff[f] = m->veclen;
+        m->veclen += featlen[f];
+    }
+    m->mean = mean; m->var = var; m->det = det; m->mixw = mixw; m->row_bytes = row_bytes;
+    m->n_clust = n_clust; m->mixw_cb = mixw_cb; m->sen2cb = sen2cb;
+    m->lm8 = orc_logmath_init(logbase, SHIFT, 1);
+    m->hist[0] = malloc(sizeof(topn_t) * (size_t)n_mgau * n_feat * topn);
+    m->hist[1] = malloc(sizeof(topn_t) * (size_t)n_mgau * n_feat * topn);
+    m->cb_active = malloc(n_mgau);
+    orc_tied_reset(m);
+    return m;
+}
+
+void
+orc_tied_free(orc_tied_model_t *m)
+{
+    if (!m) return;
+    orc_logmath_free(m->lm8);
+    free(m->hist[0]); free(m->hist[1]); free(m->cb_active); free(m);
+}
+
+/* ptm_mgau.c:846-865, s2_semi_mgau.c:1313-1324 */
+void
+orc_tied_reset(orc_tied_model_t *m)
+{
+    int h, i, k, n = m->n_mgau * m->n_feat;
+    for (h = 0; h < 2; ++h)
+        for (i = 0; i < n; ++i)
+            for (k = 0; k < m->topn; ++k) {
+                m->hist[h][i * m->topn + k].cw = k;
+                m->hist[h][i * m->topn + k].score = ORC_WORST_DIST;
+            }
+    m->f = m->hist[0];
+    m->frame_idx = 0;
+    memset(m->cb_active, 1, m->n_mgau);
+}
+
+static float
+tied_dist(const orc_tied_model_t *m, int cb, int feat, int cw, const float *z)
+{
+    int len = m->featlen[feat], i;
+    long base = (long)cb * m->n_density * m->veclen + (long)m->n_density * m->featoff[feat] + (long)cw * len;
+    float d = m->det[((long)cb * m->n_feat + feat) * m->n_density + cw];
+    for (i = 0; i < len; ++i) {
+        float diff = z[i] - m->mean[base + i];
+        float sq = diff * diff;
+        float c = sq * m->var[base + i];
+        d = d - c;
+    }
+    return d;
+}
+
+/* ptm_mgau.c:98-144, s2_semi_mgau.c:80-117: re-score last frame's codewords */
+static void
+tied_eval_topn(orc_tied_model_t *m, int cb, int feat, const float *z)
+{
+    topn_t *topn = m->f + ((long)cb * m->n_feat + feat) * m->topn;
+    int i, j;
+    for (i = 0; i < m->topn; ++i) {
+        topn_t v;
+        int32_t d = (int32_t)tied_dist(m, cb, feat, topn[i].cw, z);
+        topn[i].score = d;
+        if (i == 0)
+            continue;
+        v = topn[i];
+        for (j = i - 1; j >= 0 && d > topn[j].score; --j)
+            topn[j + 1] = topn[j];
+        topn[j + 1] = v;
+    }
+}
+
+/* ptm_mgau.c:159-231, s2_semi_mgau.c:119-173: scan the codebook.  The
+ * dimension loop's early exit only skips work (partial sums decrease
+ * monotonically) except that it is evaluated on the value BEFORE each
+ * dimension (ptm: before each group of four after the first len%4), which
+ * is what the literal loop below reproduces. */
+static void
+tied_eval_cb(orc_tied_model_t *m, int cb, int feat, const float *z)
+{
+    topn_t *topn = m->f + ((long)cb * m->n_feat + feat) * m->topn;
+    topn_t *worst = topn + m->topn - 1;
+    int len = m->featlen[feat], cw, i, j;
+    long pbase = (long)cb * m->n_density * m->veclen + (long)m->n_density * m->featoff[feat];
+    const float *det = m->det + ((long)cb * m->n_feat + feat) * m->n_density;
+
+    for (cw = 0; cw < m->n_density; ++cw) {
+        const float *mean = m->mean + pbase + (long)cw * len;
+        const float *var = m->var + pbase + (long)cw * len;
+        float d = det[cw];
+        topn_t *cur;
+        if (m->kind == 1) {
+            float thresh = (float)worst->score;
+            for (j = 0; j < len % 4 && d >= thresh; ++j) {
+                float diff = z[j] - mean[j];
+                d = d - (diff * diff) * var[j];
+            }
+            for (; j < len && d >= thresh; j += 4) {
+                float c0, c1, c2, c3, df;
+                df = z[j] - mean[j];         c0 = (df * df) * var[j];
+                df = z[j + 1] - mean[j + 1]; c1 = (df * df) * var[j + 1];
+                df = z[j + 2] - mean[j + 2]; c2 = (df * df) * var[j + 2];
+                df = z[j + 3] - mean[j + 3]; c3 = (df * df) * var[j + 3];
+                d = d - c0; d = d - c1; d = d - c2; d = d - c3;
+            }
+            if (j < len)
+                continue;
+            if (d < thresh)
+                continue;
+        }
+        else {
+            for (j = 0; j < len && d >= worst->score; ++j) {
+                float diff = z[j] - mean[j];
+                d = d - (diff * diff) * var[j];
+            }
+            if (j < len)
+                continue;
+            if ((int32_t)d < worst->score)
+                continue;
+        }
+        for (i = 0; i < m->topn; ++i)
+            if (topn[i].cw == cw)
+                break;
+        if (i < m->topn)
+            continue;
+        for (cur = worst - 1; cur >= topn && (int32_t)d >= cur->score; --cur)
+            cur[1] = cur[0];
+        ++cur;
+        cur->cw = cw;
+        cur->score = (int32_t)d;
+    }
+}
+
+static int
+tied_mixw(const orc_tied_model_t *m, int f, int cw, int sen)
+{
+    const uint8_t *row = m->mixw + ((long)f * m->n_density + cw) * m->row_bytes;
+    if (m->n_clust) {
+        int b = row[sen / 2];
+        return m->mixw_cb[(sen & 1) ? (b >> 4) : (b & 0x0f)];
+    }
+    return row[sen];
+}
+
+/* ptm_mgau.c:405-450 + :236-400; s2_semi_mgau.c:840-886 + :189-207 + get_scores_* */
+int
+orc_tied_frame_eval(orc_tied_model_t *m, const float *feat, const uint8_t *senone_active,
+                    int n_senone_active, int compallsen, int frame, int16_t *senscr)
+{
+    int C = m->n_mgau, F = m->n_feat, N = m->topn, i, j, k, f, l;
+    size_t lbytes = sizeof(topn_t) * (size_t)C * F * N;
+    topn_t *lastf;
+
+    m->f = m->hist[frame % 2];
+    lastf = m->hist[(frame + 1) % 2];
+    if (frame >= m->frame_idx) {
+        memcpy(m->f, lastf, lbytes);
+        if (m->kind == 1) {
+            if (compallsen)
+                memset(m->cb_active, 1, C);
+            else {
+                memset(m->cb_active, 0, C);
+                for (i = 0, l = 0; i < n_senone_active; ++i) {
+                    l += senone_active[i];
+                    m->cb_active[m->sen2cb[l]] = 1;
+                }
+            }
+            for (i = 0; i < C; ++i)
+                for (j = 0; j < F; ++j)
+                    tied_eval_topn(m, i, j, feat + m->featoff[j]);
+            for (i = 0; i < C; ++i)
+                if (m->cb_active[i])
+                    for (j = 0; j < F; ++j)
+                        tied_eval_cb(m, i, j, feat + m->featoff[j]);
+            for (j = 0; j < F; ++j) {
+                int32_t norm = 0x7fffffff;
+                for (i = 0; i < C; ++i)
+                    if (m->cb_active[i] && norm > (m->f[((long)i * F + j) * N].score >> SHIFT))
+                        norm = m->f[((long)i * F + j) * N].score >> SHIFT;
+                for (i = 0; i < C; ++i) {
+                    if (!m->cb_active[i])
+                        continue;
+                    for (k = 0; k < N; ++k) {
+                        topn_t *e = &m->f[((long)i * F + j) * N + k];
+                        e->score = -((e->score >> SHIFT) - norm);
+                        if (e->score > 96)
+                            e->score = 96;
+                    }
+                }
+            }
+        }
+        else {
+            for (j = 0; j < F; ++j) {
+                topn_t *t = m->f + (long)j * N;
+                int32_t norm;
+                tied_eval_topn(m, 0, j, feat + m->featoff[j]);
+                tied_eval_cb(m, 0, j, feat + m->featoff[j]);
+                norm = t[0].score >> SHIFT;
+                for (k = 0; k < N; ++k) {
+                    t[k].score = -((t[k].score >> SHIFT) - norm);
+                    if (t[k].score > 96)
+                        t[k].score = 96;
+                }
+            }
+        }
+        m->frame_idx = frame + 1;   /* what acmod_advance does (acmod.c:880) */
+    }
+
+    memset(senscr, 0, sizeof(int16_t) * m->n_sen);
+    {
+        int n = compallsen ? m->n_sen : n_senone_active;
+        int32_t best = 0x7fffffff;
+        for (i = 0, l = 0; i < n; ++i) {
+            int sen, cb;
+            int32_t ascore = 0;
+            if (compallsen) sen = i;
+            else { l += senone_active[i]; sen = l; }
+            cb = m->kind == 1 ? m->sen2cb[sen] : 0;
+            if (m->kind == 1 && !m->cb_active[cb])
+                for (f = 0; f < F; ++f)
+                    for (k = 0; k < N; ++k)
+                        m->f[((long)cb * F + f) * N + k].score = 96;
+            for (f = 0; f < F; ++f) {
+                const topn_t *t = m->f + ((long)cb * F + f) * N;
+                int fden = 0;
+                for (k = 0; k < N; ++k) {
+                    int w = tied_mixw(m, f, t[k].cw, sen) + t[k].score;
+                    fden = (k == 0) ? w : fast_add(m->lm8, fden, w);
+                }
+                ascore += fden;
+            }
+            if (m->kind == 1) {
+                if (ascore < best) best = ascore;
+                senscr[sen] = (int16_t)ascore;
+            }
+            else
+                senscr[sen] = (int16_t)(senscr[sen] + ascore);
+        }
+        if (m->kind == 1)
+            for (i = 0; i < m->n_sen; ++i)
+                senscr[i] = (int16_t)(senscr[i] - best);
+    }
+    return 0;
+}
+
+int
+orc_tied_eval_all(orc_tied_model_t *m, const float *feat, int T, int16_t *out)
+{
+    int t;
+    for (t = 0; t < T; ++t)
+        orc_tied_frame_eval(m, feat + (long)t * m->veclen, NULL, 0, 1, t, out + (long)t * m->n_sen);
+    return 0;
+}
+
+void
+orc_tied_lists(const orc_tied_model_t *m, int32_t *cw, int32_t *score)
+{
+    long i, n = (long)m->n_mgau * m->n_feat * m->topn;
+    for (i = 0; i < n; ++i) {
+        cw[i] = m->f[i].cw;
+        score[i] = m->f[i].score;
+    }
+}
+
+/* ------------------------------------------------------------------- HMM
+ * hmm.c:224-807, restated over HMM-major arrays. */
+#define W ORC_WORST_SCORE
+
+static int32_t
+clampw(int32_t s)
+{
+    return s < W ? W : s;
+}
+
+/* Picks among self (t0), previous (t1) and skip (t2) exactly like the nested
+ * if/else of hmm.c:556-571: returns 0, 1 or 2. */
+static int
+pick3(int32_t t0, int32_t t1, int32_t t2)
+{
+    if (t0 > t1)
+        return t2 > t0 ? 2 : 0;
+    return t2 > t1 ? 2 : 1;
+}
+
+static int32_t
+hmm_eval_one(int ne, const uint8_t *tp, const uint16_t *sseq, const int16_t *senscr, int32_t *sc, int32_t *hi,
+             int32_t *out_sc, int32_t *out_hi, uint16_t *sid, int mpx)
+{
+    int32_t s[5], best, t0, t1, t2, x;
+    int nc = ne + 1, st, w;
+#define TP(i, j) (-(int32_t)tp[(i) * nc + (j)])
+#define SEN(st) (mpx ? senscr[sseq[(long)sid[st] * ne + (st)]] : senscr[sid[st]])
+
+    if (ne == 3 && !mpx) {   /* hmm.c:531-609 */
+        s[2] = sc[2] - SEN(2); s[1] = sc[1] - SEN(1); s[0] = sc[0] - SEN(0);
+        best = W;
+        t2 = INT_MIN;
+        if (s[1] > W) {
+            t1 = s[2] + TP(2, 3);
+            if (TP(1, 3) > ORC_TMAT_WORST) t2 = s[1] + TP(1, 3);
+            if (t1 > t2) { x = t1; *out_hi = hi[2]; } else { x = t2; *out_hi = hi[1]; }
+            *out_sc = best = clampw(x);
+        }
+        t0 = s[2] + TP(2, 2); t1 = s[1] + TP(1, 2);
+        if (TP(0, 2) > ORC_TMAT_WORST) t2 = s[0] + TP(0, 2);
+        w = pick3(t0, t1, t2);
+        x = w == 0 ? t0 : (w == 1 ? t1 : t2);
+        if (w == 2) hi[2] = hi[0]; else if (w == 1) hi[2] = hi[1];
+        sc[2] = clampw(x); if (sc[2] > best) best = sc[2];
+        t0 = s[1] + TP(1, 1); t1 = s[0] + TP(0, 1);
+        if (t0 > t1) x = t0; else { x = t1; hi[1] = hi[0]; }
+        sc[1] = clampw(x); if (sc[1] > best) best = sc[1];
+        sc[0] = clampw(s[0] + TP(0, 0)); if (sc[0] > best) best = sc[0];
+        return best;
+    }
+    if (ne == 3 && mpx) {    /* hmm.c:611-709 */
+        t2 = INT_MIN;
+        if (sid[2] == ORC_BAD_SSID) s[2] = t1 = W;
+        else { s[2] = sc[2] - SEN(2); t1 = s[2] + TP(2, 3); }
+        if (sid[1] == ORC_BAD_SSID) s[1] = t2 = W;
+        else { s[1] = sc[1] - SEN(1); if (TP(1, 3) > ORC_TMAT_WORST) t2 = s[1] + TP(1, 3); }
+        if (t1 > t2) { x = t1; *out_hi = hi[2]; } else { x = t2; *out_hi = hi[1]; }
+        *out_sc = best = clampw(x);
+        s[0] = sc[0] - SEN(0);
+        t0 = t1 = W;
+        if (s[2] != W) t0 = s[2] + TP(2, 2);
+        if (s[1] != W) t1 = s[1] + TP(1, 2);
+        if (TP(0, 2) > ORC_TMAT_WORST) t2 = s[0] + TP(0, 2);
+        w = pick3(t0, t1, t2);
+        x = w == 0 ? t0 : (w == 1 ? t1 : t2);
+        if (w == 2) { hi[2] = hi[0]; sid[2] = sid[0]; } else if (w == 1) { hi[2] = hi[1]; sid[2] = sid[1]; }
+        sc[2] = clampw(x); if (sc[2] > best) best = sc[2];
+        t0 = W;
+        if (s[1] != W) t0 = s[1] + TP(1, 1);
+        t1 = s[0] + TP(0, 1);
+        if (t0 > t1) x = t0; else { x = t1; hi[1] = hi[0]; sid[1] = sid[0]; }
+        sc[1] = clampw(x); if (sc[1] > best) best = sc[1];
+        sc[0] = clampw(s[0] + TP(0, 0)); if (sc[0] > best) best = sc[0];
+        return best;
+    }
+    if (ne == 5 && !mpx) {   /* hmm.c:224-352 */
+        best = W;
+        s[4] = sc[4] - SEN(4); s[3] = sc[3] - SEN(3);
+        if (s[3] > W) {
+            t1 = s[4] + TP(4, 5); t2 = s[3] + TP(3, 5);
+            if (t1 > t2) { x = t1; *out_hi = hi[4]; } else { x = t2; *out_hi = hi[3]; }
+            *out_sc = best = clampw(x);
+        }
+        for (st = 4; st >= 2; --st) {
+            /* state st's block runs only if the state two below is alive
+             * (states 4 and 3); state 2's block always runs. */
+            s[st - 2] = sc[st - 2] - SEN(st - 2);
+            if (st > 2 && !(s[st - 2] > W))
+                continue;
+            t0 = s[st] + TP(st, st); t1 = s[st - 1] + TP(st - 1, st); t2 = s[st - 2] + TP(st - 2, st);
+            w = pick3(t0, t1, t2);
+            x = w == 0 ? t0 : (w == 1 ? t1 : t2);
+            if (w == 2) hi[st] = hi[st - 2]; else if (w == 1) hi[st] = hi[st - 1];
+            s[st] = clampw(x); if (s[st] > best) best = s[st];
+            sc[st] = s[st];
+        }
+        t0 = s[1] + TP(1, 1); t1 = s[0] + TP(0, 1);
+        if (t0 > t1) x = t0; else { x = t1; hi[1] = hi[0]; }
+        sc[1] = clampw(x); if (sc[1] > best) best = sc[1];
+        sc[0] = clampw(s[0] + TP(0, 0)); if (sc[0] > best) best = sc[0];
+        return best;
+    }
+    /* ne == 5 && mpx: hmm.c:357-527 */
+    if (sid[4] == ORC_BAD_SSID) s[4] = t1 = W;
+    else { s[4] = sc[4] - SEN(4); t1 = s[4] + TP(4, 5); }
+    if (sid[3] == ORC_BAD_SSID) s[3] = t2 = W;
+    else { s[3] = sc[3] - SEN(3); t2 = s[3] + TP(3, 5); }
+    if (t1 > t2) { x = t1; *out_hi = hi[4]; } else { x = t2; *out_hi = hi[3]; }
+    *out_sc = best = clampw(x);
+    for (st = 4; st >= 2; --st) {
+        int lo = st - 2;
+        if (lo == 0) { s[0] = sc[0] - SEN(0); t2 = s[0] + TP(0, st); }
+        else if (sid[lo] == ORC_BAD_SSID) s[lo] = t2 = W;
+        else { s[lo] = sc[lo] - SEN(lo); t2 = s[lo] + TP(lo, st); }
+        t0 = t1 = W;
+        if (s[st] != W) t0 = s[st] + TP(st, st);
+        if (s[st - 1] != W) t1 = s[st - 1] + TP(st - 1, st);
+        w = pick3(t0, t1, t2);
+        x = w == 0 ? t0 : (w == 1 ? t1 : t2);
+        if (w == 2) { hi[st] = hi[lo]; sid[st] = sid[lo]; }
+        else if (w == 1) { hi[st] = hi[st - 1]; sid[st] = sid[st - 1]; }
+        /* NB: s[st] keeps the pre-update sum for the next block's "t1" only
+         * through s[st-1]; s[st] itself is not read again. */
+        x = clampw(x); if (x > best) best = x;
+        sc[st] = x;
+    }
+    t0 = W;
+    if (s[1] != W) t0 = s[1] + TP(1, 1);
+    t1 = s[0] + TP(0, 1);
+    if (t0 > t1) x = t0; else { x = t1; hi[1] = hi[0]; sid[1] = sid[0]; }
+    sc[1] = clampw(x); if (sc[1] > best) best = sc[1];
+    sc[0] = clampw(s[0] + TP(0, 0)); if (sc[0] > best) best = sc[0];
+    return best;
+#undef TP
+#undef SEN
+}
+
+int32_t
+orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat, const uint16_t *sseq, int n_sseq,
+                   const int16_t *senscr, int32_t *score, int32_t *history, int32_t *out_score,
+                   int32_t *out_history, uint16_t *senid, const uint16_t *ssid, const int16_t *tmatid,
+                   const uint8_t *mpx, int32_t *bestscore, int n_frames_repeat)
+{
+    int32_t best = W;
+    int i, r;
+    (void)n_tmat; (void)n_sseq; (void)ssid;
+    if (n_emit != 3 && n_emit != 5)
+        return W;
+    for (r = 0; r < (n_frames_repeat > 0 ? n_frames_repeat : 1); ++r) {
+        best = W;
+        for (i = 0; i < n_hmm; ++i) {
+            int32_t b = hmm_eval_one(n_emit, tp + (long)tmatid[i] * n_emit * (n_emit + 1), sseq, senscr,
+                                     score + (long)i * n_emit, history + (long)i * n_emit, &out_score[i],
+                                     &out_history[i], senid + (long)i * n_emit, mpx[i]);
+            bestscore[i] = b;
+            if (b > best) best = b;
+        }
+    }
+    return best;
+}

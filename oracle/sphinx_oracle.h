@@ -85,7 +85,37 @@ int orc_ms_frame_eval(const orc_ms_model_t *m, const float *feat,
 int orc_ms_eval_all(const orc_ms_model_t *m, const float *feat, int T,
                     int16_t *out);
 
+/* ---- tied-mixture scoring: ptm_mgau.c (kind 1) / s2_semi_mgau.c (kind 2) ----
+ * Sequential, stateful restatement: the top-N lists of the previous frame
+ * seed the current one exactly as the reference's rotating history does
+ * (ptm_mgau.c:405-450, s2_semi_mgau.c:840-886; -pl_window 0 => 2 slots). */
+typedef struct orc_tied_model orc_tied_model_t;
+orc_tied_model_t *orc_tied_new(int kind, int n_mgau, int n_feat, const int *featlen,
+                               int n_density, int n_sen, int topn,
+                               const float *mean, const float *var, const float *det,
+                               const uint8_t *mixw /* [feat][density][row_bytes] */,
+                               int row_bytes, int n_clust, const uint8_t *mixw_cb,
+                               const uint8_t *sen2cb, double logbase);
+void orc_tied_free(orc_tied_model_t *m);
+void orc_tied_reset(orc_tied_model_t *m);   /* fresh history, as after *_init */
+/* One frame_eval call; frames must be fed in increasing order. */
+int orc_tied_frame_eval(orc_tied_model_t *m, const float *feat,
+                        const uint8_t *senone_active, int n_senone_active,
+                        int compallsen, int frame, int16_t *senscr);
+int orc_tied_eval_all(orc_tied_model_t *m, const float *feat, int T, int16_t *out);
+/* Copies the current frame's lists: cw/score [n_mgau][n_feat][topn]. */
+void orc_tied_lists(const orc_tied_model_t *m, int32_t *cw, int32_t *score);
+
+/* tied mixw quantiser (ptm_mgau.c:720-742): in [sen][feat][cw] float (modified),
+ * out [feat][cw][sen] uint8. */
+int orc_mixw_quantize_tied(float *mixw, uint8_t *out, int n_sen, int n_feat,
+                           int n_cw, float mixwfloor, double logbase);
+
+/* acmod_flags2list (acmod.c:1219-1271) over a 32-bit-word bitmask. */
+int orc_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas);
+
 /* ---- HMM Viterbi step (hmm.c:224-807), SoA batch ---- */
+/* Arrays are HMM-major ([hmm][state]) like the reference shim's. */
 int32_t orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat,
                            const uint16_t *sseq, int n_sseq,
                            const int16_t *senscr, int32_t *score,

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref: the
+unmodified reference sources compiled by oracle/Makefile, driven through
+oracle/ref_shim.c).  Run in the build container (needs /root/reference for
+`make -C oracle ref`):   python tests/golden/make_golden.py
+The .npz files are committed; tests never need /root/reference.
+"""
+import ctypes as C
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import orc  # noqa: E402
+from cmusphinx_b200 import s3io, synth  # noqa: E402
+
+R = orc.ref()
+LB = orc.LOGBASE
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **kw)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def logmath():
+    n = R.ref_logadd_table(LB, 10, None, 0)
+    tab = np.zeros(n, np.int32)
+    R.ref_logadd_table(LB, 10, orc._p(tab, C.c_int32), n)
+    rng = np.random.default_rng(0)
+    p = np.concatenate([10.0 ** rng.uniform(-150, 3, 500), [0.0, 1.0, 42.0, 1e-150]])
+    logs = {}
+    for sh in (0, 10):
+        o = np.zeros(p.size, np.int32)
+        R.ref_logmath_log(LB, sh, p.ctypes.data_as(C.POINTER(C.c_double)), p.size, orc._p(o, C.c_int32))
+        logs[f"log_shift{sh}"] = o
+    x = rng.integers(-600, 100, 2000).astype(np.int32)
+    y = rng.integers(-600, 100, 2000).astype(np.int32)
+    x[:20] = -2 ** 31 >> 12
+    add = np.zeros(x.size, np.int32)
+    R.ref_logmath_add(LB, 10, orc._p(x, C.c_int32), orc._p(y, C.c_int32), x.size, orc._p(add, C.c_int32))
+    save("logmath.npz", base=LB, table10=tab, p=p, add_x=x, add_y=y, add_out=add, **logs)
+
+
+def ms_case(name, n_sen, n_density, dim, n_feat, topn, T, seed):
+    mean, var, mixw = synth.cont_model(n_sen, n_density, dim, seed, n_feat)
+    var[0, 0, :3] = 1e-6
+    mixw[1, 0, :2] = 0.0
+    vl = [dim] * n_feat
+    with tempfile.TemporaryDirectory() as d:
+        mf, vf, wf = (os.path.join(d, n) for n in ("means", "variances", "mixture_weights"))
+        s3io.write_gauden(mf, [mean.reshape(n_sen, n_density, n_feat, dim)[:, :, f, :] for f in range(n_feat)], vl)
+        s3io.write_gauden(vf, [var.reshape(n_sen, n_density, n_feat, dim)[:, :, f, :] for f in range(n_feat)], vl)
+        s3io.write_mixw(wf, mixw)
+        h = R.ref_ms_init(mf.encode(), vf.encode(), wf.encode(), b".cont.", 1e-4, 1e-7, topn, 1, LB)
+    tot = mean.size
+    rmean, rvar = np.zeros(tot, np.float32), np.zeros(tot, np.float32)
+    rdet = np.zeros(n_sen * n_feat * n_density, np.float32)
+    rmixw = np.zeros(n_sen * n_feat * n_density, np.uint8)
+    R.ref_ms_params(h, orc._p(rmean, C.c_float), orc._p(rvar, C.c_float), orc._p(rdet, C.c_float),
+                    orc._p(rmixw, C.c_uint8))
+    feat = synth.cont_features(mean, var, T, seed + 1)
+    dense = np.zeros((T, n_sen), np.int16)
+    R.ref_ms_eval_all(h, orc._p(feat, C.c_float), T, orc._p(dense, C.c_int16))
+    rng = np.random.default_rng(seed + 2)
+    act_deltas, act_scores = [], []
+    for t in range(min(T, 6)):
+        mask = np.zeros((n_sen + 31) // 32, np.uint32)
+        for s in rng.choice(n_sen, max(1, n_sen // 3), replace=False):
+            mask[s // 32] |= np.uint32(1 << (s % 32))
+        dl = orc.port_flags2list(mask, n_sen)
+        o = np.full(n_sen, 12345, np.int16)
+        R.ref_ms_eval_active(h, orc._p(feat[t], C.c_float), orc._p(dl, C.c_uint8), dl.size, t, orc._p(o, C.c_int16))
+        pad = np.zeros(2 * n_sen, np.uint8)
+        pad[:dl.size] = dl
+        act_deltas.append(np.concatenate([[dl.size], pad]).astype(np.int32))
+        act_scores.append(o)
+    R.ref_ms_free(h)
+    save(name, dims=np.array([n_sen, n_density, dim, n_feat, topn, T]), mean_raw=synth.to_ref_layout(mean, n_feat, dim),
+         var_raw=synth.to_ref_layout(var, n_feat, dim), mixw_raw=mixw, mean=rmean, var=rvar, det=rdet, mixw=rmixw,
+         feat=feat, dense=dense, act_deltas=np.array(act_deltas), act_scores=np.array(act_scores))
+
+
+def tmat_hmm():
+    tp_raw = synth.bakis_tmat(23, 3, 5)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "tmat")
+        s3io.write_tmat(f, tp_raw)
+        out = np.zeros(tp_raw.size, np.uint8)
+        ns = C.c_int32()
+        R.ref_tmat_load(f.encode(), 1e-4, LB, orc._p(out, C.c_uint8), out.size, C.byref(ns))
+    keep = dict(tp_raw=tp_raw, tp=out.reshape(tp_raw.shape))
+    for ne in (3, 5):
+        n_sen, n_tmat, n_sseq, n_hmm, nfr = 400, 13, 200, 1500, 4
+        tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 3))
+        pop = synth.hmm_population(n_hmm, ne, n_sen, n_tmat, n_sseq, seed=ne, mpx_fraction=0.3)
+        sen = synth.senscr_frames(nfr, n_sen, ne + 10)
+        a = {k: v.copy() for k, v in pop.items()}
+        bests = []
+        for f in range(nfr):
+            bests.append(orc.hmm_eval(R.ref_hmm_eval_batch, ne, tp, pop["sseq"], sen[f], a["score"], a["history"],
+                                      a["out_score"], a["out_history"], a["senid"], a["tmatid"], a["mpx"],
+                                      a["bestscore"]))
+        for k, v in pop.items():
+            keep[f"h{ne}_in_{k}"] = v
+        for k in ("score", "history", "out_score", "out_history", "senid", "bestscore"):
+            keep[f"h{ne}_out_{k}"] = a[k]
+        keep[f"h{ne}_tp"] = tp
+        keep[f"h{ne}_senscr"] = sen
+        keep[f"h{ne}_best"] = np.array(bests, np.int32)
+    save("tmat_hmm.npz", **keep)
+
+
+def real_model(name, hmmdir, mfc, n_frames, senmgau="", topn=4):
+    r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", hmmdir), senmgau, topn)
+    cep = orc.read_mfc(os.path.join(orc.DATA_DIR, "test", mfc))
+    feat = r.cep2feat(cep)[:n_frames]
+    dense = r.score(feat)
+    extra = {}
+    if r.backend == "ptm":
+        extra["sen2cb"] = r.sen2cimap()
+    tp, sseq = r.tables()
+    r.close()
+    # active-list calls on a fresh decoder
+    r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", hmmdir), senmgau, topn)
+    rng = np.random.default_rng(5)
+    dl_all, sc_all = [], []
+    for t in range(min(n_frames, 8)):
+        mask = np.zeros((r.n_sen + 31) // 32, np.uint32)
+        if r.backend == "ptm":
+            cbs = rng.choice(50, 7, replace=False)
+            sel = np.nonzero(np.isin(extra["sen2cb"], cbs))[0][::3]
+        else:
+            sel = rng.choice(r.n_sen, 700, replace=False)
+        for s in sel:
+            mask[s // 32] |= np.uint32(1 << (s % 32))
+        dl = orc.port_flags2list(mask, r.n_sen)
+        o = np.full(r.n_sen, 12345, np.int16)
+        r.frame_eval(feat[t], dl, t, False, o)
+        pad = np.zeros(2 * r.n_sen, np.uint8)
+        pad[:dl.size] = dl
+        dl_all.append(np.concatenate([[dl.size], pad]).astype(np.int32))
+        sc_all.append(o)
+    save(name, backend=r.backend, n_sen=r.n_sen, streamlen=np.array(r.streamlen), feat=feat, dense=dense,
+         act_deltas=np.array(dl_all), act_scores=np.array(sc_all), tp=tp, topn=topn, **extra)
+    r.close()
+
+
+if __name__ == "__main__":
+    assert orc.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    logmath()
+    ms_case("ms_small.npz", 48, 8, 13, 1, 4, 33, 11)
+    ms_case("ms_3stream.npz", 40, 16, 7, 3, 4, 21, 12)
+    ms_case("ms_allden.npz", 33, 8, 39, 1, 8, 17, 13)
+    ms_case("ms_cont32.npz", 64, 32, 39, 1, 4, 130, 14)
+    tmat_hmm()
+    real_model("semi_hub4wsj.npz", "hub4wsj_sc_8k", "wsj/440c0201.mfc", 24)
+    real_model("ptm_hub4wsj.npz", "ptm", "wsj/442c0201.mfc", 16)
+    real_model("cont_hub4_topn4.npz", "cont", "pittsburgh.littleendian.mfc", 20, ".cont.", 4)
+    real_model("cont_hub4_topn8.npz", "cont", "pittsburgh.littleendian.mfc", 12, ".cont.", 8)

@@ -1,0 +1,312 @@
+"""Test-only access to the oracle (oracle/liboracle.so: our C restatement) and,
+when present, the reference itself (oracle/_ref/libref_shim.so: the unmodified
+reference sources compiled by oracle/Makefile).  Never imported by the product.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+DATA_DIR = os.path.join(REF_DIR, "data")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# -logbase is a float32 option (cmd_ln_float32_r, pocketsphinx.c:223): the
+# reference's effective base is (double)(float)1.0001.
+LOGBASE = float(np.float32(1.0001))
+
+f32p, i32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+i16p, u16p, u8p = C.POINTER(C.c_int16), C.POINTER(C.c_uint16), C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _load_port():
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "sphinx_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(so)
+    L.orc_logmath_init.restype = vp
+    L.orc_logmath_init.argtypes = [C.c_double, C.c_int, C.c_int]
+    L.orc_logmath_free.argtypes = [vp]
+    L.orc_logmath_table.argtypes = [vp, i32p, C.c_int]
+    L.orc_logmath_log.argtypes = [vp, C.c_double]
+    L.orc_logmath_add.argtypes = [vp, C.c_int32, C.c_int32]
+    L.orc_gauden_precompute.argtypes = [f32p, f32p, C.c_long, C.c_int, C.c_float, C.c_double]
+    L.orc_mixw_quantize.argtypes = [f32p, u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double]
+    L.orc_mixw_quantize_tied.argtypes = [f32p, u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double]
+    L.orc_tmat_quantize.argtypes = [f32p, u8p, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.orc_flags2list.argtypes = [u32p, C.c_int, u8p]
+    L.orc_ms_model_new.restype = vp
+    L.orc_ms_model_new.argtypes = [C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
+                                   u8p, u32p, C.c_double]
+    L.orc_ms_model_free.argtypes = [vp]
+    L.orc_ms_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, i16p]
+    L.orc_ms_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
+    L.orc_tied_new.restype = vp
+    L.orc_tied_new.argtypes = [C.c_int, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, u8p,
+                               C.c_int, C.c_int, u8p, u8p, C.c_double]
+    L.orc_tied_free.argtypes = [vp]
+    L.orc_tied_reset.argtypes = [vp]
+    L.orc_tied_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, C.c_int, i16p]
+    L.orc_tied_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
+    L.orc_tied_lists.argtypes = [vp, i32p, i32p]
+    L.orc_hmm_eval_batch.restype = C.c_int32
+    L.orc_hmm_eval_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_int, u16p, C.c_int, i16p, i32p, i32p, i32p, i32p,
+                                     u16p, u16p, i16p, u8p, i32p, C.c_int]
+    return L
+
+
+port = _load_port()
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "libref_shim.so"))
+
+
+_ref = None
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libref_shim.so"))
+        L.ref_logadd_table.argtypes = [C.c_double, C.c_int, i32p, C.c_int]
+        L.ref_logmath_zero.argtypes = [C.c_double, C.c_int]
+        L.ref_logmath_log.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int, i32p]
+        L.ref_logmath_add.argtypes = [C.c_double, C.c_int, i32p, i32p, C.c_int, i32p]
+        L.ref_ms_init.restype = vp
+        L.ref_ms_init.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_int,
+                                  C.c_int, C.c_double]
+        L.ref_ms_free.argtypes = [vp]
+        L.ref_ms_dims.argtypes = [vp, i32p, i32p]
+        L.ref_ms_params.argtypes = [vp, f32p, f32p, f32p, u8p]
+        L.ref_ms_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
+        L.ref_ms_eval_active.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, i16p]
+        L.ref_acmod_open.restype = vp
+        L.ref_acmod_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double]
+        L.ref_acmod_close.argtypes = [vp]
+        L.ref_acmod_backend.restype = C.c_char_p
+        L.ref_acmod_backend.argtypes = [vp]
+        L.ref_acmod_info.argtypes = [vp, i32p, i32p]
+        L.ref_acmod_score_feats.argtypes = [vp, f32p, C.c_int, i16p]
+        L.ref_acmod_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, C.c_int, i16p]
+        L.ref_acmod_sen2cimap.argtypes = [vp, u8p]
+        L.ref_acmod_cep2feat.argtypes = [vp, f32p, C.c_int, C.c_int, f32p, C.c_int]
+        L.ref_acmod_tables.argtypes = [vp, i32p, u8p, u16p]
+        L.ref_tmat_load.argtypes = [C.c_char_p, C.c_double, C.c_double, u8p, C.c_int, i32p]
+        L.ref_hmm_eval_batch.restype = C.c_int32
+        L.ref_hmm_eval_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_int, u16p, C.c_int, i16p, i32p, i32p, i32p,
+                                         i32p, u16p, u16p, i16p, u8p, i32p, C.c_int]
+        _ref = L
+    return _ref
+
+
+# ------------------------------------------------------------------ wrappers
+def port_logadd_table(base=1.0001, shift=10):
+    lm = port.orc_logmath_init(base, shift, 1)
+    n = port.orc_logmath_table(lm, None, 0)
+    out = np.zeros(n, np.int32)
+    port.orc_logmath_table(lm, _p(out, C.c_int32), n)
+    port.orc_logmath_free(lm)
+    return out
+
+
+def port_precompute(var, length, varfloor=1e-4, logbase=LOGBASE):
+    v = _c(var, np.float32).copy().reshape(-1, length)
+    det = np.zeros(v.shape[0], np.float32)
+    port.orc_gauden_precompute(_p(v, C.c_float), _p(det, C.c_float), v.shape[0], length, varfloor, logbase)
+    return v.reshape(var.shape), det.reshape(var.shape[:-1])
+
+
+def port_mixw_quantize(mixw, floor=1e-7, logbase=LOGBASE):
+    m = _c(mixw, np.float32).copy()
+    out = np.zeros(m.shape, np.uint8)
+    port.orc_mixw_quantize(_p(m, C.c_float), _p(out, C.c_uint8), m.shape[0], m.shape[1], m.shape[2], floor, logbase)
+    return out
+
+
+def port_mixw_quantize_tied(mixw, floor=1e-7, logbase=LOGBASE):
+    m = _c(mixw, np.float32).copy()
+    out = np.zeros((m.shape[1], m.shape[2], m.shape[0]), np.uint8)
+    port.orc_mixw_quantize_tied(_p(m, C.c_float), _p(out, C.c_uint8), m.shape[0], m.shape[1], m.shape[2], floor,
+                                logbase)
+    return out
+
+
+def port_tmat_quantize(tp, floor=1e-4, logbase=LOGBASE):
+    t = _c(tp, np.float32).copy()
+    out = np.zeros(t.shape, np.uint8)
+    port.orc_tmat_quantize(_p(t, C.c_float), _p(out, C.c_uint8), t.shape[0], t.shape[1], floor, logbase)
+    return out
+
+
+def port_flags2list(mask, n_sen):
+    m = _c(mask, np.uint32)
+    out = np.zeros(2 * n_sen + 8, np.uint8)
+    n = port.orc_flags2list(_p(m, C.c_uint32), n_sen, _p(out, C.c_uint8))
+    return out[:n].copy()
+
+
+class PortMs:
+    """orc_ms_model_t: arrays are PRECOMPUTED mean/var/det [mgau][feat][density][len], mixw [sen][feat][cw]."""
+
+    def __init__(self, n_mgau, n_feat, featlen, n_density, n_sen, topn, aw, mean, var, det, mixw, sen2mgau,
+                 logbase=LOGBASE):
+        self.keep = [_c(mean, np.float32), _c(var, np.float32), _c(det, np.float32), _c(mixw, np.uint8),
+                     _c(sen2mgau, np.uint32), _c(featlen, np.int32)]
+        k = self.keep
+        self.h = port.orc_ms_model_new(n_mgau, n_feat, _p(k[5], C.c_int32), n_density, n_sen, topn, aw,
+                                       _p(k[0], C.c_float), _p(k[1], C.c_float), _p(k[2], C.c_float),
+                                       _p(k[3], C.c_uint8), _p(k[4], C.c_uint32), logbase)
+        self.n_sen = n_sen
+        self.veclen = int(sum(featlen))
+
+    def eval_all(self, feat):
+        feat = _c(feat, np.float32).reshape(-1, self.veclen)
+        out = np.zeros((feat.shape[0], self.n_sen), np.int16)
+        port.orc_ms_eval_all(self.h, _p(feat, C.c_float), feat.shape[0], _p(out, C.c_int16))
+        return out
+
+    def frame_eval(self, feat, deltas, compallsen, senscr=None):
+        feat = _c(feat, np.float32)
+        if senscr is None:
+            senscr = np.zeros(self.n_sen, np.int16)
+        d = _c(deltas if deltas is not None else [], np.uint8)
+        port.orc_ms_frame_eval(self.h, _p(feat, C.c_float), _p(d, C.c_uint8), d.size, 1 if compallsen else 0,
+                               _p(senscr, C.c_int16))
+        return senscr
+
+    def __del__(self):
+        port.orc_ms_model_free(self.h)
+
+
+class PortTied:
+    def __init__(self, kind, n_mgau, n_feat, featlen, n_density, n_sen, topn, mean, var, det, mixw_rows, n_clust,
+                 mixw_cb, sen2cb, logbase=LOGBASE):
+        mixw_rows = _c(mixw_rows, np.uint8)
+        self.keep = [_c(mean, np.float32), _c(var, np.float32), _c(det, np.float32), mixw_rows,
+                     _c(mixw_cb if mixw_cb is not None else np.zeros(16), np.uint8),
+                     _c(sen2cb if sen2cb is not None else np.zeros(n_sen), np.uint8), _c(featlen, np.int32)]
+        k = self.keep
+        self.h = port.orc_tied_new(kind, n_mgau, n_feat, _p(k[6], C.c_int32), n_density, n_sen, topn,
+                                   _p(k[0], C.c_float), _p(k[1], C.c_float), _p(k[2], C.c_float),
+                                   _p(k[3], C.c_uint8), mixw_rows.shape[-1], int(n_clust), _p(k[4], C.c_uint8),
+                                   _p(k[5], C.c_uint8), logbase)
+        self.n_sen, self.veclen = n_sen, int(sum(featlen))
+        self.shape = (n_mgau, n_feat, topn)
+
+    def reset(self):
+        port.orc_tied_reset(self.h)
+
+    def eval_all(self, feat):
+        feat = _c(feat, np.float32).reshape(-1, self.veclen)
+        out = np.zeros((feat.shape[0], self.n_sen), np.int16)
+        port.orc_tied_eval_all(self.h, _p(feat, C.c_float), feat.shape[0], _p(out, C.c_int16))
+        return out
+
+    def frame_eval(self, feat, deltas, compallsen, frame):
+        feat = _c(feat, np.float32)
+        out = np.zeros(self.n_sen, np.int16)
+        d = _c(deltas if deltas is not None else [], np.uint8)
+        port.orc_tied_frame_eval(self.h, _p(feat, C.c_float), _p(d, C.c_uint8), d.size, 1 if compallsen else 0,
+                                 frame, _p(out, C.c_int16))
+        return out
+
+    def lists(self):
+        cw = np.zeros(self.shape, np.int32)
+        sc = np.zeros(self.shape, np.int32)
+        port.orc_tied_lists(self.h, _p(cw, C.c_int32), _p(sc, C.c_int32))
+        return cw, sc
+
+    def __del__(self):
+        port.orc_tied_free(self.h)
+
+
+def hmm_eval(fn, n_emit, tp, sseq, senscr, score, history, out_score, out_history, senid, tmatid, mpx, bestscore,
+             repeat=1):
+    """fn = port.orc_hmm_eval_batch or ref().ref_hmm_eval_batch.  HMM-major arrays [hmm][state], in place."""
+    n_hmm = out_score.shape[0]
+    tp = _c(tp, np.uint8)
+    sseq = _c(sseq, np.uint16)
+    ssid = np.zeros(n_hmm, np.uint16)
+    return fn(n_emit, n_hmm, _p(tp, C.c_uint8), tp.shape[0], _p(sseq, C.c_uint16), sseq.shape[0],
+              _p(senscr, C.c_int16), _p(score, C.c_int32), _p(history, C.c_int32), _p(out_score, C.c_int32),
+              _p(out_history, C.c_int32), _p(senid, C.c_uint16), _p(ssid, C.c_uint16), _p(tmatid, C.c_int16),
+              _p(mpx, C.c_uint8), _p(bestscore, C.c_int32), repeat)
+
+
+class RefAcmod:
+    """The reference's acmod + whichever back-end it selects, on a model directory."""
+
+    def __init__(self, hmmdir, senmgau="", topn=4, ds=1, logbase=LOGBASE):
+        self.h = ref().ref_acmod_open(hmmdir.encode(), senmgau.encode(), topn, ds, logbase)
+        if not self.h:
+            raise RuntimeError(f"reference acmod_init failed for {hmmdir}")
+        info = (C.c_int32 * 4)()
+        sl = (C.c_int32 * 8)()
+        ref().ref_acmod_info(self.h, info, sl)
+        self.n_sen, self.n_feat, self.featdim, self.n_emit = info[0], info[1], info[2], info[3]
+        self.streamlen = [sl[i] for i in range(self.n_feat)]
+        self.backend = ref().ref_acmod_backend(self.h).decode()
+
+    def cep2feat(self, cep):
+        cep = _c(cep, np.float32)
+        out = np.zeros((cep.shape[0] + 16, self.featdim), np.float32)
+        n = ref().ref_acmod_cep2feat(self.h, _p(cep, C.c_float), cep.shape[0], cep.shape[1], _p(out, C.c_float),
+                                     out.shape[0])
+        return out[:n].copy()
+
+    def score(self, feat):
+        feat = _c(feat, np.float32)
+        out = np.zeros((feat.shape[0], self.n_sen), np.int16)
+        ref().ref_acmod_score_feats(self.h, _p(feat, C.c_float), feat.shape[0], _p(out, C.c_int16))
+        return out
+
+    def frame_eval(self, feat, deltas, frame, compallsen, out=None):
+        feat = _c(feat, np.float32)
+        if out is None:
+            out = np.zeros(self.n_sen, np.int16)
+        d = _c(deltas if deltas is not None else [], np.uint8)
+        ref().ref_acmod_frame_eval(self.h, _p(feat, C.c_float), _p(d, C.c_uint8), d.size, frame,
+                                   1 if compallsen else 0, _p(out, C.c_int16))
+        return out
+
+    def sen2cimap(self):
+        out = np.zeros(self.n_sen, np.uint8)
+        ref().ref_acmod_sen2cimap(self.h, _p(out, C.c_uint8))
+        return out
+
+    def tables(self):
+        sizes = (C.c_int32 * 3)()
+        ref().ref_acmod_tables(self.h, sizes, None, None)
+        tp = np.zeros((sizes[0], sizes[1], sizes[1] + 1), np.uint8)
+        sseq = np.zeros((sizes[2], self.n_emit), np.uint16)
+        ref().ref_acmod_tables(self.h, sizes, _p(tp, C.c_uint8), _p(sseq, C.c_uint16))
+        return tp, sseq
+
+    def close(self):
+        if self.h:
+            ref().ref_acmod_close(self.h)
+            self.h = None
+
+
+def read_mfc(path):
+    raw = np.fromfile(path, dtype="<i4", count=1)
+    n = int(raw[0])
+    data = np.fromfile(path, dtype="<f4", offset=4)
+    if data.size != n:
+        n = int(np.frombuffer(raw.tobytes(), dtype=">i4")[0])
+        data = np.fromfile(path, dtype=">f4", offset=4).astype(np.float32)
+    return data.reshape(-1, 13).astype(np.float32)

@@ -1,0 +1,126 @@
+"""GPU parity tests for the batched hmm_vit_eval kernel, the beam/compaction
+step and the active-senone gather: bit-exact against the oracle and the
+reference-generated goldens."""
+import numpy as np
+import pytest
+
+import cases
+import orc
+import cmusphinx_b200 as b
+from cmusphinx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("score", "history", "out_score", "out_history", "senid", "bestscore")
+
+
+def _to_pop(d, ne):
+    n = d["out_score"].shape[0]
+    p = b.HmmPopulation(n, ne)
+    p.score[:] = d["score"].T
+    p.history[:] = d["history"].T
+    p.senid[:] = d["senid"].T
+    p.out_score[:] = d["out_score"]
+    p.out_history[:] = d["out_history"]
+    p.tmatid[:] = d["tmatid"]
+    p.mpx[:] = d["mpx"]
+    p.bestscore[:] = d["bestscore"]
+    return p
+
+
+def _assert_pop(p, d):
+    np.testing.assert_array_equal(p.score.T, d["score"])
+    np.testing.assert_array_equal(p.history.T, d["history"])
+    np.testing.assert_array_equal(p.senid.T, d["senid"])
+    np.testing.assert_array_equal(p.out_score, d["out_score"])
+    np.testing.assert_array_equal(p.out_history, d["out_history"])
+    np.testing.assert_array_equal(p.bestscore, d["bestscore"])
+
+
+@pytest.mark.parametrize("ne", [3, 5])
+def test_hmm_vit_eval_golden(ne):
+    g = cases.load("tmat_hmm.npz")
+    src = {k: g[f"h{ne}_in_{k}"] for k in ("score", "history", "out_score", "out_history", "senid", "tmatid", "mpx",
+                                           "bestscore")}
+    sen = g[f"h{ne}_senscr"]
+    ctx = b.HmmContext(ne, g[f"h{ne}_tp"], g[f"h{ne}_in_sseq"], sen.shape[1])
+    pop = _to_pop(src, ne)
+    best = ctx.vit_eval(pop, sen)
+    np.testing.assert_array_equal(best, g[f"h{ne}_best"])
+    _assert_pop(pop, {k: g[f"h{ne}_out_{k}"] for k in FIELDS})
+    ctx.free()
+
+
+@pytest.mark.parametrize("ne,n_hmm", [(3, 50000), (5, 20011), (3, 1), (3, 255), (5, 257)])
+def test_hmm_vit_eval_vs_oracle_config4(ne, n_hmm):
+    """BASELINE config 4 population (50k HMMs, 10 % mpx, both skip / no-skip
+    transition matrices) over several frames."""
+    n_sen, n_tmat, n_sseq, nfr = 5000, 50, 27000, 5
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n_hmm, ne, n_sen, n_tmat, n_sseq, seed=42, mpx_fraction=0.1)
+    sen = synth.senscr_frames(nfr, n_sen, 99)
+    o = {k: v.copy() for k, v in d.items()}
+    bests = [orc.hmm_eval(orc.port.orc_hmm_eval_batch, ne, tp, d["sseq"], sen[f], o["score"], o["history"],
+                          o["out_score"], o["out_history"], o["senid"], o["tmatid"], o["mpx"], o["bestscore"])
+             for f in range(nfr)]
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    pop = _to_pop(d, ne)
+    best = ctx.vit_eval(pop, sen)
+    np.testing.assert_array_equal(best, np.array(bests, np.int32))
+    _assert_pop(pop, o)
+    ctx.free()
+
+
+def test_empty_population_and_bad_arguments():
+    tp = np.zeros((2, 3, 4), np.uint8)
+    ctx = b.HmmContext(3, tp, None, 100)
+    pop = b.HmmPopulation(0, 3)
+    best = ctx.vit_eval(pop, np.zeros((2, 100), np.int16))
+    assert (best == b.engine.WORST_SCORE).all()
+    pop = b.HmmPopulation(4, 3)
+    pop.tmatid[:] = 9
+    with pytest.raises(b.B200Error, match="tmatid"):
+        ctx.vit_eval(pop, np.zeros((1, 100), np.int16))
+    with pytest.raises(b.B200Error):
+        b.HmmContext(4, np.zeros((1, 4, 5), np.uint8), None, 10)
+    ctx.free()
+
+
+@pytest.mark.parametrize("ne", [3, 5])
+def test_step_beam_compaction_and_active_senones(ne):
+    n_sen, n_tmat, n_sseq, n_hmm = 5000, 50, 27000, 50000
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n_hmm, ne, n_sen, n_tmat, n_sseq, seed=3, mpx_fraction=0.1)
+    sen = synth.senscr_frames(3, n_sen, 5)
+    beam = -60000   # wide enough to keep a good fraction of this synthetic population
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    pop = _to_pop(d, ne)
+    ctx.upload(pop)
+    o = {k: v.copy() for k, v in d.items()}
+    for f in range(3):
+        best_o = orc.hmm_eval(orc.port.orc_hmm_eval_batch, ne, tp, d["sseq"], sen[f], o["score"], o["history"],
+                              o["out_score"], o["out_history"], o["senid"], o["tmatid"], o["mpx"], o["bestscore"])
+        best, idx, mask = ctx.step(sen[f], beam, n_hmm)
+        assert best == best_o
+        keep = np.nonzero(o["bestscore"] > best_o + beam)[0]   # PS/ngram_search_fwdtree.c:741
+        assert keep.size > 0 and keep.size < n_hmm
+        np.testing.assert_array_equal(idx, keep.astype(np.int32))
+        # acmod_activate_hmm over the survivors
+        want = np.zeros((n_sen + 31) // 32, np.uint32)
+        sid = o["senid"][keep]
+        mp = o["mpx"][keep].astype(bool)
+        for st in range(ne):
+            ids = sid[:, st].astype(np.int64)
+            nm = ids[~mp]
+            ss = ids[mp]
+            ss = ss[ss != 0xFFFF]
+            allid = np.concatenate([nm, d["sseq"][ss, st].astype(np.int64)])
+            np.bitwise_or.at(want, allid // 32, (np.uint32(1) << (allid % 32).astype(np.uint32)))
+        np.testing.assert_array_equal(mask, want)
+        np.testing.assert_array_equal(b.flags2list(mask, n_sen), orc.port_flags2list(want, n_sen))
+    got = b.HmmPopulation(n_hmm, ne)
+    got.tmatid[:] = d["tmatid"]
+    got.mpx[:] = d["mpx"]
+    ctx.download(got)
+    _assert_pop(got, o)
+    ctx.free()
