@@ -152,24 +152,28 @@ int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cu
         cudaEventRecord(m->ev[0], st);
     }
     if (m->kind == 0 && m->path == 1 && m->tc) {
-        if ((rc = tc_score(m->tc, g, d_feat, T, d_out, st, timed ? &m->ev[1] : nullptr))) return rc;
+        int T_pad = 0;
+        if ((rc = tc_score_raw(m->tc, d_feat, T, st, timed ? &m->ev[1] : nullptr, &T_pad))) return rc;
+        if (timed) cudaEventRecord(m->ev[2], st);
+        if ((rc = tc_finish(m->tc, T, T_pad, normalize ? 1 : 0, d_out, st))) return rc;
+        if (timed) cudaEventRecord(m->ev[3], st);
+        return B200_OK;
+    }
+    if (timed) cudaEventRecord(m->ev[1], st);
+    if (m->kind == 0 && m->cont) {
+        for (int t0 = 0; t0 < T; t0 += 65535 * 128) {   // grid.y limit
+            int tn = std::min(T - t0, 65535 * 128);
+            if ((rc = gmm_launch_topn(g, 0, d_feat, T, t0, tn, nullptr, d_out, 1, st))) return rc;
+        }
     } else {
-        if (timed) cudaEventRecord(m->ev[1], st);
-        if (m->kind == 0 && m->cont) {
-            for (int t0 = 0; t0 < T; t0 += 65535 * 128) {   // grid.y limit
-                int tn = std::min(T - t0, 65535 * 128);
-                if ((rc = gmm_launch_topn(g, 0, d_feat, T, t0, tn, nullptr, d_out, 1, st))) return rc;
-            }
-        } else {
-            const int chunk = frames_per_list_chunk(m);
-            if ((rc = ensure((void **)&m->d_lists, &m->lists_cap, (size_t)chunk * list_bytes_per_frame(m)))) return rc;
-            for (int t0 = 0; t0 < T; t0 += chunk) {
-                int tn = std::min(T - t0, chunk);
-                if ((rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st))) return rc;
-                if (m->kind == 0) rc = gmm_launch_ms_senone(g, m->d_lists, T, t0, tn, d_out, st);
-                else rc = gmm_launch_tied_senone(g, m->d_lists, T, t0, tn, m->kind == 2, nullptr, 0, d_out, st);
-                if (rc) return rc;
-            }
+        const int chunk = frames_per_list_chunk(m);
+        if ((rc = ensure((void **)&m->d_lists, &m->lists_cap, (size_t)chunk * list_bytes_per_frame(m)))) return rc;
+        for (int t0 = 0; t0 < T; t0 += chunk) {
+            int tn = std::min(T - t0, chunk);
+            if ((rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st))) return rc;
+            if (m->kind == 0) rc = gmm_launch_ms_senone(g, m->d_lists, T, t0, tn, d_out, st);
+            else rc = gmm_launch_tied_senone(g, m->d_lists, T, t0, tn, m->kind == 2, nullptr, 0, d_out, st);
+            if (rc) return rc;
         }
     }
     if (timed) cudaEventRecord(m->ev[2], st);

@@ -41,8 +41,10 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
                        const uint8_t *h_mixw_sfc /* [sen][feat][cw] */, int device);
 void tc_plan_free(TcPlan *p);
 bool tc_shape_supported(const GmmDev &g);
-// scores T frames into raw (un-normalised int16 [T][n_sen]); ms[0]=prep, ms[1]=main
-int tc_score(TcPlan *p, const GmmDev &g, const float *d_feat, int T, int16_t *d_raw, cudaStream_t st,
-             cudaEvent_t *ev_prep /* recorded after operand prep, or NULL */);
+// Stage 1: operand prep + scoring kernel -> tile-major raw scores inside the
+// plan (ev_prep, if given, is recorded between the two kernels).  Stage 2:
+// transpose to row-major d_out[T][n_sen], minus the frame best if asked.
+int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out);
+int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st);
 
 }  // namespace b200

@@ -1,12 +1,621 @@
-// mahal_tc.cu -- placeholder (filled in by the tcgen05 kernel).
+// mahal_tc.cu -- tensor-core Mahalanobis scoring for fully-continuous models
+// (single stream, one codebook per senone): the K1+K2 kernel of SURVEY.md
+// section 2.4 written for sm_100a with tcgen05 / TMEM / bulk-TMA.
+//
+// Reference arithmetic being reproduced (pocketsphinx/src/libpocketsphinx):
+//   ms_gauden.c:417-523  d[t,g] = det[g] - sum_i (x[t,i]-mu[g,i])^2 * v[g,i]
+//   ms_senone.c:372-421  top-N of the M densities of a senone,
+//                        fden = ((int32)d + 1023) >> 10, table log-add of
+//                        (fden - mixw) in descending-d order, negate, /aw,
+//                        clamp to int16
+// (the per-frame best-score subtraction of ms_mgau.c:188-204 runs as a
+// separate streaming pass, gmm_launch_normalize-style, fused with the
+// tile-major -> row-major transpose of the scores).
+//
+// GEMM restatement.  d[t,g] = sum_k A[t,k] * B[g,k] with K = 2D+2 columns
+//     k = 0,1      : A = 1             B = (det - sum_i mu^2 v) in two pieces
+//     k = 2+2i     : A = x_i^2         B = -v_i
+//     k = 3+2i     : A = x_i           B = 2 mu_i v_i
+// padded to a multiple of 8.  Scores must be right to about one raw log unit
+// in 10^5..10^6, i.e. fp32-class operands: every operand is split into two
+// TF32 numbers (hi + lo, 2 x 11 significant bits) and the product is formed as
+//     Ahi*Bhi + Ahi*Blo + Alo*Bhi          ("TF32x3")
+// with fp32 accumulation in TMEM.  The constant comes first in K so partial
+// sums stay near the final magnitude.
+//
+// Data layout in HBM (all pre-tiled so that every shared-memory stage is ONE
+// contiguous bulk copy, in the UMMA K-major no-swizzle canonical layout:
+// 16-byte K-chunks, 8-row core matrices, SBO = 128 B, LBO = rows*16 B):
+//   B  [n_tile][kstep][hi|lo][chunk 0|1][256 rows][4 f32]   16 KB / kstep, static
+//   A  [m_tile][kstep][hi|lo][chunk 0|1][128 rows][4 f32]    8 KB / kstep, per call
+//   raw scores, tile-major [n_tile][T_pad][256/M] int16  (coalesced 16 B stores)
+//
+// Kernel (persistent, 1 CTA / SM, 320 threads):
+//   warp 0      bulk-TMA producer: the unit's B tile once (resident, 160 KB),
+//               then the A k-steps of successive frame tiles through a ring
+//   warp 1      single-thread tcgen05.mma issuer, 128x256x8 kind::tf32,
+//               3 MMAs per k-step, two 256-column TMEM accumulators
+//   warps 2..9  epilogue: tcgen05.ld 32 columns (= one 32-density senone) per
+//               thread, integer keys (trunc(d) << log2 M | density id), top-4 by
+//               a sort4 + bitonic-merge network in registers, table log-add
+//               from shared memory, int16 stores
+// A work unit is (n_tile, frame-range); units are ordered so that concurrently
+// running CTAs stream the same A tiles (L2 reuse) against different B tiles.
 #include "gmm_dev.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 namespace b200 {
-struct TcPlan { int dummy; };
-bool tc_shape_supported(const GmmDev &) { return false; }
-TcPlan *tc_plan_create(const GmmDev &, const float *, const float *, const float *, const uint8_t *, int) { return nullptr; }
-void tc_plan_free(TcPlan *p) { delete p; }
-int tc_score(TcPlan *, const GmmDev &, const float *, int, int16_t *, cudaStream_t, cudaEvent_t *) {
-    set_error("tensor-core path not built");
+
+namespace {
+
+constexpr int kTileM = 128;           // frames per tile (UMMA M)
+constexpr int kTileN = 256;           // Gaussians per tile (UMMA N)
+constexpr int kStages = 6;            // A ring depth (k-steps)
+constexpr int kAStageBytes = 2 * 2 * kTileM * 16;   // hi|lo x 2 chunks x 128 rows x 16 B = 8 KB
+constexpr int kBStageBytes = 2 * 2 * kTileN * 16;   // 16 KB per k-step
+constexpr int kMaxKSteps = 10;        // K <= 80  (D <= 39)
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+struct TcParams {
+    const float *gB;        // pre-tiled B operand
+    const float *gA;        // pre-tiled A operand
+    const uint8_t *gMixw;   // [n_tiles_n][256] mixture weights in tile row order
+    int16_t *raw;           // [n_tiles_n][T_pad][spt]
+    int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
+    uint8_t logadd[256];
+};
+
+// ------------------------------------------------------------------ PTX glue
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Spin with a watchdog: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32
+// (2<<7, 2<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                            ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ------------------------------------------------------------- top-4 network
+__device__ __forceinline__ void ce(int32_t &a, int32_t &b) {   // a >= b afterwards
+    const int32_t hi = max(a, b), lo = min(a, b);
+    a = hi; b = lo;
+}
+__device__ __forceinline__ void sort4(int32_t &a, int32_t &b, int32_t &c, int32_t &d) {
+    ce(a, b); ce(c, d); ce(a, c); ce(b, d); ce(b, c);
+}
+// top[0..3] (sorted desc) <- top-4 of top U {a,b,c,d}
+__device__ __forceinline__ void merge4(int32_t (&top)[4], int32_t a, int32_t b, int32_t c, int32_t d) {
+    sort4(a, b, c, d);
+    int32_t m0 = max(top[0], d), m1 = max(top[1], c), m2 = max(top[2], b), m3 = max(top[3], a);
+    ce(m0, m2); ce(m1, m3); ce(m0, m1); ce(m2, m3);   // bitonic merge
+    top[0] = m0; top[1] = m1; top[2] = m2; top[3] = m3;
+}
+
+template <int M>
+struct IdBits { static constexpr int v = (M == 8) ? 3 : (M == 16) ? 4 : 5; };
+
+// Integer key: trunc(d) in the high bits (what the reference's (int32)dist
+// keeps), density id in the low bits so that the later density wins ties
+// (ms_gauden.c:510-514).
+template <int M>
+__device__ __forceinline__ int32_t make_key(uint32_t bits, int id) {
+    float d = fmaxf(__uint_as_float(bits), -3.0e7f);   // keep trunc(d) << 5 inside int32
+    return (__float2int_rz(d) << IdBits<M>::v) | id;
+}
+
+// senone_eval for one senone from its 4 best keys.
+template <int M>
+__device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], const uint8_t *mixw,
+                                                    const uint8_t *tab, int aw) {
+    constexpr int IB = IdBits<M>::v;
+    int32_t fscr = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int32_t dint = top[j] >> IB;
+        const int32_t fden = (dint + ((1 << kShift) - 1)) >> kShift;
+        const int32_t fw = fden - (int32_t)mixw[top[j] & (M - 1)];
+        fscr = (j == 0) ? fw : logadd_tab(tab, fscr, fw);
+    }
+    int32_t scr = -fscr;
+    if (aw != 1) scr /= aw;
+    return clamp16(scr);
+}
+
+// ------------------------------------------------------------------- kernels
+// Feature rows -> pre-tiled, split A operand.
+__global__ void __launch_bounds__(kTileM)
+tc_prep_kernel(const float *__restrict__ feat, int T, int D, int ksteps, float *__restrict__ gA) {
+    const int mt = blockIdx.x, j = blockIdx.y, r = threadIdx.x;
+    const int t = mt * kTileM + r;
+    float hi[8], lo[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const int k = j * 8 + kk;
+        float a = 0.f;
+        if (t < T) {
+            if (k < 2) a = 1.f;
+            else {
+                const int i = (k - 2) >> 1;
+                if (i < D) {
+                    const float x = feat[(size_t)t * D + i];
+                    a = ((k - 2) & 1) ? x : __fmul_rn(x, x);
+                }
+            }
+        }
+        uint32_t h, l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+        const float rem = __fsub_rn(a, __uint_as_float(h));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
+        hi[kk] = __uint_as_float(h);
+        lo[kk] = __uint_as_float(l);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(gA + ((size_t)mt * ksteps + j) * (kAStageBytes / 4));
+    dst[0 * kTileM + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_score_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int SPT = kTileN / M;       // senones per tile
+    constexpr int SPH = SPT / 2;          // senones per epilogue thread (half of the columns)
+    uint8_t *sB = smem;                                         // ksteps * 16 KB
+    uint8_t *sA = smem + kMaxKSteps * kBStageBytes;             // kStages * 8 KB
+    uint8_t *sMixw = sA + kStages * kAStageBytes;               // 256 B
+    uint8_t *sTab = sMixw + 256;                                // 256 B
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256);
+    // barrier map: 0 b_full, 1 b_empty, 2..2+S a_full, 2+S..2+2S a_empty, then tmem_full[2], tmem_empty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + 2 * kStages + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    constexpr int B_FULL = 0, B_EMPTY = 1, A_FULL = 2, A_EMPTY = 2 + kStages, T_FULL = 2 + 2 * kStages, T_EMPTY = T_FULL + 2;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(B_FULL), 1);
+        mbar_init(BAR(B_EMPTY), 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), 1); mbar_init(BAR(A_EMPTY + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), kEpiThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256; i += kThreads) sTab[i] = p.logadd[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksteps = p.ksteps;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, bphase = 0;
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
+                const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+                mbar_wait(BAR(B_EMPTY), bphase ^ 1);
+                mbar_expect_tx(BAR(B_FULL), (uint32_t)ksteps * kBStageBytes);
+                const uint8_t *gb = reinterpret_cast<const uint8_t *>(p.gB) + (size_t)nt * ksteps * kBStageBytes;
+                for (int j = 0; j < ksteps; ++j)
+                    bulk_g2s(smem_u32(sB + j * kBStageBytes), gb + (size_t)j * kBStageBytes, kBStageBytes, BAR(B_FULL));
+                bphase ^= 1;
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    const uint8_t *ga = reinterpret_cast<const uint8_t *>(p.gA) + (size_t)mt * ksteps * kAStageBytes;
+                    for (int j = 0; j < ksteps; ++j) {
+                        mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
+                        mbar_expect_tx(BAR(A_FULL + stage), kAStageBytes);
+                        bulk_g2s(smem_u32(sA + stage * kAStageBytes), ga + (size_t)j * kAStageBytes, kAStageBytes,
+                                 BAR(A_FULL + stage));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0; uint32_t phase = 0, bphase = 0, accphase = 0;
+            const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                const int mc = u / p.n_tiles_n;
+                const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+                mbar_wait(BAR(B_FULL), bphase);
+                bphase ^= 1;
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    mbar_wait(BAR(T_EMPTY + acc), accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTileN;
+                    for (int j = 0; j < ksteps; ++j) {
+                        mbar_wait(BAR(A_FULL + stage), phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = sA0 + stage * kAStageBytes, a_lo = a_hi + kAStageBytes / 2;
+                        const uint32_t b_hi = sB0 + j * kBStageBytes, b_lo = b_hi + kBStageBytes / 2;
+                        const uint64_t dAhi = make_desc(a_hi, kTileM * 16, 128), dAlo = make_desc(a_lo, kTileM * 16, 128);
+                        const uint64_t dBhi = make_desc(b_hi, kTileN * 16, 128), dBlo = make_desc(b_lo, kTileN * 16, 128);
+                        tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
+                        tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
+                        tc_commit(BAR(A_EMPTY + stage));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(BAR(T_FULL + acc));
+                    if (++acc == 2) { acc = 0; accphase ^= 1; }
+                }
+                tc_commit(BAR(B_EMPTY));
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps) =====================
+        const int et = threadIdx.x - 64;                 // 0..255
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                // which 128 columns
+        const int row = q * 32 + lane;                   // frame row in the tile
+        int acc = 0; uint32_t accphase = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
+            const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+            epi_bar();
+            sMixw[et] = p.gMixw[(size_t)nt * kTileN + et];
+            epi_bar();
+            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
+            for (int mt = mt0; mt < mt1; ++mt) {
+                mbar_wait(BAR(T_FULL + acc), accphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + half * 128);
+                int16_t res[SPH];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {            // 4 chunks of 32 columns
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 3) {
+                        // every column of this thread has been read: release the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+                    }
+#pragma unroll
+                    for (int s = 0; s < 32 / M; ++s) {   // senones inside the chunk
+                        int32_t top[4];
+                        top[0] = make_key<M>(v[s * M + 0], 0); top[1] = make_key<M>(v[s * M + 1], 1);
+                        top[2] = make_key<M>(v[s * M + 2], 2); top[3] = make_key<M>(v[s * M + 3], 3);
+                        sort4(top[0], top[1], top[2], top[3]);
+#pragma unroll
+                        for (int g = 4; g < M; g += 4)
+                            merge4(top, make_key<M>(v[s * M + g], g), make_key<M>(v[s * M + g + 1], g + 1),
+                                   make_key<M>(v[s * M + g + 2], g + 2), make_key<M>(v[s * M + g + 3], g + 3));
+                        const int sl = c * (32 / M) + s;                  // senone within this thread's half
+                        res[sl] = (int16_t)senone_from_keys<M>(top, sMixw + (half * SPH + sl) * M, sTab, p.aw);
+                    }
+                }
+                const int t = mt * kTileM + row;
+                if (t < p.T) {
+                    int16_t *dst = rawt + (size_t)t * SPT + half * SPH;
+                    if (SPH == 4) {
+                        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(res);
+                    } else if (SPH == 8) {
+                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(res);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < SPH; k += 8)
+                            *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(res + k);
+                    }
+                }
+                if (++acc == 2) { acc = 0; accphase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// Tile-major raw scores -> row-major [T][n_sen], optionally minus the frame's
+// best (ms_mgau.c:188-204).  One block per 8 frames: reads are 8 frames x spt
+// senones = contiguous runs, writes are whole rows.
+constexpr int kNormFrames = 8;
+__global__ void __launch_bounds__(256)
+tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
+                 int subtract_best, int16_t *__restrict__ out) {
+    extern __shared__ int16_t s_rows[];              // [8][n_sen_pad]
+    __shared__ int s_best[kNormFrames];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * kNormFrames;
+    const int nf = min(kNormFrames, T - t0);
+    const int stride = n_tiles_n * spt;              // padded senone count
+    if (tid < kNormFrames) s_best[tid] = 0x7fffffff;
+    __syncthreads();
+    int32_t best[kNormFrames];
+#pragma unroll
+    for (int f = 0; f < kNormFrames; ++f) best[f] = 0x7fffffff;
+    // element e = (nt, f, k): raw[(nt*T_pad + t0 + f)*spt + k]
+    const int per_tile = kNormFrames * spt;
+    for (int e = tid; e < n_tiles_n * per_tile; e += blockDim.x) {
+        const int nt = e / per_tile, rem = e - nt * per_tile;
+        const int f = rem / spt, k = rem - f * spt;
+        const int s = nt * spt + k;
+        if (f < nf && s < n_sen) {
+            const int16_t v = raw[((size_t)nt * T_pad + t0 + f) * spt + k];
+            s_rows[f * stride + s] = v;
+#pragma unroll
+            for (int ff = 0; ff < kNormFrames; ++ff)
+                if (ff == f) best[ff] = min(best[ff], (int32_t)v);
+        }
+    }
+    if (subtract_best) {
+#pragma unroll
+        for (int f = 0; f < kNormFrames; ++f) {
+            int32_t b = best[f];
+            for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+            if ((tid & 31) == 0) atomicMin(&s_best[f], b);
+        }
+    }
+    __syncthreads();
+    for (int f = 0; f < nf; ++f) {
+        const int32_t b = subtract_best ? s_best[f] : 0;
+        int16_t *o = out + (size_t)(t0 + f) * n_sen;
+        for (int s = tid; s < n_sen; s += blockDim.x) o[s] = (int16_t)clamp16((int32_t)s_rows[f * stride + s] - b);
+    }
+}
+
+// host-side TF32 rounding (round to nearest, ties away, like cvt.rna.tf32.f32)
+float tf32_round(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+}  // namespace
+
+struct TcPlan {
+    int device = 0;
+    int M = 0, D = 0, S = 0, ksteps = 0, spt = 0, n_tiles_n = 0;
+    float *dB = nullptr;
+    uint8_t *dMixw = nullptr;
+    float *dA = nullptr; size_t a_cap = 0;       // bytes
+    int16_t *dRaw = nullptr; size_t raw_cap = 0; // bytes
+    int n_sm = 148;
+    int aw = 1;
+    uint8_t logadd[256];
+};
+
+bool tc_shape_supported(const GmmDev &g) {
+    if (g.n_feat != 1 || g.topn != 4 || g.n_mgau != g.n_sen) return false;
+    if (!(g.n_density == 8 || g.n_density == 16 || g.n_density == 32)) return false;
+    const int K = 2 * g.featlen[0] + 2;
+    if ((K + 7) / 8 > kMaxKSteps) return false;
+    return true;
+}
+
+void tc_plan_free(TcPlan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dRaw);
+    delete p;
+}
+
+TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var, const float *h_det,
+                       const uint8_t *h_mixw, int device) {
+    if (!tc_shape_supported(g)) return nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        return nullptr;   // tcgen05 needs sm_100; the exact path still runs
+    }
+    TcPlan *p = new TcPlan();
+    p->device = device; p->n_sm = prop.multiProcessorCount;
+    p->M = g.n_density; p->D = g.featlen[0]; p->S = g.n_sen; p->aw = g.aw;
+    const int K = 2 * p->D + 2;
+    p->ksteps = (K + 7) / 8;
+    p->spt = kTileN / p->M;
+    p->n_tiles_n = (p->S + p->spt - 1) / p->spt;
+    memcpy(p->logadd, g.logadd, 256);
+    const int KP = p->ksteps * 8, M = p->M, D = p->D;
+    const size_t tile_floats = (size_t)p->ksteps * (kBStageBytes / 4);
+    std::vector<float> B((size_t)p->n_tiles_n * tile_floats, 0.f);
+    std::vector<uint8_t> mw((size_t)p->n_tiles_n * kTileN, 0);
+    std::vector<double> col(KP);
+    for (int nt = 0; nt < p->n_tiles_n; ++nt) {
+        for (int r = 0; r < kTileN; ++r) {
+            const int s = nt * p->spt + r / M, dens = r % M;
+            std::fill(col.begin(), col.end(), 0.0);
+            double hi1 = 0, lo1 = 0, hi2 = 0, lo2 = 0;
+            if (s < p->S) {
+                const float *mu = h_mean + ((size_t)s * M + dens) * D;
+                const float *v = h_var + ((size_t)s * M + dens) * D;
+                double c = (double)h_det[(size_t)s * M + dens];
+                for (int i = 0; i < D; ++i) {
+                    c -= (double)mu[i] * (double)mu[i] * (double)v[i];
+                    col[2 + 2 * i] = -(double)v[i];
+                    col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
+                }
+                hi1 = tf32_round((float)c); lo1 = tf32_round((float)(c - hi1));
+                const double c2 = c - hi1 - lo1;
+                hi2 = tf32_round((float)c2); lo2 = tf32_round((float)(c2 - hi2));
+                mw[(size_t)nt * kTileN + r] = h_mixw[(size_t)s * M + dens];
+            } else {
+                hi1 = -3.0e7;   // padding Gaussian: far below anything real
+            }
+            float *tile = B.data() + (size_t)nt * tile_floats;
+            for (int k = 0; k < KP; ++k) {
+                float hi, lo;
+                if (k == 0) { hi = (float)hi1; lo = (float)lo1; }
+                else if (k == 1) { hi = (float)hi2; lo = (float)lo2; }
+                else { hi = tf32_round((float)col[k]); lo = tf32_round((float)(col[k] - (double)hi)); }
+                const int j = k / 8, c = (k % 8) / 4, e = k % 4;
+                // [kstep][hi|lo][chunk][256 rows][4]
+                float *st = tile + (size_t)j * (kBStageBytes / 4);
+                st[((0 * 2 + c) * kTileN + r) * 4 + e] = hi;
+                st[((1 * 2 + c) * kTileN + r) * 4 + e] = lo;
+            }
+        }
+    }
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaMalloc((void **)&p->dB, B.size() * 4) != cudaSuccess ||
+        cudaMalloc((void **)&p->dMixw, mw.size()) != cudaSuccess ||
+        cudaMemcpy(p->dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->dMixw, mw.data(), mw.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("tensor-core plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        tc_plan_free(p);
+        return nullptr;
+    }
+    return p;
+}
+
+template <int M>
+static int launch_score(const TcParams &prm, int grid, size_t smem, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    tc_score_kernel<M><<<grid, kThreads, smem, st>>>(prm);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out) {
+    const int n_tiles_m = (T + kTileM - 1) / kTileM;
+    const int T_pad = n_tiles_m * kTileM;
+    const size_t a_bytes = (size_t)n_tiles_m * p->ksteps * kAStageBytes;
+    const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->spt * sizeof(int16_t);
+    if (p->a_cap < a_bytes) {
+        cudaFree(p->dA); p->dA = nullptr; p->a_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&p->dA, a_bytes));
+        p->a_cap = a_bytes;
+    }
+    if (p->raw_cap < raw_bytes) {
+        cudaFree(p->dRaw); p->dRaw = nullptr; p->raw_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&p->dRaw, raw_bytes));
+        p->raw_cap = raw_bytes;
+    }
+    tc_prep_kernel<<<dim3(n_tiles_m, p->ksteps), kTileM, 0, st>>>(d_feat, T, p->D, p->ksteps, p->dA);
+    B200_LAUNCH_CHECK();
+    if (ev_prep) cudaEventRecord(*ev_prep, st);
+
+    TcParams prm;
+    prm.gB = p->dB; prm.gA = p->dA; prm.gMixw = p->dMixw; prm.raw = p->dRaw;
+    prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
+    prm.ksteps = p->ksteps; prm.aw = p->aw;
+    // split the frame axis so that there are >= ~16 units per CTA, but never
+    // less than 8 frame tiles per unit (B reload amortisation)
+    int m_chunks = 1;
+    while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
+    prm.m_chunks = m_chunks;
+    prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
+    prm.m_chunks = (n_tiles_m + prm.tiles_per_chunk - 1) / prm.tiles_per_chunk;
+    prm.n_units = p->n_tiles_n * prm.m_chunks;
+    memcpy(prm.logadd, p->logadd, 256);
+    const int grid = std::min(prm.n_units, p->n_sm);
+    const size_t smem = (size_t)kMaxKSteps * kBStageBytes + (size_t)kStages * kAStageBytes + 512 +
+                        (2 + 2 * kStages + 4) * 8 + 16;
+    *T_pad_out = T_pad;
+    switch (p->M) {
+        case 8: return launch_score<8>(prm, grid, smem, st);
+        case 16: return launch_score<16>(prm, grid, smem, st);
+        case 32: return launch_score<32>(prm, grid, smem, st);
+    }
+    set_error("tensor-core path: n_density %d unsupported", p->M);
     return B200_ERR_UNSUP;
 }
+
+int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
+    const size_t sh = (size_t)kNormFrames * p->n_tiles_n * p->spt * sizeof(int16_t);
+    if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    tc_finish_kernel<<<(T + kNormFrames - 1) / kNormFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
+                                                                           p->n_tiles_n, subtract_best, d_out);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 }  // namespace b200
