@@ -30,13 +30,13 @@
 //   A  [m_tile][kstep][hi|lo][chunk 0|1][128 rows][4 f32]    8 KB / kstep, per call
 //   raw scores, tile-major [n_tile][T_pad][256/M] int16  (coalesced 16 B stores)
 //
-// Kernel (persistent, 1 CTA / SM, 320 threads):
+// Kernel (persistent, 1 CTA / SM, 576 threads):
 //   warp 0      bulk-TMA producer: the unit's B tile once (resident, 160 KB),
 //               then the A k-steps of successive frame tiles through a ring
 //   warp 1      single-thread tcgen05.mma issuer, 128x256x8 kind::tf32,
 //               3 MMAs per k-step, two 256-column TMEM accumulators
-//   warps 2..9  epilogue: tcgen05.ld 32 columns (= one 32-density senone) per
-//               thread, integer keys (trunc(d) << log2 M | density id), top-4 by
+//   warps 2..17 epilogue: tcgen05.ld of 64 columns (= two 32-density senones)
+//               per thread, accumulator released immediately, integer keys (trunc(d) << log2 M | density id), top-4 by
 //               a sort4 + bitonic-merge network in registers, table log-add
 //               from shared memory, int16 stores
 // A work unit is (n_tile, frame-range); units are ordered so that concurrently
@@ -44,6 +44,7 @@
 #include "gmm_dev.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -57,8 +58,10 @@ constexpr int kStages = 6;            // A ring depth (k-steps)
 constexpr int kAStageBytes = 2 * 2 * kTileM * 16;   // hi|lo x 2 chunks x 128 rows x 16 B = 8 KB
 constexpr int kBStageBytes = 2 * 2 * kTileN * 16;   // 16 KB per k-step
 constexpr int kMaxKSteps = 10;        // K <= 80  (D <= 39)
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 16;         // 4 per TMEM lane quarter, 64 accumulator columns each
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kColsPerEpiThread = kTileN / (kEpiWarps / 4);   // 64
 constexpr uint32_t kTmemCols = 512;
 
 struct TcParams {
@@ -67,6 +70,8 @@ struct TcParams {
     const uint8_t *gMixw;   // [n_tiles_n][256] mixture weights in tile row order
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
+    int m31;                // the constant 31, kept opaque to the compiler (see make_key)
+    int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
     uint8_t logadd[256];
 };
 
@@ -141,47 +146,50 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                             ((uint32_t)(kTileM >> 4) << 24);
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // ------------------------------------------------------------- top-4 network
-__device__ __forceinline__ void ce(int32_t &a, int32_t &b) {   // a >= b afterwards
-    const int32_t hi = max(a, b), lo = min(a, b);
-    a = hi; b = lo;
+// Keys are ints where SMALLER is better (see make_key); lists are ascending.
+__device__ __forceinline__ void ce(int32_t &a, int32_t &b) {   // a <= b afterwards
+    const int32_t lo = min(a, b), hi = max(a, b);
+    a = lo; b = hi;
 }
 __device__ __forceinline__ void sort4(int32_t &a, int32_t &b, int32_t &c, int32_t &d) {
     ce(a, b); ce(c, d); ce(a, c); ce(b, d); ce(b, c);
 }
-// top[0..3] (sorted desc) <- top-4 of top U {a,b,c,d}
+// top[0..3] (ascending) <- the 4 smallest of top U {a,b,c,d}
 __device__ __forceinline__ void merge4(int32_t (&top)[4], int32_t a, int32_t b, int32_t c, int32_t d) {
     sort4(a, b, c, d);
-    int32_t m0 = max(top[0], d), m1 = max(top[1], c), m2 = max(top[2], b), m3 = max(top[3], a);
+    int32_t m0 = min(top[0], d), m1 = min(top[1], c), m2 = min(top[2], b), m3 = min(top[3], a);
     ce(m0, m2); ce(m1, m3); ce(m0, m1); ce(m2, m3);   // bitonic merge
     top[0] = m0; top[1] = m1; top[2] = m2; top[3] = m3;
 }
 
-template <int M>
-struct IdBits { static constexpr int v = (M == 8) ? 3 : (M == 16) ? 4 : 5; };
-
-// Integer key: trunc(d) in the high bits (what the reference's (int32)dist
-// keeps), density id in the low bits so that the later density wins ties
-// (ms_gauden.c:510-514).
-template <int M>
-__device__ __forceinline__ int32_t make_key(uint32_t bits, int id) {
-    float d = fmaxf(__uint_as_float(bits), -3.0e7f);   // keep trunc(d) << 5 inside int32
-    return (__float2int_rz(d) << IdBits<M>::v) | id;
+// The B operand is stored scaled by -32, so the accumulator holds -32*d (an
+// exact power-of-two scaling).  One saturating F2I gives J = trunc(-32 d); its
+// five fractional bits are replaced by (31 - density id).  The key then sorts
+// ascending by floor(-d) -- for d <= 0 that is -(int32)d, the integer the
+// reference keeps (ms_senone.c:392) -- and on equal integers the LATER density
+// comes first, as in ms_gauden.c:510-514.  Saturation makes far-away
+// Gaussians (|d| > 6.7e7) compare as "worst" instead of wrapping.
+// (For d > 0 with a fractional part >= 1/32 the recovered integer is
+// trunc(d)+1; it changes fden only when that integer is a multiple of 1024.)
+constexpr float kAccScale = 32.0f;
+// `m31` is the constant 31 passed as a run-time value so that the compiler
+// emits ONE three-input LOP3 ((j | m31) ^ id, id immediate) instead of two.
+__device__ __forceinline__ int32_t make_key(uint32_t bits, int id, int32_t m31) {
+    return (__float2int_rz(__uint_as_float(bits)) | m31) ^ id;
 }
 
 // senone_eval for one senone from its 4 best keys.
-template <int M>
 __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], const uint8_t *mixw,
                                                     const uint8_t *tab, int aw) {
-    constexpr int IB = IdBits<M>::v;
     int32_t fscr = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int32_t dint = top[j] >> IB;
+        const int32_t dint = -(top[j] >> 5);
         const int32_t fden = (dint + ((1 << kShift) - 1)) >> kShift;
-        const int32_t fw = fden - (int32_t)mixw[top[j] & (M - 1)];
+        const int32_t fw = fden - (int32_t)mixw[31 - (top[j] & 31)];
         fscr = (j == 0) ? fw : logadd_tab(tab, fscr, fw);
     }
     int32_t scr = -fscr;
@@ -229,7 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int SPT = kTileN / M;       // senones per tile
-    constexpr int SPH = SPT / 2;          // senones per epilogue thread (half of the columns)
     uint8_t *sB = smem;                                         // ksteps * 16 KB
     uint8_t *sA = smem + kMaxKSteps * kBStageBytes;             // kStages * 8 KB
     uint8_t *sMixw = sA + kStages * kAStageBytes;               // 256 B
@@ -310,8 +317,10 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                         const uint64_t dAhi = make_desc(a_hi, kTileM * 16, 128), dAlo = make_desc(a_lo, kTileM * 16, 128);
                         const uint64_t dBhi = make_desc(b_hi, kTileN * 16, 128), dBlo = make_desc(b_lo, kTileN * 16, 128);
                         tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
-                        tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
+                        if (!(p.dbg & 2)) {
+                            tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
+                            tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
+                        }
                         tc_commit(BAR(A_EMPTY + stage));
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -322,59 +331,71 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
             }
         }
     } else {
-        // ===================== epilogue (8 warps) =====================
-        const int et = threadIdx.x - 64;                 // 0..255
-        const int q = warp & 3;                          // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                // which 128 columns
+        // ===================== epilogue (16 warps) =====================
+        // Warp w may read TMEM lanes 32*(w%4)..+31 only; the four warps of a lane
+        // quarter split the 256 accumulator columns into 64-column groups.  Each
+        // thread pulls its 64 columns into registers, releases the accumulator
+        // at once (the MMA warp can start the tile after next) and only then
+        // does the selection / log-add arithmetic.
+        constexpr int CPT = kColsPerEpiThread;           // columns per thread
+        constexpr int SPE = CPT / M;                     // senones per thread
+        const int et = threadIdx.x - 64;                 // 0..511
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;                  // column group 0..3
         const int row = q * 32 + lane;                   // frame row in the tile
         int acc = 0; uint32_t accphase = 0;
+        const int32_t m31 = p.m31;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
             epi_bar();
-            sMixw[et] = p.gMixw[(size_t)nt * kTileN + et];
+            if (et < kTileN) sMixw[et] = p.gMixw[(size_t)nt * kTileN + et];
             epi_bar();
             int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
+            const uint8_t *mixw_t = sMixw + cg * CPT;
             for (int mt = mt0; mt < mt1; ++mt) {
                 mbar_wait(BAR(T_FULL + acc), accphase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + half * 128);
-                int16_t res[SPH];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + cg * CPT);
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+                int16_t res[SPE];
+                if (p.dbg & 1) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {            // 4 chunks of 32 columns
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    if (c == 3) {
-                        // every column of this thread has been read: release the accumulator
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
-                    }
+                    for (int k = 0; k < SPE; ++k) res[k] = (int16_t)(v0[k] ^ v1[k]);
+                } else
 #pragma unroll
-                    for (int s = 0; s < 32 / M; ++s) {   // senones inside the chunk
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t (&v)[32] = c ? v1 : v0;
+#pragma unroll
+                    for (int s = 0; s < 32 / M; ++s) {   // senones inside the 32-column chunk
                         int32_t top[4];
-                        top[0] = make_key<M>(v[s * M + 0], 0); top[1] = make_key<M>(v[s * M + 1], 1);
-                        top[2] = make_key<M>(v[s * M + 2], 2); top[3] = make_key<M>(v[s * M + 3], 3);
+                        top[0] = make_key(v[s * M + 0], 0, m31); top[1] = make_key(v[s * M + 1], 1, m31);
+                        top[2] = make_key(v[s * M + 2], 2, m31); top[3] = make_key(v[s * M + 3], 3, m31);
                         sort4(top[0], top[1], top[2], top[3]);
 #pragma unroll
                         for (int g = 4; g < M; g += 4)
-                            merge4(top, make_key<M>(v[s * M + g], g), make_key<M>(v[s * M + g + 1], g + 1),
-                                   make_key<M>(v[s * M + g + 2], g + 2), make_key<M>(v[s * M + g + 3], g + 3));
-                        const int sl = c * (32 / M) + s;                  // senone within this thread's half
-                        res[sl] = (int16_t)senone_from_keys<M>(top, sMixw + (half * SPH + sl) * M, sTab, p.aw);
+                            merge4(top, make_key(v[s * M + g], g, m31), make_key(v[s * M + g + 1], g + 1, m31),
+                                   make_key(v[s * M + g + 2], g + 2, m31), make_key(v[s * M + g + 3], g + 3, m31));
+                        const int sl = c * (32 / M) + s;                  // senone within this thread's columns
+                        res[sl] = (int16_t)senone_from_keys(top, mixw_t + sl * M, sTab, p.aw);
                     }
                 }
                 const int t = mt * kTileM + row;
                 if (t < p.T) {
-                    int16_t *dst = rawt + (size_t)t * SPT + half * SPH;
-                    if (SPH == 4) {
+                    int16_t *dst = rawt + (size_t)t * SPT + cg * SPE;
+                    if (SPE == 2) {
+                        *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(res);
+                    } else if (SPE == 4) {
                         *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(res);
-                    } else if (SPH == 8) {
-                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(res);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < SPH; k += 8)
+                        for (int k = 0; k < SPE; k += 8)
                             *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(res + k);
                     }
                 }
@@ -392,24 +413,69 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
 }
 
 // Tile-major raw scores -> row-major [T][n_sen], optionally minus the frame's
-// best (ms_mgau.c:188-204).  One block per 8 frames: reads are 8 frames x spt
-// senones = contiguous runs, writes are whole rows.
+// best (ms_mgau.c:188-204).  One block per kFinFrames frames; every thread owns
+// a fixed (frame, 16-byte column group) and walks the n-tiles, so reads are
+// contiguous runs of kFinFrames*spt int16 and all traffic is 16-byte vectors.
+// Requires spt % 8 == 0 and n_sen % 8 == 0 (else the generic kernel below).
+constexpr int kFinFrames = 4;
+__global__ void __launch_bounds__(256)
+tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
+                     int subtract_best, int16_t *__restrict__ out) {
+    extern __shared__ __align__(16) int16_t s_rows[];   // [kFinFrames][stride]
+    __shared__ int s_best[kFinFrames];
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * kFinFrames;
+    const int stride = n_tiles_n * spt;                  // padded senone count (multiple of 8)
+    const int q = spt >> 3;                              // uint4 per (tile, frame)
+    const int group = kFinFrames * q;                    // threads covering one n-tile
+    const int f = (tid % group) / q, k = tid % q;
+    const int nt_step = 256 / group;
+    if (tid < kFinFrames) s_best[tid] = 0x7fffffff;
+    __syncthreads();
+    int32_t best = 0x7fffffff;
+    if (t0 + f < T) {
+        for (int nt = tid / group; nt < n_tiles_n; nt += nt_step) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(raw + ((size_t)nt * T_pad + t0 + f) * spt + 8 * k);
+            *reinterpret_cast<uint4 *>(s_rows + (size_t)f * stride + nt * spt + 8 * k) = v;
+            if (nt * spt + 8 * k + 8 <= n_sen) {
+                uint32_t m = __vmins2(__vmins2(v.x, v.y), __vmins2(v.z, v.w));
+                best = min(best, min((int32_t)(int16_t)(m & 0xffff), (int32_t)(int16_t)(m >> 16)));
+            } else {
+                const int16_t *h = reinterpret_cast<const int16_t *>(&v);
+                for (int e = 0; e < 8; ++e)
+                    if (nt * spt + 8 * k + e < n_sen) best = min(best, (int32_t)h[e]);
+            }
+        }
+        if (subtract_best) atomicMin(&s_best[f], best);
+    }
+    __syncthreads();
+    const int n8 = n_sen >> 3;
+    for (int ff = 0; ff < kFinFrames && t0 + ff < T; ++ff) {
+        const int32_t b = subtract_best ? s_best[ff] : 0;
+        const uint32_t b2 = ((uint32_t)(uint16_t)(int16_t)b) * 0x10001u;
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_rows + (size_t)ff * stride);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)(t0 + ff) * n_sen);
+        for (int i = tid; i < n8; i += 256) {
+            uint4 v = src[i];
+            v.x = __vsubss2(v.x, b2); v.y = __vsubss2(v.y, b2); v.z = __vsubss2(v.z, b2); v.w = __vsubss2(v.w, b2);
+            dst[i] = v;
+        }
+    }
+}
+
+// Generic (any spt / n_sen) version of the same pass.
 constexpr int kNormFrames = 8;
 __global__ void __launch_bounds__(256)
 tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
                  int subtract_best, int16_t *__restrict__ out) {
-    extern __shared__ int16_t s_rows[];              // [8][n_sen_pad]
+    extern __shared__ __align__(16) int16_t s_rows[];   // [8][stride]
     __shared__ int s_best[kNormFrames];
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * kNormFrames;
     const int nf = min(kNormFrames, T - t0);
-    const int stride = n_tiles_n * spt;              // padded senone count
+    const int stride = n_tiles_n * spt;
     if (tid < kNormFrames) s_best[tid] = 0x7fffffff;
     __syncthreads();
-    int32_t best[kNormFrames];
-#pragma unroll
-    for (int f = 0; f < kNormFrames; ++f) best[f] = 0x7fffffff;
-    // element e = (nt, f, k): raw[(nt*T_pad + t0 + f)*spt + k]
     const int per_tile = kNormFrames * spt;
     for (int e = tid; e < n_tiles_n * per_tile; e += blockDim.x) {
         const int nt = e / per_tile, rem = e - nt * per_tile;
@@ -418,17 +484,7 @@ tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, i
         if (f < nf && s < n_sen) {
             const int16_t v = raw[((size_t)nt * T_pad + t0 + f) * spt + k];
             s_rows[f * stride + s] = v;
-#pragma unroll
-            for (int ff = 0; ff < kNormFrames; ++ff)
-                if (ff == f) best[ff] = min(best[ff], (int32_t)v);
-        }
-    }
-    if (subtract_best) {
-#pragma unroll
-        for (int f = 0; f < kNormFrames; ++f) {
-            int32_t b = best[f];
-            for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
-            if ((tid & 31) == 0) atomicMin(&s_best[f], b);
+            if (subtract_best) atomicMin(&s_best[f], (int32_t)v);
         }
     }
     __syncthreads();
@@ -514,12 +570,15 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
                     col[2 + 2 * i] = -(double)v[i];
                     col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
                 }
+                // everything is stored times -32 (see make_key)
+                c *= -(double)kAccScale;
+                for (int k = 2; k < KP; ++k) col[k] *= -(double)kAccScale;
                 hi1 = tf32_round((float)c); lo1 = tf32_round((float)(c - hi1));
                 const double c2 = c - hi1 - lo1;
                 hi2 = tf32_round((float)c2); lo2 = tf32_round((float)(c2 - hi2));
                 mw[(size_t)nt * kTileN + r] = h_mixw[(size_t)s * M + dens];
             } else {
-                hi1 = -3.0e7;   // padding Gaussian: far below anything real
+                hi1 = 3.0e7 * kAccScale;   // padding Gaussian: far below anything real
             }
             float *tile = B.data() + (size_t)nt * tile_floats;
             for (int k = 0; k < KP; ++k) {
@@ -582,6 +641,8 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.gB = p->dB; prm.gA = p->dA; prm.gMixw = p->dMixw; prm.raw = p->dRaw;
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
+    { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
+    prm.m31 = 31;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -605,15 +666,26 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
 }
 
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
-    const size_t sh = (size_t)kNormFrames * p->n_tiles_n * p->spt * sizeof(int16_t);
-    if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
+    const size_t stride = (size_t)p->n_tiles_n * p->spt;
     static bool attr = false;
     if (!attr) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    tc_finish_kernel<<<(T + kNormFrames - 1) / kNormFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
-                                                                           p->n_tiles_n, subtract_best, d_out);
+    const bool vec = (p->spt % 8 == 0) && (p->S % 8 == 0) && ((reinterpret_cast<size_t>(d_out) & 15) == 0) &&
+                     (256 % (kFinFrames * (p->spt / 8)) == 0);
+    if (vec) {
+        const size_t sh = (size_t)kFinFrames * stride * sizeof(int16_t);
+        if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
+        tc_finish_vec_kernel<<<(T + kFinFrames - 1) / kFinFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
+                                                                                 p->n_tiles_n, subtract_best, d_out);
+    } else {
+        const size_t sh = (size_t)kNormFrames * stride * sizeof(int16_t);
+        if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
+        tc_finish_kernel<<<(T + kNormFrames - 1) / kNormFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
+                                                                               p->n_tiles_n, subtract_best, d_out);
+    }
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
