@@ -27,15 +27,20 @@
 // contiguous bulk copy, in the UMMA K-major no-swizzle canonical layout:
 // 16-byte K-chunks, 8-row core matrices, SBO = 128 B, LBO = rows*16 B):
 //   B  [n_tile][kstep][hi|lo][chunk 0|1][256 rows][4 f32]   16 KB / kstep, static
-//   A  [m_tile][kstep][hi|lo][chunk 0|1][128 rows][4 f32]    8 KB / kstep, per call
+//   X  [m_tile][40 dims][128 rows] f32 -- the RAW features, tiled + transposed
+//      (20 KB / frame tile).  The 4x larger [1,1,x^2,x..] hi/lo A operand is
+//      built inside the SM: streaming it pre-expanded made the kernel L2-bound
+//      (40 GB of L2->SM traffic per 100k-frame step)
 //   raw scores, tile-major [n_tile][T_pad][256/M] int16  (coalesced 16 B stores)
 //
-// Kernel (persistent, 1 CTA / SM, 576 threads):
+// Kernel (persistent, 1 CTA / SM, 704 threads):
 //   warp 0      bulk-TMA producer: the unit's B tile once (resident, 160 KB),
-//               then the A k-steps of successive frame tiles through a ring
+//               then one raw feature tile per frame tile
+//   warps 2..5  A builders: thread = frame row; x^2, Veltkamp hi/lo split (all
+//               FMA-pipe ops) written k-step by k-step into a 5-deep A ring
 //   warp 1      single-thread tcgen05.mma issuer, 128x256x8 kind::tf32,
 //               3 MMAs per k-step, two 256-column TMEM accumulators
-//   warps 2..17 epilogue: tcgen05.ld of 64 columns (= two 32-density senones)
+//   warps 6..21 epilogue: tcgen05.ld of 64 columns (= two 32-density senones)
 //               per thread, accumulator released immediately, integer keys (trunc(d) << log2 M | density id), top-4 by
 //               a sort4 + bitonic-merge network in registers, table log-add
 //               from shared memory, int16 stores
@@ -54,19 +59,24 @@ namespace {
 
 constexpr int kTileM = 128;           // frames per tile (UMMA M)
 constexpr int kTileN = 256;           // Gaussians per tile (UMMA N)
-constexpr int kStages = 6;            // A ring depth (k-steps)
+// A ring depth (k-steps).  Chosen so that a tile's k-steps map to ring slots
+// statically (slot = j % depth): the MMA issue loop is then fully unrolled with
+// compile-time descriptor offsets -- the issuing thread is a serial resource.
+constexpr int ring_depth(int ks) { return ks == 10 ? 5 : ks; }
 constexpr int kAStageBytes = 2 * 2 * kTileM * 16;   // hi|lo x 2 chunks x 128 rows x 16 B = 8 KB
 constexpr int kBStageBytes = 2 * 2 * kTileN * 16;   // 16 KB per k-step
 constexpr int kMaxKSteps = 10;        // K <= 80  (D <= 39)
+constexpr int kBuildWarps = 4;        // A-operand builders: one thread per frame row
 constexpr int kEpiWarps = 16;         // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kFirstEpiWarp = 2 + kBuildWarps;
+constexpr int kThreads = (2 + kBuildWarps) * 32 + kEpiThreads;
 constexpr int kColsPerEpiThread = kTileN / (kEpiWarps / 4);   // 64
 constexpr uint32_t kTmemCols = 512;
 
 struct TcParams {
     const float *gB;        // pre-tiled B operand
-    const float *gA;        // pre-tiled A operand
+    const float *gX;        // features, tiled + transposed: [m_tile][4*ksteps dims][128 rows]
     const uint8_t *gMixw;   // [n_tiles_n][256] mixture weights in tile row order
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
@@ -113,6 +123,15 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred)::"memory");
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -198,62 +217,59 @@ __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], con
 }
 
 // ------------------------------------------------------------------- kernels
-// Feature rows -> pre-tiled, split A operand.
+// Feature rows [T][D] -> per frame tile, transposed and zero padded:
+// gX[m_tile][dim 0..Dp)[128 rows].  20 KB per tile for D = 39; the x^2 / hi / lo
+// expansion (4x the bytes) happens inside the SM so it never crosses L2.
 __global__ void __launch_bounds__(kTileM)
-tc_prep_kernel(const float *__restrict__ feat, int T, int D, int ksteps, float *__restrict__ gA) {
-    const int mt = blockIdx.x, j = blockIdx.y, r = threadIdx.x;
-    const int t = mt * kTileM + r;
-    float hi[8], lo[8];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        const int k = j * 8 + kk;
-        float a = 0.f;
-        if (t < T) {
-            if (k < 2) a = 1.f;
-            else {
-                const int i = (k - 2) >> 1;
-                if (i < D) {
-                    const float x = feat[(size_t)t * D + i];
-                    a = ((k - 2) & 1) ? x : __fmul_rn(x, x);
-                }
-            }
-        }
-        uint32_t h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
-        const float rem = __fsub_rn(a, __uint_as_float(h));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
-        hi[kk] = __uint_as_float(h);
-        lo[kk] = __uint_as_float(l);
-    }
-    float4 *dst = reinterpret_cast<float4 *>(gA + ((size_t)mt * ksteps + j) * (kAStageBytes / 4));
-    dst[0 * kTileM + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
-    dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+tc_prep_kernel(const float *__restrict__ feat, int T, int D, int Dp, float *__restrict__ gX) {
+    __shared__ float tile[kTileM][41];
+    const int mt = blockIdx.x, r = threadIdx.x;
+    const int t0 = mt * kTileM;
+    // coalesced read of the tile's rows (contiguous block of min(128, T-t0)*D floats)
+    const int nrow = min(kTileM, T - t0);
+    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)t0 * D + e];
+    __syncthreads();
+    for (int i = 0; i < Dp; ++i)
+        gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
 }
 
-template <int M>
+// Veltkamp split on the FMA pipe: hi carries the top 11 significant bits of a
+// (a valid TF32), lo = a - hi exactly (the tensor core reads its top 11 bits).
+__device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
+    const float c = __fmul_rn(a, 8193.0f);
+    hi = __fsub_rn(c, __fsub_rn(c, a));
+    lo = __fsub_rn(a, hi);
+}
+
+template <int M, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int SPT = kTileN / M;       // senones per tile
-    uint8_t *sB = smem;                                         // ksteps * 16 KB
-    uint8_t *sA = smem + kMaxKSteps * kBStageBytes;             // kStages * 8 KB
-    uint8_t *sMixw = sA + kStages * kAStageBytes;               // 256 B
+    constexpr int kStages = ring_depth(KS);
+    constexpr int DP = 4 * KS;            // padded dims per frame in the X tile
+    constexpr int kXBytes = DP * kTileM * 4;
+    uint8_t *sB = smem;                                         // KS * 16 KB
+    uint8_t *sA = sB + KS * kBStageBytes;                       // kStages * 8 KB
+    uint8_t *sX = sA + kStages * kAStageBytes;                  // DP * 128 * 4
+    uint8_t *sMixw = sX + kXBytes;                              // 256 B
     uint8_t *sTab = sMixw + 256;                                // 256 B
     uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256);
-    // barrier map: 0 b_full, 1 b_empty, 2..2+S a_full, 2+S..2+2S a_empty, then tmem_full[2], tmem_empty[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 + 2 * kStages + 4);
+    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2]
+    constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kStages,
+                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    constexpr int B_FULL = 0, B_EMPTY = 1, A_FULL = 2, A_EMPTY = 2 + kStages, T_FULL = 2 + 2 * kStages, T_EMPTY = T_FULL + 2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(B_FULL), 1);
         mbar_init(BAR(B_EMPTY), 1);
-        for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), 1); mbar_init(BAR(A_EMPTY + s), 1); }
+        mbar_init(BAR(X_FULL), 1);
+        mbar_init(BAR(X_EMPTY), kBuildWarps);
+        for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), kBuildWarps); mbar_init(BAR(A_EMPTY + s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), kEpiThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -268,12 +284,14 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int ksteps = p.ksteps;
+    constexpr int ksteps = KS;
 
     if (warp == 0) {
         // ===================== producer =====================
+        // Bulk-TMA: the unit's B tile (resident for the whole unit), then one raw
+        // feature tile (DP x 128 fp32) per frame tile.
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, bphase = 0;
+            uint32_t xphase = 0, bphase = 0;
             for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
                 const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
                 const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
@@ -284,50 +302,104 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     bulk_g2s(smem_u32(sB + j * kBStageBytes), gb + (size_t)j * kBStageBytes, kBStageBytes, BAR(B_FULL));
                 bphase ^= 1;
                 for (int mt = mt0; mt < mt1; ++mt) {
-                    const uint8_t *ga = reinterpret_cast<const uint8_t *>(p.gA) + (size_t)mt * ksteps * kAStageBytes;
-                    for (int j = 0; j < ksteps; ++j) {
-                        mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
-                        mbar_expect_tx(BAR(A_FULL + stage), kAStageBytes);
-                        bulk_g2s(smem_u32(sA + stage * kAStageBytes), ga + (size_t)j * kAStageBytes, kAStageBytes,
-                                 BAR(A_FULL + stage));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    }
+                    mbar_wait(BAR(X_EMPTY), xphase ^ 1);
+                    mbar_expect_tx(BAR(X_FULL), kXBytes);
+                    bulk_g2s(smem_u32(sX), reinterpret_cast<const uint8_t *>(p.gX) + (size_t)mt * kXBytes, kXBytes,
+                             BAR(X_FULL));
+                    xphase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0, acc = 0; uint32_t phase = 0, bphase = 0, accphase = 0;
-            const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-                const int mc = u / p.n_tiles_n;
-                const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
-                mbar_wait(BAR(B_FULL), bphase);
-                bphase ^= 1;
-                for (int mt = mt0; mt < mt1; ++mt) {
-                    mbar_wait(BAR(T_EMPTY + acc), accphase ^ 1);
+        // The whole warp walks the (fully unrolled) loop so control flow stays
+        // uniform; one elected lane issues.  Ring slot and barrier parity of
+        // k-step j are compile-time, descriptors are base + constant.
+        uint32_t bphase = 0, accphase = 0, tilepar = 0;
+        int acc = 0;
+        const uint64_t dA0 = make_desc(smem_u32(sA), kTileM * 16, 128);
+        const uint64_t dB0 = make_desc(smem_u32(sB), kTileN * 16, 128);
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int mc = u / p.n_tiles_n;
+            const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+            mbar_wait(BAR(B_FULL), bphase);
+            bphase ^= 1;
+            for (int mt = mt0; mt < mt1; ++mt) {
+                mbar_wait(BAR(T_EMPTY + acc), accphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTileN;
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                    constexpr int uses = KS / kStages;           // ring passes per tile (1 or 2)
+                    const int stage = j % kStages;
+                    const uint32_t par = (uses & 1) ? tilepar : (uint32_t)((j / kStages) & 1);
+                    mbar_wait(BAR(A_FULL + stage), par);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTileN;
-                    for (int j = 0; j < ksteps; ++j) {
-                        mbar_wait(BAR(A_FULL + stage), phase);
-                        tc_fence_after();
-                        const uint32_t a_hi = sA0 + stage * kAStageBytes, a_lo = a_hi + kAStageBytes / 2;
-                        const uint32_t b_hi = sB0 + j * kBStageBytes, b_lo = b_hi + kBStageBytes / 2;
-                        const uint64_t dAhi = make_desc(a_hi, kTileM * 16, 128), dAlo = make_desc(a_lo, kTileM * 16, 128);
-                        const uint64_t dBhi = make_desc(b_hi, kTileN * 16, 128), dBlo = make_desc(b_lo, kTileN * 16, 128);
+                    if (elect_one()) {
+                        // descriptor address fields are in 16-byte units
+                        const uint64_t dAhi = dA0 + (uint64_t)((stage * kAStageBytes) >> 4);
+                        const uint64_t dAlo = dAhi + (uint64_t)((kAStageBytes / 2) >> 4);
+                        const uint64_t dBhi = dB0 + (uint64_t)((j * kBStageBytes) >> 4);
+                        const uint64_t dBlo = dBhi + (uint64_t)((kBStageBytes / 2) >> 4);
                         tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
                         if (!(p.dbg & 2)) {
                             tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
                             tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
                         }
                         tc_commit(BAR(A_EMPTY + stage));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (j == KS - 1) tc_commit(BAR(T_FULL + acc));
                     }
-                    tc_commit(BAR(T_FULL + acc));
-                    if (++acc == 2) { acc = 0; accphase ^= 1; }
+                    __syncwarp();
                 }
-                tc_commit(BAR(B_EMPTY));
+                if ((KS / kStages) & 1) tilepar ^= 1;
+                if (++acc == 2) { acc = 0; accphase ^= 1; }
+            }
+            if (elect_one()) tc_commit(BAR(B_EMPTY));
+            __syncwarp();
+        }
+    } else if (warp < kFirstEpiWarp) {
+        // ===================== A-operand builders (4 warps) =====================
+        // Thread r owns frame row r of the tile: it keeps the row's DP features in
+        // registers and, k-step by k-step, writes [1,1,x^2,x,...] split into TF32
+        // hi/lo straight into the UMMA K-major layout of the A ring.
+        const int r = threadIdx.x - 64;                  // 0..127
+        const float *xs = reinterpret_cast<const float *>(sX);
+        int stage = 0; uint32_t phase = 0, xphase = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int mc = u / p.n_tiles_n;
+            const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+            for (int mt = mt0; mt < mt1; ++mt) {
+                mbar_wait(BAR(X_FULL), xphase);
+                xphase ^= 1;
+                float x[DP];
+#pragma unroll
+                for (int i = 0; i < DP; ++i) x[i] = xs[i * kTileM + r];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(X_EMPTY));     // staging buffer may be refilled
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = j * 8 + kk;
+                        if (k < 2) { hi[kk] = 1.f; lo[kk] = 0.f; }
+                        else {
+                            const int i = (k - 2) >> 1;              // i < DP by construction
+                            const float a = ((k - 2) & 1) ? x[i] : __fmul_rn(x[i], x[i]);
+                            split_tf32(a, hi[kk], lo[kk]);
+                        }
+                    }
+                    mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
+                    float4 *dst = reinterpret_cast<float4 *>(sA + stage * kAStageBytes);
+                    dst[0 * kTileM + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                    dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(A_FULL + stage));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else {
@@ -339,9 +411,9 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         // does the selection / log-add arithmetic.
         constexpr int CPT = kColsPerEpiThread;           // columns per thread
         constexpr int SPE = CPT / M;                     // senones per thread
-        const int et = threadIdx.x - 64;                 // 0..511
+        const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..511
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;                  // column group 0..3
+        const int cg = (warp - kFirstEpiWarp) >> 2;      // column group 0..3
         const int row = q * 32 + lane;                   // frame row in the tile
         int acc = 0; uint32_t accphase = 0;
         const int32_t m31 = p.m31;
@@ -513,7 +585,7 @@ struct TcPlan {
     int M = 0, D = 0, S = 0, ksteps = 0, spt = 0, n_tiles_n = 0;
     float *dB = nullptr;
     uint8_t *dMixw = nullptr;
-    float *dA = nullptr; size_t a_cap = 0;       // bytes
+    float *dA = nullptr; size_t a_cap = 0;       // tiled/transposed features (bytes)
     int16_t *dRaw = nullptr; size_t raw_cap = 0; // bytes
     int n_sm = 148;
     int aw = 1;
@@ -547,7 +619,8 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     p->device = device; p->n_sm = prop.multiProcessorCount;
     p->M = g.n_density; p->D = g.featlen[0]; p->S = g.n_sen; p->aw = g.aw;
     const int K = 2 * p->D + 2;
-    p->ksteps = (K + 7) / 8;
+    const int need = (K + 7) / 8;
+    p->ksteps = need <= 4 ? 4 : (need <= 7 ? 7 : 10);   // instantiated k-step counts
     p->spt = kTileN / p->M;
     p->n_tiles_n = (p->S + p->spt - 1) / p->spt;
     memcpy(p->logadd, g.logadd, 256);
@@ -606,22 +679,36 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     return p;
 }
 
-template <int M>
-static int launch_score(const TcParams &prm, int grid, size_t smem, cudaStream_t st) {
+template <int M, int KS>
+static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
+    const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
+                        (size_t)4 * KS * kTileM * 4 + 512 + 32 * 8 + 16;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    tc_score_kernel<M><<<grid, kThreads, smem, st>>>(prm);
+    tc_score_kernel<M, KS><<<grid, kThreads, smem, st>>>(prm);
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+template <int M>
+static int launch_score_ks(const TcParams &prm, int ks, int grid, cudaStream_t st) {
+    switch (ks) {
+        case 4: return launch_score<M, 4>(prm, grid, st);
+        case 7: return launch_score<M, 7>(prm, grid, st);
+        case 10: return launch_score<M, 10>(prm, grid, st);
+    }
+    set_error("tensor-core path: %d k-steps unsupported", ks);
+    return B200_ERR_UNSUP;
 }
 
 int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out) {
     const int n_tiles_m = (T + kTileM - 1) / kTileM;
     const int T_pad = n_tiles_m * kTileM;
-    const size_t a_bytes = (size_t)n_tiles_m * p->ksteps * kAStageBytes;
+    const int Dp = 4 * p->ksteps;
+    const size_t a_bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
     const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->spt * sizeof(int16_t);
     if (p->a_cap < a_bytes) {
         cudaFree(p->dA); p->dA = nullptr; p->a_cap = 0;
@@ -633,12 +720,12 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
         B200_CUDA_OK(cudaMalloc((void **)&p->dRaw, raw_bytes));
         p->raw_cap = raw_bytes;
     }
-    tc_prep_kernel<<<dim3(n_tiles_m, p->ksteps), kTileM, 0, st>>>(d_feat, T, p->D, p->ksteps, p->dA);
+    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, p->D, Dp, p->dA);
     B200_LAUNCH_CHECK();
     if (ev_prep) cudaEventRecord(*ev_prep, st);
 
     TcParams prm;
-    prm.gB = p->dB; prm.gA = p->dA; prm.gMixw = p->dMixw; prm.raw = p->dRaw;
+    prm.gB = p->dB; prm.gX = p->dA; prm.gMixw = p->dMixw; prm.raw = p->dRaw;
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
@@ -653,13 +740,11 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.n_units = p->n_tiles_n * prm.m_chunks;
     memcpy(prm.logadd, p->logadd, 256);
     const int grid = std::min(prm.n_units, p->n_sm);
-    const size_t smem = (size_t)kMaxKSteps * kBStageBytes + (size_t)kStages * kAStageBytes + 512 +
-                        (2 + 2 * kStages + 4) * 8 + 16;
     *T_pad_out = T_pad;
     switch (p->M) {
-        case 8: return launch_score<8>(prm, grid, smem, st);
-        case 16: return launch_score<16>(prm, grid, smem, st);
-        case 32: return launch_score<32>(prm, grid, smem, st);
+        case 8: return launch_score_ks<8>(prm, p->ksteps, grid, st);
+        case 16: return launch_score_ks<16>(prm, p->ksteps, grid, st);
+        case 32: return launch_score_ks<32>(prm, p->ksteps, grid, st);
     }
     set_error("tensor-core path: n_density %d unsupported", p->M);
     return B200_ERR_UNSUP;
