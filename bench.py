@@ -232,26 +232,22 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- model: rank 0 builds + precomputes, ONE NCCL broadcast of the packed parameters
-    n_par = N_SEN * N_DENSITY * DIM
-    n_det = N_SEN * N_DENSITY
+    params = None
     if rank == 0:
         mean, var, mixw = make_model()
         pv, pd = b.gauden_precompute(var.reshape(-1, DIM), DIM, 1e-4, LOGBASE)
         q = b.mixw_quantize_ms(mixw, 1e-7, LOGBASE)
-        blob = np.concatenate([mean.reshape(-1), pv.reshape(-1), pd.reshape(-1), var.reshape(-1),
-                               q.reshape(-1).astype(np.float32)])
-    else:
-        blob = np.zeros(3 * n_par + 2 * n_det, np.float32)
+        params = dict(mean=mean, var=pv.reshape(mean.shape), det=pd.reshape(N_SEN, N_DENSITY), mixw=q,
+                      raw_var=var)
     if world > 1:
-        tb = torch.from_numpy(blob).to(dev)
-        dist.broadcast(tb, 0)
-        blob = tb.cpu().numpy()
-        del tb
-    mean = blob[:n_par].reshape(N_SEN, N_DENSITY, DIM)
-    pv = blob[n_par:2 * n_par]
-    pd = blob[2 * n_par:2 * n_par + n_det]
-    var = blob[2 * n_par + n_det:3 * n_par + n_det].reshape(N_SEN, N_DENSITY, DIM)
-    q = blob[3 * n_par + n_det:].astype(np.uint8).reshape(N_SEN, 1, N_DENSITY)
+        from cmusphinx_b200 import shard
+        raw_var = params.pop("raw_var") if rank == 0 else None
+        params, digest = shard.broadcast_params(params, src=0, device=dev)
+        # every rank regenerates the raw variances it needs only for synthetic features
+        var = make_model()[1] if rank != 0 else raw_var
+    else:
+        var = params.pop("raw_var")
+    mean, pv, pd, q = params["mean"], params["var"], params["det"], params["mixw"]
     cfg = b.MgauConfig(N_SEN, 1, N_DENSITY, N_SEN, [DIM], topn=TOPN, logbase=LOGBASE, device=local)
     m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(N_SEN))
     if args.path is not None:

@@ -15,6 +15,6 @@ from .engine import (  # noqa: F401
     tmat_quantize, flags2list, read_gauden, read_mixw, read_tmat, read_sendump,
     device_count, launch_count,
 )
-from . import s3io, synth  # noqa: F401
+from . import s3io, synth, shard  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]
