@@ -553,9 +553,13 @@ struct b200_hmmctx {
     uint8_t *d_tp = nullptr; uint16_t *d_sseq = nullptr;
     HmmPop p{};
     size_t pop_cap = 0;  // in HMMs
-    HmmFrame *d_fr = nullptr;
+    HmmFrame *d_fr = nullptr; int fr_cap = 0;          // [n_utt]
     uint8_t *d_keep = nullptr; int32_t *d_block_count = nullptr, *d_keep_idx = nullptr;
-    uint32_t *d_mask = nullptr;
+    size_t bc_cap = 0;
+    uint32_t *d_mask = nullptr; size_t mask_cap = 0;   // [n_utt][n_words]
+    int32_t *d_utt_off = nullptr; int utt_cap = 0;
+    int32_t *d_total = nullptr;
+    std::vector<int32_t> h_utt_off;
     int16_t *d_senscr = nullptr; size_t senscr_cap = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -567,8 +571,8 @@ namespace {
 void pop_free(b200_hmmctx *c) {
     cudaFree(c->p.score); cudaFree(c->p.history); cudaFree(c->p.out_score); cudaFree(c->p.out_history);
     cudaFree(c->p.bestscore); cudaFree(c->p.senid); cudaFree(c->p.tmatid); cudaFree(c->p.mpx);
-    cudaFree(c->d_keep); cudaFree(c->d_block_count); cudaFree(c->d_keep_idx);
-    c->p = HmmPop{}; c->d_keep = nullptr; c->d_block_count = nullptr; c->d_keep_idx = nullptr; c->pop_cap = 0;
+    cudaFree(c->d_keep); cudaFree(c->d_keep_idx);
+    c->p = HmmPop{}; c->d_keep = nullptr; c->d_keep_idx = nullptr; c->pop_cap = 0;
 }
 
 int pop_reserve(b200_hmmctx *c, int n) {
@@ -585,9 +589,45 @@ int pop_reserve(b200_hmmctx *c, int n) {
     B200_CUDA_OK(cudaMalloc((void **)&c->p.tmatid, N * 2));
     B200_CUDA_OK(cudaMalloc((void **)&c->p.mpx, N));
     B200_CUDA_OK(cudaMalloc((void **)&c->d_keep, N));
-    B200_CUDA_OK(cudaMalloc((void **)&c->d_block_count, ((N + 255) / 256 + 1) * 4));
     B200_CUDA_OK(cudaMalloc((void **)&c->d_keep_idx, N * 4));
     c->pop_cap = N; c->p.n_hmm = n;
+    return B200_OK;
+}
+
+// Partition the resident population into utterances (device copies of the
+// offsets, per-utterance frame state, masks and block counters).
+int set_utts(b200_hmmctx *c, int n_utt, const int32_t *off) {
+    if (n_utt < 1 || !off || off[0] != 0 || off[n_utt] != c->p.n_hmm) { set_error("bad utterance offsets"); return B200_ERR_ARG; }
+    int mx = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        if (off[u + 1] < off[u]) { set_error("utterance offsets not monotone"); return B200_ERR_ARG; }
+        mx = std::max(mx, off[u + 1] - off[u]);
+    }
+    const int n_words = (c->c.n_sen + 31) / 32;
+    if (n_utt + 1 > c->utt_cap) {
+        cudaFree(c->d_utt_off); c->d_utt_off = nullptr; c->utt_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_utt_off, (size_t)(n_utt + 1) * 4));
+        c->utt_cap = n_utt + 1;
+    }
+    if (n_utt > c->fr_cap) {
+        cudaFree(c->d_fr); c->d_fr = nullptr; c->fr_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_fr, (size_t)n_utt * sizeof(HmmFrame)));
+        c->fr_cap = n_utt;
+    }
+    if ((size_t)n_utt * n_words > c->mask_cap) {
+        cudaFree(c->d_mask); c->d_mask = nullptr; c->mask_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_mask, (size_t)n_utt * n_words * 4));
+        c->mask_cap = (size_t)n_utt * n_words;
+    }
+    const size_t nb = (size_t)((mx + 255) / 256) * n_utt + 1;
+    if (nb > c->bc_cap) {
+        cudaFree(c->d_block_count); c->d_block_count = nullptr; c->bc_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_block_count, nb * 4));
+        c->bc_cap = nb;
+    }
+    B200_CUDA_OK(cudaMemcpy(c->d_utt_off, off, (size_t)(n_utt + 1) * 4, cudaMemcpyHostToDevice));
+    c->h_utt_off.assign(off, off + n_utt + 1);
+    c->p.n_utt = n_utt; c->p.max_per_utt = mx; c->p.utt_off = c->d_utt_off;
     return B200_OK;
 }
 
@@ -619,8 +659,7 @@ b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat, co
     const int n_words = (n_sen + 31) / 32;
     if (dev_alloc_copy(&c->d_tp, tp, (size_t)n_tmat * n_emit * (n_emit + 1)) ||
         dev_alloc_copy(&c->d_sseq, sseq, (size_t)std::max(n_sseq, 1) * n_emit * (n_sseq > 0 ? 1 : 0)) ||
-        cudaMalloc((void **)&c->d_fr, sizeof(HmmFrame)) != cudaSuccess ||
-        cudaMalloc((void **)&c->d_mask, (size_t)n_words * 4) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_total, 4) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess) {
         set_error("hmm context allocation failed"); b200_hmm_ctx_free(c); return nullptr;
@@ -634,6 +673,7 @@ void b200_hmm_ctx_free(b200_hmmctx_t *c) {
     cudaSetDevice(c->device);
     pop_free(c);
     cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr);
+    cudaFree(c->d_block_count); cudaFree(c->d_utt_off); cudaFree(c->d_total);
     if (c->st) cudaStreamDestroy(c->st);
     for (int i = 0; i < 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -646,6 +686,10 @@ int b200_hmm_pop_upload(b200_hmmctx_t *c, const b200_hmm_soa_t *h) {
     if ((rc = pop_reserve(c, h->n_hmm))) return rc;
     const size_t N = (size_t)h->n_hmm;
     const int ne = c->c.n_emit;
+    {
+        const int32_t one[2] = {0, h->n_hmm};
+        if ((rc = set_utts(c, 1, one))) return rc;
+    }
     if (N == 0) return B200_OK;
     B200_CUDA_OK(cudaMemcpy(c->p.score, h->score, N * ne * 4, cudaMemcpyHostToDevice));
     B200_CUDA_OK(cudaMemcpy(c->p.history, h->history, N * ne * 4, cudaMemcpyHostToDevice));
@@ -681,21 +725,37 @@ int b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam, v
     cudaStream_t st = stream ? (cudaStream_t)stream : c->st;
     cudaEventRecord(c->ev[0], st);
     int rc = hmm_launch_step(c->c, c->p, d_senscr, beam, c->d_fr, c->d_keep, c->d_block_count, c->d_keep_idx,
-                             c->d_mask, 1, st);
+                             c->d_mask, c->d_total, 1, st);
     cudaEventRecord(c->ev[1], st);
     return rc;
+}
+
+int b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off) {
+    if (!c) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    return set_utts(c, n_utt, utt_off);
 }
 
 int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int32_t *keep_idx, uint32_t *sen_mask) {
     if (!c) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
     B200_CUDA_OK(cudaStreamSynchronize(c->st));
-    HmmFrame fr;
-    B200_CUDA_OK(cudaMemcpy(&fr, c->d_fr, sizeof fr, cudaMemcpyDeviceToHost));
-    if (best) *best = fr.best;
-    if (n_keep) *n_keep = fr.n_keep;
-    if (keep_idx && fr.n_keep > 0) B200_CUDA_OK(cudaMemcpy(keep_idx, c->d_keep_idx, (size_t)fr.n_keep * 4, cudaMemcpyDeviceToHost));
-    if (sen_mask) B200_CUDA_OK(cudaMemcpy(sen_mask, c->d_mask, (size_t)((c->c.n_sen + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+    const int nu = std::max(c->p.n_utt, 1);
+    std::vector<HmmFrame> fr(nu);
+    int32_t total = 0;
+    if (c->p.n_hmm > 0) {
+        B200_CUDA_OK(cudaMemcpy(fr.data(), c->d_fr, sizeof(HmmFrame) * nu, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(&total, c->d_total, 4, cudaMemcpyDeviceToHost));
+    } else {
+        for (auto &f : fr) { f.best = B200_WORST_SCORE; f.n_keep = 0; }
+    }
+    for (int u = 0; u < nu; ++u) {
+        if (best) best[u] = fr[u].best;
+        if (n_keep) n_keep[u] = fr[u].n_keep;
+    }
+    if (keep_idx && total > 0) B200_CUDA_OK(cudaMemcpy(keep_idx, c->d_keep_idx, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    if (sen_mask && c->p.n_hmm > 0)
+        B200_CUDA_OK(cudaMemcpy(sen_mask, c->d_mask, (size_t)nu * ((c->c.n_sen + 31) / 32) * 4, cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[1]);
     return B200_OK;
 }
@@ -703,9 +763,10 @@ int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int3
 int b200_hmm_step_host(b200_hmmctx_t *c, const int16_t *senscr, int32_t beam) {
     if (!c || !senscr) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
-    int rc = ensure((void **)&c->d_senscr, &c->senscr_cap, (size_t)c->c.n_sen * 2);
+    const size_t nb = (size_t)c->c.n_sen * 2 * std::max(c->p.n_utt, 1);
+    int rc = ensure((void **)&c->d_senscr, &c->senscr_cap, nb);
     if (rc) return rc;
-    B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, (size_t)c->c.n_sen * 2, cudaMemcpyHostToDevice, c->st));
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, nb, cudaMemcpyHostToDevice, c->st));
     return b200_hmm_step_dev(c, c->d_senscr, beam, nullptr);
 }
 
@@ -718,7 +779,7 @@ int b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h, const int16_t *sensc
     B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, (size_t)c->c.n_sen * 2 * n_frames, cudaMemcpyHostToDevice, c->st));
     for (int f = 0; f < n_frames; ++f) {
         rc = hmm_launch_step(c->c, c->p, c->d_senscr + (size_t)f * c->c.n_sen, 0, c->d_fr, c->d_keep,
-                             c->d_block_count, c->d_keep_idx, c->d_mask, 0, c->st);
+                             c->d_block_count, c->d_keep_idx, c->d_mask, c->d_total, 0, c->st);
         if (rc) return rc;
         if (best_out) B200_CUDA_OK(cudaMemcpyAsync(&best_out[f], (const int32_t *)c->d_fr, 4, cudaMemcpyDeviceToHost, c->st));
     }

@@ -12,6 +12,8 @@ struct HmmDev {               // hmm_context_t (PS/hmm.h:136-151)
 
 struct HmmPop {               // SoA mirror of hmm_t (PS/hmm.h:156-173), state-major
     int n_hmm;
+    int n_utt, max_per_utt;   // utterances sharing the population; largest range
+    const int32_t *utt_off;   // [n_utt + 1] device
     int32_t *score, *history, *out_score, *out_history, *bestscore;
     uint16_t *senid;
     int16_t *tmatid;
@@ -22,6 +24,6 @@ struct HmmFrame { int32_t best; int32_t n_keep; };
 
 int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, int32_t beam,
                     HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
-                    uint32_t *mask, int do_beam, cudaStream_t st);
+                    uint32_t *mask, int32_t *total, int do_beam, cudaStream_t st);
 
 }  // namespace b200

@@ -228,15 +228,24 @@ __device__ __forceinline__ void eval5_mpx(HmmRegs &h, const uint8_t *tp, const i
 }
 
 // ---------------------------------------------------------------- kernels
+// All kernels take a 2-D grid: blockIdx.y = utterance.  An utterance owns the
+// contiguous HMM range [utt_off[u], utt_off[u+1]) of the population, its own
+// row of senone scores, its own frame-best / beam threshold and its own
+// active-senone mask; the compacted survivor list is global and ordered by
+// (utterance, HMM index).  n_utt == 1 is the reference's per-decoder case.
 constexpr int kHmmBlock = 256;
 
 template <int NE>
 __global__ void __launch_bounds__(kHmmBlock)
-hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr, HmmFrame *fr) {
+hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr_all, HmmFrame *fr) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
     uint8_t *s_tp = sm_raw + (((size_t)c.n_sen * 2 + 15) & ~(size_t)15);
     const int tid = threadIdx.x;
+    const int u = blockIdx.y;
+    const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+    if (lo + (int)blockIdx.x * kHmmBlock >= hi) return;   // uniform per block
+    const int16_t *senscr = senscr_all + (size_t)u * c.n_sen;
     // stage the frame's senone scores (vectorised) and the transition table
     {
         const int n16 = ((reinterpret_cast<size_t>(senscr) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
@@ -250,7 +259,7 @@ hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr, HmmFrame
     __syncthreads();
     int32_t blockbest = kWorstScore;
     const int n = p.n_hmm;
-    for (int i = blockIdx.x * kHmmBlock + tid; i < n; i += gridDim.x * kHmmBlock) {
+    for (int i = lo + blockIdx.x * kHmmBlock + tid; i < hi; i += gridDim.x * kHmmBlock) {
         HmmRegs h;
 #pragma unroll
         for (int s = 0; s < NE; ++s) {
@@ -285,32 +294,35 @@ hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr, HmmFrame
     if (tid == 0) {
         int32_t b = s_best[0];
         for (int w = 1; w < kHmmBlock / 32; ++w) b = max(b, s_best[w]);
-        atomicMax(&fr->best, b);
+        atomicMax(&fr[u].best, b);
     }
 }
 
-__global__ void hmm_frame_init_kernel(HmmFrame *fr, uint32_t *mask, int n_words) {
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) mask[i] = 0u;
-    if (threadIdx.x == 0) { fr->best = kWorstScore; fr->n_keep = 0; }
+__global__ void hmm_frame_init_kernel(HmmFrame *fr, int n_utt, uint32_t *mask, int n_mask_words) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = i0; i < n_mask_words; i += stride) mask[i] = 0u;
+    for (int i = i0; i < n_utt; i += stride) { fr[i].best = kWorstScore; fr[i].n_keep = 0; }
 }
 
 // Pass 1 of the order-preserving compaction: keep flag + per-block count.
 __global__ void __launch_bounds__(kHmmBlock)
 hmm_beam_flag_kernel(HmmPop p, const HmmFrame *fr, int32_t beam, uint8_t *keep, int32_t *block_count) {
-    const int i = blockIdx.x * kHmmBlock + threadIdx.x;
-    const int32_t thresh = fr->best + beam;
+    const int u = blockIdx.y;
+    const int i = p.utt_off[u] + blockIdx.x * kHmmBlock + threadIdx.x;
+    const int32_t thresh = fr[u].best + beam;
     bool k = false;
-    if (i < p.n_hmm) {
+    if (i < p.utt_off[u + 1]) {
         k = BT(p.bestscore[i], thresh);
         keep[i] = k ? 1 : 0;
     }
     const int cnt = __syncthreads_count(k);
-    if (threadIdx.x == 0) block_count[blockIdx.x] = cnt;
+    if (threadIdx.x == 0) block_count[u * gridDim.x + blockIdx.x] = cnt;
 }
 
-// Pass 2: exclusive scan of the block counts by one block.
+// Pass 2: exclusive scan of the block counts by one block; per-utterance
+// survivor counts land in fr[u].n_keep, the total in *total.
 __global__ void __launch_bounds__(1024)
-hmm_scan_kernel(int32_t *block_count, int n_blocks, HmmFrame *fr) {
+hmm_scan_kernel(int32_t *block_count, int n_blocks, int blocks_per_utt, HmmFrame *fr, int n_utt, int32_t *total) {
     __shared__ int32_t s_warp[32];
     __shared__ int32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -335,23 +347,33 @@ hmm_scan_kernel(int32_t *block_count, int n_blocks, HmmFrame *fr) {
         if (tid == 1023) s_carry = incl;
         __syncthreads();
     }
-    if (tid == 0) fr->n_keep = s_carry;
+    if (tid == 0) *total = s_carry;
+    __syncthreads();
+    for (int u = tid; u < n_utt; u += 1024) {
+        const int32_t b = block_count[u * blocks_per_utt];
+        const int32_t e = (u + 1 < n_utt) ? block_count[(u + 1) * blocks_per_utt] : s_carry;
+        fr[u].n_keep = e - b;
+    }
 }
 
-// Pass 3: scatter survivors (index order preserved) and OR their senones into
-// the active mask (acmod_activate_hmm).
+// Pass 3: scatter survivors (order preserved) and OR their senones into the
+// utterance's active mask (acmod_activate_hmm).
 template <int NE>
 __global__ void __launch_bounds__(kHmmBlock)
 hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block_off,
-                   int32_t *keep_idx, uint32_t *mask) {
+                   int32_t *keep_idx, uint32_t *mask_all) {
     extern __shared__ uint32_t s_mask[];
     __shared__ int32_t s_wsum[kHmmBlock / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int u = blockIdx.y;
+    const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+    if (lo + (int)blockIdx.x * kHmmBlock >= hi) return;
     const int n_words = (c.n_sen + 31) / 32;
+    uint32_t *mask = mask_all + (size_t)u * n_words;
     for (int k = tid; k < n_words; k += kHmmBlock) s_mask[k] = 0u;
     __syncthreads();
-    const int i = blockIdx.x * kHmmBlock + tid;
-    const bool k = (i < p.n_hmm) && keep[i];
+    const int i = lo + blockIdx.x * kHmmBlock + tid;
+    const bool k = (i < hi) && keep[i];
     const unsigned bal = __ballot_sync(0xffffffffu, k);
     if (lane == 0) s_wsum[w] = __popc(bal);
     if (k) {
@@ -369,7 +391,7 @@ hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block
     }
     __syncthreads();
     if (k) {
-        int off = block_off[blockIdx.x];
+        int off = block_off[u * gridDim.x + blockIdx.x];
         for (int ww = 0; ww < w; ++ww) off += s_wsum[ww];
         off += __popc(bal & ((1u << lane) - 1u));
         keep_idx[off] = i;
@@ -385,11 +407,12 @@ static size_t step_smem(const HmmDev &c) {
 
 int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, int32_t beam,
                     HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
-                    uint32_t *mask, int do_beam, cudaStream_t st) {
+                    uint32_t *mask, int32_t *total, int do_beam, cudaStream_t st) {
     const int n_words = (c.n_sen + 31) / 32;
-    const int n_blocks = (p.n_hmm + kHmmBlock - 1) / kHmmBlock;
-    if (p.n_hmm <= 0) return B200_OK;
-    hmm_frame_init_kernel<<<1, 256, 0, st>>>(fr, mask, n_words);
+    if (p.n_hmm <= 0 || p.n_utt <= 0) return B200_OK;
+    const int bpu = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock;   // blocks per utterance
+    const int n_mask = n_words * p.n_utt;
+    hmm_frame_init_kernel<<<std::max(1, std::min(148, (n_mask + 255) / 256)), 256, 0, st>>>(fr, p.n_utt, mask, n_mask);
     B200_LAUNCH_CHECK();
     const size_t sh = step_smem(c);
     if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
@@ -399,19 +422,21 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
         B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    // persistent-style grid: at most a few CTAs per SM, each strides the population
-    const int grid = std::min(n_blocks, 148 * 4);
+    // a few CTAs per SM in total; each strides its utterance's range
+    int gx = std::max(1, std::min(bpu, (148 * 8 + p.n_utt - 1) / p.n_utt));
+    dim3 grid(gx, p.n_utt);
     if (c.n_emit == 3) hmm_step_kernel<3><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
     else hmm_step_kernel<5><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
     B200_LAUNCH_CHECK();
     if (!do_beam) return B200_OK;
-    hmm_beam_flag_kernel<<<n_blocks, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
+    dim3 g2(bpu, p.n_utt);
+    hmm_beam_flag_kernel<<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
     B200_LAUNCH_CHECK();
-    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, n_blocks, fr);
+    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, bpu * p.n_utt, bpu, fr, p.n_utt, total);
     B200_LAUNCH_CHECK();
     const size_t msh = (size_t)n_words * 4;
-    if (c.n_emit == 3) hmm_scatter_kernel<3><<<n_blocks, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-    else hmm_scatter_kernel<5><<<n_blocks, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    if (c.n_emit == 3) hmm_scatter_kernel<3><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    else hmm_scatter_kernel<5><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

@@ -399,6 +399,7 @@ class HmmContext:
         return best
 
     def upload(self, pop: HmmPopulation):
+        self.n_utt = 1
         soa = pop.to_c()
         check(lib.b200_hmm_pop_upload(self._h, C.byref(soa)), "pop_upload")
 
@@ -406,21 +407,32 @@ class HmmContext:
         soa = pop.to_c()
         check(lib.b200_hmm_pop_download(self._h, C.byref(soa)), "pop_download")
 
+    def set_utts(self, utt_off):
+        """Split the resident population into utterances (see b200_hmm_pop_set_utts)."""
+        off = _c(utt_off, np.int32)
+        self.n_utt = off.size - 1
+        check(lib.b200_hmm_pop_set_utts(self._h, self.n_utt, _p(off, C.c_int32)), "pop_set_utts")
+
     def step(self, senscr, beam: int, n_hmm: int, want_idx=True):
         """One search frame on the resident population: eval + beam + compaction +
-        active-senone gather.  senscr: host int16[n_sen] or a device pointer."""
+        active-senone gather.  senscr: host int16 [n_utt][n_sen] or a device
+        pointer.  Returns (best, survivors, mask); per-utterance arrays when the
+        population is batched."""
+        nu = getattr(self, "n_utt", 1)
         if isinstance(senscr, np.ndarray):
             s = _c(senscr, np.int16)
             check(lib.b200_hmm_step_host(self._h, _p(s, C.c_int16), int(beam)), "hmm_step_host")
         else:
             check(lib.b200_hmm_step_dev(self._h, senscr, int(beam), None), "hmm_step_dev")
-        best, nk = C.c_int32(), C.c_int32()
+        best, nk = np.zeros(nu, np.int32), np.zeros(nu, np.int32)
         idx = np.zeros(n_hmm, np.int32) if want_idx else None
-        mask = np.zeros((self.n_sen + 31) // 32, np.uint32)
-        check(lib.b200_hmm_step_results(self._h, C.byref(best), C.byref(nk),
+        mask = np.zeros((nu, (self.n_sen + 31) // 32), np.uint32)
+        check(lib.b200_hmm_step_results(self._h, _p(best, C.c_int32), _p(nk, C.c_int32),
                                         _p(idx, C.c_int32) if want_idx else None, _p(mask, C.c_uint32)),
               "hmm_step_results")
-        return best.value, (idx[:nk.value] if want_idx else nk.value), mask
+        if nu == 1:
+            return int(best[0]), (idx[:nk[0]] if want_idx else int(nk[0])), mask[0]
+        return best, (idx[:nk.sum()] if want_idx else nk), mask
 
     def step_dev_async(self, d_senscr: int, beam: int):
         check(lib.b200_hmm_step_dev(self._h, d_senscr, int(beam), None), "hmm_step_dev")

@@ -242,6 +242,13 @@ int  b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h,
 /* Device-resident population for benchmarking / resident search state. */
 int  b200_hmm_pop_upload(b200_hmmctx_t *c, const b200_hmm_soa_t *h);
 int  b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h);
+/* Batched search state: split the resident population into n_utt utterances,
+ * utterance u owning HMMs [utt_off[u], utt_off[u+1]) (utt_off[0] = 0,
+ * utt_off[n_utt] = n_hmm).  Afterwards b200_hmm_step_* take n_utt rows of
+ * senone scores ([n_utt][n_sen]) and produce per-utterance best scores, beam
+ * thresholds, survivor counts and active-senone masks; the survivor list is
+ * ordered by (utterance, HMM index).  pop_upload resets to one utterance. */
+int  b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off);
 /* One frame on the resident population: hmm_vit_eval for every HMM, frame
  * best (max), then beam test bestscore > best + beam
  * (PS/ngram_search_fwdtree.c:741,800) -> keep[n_hmm] uint8 flags and an
@@ -251,9 +258,9 @@ int  b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h);
  * b200_hmm_step_results. */
 int  b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam,
                        void *stream);
-int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep,
+int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best /* [n_utt] */, int32_t *n_keep /* [n_utt] */,
                            int32_t *keep_idx /* [n_hmm] or NULL */,
-                           uint32_t *sen_mask /* [(n_sen+31)/32] or NULL */);
+                           uint32_t *sen_mask /* [n_utt][(n_sen+31)/32] or NULL */);
 /* Host-input convenience for tests: senscr on the host. */
 int  b200_hmm_step_host(b200_hmmctx_t *c, const int16_t *senscr, int32_t beam);
 float b200_hmm_last_ms(const b200_hmmctx_t *c);

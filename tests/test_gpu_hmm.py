@@ -124,3 +124,49 @@ def test_step_beam_compaction_and_active_senones(ne):
     ctx.download(got)
     _assert_pop(got, o)
     ctx.free()
+
+
+def test_batched_utterances_match_independent_decoders():
+    """B utterances sharing one resident population (b200_hmm_pop_set_utts): every
+    utterance must behave exactly like its own decoder -- own senone scores, own
+    best score / beam threshold, own active-senone mask; survivors ordered by
+    (utterance, index)."""
+    ne, n_sen, n_tmat, n_sseq = 3, 2000, 20, 5000
+    sizes = [3000, 1, 0, 777, 2560]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    n = int(off[-1])
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n, ne, n_sen, n_tmat, n_sseq, seed=11, mpx_fraction=0.2)
+    sen = synth.senscr_frames(2 * len(sizes), n_sen, 12).reshape(2, len(sizes), n_sen)
+    beam = -80000
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    ctx.upload(_to_pop(d, ne))
+    ctx.set_utts(off)
+    o = {k: v.copy() for k, v in d.items()}
+    for f in range(2):
+        want_best, want_idx, want_mask = [], [], []
+        for u, sz in enumerate(sizes):
+            sl = slice(int(off[u]), int(off[u + 1]))
+            part = {k: (o[k][sl].copy() if k != "sseq" else o[k]) for k in o}
+            bb = orc.hmm_eval(orc.port.orc_hmm_eval_batch, ne, tp, d["sseq"], sen[f, u], part["score"], part["history"],
+                              part["out_score"], part["out_history"], part["senid"], part["tmatid"], part["mpx"],
+                              part["bestscore"]) if sz else int(b.engine.WORST_SCORE)
+            for k in FIELDS:
+                o[k][sl] = part[k]
+            want_best.append(bb)
+            keep = np.nonzero(part["bestscore"] > bb + beam)[0] if sz else np.zeros(0, np.int64)
+            want_idx.append(keep + int(off[u]))
+            m = np.zeros((n_sen + 31) // 32, np.uint32)
+            for st in range(ne):
+                ids = part["senid"][keep, st].astype(np.int64)
+                mp = part["mpx"][keep].astype(bool)
+                ss = ids[mp]
+                ss = ss[ss != 0xFFFF]
+                allid = np.concatenate([ids[~mp], d["sseq"][ss, st].astype(np.int64)])
+                np.bitwise_or.at(m, allid // 32, (np.uint32(1) << (allid % 32).astype(np.uint32)))
+            want_mask.append(m)
+        best, idx, mask = ctx.step(sen[f], beam, n)
+        np.testing.assert_array_equal(best, np.array(want_best, np.int32))
+        np.testing.assert_array_equal(idx, np.concatenate(want_idx).astype(np.int32))
+        np.testing.assert_array_equal(mask, np.array(want_mask))
+    ctx.free()
