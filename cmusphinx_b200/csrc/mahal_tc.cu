@@ -334,7 +334,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     constexpr int uses = KS / kStages;           // ring passes per tile (1 or 2)
                     const int stage = j % kStages;
                     const uint32_t par = (uses & 1) ? tilepar : (uint32_t)((j / kStages) & 1);
-                    mbar_wait(BAR(A_FULL + stage), par);
+                    if (!(p.dbg & 4)) mbar_wait(BAR(A_FULL + stage), par);
                     tc_fence_after();
                     if (elect_one()) {
                         // descriptor address fields are in 16-byte units
@@ -392,11 +392,13 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     }
                     mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
                     float4 *dst = reinterpret_cast<float4 *>(sA + stage * kAStageBytes);
+                    if (!(p.dbg & 8)) {
                     dst[0 * kTileM + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
                     dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(BAR(A_FULL + stage));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
