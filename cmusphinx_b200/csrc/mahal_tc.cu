@@ -9,47 +9,43 @@
 //                        (fden - mixw) in descending-d order, negate, /aw,
 //                        clamp to int16
 // (the per-frame best-score subtraction of ms_mgau.c:188-204 runs as a
-// separate streaming pass fused with the tile-major -> row-major transpose).
+// separate streaming pass, gmm_launch_normalize-style, fused with the
+// tile-major -> row-major transpose of the scores).
 //
 // GEMM restatement.  d[t,g] = sum_k A[t,k] * B[g,k] with K = 2D+2 columns
 //     k = 0,1      : A = 1             B = (det - sum_i mu^2 v) in two pieces
 //     k = 2+2i     : A = x_i^2         B = -v_i
 //     k = 3+2i     : A = x_i           B = 2 mu_i v_i
-// padded to a multiple of 16.  Scores must be right to about one raw log unit
+// padded to a multiple of 8.  Scores must be right to about one raw log unit
 // in 10^5..10^6, i.e. fp32-class operands: every operand is split into two
 // TF32 numbers (hi + lo, 2 x 11 significant bits) and the product is formed as
 //     Ahi*Bhi + Ahi*Blo + Alo*Bhi          ("TF32x3")
 // with fp32 accumulation in TMEM.  The constant comes first in K so partial
-// sums stay near the final magnitude.  B is stored times -32 (see make_key).
+// sums stay near the final magnitude.
 //
-// Where the operands live (this is what the design is about):
-//   B  resident in SHARED MEMORY for a whole work unit: 192 Gaussians x K,
-//      hi and lo, in the UMMA K-major no-swizzle canonical layout (16-byte
-//      K-chunks, 8-row core matrices, SBO = 128 B, LBO = rows*16 B); HBM holds
-//      it pre-tiled [n_tile][kstep][hi|lo][chunk 0|1][192 rows][4 f32] so a
-//      k-step is one contiguous 12 KB bulk copy.
-//   A  lives in TENSOR MEMORY.  Only the raw features cross L2 (one 20 KB
-//      [40 dims][128 rows] tile per frame tile); four builder warps (thread =
-//      frame row = TMEM lane) expand them to [1,1,x^2,x,..], split hi/lo with
-//      FMA-pipe arithmetic and tcgen05.st them into a 3-slot ring of TMEM
-//      columns.  The MMAs are the TS form (A from TMEM, B from smem).
-//      Streaming A pre-expanded from HBM was L2-bound (40 GB of L2->SM traffic
-//      per 100k-frame step); staging it in shared memory left the kernel
-//      shared-memory-bandwidth-bound (SS-mode MMAs read 12 KB per 128 cycles).
-//   D  two 192-column fp32 accumulators in TMEM (double buffered).
-//   TMEM columns: [0,192) acc0, [192,384) acc1, [384,480) A ring.
+// Data layout in HBM (all pre-tiled so that every shared-memory stage is ONE
+// contiguous bulk copy, in the UMMA K-major no-swizzle canonical layout:
+// 16-byte K-chunks, 8-row core matrices, SBO = 128 B, LBO = rows*16 B):
+//   B  [n_tile][kstep][hi|lo][chunk 0|1][256 rows][4 f32]   16 KB / kstep, static
+//   X  [m_tile][40 dims][128 rows] f32 -- the RAW features, tiled + transposed
+//      (20 KB / frame tile).  The 4x larger [1,1,x^2,x..] hi/lo A operand is
+//      built inside the SM: streaming it pre-expanded made the kernel L2-bound
+//      (40 GB of L2->SM traffic per 100k-frame step)
+//   raw scores, tile-major [n_tile][T_pad][256/M] int16  (coalesced 16 B stores)
 //
-// Kernel (persistent, 1 CTA / SM, 576 threads):
-//   warp 0      bulk-TMA producer (B tile per unit, feature tile per frame tile)
-//   warp 1      MMA issuer: per 2 k-steps one barrier wait, six
-//               tcgen05.mma.cta_group::1.kind::tf32 128x192x8, one commit
-//   warps 2..5  A builders
-//   warps 6..17 epilogue: tcgen05.ld of 64 accumulator columns per thread, the
-//               accumulator is released at once, then integer keys, a sort4 +
-//               bitonic-merge network for the 4 best of each senone, table
-//               log-add from shared memory, int16 stores
+// Kernel (persistent, 1 CTA / SM, 704 threads):
+//   warp 0      bulk-TMA producer: the unit's B tile once (resident, 160 KB),
+//               then one raw feature tile per frame tile
+//   warps 2..5  A builders: thread = frame row; x^2, Veltkamp hi/lo split (all
+//               FMA-pipe ops) written k-step by k-step into a 5-deep A ring
+//   warp 1      single-thread tcgen05.mma issuer, 128x256x8 kind::tf32,
+//               3 MMAs per k-step, two 256-column TMEM accumulators
+//   warps 6..21 epilogue: tcgen05.ld of 64 columns (= two 32-density senones)
+//               per thread, accumulator released immediately, integer keys (trunc(d) << log2 M | density id), top-4 by
+//               a sort4 + bitonic-merge network in registers, table log-add
+//               from shared memory, int16 stores
 // A work unit is (n_tile, frame-range); units are ordered so that concurrently
-// running CTAs stream the same feature tiles against different B tiles.
+// running CTAs stream the same A tiles (L2 reuse) against different B tiles.
 #include "gmm_dev.cuh"
 
 #include <cmath>
@@ -62,26 +58,28 @@ namespace b200 {
 namespace {
 
 constexpr int kTileM = 128;           // frames per tile (UMMA M)
-constexpr int kTileN = 192;           // Gaussians per tile (UMMA N)
-constexpr int kBStageBytes = 2 * 2 * kTileN * 16;   // hi|lo x 2 chunks x 192 rows x 16 B = 12 KB per k-step
+constexpr int kTileN = 256;           // Gaussians per tile (UMMA N)
+// A ring depth (k-steps).  Chosen so that a tile's k-steps map to ring slots
+// statically (slot = j % depth): the MMA issue loop is then fully unrolled with
+// compile-time descriptor offsets -- the issuing thread is a serial resource.
+constexpr int ring_depth(int ks) { return ks == 10 ? 5 : ks; }
+constexpr int kAStageBytes = 2 * 2 * kTileM * 16;   // hi|lo x 2 chunks x 128 rows x 16 B = 8 KB
+constexpr int kBStageBytes = 2 * 2 * kTileN * 16;   // 16 KB per k-step
 constexpr int kMaxKSteps = 10;        // K <= 80  (D <= 39)
 constexpr int kBuildWarps = 4;        // A-operand builders: one thread per frame row
-constexpr int kEpiWarps = 12;         // 3 per TMEM lane quarter, 64 accumulator columns each
+constexpr int kEpiWarps = 16;         // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kFirstEpiWarp = 2 + kBuildWarps;
 constexpr int kThreads = (2 + kBuildWarps) * 32 + kEpiThreads;
-constexpr int kColsPerEpiThread = 64;
+constexpr int kColsPerEpiThread = kTileN / (kEpiWarps / 4);   // 64
 constexpr uint32_t kTmemCols = 512;
-constexpr int kASlots = 3;            // A ring: slots of 2 k-steps
-constexpr int kASlotCols = 32;        // [k0 hi 8][k0 lo 8][k1 hi 8][k1 lo 8]
-constexpr uint32_t kAColBase = 2 * kTileN;   // 384
 
 struct TcParams {
     const float *gB;        // pre-tiled B operand
     const float *gX;        // features, tiled + transposed: [m_tile][4*ksteps dims][128 rows]
-    const uint8_t *gMixw;   // [n_tiles_n][192] mixture weights in tile row order
-    int16_t *raw;           // [n_tiles_n][T_pad][rs]
-    int T, T_pad, n_sen, n_tiles_m, n_tiles_n, m_chunks, tiles_per_chunk, n_units, aw, rs;
+    const uint8_t *gMixw;   // [n_tiles_n][256] mixture weights in tile row order
+    int16_t *raw;           // [n_tiles_n][T_pad][spt]
+    int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
     int m31;                // the constant 31, kept opaque to the compiler (see make_key)
     int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
     uint8_t logadd[256];
@@ -99,22 +97,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the
-// phase completes (or the hint expires) instead of burning issue slots.
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Wait with a watchdog: a protocol bug must trap, not hang the GPU box.
+// Spin with a watchdog: a protocol bug must trap, not hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if (++spins > 4000000u) __trap();
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -135,14 +133,13 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred)::"memory");
     return pred != 0;
 }
-// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32 (the "TS" form).
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                               uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -156,19 +153,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr),
-          "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
-          "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
-          "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
-          "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
 // [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=0.
@@ -209,9 +193,9 @@ __device__ __forceinline__ void merge4(int32_t (&top)[4], int32_t a, int32_t b, 
 // Gaussians (|d| > 6.7e7) compare as "worst" instead of wrapping.
 // (For d > 0 with a fractional part >= 1/32 the recovered integer is
 // trunc(d)+1; it changes fden only when that integer is a multiple of 1024.)
+constexpr float kAccScale = 32.0f;
 // `m31` is the constant 31 passed as a run-time value so that the compiler
 // emits ONE three-input LOP3 ((j | m31) ^ id, id immediate) instead of two.
-constexpr float kAccScale = 32.0f;
 __device__ __forceinline__ int32_t make_key(uint32_t bits, int id, int32_t m31) {
     return (__float2int_rz(__uint_as_float(bits)) | m31) ^ id;
 }
@@ -250,6 +234,7 @@ tc_prep_kernel(const float *__restrict__ feat, int T, int D, int Dp, float *__re
     __shared__ float tile[kTileM][41];
     const int mt = blockIdx.x, r = threadIdx.x;
     const int t0 = mt * kTileM;
+    // coalesced read of the tile's rows (contiguous block of min(128, T-t0)*D floats)
     const int nrow = min(kTileM, T - t0);
     for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)t0 * D + e];
     __syncthreads();
@@ -268,18 +253,20 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
 template <int M, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
-    static_assert(KS % 2 == 0, "k-steps are consumed in pairs");
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int SPT = kTileN / M;       // senones per tile
+    constexpr int kStages = ring_depth(KS);
     constexpr int DP = 4 * KS;            // padded dims per frame in the X tile
     constexpr int kXBytes = DP * kTileM * 4;
-    constexpr int KP2 = KS / 2;           // k-step pairs per tile
-    uint8_t *sB = smem;                                         // KS * 12 KB
-    uint8_t *sX = sB + KS * kBStageBytes;                       // DP * 128 * 4
-    uint8_t *sMixw = sX + kXBytes;                              // 192 B (reversed per senone)
+    uint8_t *sB = smem;                                         // KS * 16 KB
+    uint8_t *sA = sB + KS * kBStageBytes;                       // kStages * 8 KB
+    uint8_t *sX = sA + kStages * kAStageBytes;                  // DP * 128 * 4
+    uint8_t *sMixw = sX + kXBytes;                              // 256 B
     uint8_t *sTab = sMixw + 256;                                // 256 B
     uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256);
-    constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kASlots,
-                  T_FULL = 4 + 2 * kASlots, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
+    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2]
+    constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kStages,
+                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -291,8 +278,8 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         mbar_init(BAR(B_EMPTY), 1);
         mbar_init(BAR(X_FULL), 1);
         mbar_init(BAR(X_EMPTY), kBuildWarps);
-        for (int s = 0; s < kASlots; ++s) { mbar_init(BAR(A_FULL + s), kBuildWarps); mbar_init(BAR(A_EMPTY + s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), kEpiWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), kBuildWarps); mbar_init(BAR(A_EMPTY + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), kEpiThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -306,17 +293,21 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    constexpr int ksteps = KS;
+
     if (warp == 0) {
         // ===================== producer =====================
+        // Bulk-TMA: the unit's B tile (resident for the whole unit), then one raw
+        // feature tile (DP x 128 fp32) per frame tile.
         if (lane == 0) {
             uint32_t xphase = 0, bphase = 0;
             for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
                 const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
                 const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
                 mbar_wait(BAR(B_EMPTY), bphase ^ 1);
-                mbar_expect_tx(BAR(B_FULL), (uint32_t)KS * kBStageBytes);
-                const uint8_t *gb = reinterpret_cast<const uint8_t *>(p.gB) + (size_t)nt * KS * kBStageBytes;
-                for (int j = 0; j < KS; ++j)
+                mbar_expect_tx(BAR(B_FULL), (uint32_t)ksteps * kBStageBytes);
+                const uint8_t *gb = reinterpret_cast<const uint8_t *>(p.gB) + (size_t)nt * ksteps * kBStageBytes;
+                for (int j = 0; j < ksteps; ++j)
                     bulk_g2s(smem_u32(sB + j * kBStageBytes), gb + (size_t)j * kBStageBytes, kBStageBytes, BAR(B_FULL));
                 bphase ^= 1;
                 for (int mt = mt0; mt < mt1; ++mt) {
@@ -330,10 +321,12 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // The whole warp walks the unrolled loop (uniform control flow); one
-        // elected lane issues.  B descriptors are base + compile-time offsets.
-        uint32_t bphase = 0, accphase = 0, aphase = 0;
-        int acc = 0, slot = 0;
+        // The whole warp walks the (fully unrolled) loop so control flow stays
+        // uniform; one elected lane issues.  Ring slot and barrier parity of
+        // k-step j are compile-time, descriptors are base + constant.
+        uint32_t bphase = 0, accphase = 0, tilepar = 0;
+        int acc = 0;
+        const uint64_t dA0 = make_desc(smem_u32(sA), kTileM * 16, 128);
         const uint64_t dB0 = make_desc(smem_u32(sB), kTileN * 16, 128);
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int mc = u / p.n_tiles_n;
@@ -345,30 +338,29 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTileN;
 #pragma unroll
-                for (int j2 = 0; j2 < KP2; ++j2) {
-                    mbar_wait(BAR(A_FULL + slot), aphase);
+                for (int j = 0; j < KS; ++j) {
+                    constexpr int uses = KS / kStages;           // ring passes per tile (1 or 2)
+                    const int stage = j % kStages;
+                    const uint32_t par = (uses & 1) ? tilepar : (uint32_t)((j / kStages) & 1);
+                    mbar_wait(BAR(A_FULL + stage), par);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a0 = tmem_base + kAColBase + (uint32_t)slot * kASlotCols;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int j = 2 * j2 + h;
-                            const uint32_t aHi = a0 + h * 16, aLo = aHi + 8;
-                            // descriptor address fields are in 16-byte units
-                            const uint64_t dBhi = dB0 + (uint64_t)((j * kBStageBytes) >> 4);
-                            const uint64_t dBlo = dBhi + (uint64_t)((kBStageBytes / 2) >> 4);
-                            tc_mma_tf32_ts(d_tmem, aHi, dBhi, kIdesc, j > 0 ? 1u : 0u);
-                            if (!(p.dbg & 2)) {
-                                tc_mma_tf32_ts(d_tmem, aHi, dBlo, kIdesc, 1u);
-                                tc_mma_tf32_ts(d_tmem, aLo, dBhi, kIdesc, 1u);
-                            }
+                        // descriptor address fields are in 16-byte units
+                        const uint64_t dAhi = dA0 + (uint64_t)((stage * kAStageBytes) >> 4);
+                        const uint64_t dAlo = dAhi + (uint64_t)((kAStageBytes / 2) >> 4);
+                        const uint64_t dBhi = dB0 + (uint64_t)((j * kBStageBytes) >> 4);
+                        const uint64_t dBlo = dBhi + (uint64_t)((kBStageBytes / 2) >> 4);
+                        tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
+                        if (!(p.dbg & 2)) {
+                            tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
+                            tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
                         }
-                        tc_commit(BAR(A_EMPTY + slot));
-                        if (j2 == KP2 - 1) tc_commit(BAR(T_FULL + acc));
+                        tc_commit(BAR(A_EMPTY + stage));
+                        if (j == KS - 1) tc_commit(BAR(T_FULL + acc));
                     }
                     __syncwarp();
-                    if (++slot == kASlots) { slot = 0; aphase ^= 1; }
                 }
+                if ((KS / kStages) & 1) tilepar ^= 1;
                 if (++acc == 2) { acc = 0; accphase ^= 1; }
             }
             if (elect_one()) tc_commit(BAR(B_EMPTY));
@@ -376,13 +368,12 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         }
     } else if (warp < kFirstEpiWarp) {
         // ===================== A-operand builders (4 warps) =====================
-        // Thread = frame row = TMEM lane (a warp may only touch the lane quarter
-        // warp%4).  The row's DP features sit in registers; per pair of k-steps
-        // the thread forms [1,1,x^2,x,...], splits hi/lo and stores 32 columns.
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
+        // Thread r owns frame row r of the tile: it keeps the row's DP features in
+        // registers and, k-step by k-step, writes [1,1,x^2,x,...] split into TF32
+        // hi/lo straight into the UMMA K-major layout of the A ring.
+        const int r = threadIdx.x - 64;                  // 0..127
         const float *xs = reinterpret_cast<const float *>(sX);
-        int slot = 0; uint32_t aphase = 0, xphase = 0;
+        int stage = 0; uint32_t phase = 0, xphase = 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int mc = u / p.n_tiles_n;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
@@ -395,47 +386,43 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(X_EMPTY));     // staging buffer may be refilled
 #pragma unroll
-                for (int j2 = 0; j2 < KP2; ++j2) {
-                    float v[32];
+                for (int j = 0; j < KS; ++j) {
+                    float hi[8], lo[8];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const int k = (2 * j2 + h) * 8 + kk;
-                            float hi, lo;
-                            if (k < 2) { hi = 1.f; lo = 0.f; }
-                            else {
-                                const int i = (k - 2) >> 1;              // i < DP by construction
-                                const float a = ((k - 2) & 1) ? x[i] : __fmul_rn(x[i], x[i]);
-                                split_tf32(a, hi, lo);
-                            }
-                            v[h * 16 + kk] = hi;
-                            v[h * 16 + 8 + kk] = lo;
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = j * 8 + kk;
+                        if (k < 2) { hi[kk] = 1.f; lo[kk] = 0.f; }
+                        else {
+                            const int i = (k - 2) >> 1;              // i < DP by construction
+                            const float a = ((k - 2) & 1) ? x[i] : __fmul_rn(x[i], x[i]);
+                            split_tf32(a, hi[kk], lo[kk]);
                         }
                     }
-                    mbar_wait(BAR(A_EMPTY + slot), aphase ^ 1);
-                    tc_fence_after();
-                    tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + kAColBase + (uint32_t)slot * kASlotCols, v);
-                    tmem_st_wait();
-                    tc_fence_before();
+                    mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
+                    float4 *dst = reinterpret_cast<float4 *>(sA + stage * kAStageBytes);
+                    dst[0 * kTileM + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                    dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR(A_FULL + slot));
-                    if (++slot == kASlots) { slot = 0; aphase ^= 1; }
+                    if (lane == 0) mbar_arrive(BAR(A_FULL + stage));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else {
-        // ===================== epilogue (12 warps) =====================
-        // Warp w may read TMEM lanes 32*(w%4)..+31 only; the three warps of a lane
-        // quarter split the 192 accumulator columns into 64-column groups.  Each
+        // ===================== epilogue (16 warps) =====================
+        // Warp w may read TMEM lanes 32*(w%4)..+31 only; the four warps of a lane
+        // quarter split the 256 accumulator columns into 64-column groups.  Each
         // thread pulls its 64 columns into registers, releases the accumulator
         // at once (the MMA warp can start the tile after next) and only then
         // does the selection / log-add arithmetic.
         constexpr int CPT = kColsPerEpiThread;           // columns per thread
         constexpr int SPE = CPT / M;                     // senones per thread
-        const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..383
+        const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..511
         const int q = warp & 3;
-        const int cg = (warp - kFirstEpiWarp) >> 2;      // column group 0..2
+        const int cg = (warp - kFirstEpiWarp) >> 2;      // column group 0..3
         const int row = q * 32 + lane;                   // frame row in the tile
         int acc = 0; uint32_t accphase = 0;
         const int32_t m31 = p.m31;
@@ -449,7 +436,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 sMixw[sl * M + (M - 1 - dens)] = p.gMixw[(size_t)nt * kTileN + et];
             }
             epi_bar();
-            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * p.rs;
+            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
             // key & 31 = 31 - id = (32 - M) + (M - 1 - id): bias the table pointer for M < 32
             const uint8_t *mixw_t = sMixw + cg * CPT - (32 - M);
             for (int mt = mt0; mt < mt1; ++mt) {
@@ -487,7 +474,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 }
                 const int t = mt * kTileM + row;
                 if (t < p.T) {
-                    int16_t *dst = rawt + (size_t)t * p.rs + cg * SPE;
+                    int16_t *dst = rawt + (size_t)t * SPT + cg * SPE;
                     if (SPE == 2) {
                         *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(res);
                     } else if (SPE == 4) {
@@ -512,21 +499,20 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
 }
 
 // Tile-major raw scores -> row-major [T][n_sen], optionally minus the frame's
-// best (ms_mgau.c:188-204).  raw holds rs int16 per (n-tile, frame) of which the
-// first spt are senones.  One block per kFinFrames frames; every thread owns a
-// fixed (frame, 16-byte group) and walks the n-tiles, so reads are contiguous
-// runs and all global traffic is 16-byte vectors.
-// Requires rs % 8 == 0, spt even, n_sen % 8 == 0 (else the generic kernel).
+// best (ms_mgau.c:188-204).  One block per kFinFrames frames; every thread owns
+// a fixed (frame, 16-byte column group) and walks the n-tiles, so reads are
+// contiguous runs of kFinFrames*spt int16 and all traffic is 16-byte vectors.
+// Requires spt % 8 == 0 and n_sen % 8 == 0 (else the generic kernel below).
 constexpr int kFinFrames = 4;
 __global__ void __launch_bounds__(256)
-tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int rs, int n_tiles_n,
+tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
                      int subtract_best, int16_t *__restrict__ out) {
-    extern __shared__ __align__(16) int16_t s_rows[];   // [kFinFrames][stride], compact senone order
+    extern __shared__ __align__(16) int16_t s_rows[];   // [kFinFrames][stride]
     __shared__ int s_best[kFinFrames];
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * kFinFrames;
-    const int stride = (n_tiles_n * spt + 7) & ~7;
-    const int q = rs >> 3;                               // uint4 per (tile, frame)
+    const int stride = n_tiles_n * spt;                  // padded senone count (multiple of 8)
+    const int q = spt >> 3;                              // uint4 per (tile, frame)
     const int group = kFinFrames * q;                    // threads covering one n-tile
     const int f = (tid % group) / q, k = tid % q;
     const int nt_step = 256 / group;
@@ -535,18 +521,15 @@ tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_se
     int32_t best = 0x7fffffff;
     if (t0 + f < T) {
         for (int nt = tid / group; nt < n_tiles_n; nt += nt_step) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(raw + ((size_t)nt * T_pad + t0 + f) * rs + 8 * k);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t *dst = reinterpret_cast<uint32_t *>(s_rows + (size_t)f * stride + nt * spt + 8 * k);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int sl = 8 * k + 2 * e;            // senone slot inside the tile (pairs)
-                if (sl < spt) {
-                    dst[e] = w[e];
-                    const int s = nt * spt + sl;
-                    if (s < n_sen) best = min(best, (int32_t)(int16_t)(w[e] & 0xffff));
-                    if (s + 1 < n_sen) best = min(best, (int32_t)(int16_t)(w[e] >> 16));
-                }
+            const uint4 v = *reinterpret_cast<const uint4 *>(raw + ((size_t)nt * T_pad + t0 + f) * spt + 8 * k);
+            *reinterpret_cast<uint4 *>(s_rows + (size_t)f * stride + nt * spt + 8 * k) = v;
+            if (nt * spt + 8 * k + 8 <= n_sen) {
+                uint32_t m = __vmins2(__vmins2(v.x, v.y), __vmins2(v.z, v.w));
+                best = min(best, min((int32_t)(int16_t)(m & 0xffff), (int32_t)(int16_t)(m >> 16)));
+            } else {
+                const int16_t *h = reinterpret_cast<const int16_t *>(&v);
+                for (int e = 0; e < 8; ++e)
+                    if (nt * spt + 8 * k + e < n_sen) best = min(best, (int32_t)h[e]);
             }
         }
         if (subtract_best) atomicMin(&s_best[f], best);
@@ -566,10 +549,10 @@ tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_se
     }
 }
 
-// Generic (any shape) version of the same pass.
+// Generic (any spt / n_sen) version of the same pass.
 constexpr int kNormFrames = 8;
 __global__ void __launch_bounds__(256)
-tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int rs, int n_tiles_n,
+tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
                  int subtract_best, int16_t *__restrict__ out) {
     extern __shared__ __align__(16) int16_t s_rows[];   // [8][stride]
     __shared__ int s_best[kNormFrames];
@@ -585,7 +568,7 @@ tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, i
         const int f = rem / spt, k = rem - f * spt;
         const int s = nt * spt + k;
         if (f < nf && s < n_sen) {
-            const int16_t v = raw[((size_t)nt * T_pad + t0 + f) * rs + k];
+            const int16_t v = raw[((size_t)nt * T_pad + t0 + f) * spt + k];
             s_rows[f * stride + s] = v;
             if (subtract_best) atomicMin(&s_best[f], (int32_t)v);
         }
@@ -613,7 +596,7 @@ float tf32_round(float x) {
 
 struct TcPlan {
     int device = 0;
-    int M = 0, D = 0, S = 0, ksteps = 0, spt = 0, rs = 0, n_tiles_n = 0;
+    int M = 0, D = 0, S = 0, ksteps = 0, spt = 0, n_tiles_n = 0;
     float *dB = nullptr;
     uint8_t *dMixw = nullptr;
     float *dA = nullptr; size_t a_cap = 0;       // tiled/transposed features (bytes)
@@ -651,9 +634,8 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     p->M = g.n_density; p->D = g.featlen[0]; p->S = g.n_sen; p->aw = g.aw;
     const int K = 2 * p->D + 2;
     const int need = (K + 7) / 8;
-    p->ksteps = need <= 4 ? 4 : (need <= 8 ? 8 : 10);   // instantiated (even) k-step counts
+    p->ksteps = need <= 4 ? 4 : (need <= 7 ? 7 : 10);   // instantiated k-step counts
     p->spt = kTileN / p->M;
-    p->rs = (p->spt + 7) & ~7;
     p->n_tiles_n = (p->S + p->spt - 1) / p->spt;
     memcpy(p->logadd, g.logadd, 256);
     const int KP = p->ksteps * 8, M = p->M, D = p->D;
@@ -692,7 +674,7 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
                 else if (k == 1) { hi = (float)hi2; lo = (float)lo2; }
                 else { hi = tf32_round((float)col[k]); lo = tf32_round((float)(col[k] - (double)hi)); }
                 const int j = k / 8, c = (k % 8) / 4, e = k % 4;
-                // [kstep][hi|lo][chunk][192 rows][4]
+                // [kstep][hi|lo][chunk][256 rows][4]
                 float *st = tile + (size_t)j * (kBStageBytes / 4);
                 st[((0 * 2 + c) * kTileN + r) * 4 + e] = hi;
                 st[((1 * 2 + c) * kTileN + r) * 4 + e] = lo;
@@ -713,7 +695,8 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
 
 template <int M, int KS>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
-    const size_t smem = (size_t)KS * kBStageBytes + (size_t)4 * KS * kTileM * 4 + 512 + 32 * 8 + 16;
+    const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
+                        (size_t)4 * KS * kTileM * 4 + 512 + 32 * 8 + 16;
     static bool attr = false;
     if (!attr) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -728,7 +711,7 @@ template <int M>
 static int launch_score_ks(const TcParams &prm, int ks, int grid, cudaStream_t st) {
     switch (ks) {
         case 4: return launch_score<M, 4>(prm, grid, st);
-        case 8: return launch_score<M, 8>(prm, grid, st);
+        case 7: return launch_score<M, 7>(prm, grid, st);
         case 10: return launch_score<M, 10>(prm, grid, st);
     }
     set_error("tensor-core path: %d k-steps unsupported", ks);
@@ -740,7 +723,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     const int T_pad = n_tiles_m * kTileM;
     const int Dp = 4 * p->ksteps;
     const size_t a_bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
-    const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->rs * sizeof(int16_t);
+    const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->spt * sizeof(int16_t);
     if (p->a_cap < a_bytes) {
         cudaFree(p->dA); p->dA = nullptr; p->a_cap = 0;
         B200_CUDA_OK(cudaMalloc((void **)&p->dA, a_bytes));
@@ -758,7 +741,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     TcParams prm;
     prm.gB = p->dB; prm.gX = p->dA; prm.gMixw = p->dMixw; prm.raw = p->dRaw;
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
-    prm.aw = p->aw; prm.rs = p->rs;
+    prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
     prm.m31 = 31;
     // split the frame axis so that there are >= ~16 units per CTA, but never
@@ -782,24 +765,24 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
 }
 
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
+    const size_t stride = (size_t)p->n_tiles_n * p->spt;
     static bool attr = false;
     if (!attr) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    const bool vec = (p->rs % 8 == 0) && (p->spt % 2 == 0) && (p->S % 8 == 0) &&
-                     ((reinterpret_cast<size_t>(d_out) & 15) == 0) && (256 % (kFinFrames * (p->rs / 8)) == 0);
+    const bool vec = (p->spt % 8 == 0) && (p->S % 8 == 0) && ((reinterpret_cast<size_t>(d_out) & 15) == 0) &&
+                     (256 % (kFinFrames * (p->spt / 8)) == 0);
     if (vec) {
-        const size_t stride = ((size_t)p->n_tiles_n * p->spt + 7) & ~(size_t)7;
-        const size_t sh = (size_t)kFinFrames * stride * sizeof(int16_t) + 64;
+        const size_t sh = (size_t)kFinFrames * stride * sizeof(int16_t);
         if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
-        tc_finish_vec_kernel<<<(T + kFinFrames - 1) / kFinFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt, p->rs,
+        tc_finish_vec_kernel<<<(T + kFinFrames - 1) / kFinFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
                                                                                  p->n_tiles_n, subtract_best, d_out);
     } else {
-        const size_t sh = (size_t)kNormFrames * p->n_tiles_n * p->spt * sizeof(int16_t);
+        const size_t sh = (size_t)kNormFrames * stride * sizeof(int16_t);
         if (sh > 200 * 1024) { set_error("n_sen too large for the finish kernel"); return B200_ERR_UNSUP; }
-        tc_finish_kernel<<<(T + kNormFrames - 1) / kNormFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt, p->rs,
+        tc_finish_kernel<<<(T + kNormFrames - 1) / kNormFrames, 256, sh, st>>>(p->dRaw, T, T_pad, p->S, p->spt,
                                                                                p->n_tiles_n, subtract_best, d_out);
     }
     B200_LAUNCH_CHECK();
