@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""bench_ptm.py -- BASELINE.json configs[2]: ptm_mgau, 256 phonetic codebooks x
+4096 densities x 39 dims, 5000 senone mixture-weight rows, top-4 fast-eval, one
+B200.  Secondary benchmark; one JSON line.  Round 1 runs the codebook stage on
+the exact CUDA-core kernel (bit-exact integer top-N); the tensor-core GEMM of
+bench.py with a per-codebook top-N epilogue is the planned replacement."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+C, M, D, S = 256, 4096, 39, 5000
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import cmusphinx_b200 as b
+    from cmusphinx_b200.engine import LOGBASE
+    rng = np.random.default_rng(1234)
+    mean = rng.standard_normal((C, M * D)).astype(np.float32)
+    var = np.exp(rng.uniform(np.log(0.05), np.log(5.0), (C, M * D))).astype(np.float32)
+    pv, pd = b.gauden_precompute(var.reshape(-1, D), D, 1e-4, LOGBASE)
+    mixw = rng.integers(0, 160, (1, M, S)).astype(np.uint8)
+    s2c = (np.arange(S) * C // S).astype(np.uint8)
+    cfg = b.MgauConfig(C, 1, M, S, [D], topn=4, logbase=LOGBASE)
+    m = b.ptm_from_arrays(cfg, mean, pv.reshape(C, -1), pd.reshape(C, 1, M), mixw, s2c)
+    T = args.frames
+    feat = torch.from_numpy((rng.standard_normal((T, D)) * 1.5).astype(np.float32)).cuda()
+    out = torch.empty((T, S), dtype=torch.int16, device="cuda")
+    m.score_dev(feat.data_ptr(), T, out.data_ptr())
+    ms = []
+    for _ in range(args.steps):
+        m.score_dev(feat.data_ptr(), T, out.data_ptr())
+        ms.append(m.last_ms(0))
+    t = float(np.mean(ms))
+    flop = 4.0 * D * C * M       # per frame
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1325.0
+    ach = flop * T / (t / 1e3) / 1e12
+    print(json.dumps({"metric": "frames_x_senones_scored_per_sec", "value": T * S / (t / 1e3), "unit": "frame*senones/s",
+                      "n_gpus": 1, "steps": args.steps, "ms_per_step": t, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"ptm_mgau {C} codebooks x {M} densities x {D} dims, {S} senones, topn 4, "
+                                             f"{T} frames/step (BASELINE configs[2])", "kernel_path": "exact CUDA-core"},
+                      "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                   "algorithmic_flop_per_unit": flop / S, "traffic": None},
+                      "checksum": int(out[:8].to(torch.int64).sum().item())}))
+    m.free()
+
+
+if __name__ == "__main__":
+    main()

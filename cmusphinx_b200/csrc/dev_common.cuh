@@ -41,11 +41,18 @@ __device__ __forceinline__ int32_t logadd_tab(const uint8_t *tab, int32_t x, int
     return r + (int32_t)tab[d];
 }
 
-// tied_mgau_common.h:104-121 fast_logmath_add on negated scores.
+// tied_mgau_common.h:104-121 fast_logmath_add on negated scores.  The reference
+// indexes its 256-byte table with |x - y| unchecked; ptm_mgau.c:267-288
+// normalises with the MINIMUM of the codebooks' top-1 scores, so normalised
+// scores go negative and |x - y| can exceed 255 -- the reference then reads
+// whatever follows the table on its heap (its scores become history dependent;
+// measured: 8 % of PTM scores differ between a fresh decoder and one that has
+// already decoded another utterance).  We return the intended value instead:
+// beyond the table the correction term is 0.
 __device__ __forceinline__ int32_t fast_logadd_neg(const uint8_t *tab, int32_t mlx, int32_t mly) {
     int32_t d, r;
     if (mlx > mly) { d = mlx - mly; r = mly; } else { d = mly - mlx; r = mlx; }
-    return r - (int32_t)tab[d & 255];
+    return r - (d < 256 ? (int32_t)tab[d] : 0);
 }
 
 __device__ __forceinline__ int32_t clamp16(int32_t v) {

@@ -104,14 +104,18 @@ orc_logmath_add(const orc_logmath_t *lm, int32_t x, int32_t y)
     return r + (int32_t)lm->table[d];
 }
 
-/* tied_mgau_common.h:104-121 */
+/* tied_mgau_common.h:104-121.  NB the reference does NOT range-check d: with
+ * ptm's min-normalisation (ptm_mgau.c:267-288) d can exceed the 256-entry
+ * table and the reference reads past it (heap-dependent garbage).  The oracle
+ * returns the intended value (correction 0 beyond the table), so oracle ==
+ * reference only on frames where the reference stays inside its table. */
 static int
 fast_add(const orc_logmath_t *lm, int mlx, int mly)
 {
     int d, r;
     if (mlx > mly) { d = mlx - mly; r = mly; }
     else { d = mly - mlx; r = mlx; }
-    return r - (int)lm->table[d];
+    return r - ((unsigned)d < lm->table_size ? (int)lm->table[d] : 0);
 }
 
 /* ------------------------------------------------------ load-time precompute */

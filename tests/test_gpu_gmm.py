@@ -234,3 +234,117 @@ def test_full_size_properties():
         np.testing.assert_array_equal(m.score(feat[perm]), full[perm])
         np.testing.assert_array_equal(m.score(feat[9000:9777]), full[9000:9777])
     m.free()
+
+
+@pytest.mark.parametrize("S,M,D,T", [(64, 32, 39, 300), (250, 8, 39, 515), (100, 16, 13, 129), (37, 32, 20, 77),
+                                     (4999, 32, 39, 130)])
+def test_tensor_core_path_within_one_of_exact(S, M, D, T):
+    """tcgen05 path (TF32x3 + integer-key epilogue) against the exact path, which is
+    itself bit-exact against the oracle: max |d| <= 1 (north_star tolerance), and
+    the disagreement rate stays at the log-add quantisation noise floor.  Shapes
+    cover all template instantiations (M = 8/16/32, 4/8/10 k-steps), padded
+    tiles, ragged frame counts and an n_sen that forces the generic finish pass."""
+    mean, var, mixw = synth.cont_model(S, M, D, 31)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+    assert m.path == 1, "tensor-core path should be the default for this shape"
+    feat = synth.cont_features(mean, var, T, 32)
+    got = m.score(feat)
+    m.set_path(0)
+    want = m.score(feat)
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    print(f"S={S} M={M} D={D} T={T}: mismatch {float((diff != 0).mean()):.2e} max {diff.max()}")
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2
+    if S <= 250:
+        pm = orc.PortMs(S, 1, [D], M, S, 4, 1, mean, pv, pd, q, np.arange(S), orc.LOGBASE)
+        np.testing.assert_array_equal(want, pm.eval_all(feat))
+    # un-normalised serving path (utt_begin/utt_frame) goes through the same kernels
+    m.set_path(1)
+    m.utt_begin(feat[:40])
+    row = np.zeros(S, np.int16)
+    m.utt_frame(row, None, 0, 7, True)
+    assert np.abs(row.astype(np.int32) - want[7].astype(np.int32)).max() <= 1
+    m.free()
+
+
+def test_tensor_core_path_unsupported_shapes_fall_back_loudly():
+    mean, var, mixw = synth.cont_model(40, 32, 39, 3)
+    pv, pd = orc.port_precompute(var.reshape(-1, 39), 39, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(40, 1, 32, 40, [39], topn=3, logbase=orc.LOGBASE)   # topn != 4
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(40))
+    assert m.path == 0
+    with pytest.raises(b.B200Error, match="unavailable"):
+        m.set_path(1)
+    m.free()
+
+
+def test_config3_ptm_shape_vs_oracle():
+    """BASELINE config 3 shape: 256 codebooks x 4096 densities x 39 dims, 5000
+    senones, 8-bit mixw, topn 4 -- a few frames against the (sequential) oracle.
+    Every codebook holds the same Gaussians in a different order, so all
+    codebooks share one top-1 score and the normalised scores stay inside the
+    0..96 range that the reference's fast_logmath_add assumes (tied_mgau_common.h:
+    82-85; random codebooks drive the REFERENCE itself out of its table)."""
+    rng = np.random.default_rng(9)
+    C, Mden, D, S, T = 256, 4096, 39, 5000, 3
+    base_m = rng.standard_normal((Mden, D)).astype(np.float32)
+    base_v = np.exp(rng.uniform(np.log(0.05), np.log(5.0), (Mden, D))).astype(np.float32)
+    mean = np.empty((C, Mden * D), np.float32)
+    var = np.empty((C, Mden * D), np.float32)
+    for c in range(C):
+        perm = rng.permutation(Mden)
+        mean[c] = base_m[perm].reshape(-1)
+        var[c] = base_v[perm].reshape(-1)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    pv = pv.reshape(C, -1)
+    pd = pd.reshape(C, 1, Mden)
+    mixw = rng.integers(0, 160, (1, Mden, S)).astype(np.uint8)
+    s2c = (np.arange(S) * C // S).astype(np.uint8)
+    feat = (base_m[rng.integers(0, Mden, T)] + rng.standard_normal((T, D)) * 0.3).astype(np.float32)
+    pt = orc.PortTied(1, C, 1, [D], Mden, S, 4, mean, pv, pd, mixw, 0, None, s2c, orc.LOGBASE)
+    want = []
+    for t in range(T):
+        pt.reset()
+        want.append(pt.frame_eval(feat[t], None, True, 0))
+    cfg = b.MgauConfig(C, 1, Mden, S, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ptm_from_arrays(cfg, mean, pv, pd, mixw, s2c)
+    got = m.score(feat)
+    np.testing.assert_array_equal(got, np.stack(want))
+    m.free()
+
+
+def test_ptm_speech_frames_bit_exact_vs_oracle():
+    """200 speech frames of the real 50-codebook PTM model: GPU == oracle port,
+    bit for bit, dense and with codebook pruning (the reference itself is not a
+    usable yardstick there, see test_reference_ptm_reads_past_its_logadd_table)."""
+    name = "ptm_hub4wsj.npz"
+    if not cases.have_model(name) or not orc.have_ref():
+        pytest.skip("model files / oracle/_ref not present")
+    g = cases.load(name)
+    hmm = cases.model_dir(name)
+    r = orc.RefAcmod(hmm)
+    feat = r.cep2feat(orc.read_mfc(os.path.join(orc.DATA_DIR, "test", "wsj", "441c0201.mfc")))[:200]
+    r.close()
+    gm, gv, sd, n_sen = cases.tied_arrays(name, g)
+    pv, pd = orc.port_precompute(gv["data"].reshape(-1, 13), 13, 1e-4, orc.LOGBASE)
+    pt = orc.PortTied(1, 50, 3, [13, 13, 13], gm["n_density"], n_sen, 4, gm["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], g["sen2cb"], orc.LOGBASE)
+    want = pt.eval_all(feat)
+    m = _tied_product(name, g, 1)
+    np.testing.assert_array_equal(m.score(feat), want)
+    pt.reset()
+    m.utt_begin(feat)
+    rng = np.random.default_rng(8)
+    for t in range(120, 160):
+        mask = np.zeros((n_sen + 31) // 32, np.uint32)
+        cbs = rng.choice(50, 9, replace=False)
+        for s in np.nonzero(np.isin(g["sen2cb"], cbs))[0][::2]:
+            mask[s // 32] |= np.uint32(1 << (s % 32))
+        dl = orc.port_flags2list(mask, n_sen)
+        got = np.zeros(n_sen, np.int16)
+        m.utt_frame(got, dl, dl.size, t, False)
+        np.testing.assert_array_equal(got, pt.frame_eval(feat[t], dl, False, t))
+    m.free()
