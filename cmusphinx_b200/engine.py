@@ -117,6 +117,17 @@ def read_tmat(path: str) -> np.ndarray:
     return _read4(lib.b200_s3_read_tmat, path)
 
 
+def read_s3_cont_arrays(meanfile: str, varfile: str, mixwfile: str):
+    """Single-stream continuous model files -> raw (mean, var [S][M][D], mixw [S][M])
+    as mgau_file_read / mgau_mixw_read see them (S3/libam/cont_mgau.c:160-400, 480-680)."""
+    gm, gv = read_gauden(meanfile), read_gauden(varfile)
+    if gm["n_feat"] != 1:
+        raise B200Error("continuous model must have one feature stream")
+    S, M, D = gm["n_mgau"], gm["n_density"], gm["veclen"][0]
+    w = read_mixw(mixwfile)
+    return gm["data"].reshape(S, M, D), gv["data"].reshape(S, M, D), w.reshape(S, M)
+
+
 def read_sendump(path: str, n_feat: int, n_density: int, n_sen: int):
     dims = (C.c_int32 * 5)(n_feat, n_density, n_sen, 0, 0)
     check(lib.b200_s3_read_sendump(path.encode(), dims, None, None), "read_sendump")

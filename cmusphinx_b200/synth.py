@@ -89,3 +89,59 @@ def senscr_frames(n_frames, n_sen, seed=99):
     rng = np.random.default_rng(seed)
     s = np.abs(rng.standard_normal((n_frames, n_sen)) * 800.0)
     return np.clip(s, 0, 32767).astype(np.int16)
+
+
+def s3_model(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=77):
+    """sphinx3-style fully continuous model: CI senones first, every CD senone
+    has a CI parent (mdef cd2cisen); CD Gaussians are perturbations of their
+    parent's so the CI beam is informative.  A few components are left
+    uninitialised (zero variance vector) to exercise mgau_uninit_compact
+    (S3/libam/cont_mgau.c:700-790) and one senone has an all-zero mixw row."""
+    rng = np.random.default_rng(seed)
+    cd2ci = np.arange(n_sen, dtype=np.int32)
+    cd2ci[n_ci_sen:] = rng.integers(0, n_ci_sen, n_sen - n_ci_sen)
+    mean = np.zeros((n_sen, n_density, dim), np.float32)
+    var = np.zeros((n_sen, n_density, dim), np.float32)
+    mean[:n_ci_sen] = rng.standard_normal((n_ci_sen, n_density, dim)) * 1.5
+    var[:n_ci_sen] = np.exp(rng.uniform(np.log(0.2), np.log(4.0), (n_ci_sen, n_density, dim)))
+    par = cd2ci[n_ci_sen:]
+    mean[n_ci_sen:] = mean[par] + rng.standard_normal((n_sen - n_ci_sen, n_density, dim)) * 0.4
+    var[n_ci_sen:] = var[par] * np.exp(rng.uniform(-0.7, 0.3, (n_sen - n_ci_sen, n_density, dim)))
+    var[var < 2e-4] = 5e-5          # some values under the 1e-4 floor
+    mixw = rng.dirichlet(np.ones(n_density), n_sen).astype(np.float32) * 1000.0   # un-normalised counts
+    mixw[mixw < 1e-3] = 0.0
+    for s in rng.integers(n_ci_sen, n_sen, max(1, n_sen // 50)):   # uninitialised components
+        var[s, rng.integers(0, n_density)] = 0.0
+    mixw[n_sen - 1] = 0.0
+    return mean.astype(np.float32), var.astype(np.float32), mixw.astype(np.float32), cd2ci, n_ci_sen
+
+
+def s3_features(mean, var, T, seed=88):
+    """A slowly moving trajectory through the CI Gaussians plus noise, so
+    consecutive frames keep similar best CI phones."""
+    rng = np.random.default_rng(seed)
+    n_sen, n_density, dim = mean.shape
+    x = np.zeros((T, dim), np.float32)
+    s = rng.integers(0, n_sen); d = rng.integers(0, n_density)
+    for t in range(T):
+        if rng.random() < 0.15:
+            s = rng.integers(0, n_sen); d = rng.integers(0, n_density)
+        v = np.where(var[s, d] > 0, var[s, d], 1.0)
+        x[t] = mean[s, d] + rng.standard_normal(dim) * np.sqrt(v) * 0.9
+    return x
+
+
+def s3_active(n_sen, n_ci_sen, T, seed=99, p_on=0.12, p_off=0.25):
+    """Bursty per-frame active-senone flags [T][n_sen] (the search keeps a
+    senone active for a few frames); CI entries are left 0 -- the scorer
+    forces them to 1."""
+    rng = np.random.default_rng(seed)
+    act = np.zeros((T, n_sen), np.uint8)
+    cur = rng.random(n_sen) < 0.4
+    for t in range(T):
+        on = rng.random(n_sen) < p_on
+        off = rng.random(n_sen) < p_off
+        cur = (cur & ~off) | on
+        act[t] = cur
+    act[:, :n_ci_sen] = 0
+    return act

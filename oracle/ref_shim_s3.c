@@ -1,0 +1,179 @@
+/* oracle/ref_shim_s3.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * ctypes-callable marshalling around the reference's OWN sphinx3 functions
+ * (mgau_init, mgau_eval, approx_cont_mgau_ci_eval, approx_cont_mgau_frame_eval,
+ * fast_gmm_init, mdef_init), compiled against /root/reference by
+ * oracle/Makefile (target ref3) into oracle/_ref/libref_shim_s3.so.  No
+ * algorithm lives here: it only builds the structs the reference functions
+ * take and loops over frames the way S3/libsearch/srch.c does.
+ */
+#include <string.h>
+#include <stdlib.h>
+
+#include <sphinxbase/ckd_alloc.h>
+#include <sphinxbase/logmath.h>
+#include <sphinxbase/profile.h>
+
+#include "s3types.h"
+#include "cont_mgau.h"
+#include "approx_cont_mgau.h"
+#include "fast_algo_struct.h"
+#include "ascr.h"
+#include "mdef.h"
+#include "logs3.h"
+
+typedef struct {
+    logmath_t *lmath;
+    mgau_model_t *g;
+    mdef_t *mdef;
+    int own_mdef;       /* 1: hand-built minimal mdef_t */
+    fast_gmm_t *fg;
+    ascr_t a;           /* only senscr / sen_active / rec_sen_active used */
+    ptmr_t tm;
+} s3h_t;
+
+void *
+ref_s3_open(const char *mean, const char *var, const char *mixw, const char *mdef_file,
+            const int32 *cd2cisen, int n_sen, int n_ci_sen, double varfloor, double mixwfloor,
+            double logbase)
+{
+    s3h_t *h = ckd_calloc(1, sizeof(*h));
+    int i;
+    h->lmath = logs3_init(logbase, 0, 1);
+    h->g = mgau_init(mean, var, varfloor, mixw, mixwfloor, 1, ".cont.", MIX_INT_FLOAT_COMP, h->lmath);
+    if (mdef_file) {
+        h->mdef = mdef_init(mdef_file, 0);
+    } else {
+        h->mdef = ckd_calloc(1, sizeof(mdef_t));
+        h->own_mdef = 1;
+        h->mdef->n_sen = n_sen;
+        h->mdef->n_ci_sen = n_ci_sen;
+        h->mdef->cd2cisen = ckd_calloc(n_sen, sizeof(s3senid_t));
+        for (i = 0; i < n_sen; ++i)
+            h->mdef->cd2cisen[i] = (s3senid_t)cd2cisen[i];
+    }
+    h->fg = fast_gmm_init(1, 0, 0, 1, 0, 1e-80, 1e-80, 0.5f, 100000, h->mdef->n_ci_sen, h->lmath);
+    h->a.senscr = ckd_calloc(h->g->n_mgau, sizeof(int32));
+    h->a.sen_active = ckd_calloc(h->g->n_mgau, 1);
+    h->a.rec_sen_active = ckd_calloc(h->g->n_mgau, 1);
+    ptmr_init(&h->tm);
+    return h;
+}
+
+void
+ref_s3_set_fast(void *vh, double ci_pbeam, int max_cd, int ds_ratio, float tighten)
+{
+    s3h_t *h = vh;
+    int n_ci = h->mdef->n_ci_sen;
+    fast_gmm_free(h->fg);
+    h->fg = fast_gmm_init(ds_ratio, 0, 0, 1, 0, 1e-80, ci_pbeam, tighten, max_cd, n_ci, h->lmath);
+}
+
+void
+ref_s3_dims(void *vh, int32 *d)
+{
+    s3h_t *h = vh;
+    d[0] = h->g->n_mgau; d[1] = h->g->max_comp; d[2] = h->g->veclen;
+    d[3] = h->mdef->n_ci_sen; d[4] = h->fg->gmms->ci_pbeam;
+}
+
+void
+ref_s3_cd2cisen(void *vh, int32 *out)
+{
+    s3h_t *h = vh;
+    int i;
+    for (i = 0; i < h->g->n_mgau; ++i) out[i] = h->mdef->cd2cisen[i];
+}
+
+/* precomputed parameters, padded to [n_mgau][max_comp][...] */
+void
+ref_s3_params(void *vh, int32 *n_comp, float *mean, float *var, float *lrd, int32 *mixw, double *scal)
+{
+    s3h_t *h = vh;
+    mgau_model_t *g = h->g;
+    int s, c, L = g->veclen, M = g->max_comp;
+    for (s = 0; s < g->n_mgau; ++s) {
+        n_comp[s] = g->mgau[s].n_comp;
+        for (c = 0; c < g->mgau[s].n_comp; ++c) {
+            memcpy(mean + ((size_t)s * M + c) * L, g->mgau[s].mean[c], L * sizeof(float));
+            memcpy(var + ((size_t)s * M + c) * L, g->mgau[s].var[c], L * sizeof(float));
+            lrd[(size_t)s * M + c] = g->mgau[s].lrd[c];
+            mixw[(size_t)s * M + c] = g->mgau[s].mixw[c];
+        }
+    }
+    scal[0] = g->distfloor;
+    scal[1] = 1.0 / log(logmath_get_base(g->logmath));
+}
+
+void
+ref_s3_utt_reset(void *vh)
+{
+    s3h_t *h = vh;
+    int i;
+    /* S3/libsearch/srch_time_switch_tree.c:484-490 */
+    for (i = 0; i < h->g->n_mgau; i++) {
+        h->g->mgau[i].bstidx = NO_BSTIDX;
+        h->g->mgau[i].updatetime = NOT_UPDATED;
+    }
+}
+
+void
+ref_s3_state(void *vh, int32 *bstidx, int32 *updatetime)
+{
+    s3h_t *h = vh;
+    int i;
+    for (i = 0; i < h->g->n_mgau; i++) {
+        bstidx[i] = h->g->mgau[i].bstidx;
+        updatetime[i] = h->g->mgau[i].updatetime;
+    }
+}
+
+/* dense: mgau_eval(g, s, NULL, x, t, 1) for every senone and frame */
+void
+ref_s3_eval_dense(void *vh, const float *feat, int T, int32 *out)
+{
+    s3h_t *h = vh;
+    int t, s, S = h->g->n_mgau, L = h->g->veclen;
+    for (t = 0; t < T; ++t)
+        for (s = 0; s < S; ++s)
+            out[(size_t)t * S + s] = mgau_eval(h->g, s, NULL, (float32 *)feat + (size_t)t * L, t, 1);
+}
+
+/* per utterance: CI pass then approx_cont_mgau_frame_eval per frame.
+ * sen_active [T][S] in/out or NULL (= all ones each frame); senscr_io [S]. */
+void
+ref_s3_eval_utt(void *vh, const float *feat, int T, int frame0, uint8 *sen_active,
+                int32 *senscr_io, int32 *out, int32 *best)
+{
+    s3h_t *h = vh;
+    int t, S = h->g->n_mgau, L = h->g->veclen;
+    int32 *ci = ckd_calloc(h->mdef->n_ci_sen > 0 ? h->mdef->n_ci_sen : 1, sizeof(int32));
+    int32 cib;
+    memcpy(h->a.senscr, senscr_io, S * sizeof(int32));
+    for (t = 0; t < T; ++t) {
+        float32 *x = (float32 *)feat + (size_t)t * L;
+        if (sen_active) memcpy(h->a.sen_active, sen_active + (size_t)t * S, S);
+        else memset(h->a.sen_active, 1, S);
+        approx_cont_mgau_ci_eval(NULL, NULL, h->g, h->fg, h->mdef, x, ci, &cib, frame0 + t, h->lmath);
+        best[t] = approx_cont_mgau_frame_eval(h->mdef, NULL, NULL, h->g, h->fg, &h->a, x, frame0 + t,
+                                              ci, &h->tm, h->lmath);
+        memcpy(out + (size_t)t * S, h->a.senscr, S * sizeof(int32));
+        if (sen_active) memcpy(sen_active + (size_t)t * S, h->a.sen_active, S);
+    }
+    memcpy(senscr_io, h->a.senscr, S * sizeof(int32));
+    ckd_free(ci);
+}
+
+void
+ref_s3_close(void *vh)
+{
+    s3h_t *h = vh;
+    if (!h) return;
+    fast_gmm_free(h->fg);
+    mgau_free(h->g);
+    if (h->own_mdef) { ckd_free(h->mdef->cd2cisen); ckd_free(h->mdef); }
+    else mdef_free(h->mdef);
+    ckd_free(h->a.senscr); ckd_free(h->a.sen_active); ckd_free(h->a.rec_sen_active);
+    logmath_free(h->lmath);
+    ckd_free(h);
+}

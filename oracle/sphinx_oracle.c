@@ -860,3 +860,309 @@ orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat, const u
     }
     return best;
 }
+
+/* ======================================================================
+ * sphinx3 flavour of the path: approx_cont_mgau_frame_eval and friends.
+ * S3 = sphinx3/src/libs3decoder.  Scores are int32 logs (base -logbase,
+ * default 1.0003, shift 0), higher = better; the Mahalanobis sum runs in
+ * float64 over float32 differences (S3/libam/cont_mgau.c:1033-1205).
+ * ====================================================================== */
+#define S3_ZERO ((int32_t)0xc8000000)   /* sphinx3/include/s3types.h:192 */
+#define S3_NO_BSTIDX (-1)               /* sphinx3/include/cont_mgau.h:134 */
+#define S3_NOT_UPDATED (-100)           /* :135 */
+
+struct orc_s3_model {
+    int n_sen, n_ci_sen, max_comp, veclen;
+    int *n_comp;                 /* [n_sen] after mgau_uninit_compact */
+    float *mean, *var, *lrd;     /* [s][max_comp][veclen], [s][max_comp] */
+    int32_t *mixw;               /* [s][max_comp] */
+    int32_t *cd2cisen;
+    double distfloor, f;
+    orc_logmath_t *lmath;
+    int32_t ci_pbeam; int max_cd; int ds_ratio; float tighten_factor;
+    int32_t *bstidx, *bstscr, *updatetime;
+    int32_t *ci_occ, *idx;
+    int64_t n_sen_eval, n_gau_eval;
+};
+
+/* S3/libcommon/vector.c:181-204 */
+static int s3_vec_is_zero(const float *v, int n) { int i; for (i = 0; i < n && v[i] == 0.0; ++i); return i == n; }
+static int s3_vec_is_nan(const float *v, int n) { int i; for (i = 0; i < n; ++i) if (isnan(v[i])) return 1; return 0; }
+
+/* mgau_init (S3/libam/cont_mgau.c:900-958) on arrays instead of files:
+ * mixw read/normalise/log (:480-680), mgau_uninit_compact (:700-790),
+ * mgau_var_floor (:798-825), mgau_precomp (:852-894), distfloor (:951). */
+orc_s3_model_t *
+orc_s3_new(int n_sen, int n_comp, int veclen, const float *mean, const float *var, const float *mixw,
+           double varfloor, double mixwfloor, double logbase, const int32_t *cd2cisen, int n_ci_sen)
+{
+    orc_s3_model_t *m = calloc(1, sizeof *m);
+    size_t nv = (size_t)n_sen * n_comp * veclen, nc = (size_t)n_sen * n_comp;
+    int s, c, i, c2;
+    float *pdf = malloc(sizeof(float) * n_comp);
+    m->n_sen = n_sen; m->n_ci_sen = n_ci_sen; m->max_comp = n_comp; m->veclen = veclen;
+    m->lmath = orc_logmath_init(logbase, 0, 1);
+    m->n_comp = malloc(sizeof(int) * n_sen);
+    m->mean = malloc(sizeof(float) * nv); memcpy(m->mean, mean, sizeof(float) * nv);
+    m->var = malloc(sizeof(float) * nv); memcpy(m->var, var, sizeof(float) * nv);
+    m->lrd = calloc(nc, sizeof(float));
+    m->mixw = calloc(nc, sizeof(int32_t));
+    m->cd2cisen = malloc(sizeof(int32_t) * n_sen); memcpy(m->cd2cisen, cd2cisen, sizeof(int32_t) * n_sen);
+    m->bstidx = malloc(sizeof(int32_t) * n_sen); m->bstscr = malloc(sizeof(int32_t) * n_sen);
+    m->updatetime = malloc(sizeof(int32_t) * n_sen);
+    m->ci_occ = calloc(n_ci_sen > 0 ? n_ci_sen : 1, sizeof(int32_t)); m->idx = calloc(n_ci_sen > 0 ? n_ci_sen : 1, sizeof(int32_t));
+    /* mixture weights */
+    for (s = 0; s < n_sen; ++s) {
+        memcpy(pdf, mixw + (size_t)s * n_comp, sizeof(float) * n_comp);
+        if (s3_vec_is_zero(pdf, n_comp)) {
+            for (c = 0; c < n_comp; ++c) m->mixw[(size_t)s * n_comp + c] = S3_ZERO;
+        } else {
+            double sum = 0.0, f;
+            for (c = 0; c < n_comp; ++c) if (pdf[c] != 0.0 && pdf[c] < mixwfloor) pdf[c] = (float)mixwfloor;
+            for (c = 0; c < n_comp; ++c) sum += pdf[c];
+            if (sum != 0.0) { f = 1.0 / sum; for (c = 0; c < n_comp; ++c) pdf[c] = (float)((double)pdf[c] * f); }
+            for (c = 0; c < n_comp; ++c)
+                m->mixw[(size_t)s * n_comp + c] = (pdf[c] != 0.0) ? (pdf[c] <= 0.0 ? S3_ZERO : orc_logmath_log(m->lmath, pdf[c])) : S3_ZERO;
+        }
+    }
+    free(pdf);
+    /* compaction of uninitialised components */
+    for (s = 0; s < n_sen; ++s) {
+        for (c = 0, c2 = 0; c < n_comp; ++c) {
+            float *mu = m->mean + ((size_t)s * n_comp + c) * veclen, *va = m->var + ((size_t)s * n_comp + c) * veclen;
+            int keep = !(s3_vec_is_nan(mu, veclen) || s3_vec_is_nan(va, veclen) || s3_vec_is_zero(va, veclen));
+            if (keep) {
+                if (c2 != c) {
+                    memcpy(m->mean + ((size_t)s * n_comp + c2) * veclen, mu, sizeof(float) * veclen);
+                    memcpy(m->var + ((size_t)s * n_comp + c2) * veclen, va, sizeof(float) * veclen);
+                    m->mixw[(size_t)s * n_comp + c2] = m->mixw[(size_t)s * n_comp + c];
+                }
+                ++c2;
+            }
+        }
+        m->n_comp[s] = c2;
+    }
+    /* variance floor, then precompute */
+    for (s = 0; s < n_sen; ++s)
+        for (c = 0; c < m->n_comp[s]; ++c) {
+            float *va = m->var + ((size_t)s * n_comp + c) * veclen;
+            double lrd = 0.0;
+            if (varfloor > 0.0)
+                for (i = 0; i < veclen; ++i) if (va[i] < varfloor) va[i] = (float)varfloor;
+            for (i = 0; i < veclen; ++i) {
+                lrd += log(va[i]);
+                va[i] = (float)(1.0 / (va[i] * 2.0));
+            }
+            lrd += veclen * log(2.0 * M_PI);
+            m->lrd[(size_t)s * n_comp + c] = (float)(-0.5 * lrd);
+        }
+    m->distfloor = (double)S3_ZERO * log(logbase);   /* logmath_log_to_ln, logmath.c:467-471 */
+    m->f = 1.0 / log(logbase);
+    m->ci_pbeam = orc_logmath_log(m->lmath, 1e-80); m->max_cd = 100000; m->ds_ratio = 1; m->tighten_factor = 0.5f;
+    orc_s3_utt_reset(m);
+    for (s = 0; s < n_sen; ++s) m->bstscr[s] = S3_ZERO;
+    return m;
+}
+
+void
+orc_s3_free(orc_s3_model_t *m)
+{
+    if (!m) return;
+    free(m->n_comp); free(m->mean); free(m->var); free(m->lrd); free(m->mixw); free(m->cd2cisen);
+    free(m->bstidx); free(m->bstscr); free(m->updatetime); free(m->ci_occ); free(m->idx);
+    orc_logmath_free(m->lmath); free(m);
+}
+
+/* fast_gmm_init (S3/libam/fast_algo_struct.c:420-467): beam given as a
+ * probability, converted with logs3. */
+void
+orc_s3_set_fast(orc_s3_model_t *m, double ci_pbeam, int max_cd, int ds_ratio, float tighten_factor)
+{
+    m->ci_pbeam = ci_pbeam <= 0.0 ? S3_ZERO : orc_logmath_log(m->lmath, ci_pbeam);
+    m->max_cd = max_cd; m->ds_ratio = ds_ratio; m->tighten_factor = tighten_factor;
+}
+
+int32_t orc_s3_ci_pbeam(const orc_s3_model_t *m) { return m->ci_pbeam; }
+
+/* per-utterance re-initialisation, S3/libsearch/srch_time_switch_tree.c:484-490 */
+void
+orc_s3_utt_reset(orc_s3_model_t *m)
+{
+    int s;
+    for (s = 0; s < m->n_sen; ++s) { m->bstidx[s] = S3_NO_BSTIDX; m->updatetime[s] = S3_NOT_UPDATED; }
+}
+
+void
+orc_s3_params(const orc_s3_model_t *m, int32_t *n_comp, float *mean, float *var, float *lrd, int32_t *mixw, double *scal)
+{
+    size_t nv = (size_t)m->n_sen * m->max_comp * m->veclen, nc = (size_t)m->n_sen * m->max_comp;
+    int s;
+    for (s = 0; s < m->n_sen; ++s) n_comp[s] = m->n_comp[s];
+    memcpy(mean, m->mean, sizeof(float) * nv); memcpy(var, m->var, sizeof(float) * nv);
+    memcpy(lrd, m->lrd, sizeof(float) * nc); memcpy(mixw, m->mixw, sizeof(int32_t) * nc);
+    scal[0] = m->distfloor; scal[1] = m->f;
+}
+
+void
+orc_s3_state(const orc_s3_model_t *m, int32_t *bstidx, int32_t *updatetime)
+{
+    memcpy(bstidx, m->bstidx, sizeof(int32_t) * m->n_sen); memcpy(updatetime, m->updatetime, sizeof(int32_t) * m->n_sen);
+}
+
+/* one density: the float64 accumulation of cont_mgau.c:1062-1068 */
+static double
+s3_dval(const orc_s3_model_t *m, int s, int c, const float *x)
+{
+    const float *mu = m->mean + ((size_t)s * m->max_comp + c) * m->veclen;
+    const float *va = m->var + ((size_t)s * m->max_comp + c) * m->veclen;
+    double dval = m->lrd[(size_t)s * m->max_comp + c], diff;
+    int i;
+    for (i = 0; i < m->veclen; ++i) {
+        diff = x[i] - mu[i];          /* float32 subtraction, then widened */
+        dval -= diff * diff * va[i];
+    }
+    return dval;
+}
+
+/* mgau_eval (cont_mgau.c:1171-1205) with mgau_eval_all (:1033-1123) and
+ * mgau_eval_active (:1125-1165); diagonal covariances only. */
+int32_t
+orc_s3_mgau_eval(orc_s3_model_t *m, int s, const int32_t *active, const float *x, int fr, int update_best_id)
+{
+    const int32_t *mw = m->mixw + (size_t)s * m->max_comp;
+    int32_t score = S3_ZERO, gauscr;
+    int c, j, nc = m->n_comp[s];
+    double d1, d2;
+    if (update_best_id) { m->bstidx[s] = S3_NO_BSTIDX; m->bstscr[s] = S3_ZERO; m->updatetime[s] = fr; }
+    if (!active) {
+        for (c = 0; c < nc - 1; c += 2) {
+            d1 = s3_dval(m, s, c, x); d2 = s3_dval(m, s, c + 1, x);
+            if (d1 < m->distfloor) d1 = m->distfloor;
+            if (d2 < m->distfloor) d2 = m->distfloor;
+            gauscr = (int32_t)(m->f * d1) + mw[c];
+            score = orc_logmath_add(m->lmath, score, gauscr);
+            if (gauscr > m->bstscr[s]) { m->bstidx[s] = c; m->bstscr[s] = gauscr; }   /* :1080, no update_best_id test */
+            gauscr = (int32_t)(m->f * d2) + mw[c + 1];
+            score = orc_logmath_add(m->lmath, score, gauscr);
+            if (update_best_id && gauscr > m->bstscr[s]) { m->bstidx[s] = c + 1; m->bstscr[s] = gauscr; }
+        }
+        if (c < nc) {
+            d1 = s3_dval(m, s, c, x);
+            if (d1 < m->distfloor) d1 = m->distfloor;
+            gauscr = (int32_t)(m->f * d1) + mw[c];
+            score = orc_logmath_add(m->lmath, score, gauscr);
+            if (update_best_id && gauscr > m->bstscr[s]) { m->bstidx[s] = c; m->bstscr[s] = gauscr; }
+        }
+    } else {
+        for (j = 0; active[j] >= 0; ++j) {
+            c = active[j];
+            d1 = s3_dval(m, s, c, x);
+            if (d1 < m->distfloor) d1 = m->distfloor;
+            gauscr = (int32_t)(m->f * d1) + mw[c];
+            score = orc_logmath_add(m->lmath, score, gauscr);
+            if (update_best_id && gauscr > m->bstscr[s]) { m->bstidx[s] = c; m->bstscr[s] = gauscr; }
+        }
+    }
+    if (score <= S3_ZERO) score = S3_ZERO;
+    return score;
+}
+
+/* approx_cont_mgau_ci_eval (S3/libam/approx_cont_mgau.c:368-431), no GS/SVQ */
+void
+orc_s3_ci_eval(orc_s3_model_t *m, const float *x, int32_t *ci_senscr, int32_t *best, int fr)
+{
+    int s;
+    for (s = 0; s < m->n_ci_sen; ++s) ci_senscr[s] = orc_s3_mgau_eval(m, s, NULL, x, fr, 1);
+    *best = INT_MIN;
+    for (s = 0; s < m->n_ci_sen; ++s) if (ci_senscr[s] > *best) *best = ci_senscr[s];
+}
+
+static const int32_t *s3_sort_key;
+static int s3_intcmp(const void *a, const void *b) { return s3_sort_key[*(const int32_t *)b] - s3_sort_key[*(const int32_t *)a]; }
+
+/* approx_compute_dyn_ci_pbeam (approx_cont_mgau.c:302-358) */
+static int32_t
+s3_dyn_beam(orc_s3_model_t *m, const uint8_t *sen_active, const int32_t *ci)
+{
+    int s, total = 0;
+    int32_t pbest, beam = m->ci_pbeam;
+    for (s = 0; s < m->n_sen; ++s) {
+        if (s < m->n_ci_sen) m->ci_occ[s] = 0;
+        else if (!sen_active || sen_active[s]) m->ci_occ[m->cd2cisen[s]]++;
+    }
+    for (s = 0; s < m->n_ci_sen; ++s) m->idx[s] = s;
+    s3_sort_key = ci;
+    qsort(m->idx, m->n_ci_sen, sizeof(int32_t), s3_intcmp);
+    pbest = ci[m->idx[0]];
+    for (s = 0; s < m->n_ci_sen && ci[m->idx[s]] > pbest + m->ci_pbeam; ++s) {
+        total += m->ci_occ[m->idx[s]];
+        if (total > m->max_cd) { beam = ci[m->idx[s]] - pbest; break; }
+    }
+    return beam;
+}
+
+/* approx_cont_mgau_frame_eval (approx_cont_mgau.c:433-616), no GS/SVQ,
+ * approx_isskip (:93-143) with plain -ds only.  sen_active is in/out (CI
+ * entries are forced to 1); senscr entries of inactive CD senones are left
+ * as they were. */
+int32_t
+orc_s3_frame_eval(orc_s3_model_t *m, const float *x, int frame, const int32_t *cache_ci_senscr,
+                  uint8_t *sen_active, int32_t *senscr)
+{
+    int32_t best = INT_MIN, pbest = INT_MIN, dyn, single[2] = { -1, -1 };
+    int s, is_skip;
+    int64_t ns = 0, ng = 0;
+    if (m->max_cd < m->n_sen - m->n_ci_sen) dyn = s3_dyn_beam(m, sen_active, cache_ci_senscr);
+    else dyn = m->ci_pbeam;
+    is_skip = (frame % m->ds_ratio) != 0;
+    if (is_skip) dyn = (int32_t)((float)dyn * m->tighten_factor);
+    for (s = 0; s < m->n_sen; ++s) {
+        if (s < m->n_ci_sen) {
+            senscr[s] = cache_ci_senscr[s];
+            if (pbest < senscr[s]) pbest = senscr[s];
+            if (best < senscr[s]) best = senscr[s];
+            sen_active[s] = 1;
+        } else if (sen_active[s]) {
+            if (senscr[m->cd2cisen[s]] >= pbest + dyn) {
+                senscr[s] = orc_s3_mgau_eval(m, s, NULL, x, frame, 1);
+                ng += m->n_comp[s]; ns++;
+            } else if (m->bstidx[s] == S3_NO_BSTIDX || m->updatetime[s] != frame - 1) {
+                senscr[s] = senscr[m->cd2cisen[s]];
+            } else {
+                single[0] = m->bstidx[s];
+                senscr[s] = orc_s3_mgau_eval(m, s, single, x, frame, is_skip ? 1 : 0);
+                ng++;
+            }
+            if (best < senscr[s]) best = senscr[s];
+        }
+    }
+    for (s = 0; s < m->n_sen; ++s) if (sen_active[s]) senscr[s] -= best;
+    m->n_sen_eval += ns; m->n_gau_eval += ng;
+    return best;
+}
+
+/* The decoder's per-utterance sequence (S3/libsearch/srch.c lv1 + lv2 with a
+ * zero look-ahead window): for each frame the CI pass, then the frame eval.
+ * sen_active [T][n_sen] in/out (NULL = all active); senscr_io [n_sen] holds
+ * the score buffer before the first frame on entry; out [T][n_sen];
+ * best [T]. */
+void
+orc_s3_eval_utt(orc_s3_model_t *m, const float *feat, int T, int frame0, uint8_t *sen_active,
+                int32_t *senscr_io, int32_t *out, int32_t *best)
+{
+    int t;
+    int32_t *ci = malloc(sizeof(int32_t) * (m->n_ci_sen > 0 ? m->n_ci_sen : 1)), cib;
+    uint8_t *all = NULL;
+    if (!sen_active) { all = malloc(m->n_sen); }
+    for (t = 0; t < T; ++t) {
+        const float *x = feat + (size_t)t * m->veclen;
+        uint8_t *act = sen_active ? sen_active + (size_t)t * m->n_sen : all;
+        if (all) memset(all, 1, m->n_sen);
+        orc_s3_ci_eval(m, x, ci, &cib, frame0 + t);
+        best[t] = orc_s3_frame_eval(m, x, frame0 + t, ci, act, senscr_io);
+        memcpy(out + (size_t)t * m->n_sen, senscr_io, sizeof(int32_t) * m->n_sen);
+    }
+    free(ci); free(all);
+}
+
+void orc_s3_counts(const orc_s3_model_t *m, int64_t *c) { c[0] = m->n_sen_eval; c[1] = m->n_gau_eval; }

@@ -125,6 +125,35 @@ int32_t orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat,
                            const uint8_t *mpx, int32_t *bestscore,
                            int n_frames_repeat);
 
+/* ---- sphinx3 flavour: approx_cont_mgau_frame_eval (S3/libam/approx_cont_mgau.c,
+ * cont_mgau.c, fast_algo_struct.c); int32 scores, float64 accumulation ---- */
+typedef struct orc_s3_model orc_s3_model_t;
+/* mgau_init on arrays: mean/var [n_sen][n_comp][veclen] RAW (variances not yet
+ * inverted), mixw [n_sen][n_comp] raw counts. */
+orc_s3_model_t *orc_s3_new(int n_sen, int n_comp, int veclen, const float *mean,
+                           const float *var, const float *mixw, double varfloor,
+                           double mixwfloor, double logbase,
+                           const int32_t *cd2cisen, int n_ci_sen);
+void orc_s3_free(orc_s3_model_t *m);
+void orc_s3_set_fast(orc_s3_model_t *m, double ci_pbeam, int max_cd, int ds_ratio,
+                     float tighten_factor);
+int32_t orc_s3_ci_pbeam(const orc_s3_model_t *m);
+void orc_s3_utt_reset(orc_s3_model_t *m);
+void orc_s3_params(const orc_s3_model_t *m, int32_t *n_comp, float *mean, float *var,
+                   float *lrd, int32_t *mixw, double *scal /* distfloor, f */);
+void orc_s3_state(const orc_s3_model_t *m, int32_t *bstidx, int32_t *updatetime);
+int32_t orc_s3_mgau_eval(orc_s3_model_t *m, int s, const int32_t *active,
+                         const float *x, int fr, int update_best_id);
+void orc_s3_ci_eval(orc_s3_model_t *m, const float *x, int32_t *ci_senscr,
+                    int32_t *best, int fr);
+int32_t orc_s3_frame_eval(orc_s3_model_t *m, const float *x, int frame,
+                          const int32_t *cache_ci_senscr, uint8_t *sen_active,
+                          int32_t *senscr);
+void orc_s3_eval_utt(orc_s3_model_t *m, const float *feat, int T, int frame0,
+                     uint8_t *sen_active, int32_t *senscr_io, int32_t *out,
+                     int32_t *best);
+void orc_s3_counts(const orc_s3_model_t *m, int64_t *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,3 +310,133 @@ def read_mfc(path):
         n = int(np.frombuffer(raw.tobytes(), dtype=">i4")[0])
         data = np.fromfile(path, dtype=">f4", offset=4).astype(np.float32)
     return data.reshape(-1, 13).astype(np.float32)
+
+
+# ------------------------------------------------------- sphinx3 flavour
+# sphinx3's -logbase default is the float32 option 1.0003 (cmdln_macro.h:246).
+S3_LOGBASE = float(np.float32(1.0003))
+S3_ZERO = np.int32(-939524096)   # 0xc8000000, s3types.h:192
+i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
+
+port.orc_s3_new.restype = vp
+port.orc_s3_new.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_double, C.c_double, C.c_double, i32p, C.c_int]
+port.orc_s3_free.argtypes = [vp]
+port.orc_s3_set_fast.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_float]
+port.orc_s3_ci_pbeam.restype = C.c_int32
+port.orc_s3_ci_pbeam.argtypes = [vp]
+port.orc_s3_utt_reset.argtypes = [vp]
+port.orc_s3_params.argtypes = [vp, i32p, f32p, f32p, f32p, i32p, f64p]
+port.orc_s3_state.argtypes = [vp, i32p, i32p]
+port.orc_s3_mgau_eval.restype = C.c_int32
+port.orc_s3_mgau_eval.argtypes = [vp, C.c_int, i32p, f32p, C.c_int, C.c_int]
+port.orc_s3_eval_utt.argtypes = [vp, f32p, C.c_int, C.c_int, u8p, i32p, i32p, i32p]
+port.orc_s3_counts.argtypes = [vp, i64p]
+
+
+def have_ref_s3():
+    return os.path.exists(os.path.join(REF_DIR, "libref_shim_s3.so"))
+
+
+_ref3 = None
+
+
+def ref_s3():
+    global _ref3
+    if _ref3 is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libref_shim_s3.so"))
+        L.ref_s3_open.restype = vp
+        L.ref_s3_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, i32p, C.c_int, C.c_int, C.c_double,
+                                  C.c_double, C.c_double]
+        L.ref_s3_set_fast.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_float]
+        L.ref_s3_dims.argtypes = [vp, i32p]
+        L.ref_s3_cd2cisen.argtypes = [vp, i32p]
+        L.ref_s3_params.argtypes = [vp, i32p, f32p, f32p, f32p, i32p, f64p]
+        L.ref_s3_utt_reset.argtypes = [vp]
+        L.ref_s3_state.argtypes = [vp, i32p, i32p]
+        L.ref_s3_eval_dense.argtypes = [vp, f32p, C.c_int, i32p]
+        L.ref_s3_eval_utt.argtypes = [vp, f32p, C.c_int, C.c_int, u8p, i32p, i32p, i32p]
+        L.ref_s3_close.argtypes = [vp]
+        _ref3 = L
+    return _ref3
+
+
+class _S3Common:
+    """Same surface for the port (PortS3) and the reference shim (RefS3)."""
+
+    def eval_utt(self, feat, sen_active=None, frame0=0, senscr0=None):
+        """-> (out [T][S] int32, best [T], sen_active after (or None))."""
+        feat = _c(feat, np.float32)
+        T = feat.shape[0]
+        act = None if sen_active is None else np.ascontiguousarray(sen_active, np.uint8).copy()
+        io = np.zeros(self.n_sen, np.int32) if senscr0 is None else _c(senscr0, np.int32).copy()
+        out = np.zeros((T, self.n_sen), np.int32)
+        best = np.zeros(T, np.int32)
+        self._eval_utt(self.h, _p(feat, C.c_float), T, frame0, None if act is None else _p(act, C.c_uint8),
+                       _p(io, C.c_int32), _p(out, C.c_int32), _p(best, C.c_int32))
+        self.last_row = io
+        return out, best, act
+
+    def params(self):
+        S, M, D = self.n_sen, self.max_comp, self.veclen
+        nc = np.zeros(S, np.int32)
+        mean = np.zeros((S, M, D), np.float32); var = np.zeros((S, M, D), np.float32)
+        lrd = np.zeros((S, M), np.float32); mixw = np.zeros((S, M), np.int32); scal = np.zeros(2, np.float64)
+        self._params(self.h, _p(nc, C.c_int32), _p(mean, C.c_float), _p(var, C.c_float), _p(lrd, C.c_float),
+                     _p(mixw, C.c_int32), _p(scal, C.c_double))
+        return nc, mean, var, lrd, mixw, scal
+
+    def state(self):
+        b = np.zeros(self.n_sen, np.int32); u = np.zeros(self.n_sen, np.int32)
+        self._state(self.h, _p(b, C.c_int32), _p(u, C.c_int32))
+        return b, u
+
+    def set_fast(self, ci_pbeam=1e-80, max_cd=100000, ds_ratio=1, tighten=0.5):
+        self._set_fast(self.h, ci_pbeam, max_cd, ds_ratio, tighten)
+
+    def utt_reset(self):
+        self._reset(self.h)
+
+
+class PortS3(_S3Common):
+    def __init__(self, mean, var, mixw, cd2cisen, n_ci_sen, varfloor=1e-4, mixwfloor=1e-7, logbase=S3_LOGBASE):
+        mean, var, mixw = _c(mean, np.float32), _c(var, np.float32), _c(mixw, np.float32)
+        self.n_sen, self.max_comp, self.veclen = mean.shape
+        cd = _c(cd2cisen, np.int32)
+        self.h = port.orc_s3_new(self.n_sen, self.max_comp, self.veclen, _p(mean, C.c_float), _p(var, C.c_float),
+                                 _p(mixw, C.c_float), varfloor, mixwfloor, logbase, _p(cd, C.c_int32), n_ci_sen)
+        self._eval_utt, self._params, self._state = port.orc_s3_eval_utt, port.orc_s3_params, port.orc_s3_state
+        self._set_fast, self._reset = port.orc_s3_set_fast, port.orc_s3_utt_reset
+
+    def free(self):
+        port.orc_s3_free(self.h)
+
+
+class RefS3(_S3Common):
+    def __init__(self, meanfile, varfile, mixwfile, mdef_file=None, cd2cisen=None, n_ci_sen=0, varfloor=1e-4,
+                 mixwfloor=1e-7, logbase=S3_LOGBASE):
+        L = ref_s3()
+        cd = None if cd2cisen is None else _c(cd2cisen, np.int32)
+        self.h = L.ref_s3_open(meanfile.encode(), varfile.encode(), mixwfile.encode(),
+                               None if mdef_file is None else mdef_file.encode(),
+                               None if cd is None else _p(cd, C.c_int32), 0 if cd is None else len(cd), n_ci_sen,
+                               varfloor, mixwfloor, logbase)
+        d = np.zeros(5, np.int32)
+        L.ref_s3_dims(self.h, _p(d, C.c_int32))
+        self.n_sen, self.max_comp, self.veclen, self.n_ci_sen, self.ci_pbeam = (int(v) for v in d)
+        self._eval_utt, self._params, self._state = L.ref_s3_eval_utt, L.ref_s3_params, L.ref_s3_state
+        self._set_fast, self._reset = L.ref_s3_set_fast, L.ref_s3_utt_reset
+
+    def cd2cisen(self):
+        out = np.zeros(self.n_sen, np.int32)
+        ref_s3().ref_s3_cd2cisen(self.h, _p(out, C.c_int32))
+        return out
+
+    def eval_dense(self, feat):
+        feat = _c(feat, np.float32)
+        out = np.zeros((feat.shape[0], self.n_sen), np.int32)
+        ref_s3().ref_s3_eval_dense(self.h, _p(feat, C.c_float), feat.shape[0], _p(out, C.c_int32))
+        return out
+
+    def free(self):
+        ref_s3().ref_s3_close(self.h)
