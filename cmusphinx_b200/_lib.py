@@ -89,6 +89,22 @@ _sig("b200_hmm_step_dev", C.c_int, vp, vp, C.c_int32, vp)
 _sig("b200_hmm_step_results", C.c_int, vp, c_i32p, c_i32p, c_i32p, c_u32p)
 _sig("b200_hmm_step_host", C.c_int, vp, c_i16p, C.c_int32)
 _sig("b200_hmm_last_ms", C.c_float, vp)
+_sig("b200_s3_create", vp, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, C.c_double, C.c_double, C.c_double,
+     c_i32p, C.c_int, C.c_int)
+_sig("b200_s3_load", vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_double, c_i32p, C.c_int,
+     C.c_int)
+_sig("b200_s3_free", None, vp)
+_sig("b200_s3_dims", C.c_int, vp, c_i32p)
+_sig("b200_s3_set_fast", C.c_int, vp, C.c_double, C.c_int, C.c_int, C.c_float)
+_sig("b200_s3_utt_reset", C.c_int, vp)
+_sig("b200_s3_params", C.c_int, vp, c_i32p, c_f32p, c_f32p, c_f32p, c_i32p, C.POINTER(C.c_double))
+_sig("b200_s3_state", C.c_int, vp, c_i32p, c_i32p)
+_sig("b200_s3_dense_host", C.c_int, vp, c_f32p, C.c_int, c_i32p)
+_sig("b200_s3_dense_dev", C.c_int, vp, vp, C.c_int, vp, vp)
+_sig("b200_s3_score_utt_host", C.c_int, vp, c_f32p, C.c_int, C.c_int, c_u8p, c_i32p, c_i32p, c_i32p)
+_sig("b200_s3_score_utt_dev", C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp)
+_sig("b200_s3_frame_eval", C.c_int, vp, c_f32p, C.c_int32, c_u8p, c_i32p, c_i32p)
+_sig("b200_s3_last_ms", C.c_float, vp)
 _sig("b200_flags2list", C.c_int, c_u32p, C.c_int, c_u8p, C.c_int)
 _sig("b200_dev_alloc", vp, C.c_size_t, C.c_int)
 _sig("b200_dev_free", None, vp)

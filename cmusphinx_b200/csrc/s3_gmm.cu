@@ -1,0 +1,667 @@
+// s3_gmm.cu -- sphinx3's flavour of the acoustic-scoring path on the GPU.
+//
+// Reference (S3 = sphinx3/src/libs3decoder):
+//   approx_cont_mgau_frame_eval   S3/libam/approx_cont_mgau.c:433-616
+//   approx_cont_mgau_ci_eval      S3/libam/approx_cont_mgau.c:368-431
+//   approx_compute_dyn_ci_pbeam   S3/libam/approx_cont_mgau.c:302-358
+//   approx_isskip (-ds only)      S3/libam/approx_cont_mgau.c:93-143
+//   mgau_eval / _all / _active    S3/libam/cont_mgau.c:1033-1205
+//   mgau_init, mgau_precomp,
+//   mgau_uninit_compact           S3/libam/cont_mgau.c:700-958
+//   fast_gmm_init                 S3/libam/fast_algo_struct.c:420-467
+//
+// Arithmetic contract (bit-exact with the reference): differences x-m in
+// float32, widened to float64; dval -= (diff*diff)*v with separately rounded
+// float64 multiplies and subtract, sequential over dimensions; gauscr =
+// (int32)(f*dval) + mixw; integer table log-add (shift 0) in component order.
+//
+// Device decomposition of one utterance chunk of T frames:
+//   K1 s3_eval_kernel   (CI senones, all frames)  -> raw CI scores
+//   K2 s3_decide_kernel (block per frame)         -> CI best, (dynamic) beam,
+//                                                    per (t,s) flag {0 inactive,1 full,2 back-off}
+//   K1 s3_eval_kernel   (CD senones, flagged)     -> raw scores + best component
+//   K3 s3_time_kernel   (thread per CD senone, sequential in t): best-index /
+//                        update-time state machine, CI or best-Gaussian back-off
+//   K4 s3_best_kernel   (block per frame)         -> frame best over active
+//   K5 s3_norm_kernel   (thread per senone, sequential in t): subtract best on
+//                        active entries, carry stale entries forward
+// The frame axis is sequential only in K3/K5, which touch a few bytes per
+// (t,s); all Gaussian arithmetic (K1) is parallel over frames and senones.
+#include "dev_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+constexpr int32_t kS3Zero = (int32_t)0xc8000000;   // s3types.h:192
+constexpr int kNoBst = -1;                         // cont_mgau.h:134
+constexpr int kNotUpdated = -100;                  // cont_mgau.h:135
+constexpr int kFB = 32;                            // frames per block in K1
+constexpr int kEvalThreads = 128;
+
+struct S3Dev {
+    int n_sen, n_ci, veclen, cpt;   // cpt = padded components per senone
+    const float *mean;     // [s][i][cpt]
+    const double *var;     // [s][i][cpt]  1/(2 var) widened at load
+    const float *lrd;      // [s][cpt]
+    const int32_t *mixw;   // [s][cpt]
+    const int32_t *ncomp;  // [s]
+    const int32_t *cd2ci;  // [s]
+    const uint16_t *tab16; const uint32_t *tab32; uint32_t tab_size;
+    int32_t lzero;         // logmath zero (MIN_INT32 >> 2)
+    double distfloor, f;
+};
+
+// logmath_add, SB/util/logmath.c:391-436 (shift 0 table, 16 or 32 bit wide)
+__device__ __forceinline__ int32_t s3_logadd(const S3Dev &g, int32_t x, int32_t y) {
+    if (x <= g.lzero) return y;
+    if (y <= g.lzero) return x;
+    int32_t d, r;
+    if (x > y) { d = x - y; r = x; } else { d = y - x; r = y; }
+    if (d < 0 || (uint32_t)d >= g.tab_size) return r;
+    return r + (g.tab16 ? (int32_t)__ldg(g.tab16 + d) : (int32_t)__ldg(g.tab32 + d));
+}
+
+// one density against one frame: cont_mgau.c:1062-1068
+__device__ __forceinline__ double s3_dval(const S3Dev &g, int s, int c, const float *x) {
+    const float *mp = g.mean + (size_t)s * g.veclen * g.cpt + c;
+    const double *vp = g.var + (size_t)s * g.veclen * g.cpt + c;
+    double dval = (double)__ldg(g.lrd + (size_t)s * g.cpt + c);
+#pragma unroll 3
+    for (int i = 0; i < g.veclen; ++i) {
+        float diff = __fsub_rn(x[i], __ldg(mp + (size_t)i * g.cpt));
+        double dd = (double)diff;
+        dval = __dsub_rn(dval, __dmul_rn(__dmul_rn(dd, dd), __ldg(vp + (size_t)i * g.cpt)));
+    }
+    return dval;
+}
+
+__device__ __forceinline__ int32_t s3_gauscr(const S3Dev &g, int s, int c, double dval) {
+    if (dval < g.distfloor) dval = g.distfloor;
+    return __double2int_rz(__dmul_rn(g.f, dval)) + __ldg(g.mixw + (size_t)s * g.cpt + c);
+}
+
+// K1: CP lanes per senone (one component each, KC rounds when a senone has
+// more than 32 components).  flags == nullptr: every frame of every senone in
+// [s_lo, s_hi).  Writes raw[t][s] and (bst != nullptr) the arg-max component.
+template <int CP, int KC>
+__global__ void __launch_bounds__(kEvalThreads)
+s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_hi,
+               const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, int16_t *__restrict__ bst) {
+    extern __shared__ float xs[];   // [kFB][veclen]
+    constexpr int G = kEvalThreads / CP;
+    const int t0 = blockIdx.y * kFB;
+    const int nf = min(kFB, T - t0);
+    for (int i = threadIdx.x; i < nf * g.veclen; i += kEvalThreads) xs[i] = feat[(size_t)t0 * g.veclen + i];
+    __syncthreads();
+    const int grp = threadIdx.x / CP, lc = threadIdx.x % CP;
+    const int s = s_lo + blockIdx.x * G + grp;
+    if (s >= s_hi) return;
+    const unsigned gmask = CP == 32 ? 0xffffffffu : (((1u << CP) - 1u) << ((threadIdx.x % 32) / CP * CP));
+    const int lane0 = (threadIdx.x % 32) / CP * CP;
+    // frames of this block that need this senone
+    uint32_t mask = 0;
+    if (flags) {
+        for (int k = lc; k < nf; k += CP)
+            if (flags[(size_t)(t0 + k) * g.n_sen + s] == 1) mask |= 1u << k;
+#pragma unroll
+        for (int o = CP / 2; o > 0; o >>= 1) mask |= __shfl_xor_sync(gmask, mask, o);
+    } else {
+        mask = nf == 32 ? 0xffffffffu : ((1u << nf) - 1u);
+    }
+    const int nc = __ldg(g.ncomp + s);
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float *x = xs + k * g.veclen;
+        int32_t gs[KC];
+#pragma unroll
+        for (int r = 0; r < KC; ++r) {
+            const int c = lc + r * CP;
+            gs[r] = c < nc ? s3_gauscr(g, s, c, s3_dval(g, s, c, x)) : kS3Zero;
+        }
+        // sequential log-add in component order (mgau_eval_all); with
+        // update_best_id == 1 the best component is the first strict maximum
+        int32_t score = kS3Zero, bscr = kS3Zero; int bidx = kNoBst;
+#pragma unroll
+        for (int r = 0; r < KC; ++r)
+            for (int c = 0; c < CP; ++c) {
+                const int32_t v = __shfl_sync(gmask, gs[r], lane0 + c);
+                if (c + r * CP < nc) {
+                    score = s3_logadd(g, score, v);
+                    if (v > bscr) { bscr = v; bidx = c + r * CP; }
+                }
+            }
+        if (score <= kS3Zero) score = kS3Zero;
+        if (lc == 0) {
+            raw[(size_t)(t0 + k) * g.n_sen + s] = score;
+            if (bst) bst[(size_t)(t0 + k) * g.n_sen + s] = (int16_t)bidx;
+        }
+    }
+}
+
+// K2: one block per frame.
+__global__ void __launch_bounds__(256)
+s3_decide_kernel(S3Dev g, int T, int frame0, int32_t ci_pbeam, int max_cd, int ds_ratio, float tighten,
+                 const int32_t *__restrict__ raw, uint8_t *__restrict__ act /* may be null */,
+                 uint8_t *__restrict__ flags, int32_t *__restrict__ beam_out) {
+    extern __shared__ int32_t sm[];      // ci[n_ci] | occ[n_ci] | order[n_ci]
+    int32_t *ci = sm, *occ = sm + g.n_ci, *order = sm + 2 * g.n_ci;
+    __shared__ int32_t s_pbest, s_beam;
+    const int t = blockIdx.x;
+    const int32_t *row = raw + (size_t)t * g.n_sen;
+    uint8_t *arow = act ? act + (size_t)t * g.n_sen : nullptr;
+    if (threadIdx.x == 0) s_pbest = INT32_MIN;
+    for (int i = threadIdx.x; i < g.n_ci; i += blockDim.x) { ci[i] = row[i]; occ[i] = 0; }
+    __syncthreads();
+    int32_t m = INT32_MIN;
+    for (int i = threadIdx.x; i < g.n_ci; i += blockDim.x) m = max(m, ci[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x % 32 == 0) atomicMax(&s_pbest, m);
+    __syncthreads();
+    const int32_t pbest = s_pbest;
+    int32_t beam = ci_pbeam;
+    if (max_cd < g.n_sen - g.n_ci) {
+        // approx_compute_dyn_ci_pbeam: occupancy of every CI senone by active
+        // CD senones, CI scores sorted descending, cumulative occupancy.
+        for (int s = g.n_ci + threadIdx.x; s < g.n_sen; s += blockDim.x)
+            if (!arow || arow[s]) atomicAdd(&occ[g.cd2ci[s]], 1);
+        __syncthreads();
+        for (int i = threadIdx.x; i < g.n_ci; i += blockDim.x) {
+            const int32_t v = ci[i];
+            int r = 0;
+            for (int j = 0; j < g.n_ci; ++j) r += (ci[j] > v) || (ci[j] == v && j < i);
+            order[r] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int total = 0;
+            for (int k = 0; k < g.n_ci && ci[order[k]] > pbest + ci_pbeam; ++k) {
+                total += occ[order[k]];
+                if (total > max_cd) { beam = ci[order[k]] - pbest; break; }
+            }
+            s_beam = beam;
+        }
+        __syncthreads();
+        beam = s_beam;
+    }
+    const bool skip = ((frame0 + t) % ds_ratio) != 0;
+    if (skip) beam = (int32_t)__fmul_rn((float)beam, tighten);
+    if (threadIdx.x == 0) beam_out[t] = beam;
+    const int32_t thr = pbest + beam;
+    uint8_t *frow = flags + (size_t)t * g.n_sen;
+    for (int s = threadIdx.x; s < g.n_sen; s += blockDim.x) {
+        if (s < g.n_ci) { frow[s] = 1; if (arow) arow[s] = 1; continue; }
+        uint8_t f = 0;
+        if (!arow || arow[s]) f = ci[g.cd2ci[s]] >= thr ? 1 : 2;
+        frow[s] = f;
+    }
+}
+
+// K3: one thread per CD senone, sequential over the chunk's frames.
+__global__ void __launch_bounds__(128)
+s3_time_kernel(S3Dev g, const float *__restrict__ feat, int T, int frame0, int ds_ratio,
+               const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, const int16_t *__restrict__ bst,
+               int32_t *__restrict__ st_bstidx, int32_t *__restrict__ st_update) {
+    const int s = g.n_ci + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n_sen) return;
+    int bidx = st_bstidx[s], upd = st_update[s];
+    const int par = g.cd2ci[s];
+    for (int t = 0; t < T; ++t) {
+        const int frame = frame0 + t;
+        const uint8_t f = flags[(size_t)t * g.n_sen + s];
+        if (f == 1) {
+            bidx = bst[(size_t)t * g.n_sen + s];
+            upd = frame;
+        } else if (f == 2) {
+            if (bidx == kNoBst || upd != frame - 1) {
+                raw[(size_t)t * g.n_sen + s] = raw[(size_t)t * g.n_sen + par];
+            } else {
+                // mgau_eval(g, s, {bstidx,-1}, x, frame, is_skip)
+                const int32_t v = s3_gauscr(g, s, bidx, s3_dval(g, s, bidx, feat + (size_t)t * g.veclen));
+                int32_t score = s3_logadd(g, kS3Zero, v);
+                if (score <= kS3Zero) score = kS3Zero;
+                raw[(size_t)t * g.n_sen + s] = score;
+                if ((frame % ds_ratio) != 0) {      // skipped frame: update_best_id = 1
+                    bidx = v > kS3Zero ? bidx : kNoBst;
+                    upd = frame;
+                }
+            }
+        }
+    }
+    st_bstidx[s] = bidx; st_update[s] = upd;
+}
+
+// CI senones are re-evaluated with update_best_id = 1 every frame
+// (approx_cont_mgau_ci_eval): their state after the chunk is that of the last frame.
+__global__ void s3_ci_state_kernel(S3Dev g, int T, int frame0, const int16_t *__restrict__ bst,
+                                   int32_t *__restrict__ st_bstidx, int32_t *__restrict__ st_update) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n_ci) return;
+    st_bstidx[s] = bst[(size_t)(T - 1) * g.n_sen + s];
+    st_update[s] = frame0 + T - 1;
+}
+
+// K4: frame best over active senones.
+__global__ void __launch_bounds__(256)
+s3_best_kernel(int n_sen, const uint8_t *__restrict__ flags, const int32_t *__restrict__ raw,
+               int32_t *__restrict__ best) {
+    __shared__ int32_t s_best;
+    const int t = blockIdx.x;
+    if (threadIdx.x == 0) s_best = INT32_MIN;
+    __syncthreads();
+    int32_t m = INT32_MIN;
+    for (int s = threadIdx.x; s < n_sen; s += blockDim.x)
+        if (flags[(size_t)t * n_sen + s]) m = max(m, raw[(size_t)t * n_sen + s]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x % 32 == 0) atomicMax(&s_best, m);
+    __syncthreads();
+    if (threadIdx.x == 0) best[t] = s_best;
+}
+
+// K5: normalise active entries, carry inactive ones forward.
+__global__ void __launch_bounds__(128)
+s3_norm_kernel(int n_sen, int T, const uint8_t *__restrict__ flags, const int32_t *__restrict__ raw,
+               const int32_t *__restrict__ best, int32_t *__restrict__ prev, int32_t *__restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sen) return;
+    int32_t p = prev[s];
+    for (int t = 0; t < T; ++t) {
+        if (flags[(size_t)t * n_sen + s]) p = raw[(size_t)t * n_sen + s] - best[t];
+        out[(size_t)t * n_sen + s] = p;
+    }
+    prev[s] = p;
+}
+
+int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+struct b200_s3mgau {
+    int device = 0;
+    int n_sen = 0, n_ci = 0, max_comp = 0, veclen = 0, cp = 1, kc = 1, cpt = 1;
+    double logbase = 0, distfloor = 0, f = 0;
+    int32_t ci_pbeam = 0; int max_cd = 100000, ds_ratio = 1; float tighten = 0.5f;
+    LogMath *lm = nullptr;
+    // host copies (reference layout, padded to max_comp) for b200_s3_params
+    std::vector<int32_t> h_ncomp, h_mixw, h_cd2ci;
+    std::vector<float> h_mean, h_var, h_lrd;
+    // device
+    float *d_mean = nullptr, *d_lrd = nullptr; double *d_var = nullptr;
+    int32_t *d_mixw = nullptr, *d_ncomp = nullptr, *d_cd2ci = nullptr;
+    uint16_t *d_tab16 = nullptr; uint32_t *d_tab32 = nullptr;
+    int32_t *d_bstidx = nullptr, *d_update = nullptr, *d_prev = nullptr;
+    // scratch (chunk of frames)
+    size_t capT = 0;
+    float *d_feat = nullptr; uint8_t *d_act = nullptr, *d_flags = nullptr;
+    int32_t *d_raw = nullptr, *d_out = nullptr, *d_beam = nullptr, *d_best = nullptr; int16_t *d_bst = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    float last_ms = 0.f;
+    S3Dev dev() const {
+        S3Dev g{};
+        g.n_sen = n_sen; g.n_ci = n_ci; g.veclen = veclen; g.cpt = cpt;
+        g.mean = d_mean; g.var = d_var; g.lrd = d_lrd; g.mixw = d_mixw; g.ncomp = d_ncomp; g.cd2ci = d_cd2ci;
+        g.tab16 = d_tab16; g.tab32 = d_tab32; g.tab_size = (uint32_t)lm->table.size();
+        g.lzero = lm->zero; g.distfloor = distfloor; g.f = f;
+        return g;
+    }
+};
+
+namespace {
+
+constexpr int kChunkT = 2048;
+
+int s3_reserve(b200_s3mgau *m, int T) {
+    if ((size_t)T <= m->capT) return B200_OK;
+    void *ptrs[] = {m->d_feat, m->d_act, m->d_flags, m->d_raw, m->d_out, m->d_beam, m->d_best, m->d_bst};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    m->d_feat = nullptr; m->d_act = m->d_flags = nullptr; m->d_raw = m->d_out = m->d_beam = m->d_best = nullptr; m->d_bst = nullptr;
+    m->capT = 0;
+    const size_t S = m->n_sen, t = T;
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_feat, t * m->veclen * sizeof(float)));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_act, t * S));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_flags, t * S));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_raw, t * S * sizeof(int32_t)));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_out, t * S * sizeof(int32_t)));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_bst, t * S * sizeof(int16_t)));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_beam, t * sizeof(int32_t)));
+    B200_CUDA_OK(cudaMalloc((void **)&m->d_best, t * sizeof(int32_t)));
+    m->capT = T;
+    return B200_OK;
+}
+
+template <int CP, int KC>
+int launch_eval_t(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
+                  int32_t *raw, int16_t *bst, cudaStream_t st) {
+    if (s_hi <= s_lo || T <= 0) return B200_OK;
+    constexpr int G = kEvalThreads / CP;
+    dim3 grid((s_hi - s_lo + G - 1) / G, (T + kFB - 1) / kFB);
+    size_t smem = (size_t)kFB * m->veclen * sizeof(float);
+    s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int launch_eval(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
+                int32_t *raw, int16_t *bst, cudaStream_t st) {
+    switch (m->cp * 8 + m->kc) {
+    case 1 * 8 + 1: return launch_eval_t<1, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 2 * 8 + 1: return launch_eval_t<2, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 4 * 8 + 1: return launch_eval_t<4, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 8 * 8 + 1: return launch_eval_t<8, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 16 * 8 + 1: return launch_eval_t<16, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 32 * 8 + 1: return launch_eval_t<32, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 32 * 8 + 2: return launch_eval_t<32, 2>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 32 * 8 + 4: return launch_eval_t<32, 4>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    }
+    set_error("unsupported component count");
+    return B200_ERR_UNSUP;
+}
+
+// One chunk, everything device-resident.  d_act may be null (all active).
+int s3_chunk_dev(b200_s3mgau *m, const float *d_feat, int T, int frame0, uint8_t *d_act, int32_t *d_out,
+                 int32_t *d_best, cudaStream_t st) {
+    const S3Dev g = m->dev();
+    int rc;
+    if ((rc = launch_eval(m, d_feat, T, 0, m->n_ci, nullptr, m->d_raw, m->d_bst, st))) return rc;
+    s3_decide_kernel<<<T, 256, (size_t)3 * std::max(m->n_ci, 1) * sizeof(int32_t), st>>>(
+        g, T, frame0, m->ci_pbeam, m->max_cd, m->ds_ratio, m->tighten, m->d_raw, d_act, m->d_flags, m->d_beam);
+    B200_LAUNCH_CHECK();
+    if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st))) return rc;
+    const int n_cd = m->n_sen - m->n_ci;
+    if (n_cd > 0) {
+        s3_time_kernel<<<(n_cd + 127) / 128, 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags, m->d_raw,
+                                                           m->d_bst, m->d_bstidx, m->d_update);
+        B200_LAUNCH_CHECK();
+    }
+    if (m->n_ci > 0) {
+        s3_ci_state_kernel<<<(m->n_ci + 127) / 128, 128, 0, st>>>(g, T, frame0, m->d_bst, m->d_bstidx, m->d_update);
+        B200_LAUNCH_CHECK();
+    }
+    s3_best_kernel<<<T, 256, 0, st>>>(m->n_sen, m->d_flags, m->d_raw, d_best);
+    B200_LAUNCH_CHECK();
+    s3_norm_kernel<<<(m->n_sen + 127) / 128, 128, 0, st>>>(m->n_sen, T, m->d_flags, m->d_raw, d_best, m->d_prev, d_out);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+b200_s3mgau_t *b200_s3_create(int n_sen, int n_comp, int veclen, const float *mean, const float *var,
+                              const float *mixw, double varfloor, double mixwfloor, double logbase,
+                              const int32_t *cd2cisen, int n_ci_sen, int device) {
+    if (!mean || !var || !mixw || !cd2cisen || n_sen <= 0 || n_comp <= 0 || veclen <= 0 || n_ci_sen < 0 ||
+        n_ci_sen > n_sen) { set_error("b200_s3_create: bad argument"); return nullptr; }
+    if (n_comp > 128) { set_error("more than 128 components per senone is not supported"); return nullptr; }
+    if (n_ci_sen > 4096) { set_error("more than 4096 CI senones is not supported"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libb200sphinx has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { set_error("bad device %d", device); return nullptr; }
+    b200_s3mgau *m = new (std::nothrow) b200_s3mgau();
+    if (!m) return nullptr;
+    m->device = device; m->n_sen = n_sen; m->n_ci = n_ci_sen; m->max_comp = n_comp; m->veclen = veclen;
+    m->logbase = logbase;
+    m->lm = new LogMath(logbase, 0, true);
+    const size_t S = n_sen, M = n_comp, D = veclen;
+    m->h_mean.assign(mean, mean + S * M * D); m->h_var.assign(var, var + S * M * D);
+    m->h_lrd.assign(S * M, 0.f); m->h_mixw.assign(S * M, 0); m->h_ncomp.assign(S, 0);
+    m->h_cd2ci.assign(cd2cisen, cd2cisen + S);
+    // ---- mgau_mixw_read (cont_mgau.c:624-668): floor non-zero, normalise, logs3
+    std::vector<float> pdf(M);
+    for (size_t s = 0; s < S; ++s) {
+        std::copy(mixw + s * M, mixw + (s + 1) * M, pdf.begin());
+        bool zero = true;
+        for (size_t c = 0; c < M; ++c) if (pdf[c] != 0.0f) { zero = false; break; }
+        if (zero) { for (size_t c = 0; c < M; ++c) m->h_mixw[s * M + c] = kS3Zero; continue; }
+        for (size_t c = 0; c < M; ++c) if (pdf[c] != 0.0 && pdf[c] < mixwfloor) pdf[c] = (float)mixwfloor;
+        double sum = 0.0;
+        for (size_t c = 0; c < M; ++c) sum += pdf[c];
+        if (sum != 0.0) { double f = 1.0 / sum; for (size_t c = 0; c < M; ++c) pdf[c] = (float)((double)pdf[c] * f); }
+        for (size_t c = 0; c < M; ++c)
+            m->h_mixw[s * M + c] = (pdf[c] != 0.0 && pdf[c] > 0.0) ? m->lm->log(pdf[c]) : kS3Zero;
+    }
+    // ---- mgau_uninit_compact (:700-790), mgau_var_floor (:798-825), mgau_precomp (:852-894)
+    auto is_nan = [&](const float *v) { for (size_t i = 0; i < D; ++i) if (std::isnan(v[i])) return true; return false; };
+    auto is_zero = [&](const float *v) { for (size_t i = 0; i < D; ++i) if (v[i] != 0.0f) return false; return true; };
+    for (size_t s = 0; s < S; ++s) {
+        size_t c2 = 0;
+        for (size_t c = 0; c < M; ++c) {
+            float *mu = &m->h_mean[(s * M + c) * D], *va = &m->h_var[(s * M + c) * D];
+            if (is_nan(mu) || is_nan(va) || is_zero(va)) continue;
+            if (c2 != c) {
+                std::memcpy(&m->h_mean[(s * M + c2) * D], mu, D * sizeof(float));
+                std::memcpy(&m->h_var[(s * M + c2) * D], va, D * sizeof(float));
+                m->h_mixw[s * M + c2] = m->h_mixw[s * M + c];
+            }
+            ++c2;
+        }
+        m->h_ncomp[s] = (int32_t)c2;
+        for (size_t c = 0; c < c2; ++c) {
+            float *va = &m->h_var[(s * M + c) * D];
+            double lrd = 0.0;
+            if (varfloor > 0.0) for (size_t i = 0; i < D; ++i) if (va[i] < varfloor) va[i] = (float)varfloor;
+            for (size_t i = 0; i < D; ++i) {
+                lrd += std::log((double)va[i]);
+                va[i] = (float)(1.0 / (va[i] * 2.0));
+            }
+            lrd += (double)veclen * std::log(2.0 * M_PI);
+            m->h_lrd[s * M + c] = (float)(-0.5 * lrd);
+        }
+    }
+    m->distfloor = (double)kS3Zero * m->lm->log_of_base;   // logmath_log_to_ln
+    m->f = 1.0 / std::log(logbase);
+    m->ci_pbeam = m->lm->log(1e-80);
+    // ---- device layout: components innermost, padded to cp*kc
+    m->cp = std::min(32, pow2ceil(n_comp));
+    m->kc = n_comp <= 32 ? 1 : (n_comp <= 64 ? 2 : 4);
+    m->cpt = m->cp * m->kc;
+    const size_t CPT = m->cpt;
+    std::vector<float> t_mean(S * D * CPT, 0.f), t_lrd(S * CPT, 0.f);
+    std::vector<double> t_var(S * D * CPT, 0.0);
+    std::vector<int32_t> t_mixw(S * CPT, kS3Zero);
+    for (size_t s = 0; s < S; ++s)
+        for (size_t c = 0; c < (size_t)m->h_ncomp[s]; ++c) {
+            for (size_t i = 0; i < D; ++i) {
+                t_mean[(s * D + i) * CPT + c] = m->h_mean[(s * M + c) * D + i];
+                t_var[(s * D + i) * CPT + c] = (double)m->h_var[(s * M + c) * D + i];
+            }
+            t_lrd[s * CPT + c] = m->h_lrd[s * M + c];
+            t_mixw[s * CPT + c] = m->h_mixw[s * M + c];
+        }
+    auto up = [&](void **dst, const void *src, size_t bytes) {
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    bool ok = up((void **)&m->d_mean, t_mean.data(), t_mean.size() * sizeof(float)) &&
+              up((void **)&m->d_var, t_var.data(), t_var.size() * sizeof(double)) &&
+              up((void **)&m->d_lrd, t_lrd.data(), t_lrd.size() * sizeof(float)) &&
+              up((void **)&m->d_mixw, t_mixw.data(), t_mixw.size() * sizeof(int32_t)) &&
+              up((void **)&m->d_ncomp, m->h_ncomp.data(), S * sizeof(int32_t)) &&
+              up((void **)&m->d_cd2ci, m->h_cd2ci.data(), S * sizeof(int32_t));
+    if (ok) {
+        if (m->lm->width <= 2) {
+            std::vector<uint16_t> t16(m->lm->table.begin(), m->lm->table.end());
+            ok = up((void **)&m->d_tab16, t16.data(), t16.size() * sizeof(uint16_t));
+        } else {
+            ok = up((void **)&m->d_tab32, m->lm->table.data(), m->lm->table.size() * sizeof(uint32_t));
+        }
+    }
+    ok = ok && cudaMalloc((void **)&m->d_bstidx, S * 4) == cudaSuccess && cudaMalloc((void **)&m->d_update, S * 4) == cudaSuccess &&
+         cudaMalloc((void **)&m->d_prev, S * 4) == cudaSuccess && cudaMemset(m->d_prev, 0, S * 4) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreate(&m->ev[0]) == cudaSuccess && cudaEventCreate(&m->ev[1]) == cudaSuccess;
+    if (!ok) { set_error("b200_s3_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError())); b200_s3_free(m); return nullptr; }
+    if (b200_s3_utt_reset(m) != B200_OK) { b200_s3_free(m); return nullptr; }
+    return m;
+}
+
+b200_s3mgau_t *b200_s3_load(const char *meanfile, const char *varfile, const char *mixwfile, double varfloor,
+                            double mixwfloor, double logbase, const int32_t *cd2cisen, int n_ci_sen, int device) {
+    int32_t dm[4], dv[4], dw[4], vl[64];
+    if (b200_s3_read_gauden(meanfile, dm, vl, nullptr) || b200_s3_read_gauden(varfile, dv, vl, nullptr) ||
+        b200_s3_read_mixw(mixwfile, dw, nullptr)) return nullptr;
+    if (dm[1] != 1) { set_error("#Features streams(%d) != 1 in continuous HMM", dm[1]); return nullptr; }   // cont_mgau.c:561-565
+    if (dm[0] != dv[0] || dm[2] != dv[2] || dm[3] != dv[3]) { set_error("means/variances dimensions differ (full covariances are not supported)"); return nullptr; }
+    if (dw[0] != dm[0] || dw[1] != 1 || dw[2] != dm[2]) { set_error("mixture weights do not match the Gaussians"); return nullptr; }
+    std::vector<float> mean(dm[3]), var(dv[3]), mixw(dw[3]);
+    if (b200_s3_read_gauden(meanfile, dm, vl, mean.data()) || b200_s3_read_gauden(varfile, dv, vl, var.data()) ||
+        b200_s3_read_mixw(mixwfile, dw, mixw.data())) return nullptr;
+    return b200_s3_create(dm[0], dm[2], vl[0], mean.data(), var.data(), mixw.data(), varfloor, mixwfloor, logbase,
+                          cd2cisen, n_ci_sen, device);
+}
+
+void b200_s3_free(b200_s3mgau_t *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    void *ptrs[] = {m->d_mean, m->d_var, m->d_lrd, m->d_mixw, m->d_ncomp, m->d_cd2ci, m->d_tab16, m->d_tab32, m->d_bstidx,
+                    m->d_update, m->d_prev, m->d_feat, m->d_act, m->d_flags, m->d_raw, m->d_out, m->d_beam, m->d_best, m->d_bst};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (m->st) cudaStreamDestroy(m->st);
+    for (auto &e : m->ev) if (e) cudaEventDestroy(e);
+    delete m->lm;
+    delete m;
+}
+
+int b200_s3_dims(const b200_s3mgau_t *m, int32_t dims[5]) {
+    if (!m || !dims) { set_error("null argument"); return B200_ERR_ARG; }
+    dims[0] = m->n_sen; dims[1] = m->max_comp; dims[2] = m->veclen; dims[3] = m->n_ci; dims[4] = m->ci_pbeam;
+    return B200_OK;
+}
+
+int b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio, float tighten_factor) {
+    if (!m || ds_ratio < 1) { set_error("b200_s3_set_fast: bad argument"); return B200_ERR_ARG; }
+    m->ci_pbeam = ci_pbeam <= 0.0 ? kS3Zero : m->lm->log(ci_pbeam);   // logs3(), S3/libcommon/logs3.c:110-118
+    m->max_cd = max_cd; m->ds_ratio = ds_ratio; m->tighten = tighten_factor;
+    return B200_OK;
+}
+
+int b200_s3_utt_reset(b200_s3mgau_t *m) {
+    if (!m) { set_error("null argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    std::vector<int32_t> a(m->n_sen, kNoBst), b(m->n_sen, kNotUpdated);
+    B200_CUDA_OK(cudaMemcpy(m->d_bstidx, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(m->d_update, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+int b200_s3_params(const b200_s3mgau_t *m, int32_t *n_comp, float *mean, float *var, float *lrd, int32_t *mixw,
+                   double scal[2]) {
+    if (!m) { set_error("null argument"); return B200_ERR_ARG; }
+    if (n_comp) std::copy(m->h_ncomp.begin(), m->h_ncomp.end(), n_comp);
+    if (mean) std::copy(m->h_mean.begin(), m->h_mean.end(), mean);
+    if (var) std::copy(m->h_var.begin(), m->h_var.end(), var);
+    if (lrd) std::copy(m->h_lrd.begin(), m->h_lrd.end(), lrd);
+    if (mixw) std::copy(m->h_mixw.begin(), m->h_mixw.end(), mixw);
+    if (scal) { scal[0] = m->distfloor; scal[1] = m->f; }
+    return B200_OK;
+}
+
+int b200_s3_state(b200_s3mgau_t *m, int32_t *bstidx, int32_t *updatetime) {
+    if (!m || !bstidx || !updatetime) { set_error("null argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    B200_CUDA_OK(cudaMemcpy(bstidx, m->d_bstidx, (size_t)m->n_sen * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_OK(cudaMemcpy(updatetime, m->d_update, (size_t)m->n_sen * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_s3_dense_dev(b200_s3mgau_t *m, const float *d_feat, int T, int32_t *d_out, void *stream) {
+    if (!m || !d_feat || !d_out || T < 0) { set_error("b200_s3_dense_dev: bad argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->st;
+    B200_CUDA_OK(cudaEventRecord(m->ev[0], st));
+    int rc = launch_eval(m, d_feat, T, 0, m->n_sen, nullptr, d_out, nullptr, st);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaEventRecord(m->ev[1], st));
+    return B200_OK;
+}
+
+int b200_s3_dense_host(b200_s3mgau_t *m, const float *feat, int T, int32_t *out) {
+    if (!m || !feat || !out || T < 0) { set_error("b200_s3_dense_host: bad argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    for (int t0 = 0; t0 < T; t0 += kChunkT) {
+        const int n = std::min(kChunkT, T - t0);
+        int rc = s3_reserve(m, n);
+        if (rc) return rc;
+        B200_CUDA_OK(cudaMemcpyAsync(m->d_feat, feat + (size_t)t0 * m->veclen, (size_t)n * m->veclen * 4, cudaMemcpyHostToDevice, m->st));
+        if ((rc = b200_s3_dense_dev(m, m->d_feat, n, m->d_out, m->st))) return rc;
+        B200_CUDA_OK(cudaMemcpyAsync(out + (size_t)t0 * m->n_sen, m->d_out, (size_t)n * m->n_sen * 4, cudaMemcpyDeviceToHost, m->st));
+        B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    }
+    return B200_OK;
+}
+
+int b200_s3_score_utt_dev(b200_s3mgau_t *m, const float *d_feat, int T, int frame0, uint8_t *d_sen_active,
+                          int32_t *d_out, int32_t *d_best, void *stream) {
+    if (!m || !d_feat || !d_out || !d_best || T < 0) { set_error("b200_s3_score_utt_dev: bad argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->st;
+    B200_CUDA_OK(cudaEventRecord(m->ev[0], st));
+    for (int t0 = 0; t0 < T; t0 += kChunkT) {
+        const int n = std::min(kChunkT, T - t0);
+        int rc = s3_reserve(m, n);
+        if (rc) return rc;
+        rc = s3_chunk_dev(m, d_feat + (size_t)t0 * m->veclen, n, frame0 + t0,
+                          d_sen_active ? d_sen_active + (size_t)t0 * m->n_sen : nullptr,
+                          d_out + (size_t)t0 * m->n_sen, d_best + t0, st);
+        if (rc) return rc;
+    }
+    B200_CUDA_OK(cudaEventRecord(m->ev[1], st));
+    return B200_OK;
+}
+
+int b200_s3_score_utt_host(b200_s3mgau_t *m, const float *feat, int T, int frame0, uint8_t *sen_active,
+                           int32_t *senscr_io, int32_t *out, int32_t *best) {
+    if (!m || !feat || !out || !best || T < 0) { set_error("b200_s3_score_utt_host: bad argument"); return B200_ERR_ARG; }
+    cudaSetDevice(m->device);
+    const size_t S = m->n_sen;
+    if (senscr_io) B200_CUDA_OK(cudaMemcpyAsync(m->d_prev, senscr_io, S * 4, cudaMemcpyHostToDevice, m->st));
+    for (int t0 = 0; t0 < T; t0 += kChunkT) {
+        const int n = std::min(kChunkT, T - t0);
+        int rc = s3_reserve(m, n);
+        if (rc) return rc;
+        B200_CUDA_OK(cudaMemcpyAsync(m->d_feat, feat + (size_t)t0 * m->veclen, (size_t)n * m->veclen * 4, cudaMemcpyHostToDevice, m->st));
+        if (sen_active)
+            B200_CUDA_OK(cudaMemcpyAsync(m->d_act, sen_active + (size_t)t0 * S, (size_t)n * S, cudaMemcpyHostToDevice, m->st));
+        if ((rc = s3_chunk_dev(m, m->d_feat, n, frame0 + t0, sen_active ? m->d_act : nullptr, m->d_out, m->d_best, m->st))) return rc;
+        B200_CUDA_OK(cudaMemcpyAsync(out + (size_t)t0 * S, m->d_out, (size_t)n * S * 4, cudaMemcpyDeviceToHost, m->st));
+        B200_CUDA_OK(cudaMemcpyAsync(best + t0, m->d_best, (size_t)n * 4, cudaMemcpyDeviceToHost, m->st));
+        if (sen_active)
+            B200_CUDA_OK(cudaMemcpyAsync(sen_active + (size_t)t0 * S, m->d_act, (size_t)n * S, cudaMemcpyDeviceToHost, m->st));
+        B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    }
+    if (senscr_io) {
+        B200_CUDA_OK(cudaMemcpyAsync(senscr_io, m->d_prev, S * 4, cudaMemcpyDeviceToHost, m->st));
+        B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    }
+    return B200_OK;
+}
+
+int b200_s3_frame_eval(b200_s3mgau_t *m, const float *feat, int32_t frame, uint8_t *sen_active, int32_t *senscr,
+                       int32_t *best) {
+    if (!m || !feat || !sen_active || !senscr || !best) { set_error("b200_s3_frame_eval: null argument"); return B200_ERR_ARG; }
+    std::vector<int32_t> row(m->n_sen);
+    int rc = b200_s3_score_utt_host(m, feat, 1, frame, sen_active, senscr, row.data(), best);
+    return rc;
+}
+
+float b200_s3_last_ms(b200_s3mgau_t *m) {
+    if (!m) return -1.f;
+    float ms = 0.f;
+    if (cudaEventSynchronize(m->ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) != cudaSuccess) return -1.f;
+    m->last_ms = ms;
+    return ms;
+}
+
+}  // extern "C"

@@ -450,3 +450,96 @@ class HmmContext:
 
     def last_ms(self) -> float:
         return lib.b200_hmm_last_ms(self._h)
+
+
+# ------------------------------------------------------------ sphinx3 GMM
+S3_LOGBASE = float(np.float32(1.0003))   # sphinx3 -logbase default (float32 option, cmdln_macro.h:246)
+
+
+class S3Mgau:
+    """sphinx3's mgau_model_t + fast_gmm_t behind the C ABI (S3/libam/cont_mgau.c,
+    approx_cont_mgau.c).  Scores are int32, higher = better."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise B200Error(f"sphinx3 scorer: {_lib.last_error()}")
+        self.h = handle
+        d = (C.c_int32 * 5)()
+        check(lib.b200_s3_dims(self.h, d), "s3_dims")
+        self.n_sen, self.max_comp, self.veclen, self.n_ci_sen, self.ci_pbeam = (int(v) for v in d)
+
+    @classmethod
+    def from_arrays(cls, mean, var, mixw, cd2cisen, n_ci_sen, varfloor=1e-4, mixwfloor=1e-7, logbase=S3_LOGBASE,
+                    device=0):
+        mean, var, mixw = _c(mean, np.float32), _c(var, np.float32), _c(mixw, np.float32)
+        S, M, D = mean.shape
+        cd = _c(cd2cisen, np.int32)
+        return cls(lib.b200_s3_create(S, M, D, _p(mean, C.c_float), _p(var, C.c_float), _p(mixw, C.c_float),
+                                      varfloor, mixwfloor, logbase, _p(cd, C.c_int32), n_ci_sen, device))
+
+    @classmethod
+    def from_files(cls, meanfile, varfile, mixwfile, cd2cisen, n_ci_sen, varfloor=1e-4, mixwfloor=1e-7,
+                   logbase=S3_LOGBASE, device=0):
+        cd = _c(cd2cisen, np.int32)
+        return cls(lib.b200_s3_load(meanfile.encode(), varfile.encode(), mixwfile.encode(), varfloor, mixwfloor,
+                                    logbase, _p(cd, C.c_int32), n_ci_sen, device))
+
+    def set_fast(self, ci_pbeam=1e-80, max_cd=100000, ds_ratio=1, tighten=0.5):
+        check(lib.b200_s3_set_fast(self.h, ci_pbeam, max_cd, ds_ratio, tighten), "s3_set_fast")
+        d = (C.c_int32 * 5)()
+        lib.b200_s3_dims(self.h, d)
+        self.ci_pbeam = int(d[4])
+
+    def utt_reset(self):
+        check(lib.b200_s3_utt_reset(self.h), "s3_utt_reset")
+
+    def params(self):
+        S, M, D = self.n_sen, self.max_comp, self.veclen
+        nc = np.zeros(S, np.int32)
+        mean = np.zeros((S, M, D), np.float32); var = np.zeros((S, M, D), np.float32)
+        lrd = np.zeros((S, M), np.float32); mixw = np.zeros((S, M), np.int32); scal = np.zeros(2, np.float64)
+        check(lib.b200_s3_params(self.h, _p(nc, C.c_int32), _p(mean, C.c_float), _p(var, C.c_float),
+                                 _p(lrd, C.c_float), _p(mixw, C.c_int32), _p(scal, C.c_double)), "s3_params")
+        return nc, mean, var, lrd, mixw, scal
+
+    def state(self):
+        b = np.zeros(self.n_sen, np.int32); u = np.zeros(self.n_sen, np.int32)
+        check(lib.b200_s3_state(self.h, _p(b, C.c_int32), _p(u, C.c_int32)), "s3_state")
+        return b, u
+
+    def eval_dense(self, feat):
+        """mgau_eval(g, s, NULL, x, t, 1) for every frame and senone -> int32 [T][n_sen]."""
+        feat = _c(feat, np.float32)
+        out = np.zeros((feat.shape[0], self.n_sen), np.int32)
+        check(lib.b200_s3_dense_host(self.h, _p(feat, C.c_float), feat.shape[0], _p(out, C.c_int32)), "s3_dense")
+        return out
+
+    def eval_utt(self, feat, sen_active=None, frame0=0, senscr0=None):
+        """Per frame: CI pass + approx_cont_mgau_frame_eval.  -> (senscr [T][S], best [T], sen_active after)."""
+        feat = _c(feat, np.float32)
+        T = feat.shape[0]
+        act = None if sen_active is None else np.ascontiguousarray(sen_active, np.uint8).copy()
+        io = np.zeros(self.n_sen, np.int32) if senscr0 is None else _c(senscr0, np.int32).copy()
+        out = np.zeros((T, self.n_sen), np.int32)
+        best = np.zeros(T, np.int32)
+        check(lib.b200_s3_score_utt_host(self.h, _p(feat, C.c_float), T, frame0,
+                                         None if act is None else _p(act, C.c_uint8), _p(io, C.c_int32),
+                                         _p(out, C.c_int32), _p(best, C.c_int32)), "s3_score_utt")
+        self.last_row = io
+        return out, best, act
+
+    def frame_eval(self, x, frame, sen_active, senscr):
+        """In-place single-frame drop-in (gmm_compute_lv1 + lv2); returns best."""
+        x = _c(x, np.float32)
+        best = C.c_int32(0)
+        check(lib.b200_s3_frame_eval(self.h, _p(x, C.c_float), frame, _p(sen_active, C.c_uint8),
+                                     _p(senscr, C.c_int32), C.byref(best)), "s3_frame_eval")
+        return best.value
+
+    def last_ms(self):
+        return lib.b200_s3_last_ms(self.h)
+
+    def free(self):
+        if self.h:
+            lib.b200_s3_free(self.h)
+            self.h = None

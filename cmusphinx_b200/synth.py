@@ -107,7 +107,7 @@ def s3_model(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=77):
     par = cd2ci[n_ci_sen:]
     mean[n_ci_sen:] = mean[par] + rng.standard_normal((n_sen - n_ci_sen, n_density, dim)) * 0.4
     var[n_ci_sen:] = var[par] * np.exp(rng.uniform(-0.7, 0.3, (n_sen - n_ci_sen, n_density, dim)))
-    var[var < 2e-4] = 5e-5          # some values under the 1e-4 floor
+    var[rng.random(var.shape) < 0.002] = 5e-5          # some values under the 1e-4 floor
     mixw = rng.dirichlet(np.ones(n_density), n_sen).astype(np.float32) * 1000.0   # un-normalised counts
     mixw[mixw < 1e-3] = 0.0
     for s in rng.integers(n_ci_sen, n_sen, max(1, n_sen // 50)):   # uninitialised components

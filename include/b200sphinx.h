@@ -269,6 +269,81 @@ float b200_hmm_last_ms(const b200_hmmctx_t *c);
  * the reference's lossy >255 bridging.  Host utility; returns n written. */
 int  b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_out);
 
+/* ================================================= sphinx3 GMM scoring
+ * sphinx3's flavour of the path (S3/libam/approx_cont_mgau.c, cont_mgau.c):
+ * one mixture per senone, float64 Mahalanobis accumulation, int32 log scores
+ * (base -logbase, default 1.0003, unshifted; HIGHER = better), CI-senone beam
+ * with best-Gaussian / CI back-off, optional frame down-sampling.  Stands in
+ * for srch_funcs_t.gmm_compute_lv1 / gmm_compute_lv2 (sphinx3/include/srch.h:
+ * 590-612 -> S3/libsearch/gmm_wrap.c:80-214).  Diagonal covariances, no
+ * Gaussian-selection / sub-VQ shortlists.
+ */
+typedef struct b200_s3mgau b200_s3mgau_t;
+
+/* mgau_init(meanfile, varfile, varfloor, mixwfile, mixwfloor, precomp=1,
+ * ".cont.", MIX_INT_FLOAT_COMP, logmath) -- S3/libam/cont_mgau.c:900-958 --
+ * on arrays: mean/var [n_sen][n_comp][veclen] RAW values as stored in the
+ * files, mixw [n_sen][n_comp] raw counts.  Does mixw normalisation,
+ * mgau_uninit_compact, mgau_var_floor and mgau_precomp on the host exactly as
+ * the reference.  cd2cisen[n_sen] / n_ci_sen come from the mdef
+ * (sphinx3/include/mdef.h:188-201; CI senones first). */
+b200_s3mgau_t *b200_s3_create(int n_sen, int n_comp, int veclen, const float *mean,
+                              const float *var, const float *mixw, double varfloor,
+                              double mixwfloor, double logbase,
+                              const int32_t *cd2cisen, int n_ci_sen, int device);
+/* Same from the S3 binary files (mgau_file_read :160-400, mgau_mixw_read :480-680). */
+b200_s3mgau_t *b200_s3_load(const char *meanfile, const char *varfile,
+                            const char *mixwfile, double varfloor, double mixwfloor,
+                            double logbase, const int32_t *cd2cisen, int n_ci_sen,
+                            int device);
+void b200_s3_free(b200_s3mgau_t *m);           /* mgau_free */
+/* dims = {n_sen, max_comp, veclen, n_ci_sen, ci_pbeam (log)} */
+int  b200_s3_dims(const b200_s3mgau_t *m, int32_t dims[5]);
+/* fast_gmm_init (S3/libam/fast_algo_struct.c:420-467): -ci_pbeam (a
+ * probability), -maxcdsenpf, -ds, -tighten_factor. */
+int  b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio,
+                      float tighten_factor);
+/* per-utterance reset of bstidx / updatetime (S3/libsearch/srch_time_switch_tree.c:484-490) */
+int  b200_s3_utt_reset(b200_s3mgau_t *m);
+/* Host copies of the precomputed parameters in the reference's order, padded
+ * to max_comp: n_comp[n_sen], mean/var [n_sen][max_comp][veclen] (var =
+ * 1/(2 var)), lrd/mixw [n_sen][max_comp], scal = {distfloor, 1/ln(base)}.
+ * Any pointer may be NULL. */
+int  b200_s3_params(const b200_s3mgau_t *m, int32_t *n_comp, float *mean, float *var,
+                    float *lrd, int32_t *mixw, double scal[2]);
+/* mgau_t.bstidx / updatetime of every senone (cont_mgau.h:174-176) */
+int  b200_s3_state(b200_s3mgau_t *m, int32_t *bstidx, int32_t *updatetime);
+
+/* Dense scoring: out[t][s] = mgau_eval(g, s, NULL, feat[t], t, 1)
+ * (cont_mgau.c:1171-1205) for every senone, un-normalised.  [T][veclen] float32
+ * in, [T][n_sen] int32 out. */
+int  b200_s3_dense_host(b200_s3mgau_t *m, const float *feat, int T, int32_t *out);
+int  b200_s3_dense_dev(b200_s3mgau_t *m, const float *d_feat, int T, int32_t *d_out,
+                       void *stream);
+
+/* One utterance (or a run of T consecutive frames starting at frame number
+ * frame0): per frame approx_cont_mgau_ci_eval (approx_cont_mgau.c:368-431) then
+ * approx_cont_mgau_frame_eval (:433-616).  sen_active [T][n_sen] uint8 is
+ * ascr_t.sen_active per frame, in/out (CI entries are set to 1); NULL = every
+ * senone active.  senscr_io [n_sen] is ascr_t.senscr before the first frame /
+ * after the last one (entries of inactive senones keep their old value, as in
+ * the reference); NULL = continue from the handle's own copy.  out
+ * [T][n_sen] = ascr_t.senscr after each frame, best [T] = the return values
+ * (srch_t.senscale). */
+int  b200_s3_score_utt_host(b200_s3mgau_t *m, const float *feat, int T, int frame0,
+                            uint8_t *sen_active, int32_t *senscr_io, int32_t *out,
+                            int32_t *best);
+int  b200_s3_score_utt_dev(b200_s3mgau_t *m, const float *d_feat, int T, int frame0,
+                           uint8_t *d_sen_active, int32_t *d_out, int32_t *d_best,
+                           void *stream);
+/* Drop-in for one frame: s3_cd_gmm_compute_sen (gmm_wrap.c:103-171) with the
+ * CI pass of approx_ci_gmm_compute (:174-214) folded in.  senscr is updated in
+ * place; *best receives the return value of approx_cont_mgau_frame_eval. */
+int  b200_s3_frame_eval(b200_s3mgau_t *m, const float *feat, int32_t frame,
+                        uint8_t *sen_active, int32_t *senscr, int32_t *best);
+/* Device time of the last *_dev / score call in ms (CUDA events). */
+float b200_s3_last_ms(b200_s3mgau_t *m);
+
 /* -------------------------------------------------- device memory helpers
  * (so a non-torch host can keep buffers resident) */
 void *b200_dev_alloc(size_t bytes, int device);

@@ -151,6 +151,42 @@ def real_model(name, hmmdir, mfc, n_frames, senmgau="", topn=4):
     r.close()
 
 
+S3_CFGS = [
+    dict(ci_pbeam=1e-80, max_cd=100000, ds_ratio=1, tighten=0.5),
+    dict(ci_pbeam=1e-40, max_cd=100000, ds_ratio=1, tighten=0.5),
+    dict(ci_pbeam=1e-40, max_cd=60, ds_ratio=1, tighten=0.5),
+    dict(ci_pbeam=1e-30, max_cd=100000, ds_ratio=3, tighten=0.5),
+    dict(ci_pbeam=1e-40, max_cd=80, ds_ratio=2, tighten=0.3),
+]
+
+
+def s3_case(name="s3_synth.npz", T=40):
+    """sphinx3 flavour: the reference's mgau_init / mgau_eval /
+    approx_cont_mgau_frame_eval (oracle/_ref/libs3am.so via ref_shim_s3.c) on
+    the seeded synthetic CI/CD model of synth.s3_model()."""
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=160, n_ci_sen=16)
+    D = mean.shape[2]
+    feat = synth.s3_features(mean, var, T)
+    act = synth.s3_active(mean.shape[0], n_ci, T)
+    stale0 = (np.arange(mean.shape[0]) * 7 - 1000).astype(np.int32)
+    with tempfile.TemporaryDirectory() as d:
+        mf, vf, wf = (os.path.join(d, n) for n in ("means", "variances", "mixture_weights"))
+        s3io.write_gauden(mf, mean, [D]); s3io.write_gauden(vf, var, [D]); s3io.write_mixw(wf, mixw[:, None, :])
+        r = orc.RefS3(mf, vf, wf, None, cd2ci, n_ci)
+    nc, pm, pv, lrd, pw, scal = r.params()
+    dense = r.eval_dense(feat)
+    out = {}
+    for i, cfg in enumerate(S3_CFGS):
+        r.set_fast(**cfg); r.utt_reset()
+        o, best, a = r.eval_utt(feat, act, 3, stale0)
+        bi, ut = r.state()
+        out.update({f"scr{i}": o, f"best{i}": best, f"act{i}": a, f"bstidx{i}": bi, f"upd{i}": ut})
+    save(name, mean=mean, var=var, mixw=mixw, cd2ci=cd2ci, n_ci=n_ci, feat=feat, act=act, stale0=stale0, frame0=3,
+         n_comp=nc, p_var_head=pv[:20], p_lrd=lrd, p_mixw=pw, scal=scal, dense=dense, ci_pbeam_default=r.ci_pbeam,
+         cfgs=np.array([[c["ci_pbeam"], c["max_cd"], c["ds_ratio"], c["tighten"]] for c in S3_CFGS]), **out)
+    r.free()
+
+
 if __name__ == "__main__":
     assert orc.have_ref(), "build oracle/_ref first: make -C oracle ref"
     logmath()
@@ -163,3 +199,4 @@ if __name__ == "__main__":
     real_model("ptm_hub4wsj.npz", "ptm", "wsj/442c0201.mfc", 16)
     real_model("cont_hub4_topn4.npz", "cont", "pittsburgh.littleendian.mfc", 20, ".cont.", 4)
     real_model("cont_hub4_topn8.npz", "cont", "pittsburgh.littleendian.mfc", 12, ".cont.", 8)
+    s3_case()

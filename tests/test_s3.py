@@ -1,0 +1,162 @@
+"""sphinx3 flavour of the path (approx_cont_mgau_frame_eval, S3/libam):
+ * CPU: the oracle port against the committed golden vectors generated from the
+   reference (tests/golden/s3_synth.npz, made by make_golden.py:s3_case);
+ * GPU (-m gpu): the CUDA path through the C ABI against the goldens and
+   against the oracle on fresh seeded inputs -- bit-exact (int32 scores)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import orc
+import cmusphinx_b200 as b
+from cmusphinx_b200 import synth
+
+
+def _cfgs(g):
+    return [dict(ci_pbeam=float(c[0]), max_cd=int(c[1]), ds_ratio=int(c[2]), tighten=float(c[3])) for c in g["cfgs"]]
+
+
+def _check_golden(model, g, state=True):
+    n_ci = int(g["n_ci"])
+    for i, cfg in enumerate(_cfgs(g)):
+        model.set_fast(**cfg); model.utt_reset()
+        o, best, a = model.eval_utt(g["feat"], g["act"], int(g["frame0"]), g["stale0"])
+        np.testing.assert_array_equal(best, g[f"best{i}"], err_msg=f"cfg {i}")
+        np.testing.assert_array_equal(o, g[f"scr{i}"], err_msg=f"cfg {i}")
+        np.testing.assert_array_equal(a, g[f"act{i}"])
+        if state:
+            bi, ut = model.state()
+            np.testing.assert_array_equal(bi, g[f"bstidx{i}"]); np.testing.assert_array_equal(ut, g[f"upd{i}"])
+    assert (g["scr1"] != g["scr0"]).mean() > 0.05      # the beam really pruned something
+    assert n_ci > 0
+
+
+def _check_params(model, g):
+    nc, mean, var, lrd, mixw, scal = model.params()
+    np.testing.assert_array_equal(nc, g["n_comp"])
+    valid = np.arange(lrd.shape[1])[None, :] < nc[:, None]
+    np.testing.assert_array_equal(lrd[valid], g["p_lrd"][valid])
+    np.testing.assert_array_equal(mixw[valid], g["p_mixw"][valid])
+    np.testing.assert_array_equal(var[:20][valid[:20]], g["p_var_head"][valid[:20]])
+    np.testing.assert_array_equal(scal, g["scal"])
+
+
+def test_s3_port_matches_golden():
+    g = cases.load("s3_synth.npz")
+    p = orc.PortS3(g["mean"], g["var"], g["mixw"], g["cd2ci"], int(g["n_ci"]))
+    assert orc.port.orc_s3_ci_pbeam(p.h) == int(g["ci_pbeam_default"])
+    _check_params(p, g)
+    _check_golden(p, g)
+    p.free()
+
+
+def test_s3_without_gpu_fails_loudly():
+    if b.device_count() > 0:
+        pytest.skip("GPU present")
+    g = cases.load("s3_synth.npz")
+    with pytest.raises(b.B200Error, match="no CUDA device"):
+        b.S3Mgau.from_arrays(g["mean"], g["var"], g["mixw"], g["cd2ci"], int(g["n_ci"]))
+
+
+# ------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_s3_gpu_matches_golden():
+    g = cases.load("s3_synth.npz")
+    m = b.S3Mgau.from_arrays(g["mean"], g["var"], g["mixw"], g["cd2ci"], int(g["n_ci"]))
+    assert m.ci_pbeam == int(g["ci_pbeam_default"])
+    _check_params(m, g)
+    np.testing.assert_array_equal(m.eval_dense(g["feat"]), g["dense"])
+    _check_golden(m, g)
+    m.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [
+    dict(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=1),
+    dict(n_sen=300, n_ci_sen=21, n_density=5, dim=13, seed=2),     # odd component count (tail of mgau_eval_all)
+    dict(n_sen=200, n_ci_sen=12, n_density=32, dim=39, seed=3),
+    dict(n_sen=150, n_ci_sen=9, n_density=40, dim=25, seed=4),     # > 32 components: two rounds per lane
+    dict(n_sen=97, n_ci_sen=7, n_density=1, dim=39, seed=5),
+])
+def test_s3_gpu_matches_oracle(shape):
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(**shape)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    T = 75
+    feat = synth.s3_features(mean, var, T, seed=shape["seed"] + 100)
+    act = synth.s3_active(mean.shape[0], n_ci, T, seed=shape["seed"] + 200)
+    # dense mgau_eval over every senone
+    want = np.zeros((T, mean.shape[0]), np.int32)
+    for t in range(T):
+        for s in range(mean.shape[0]):
+            want[t, s] = orc.port.orc_s3_mgau_eval(p.h, s, None, orc._p(feat[t], orc.C.c_float), t, 1)
+    np.testing.assert_array_equal(m.eval_dense(feat), want)
+    # pick beams from the spread of the CI scores of this model
+    ci = want[:, :n_ci]
+    spread = float(np.median(ci.max(1) - np.median(ci, 1)))
+    beam = float(np.float32(1.0003)) ** (-spread)
+    for cfg in (dict(), dict(ci_pbeam=beam), dict(ci_pbeam=beam, max_cd=max(4, mean.shape[0] // 12)),
+                dict(ci_pbeam=beam, ds_ratio=3), dict(ci_pbeam=beam * 1e-3, max_cd=mean.shape[0] // 8, ds_ratio=2, tighten=0.4)):
+        for active in (act, None):
+            p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+            a, c = p.eval_utt(feat, active, 2), m.eval_utt(feat, active, 2)
+            np.testing.assert_array_equal(c[1], a[1], err_msg=str(cfg))
+            np.testing.assert_array_equal(c[0], a[0], err_msg=str(cfg))
+            if active is not None:
+                np.testing.assert_array_equal(c[2], a[2])
+            np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()))
+    p.free(); m.free()
+
+
+@pytest.mark.gpu
+def test_s3_gpu_frame_by_frame_equals_batched():
+    """The per-frame drop-in (gmm_compute_lv1+lv2) carries the same state as
+    the batched call, also across a chunk boundary."""
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=200, n_ci_sen=12, seed=9)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    T = 30
+    feat = synth.s3_features(mean, var, T, seed=10)
+    act = synth.s3_active(mean.shape[0], n_ci, T, seed=11)
+    cfg = dict(ci_pbeam=1e-35, ds_ratio=2)
+    p.set_fast(**cfg); m.set_fast(**cfg)
+    want, wbest, wact = p.eval_utt(feat, act)
+    senscr = np.zeros(mean.shape[0], np.int32)
+    for t in range(T):
+        a = act[t].copy()
+        best = m.frame_eval(feat[t], t, a, senscr)
+        assert best == wbest[t]
+        np.testing.assert_array_equal(senscr, want[t]); np.testing.assert_array_equal(a, wact[t])
+    # two halves with the handle's own score buffer == one call
+    m.utt_reset()
+    o1 = m.eval_utt(feat[:17], act[:17], 0)
+    o2 = m.eval_utt(feat[17:], act[17:], 17, senscr0=m.last_row)
+    np.testing.assert_array_equal(np.concatenate([o1[0], o2[0]]), want)
+    p.free(); m.free()
+
+
+@pytest.mark.gpu
+def test_s3_gpu_real_model():
+    """hub4_cd_continuous_8gau_1s_c_d_dd through the file loader; oracle as checker."""
+    d = os.path.join(orc.DATA_DIR, "hmm", "cont")
+    mf, vf, wf = (os.path.join(d, n) for n in ("means", "variances", "mixture_weights"))
+    if not os.path.exists(mf):
+        pytest.skip("continuous model not bundled")
+    mean, var, mixw = b.read_s3_cont_arrays(mf, vf, wf)
+    S = mean.shape[0]
+    n_ci = 144                                   # 48 CI phones x 3 states
+    rng = np.random.default_rng(4)
+    cd2ci = np.arange(S, dtype=np.int32); cd2ci[n_ci:] = rng.integers(0, n_ci, S - n_ci)
+    m = b.S3Mgau.from_files(mf, vf, wf, cd2ci, n_ci)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    T = 40
+    idx = rng.integers(0, S, T)
+    feat = (mean[idx, 0] + rng.standard_normal((T, mean.shape[2])) * np.sqrt(var[idx, 0])).astype(np.float32)
+    act = synth.s3_active(S, n_ci, T, seed=6)
+    for cfg in (dict(), dict(ci_pbeam=1e-40), dict(ci_pbeam=1e-40, max_cd=400)):
+        p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+        a, c = p.eval_utt(feat, act), m.eval_utt(feat, act)
+        np.testing.assert_array_equal(c[1], a[1]); np.testing.assert_array_equal(c[0], a[0])
+    p.free(); m.free()
