@@ -20,8 +20,9 @@
 //   K2 s3_decide_kernel (block per frame)         -> CI best, (dynamic) beam,
 //                                                    per (t,s) flag {0 inactive,1 full,2 back-off}
 //   K1 s3_eval_kernel   (CD senones, flagged)     -> raw scores + best component
-//   K3 s3_time_kernel   (thread per CD senone, sequential in t): best-index /
-//                        update-time state machine, CI or best-Gaussian back-off
+//   K3 s3_backoff_kernel (thread per (t, CD senone)): best-index / update-time
+//                        state resolved by a bounded walk back over the flags, CI or
+//                        best-Gaussian back-off; s3_state_kernel: state after the chunk
 //   K4 s3_best_kernel   (block per frame)         -> frame best over active
 //   K5 s3_norm_kernel   (thread per senone, sequential in t): subtract best on
 //                        active entries, carry stale entries forward
@@ -44,6 +45,7 @@ constexpr int kNoBst = -1;                         // cont_mgau.h:134
 constexpr int kNotUpdated = -100;                  // cont_mgau.h:135
 constexpr int kFB = 32;                            // frames per block in K1
 constexpr int kEvalThreads = 128;
+constexpr int kFR = 8;                             // frames sharing one parameter pass in K1
 
 struct S3Dev {
     int n_sen, n_ci, veclen, cpt;   // cpt = padded components per senone
@@ -91,16 +93,17 @@ __device__ __forceinline__ int32_t s3_gauscr(const S3Dev &g, int s, int c, doubl
 // more than 32 components).  flags == nullptr: every frame of every senone in
 // [s_lo, s_hi).  Writes raw[t][s] and (bst != nullptr) the arg-max component.
 template <int CP, int KC>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, 8)
 s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_hi,
                const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, int16_t *__restrict__ bst) {
-    extern __shared__ float xs[];   // [kFB][veclen]
+    extern __shared__ float xs[];   // [kFB][veclen] | int32 stage[G][kFR][CP*KC]
     constexpr int G = kEvalThreads / CP;
     const int t0 = blockIdx.y * kFB;
     const int nf = min(kFB, T - t0);
     for (int i = threadIdx.x; i < nf * g.veclen; i += kEvalThreads) xs[i] = feat[(size_t)t0 * g.veclen + i];
     __syncthreads();
     const int grp = threadIdx.x / CP, lc = threadIdx.x % CP;
+    int32_t *gstage = reinterpret_cast<int32_t *>(xs + kFB * g.veclen);
     const int s = s_lo + blockIdx.x * G + grp;
     if (s >= s_hi) return;
     const unsigned gmask = CP == 32 ? 0xffffffffu : (((1u << CP) - 1u) << ((threadIdx.x % 32) / CP * CP));
@@ -116,33 +119,60 @@ s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_h
         mask = nf == 32 ? 0xffffffffu : ((1u << nf) - 1u);
     }
     const int nc = __ldg(g.ncomp + s);
+    const int D = g.veclen;
     while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float *x = xs + k * g.veclen;
-        int32_t gs[KC];
+        // up to kFR flagged frames share one pass over this senone's parameters
+        const uint32_t mask0 = mask;
+        int k[kFR], nv = 0;
+#pragma unroll
+        for (int j = 0; j < kFR; ++j) {
+            if (mask) { k[j] = __ffs(mask) - 1; mask &= mask - 1; nv = j + 1; }
+            else k[j] = k[0];
+        }
+        int32_t *stage = gstage + (size_t)grp * kFR * CP * KC;   // [kFR][CP*KC] of this lane group
 #pragma unroll
         for (int r = 0; r < KC; ++r) {
             const int c = lc + r * CP;
-            gs[r] = c < nc ? s3_gauscr(g, s, c, s3_dval(g, s, c, x)) : kS3Zero;
-        }
-        // sequential log-add in component order (mgau_eval_all); with
-        // update_best_id == 1 the best component is the first strict maximum
-        int32_t score = kS3Zero, bscr = kS3Zero; int bidx = kNoBst;
+            if (c < nc) {
+                const float *mp = g.mean + (size_t)s * D * g.cpt + c;
+                const double *vp = g.var + (size_t)s * D * g.cpt + c;
+                double dv[kFR];
+                const float *xp[kFR];
+                const double lrd = (double)__ldg(g.lrd + (size_t)s * g.cpt + c);
 #pragma unroll
-        for (int r = 0; r < KC; ++r)
-            for (int c = 0; c < CP; ++c) {
-                const int32_t v = __shfl_sync(gmask, gs[r], lane0 + c);
-                if (c + r * CP < nc) {
-                    score = s3_logadd(g, score, v);
-                    if (v > bscr) { bscr = v; bidx = c + r * CP; }
+                for (int j = 0; j < kFR; ++j) { dv[j] = lrd; xp[j] = xs + k[j] * D; }
+#pragma unroll 3
+                for (int i = 0; i < D; ++i) {
+                    const float mu = __ldg(mp + (size_t)i * g.cpt);
+                    const double va = __ldg(vp + (size_t)i * g.cpt);
+#pragma unroll
+                    for (int j = 0; j < kFR; ++j) {
+                        const double dd = (double)__fsub_rn(xp[j][i], mu);
+                        dv[j] = __dsub_rn(dv[j], __dmul_rn(__dmul_rn(dd, dd), va));
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < kFR; ++j) stage[j * CP * KC + c] = s3_gauscr(g, s, c, dv[j]);
             }
-        if (score <= kS3Zero) score = kS3Zero;
-        if (lc == 0) {
-            raw[(size_t)(t0 + k) * g.n_sen + s] = score;
-            if (bst) bst[(size_t)(t0 + k) * g.n_sen + s] = (int16_t)bidx;
         }
+        __syncwarp(gmask);
+        // sequential log-add in component order (mgau_eval_all), one lane per
+        // frame; with update_best_id == 1 the best component is the first
+        // strict maximum
+        for (int j = lc; j < nv; j += CP) {
+            int32_t score = kS3Zero, bscr = kS3Zero; int bidx = kNoBst;
+            const int32_t *sj = stage + j * CP * KC;
+            for (int c = 0; c < nc; ++c) {
+                const int32_t v = sj[c];
+                score = s3_logadd(g, score, v);
+                if (v > bscr) { bscr = v; bidx = c; }
+            }
+            if (score <= kS3Zero) score = kS3Zero;
+            const int kj = __fns(mask0, 0, j + 1);      // j-th flagged frame of this pass
+            raw[(size_t)(t0 + kj) * g.n_sen + s] = score;
+            if (bst) bst[(size_t)(t0 + kj) * g.n_sen + s] = (int16_t)bidx;
+        }
+        __syncwarp(gmask);
     }
 }
 
@@ -204,36 +234,69 @@ s3_decide_kernel(S3Dev g, int T, int frame0, int32_t ci_pbeam, int max_cd, int d
     }
 }
 
-// K3: one thread per CD senone, sequential over the chunk's frames.
+// K3a: back-off entries (flag 2), one thread per (frame, CD senone), parallel in
+// time.  The reference's per-senone state machine (bstidx, updatetime) only
+// lets a best-Gaussian back-off happen at frame t when the state was written at
+// frame t-1: by a full evaluation (flag 1), or -- on down-sampled ("skipped")
+// frames, where mgau_eval runs with update_best_id = 1 -- by a previous
+// back-off.  Such a chain is at most ds_ratio-1 frames long, so every entry
+// resolves its own state by walking back over the flags.
 __global__ void __launch_bounds__(128)
-s3_time_kernel(S3Dev g, const float *__restrict__ feat, int T, int frame0, int ds_ratio,
-               const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, const int16_t *__restrict__ bst,
-               int32_t *__restrict__ st_bstidx, int32_t *__restrict__ st_update) {
+s3_backoff_kernel(S3Dev g, const float *__restrict__ feat, int T, int frame0, int ds_ratio,
+                  const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, const int16_t *__restrict__ bst,
+                  const int32_t *__restrict__ st_bstidx, const int32_t *__restrict__ st_update) {
+    const int n_cd = g.n_sen - g.n_ci;
+    const int s = g.n_ci + blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (s >= g.n_sen || n_cd <= 0) return;
+    if (flags[(size_t)t * g.n_sen + s] != 2) return;
+    // walk back over chain-continuing frames (flag 2 on a skipped frame)
+    int u = t - 1;
+    while (u >= 0 && flags[(size_t)u * g.n_sen + s] == 2 && ((frame0 + u) % ds_ratio) != 0) --u;
+    int bidx = kNoBst;
+    if (u >= 0) {
+        if (flags[(size_t)u * g.n_sen + s] == 1) bidx = bst[(size_t)u * g.n_sen + s];
+    } else if (st_update[s] == frame0 - 1) {
+        bidx = st_bstidx[s];
+    }
+    // replay the chain: a back-off on a skipped frame keeps the index only while
+    // its Gaussian score stays above S3_LOGPROB_ZERO
+    int32_t v = 0;
+    for (int w = u + 1; w <= t && bidx != kNoBst; ++w) {
+        v = s3_gauscr(g, s, bidx, s3_dval(g, s, bidx, feat + (size_t)w * g.veclen));
+        if (w < t && !(v > kS3Zero)) bidx = kNoBst;
+    }
+    int32_t score;
+    if (bidx == kNoBst) {
+        score = raw[(size_t)t * g.n_sen + g.cd2ci[s]];
+    } else {
+        score = s3_logadd(g, kS3Zero, v);
+        if (score <= kS3Zero) score = kS3Zero;
+    }
+    raw[(size_t)t * g.n_sen + s] = score;
+}
+
+// K3b: state after the chunk, one thread per CD senone: the last frame that
+// wrote (bstidx, updatetime).
+__global__ void __launch_bounds__(128)
+s3_state_kernel(S3Dev g, const float *__restrict__ feat, int T, int frame0, int ds_ratio,
+                const uint8_t *__restrict__ flags, const int16_t *__restrict__ bst,
+                int32_t *__restrict__ st_bstidx, int32_t *__restrict__ st_update) {
     const int s = g.n_ci + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.n_sen) return;
-    int bidx = st_bstidx[s], upd = st_update[s];
-    const int par = g.cd2ci[s];
-    for (int t = 0; t < T; ++t) {
-        const int frame = frame0 + t;
-        const uint8_t f = flags[(size_t)t * g.n_sen + s];
-        if (f == 1) {
-            bidx = bst[(size_t)t * g.n_sen + s];
-            upd = frame;
-        } else if (f == 2) {
-            if (bidx == kNoBst || upd != frame - 1) {
-                raw[(size_t)t * g.n_sen + s] = raw[(size_t)t * g.n_sen + par];
-            } else {
-                // mgau_eval(g, s, {bstidx,-1}, x, frame, is_skip)
-                const int32_t v = s3_gauscr(g, s, bidx, s3_dval(g, s, bidx, feat + (size_t)t * g.veclen));
-                int32_t score = s3_logadd(g, kS3Zero, v);
-                if (score <= kS3Zero) score = kS3Zero;
-                raw[(size_t)t * g.n_sen + s] = score;
-                if ((frame % ds_ratio) != 0) {      // skipped frame: update_best_id = 1
-                    bidx = v > kS3Zero ? bidx : kNoBst;
-                    upd = frame;
-                }
-            }
-        }
+    // last full evaluation
+    int r = T - 1;
+    while (r >= 0 && flags[(size_t)r * g.n_sen + s] != 1) --r;
+    int bidx, upd;
+    if (r >= 0) { bidx = bst[(size_t)r * g.n_sen + s]; upd = frame0 + r; }
+    else { bidx = st_bstidx[s]; upd = st_update[s]; }
+    // a chain of back-offs on skipped frames directly after it keeps updating
+    for (int w = r + 1; w < T; ++w) {
+        const int frame = frame0 + w;
+        if (flags[(size_t)w * g.n_sen + s] != 2 || (frame % ds_ratio) == 0 || bidx == kNoBst || upd != frame - 1) break;
+        const int32_t v = s3_gauscr(g, s, bidx, s3_dval(g, s, bidx, feat + (size_t)w * g.veclen));
+        bidx = v > kS3Zero ? bidx : kNoBst;
+        upd = frame;
     }
     st_bstidx[s] = bidx; st_update[s] = upd;
 }
@@ -277,6 +340,17 @@ s3_norm_kernel(int n_sen, int T, const uint8_t *__restrict__ flags, const int32_
         out[(size_t)t * n_sen + s] = p;
     }
     prev[s] = p;
+}
+
+// Measurement utility: issue rate of the FP64 pipe with the instruction mix the
+// scoring kernel is bound by (independent DMUL / DADD chains, no FMA).
+__global__ void __launch_bounds__(256) s3_fp64_probe_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __dmul_rn(x0, a); x1 = __dadd_rn(x1, b); x2 = __dmul_rn(x2, a); x3 = __dadd_rn(x3, b);
+        x4 = __dmul_rn(x4, a); x5 = __dadd_rn(x5, b); x6 = __dmul_rn(x6, a); x7 = __dadd_rn(x7, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
 int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -343,7 +417,7 @@ int launch_eval_t(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, in
     if (s_hi <= s_lo || T <= 0) return B200_OK;
     constexpr int G = kEvalThreads / CP;
     dim3 grid((s_hi - s_lo + G - 1) / G, (T + kFB - 1) / kFB);
-    size_t smem = (size_t)kFB * m->veclen * sizeof(float);
+    size_t smem = (size_t)kFB * m->veclen * sizeof(float) + (size_t)kEvalThreads * KC * kFR * sizeof(int32_t);
     s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -377,8 +451,11 @@ int s3_chunk_dev(b200_s3mgau *m, const float *d_feat, int T, int frame0, uint8_t
     if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st))) return rc;
     const int n_cd = m->n_sen - m->n_ci;
     if (n_cd > 0) {
-        s3_time_kernel<<<(n_cd + 127) / 128, 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags, m->d_raw,
-                                                           m->d_bst, m->d_bstidx, m->d_update);
+        s3_backoff_kernel<<<dim3((n_cd + 127) / 128, T), 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags,
+                                                                     m->d_raw, m->d_bst, m->d_bstidx, m->d_update);
+        B200_LAUNCH_CHECK();
+        s3_state_kernel<<<(n_cd + 127) / 128, 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags, m->d_bst,
+                                                            m->d_bstidx, m->d_update);
         B200_LAUNCH_CHECK();
     }
     if (m->n_ci > 0) {
@@ -579,7 +656,7 @@ int b200_s3_state(b200_s3mgau_t *m, int32_t *bstidx, int32_t *updatetime) {
 int b200_s3_dense_dev(b200_s3mgau_t *m, const float *d_feat, int T, int32_t *d_out, void *stream) {
     if (!m || !d_feat || !d_out || T < 0) { set_error("b200_s3_dense_dev: bad argument"); return B200_ERR_ARG; }
     cudaSetDevice(m->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : m->st;
+    cudaStream_t st = (cudaStream_t)stream;
     B200_CUDA_OK(cudaEventRecord(m->ev[0], st));
     int rc = launch_eval(m, d_feat, T, 0, m->n_sen, nullptr, d_out, nullptr, st);
     if (rc) return rc;
@@ -606,7 +683,7 @@ int b200_s3_score_utt_dev(b200_s3mgau_t *m, const float *d_feat, int T, int fram
                           int32_t *d_out, int32_t *d_best, void *stream) {
     if (!m || !d_feat || !d_out || !d_best || T < 0) { set_error("b200_s3_score_utt_dev: bad argument"); return B200_ERR_ARG; }
     cudaSetDevice(m->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : m->st;
+    cudaStream_t st = (cudaStream_t)stream;
     B200_CUDA_OK(cudaEventRecord(m->ev[0], st));
     for (int t0 = 0; t0 < T; t0 += kChunkT) {
         const int n = std::min(kChunkT, T - t0);
@@ -654,6 +731,31 @@ int b200_s3_frame_eval(b200_s3mgau_t *m, const float *feat, int32_t frame, uint8
     std::vector<int32_t> row(m->n_sen);
     int rc = b200_s3_score_utt_host(m, feat, 1, frame, sen_active, senscr, row.data(), best);
     return rc;
+}
+
+double b200_fp64_issue_rate(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("bad device %d", device); return -1.0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)blocks * 256 * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        s3_fp64_probe_kernel<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)blocks * 256 * iters * 8 / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return best;
 }
 
 float b200_s3_last_ms(b200_s3mgau_t *m) {

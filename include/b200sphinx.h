@@ -343,6 +343,10 @@ int  b200_s3_frame_eval(b200_s3mgau_t *m, const float *feat, int32_t frame,
                         uint8_t *sen_active, int32_t *senscr, int32_t *best);
 /* Device time of the last *_dev / score call in ms (CUDA events). */
 float b200_s3_last_ms(b200_s3mgau_t *m);
+/* Measurement utility for the roofline of the float64 kernel: sustained
+ * thread-level FP64 instructions per second (independent DMUL/DADD chains, the
+ * non-fused mix the reference's arithmetic forces), measured on `device`. */
+double b200_fp64_issue_rate(int device);
 
 /* -------------------------------------------------- device memory helpers
  * (so a non-torch host can keep buffers resident) */
