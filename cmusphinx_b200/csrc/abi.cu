@@ -40,6 +40,7 @@ struct b200_mgau {
     bool cont = false;  // ms with identity senone->codebook map
     int path = 0;
     TcPlan *tc = nullptr;
+    TcTied *tct = nullptr;   // tensor-core codebook stage of the tied back-ends
     float *d_mean = nullptr, *d_var = nullptr, *d_det = nullptr;
     uint8_t *d_mixw = nullptr, *d_sen2cb = nullptr;
     uint32_t *d_sen2mgau = nullptr;
@@ -170,7 +171,9 @@ int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cu
         if ((rc = ensure((void **)&m->d_lists, &m->lists_cap, (size_t)chunk * list_bytes_per_frame(m)))) return rc;
         for (int t0 = 0; t0 < T; t0 += chunk) {
             int tn = std::min(T - t0, chunk);
-            if ((rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st))) return rc;
+            if (m->kind != 0 && m->path == 1 && m->tct) rc = tc_tied_lists(m->tct, g, d_feat, t0, tn, m->d_lists, st);
+            else rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st);
+            if (rc) return rc;
             if (m->kind == 0) rc = gmm_launch_ms_senone(g, m->d_lists, T, t0, tn, d_out, st);
             else rc = gmm_launch_tied_senone(g, m->d_lists, T, t0, tn, m->kind == 2, nullptr, 0, d_out, st);
             if (rc) return rc;
@@ -262,6 +265,10 @@ static b200_mgau_t *tied_create(int kind, const b200_mgau_cfg_t *cfg, const floa
     if (gmm_tied_smem(g, g.n_sen + g.n_sen / 255 + 1) > 200 * 1024) {
         set_error("model too large for the tied senone kernel's shared memory"); b200_mgau_free(m); return nullptr;
     }
+    // tensor-core codebook stage (bit-identical lists); the exact kernel stays as path 0
+    m->path = 0;
+    m->tct = tc_tied_create(g, kind, mean, var, det, m->device);
+    if (m->tct) m->path = 1;
     return m;
 }
 
@@ -329,6 +336,7 @@ void b200_mgau_free(b200_mgau_t *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->tc) tc_plan_free(m->tc);
+    if (m->tct) tc_tied_free(m->tct);
     cudaFree(m->d_mean); cudaFree(m->d_var); cudaFree(m->d_det); cudaFree(m->d_mixw);
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2mgau); cudaFree(m->d_lists);
     for (int i = 0; i < 2; ++i) { cudaFree(m->d_feat[i]); cudaFree(m->d_out[i]); if (m->st[i]) cudaStreamDestroy(m->st[i]); }
@@ -367,12 +375,29 @@ int b200_mgau_update_params(b200_mgau_t *m, const float *mean, const float *var,
         m->tc = tc_plan_create(m->g, mean, var, det, mixw_sfc.data(), m->device);
         if (!m->tc) m->path = 0;
     }
+    if (m->tct) {
+        const int was = m->path;
+        tc_tied_free(m->tct);
+        m->tct = tc_tied_create(m->g, m->kind, mean, var, det, m->device);
+        m->path = m->tct ? was : 0;
+    }
+    return B200_OK;
+}
+
+int b200_mgau_tied_stats(b200_mgau_t *m, long long out[2]) {
+    if (!m || !out) { set_error("null argument"); return B200_ERR_ARG; }
+    out[0] = out[1] = 0;
+    if (m->tct) tc_tied_stats(m->tct, out);
     return B200_OK;
 }
 
 int b200_mgau_set_path(b200_mgau_t *m, int path) {
     if (!m) return B200_ERR_ARG;
     if (path == 0) { m->path = 0; return B200_OK; }
+    if (path == 1 && m->kind != 0) {
+        if (!m->tct) { set_error("tensor-core path unavailable for this model shape"); return B200_ERR_UNSUP; }
+        m->path = 1; return B200_OK;
+    }
     if (path == 1) {
         if (!m->tc) { set_error("tensor-core path unavailable for this model shape"); return B200_ERR_UNSUP; }
         m->path = 1; return B200_OK;
@@ -472,8 +497,10 @@ int b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T) {
         for (int t0 = 0; t0 < T; t0 += 65535 * 128) {
             int tn = std::min(T - t0, 65535 * 128);
             // lists for frame t land at index (t - 0): pass t0 = 0 base by offsetting the pointer
-            if ((rc = gmm_launch_topn(g, m->kind, m->d_ufeat, T, t0, tn,
-                                      m->d_ulists + (size_t)t0 * g.n_mgau * g.n_feat * g.topn, nullptr, 0, st))) return rc;
+            int2 *dst = m->d_ulists + (size_t)t0 * g.n_mgau * g.n_feat * g.topn;
+            if (m->path == 1 && m->tct) rc = tc_tied_lists(m->tct, g, m->d_ufeat, t0, tn, dst, st);
+            else rc = gmm_launch_topn(g, m->kind, m->d_ufeat, T, t0, tn, dst, nullptr, 0, st);
+            if (rc) return rc;
         }
     }
     B200_CUDA_OK(cudaStreamSynchronize(st));

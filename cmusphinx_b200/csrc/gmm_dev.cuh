@@ -23,6 +23,43 @@ struct GmmDev {
     uint8_t logadd[256];        // logmath_init(base, 10, 1) byte table
 };
 
+// Integer top-N list of the tied back-ends (shared by the exact kernel and the
+// tensor-core path's fallback).
+template <int N>
+struct TopI {  // ptm / s2_semi: int32 scores, codewords
+    int32_t s[N];
+    int cw[N];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { s[j] = kWorstDistI; cw[j] = j; }
+    }
+    // eval_topn's insertion_sort_topn (ptm_mgau.c:82-96): entry i receives
+    // score d and bubbles up past strictly smaller scores.
+    __device__ __forceinline__ void seed(int i, int32_t d) {
+        int c = cw[i];
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {
+            if (j > i) continue;
+            if (j > 0 && d > s[j - 1]) { s[j] = s[j - 1]; cw[j] = cw[j - 1]; }
+            else { s[j] = d; cw[j] = c; break; }
+        }
+    }
+    __device__ __forceinline__ bool has(int c) const {
+        bool h = false;
+#pragma unroll
+        for (int j = 0; j < N; ++j) h |= (cw[j] == c);
+        return h;
+    }
+    // eval_cb's insertion (ptm_mgau.c:146-157): ahead of equal scores.
+    __device__ __forceinline__ void insert(int32_t d, int c) {
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {
+            if (j > 0 && d >= s[j - 1]) { s[j] = s[j - 1]; cw[j] = cw[j - 1]; }
+            else { s[j] = d; cw[j] = c; break; }
+        }
+    }
+};
+
 int gmm_launch_topn(const GmmDev &g, int mode, const float *d_feat, int T, int t0, int tn, int2 *lists,
                     int16_t *raw, int fused, cudaStream_t st);
 int gmm_launch_ms_senone(const GmmDev &g, const int2 *lists, int T, int t0, int tn, int16_t *raw,
@@ -34,6 +71,17 @@ int gmm_launch_tied_senone(const GmmDev &g, const int2 *lists, int T, int t0, in
 size_t gmm_tied_smem(const GmmDev &g, int n_active);
 int gmm_launch_ms_active_normalize(const int16_t *raw, const uint8_t *d_active, int n_active,
                                    int16_t *out, cudaStream_t st);
+
+// mahal_tc.cu: tensor-core codebook stage of the tied back-ends (ptm / s2_semi):
+// lists [tn][n_mgau*n_feat][topn] {codeword, (int32)score} for frames
+// [t0, t0+tn) of d_feat, bit-identical to gmm_launch_topn(mode 1|2).
+struct TcTied;
+TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const float *h_var, const float *h_det,
+                       int device);
+void tc_tied_free(TcTied *p);
+int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int tn, int2 *lists, cudaStream_t st);
+// statistics of the last call: {pairs, pairs sent to the exact fallback}
+void tc_tied_stats(TcTied *p, long long out[2]);
 
 // mahal_tc.cu: tensor-core path for single-stream .cont. models.
 struct TcPlan;

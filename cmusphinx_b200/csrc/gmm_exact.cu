@@ -41,41 +41,6 @@ struct TopF {  // ms: float distances, ids
     }
 };
 
-template <int N>
-struct TopI {  // ptm / s2_semi: int32 scores, codewords
-    int32_t s[N];
-    int cw[N];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int j = 0; j < N; ++j) { s[j] = kWorstDistI; cw[j] = j; }
-    }
-    // eval_topn's insertion_sort_topn (ptm_mgau.c:82-96): entry i receives
-    // score d and bubbles up past strictly smaller scores.
-    __device__ __forceinline__ void seed(int i, int32_t d) {
-        int c = cw[i];
-#pragma unroll
-        for (int j = N - 1; j >= 0; --j) {
-            if (j > i) continue;
-            if (j > 0 && d > s[j - 1]) { s[j] = s[j - 1]; cw[j] = cw[j - 1]; }
-            else { s[j] = d; cw[j] = c; break; }
-        }
-    }
-    __device__ __forceinline__ bool has(int c) const {
-        bool h = false;
-#pragma unroll
-        for (int j = 0; j < N; ++j) h |= (cw[j] == c);
-        return h;
-    }
-    // eval_cb's insertion (ptm_mgau.c:146-157): ahead of equal scores.
-    __device__ __forceinline__ void insert(int32_t d, int c) {
-#pragma unroll
-        for (int j = N - 1; j >= 0; --j) {
-            if (j > 0 && d >= s[j - 1]) { s[j] = s[j - 1]; cw[j] = cw[j - 1]; }
-            else { s[j] = d; cw[j] = c; break; }
-        }
-    }
-};
-
 // Exact sequential distance of frame (column `tid` of xs) to one density.
 __device__ __forceinline__ float seq_dist(const float *xs, int tid, const float *m,
                                           const float *v, float det, int len) {

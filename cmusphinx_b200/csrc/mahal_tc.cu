@@ -80,7 +80,8 @@ struct TcParams {
     const uint8_t *gMixw;   // [n_tiles_n][256] mixture weights in tile row order
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
-    int m31;                // the constant 31, kept opaque to the compiler (see make_key)
+    int m31;                // the constant 31 (63 for tied lists), kept opaque to the compiler (see make_key)
+    uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
     int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
     uint8_t logadd[256];
 };
@@ -230,13 +231,13 @@ __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], con
 // gX[m_tile][dim 0..Dp)[128 rows].  20 KB per tile for D = 39; the x^2 / hi / lo
 // expansion (4x the bytes) happens inside the SM so it never crosses L2.
 __global__ void __launch_bounds__(kTileM)
-tc_prep_kernel(const float *__restrict__ feat, int T, int D, int Dp, float *__restrict__ gX) {
+tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D, int Dp, float *__restrict__ gX) {
     __shared__ float tile[kTileM][41];
     const int mt = blockIdx.x, r = threadIdx.x;
     const int t0 = mt * kTileM;
-    // coalesced read of the tile's rows (contiguous block of min(128, T-t0)*D floats)
+    // coalesced read of the tile's rows (stream `off`..`off+D` of each frame vector)
     const int nrow = min(kTileM, T - t0);
-    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)t0 * D + e];
+    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)(t0 + e / D) * stride + off + e % D];
     __syncthreads();
     for (int i = 0; i < Dp; ++i)
         gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
@@ -250,7 +251,12 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
     lo = __fsub_rn(a, hi);
 }
 
-template <int M, int KS>
+// MODE 0: fully-continuous senones (top-4 of each senone's M densities, log-add,
+//         int16 score).  MODE 1: tied codebooks (ptm / s2_semi): every thread
+//         reduces its 64 accumulator columns to their 4 best keys and stores
+//         them; tied_select_kernel merges the groups of a codebook and rescores
+//         the survivors exactly.
+template <int M, int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -429,14 +435,17 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
-            epi_bar();
-            if (et < kTileN) {
-                // stored reversed inside each senone so that key & 31 indexes it directly
-                const int sl = et / M, dens = et % M;
-                sMixw[sl * M + (M - 1 - dens)] = p.gMixw[(size_t)nt * kTileN + et];
+            if (MODE == 0) {
+                epi_bar();
+                if (et < kTileN) {
+                    // stored reversed inside each senone so that key & 31 indexes it directly
+                    const int sl = et / M, dens = et % M;
+                    sMixw[sl * M + (M - 1 - dens)] = p.gMixw[(size_t)nt * kTileN + et];
+                }
+                epi_bar();
             }
-            epi_bar();
-            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
+            int16_t *rawt = MODE == 0 ? p.raw + (size_t)nt * p.T_pad * SPT : nullptr;
+            uint4 *partt = MODE == 1 ? p.part + (size_t)nt * p.T_pad * 4 : nullptr;
             // key & 31 = 31 - id = (32 - M) + (M - 1 - id): bias the table pointer for M < 32
             const uint8_t *mixw_t = sMixw + cg * CPT - (32 - M);
             for (int mt = mt0; mt < mt1; ++mt) {
@@ -450,6 +459,27 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+                if (MODE == 1) {
+                    // keys carry a 6-bit id (63 - column within the thread's 64)
+                    int32_t ta[4], tb[4];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t (&v)[32] = c ? v1 : v0;
+                        int32_t (&top)[4] = c ? tb : ta;
+                        top[0] = make_key(v[0], c * 32 + 0, m31); top[1] = make_key(v[1], c * 32 + 1, m31);
+                        top[2] = make_key(v[2], c * 32 + 2, m31); top[3] = make_key(v[3], c * 32 + 3, m31);
+                        sort4(top[0], top[1], top[2], top[3]);
+#pragma unroll
+                        for (int g = 4; g < 32; g += 4)
+                            merge4(top, make_key(v[g], c * 32 + g, m31), make_key(v[g + 1], c * 32 + g + 1, m31),
+                                   make_key(v[g + 2], c * 32 + g + 2, m31), make_key(v[g + 3], c * 32 + g + 3, m31));
+                    }
+                    int32_t m0 = min(ta[0], tb[3]), m1 = min(ta[1], tb[2]), m2 = min(ta[2], tb[1]), m3 = min(ta[3], tb[0]);
+                    ce(m0, m2); ce(m1, m3); ce(m0, m1); ce(m2, m3);
+                    partt[(size_t)(mt * kTileM + row) * 4 + cg] = make_uint4((uint32_t)m0, (uint32_t)m1, (uint32_t)m2, (uint32_t)m3);
+                    if (++acc == 2) { acc = 0; accphase ^= 1; }
+                    continue;
+                }
                 int16_t res[SPE];
                 if (p.dbg & 1) {
 #pragma unroll
@@ -592,6 +622,41 @@ float tf32_round(float x) {
     return r;
 }
 
+// One row (= one Gaussian) of a B tile: K columns [c_hi, c_lo, -v_0, 2 mu_0 v_0, ...]
+// times -32, each split into TF32 hi/lo, in the [kstep][hi|lo][chunk][256 rows][4]
+// layout.  mu == nullptr: a padding Gaussian far below anything real.
+void build_b_row(float *tile, int r, int ksteps, int D, const float *mu, const float *v, float det) {
+    const int KP = ksteps * 8;
+    std::vector<double> col(KP, 0.0);
+    double hi1 = 0, lo1 = 0, hi2 = 0, lo2 = 0;
+    if (mu) {
+        double c = (double)det;
+        for (int i = 0; i < D; ++i) {
+            c -= (double)mu[i] * (double)mu[i] * (double)v[i];
+            col[2 + 2 * i] = -(double)v[i];
+            col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
+        }
+        // everything is stored times -32 (see make_key)
+        c *= -(double)kAccScale;
+        for (int k = 2; k < KP; ++k) col[k] *= -(double)kAccScale;
+        hi1 = tf32_round((float)c); lo1 = tf32_round((float)(c - hi1));
+        const double c2 = c - hi1 - lo1;
+        hi2 = tf32_round((float)c2); lo2 = tf32_round((float)(c2 - hi2));
+    } else {
+        hi1 = 3.0e7 * kAccScale;
+    }
+    for (int k = 0; k < KP; ++k) {
+        float hi, lo;
+        if (k == 0) { hi = (float)hi1; lo = (float)lo1; }
+        else if (k == 1) { hi = (float)hi2; lo = (float)lo2; }
+        else { hi = tf32_round((float)col[k]); lo = tf32_round((float)(col[k] - (double)hi)); }
+        const int j = k / 8, c = (k % 8) / 4, e = k % 4;
+        float *st = tile + (size_t)j * (kBStageBytes / 4);
+        st[((0 * 2 + c) * kTileN + r) * 4 + e] = hi;
+        st[((1 * 2 + c) * kTileN + r) * 4 + e] = lo;
+    }
+}
+
 }  // namespace
 
 struct TcPlan {
@@ -638,49 +703,22 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     p->spt = kTileN / p->M;
     p->n_tiles_n = (p->S + p->spt - 1) / p->spt;
     memcpy(p->logadd, g.logadd, 256);
-    const int KP = p->ksteps * 8, M = p->M, D = p->D;
+    const int M = p->M, D = p->D;
     const size_t tile_floats = (size_t)p->ksteps * (kBStageBytes / 4);
     std::vector<float> B((size_t)p->n_tiles_n * tile_floats, 0.f);
     std::vector<uint8_t> mw((size_t)p->n_tiles_n * kTileN, 0);
-    std::vector<double> col(KP);
-    for (int nt = 0; nt < p->n_tiles_n; ++nt) {
+    for (int nt = 0; nt < p->n_tiles_n; ++nt)
         for (int r = 0; r < kTileN; ++r) {
             const int s = nt * p->spt + r / M, dens = r % M;
-            std::fill(col.begin(), col.end(), 0.0);
-            double hi1 = 0, lo1 = 0, hi2 = 0, lo2 = 0;
+            float *tile = B.data() + (size_t)nt * tile_floats;
             if (s < p->S) {
-                const float *mu = h_mean + ((size_t)s * M + dens) * D;
-                const float *v = h_var + ((size_t)s * M + dens) * D;
-                double c = (double)h_det[(size_t)s * M + dens];
-                for (int i = 0; i < D; ++i) {
-                    c -= (double)mu[i] * (double)mu[i] * (double)v[i];
-                    col[2 + 2 * i] = -(double)v[i];
-                    col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
-                }
-                // everything is stored times -32 (see make_key)
-                c *= -(double)kAccScale;
-                for (int k = 2; k < KP; ++k) col[k] *= -(double)kAccScale;
-                hi1 = tf32_round((float)c); lo1 = tf32_round((float)(c - hi1));
-                const double c2 = c - hi1 - lo1;
-                hi2 = tf32_round((float)c2); lo2 = tf32_round((float)(c2 - hi2));
+                build_b_row(tile, r, p->ksteps, D, h_mean + ((size_t)s * M + dens) * D, h_var + ((size_t)s * M + dens) * D,
+                            h_det[(size_t)s * M + dens]);
                 mw[(size_t)nt * kTileN + r] = h_mixw[(size_t)s * M + dens];
             } else {
-                hi1 = 3.0e7 * kAccScale;   // padding Gaussian: far below anything real
-            }
-            float *tile = B.data() + (size_t)nt * tile_floats;
-            for (int k = 0; k < KP; ++k) {
-                float hi, lo;
-                if (k == 0) { hi = (float)hi1; lo = (float)lo1; }
-                else if (k == 1) { hi = (float)hi2; lo = (float)lo2; }
-                else { hi = tf32_round((float)col[k]); lo = tf32_round((float)(col[k] - (double)hi)); }
-                const int j = k / 8, c = (k % 8) / 4, e = k % 4;
-                // [kstep][hi|lo][chunk][256 rows][4]
-                float *st = tile + (size_t)j * (kBStageBytes / 4);
-                st[((0 * 2 + c) * kTileN + r) * 4 + e] = hi;
-                st[((1 * 2 + c) * kTileN + r) * 4 + e] = lo;
+                build_b_row(tile, r, p->ksteps, D, nullptr, nullptr, 0.f);
             }
         }
-    }
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaMalloc((void **)&p->dB, B.size() * 4) != cudaSuccess ||
         cudaMalloc((void **)&p->dMixw, mw.size()) != cudaSuccess ||
@@ -693,26 +731,26 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     return p;
 }
 
-template <int M, int KS>
+template <int M, int KS, int MODE>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
     const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
                         (size_t)4 * KS * kTileM * 4 + 512 + 32 * 8 + 16;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    tc_score_kernel<M, KS><<<grid, kThreads, smem, st>>>(prm);
+    tc_score_kernel<M, KS, MODE><<<grid, kThreads, smem, st>>>(prm);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
-template <int M>
+template <int M, int MODE>
 static int launch_score_ks(const TcParams &prm, int ks, int grid, cudaStream_t st) {
     switch (ks) {
-        case 4: return launch_score<M, 4>(prm, grid, st);
-        case 7: return launch_score<M, 7>(prm, grid, st);
-        case 10: return launch_score<M, 10>(prm, grid, st);
+        case 4: return launch_score<M, 4, MODE>(prm, grid, st);
+        case 7: return launch_score<M, 7, MODE>(prm, grid, st);
+        case 10: return launch_score<M, 10, MODE>(prm, grid, st);
     }
     set_error("tensor-core path: %d k-steps unsupported", ks);
     return B200_ERR_UNSUP;
@@ -734,7 +772,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
         B200_CUDA_OK(cudaMalloc((void **)&p->dRaw, raw_bytes));
         p->raw_cap = raw_bytes;
     }
-    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, p->D, Dp, p->dA);
+    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, p->D, 0, p->D, Dp, p->dA);
     B200_LAUNCH_CHECK();
     if (ev_prep) cudaEventRecord(*ev_prep, st);
 
@@ -743,7 +781,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.m31 = 31;
+    prm.m31 = 31; prm.part = nullptr;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -756,9 +794,9 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     const int grid = std::min(prm.n_units, p->n_sm);
     *T_pad_out = T_pad;
     switch (p->M) {
-        case 8: return launch_score_ks<8>(prm, p->ksteps, grid, st);
-        case 16: return launch_score_ks<16>(prm, p->ksteps, grid, st);
-        case 32: return launch_score_ks<32>(prm, p->ksteps, grid, st);
+        case 8: return launch_score_ks<8, 0>(prm, p->ksteps, grid, st);
+        case 16: return launch_score_ks<16, 0>(prm, p->ksteps, grid, st);
+        case 32: return launch_score_ks<32, 0>(prm, p->ksteps, grid, st);
     }
     set_error("tensor-core path: n_density %d unsupported", p->M);
     return B200_ERR_UNSUP;
@@ -786,6 +824,314 @@ int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cu
                                                                                p->n_tiles_n, subtract_best, d_out);
     }
     B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+
+// ====================================================================
+// Tied codebooks (ptm_mgau / s2_semi_mgau): the codebook stage
+// (PS/ptm_mgau.c:98-231 eval_topn + eval_cb, PS/s2_semi_mgau.c:80-187) on
+// the tensor cores, bit-identical to the exact kernel (gmm_topn_kernel<N,1|2>).
+//
+//   1. tc_score_kernel<32,KS,1>: the same TF32x3 GEMM; every epilogue thread
+//      keeps the 4 best keys of its 64 accumulator columns       (approximate d)
+//   2. tied_select_kernel: per (frame, codebook) the 8 best keys over all
+//      column groups -> EXACT sequential float32 distances of those 8
+//      candidates (the reference's arithmetic) -> top-N.  Two cheap sufficient
+//      conditions prove that the result equals the reference's full scan:
+//        (a) the 5 best candidates have pairwise different (int32) scores
+//            (then no tie / same-integer-bucket rule of eval_cb can matter), and
+//        (b) the 5th best exact distance beats  d~(8th candidate) + eps, an
+//            upper bound on every density that is not a candidate.
+//   3. tied_fallback_kernel: the few pairs where (a) or (b) fails (~1e-3) get
+//      the reference's literal scan over the whole codebook.
+// ====================================================================
+namespace {
+
+constexpr int kCand = 8;
+constexpr float kTiedEps = 32.f;      // bound on |approximate - exact| distance (raw log units)
+
+__device__ __forceinline__ float exact_dist(const float *xs, int tid, const float *m, const float *v, float det,
+                                            int len) {
+    float d = det;
+    for (int i = 0; i < len; ++i) {
+        const float diff = __fsub_rn(xs[i * 128 + tid], __ldg(m + i));
+        d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), __ldg(v + i)));
+    }
+    return d;
+}
+
+// block = 128 frames x one codebook (blockIdx.y), stream f
+template <int N>
+__global__ void __launch_bounds__(128)
+tied_select_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int tn, int T_pad, int tpc,
+                   const uint4 *__restrict__ part, int2 *__restrict__ lists, int2 *__restrict__ flagged,
+                   int *__restrict__ n_flagged) {
+    extern __shared__ float xs[];   // [len][128]
+    const int tid = threadIdx.x, mg = blockIdx.y;
+    const int tl = blockIdx.x * 128 + tid;          // frame inside the chunk
+    const bool live = tl < tn;
+    const int len = g.featlen[f];
+    for (int i = 0; i < len; ++i)
+        xs[i * 128 + tid] = live ? feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i] : 0.f;
+    if (!live) return;
+    // 8 smallest keys over the codebook's tpc tiles x 4 column groups
+    int32_t k8[kCand]; int p8[kCand];
+#pragma unroll
+    for (int j = 0; j < kCand; ++j) { k8[j] = 0x7fffffff; p8[j] = 0; }
+    for (int j = 0; j < tpc; ++j) {
+        const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) {
+            const uint4 q = src[cg];
+            const int32_t key[4] = {(int32_t)q.x, (int32_t)q.y, (int32_t)q.z, (int32_t)q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
+                const int pos = j * 4 + cg;
+#pragma unroll
+                for (int r = kCand - 1; r >= 0; --r) {
+                    if (r > 0 && key[e] < k8[r - 1]) { k8[r] = k8[r - 1]; p8[r] = p8[r - 1]; }
+                    else { k8[r] = key[e]; p8[r] = pos; break; }
+                }
+            }
+        }
+    }
+    // exact distances of the candidates, sorted descending
+    const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+    const size_t dbase = ((size_t)mg * g.n_feat + f) * g.n_density;
+    float ed[kCand]; int ei[kCand];
+    int n_ok = 0;
+#pragma unroll
+    for (int c = 0; c < kCand; ++c) {
+        float d = -3.0e38f; int idx = -1;
+        if (k8[c] != 0x7fffffff) {
+            idx = (p8[c] >> 2) * kTileN + (p8[c] & 3) * 64 + (63 - (k8[c] & 63));
+            if (idx < g.n_density) {
+                d = exact_dist(xs, tid, g.mean + pbase + (size_t)idx * len, g.var + pbase + (size_t)idx * len,
+                               __ldg(g.det + dbase + idx), len);
+                ++n_ok;
+            } else idx = -1;
+        }
+#pragma unroll
+        for (int r = kCand - 1; r >= 0; --r) {
+            if (r > c) continue;
+            if (r > 0 && d > ed[r - 1]) { ed[r] = ed[r - 1]; ei[r] = ei[r - 1]; }
+            else { ed[r] = d; ei[r] = idx; break; }
+        }
+    }
+    // (b): every non-candidate has approximate distance <= -k8[7]/32 (+2 for the id bits)
+    const float bound = -(float)k8[kCand - 1] * (1.0f / kAccScale) + kTiedEps + 1.5e-5f * fabsf(ed[N]);
+    bool ok = n_ok == kCand && ed[N] > bound;
+    // (a): strictly decreasing integers over the N+1 best
+#pragma unroll
+    for (int j = 0; j < N; ++j) ok = ok && ((int32_t)ed[j] > (int32_t)ed[j + 1]);
+    int2 *o = lists + ((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N;
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = make_int2(ei[j], (int32_t)ed[j]);
+    } else {
+        flagged[atomicAdd(n_flagged, 1)] = make_int2(tl, mg);
+    }
+}
+
+// The reference's literal scan for the flagged (frame, codebook) pairs: all
+// distances in parallel into shared memory, then one thread replays eval_topn +
+// eval_cb in index order (same code as gmm_topn_kernel).
+template <int N, int MODE>
+__global__ void __launch_bounds__(128)
+tied_fallback_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, const int2 *__restrict__ flagged,
+                     const int *__restrict__ n_flagged, int2 *__restrict__ lists) {
+    extern __shared__ float sh[];   // x[len] | d[n_density]
+    const int len = g.featlen[f];
+    float *x = sh, *dd = sh + ((len + 3) & ~3);
+    const int n = *n_flagged;
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        const int tl = flagged[w].x, mg = flagged[w].y;
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += blockDim.x) x[i] = feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i];
+        __syncthreads();
+        const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+        const size_t dbase = ((size_t)mg * g.n_feat + f) * g.n_density;
+        for (int c = threadIdx.x; c < g.n_density; c += blockDim.x) {
+            const float *m = g.mean + pbase + (size_t)c * len, *v = g.var + pbase + (size_t)c * len;
+            float d = g.det[dbase + c];
+            for (int i = 0; i < len; ++i) {
+                const float diff = __fsub_rn(x[i], m[i]);
+                d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), v[i]));
+            }
+            dd[c] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            TopI<N> ti;
+            ti.init();
+#pragma unroll
+            for (int i = 0; i < N; ++i) ti.seed(i, (int32_t)dd[i]);
+            for (int c = N; c < g.n_density; ++c) {
+                const float d = dd[c];
+                const int32_t worst = ti.s[N - 1];
+                if (MODE == 1) { if (d < (float)worst) continue; }
+                else { if ((int32_t)d < worst) continue; }
+                ti.insert((int32_t)d, c);
+            }
+            int2 *o = lists + ((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) o[j] = make_int2(ti.cw[j], ti.s[j]);
+        }
+    }
+}
+
+__global__ void tied_count_roll(int *c) { c[1] += c[0]; c[0] = 0; }
+
+}  // namespace
+
+struct TcTied {
+    int device = 0, mode = 1, n_feat = 0, tpc = 0, n_tiles_n = 0, n_sm = 148, topn = 4;
+    int ksteps[B200_MAX_STREAMS] = {0, 0, 0, 0};
+    float *dB[B200_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    float *dX = nullptr; size_t x_cap = 0;
+    uint4 *dPart = nullptr; size_t part_cap = 0;
+    int2 *dFlag = nullptr; size_t flag_cap = 0;
+    int *dCount = nullptr;          // [1 + n_feat]: running total per stream launch
+    long long pairs = 0;
+    int chunk = 0;                  // frames per internal chunk
+};
+
+void tc_tied_free(TcTied *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (auto b : p->dB) cudaFree(b);
+    cudaFree(p->dX); cudaFree(p->dPart); cudaFree(p->dFlag); cudaFree(p->dCount);
+    delete p;
+}
+
+TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const float *h_var, const float *h_det,
+                       int device) {
+    if (g.n_density % kTileN != 0 || g.topn > 4 || g.topn + 1 > kCand || g.n_density < 8) return nullptr;
+    for (int f = 0; f < g.n_feat; ++f)
+        if ((2 * g.featlen[f] + 2 + 7) / 8 > kMaxKSteps) return nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) { cudaGetLastError(); return nullptr; }
+    TcTied *p = new TcTied();
+    p->device = device; p->mode = mode; p->n_feat = g.n_feat; p->topn = g.topn; p->n_sm = prop.multiProcessorCount;
+    p->tpc = g.n_density / kTileN;
+    p->n_tiles_n = g.n_mgau * p->tpc;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    for (int f = 0; f < g.n_feat && ok; ++f) {
+        const int D = g.featlen[f];
+        const int need = (2 * D + 2 + 7) / 8;
+        p->ksteps[f] = need <= 4 ? 4 : (need <= 7 ? 7 : 10);
+        const size_t tile_floats = (size_t)p->ksteps[f] * (kBStageBytes / 4);
+        std::vector<float> B((size_t)p->n_tiles_n * tile_floats, 0.f);
+        for (int mg = 0; mg < g.n_mgau; ++mg) {
+            const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+            const size_t dbase = ((size_t)mg * g.n_feat + f) * g.n_density;
+            for (int c = 0; c < g.n_density; ++c)
+                build_b_row(B.data() + (size_t)(mg * p->tpc + c / kTileN) * tile_floats, c % kTileN, p->ksteps[f], D,
+                            h_mean + pbase + (size_t)c * D, h_var + pbase + (size_t)c * D, h_det[dbase + c]);
+        }
+        ok = cudaMalloc((void **)&p->dB[f], B.size() * 4) == cudaSuccess &&
+             cudaMemcpy(p->dB[f], B.data(), B.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc((void **)&p->dCount, 16 * sizeof(int)) == cudaSuccess;
+    if (!ok) {
+        set_error("tensor-core plan (tied) allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        tc_tied_free(p);
+        return nullptr;
+    }
+    // internal frame chunk: partial lists are 64 B per (tile, frame); keep them under ~2 GB
+    long long c = (2LL << 30) / ((long long)p->n_tiles_n * 64);
+    c = std::max(1024LL, std::min(32768LL, c)) / kTileM * kTileM;
+    p->chunk = (int)c;
+    return p;
+}
+
+void tc_tied_stats(TcTied *p, long long out[2]) {
+    out[0] = p ? p->pairs : 0;
+    out[1] = 0;
+    if (!p) return;
+    int c = 0;
+    cudaSetDevice(p->device);
+    if (cudaMemcpy(&c, p->dCount + 1, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) out[1] = c;
+}
+
+template <int N>
+static int tied_select_launch(TcTied *p, const GmmDev &g, int f, const float *d_feat, int t0, int tn, int T_pad,
+                              int2 *lists, cudaStream_t st) {
+    const int len = g.featlen[f];
+    tied_select_kernel<N><<<dim3((tn + 127) / 128, g.n_mgau), 128, (size_t)len * 128 * 4, st>>>(
+        g, f, d_feat, t0, tn, T_pad, p->tpc, p->dPart, lists, p->dFlag, p->dCount);
+    B200_LAUNCH_CHECK();
+    const size_t sh = ((size_t)((len + 3) & ~3) + g.n_density) * 4;
+    if (sh > 200 * 1024) { set_error("codebook too large for the fallback kernel"); return B200_ERR_UNSUP; }
+    auto kern = p->mode == 1 ? tied_fallback_kernel<N, 1> : tied_fallback_kernel<N, 2>;
+    static bool attr[2] = {false, false};
+    if (!attr[p->mode - 1]) {
+        B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr[p->mode - 1] = true;
+    }
+    kern<<<p->n_sm * 2, 128, sh, st>>>(g, f, d_feat, t0, p->dFlag, p->dCount, lists);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int tn, int2 *lists, cudaStream_t st) {
+    p->pairs = 0;
+    B200_CUDA_OK(cudaMemsetAsync(p->dCount, 0, 16 * sizeof(int), st));
+    for (int c0 = 0; c0 < tn; c0 += p->chunk) {
+        const int cn = std::min(p->chunk, tn - c0);
+        const int n_tiles_m = (cn + kTileM - 1) / kTileM, T_pad = n_tiles_m * kTileM;
+        const size_t part_bytes = (size_t)p->n_tiles_n * T_pad * 4 * sizeof(uint4);
+        const size_t flag_bytes = (size_t)cn * g.n_mgau * sizeof(int2);
+        if (p->part_cap < part_bytes) {
+            cudaFree(p->dPart); p->dPart = nullptr; p->part_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&p->dPart, part_bytes));
+            p->part_cap = part_bytes;
+        }
+        if (p->flag_cap < flag_bytes) {
+            cudaFree(p->dFlag); p->dFlag = nullptr; p->flag_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&p->dFlag, flag_bytes));
+            p->flag_cap = flag_bytes;
+        }
+        int2 *lc = lists + (size_t)c0 * g.n_mgau * g.n_feat * g.topn;
+        for (int f = 0; f < g.n_feat; ++f) {
+            const int Dp = 4 * p->ksteps[f];
+            const size_t x_bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
+            if (p->x_cap < x_bytes) {
+                cudaFree(p->dX); p->dX = nullptr; p->x_cap = 0;
+                B200_CUDA_OK(cudaMalloc((void **)&p->dX, x_bytes));
+                p->x_cap = x_bytes;
+            }
+            tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat + (size_t)(t0 + c0) * g.veclen, cn, g.veclen, g.featoff[f],
+                                                        g.featlen[f], Dp, p->dX);
+            B200_LAUNCH_CHECK();
+            TcParams prm;
+            prm.gB = p->dB[f]; prm.gX = p->dX; prm.gMixw = nullptr; prm.raw = nullptr; prm.part = p->dPart;
+            prm.T = cn; prm.T_pad = T_pad; prm.n_sen = 0; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
+            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63;
+            int m_chunks = 1;
+            while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
+            prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
+            prm.m_chunks = (n_tiles_m + prm.tiles_per_chunk - 1) / prm.tiles_per_chunk;
+            prm.n_units = p->n_tiles_n * prm.m_chunks;
+            memset(prm.logadd, 0, 256);
+            const int grid = std::min(prm.n_units, p->n_sm);
+            int rc = launch_score_ks<32, 1>(prm, p->ksteps[f], grid, st);
+            if (rc) return rc;
+            // flagged pairs of this launch: reset the per-launch counter, keep a running total in dCount[1]
+            switch (g.topn) {
+                case 1: rc = tied_select_launch<1>(p, g, f, d_feat, t0 + c0, cn, T_pad, lc, st); break;
+                case 2: rc = tied_select_launch<2>(p, g, f, d_feat, t0 + c0, cn, T_pad, lc, st); break;
+                case 3: rc = tied_select_launch<3>(p, g, f, d_feat, t0 + c0, cn, T_pad, lc, st); break;
+                default: rc = tied_select_launch<4>(p, g, f, d_feat, t0 + c0, cn, T_pad, lc, st); break;
+            }
+            if (rc) return rc;
+            tied_count_roll<<<1, 1, 0, st>>>(p->dCount);
+            B200_LAUNCH_CHECK();
+            p->pairs += (long long)cn * g.n_mgau;
+        }
+    }
     return B200_OK;
 }
 

@@ -186,6 +186,13 @@ class Mgau:
     def set_path(self, path: int):
         check(lib.b200_mgau_set_path(self._h, path), "set_path")
 
+    def tied_stats(self):
+        """(lists produced, lists re-done by the exact-scan fallback) of the last
+        tensor-core scoring call of a ptm / s2_semi back-end."""
+        out = (C.c_longlong * 2)()
+        check(lib.b200_mgau_tied_stats(self._h, out), "tied_stats")
+        return int(out[0]), int(out[1])
+
     # vt->free
     def free(self):
         if self._h:

@@ -161,8 +161,18 @@ int  b200_mgau_update_params(b200_mgau_t *m, const float *mean,
  *   1 = tcgen05 tensor-core Mahalanobis GEMM (TF32x3 split, fused top-N /
  *       log-add epilogue; .cont. single-stream models only).
  * Default: 1 when the model shape allows it, else 0. */
+/* For the ptm / s2_semi back-ends path 1 runs the codebook stage (eval_topn +
+ * eval_cb, PS/ptm_mgau.c:98-231, PS/s2_semi_mgau.c:80-187) as the same
+ * tensor-core GEMM followed by an exact float32 re-scoring of the 8 best
+ * candidates per (frame, codebook); pairs for which exactness cannot be proven
+ * (integer-score ties near rank N) are re-done with the reference's literal
+ * scan, so both paths return identical top-N lists and scores.  Needs
+ * n_density % 256 == 0 and topn <= 4; default 1 when available. */
 int  b200_mgau_set_path(b200_mgau_t *m, int path);
 int  b200_mgau_get_path(const b200_mgau_t *m);
+/* Tied back-ends, tensor-core path: {(frame, codebook, stream) lists produced,
+ * lists that went through the exact-scan fallback} of the last scoring call. */
+int  b200_mgau_tied_stats(b200_mgau_t *m, long long out[2]);
 
 /* Batched dense scoring == ps_mgau_frame_eval(..., compallsen=1) for frames
  * 0..T-1 (PS/ms_mgau.c:162-205, PS/ptm_mgau.c:405-450,

@@ -348,3 +348,55 @@ def test_ptm_speech_frames_bit_exact_vs_oracle():
         m.utt_frame(got, dl, dl.size, t, False)
         np.testing.assert_array_equal(got, pt.frame_eval(feat[t], dl, False, t))
     m.free()
+
+
+@pytest.mark.parametrize("C,Mden,streams,S,T,kind", [
+    (6, 1024, [39], 300, 700, 1),          # ptm, 4 tiles per codebook, 10 k-steps
+    (3, 256, [13, 13, 13], 200, 1500, 1),  # ptm, real-model shape: 3 streams x 13 dims (4 k-steps)
+    (1, 256, [13, 13, 13], 150, 900, 2),   # s2_semi
+    (4, 512, [25], 100, 300, 1),           # 7 k-steps
+])
+def test_tied_tensor_core_path_identical_to_exact(C, Mden, streams, S, T, kind):
+    """ptm / s2_semi codebook stage on the tensor cores (GEMM candidates + exact
+    re-scoring + exact-scan fallback) must return the same scores as the exact
+    CUDA-core scan, bit for bit -- including frames built to produce integer
+    score ties at rank 4/5 (duplicated Gaussians), which must go through the
+    fallback."""
+    rng = np.random.default_rng(C * 1000 + Mden)
+    F, V = len(streams), sum(streams)
+    mean = rng.standard_normal((C, F, Mden, max(streams))).astype(np.float32)
+    var = np.exp(rng.uniform(np.log(0.05), np.log(5.0), mean.shape)).astype(np.float32)
+    # duplicated Gaussians (identical distance for every frame) in codebook 0, stream 0
+    mean[0, 0, 700 % Mden] = mean[0, 0, 3]; var[0, 0, 700 % Mden] = var[0, 0, 3]
+    mean[0, 0, 200] = mean[0, 0, 100]; var[0, 0, 200] = var[0, 0, 100]
+    flat_m = np.concatenate([mean[:, f, :, :L].reshape(C, -1) for f, L in enumerate(streams)], 1)
+    flat_v = np.concatenate([var[:, f, :, :L].reshape(C, -1) for f, L in enumerate(streams)], 1)
+    pv_parts, pd_parts = [], []
+    for f, L in enumerate(streams):
+        a, d = orc.port_precompute(var[:, f, :, :L].reshape(-1, L), L, 1e-4, orc.LOGBASE)
+        pv_parts.append(a.reshape(C, -1)); pd_parts.append(d.reshape(C, 1, Mden))
+    pv = np.concatenate(pv_parts, 1); pd = np.concatenate(pd_parts, 1)
+    mixw = rng.integers(0, 160, (F, Mden, S)).astype(np.uint8)
+    s2c = (np.arange(S) * C // S).astype(np.uint8)
+    cfg = b.MgauConfig(C, F, Mden, S, streams, topn=4, logbase=orc.LOGBASE)
+    m = (b.ptm_from_arrays(cfg, flat_m, pv, pd, mixw, s2c) if kind == 1 else b.semi_from_arrays(cfg, flat_m, pv, pd, mixw))
+    assert m.path == 1, "tensor-core codebook stage should be the default for this shape"
+    feat = (rng.standard_normal((T, V)) * 1.3).astype(np.float32)
+    # frames sitting on the duplicated Gaussians: exact ties inside the top 4
+    feat[5, :streams[0]] = mean[0, 0, 3, :streams[0]]
+    feat[6, :streams[0]] = mean[0, 0, 100, :streams[0]] + 0.01
+    got_tc = m.score(feat)
+    n_lists, n_fallback = m.tied_stats()
+    assert n_lists == T * C * F
+    assert 1 <= n_fallback <= max(4, n_lists // 10), (n_lists, n_fallback)   # the duplicates are in many top-5s
+    m.set_path(0)
+    got_exact = m.score(feat)
+    np.testing.assert_array_equal(got_tc, got_exact)
+    # utterance cache + per-frame serving goes through the same lists
+    m.set_path(1)
+    m.utt_begin(feat[:64])
+    out = np.zeros(S, np.int16)
+    m.utt_frame(out, None, 0, 17, True)
+    np.testing.assert_array_equal(out, got_exact[17])
+    print(f"tied TC: {n_lists} lists, {n_fallback} via exact fallback ({n_fallback / n_lists:.2e})")
+    m.free()
