@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench_ptm.py -- BASELINE.json configs[2]: ptm_mgau, 256 phonetic codebooks x
 4096 densities x 39 dims, 5000 senone mixture-weight rows, top-4 fast-eval, one
-B200.  Secondary benchmark; one JSON line.  Round 1 runs the codebook stage on
-the exact CUDA-core kernel (bit-exact integer top-N); the tensor-core GEMM of
-bench.py with a per-codebook top-N epilogue is the planned replacement."""
+B200.  Secondary benchmark; one JSON line.  The codebook stage runs on the
+tensor cores (the TF32x3 GEMM of bench.py producing candidate keys, exact
+float32 re-scoring of the 8 best per (frame, codebook), exact-scan fallback for
+unprovable ties) and is checked here against the exact CUDA-core scan: scores
+must be identical."""
 import argparse
 import json
 import os
@@ -18,8 +20,9 @@ C, M, D, S = 256, 4096, 39, 5000
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=4096)
+    ap.add_argument("--frames", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=48)
     args = ap.parse_args()
     import torch
     import cmusphinx_b200 as b
@@ -41,16 +44,44 @@ def main():
         m.score_dev(feat.data_ptr(), T, out.data_ptr())
         ms.append(m.last_ms(0))
     t = float(np.mean(ms))
+    path = m.path
+    stats = m.tied_stats() if path == 1 else (0, 0)
+    # the exact CUDA-core scan on a small slice: must give identical scores
+    n_chk = min(T, 256)
+    chk_tc = out[:n_chk].cpu().numpy().copy()
+    m.set_path(0)
+    out0 = torch.empty((n_chk, S), dtype=torch.int16, device="cuda")
+    m.score_dev(feat.data_ptr(), n_chk, out0.data_ptr())
+    t_exact = m.last_ms(0) * T / n_chk
+    assert np.array_equal(chk_tc, out0.cpu().numpy()), "tensor-core path != exact path"
     flop = 4.0 * D * C * M       # per frame
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1325.0
     ach = flop * T / (t / 1e3) / 1e12
+    # CPU baseline: the oracle port (checker only), one core, a bounded sample of the same workload
+    import time
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    n_cpu = args.cpu_frames
+    pt = orc.PortTied(1, C, 1, [D], M, S, 4, mean, pv.reshape(C, -1), pd.reshape(C, 1, M), mixw, 0, None, s2c, LOGBASE)
+    fh = feat[:n_cpu].cpu().numpy()
+    t0c = time.perf_counter()
+    want = pt.eval_all(fh)
+    dtc = time.perf_counter() - t0c
+    first = chk_tc[0]
+    cpu_same_frame0 = bool(np.array_equal(first, want[0]))   # later frames: the oracle seeds with the previous frame's list
     print(json.dumps({"metric": "frames_x_senones_scored_per_sec", "value": T * S / (t / 1e3), "unit": "frame*senones/s",
                       "n_gpus": 1, "steps": args.steps, "ms_per_step": t, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"ptm_mgau {C} codebooks x {M} densities x {D} dims, {S} senones, topn 4, "
-                                             f"{T} frames/step (BASELINE configs[2])", "kernel_path": "exact CUDA-core"},
+                                             f"{T} frames/step (BASELINE configs[2])",
+                                 "kernel_path": "tcgen05 GEMM candidates + exact re-scoring (bit-identical to the exact scan)" if path == 1 else "exact CUDA-core",
+                                 "lists": stats[0], "lists_via_exact_fallback": stats[1],
+                                 "exact_path_ms_per_step_extrapolated": t_exact},
                       "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                    "algorithmic_flop_per_unit": flop / S, "traffic": None},
+                      "cpu_baseline": {"value": n_cpu * S / dtc, "unit": "frame*senones/s", "cores": 1, "kind": "port",
+                                       "sample": f"{n_cpu} frames of the same workload ({dtc:.1f} s); frame 0 identical to the GPU: {cpu_same_frame0}"},
+                      "gpu_launches": int(b.launch_count()),
                       "checksum": int(out[:8].to(torch.int64).sum().item())}))
     m.free()
 

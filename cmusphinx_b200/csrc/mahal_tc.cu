@@ -851,40 +851,27 @@ namespace {
 constexpr int kCand = 8;
 constexpr float kTiedEps = 32.f;      // bound on |approximate - exact| distance (raw log units)
 
-__device__ __forceinline__ float exact_dist(const float *xs, int tid, const float *m, const float *v, float det,
-                                            int len) {
-    float d = det;
-    for (int i = 0; i < len; ++i) {
-        const float diff = __fsub_rn(xs[i * 128 + tid], __ldg(m + i));
-        d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), __ldg(v + i)));
-    }
-    return d;
-}
-
-// block = 128 frames x one codebook (blockIdx.y), stream f
-template <int N>
+// Stage 2a: per (frame, codebook) the 8 best keys over the codebook's tiles x 4
+// column groups -> candidate density indices (+ the bound of condition (b)).
+// block = 128 frames x one codebook (blockIdx.y); reads are 64 B per thread and
+// tile, contiguous across the warp.
 __global__ void __launch_bounds__(128)
-tied_select_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int tn, int T_pad, int tpc,
-                   const uint4 *__restrict__ part, int2 *__restrict__ lists, int2 *__restrict__ flagged,
-                   int *__restrict__ n_flagged) {
-    extern __shared__ float xs[];   // [len][128]
-    const int tid = threadIdx.x, mg = blockIdx.y;
-    const int tl = blockIdx.x * 128 + tid;          // frame inside the chunk
-    const bool live = tl < tn;
-    const int len = g.featlen[f];
-    for (int i = 0; i < len; ++i)
-        xs[i * 128 + tid] = live ? feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i] : 0.f;
-    if (!live) return;
-    // 8 smallest keys over the codebook's tpc tiles x 4 column groups
+tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__restrict__ part,
+                  int32_t *__restrict__ cand /* [n_mgau][tn][8] */, float *__restrict__ bound /* [n_mgau][tn] */) {
+    const int tl = blockIdx.x * 128 + threadIdx.x, mg = blockIdx.y;
+    if (tl >= tn) return;
     int32_t k8[kCand]; int p8[kCand];
 #pragma unroll
     for (int j = 0; j < kCand; ++j) { k8[j] = 0x7fffffff; p8[j] = 0; }
+#pragma unroll 4
     for (int j = 0; j < tpc; ++j) {
         const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
+        uint4 q4[4];
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) q4[cg] = src[cg];
 #pragma unroll
         for (int cg = 0; cg < 4; ++cg) {
-            const uint4 q = src[cg];
-            const int32_t key[4] = {(int32_t)q.x, (int32_t)q.y, (int32_t)q.z, (int32_t)q.w};
+            const int32_t key[4] = {(int32_t)q4[cg].x, (int32_t)q4[cg].y, (int32_t)q4[cg].z, (int32_t)q4[cg].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
@@ -897,40 +884,80 @@ tied_select_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int 
             }
         }
     }
-    // exact distances of the candidates, sorted descending
-    const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
-    const size_t dbase = ((size_t)mg * g.n_feat + f) * g.n_density;
-    float ed[kCand]; int ei[kCand];
-    int n_ok = 0;
+    int32_t *o = cand + ((size_t)mg * tn + tl) * kCand;
+    int4 lo, hi;
+    int32_t idx[kCand];
 #pragma unroll
     for (int c = 0; c < kCand; ++c) {
-        float d = -3.0e38f; int idx = -1;
-        if (k8[c] != 0x7fffffff) {
-            idx = (p8[c] >> 2) * kTileN + (p8[c] & 3) * 64 + (63 - (k8[c] & 63));
-            if (idx < g.n_density) {
-                d = exact_dist(xs, tid, g.mean + pbase + (size_t)idx * len, g.var + pbase + (size_t)idx * len,
-                               __ldg(g.det + dbase + idx), len);
-                ++n_ok;
-            } else idx = -1;
-        }
+        const int i = (p8[c] >> 2) * kTileN + (p8[c] & 3) * 64 + (63 - (k8[c] & 63));
+        idx[c] = (k8[c] != 0x7fffffff && i < n_density) ? i : -1;
+    }
+    lo = make_int4(idx[0], idx[1], idx[2], idx[3]); hi = make_int4(idx[4], idx[5], idx[6], idx[7]);
+    reinterpret_cast<int4 *>(o)[0] = lo; reinterpret_cast<int4 *>(o)[1] = hi;
+    // every density that is not a candidate has approximate distance <= -k8[7]/32
+    bound[(size_t)mg * tn + tl] = -(float)k8[kCand - 1] * (1.0f / kAccScale);
+}
+
+// Stage 2b: 8 lanes per (frame, codebook), one candidate each: exact sequential
+// float32 distance (the reference's arithmetic) from a padded parameter copy
+// (row = [mean[lenp] | var[lenp]], 16-byte gathers), rank by shuffles, prove
+// conditions (a) and (b), write the top-N list or flag the pair.
+template <int N>
+__global__ void __launch_bounds__(128)
+tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int tn,
+                    const int32_t *__restrict__ cand, const float *__restrict__ bound,
+                    const float4 *__restrict__ rows, int lenp, int2 *__restrict__ lists,
+                    int2 *__restrict__ flagged, int *__restrict__ n_flagged) {
+    const int mg = blockIdx.y;
+    const int c = threadIdx.x & 7;
+    const int tl = blockIdx.x * 16 + (threadIdx.x >> 3);
+    if (tl >= tn) return;                      // whole 8-lane groups leave together
+    const unsigned gm = 0xffu << (threadIdx.x & 24);
+    const int len = g.featlen[f], q = lenp >> 2;
+    const int idx0 = cand[((size_t)mg * tn + tl) * kCand + c];
+    const int idx = idx0 >= 0 ? idx0 : 0;
+    const float4 *rp = rows + ((size_t)mg * g.n_density + idx) * (2 * q);
+    const float *x = feat + (size_t)(t0 + tl) * g.veclen + g.featoff[f];
+    float d = __ldg(g.det + ((size_t)mg * g.n_feat + f) * g.n_density + idx);
+#pragma unroll 2
+    for (int i4 = 0; i4 < q; ++i4) {
+        const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-        for (int r = kCand - 1; r >= 0; --r) {
-            if (r > c) continue;
-            if (r > 0 && d > ed[r - 1]) { ed[r] = ed[r - 1]; ei[r] = ei[r - 1]; }
-            else { ed[r] = d; ei[r] = idx; break; }
+        for (int e = 0; e < 4; ++e) {
+            if (i4 * 4 + e < len) {
+                const float diff = __fsub_rn(__ldg(x + i4 * 4 + e), mm[e]);
+                d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
+            }
         }
     }
-    // (b): every non-candidate has approximate distance <= -k8[7]/32 (+2 for the id bits)
-    const float bound = -(float)k8[kCand - 1] * (1.0f / kAccScale) + kTiedEps + 1.5e-5f * fabsf(ed[N]);
-    bool ok = n_ok == kCand && ed[N] > bound;
-    // (a): strictly decreasing integers over the N+1 best
+    if (idx0 < 0) d = -3.0e38f;
+    // rank among the 8 (descending, earlier candidate first on equal distances)
+    int rank = 0;
 #pragma unroll
-    for (int j = 0; j < N; ++j) ok = ok && ((int32_t)ed[j] > (int32_t)ed[j + 1]);
-    int2 *o = lists + ((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N;
+    for (int o = 1; o < 8; ++o) {
+        const int src = (c + o) & 7;
+        const float od = __shfl_sync(gm, d, (threadIdx.x & 24) + src, 32);
+        rank += (od > d || (od == d && src < c)) ? 1 : 0;
+    }
+    // (a): the N+1 best have pairwise different integer scores
+    const int32_t di = (int32_t)d;
+    bool clash = false;
+#pragma unroll
+    for (int o = 1; o < 8; ++o) {
+        const int src = (threadIdx.x & 24) + ((c + o) & 7);
+        const int orank = __shfl_sync(gm, rank, src, 32);
+        const int32_t odi = __shfl_sync(gm, di, src, 32);
+        clash |= (rank <= N && orank <= N && odi == di);
+    }
+    // (b): the (N+1)-th best beats everything that is not a candidate
+    const float bd = bound[(size_t)mg * tn + tl] + kTiedEps + 1.5e-5f * fabsf(d);
+    const bool bad = clash || idx0 < 0 || (rank == N && !(d > bd));
+    const bool ok = (__ballot_sync(gm, bad) & gm) == 0;
     if (ok) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = make_int2(ei[j], (int32_t)ed[j]);
-    } else {
+        if (rank < N)
+            lists[((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N + rank] = make_int2(idx0, di);
+    } else if (c == 0) {
         flagged[atomicAdd(n_flagged, 1)] = make_int2(tl, mg);
     }
 }
@@ -939,45 +966,70 @@ tied_select_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int 
 // distances in parallel into shared memory, then one thread replays eval_topn +
 // eval_cb in index order (same code as gmm_topn_kernel).
 template <int N, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 tied_fallback_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, const int2 *__restrict__ flagged,
-                     const int *__restrict__ n_flagged, int2 *__restrict__ lists) {
-    extern __shared__ float sh[];   // x[len] | d[n_density]
-    const int len = g.featlen[f];
-    float *x = sh, *dd = sh + ((len + 3) & ~3);
+                     const int *__restrict__ n_flagged, const float4 *__restrict__ rows, int lenp,
+                     int2 *__restrict__ lists) {
+    extern __shared__ float sh[];   // x[lenp] | d[n_density]
+    const int len = g.featlen[f], q = lenp >> 2;
+    float *x = sh, *dd = sh + lenp;
     const int n = *n_flagged;
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
         const int tl = flagged[w].x, mg = flagged[w].y;
         __syncthreads();
-        for (int i = threadIdx.x; i < len; i += blockDim.x) x[i] = feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i];
+        for (int i = threadIdx.x; i < lenp; i += blockDim.x)
+            x[i] = i < len ? feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i] : 0.f;
         __syncthreads();
-        const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
         const size_t dbase = ((size_t)mg * g.n_feat + f) * g.n_density;
         for (int c = threadIdx.x; c < g.n_density; c += blockDim.x) {
-            const float *m = g.mean + pbase + (size_t)c * len, *v = g.var + pbase + (size_t)c * len;
+            const float4 *rp = rows + ((size_t)mg * g.n_density + c) * (2 * q);
             float d = g.det[dbase + c];
-            for (int i = 0; i < len; ++i) {
-                const float diff = __fsub_rn(x[i], m[i]);
-                d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), v[i]));
+#pragma unroll 5
+            for (int i4 = 0; i4 < q; ++i4) {
+                const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4);
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (i4 * 4 + e < len) {
+                        const float diff = __fsub_rn(x[i4 * 4 + e], mm[e]);
+                        d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
+                    }
+                }
             }
             dd[c] = d;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            // warp 0 replays the scan: the list is replicated in every lane; 32
+            // densities are tested at once against the current worst score (it
+            // only ever rises, so a density that fails now would fail later too)
+            // and the survivors are inserted one by one in index order.
+            const int lane = threadIdx.x;
             TopI<N> ti;
             ti.init();
 #pragma unroll
             for (int i = 0; i < N; ++i) ti.seed(i, (int32_t)dd[i]);
-            for (int c = N; c < g.n_density; ++c) {
-                const float d = dd[c];
-                const int32_t worst = ti.s[N - 1];
-                if (MODE == 1) { if (d < (float)worst) continue; }
-                else { if ((int32_t)d < worst) continue; }
-                ti.insert((int32_t)d, c);
+            for (int c0 = 0; c0 < g.n_density; c0 += 32) {
+                const int c = c0 + lane;
+                const float d = c < g.n_density ? dd[c] : 0.f;
+                bool pend = c >= N && c < g.n_density;
+                for (;;) {
+                    const int32_t worst = ti.s[N - 1];
+                    if (MODE == 1) pend = pend && !(d < (float)worst);
+                    else pend = pend && !((int32_t)d < worst);
+                    const unsigned m = __ballot_sync(0xffffffffu, pend);
+                    if (!m) break;
+                    const int src = __ffs(m) - 1;
+                    const float ds = __shfl_sync(0xffffffffu, d, src);
+                    ti.insert((int32_t)ds, c0 + src);
+                    if (lane == src) pend = false;
+                }
             }
-            int2 *o = lists + ((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N;
+            if (lane == 0) {
+                int2 *o = lists + ((size_t)tl * g.n_mgau * g.n_feat + (size_t)mg * g.n_feat + f) * N;
 #pragma unroll
-            for (int j = 0; j < N; ++j) o[j] = make_int2(ti.cw[j], ti.s[j]);
+                for (int j = 0; j < N; ++j) o[j] = make_int2(ti.cw[j], ti.s[j]);
+            }
         }
     }
 }
@@ -990,9 +1042,12 @@ struct TcTied {
     int device = 0, mode = 1, n_feat = 0, tpc = 0, n_tiles_n = 0, n_sm = 148, topn = 4;
     int ksteps[B200_MAX_STREAMS] = {0, 0, 0, 0};
     float *dB[B200_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    float4 *dRows[B200_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [mgau][density][mean lenp | var lenp]
+    int lenp[B200_MAX_STREAMS] = {0, 0, 0, 0};
     float *dX = nullptr; size_t x_cap = 0;
     uint4 *dPart = nullptr; size_t part_cap = 0;
     int2 *dFlag = nullptr; size_t flag_cap = 0;
+    int32_t *dCand = nullptr; float *dBound = nullptr; size_t cand_cap = 0;   // pairs
     int *dCount = nullptr;          // [1 + n_feat]: running total per stream launch
     long long pairs = 0;
     int chunk = 0;                  // frames per internal chunk
@@ -1002,7 +1057,8 @@ void tc_tied_free(TcTied *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     for (auto b : p->dB) cudaFree(b);
-    cudaFree(p->dX); cudaFree(p->dPart); cudaFree(p->dFlag); cudaFree(p->dCount);
+    for (auto b : p->dRows) cudaFree(b);
+    cudaFree(p->dX); cudaFree(p->dPart); cudaFree(p->dFlag); cudaFree(p->dCount); cudaFree(p->dCand); cudaFree(p->dBound);
     delete p;
 }
 
@@ -1033,6 +1089,20 @@ TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const flo
         }
         ok = cudaMalloc((void **)&p->dB[f], B.size() * 4) == cudaSuccess &&
              cudaMemcpy(p->dB[f], B.data(), B.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        // padded parameter rows for the exact re-scoring gathers
+        const int lenp = (D + 3) & ~3;
+        p->lenp[f] = lenp;
+        std::vector<float> R((size_t)g.n_mgau * g.n_density * 2 * lenp, 0.f);
+        for (int mg = 0; mg < g.n_mgau; ++mg) {
+            const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+            for (int c = 0; c < g.n_density; ++c) {
+                float *row = R.data() + ((size_t)mg * g.n_density + c) * 2 * lenp;
+                memcpy(row, h_mean + pbase + (size_t)c * D, D * sizeof(float));
+                memcpy(row + lenp, h_var + pbase + (size_t)c * D, D * sizeof(float));
+            }
+        }
+        ok = ok && cudaMalloc((void **)&p->dRows[f], R.size() * 4) == cudaSuccess &&
+             cudaMemcpy(p->dRows[f], R.data(), R.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     ok = ok && cudaMalloc((void **)&p->dCount, 16 * sizeof(int)) == cudaSuccess;
     if (!ok) {
@@ -1060,10 +1130,13 @@ template <int N>
 static int tied_select_launch(TcTied *p, const GmmDev &g, int f, const float *d_feat, int t0, int tn, int T_pad,
                               int2 *lists, cudaStream_t st) {
     const int len = g.featlen[f];
-    tied_select_kernel<N><<<dim3((tn + 127) / 128, g.n_mgau), 128, (size_t)len * 128 * 4, st>>>(
-        g, f, d_feat, t0, tn, T_pad, p->tpc, p->dPart, lists, p->dFlag, p->dCount);
+    tied_merge_kernel<<<dim3((tn + 127) / 128, g.n_mgau), 128, 0, st>>>(g.n_density, tn, T_pad, p->tpc, p->dPart,
+                                                                       p->dCand, p->dBound);
     B200_LAUNCH_CHECK();
-    const size_t sh = ((size_t)((len + 3) & ~3) + g.n_density) * 4;
+    tied_rescore_kernel<N><<<dim3((tn + 15) / 16, g.n_mgau), 128, 0, st>>>(
+        g, f, d_feat, t0, tn, p->dCand, p->dBound, p->dRows[f], p->lenp[f], lists, p->dFlag, p->dCount);
+    B200_LAUNCH_CHECK();
+    const size_t sh = ((size_t)p->lenp[f] + g.n_density) * 4;
     if (sh > 200 * 1024) { set_error("codebook too large for the fallback kernel"); return B200_ERR_UNSUP; }
     auto kern = p->mode == 1 ? tied_fallback_kernel<N, 1> : tied_fallback_kernel<N, 2>;
     static bool attr[2] = {false, false};
@@ -1071,8 +1144,9 @@ static int tied_select_launch(TcTied *p, const GmmDev &g, int f, const float *d_
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr[p->mode - 1] = true;
     }
-    kern<<<p->n_sm * 2, 128, sh, st>>>(g, f, d_feat, t0, p->dFlag, p->dCount, lists);
+    kern<<<p->n_sm * 2, 256, sh, st>>>(g, f, d_feat, t0, p->dFlag, p->dCount, p->dRows[f], p->lenp[f], lists);
     B200_LAUNCH_CHECK();
+    (void)len;
     return B200_OK;
 }
 
@@ -1088,6 +1162,12 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             cudaFree(p->dPart); p->dPart = nullptr; p->part_cap = 0;
             B200_CUDA_OK(cudaMalloc((void **)&p->dPart, part_bytes));
             p->part_cap = part_bytes;
+        }
+        if (p->cand_cap < (size_t)cn * g.n_mgau) {
+            cudaFree(p->dCand); cudaFree(p->dBound); p->dCand = nullptr; p->dBound = nullptr; p->cand_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&p->dCand, (size_t)cn * g.n_mgau * kCand * sizeof(int32_t)));
+            B200_CUDA_OK(cudaMalloc((void **)&p->dBound, (size_t)cn * g.n_mgau * sizeof(float)));
+            p->cand_cap = (size_t)cn * g.n_mgau;
         }
         if (p->flag_cap < flag_bytes) {
             cudaFree(p->dFlag); p->dFlag = nullptr; p->flag_cap = 0;
