@@ -75,7 +75,7 @@ def main():
                       "config": {"workload": f"ptm_mgau {C} codebooks x {M} densities x {D} dims, {S} senones, topn 4, "
                                              f"{T} frames/step (BASELINE configs[2])",
                                  "kernel_path": "tcgen05 GEMM candidates + exact re-scoring (bit-identical to the exact scan)" if path == 1 else "exact CUDA-core",
-                                 "lists": stats[0], "lists_via_exact_fallback": stats[1],
+                                 "lists": stats[0], "lists_via_exact_fallback": stats[1], "max_gemm_vs_exact_raw_units": getattr(m, "tied_max_err", 0),
                                  "exact_path_ms_per_step_extrapolated": t_exact},
                       "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                    "algorithmic_flop_per_unit": flop / S, "traffic": None},

@@ -384,9 +384,9 @@ int b200_mgau_update_params(b200_mgau_t *m, const float *mean, const float *var,
     return B200_OK;
 }
 
-int b200_mgau_tied_stats(b200_mgau_t *m, long long out[2]) {
+int b200_mgau_tied_stats(b200_mgau_t *m, long long out[3]) {
     if (!m || !out) { set_error("null argument"); return B200_ERR_ARG; }
-    out[0] = out[1] = 0;
+    out[0] = out[1] = out[2] = 0;
     if (m->tct) tc_tied_stats(m->tct, out);
     return B200_OK;
 }

@@ -80,8 +80,9 @@ TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const flo
                        int device);
 void tc_tied_free(TcTied *p);
 int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int tn, int2 *lists, cudaStream_t st);
-// statistics of the last call: {pairs, pairs sent to the exact fallback}
-void tc_tied_stats(TcTied *p, long long out[2]);
+// statistics of the last call: {lists, lists sent to the exact fallback, largest
+// |GEMM - exact| distance seen on a best candidate (raw log units, 0 if <= 4)}
+void tc_tied_stats(TcTied *p, long long out[3]);
 
 // mahal_tc.cu: tensor-core path for single-stream .cont. models.
 struct TcPlan;

@@ -857,7 +857,7 @@ constexpr float kTiedEps = 32.f;      // bound on |approximate - exact| distance
 // tile, contiguous across the warp.
 __global__ void __launch_bounds__(128)
 tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__restrict__ part,
-                  int32_t *__restrict__ cand /* [n_mgau][tn][8] */, float *__restrict__ bound /* [n_mgau][tn] */) {
+                  int32_t *__restrict__ cand /* [n_mgau][tn][8] */, float *__restrict__ bound /* [n_mgau][tn][2] */) {
     const int tl = blockIdx.x * 128 + threadIdx.x, mg = blockIdx.y;
     if (tl >= tn) return;
     int32_t k8[kCand]; int p8[kCand];
@@ -895,7 +895,8 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     lo = make_int4(idx[0], idx[1], idx[2], idx[3]); hi = make_int4(idx[4], idx[5], idx[6], idx[7]);
     reinterpret_cast<int4 *>(o)[0] = lo; reinterpret_cast<int4 *>(o)[1] = hi;
     // every density that is not a candidate has approximate distance <= -k8[7]/32
-    bound[(size_t)mg * tn + tl] = -(float)k8[kCand - 1] * (1.0f / kAccScale);
+    bound[((size_t)mg * tn + tl) * 2] = -(float)k8[kCand - 1] * (1.0f / kAccScale);
+    bound[((size_t)mg * tn + tl) * 2 + 1] = -(float)k8[0] * (1.0f / kAccScale);   // approximate best, for the error statistic
 }
 
 // Stage 2b: 8 lanes per (frame, codebook), one candidate each: exact sequential
@@ -951,7 +952,12 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
         clash |= (rank <= N && orank <= N && odi == di);
     }
     // (b): the (N+1)-th best beats everything that is not a candidate
-    const float bd = bound[(size_t)mg * tn + tl] + kTiedEps + 1.5e-5f * fabsf(d);
+    const float bd = bound[((size_t)mg * tn + tl) * 2] + kTiedEps + 1.5e-5f * fabsf(d);
+    // statistic: largest |GEMM distance - exact distance| seen on a best candidate (+2 for the id bits)
+    if (c == 0 && idx0 >= 0) {
+        const float err = fabsf(bound[((size_t)mg * tn + tl) * 2 + 1] - d);
+        if (err > 4.f) atomicMax(n_flagged + 2, (int)fminf(err, 1.0e9f));
+    }
     const bool bad = clash || idx0 < 0 || (rank == N && !(d > bd));
     const bool ok = (__ballot_sync(gm, bad) & gm) == 0;
     if (ok) {
@@ -1117,13 +1123,13 @@ TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const flo
     return p;
 }
 
-void tc_tied_stats(TcTied *p, long long out[2]) {
+void tc_tied_stats(TcTied *p, long long out[3]) {
     out[0] = p ? p->pairs : 0;
-    out[1] = 0;
+    out[1] = out[2] = 0;
     if (!p) return;
-    int c = 0;
+    int c[3] = {0, 0, 0};
     cudaSetDevice(p->device);
-    if (cudaMemcpy(&c, p->dCount + 1, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) out[1] = c;
+    if (cudaMemcpy(c, p->dCount, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) { out[1] = c[1]; out[2] = c[2]; }
 }
 
 template <int N>
@@ -1166,7 +1172,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
         if (p->cand_cap < (size_t)cn * g.n_mgau) {
             cudaFree(p->dCand); cudaFree(p->dBound); p->dCand = nullptr; p->dBound = nullptr; p->cand_cap = 0;
             B200_CUDA_OK(cudaMalloc((void **)&p->dCand, (size_t)cn * g.n_mgau * kCand * sizeof(int32_t)));
-            B200_CUDA_OK(cudaMalloc((void **)&p->dBound, (size_t)cn * g.n_mgau * sizeof(float)));
+            B200_CUDA_OK(cudaMalloc((void **)&p->dBound, (size_t)cn * g.n_mgau * 2 * sizeof(float)));
             p->cand_cap = (size_t)cn * g.n_mgau;
         }
         if (p->flag_cap < flag_bytes) {

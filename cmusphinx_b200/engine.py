@@ -189,8 +189,9 @@ class Mgau:
     def tied_stats(self):
         """(lists produced, lists re-done by the exact-scan fallback) of the last
         tensor-core scoring call of a ptm / s2_semi back-end."""
-        out = (C.c_longlong * 2)()
+        out = (C.c_longlong * 3)()
         check(lib.b200_mgau_tied_stats(self._h, out), "tied_stats")
+        self.tied_max_err = int(out[2])
         return int(out[0]), int(out[1])
 
     # vt->free

@@ -171,8 +171,10 @@ int  b200_mgau_update_params(b200_mgau_t *m, const float *mean,
 int  b200_mgau_set_path(b200_mgau_t *m, int path);
 int  b200_mgau_get_path(const b200_mgau_t *m);
 /* Tied back-ends, tensor-core path: {(frame, codebook, stream) lists produced,
- * lists that went through the exact-scan fallback} of the last scoring call. */
-int  b200_mgau_tied_stats(b200_mgau_t *m, long long out[2]);
+ * lists that went through the exact-scan fallback, largest |GEMM - exact|
+ * distance observed on a best candidate in raw log units (0 if <= 4)} of the
+ * last scoring call. */
+int  b200_mgau_tied_stats(b200_mgau_t *m, long long out[3]);
 
 /* Batched dense scoring == ps_mgau_frame_eval(..., compallsen=1) for frames
  * 0..T-1 (PS/ms_mgau.c:162-205, PS/ptm_mgau.c:405-450,
