@@ -318,6 +318,9 @@ ms_mgau_init(cmd_ln_t *config, logmath_t *lmath, bin_mdef_t *mdef)
                        cmd_ln_int32_r(config, "-topn"), cmd_ln_int32_r(config, "-aw"), lb,
                        getenv("B200_DEVICE") ? atoi(getenv("B200_DEVICE")) : 0);
     ckd_free(s2c);
+    /* B200_MS_PATH=0 forces the exact CUDA-core kernels, 1 the tensor-core GEMM */
+    if (gpu && getenv("B200_MS_PATH") && b200_mgau_set_path(gpu, atoi(getenv("B200_MS_PATH"))))
+        E_WARN("b200: %s\n", b200_last_error());
     s = wrap(gpu, 0, config, NULL, &g, lb);
     return (ps_mgau_t *)s;
 }

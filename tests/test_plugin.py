@@ -72,3 +72,41 @@ def test_identical_hypotheses_ptm_and_compallsen(tmp_path):
         assert "b200_ptm back-end on GPU" in log
         assert [l.rsplit("(", 1)[0] for l in got] == [l.rsplit("(", 1)[0] for l in ref]
     assert "bids totaling five hundred twenty five" in ref[0]
+
+
+@needs
+@pytest.mark.gpu
+@pytest.mark.parametrize("passes", [[], ["-fwdflat", "no", "-bestpath", "no"]], ids=["3pass", "fwdtree"])
+def test_identical_hypotheses_fully_continuous(tmp_path, passes):
+    """hub4_cd_continuous_8gau_1s_c_d_dd (6144 senones x 8 Gaussians x 39 dims) goes
+    through the reference's generic ms back-end; the plug-in serves it from the
+    exact kernels (path 0: identical path score required) and from the tcgen05
+    Mahalanobis GEMM (path 1, scores within +-1: identical words required, and
+    the path score may move by at most a few units)."""
+    an4 = os.path.join(D, "lm", "an4")
+    if not os.path.exists(os.path.join(an4, "an4.dict")):
+        pytest.skip("an4 LM/dictionary not copied (make -C oracle ref)")
+    ctl = tmp_path / "c.ctl"
+    ctl.write_text("pittsburgh.littleendian\n")
+
+    def run(tag, env_extra):
+        hyp = tmp_path / f"{tag}.hyp"
+        cmd = [BATCH, "-hmm", os.path.join(D, "hmm", "cont"), "-lm", os.path.join(an4, "an4.ug.lm.DMP"), "-dict",
+               os.path.join(an4, "an4.dict"), "-fdict", os.path.join(an4, "filler.dict"), "-ctl", str(ctl), "-cepdir",
+               os.path.join(D, "test"), "-cepext", ".mfc", "-hyp", str(hyp), "-logfn", str(tmp_path / f"{tag}.log")] + passes
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+        env.update(env_extra)
+        subprocess.run(cmd, env=env, check=True, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        line = hyp.read_text().strip()
+        words, rest = line.rsplit("(", 1)
+        return words.strip(), int(rest.split()[-1].rstrip(")")), (tmp_path / f"{tag}.log").read_text(errors="replace")
+
+    w_cpu, s_cpu, _ = run("cpu", {})
+    w_ex, s_ex, log = run("exact", {"LD_PRELOAD": PLUGIN, "B200_MS_PATH": "0"})
+    assert "b200" in log.lower()
+    w_tc, s_tc, _ = run("tc", {"LD_PRELOAD": PLUGIN, "B200_MS_PATH": "1"})
+    if not passes:
+        assert w_cpu.split() == "P I T T S B U R G H".split()    # SURVEY.md Appendix B (-13086)
+    assert (w_ex, s_ex) == (w_cpu, s_cpu)
+    assert w_tc == w_cpu and abs(s_tc - s_cpu) <= 40, (s_tc, s_cpu)
