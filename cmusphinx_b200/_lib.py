@@ -107,6 +107,8 @@ _sig("b200_s3_score_utt_dev", C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp)
 _sig("b200_s3_frame_eval", C.c_int, vp, c_f32p, C.c_int32, c_u8p, c_i32p, c_i32p)
 _sig("b200_s3_last_ms", C.c_float, vp)
 _sig("b200_fp64_issue_rate", C.c_double, C.c_int)
+_sig("b200_feat_1s_c_d_dd_dev", C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp)
+_sig("b200_feat_1s_c_d_dd_host", C.c_int, c_f32p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int)
 _sig("b200_flags2list", C.c_int, c_u32p, C.c_int, c_u8p, C.c_int)
 _sig("b200_dev_alloc", vp, C.c_size_t, C.c_int)
 _sig("b200_dev_free", None, vp)

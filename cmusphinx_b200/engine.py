@@ -460,6 +460,20 @@ class HmmContext:
         return lib.b200_hmm_last_ms(self._h)
 
 
+# ------------------------------------------------------------ feature stage
+def feat_1s_c_d_dd(cep, utt_off=None, cmn: bool = True, device: int = 0) -> np.ndarray:
+    """Cepstra [T][13] of one or several utterances (utt_off: frame offsets,
+    len n_utt+1) -> [T][39] features: feat_s2mfc2feat_block_utt + cmn current +
+    feat_1s_c_d_dd_cep2feat (SB/feat/feat.c:726-769,1241-1265; cmn.c:150-186)."""
+    cep = _c(cep, np.float32)
+    T, cs = cep.shape
+    off = np.array([0, T], np.int32) if utt_off is None else _c(utt_off, np.int32)
+    out = np.zeros((T, 3 * cs), np.float32)
+    check(lib.b200_feat_1s_c_d_dd_host(_p(cep, C.c_float), _p(off, C.c_int32), off.size - 1, cs, 1 if cmn else 0,
+                                       _p(out, C.c_float), device), "feat_1s_c_d_dd")
+    return out
+
+
 # ------------------------------------------------------------ sphinx3 GMM
 S3_LOGBASE = float(np.float32(1.0003))   # sphinx3 -logbase default (float32 option, cmdln_macro.h:246)
 

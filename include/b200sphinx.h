@@ -360,6 +360,22 @@ float b200_s3_last_ms(b200_s3mgau_t *m);
  * non-fused mix the reference's arithmetic forces), measured on `device`. */
 double b200_fp64_issue_rate(int device);
 
+/* ===================================================== feature stage
+ * Full-utterance cepstra -> `1s_c_d_dd` dynamic features with `-cmn current`
+ * (or none), as acmod_process_cep(full_utt) computes them for batch decoding:
+ * feat_s2mfc2feat_block_utt (SB/feat/feat.c:1241-1265: pad with 3 copies of the
+ * first/last frame, then normalise), cmn (SB/feat/cmn.c:150-186),
+ * feat_1s_c_d_dd_cep2feat (feat.c:726-769).  Bit-exact.  The 3-stream
+ * `-svspec 0-12/13-25/26-38` models use the same layout.
+ * cep [T_total][cepsize] holds n_utt utterances back to back, utterance u =
+ * frames [utt_off[u], utt_off[u+1]); feat [T_total][3*cepsize].
+ * d_mean_scratch: n_utt*cepsize floats (cmn == 1). */
+int  b200_feat_1s_c_d_dd_dev(const float *d_cep, const int32_t *d_utt_off, int n_utt,
+                             int T_total, int cepsize, int cmn, float *d_mean_scratch,
+                             float *d_feat, void *stream);
+int  b200_feat_1s_c_d_dd_host(const float *cep, const int32_t *utt_off, int n_utt,
+                              int cepsize, int cmn, float *feat, int device);
+
 /* -------------------------------------------------- device memory helpers
  * (so a non-torch host can keep buffers resident) */
 void *b200_dev_alloc(size_t bytes, int device);

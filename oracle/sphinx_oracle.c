@@ -1166,3 +1166,49 @@ orc_s3_eval_utt(orc_s3_model_t *m, const float *feat, int T, int frame0, uint8_t
 }
 
 void orc_s3_counts(const orc_s3_model_t *m, int64_t *c) { c[0] = m->n_sen_eval; c[1] = m->n_gau_eval; }
+
+/* ======================================================================
+ * Feature stage next to the scorer ("next" row of the scope table):
+ * full-utterance 13-dim cepstra -> 39-dim 1s_c_d_dd features with
+ * -cmn current, as acmod_process_cep(full_utt) computes them:
+ *   feat_s2mfc2feat_block_utt  sphinxbase/src/libsphinxbase/feat/feat.c:1241-1265
+ *     (the utterance is padded with `win` = 3 copies of its first and last
+ *      frame BEFORE normalisation, so the padding enters the mean)
+ *   cmn()                      sphinxbase/src/libsphinxbase/feat/cmn.c:150-186
+ *     (float32 running sum in frame order, mean = sum / n, subtract)
+ *   feat_1s_c_d_dd_cep2feat    feat.c:726-769
+ * cep [T][cepsize] -> feat [T][3*cepsize].  cmn: 0 none, 1 current. */
+void
+orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *feat)
+{
+    const int win = 3, n = T + 2 * win;
+    float *buf = malloc(sizeof(float) * (size_t)n * cepsize), *mean = calloc(cepsize, sizeof(float));
+    int t, i;
+    if (T <= 0) { free(buf); free(mean); return; }
+    for (t = 0; t < n; ++t) {
+        int src = t - win;
+        if (src < 0) src = 0;
+        if (src > T - 1) src = T - 1;
+        memcpy(buf + (size_t)t * cepsize, cep + (size_t)src * cepsize, sizeof(float) * cepsize);
+    }
+    if (cmn) {
+        for (t = 0; t < n; ++t)
+            for (i = 0; i < cepsize; ++i) mean[i] += buf[(size_t)t * cepsize + i];
+        for (i = 0; i < cepsize; ++i) mean[i] /= n;
+        for (t = 0; t < n; ++t)
+            for (i = 0; i < cepsize; ++i) buf[(size_t)t * cepsize + i] -= mean[i];
+    }
+    for (t = 0; t < T; ++t) {
+        const float *c = buf + (size_t)(t + win) * cepsize;
+        float *f = feat + (size_t)t * 3 * cepsize;
+        for (i = 0; i < cepsize; ++i) {
+            float d1, d2;
+            f[i] = c[i];
+            f[cepsize + i] = c[2 * cepsize + i] - c[-2 * cepsize + i];
+            d1 = c[3 * cepsize + i] - c[-1 * cepsize + i];
+            d2 = c[1 * cepsize + i] - c[-3 * cepsize + i];
+            f[2 * cepsize + i] = d1 - d2;
+        }
+    }
+    free(buf); free(mean);
+}

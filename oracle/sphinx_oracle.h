@@ -154,6 +154,10 @@ void orc_s3_eval_utt(orc_s3_model_t *m, const float *feat, int T, int frame0,
                      int32_t *best);
 void orc_s3_counts(const orc_s3_model_t *m, int64_t *c);
 
+/* ---- feature stage: full-utterance cepstra -> 1s_c_d_dd features, -cmn current
+ * (feat.c:726-769, 1241-1265; cmn.c:150-186).  cep [T][cepsize], feat [T][3*cepsize]. */
+void orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *feat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,7 +262,7 @@ class RefAcmod:
         self.backend = ref().ref_acmod_backend(self.h).decode()
 
     def cep2feat(self, cep):
-        cep = _c(cep, np.float32)
+        cep = _c(cep, np.float32).copy()   # the reference normalises its input IN PLACE (feat.c:1308)
         out = np.zeros((cep.shape[0] + 16, self.featdim), np.float32)
         n = ref().ref_acmod_cep2feat(self.h, _p(cep, C.c_float), cep.shape[0], cep.shape[1], _p(out, C.c_float),
                                      out.shape[0])
@@ -440,3 +440,14 @@ class RefS3(_S3Common):
 
     def free(self):
         ref_s3().ref_s3_close(self.h)
+
+
+# ------------------------------------------------------- feature stage
+port.orc_feat_1s_c_d_dd.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p]
+
+
+def port_feat_1s_c_d_dd(cep, cmn=True):
+    cep = _c(cep, np.float32)
+    out = np.zeros((cep.shape[0], 3 * cep.shape[1]), np.float32)
+    port.orc_feat_1s_c_d_dd(_p(cep, C.c_float), cep.shape[0], cep.shape[1], 1 if cmn else 0, _p(out, C.c_float))
+    return out
