@@ -332,7 +332,10 @@ def run_ours(args):
                     "l2": f"inputs rotate over {N_FEAT_SETS} feature batches and every step streams a 1.0 GB score "
                           "matrix (> 126 MB L2) plus the parameter operand; no explicit flush"}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * DIM * 4,
-                        "d2h_bytes_per_step": T * N_SEN * 2, "steps": e2e_steps, "checksum": checksum},
+                        "d2h_bytes_per_step": T * N_SEN * 2, "steps": e2e_steps, "checksum": checksum,
+                        "bound": "host link: every step returns the 1.0 GB int16 score matrix the reference's API "
+                                 "hands to the search (acmod_score), so e2e runs at the PCIe D2H rate",
+                        "d2h_gbs_per_gpu": T * N_SEN * 2 * e2e_steps / float(t.item()) / 1e9},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -366,7 +369,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", type=int, default=None, help="force kernel family: 0 exact, 1 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--workload", default="ms_cont", choices=["ms_cont", "ptm", "hmm", "s3", "e2e_decode"],
+                    help="ms_cont = the headline (BASELINE configs[1]); the others run the secondary benches "
+                         "(bench_ptm.py configs[2], bench_hmm.py configs[3], bench_s3.py sphinx3 flavour, "
+                         "bench_e2e.py configs[0]/[4] subset) on one GPU")
+    args, rest = ap.parse_known_args()
+    if args.workload != "ms_cont":
+        import runpy
+        script = {"ptm": "bench_ptm.py", "hmm": "bench_hmm.py", "s3": "bench_s3.py", "e2e_decode": "bench_e2e.py"}[args.workload]
+        sys.argv = [script] + rest
+        runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), script), run_name="__main__")
+        return
+    if rest:
+        ap.error("unrecognised arguments: " + " ".join(rest))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
