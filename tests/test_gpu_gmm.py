@@ -401,3 +401,30 @@ def test_tied_tensor_core_path_identical_to_exact(C, Mden, streams, S, T, kind):
     np.testing.assert_array_equal(out, got_exact[17])
     print(f"tied TC: {n_lists} lists, {n_fallback} via exact fallback ({n_fallback / n_lists:.2e})")
     m.free()
+
+
+def test_config2_tolerance_at_scale():
+    """1e8 scores of BASELINE config 2 (frames 40000..59999 of the sweep in
+    tools/tc_fullscale_check.py): tcgen05 path vs the exact path.  The
+    north_star tolerance (+-1) must hold everywhere except for rank-4/rank-5
+    Gaussian pairs that the reference's OWN float32 rounding orders -- the
+    full 5e8-score sweep has exactly one (frame 43770, senone 3943: two
+    densities 0.4 raw log units apart in the reference's arithmetic, in the
+    other order in exact arithmetic, mixture weights 24 vs 52 -> |d| = 2;
+    profiles/r1_tc_fullscale_parity.json)."""
+    n_sen, M, D = 5000, 32, 39
+    mean, var, mixw = synth.cont_model(n_sen, M, D, 1234)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(n_sen, 1, M, n_sen, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(n_sen))
+    feat = synth.cont_features(mean, var, 20000, 5678 + 40000)
+    got = m.score(feat).astype(np.int32)
+    m.set_path(0)
+    want = m.score(feat).astype(np.int32)
+    d = np.abs(got - want)
+    beyond = np.argwhere(d > 1)
+    print(f"mismatch {float((d != 0).mean()):.3e}, beyond tolerance {len(beyond)}, max {d.max()}")
+    assert (d != 0).mean() < 5e-3 and d.max() <= 2
+    assert len(beyond) <= 1 and all((t, s) == (3770, 3943) for t, s in beyond)
+    m.free()
