@@ -391,3 +391,94 @@ int b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_ou
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------ .sen files
+// Senone-score dumps (PS/acmod.c:349-361 header, :885-923 acmod_write_scores,
+// :928-982 acmod_read_scores_internal): S3 header {version 0.1, mdef_file,
+// n_sen, logbase}, then per frame int16 n_active and either n_sen int16 scores
+// (all active) or n_active uint8 deltas + n_active int16 scores.
+extern "C" int b200_sen_write(const char *path, const char *mdef_file, int n_sen, double logbase,
+                              const int16_t *scores, int n_frames, const uint8_t *const *active,
+                              const int32_t *n_active) {
+    using namespace b200;
+    if (!path || !scores || n_sen <= 0 || n_sen > 32767 || n_frames < 0) { set_error("b200_sen_write: bad argument"); return B200_ERR_ARG; }
+    FILE *fp = fopen(path, "wb");
+    if (!fp) { set_error("cannot create '%s'", path); return B200_ERR_IO; }
+    fprintf(fp, "s3\nversion 0.1\nmdef_file %s\nn_sen %d\nlogbase %f\nendhdr\n", mdef_file ? mdef_file : "(null)", n_sen, logbase);
+    const uint32_t magic = 0x11223344u;
+    bool ok = fwrite(&magic, 4, 1, fp) == 1;
+    for (int t = 0; t < n_frames && ok; ++t) {
+        const int16_t *row = scores + (size_t)t * n_sen;
+        const int na = (active && n_active && active[t]) ? n_active[t] : n_sen;
+        const int16_t na16 = (int16_t)na;
+        ok = fwrite(&na16, 2, 1, fp) == 1;
+        if (na == n_sen) {
+            ok = ok && fwrite(row, 2, (size_t)n_sen, fp) == (size_t)n_sen;
+        } else {
+            ok = ok && fwrite(active[t], 1, (size_t)na, fp) == (size_t)na;
+            for (int i = 0, n = 0; i < na && ok; ++i) {
+                n += active[t][i];
+                if (n >= n_sen) { set_error("b200_sen_write: active list of frame %d leaves the senone range", t); fclose(fp); return B200_ERR_ARG; }
+                ok = fwrite(row + n, 2, 1, fp) == 1;
+            }
+        }
+    }
+    if (fclose(fp) != 0) ok = false;
+    if (!ok) { set_error("write to '%s' failed", path); return B200_ERR_IO; }
+    return B200_OK;
+}
+
+extern "C" int b200_sen_read(const char *path, int32_t dims[2], double *logbase, int16_t *scores, int32_t *n_active) {
+    using namespace b200;
+    if (!path || !dims) { set_error("b200_sen_read: bad argument"); return B200_ERR_ARG; }
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { set_error("cannot open '%s'", path); return B200_ERR_IO; }
+    char line[16384], key[4096], val[4096];
+    int n_sen = 0; double lb = 0.0; bool ok = true;
+    if (!fgets(line, sizeof line, fp) || strcmp(line, "s3\n") != 0) { set_error("%s: not an s3 file", path); fclose(fp); return B200_ERR_IO; }
+    for (;;) {
+        if (!fgets(line, sizeof line, fp)) { ok = false; break; }
+        if (sscanf(line, "%4095s", key) != 1) { ok = false; break; }
+        if (strcmp(key, "endhdr") == 0) break;
+        if (sscanf(line + strlen(key), "%4095s", val) != 1) continue;
+        if (strcmp(key, "n_sen") == 0) n_sen = atoi(val);
+        if (strcmp(key, "logbase") == 0) lb = atof(val);
+    }
+    uint32_t magic = 0;
+    if (!ok || fread(&magic, 4, 1, fp) != 1 || n_sen <= 0) { set_error("%s: bad senone-dump header", path); fclose(fp); return B200_ERR_IO; }
+    const bool swap = magic != 0x11223344u;
+    if (swap && bswap32(magic) != 0x11223344u) { set_error("%s: bad byte-order magic", path); fclose(fp); return B200_ERR_IO; }
+    auto sw16 = [&](int16_t v) { return swap ? (int16_t)__builtin_bswap16((uint16_t)v) : v; };
+    const int max_frames = scores ? dims[1] : 0x7fffffff;
+    int t = 0;
+    std::vector<uint8_t> deltas;
+    std::vector<int16_t> row((size_t)n_sen);
+    for (; t < max_frames; ++t) {
+        int16_t na16;
+        if (fread(&na16, 2, 1, fp) != 1) break;
+        const int na = sw16(na16);
+        if (na < 0 || na > n_sen) { set_error("%s: frame %d has %d active senones", path, t, na); fclose(fp); return B200_ERR_IO; }
+        std::fill(row.begin(), row.end(), (int16_t)0x7fff);     // SENSCR_DUMMY, PS/hmm.h
+        if (na == n_sen) {
+            if (fread(row.data(), 2, (size_t)n_sen, fp) != (size_t)n_sen) break;
+            for (auto &v : row) v = sw16(v);
+        } else {
+            deltas.resize((size_t)na);
+            if (na && fread(deltas.data(), 1, (size_t)na, fp) != (size_t)na) break;
+            bool short_read = false;
+            for (int i = 0, n = 0; i < na; ++i) {
+                n += deltas[i];
+                int16_t v;
+                if (n >= n_sen || fread(&v, 2, 1, fp) != 1) { short_read = true; break; }
+                row[n] = sw16(v);
+            }
+            if (short_read) break;
+        }
+        if (scores) std::copy(row.begin(), row.end(), scores + (size_t)t * n_sen);
+        if (n_active) n_active[t] = na;
+    }
+    fclose(fp);
+    dims[0] = n_sen; dims[1] = t;
+    if (logbase) *logbase = lb;
+    return B200_OK;
+}

@@ -139,6 +139,24 @@ def read_sendump(path: str, n_feat: int, n_density: int, n_sen: int):
                 mixw=mixw, mixw_cb=cb)
 
 
+def sen_write(path: str, scores: np.ndarray, logbase: float = LOGBASE, mdef_file: str = "(null)"):
+    """Dense senone-score dump readable by `-senin yes` / ps_decode_senscr (PS/acmod.c:349-361,885-923)."""
+    sc = _c(scores, np.int16)
+    check(lib.b200_sen_write(path.encode(), mdef_file.encode(), sc.shape[1], logbase, _p(sc, C.c_int16), sc.shape[0],
+                             None, None), "sen_write")
+
+
+def sen_read(path: str):
+    """-> (scores [T][n_sen] int16 with 0x7fff for unlisted senones, n_active [T], logbase)."""
+    dims = (C.c_int32 * 2)()
+    lb = C.c_double(0)
+    check(lib.b200_sen_read(path.encode(), dims, C.byref(lb), None, None), "sen_read")
+    sc = np.zeros((dims[1], dims[0]), np.int16)
+    na = np.zeros(dims[1], np.int32)
+    check(lib.b200_sen_read(path.encode(), dims, C.byref(lb), _p(sc, C.c_int16), _p(na, C.c_int32)), "sen_read")
+    return sc[:dims[1]], na[:dims[1]], lb.value
+
+
 # --------------------------------------------------------------------- GMM
 @dataclass
 class MgauConfig:

@@ -97,6 +97,19 @@ int  b200_s3_read_tmat(const char *path, int32_t dims[4], float *data);
 int  b200_s3_read_sendump(const char *path, int32_t dims[5], uint8_t *mixw,
                           uint8_t cb[16]);
 
+/* PS/acmod.c:349-361,885-982: senone-score dump files (`-senlogdir` output,
+ * `-senin yes` / ps_decode_senscr input).  Write: scores [n_frames][n_sen]; with
+ * active == NULL every frame is written dense, else frame t carries the
+ * n_active[t] uint8 deltas active[t] and only those scores.  Read: first call
+ * with scores == NULL fills dims = {n_sen, n_frames}; second call (dims[1] =
+ * capacity in frames) fills scores [n_frames][n_sen] (unlisted senones =
+ * SENSCR_DUMMY 0x7fff) and n_active [n_frames]. */
+int  b200_sen_write(const char *path, const char *mdef_file, int n_sen, double logbase,
+                    const int16_t *scores, int n_frames,
+                    const uint8_t *const *active, const int32_t *n_active);
+int  b200_sen_read(const char *path, int32_t dims[2], double *logbase, int16_t *scores,
+                   int32_t *n_active);
+
 /* ============================================================ GMM scoring
  * One handle type for the three pocketsphinx back-ends.  The handle owns a
  * device-resident copy of the (precomputed) parameters.

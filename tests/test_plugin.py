@@ -110,3 +110,78 @@ def test_identical_hypotheses_fully_continuous(tmp_path, passes):
         assert w_cpu.split() == "P I T T S B U R G H".split()
     assert (w_ex, s_ex) == (w_cpu, s_cpu)
     assert w_tc == w_cpu and abs(s_tc - s_cpu) <= 40, (s_tc, s_cpu)
+
+
+@needs
+def test_sen_dump_roundtrip_against_the_reference(tmp_path):
+    """CPU-only: the reference writes a senone dump (-senlogdir); our reader
+    parses it (dense and delta-compressed frames), our writer re-emits it dense,
+    and the unmodified decoder fed with OUR file (-senin yes) returns the same
+    hypothesis as from the cepstra."""
+    import numpy as np
+    import cmusphinx_b200 as b
+    senlog = tmp_path / "senlog"
+    senlog.mkdir()
+    hyp0, _ = _decode(tmp_path, "a", ["442c0201"], os.path.join(D, "test", "wsj"), ".mfc",
+                      ["-senlogdir", str(senlog), "-fwdflat", "no", "-bestpath", "no"], {})
+    sc, na, lb = b.sen_read(str(senlog / "442c0201.sen"))
+    assert sc.shape[1] == 5150 and sc.shape[0] > 100 and abs(lb - 1.0001) < 1e-3
+    assert (na < 5150).any() and (sc[na < 5150] == 0x7fff).any()         # compressed frames, dummies filled in
+    for t in (0, sc.shape[0] // 2):
+        listed = sc[t] != 0x7fff
+        assert listed.sum() == na[t] and (sc[t][listed] >= 0).all()
+    # dense scores for every senone (compallsen) through the reference, re-written by us
+    senlog2 = tmp_path / "senlog2"
+    senlog2.mkdir()
+    _decode(tmp_path, "b", ["442c0201"], os.path.join(D, "test", "wsj"), ".mfc",
+            ["-senlogdir", str(senlog2), "-compallsen", "yes", "-fwdflat", "no", "-bestpath", "no"], {})
+    sc2, na2, _ = b.sen_read(str(senlog2 / "442c0201.sen"))
+    assert (na2 == 5150).all()
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    b.sen_write(str(ours / "442c0201.sen"), sc2, lb)
+    assert (ours / "442c0201.sen").read_bytes()[-sc2.nbytes // sc2.shape[0]:] == \
+        (senlog2 / "442c0201.sen").read_bytes()[-sc2.nbytes // sc2.shape[0]:]
+    hyp1, _ = _decode(tmp_path, "c", ["442c0201"], str(ours), ".sen", ["-senin", "yes", "-fwdflat", "no", "-bestpath", "no"], {})
+    assert hyp1 == hyp0
+
+
+@needs
+@pytest.mark.gpu
+def test_gpu_scores_via_sen_file_drive_the_unmodified_decoder(tmp_path):
+    """No plug-in at all: GPU senone scores -> .sen file -> `pocketsphinx_batch
+    -senin yes`.  Same hypothesis and path score as the reference decoding the
+    cepstra itself (s2_semi model, fwdtree + fwdflat + bestpath)."""
+    import numpy as np
+    import cases
+    import cmusphinx_b200 as b
+    name = "semi_hub4wsj.npz"
+    if not cases.have_model(name) or not orc.have_ref():
+        pytest.skip("model files not present")
+    g = cases.load(name)
+    r = orc.RefAcmod(cases.model_dir(name))
+    cep = orc.read_mfc(os.path.join(D, "test", "wsj", "442c0201.mfc"))
+    feat_ref = r.cep2feat(cep)
+    r.close()
+    feat = b.feat_1s_c_d_dd(cep)                       # device feature stage
+    np.testing.assert_array_equal(feat, feat_ref)
+    m = b.tied_from_model_dir(cases.model_dir(name), int(g["n_sen"]), topn=4, logbase=orc.LOGBASE)
+    scores = m.score(feat)
+    m.free()
+    d = tmp_path / "sen"
+    d.mkdir()
+    b.sen_write(str(d / "442c0201.sen"), scores, orc.LOGBASE)
+    hyp_gpu, _ = _decode(tmp_path, "g", ["442c0201"], str(d), ".sen", ["-senin", "yes"], {})
+    # the yardstick is the reference's own dump fed back to itself: its -senin path scores the
+    # utterance 10 units differently from decoding the cepstra directly (-52953 vs -52963)
+    refdump = tmp_path / "refdump"
+    refdump.mkdir()
+    hyp_direct, _ = _decode(tmp_path, "r", ["442c0201"], os.path.join(D, "test", "wsj"), ".mfc",
+                            ["-compallsen", "yes", "-senlogdir", str(refdump)], {})
+    hyp_cpu, _ = _decode(tmp_path, "s", ["442c0201"], str(refdump), ".sen", ["-senin", "yes"], {})
+    assert hyp_gpu == hyp_cpu
+    assert [l.rsplit("(", 1)[0] for l in hyp_gpu] == [l.rsplit("(", 1)[0] for l in hyp_direct]
+    ref_sc, _, _ = b.sen_read(str(refdump / "442c0201.sen"))
+    # frame 0 identical; later frames up to the documented rank-N tie deviation of the seed-free lists
+    np.testing.assert_array_equal(scores[0], ref_sc[0])
+    assert (scores != ref_sc[:scores.shape[0]]).mean() < 1e-4
