@@ -43,7 +43,116 @@ def run(tmp, tag, hmm, preload, extra):
             "xrt_elapsed": float(x[-1][1]) if x else None, "hyp": open(hyp).read()}
 
 
+def run_sharded(tmp, tag, hmm, ctl_lines, cepdir, cepext, extra, preload, procs):
+    """The reference's own batch sharding (-ctloffset/-ctlcount, batch.c:560-640): `procs` decoder
+    processes over one control file; returns wall seconds and the concatenated hypothesis lines."""
+    import time
+    ctl = os.path.join(tmp, f"{tag}.ctl")
+    open(ctl, "w").write("\n".join(ctl_lines) + "\n")
+    n = len(ctl_lines)
+    per = (n + procs - 1) // procs
+    env = dict(os.environ, LD_LIBRARY_PATH=REF + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    if preload:
+        env["LD_PRELOAD"] = PLUGIN
+    ps, hyps = [], []
+    t0 = time.perf_counter()
+    for i in range(procs):
+        if i * per >= n:
+            break
+        hyp = os.path.join(tmp, f"{tag}.{i}.hyp")
+        hyps.append(hyp)
+        cmd = [os.path.join(REF, "pocketsphinx_batch"), "-hmm", os.path.join(D, "hmm", hmm), "-lm",
+               os.path.join(D, "lm", "wsj0vp.5000.DMP"), "-dict", os.path.join(D, "lm", "cmu07a.dic"), "-ctl", ctl,
+               "-ctloffset", str(i * per), "-ctlcount", str(per), "-cepdir", cepdir, "-cepext", cepext, "-hyp", hyp,
+               "-logfn", os.path.join(tmp, f"{tag}.{i}.log")] + extra
+        ps.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in ps:
+        if p.wait(timeout=1800) != 0:
+            raise RuntimeError(f"decoder process failed ({tag})")
+    wall = time.perf_counter() - t0
+    lines = []
+    for h in hyps:
+        lines += open(h).read().splitlines()
+    return wall, lines
+
+
+def batch_pipeline(replicas, procs):
+    """BASELINE configs[4] scaled to what the tree bundles: the 7 WSJ utterances x `replicas`,
+    whole-box wall-clock xRT with `procs` decoder processes, three ways:
+      cpu     the reference decodes the cepstra (GMM + search on the host cores)
+      plugin  same processes with the GPU plug-in LD_PRELOADed (scoring on one shared GPU)
+      senin   one GPU stage for the whole batch (features + scoring of all frames in a few
+              launches, .sen files) followed by search-only decoder processes (-senin yes)"""
+    import time
+    import numpy as np
+    import cmusphinx_b200 as b
+
+    def read_mfc(path):                      # batch.c:185-233: int32 count, float32 data, either byte order
+        n = int(np.fromfile(path, dtype="<i4", count=1)[0])
+        data = np.fromfile(path, dtype="<f4", offset=4)
+        if data.size != n:
+            data = np.fromfile(path, dtype=">f4", offset=4).astype(np.float32)
+        return data.reshape(-1, 13).astype(np.float32)
+    res = {"utterances": 7 * replicas, "decoder_processes": procs, "models": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        cepdir = os.path.join(tmp, "cep")
+        os.makedirs(cepdir)
+        names, speech_frames = [], 0
+        ceps = {}
+        for r in range(replicas):
+            for u in UTTS:
+                nm = f"{u}_{r:03d}"
+                os.symlink(os.path.join(D, "test", "wsj", u + ".mfc"), os.path.join(cepdir, nm + ".mfc"))
+                names.append(nm)
+                if u not in ceps:
+                    ceps[u] = read_mfc(os.path.join(D, "test", "wsj", u + ".mfc"))
+                speech_frames += ceps[u].shape[0]
+        speech_s = speech_frames / 100.0
+        res["speech_s"] = speech_s
+        for hmm, kind in (("ptm", 1), ("hub4wsj_sc_8k", 2)):
+            w_cpu, h_cpu = run_sharded(tmp, f"cpu_{hmm}", hmm, names, cepdir, ".mfc", [], False, procs)
+            w_plg, h_plg = run_sharded(tmp, f"plg_{hmm}", hmm, names, cepdir, ".mfc", [], True, procs)
+            # ---- GPU stage for the whole batch
+            t0 = time.perf_counter()
+            mm = b.mdef_maps(os.path.join(D, "hmm", hmm, "mdef"))
+            s2c = mm["sen2cimap"].astype(np.uint8) if kind == 1 else None   # ptm: senone -> codebook
+            n_sen = mm["n_sen"]
+            m = b.tied_from_model_dir(os.path.join(D, "hmm", hmm), n_sen, sen2cb=s2c, topn=4)
+            t_load = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sendir = os.path.join(tmp, f"sen_{hmm}")
+            os.makedirs(sendir)
+            order = [n.rsplit("_", 1)[0] for n in names]
+            cep_all = np.concatenate([ceps[u] for u in order])
+            off = np.concatenate([[0], np.cumsum([ceps[u].shape[0] for u in order])]).astype(np.int32)
+            feat = b.feat_1s_c_d_dd(cep_all, off)
+            scores = m.score(feat)
+            t_score = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for i, nm in enumerate(names):
+                b.sen_write(os.path.join(sendir, nm + ".sen"), scores[off[i]:off[i + 1]])
+            t_write = time.perf_counter() - t0
+            m.free()
+            w_sen, h_sen = run_sharded(tmp, f"sen_{hmm}", hmm, names, sendir, ".sen", ["-senin", "yes"], False, procs)
+            words = lambda hs: [l.rsplit("(", 1)[0] for l in hs]
+            res["models"].append({
+                "model": hmm, "frames": int(off[-1]),
+                "cpu": {"wall_s": w_cpu, "xrt_wall": w_cpu / speech_s},
+                "plugin": {"wall_s": w_plg, "xrt_wall": w_plg / speech_s, "identical_hyp_lines": h_plg == h_cpu,
+                           "identical_words": words(h_plg) == words(h_cpu)},
+                "senin_pipeline": {"gpu_stage_s": t_score, "sen_write_s": t_write, "search_wall_s": w_sen,
+                                   "wall_s": t_score + t_write + w_sen, "xrt_wall": (t_score + t_write + w_sen) / speech_s,
+                                   "model_load_s_excluded": t_load, "identical_words": words(h_sen) == words(h_cpu),
+                                   "gpu_frame_senones_per_s": int(off[-1]) * n_sen / t_score}})
+    return res
+
+
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--replicas", type=int, default=16, help="copies of the 7 WSJ utterances in the batch arm (0 = skip)")
+    ap.add_argument("--procs", type=int, default=os.cpu_count() or 8)
+    args = ap.parse_args()
     out = {"metric": "batch_decode_xRT", "unit": "xRT (lower is better)", "higher_is_better": False, "data": "bundled WSJ .mfc x7",
            "runs": []}
     with tempfile.TemporaryDirectory() as tmp:
@@ -57,6 +166,8 @@ def main():
                                     "identical_words": [l.rsplit("(", 1)[0] for l in cpu["hyp"].splitlines()] ==
                                                        [l.rsplit("(", 1)[0] for l in gpu["hyp"].splitlines()],
                                     "identical_path_scores": cpu["hyp"] == gpu["hyp"]})
+    if args.replicas > 0:
+        out["batch"] = batch_pipeline(args.replicas, args.procs)
     print(json.dumps(out))
 
 

@@ -60,6 +60,7 @@ _sig("b200_s3_read_gauden", C.c_int, C.c_char_p, c_i32p, c_i32p, c_f32p)
 _sig("b200_s3_read_mixw", C.c_int, C.c_char_p, c_i32p, c_f32p)
 _sig("b200_s3_read_tmat", C.c_int, C.c_char_p, c_i32p, c_f32p)
 _sig("b200_s3_read_sendump", C.c_int, C.c_char_p, c_i32p, c_u8p, c_u8p)
+_sig("b200_mdef_read_maps", C.c_int, C.c_char_p, c_i32p, c_i16p, c_i16p)
 _sig("b200_sen_write", C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_double, c_i16p, C.c_int, vp, c_i32p)
 _sig("b200_sen_read", C.c_int, C.c_char_p, c_i32p, C.POINTER(C.c_double), c_i16p, c_i32p)
 _sig("b200_ms_create", vp, C.POINTER(MgauCfg), c_f32p, c_f32p, c_f32p, c_u8p, c_u32p)

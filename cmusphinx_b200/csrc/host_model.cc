@@ -482,3 +482,146 @@ extern "C" int b200_sen_read(const char *path, int32_t dims[2], double *logbase,
     if (logbase) *logbase = lb;
     return B200_OK;
 }
+
+// ------------------------------------------------------------ mdef maps
+// The two maps the scorers need from the model definition:
+//   sen2cimap[s]  CI phone owning senone s   (ptm: senone -> codebook, PS/ptm_mgau.c:836-848)
+//   cd2cisen[s]   CI senone at the same state position (sphinx3 CI-GMM selection,
+//                 sphinx3/include/mdef.h:199-201; PS/bin_mdef.c:462-497)
+// built exactly like bin_mdef_read (PS/bin_mdef.c:330-507): walk the phones in
+// order, state position j of phone i -> senone sseq[ssid][j]; the FIRST phone
+// that uses a senone defines its CI phone.  Reads binary "BMDF" files and the
+// text format 0.3 (PS/mdef.c:505-602).
+namespace {
+struct MdefMaps { int n_ciphone = 0, n_emit = 0, n_ci_sen = 0, n_sen = 0; std::vector<int16_t> sen2ci, cd2ci; };
+
+bool mdef_finish(MdefMaps &m, const std::vector<int32_t> &phone_ci, const std::vector<std::vector<int32_t>> &phone_sen) {
+    m.sen2ci.assign((size_t)m.n_sen, -1);
+    m.cd2ci.assign((size_t)m.n_sen, -1);
+    for (int i = 0; i < m.n_ci_sen && i < m.n_sen; ++i) m.cd2ci[i] = (int16_t)i;
+    for (size_t i = 0; i < phone_sen.size(); ++i) {
+        const int ci = phone_ci[i];
+        for (size_t j = 0; j < phone_sen[i].size(); ++j) {
+            const int sn = phone_sen[i][j];
+            if (sn < 0 || sn >= m.n_sen || ci < 0 || ci >= m.n_ciphone) { b200::set_error("mdef: senone/phone id out of range"); return false; }
+            if (m.sen2ci[sn] == -1) m.sen2ci[sn] = (int16_t)ci;
+            if (j < phone_sen[ci].size()) m.cd2ci[sn] = (int16_t)phone_sen[ci][j];
+        }
+    }
+    return true;
+}
+
+bool mdef_read_bin(FILE *fh, bool swap, MdefMaps &m) {
+    auto rd32 = [&](int32_t &v) { if (fread(&v, 4, 1, fh) != 1) return false; if (swap) v = (int32_t)b200::bswap32((uint32_t)v); return true; };
+    int32_t ver, hdr, h[10];
+    if (!rd32(ver) || !rd32(hdr) || fseek(fh, hdr, SEEK_CUR) != 0) return false;
+    for (auto &v : h) if (!rd32(v)) return false;
+    const int n_ciphone = h[0], n_phone = h[1], n_emit = h[2], n_sseq = h[6], n_cd_tree = h[8];
+    m.n_ciphone = n_ciphone; m.n_emit = n_emit; m.n_ci_sen = h[3]; m.n_sen = h[4];
+    if (n_emit <= 0) { b200::set_error("mdef: heterogeneous topologies are not supported"); return false; }
+    const long pos = ftell(fh);
+    fseek(fh, 0, SEEK_END);
+    const long end = ftell(fh);
+    fseek(fh, pos, SEEK_SET);
+    std::vector<uint8_t> buf((size_t)(end - pos));
+    if (fread(buf.data(), 1, buf.size(), fh) != buf.size()) return false;
+    size_t o = 0;
+    for (int i = 0; i < n_ciphone; ++i) { while (o < buf.size() && buf[o]) ++o; ++o; }
+    o = (o + 3) & ~(size_t)3;
+    o += (size_t)n_cd_tree * 8;                       // cd_tree_t: int16 ctx, int16 n_down, int32 down
+    const size_t need = o + (size_t)n_phone * 12 + 4;
+    if (need > buf.size()) return false;
+    std::vector<int32_t> ssid((size_t)n_phone), ci((size_t)n_phone);
+    for (int i = 0; i < n_phone; ++i) {
+        int32_t v; memcpy(&v, &buf[o + (size_t)i * 12], 4);
+        ssid[i] = swap ? (int32_t)b200::bswap32((uint32_t)v) : v;
+        ci[i] = i < n_ciphone ? i : (int8_t)buf[o + (size_t)i * 12 + 9];   // info.cd.ctx[0]
+    }
+    o += (size_t)n_phone * 12;
+    int32_t sseq_size; memcpy(&sseq_size, &buf[o], 4);
+    if (swap) sseq_size = (int32_t)b200::bswap32((uint32_t)sseq_size);
+    o += 4;
+    if (o + (size_t)sseq_size * 2 > buf.size() || sseq_size < n_sseq * n_emit) return false;
+    std::vector<std::vector<int32_t>> ps((size_t)n_phone);
+    for (int i = 0; i < n_phone; ++i) {
+        if (ssid[i] < 0 || ssid[i] >= n_sseq) return false;
+        for (int j = 0; j < n_emit; ++j) {
+            uint16_t v; memcpy(&v, &buf[o + ((size_t)ssid[i] * n_emit + j) * 2], 2);
+            if (swap) v = __builtin_bswap16(v);
+            ps[i].push_back(v);
+        }
+    }
+    return mdef_finish(m, ci, ps);
+}
+
+bool mdef_read_text(FILE *fh, MdefMaps &m) {
+    char line[16384];
+    int n_base = -1, n_tri = -1, n_state_map = -1;
+    bool versioned = false;
+    std::vector<std::string> ciname;
+    std::vector<int32_t> ci;
+    std::vector<std::vector<int32_t>> ps;
+    while (fgets(line, sizeof line, fh)) {
+        char *p = line;
+        while (*p == ' ' || *p == '\t') ++p;
+        if (*p == '#' || *p == '\n' || *p == 0) continue;
+        if (!versioned) { versioned = true; if (strncmp(p, "0.3", 3) != 0) { b200::set_error("mdef: text version is not 0.3"); return false; } continue; }
+        int v; char key[64];
+        if (n_base < 0 || n_tri < 0 || n_state_map < 0 || m.n_sen == 0 || m.n_ci_sen == 0 || m.n_ciphone == -7) {
+            if (sscanf(p, "%d %63s", &v, key) == 2) {
+                if (!strcmp(key, "n_base")) { n_base = v; continue; }
+                if (!strcmp(key, "n_tri")) { n_tri = v; continue; }
+                if (!strcmp(key, "n_state_map")) { n_state_map = v; continue; }
+                if (!strcmp(key, "n_tied_state")) { m.n_sen = v; continue; }
+                if (!strcmp(key, "n_tied_ci_state")) { m.n_ci_sen = v; continue; }
+                if (!strcmp(key, "n_tied_tmat")) continue;
+            }
+        }
+        // phone line: base lft rt p attrib tmat s0 s1 ... N
+        char base[256], lft[256], rt[256], wpos[64], attrib[256];
+        int tmat, used = 0;
+        if (sscanf(p, "%255s %255s %255s %63s %255s %d%n", base, lft, rt, wpos, attrib, &tmat, &used) != 6) continue;
+        std::vector<int32_t> st;
+        char *q = p + used;
+        for (;;) {
+            while (*q == ' ' || *q == '\t') ++q;
+            if (*q == 'N' || *q == 0 || *q == '\n') break;
+            st.push_back((int32_t)strtol(q, &q, 10));
+        }
+        int cid;
+        if ((int)ciname.size() < n_base) { cid = (int)ciname.size(); ciname.push_back(base); }
+        else {
+            cid = -1;
+            for (size_t k = 0; k < ciname.size(); ++k) if (ciname[k] == base) { cid = (int)k; break; }
+            if (cid < 0) { b200::set_error("mdef: triphone of unknown base phone %s", base); return false; }
+        }
+        ci.push_back(cid);
+        ps.push_back(st);
+    }
+    if (n_base <= 0 || ps.empty()) { b200::set_error("mdef: no phones found"); return false; }
+    m.n_ciphone = n_base; m.n_emit = (int)ps[0].size();
+    return mdef_finish(m, ci, ps);
+}
+}  // namespace
+
+extern "C" int b200_mdef_read_maps(const char *path, int32_t dims[4], int16_t *sen2cimap, int16_t *cd2cisen) {
+    using namespace b200;
+    if (!path || !dims) { set_error("b200_mdef_read_maps: bad argument"); return B200_ERR_ARG; }
+    FILE *fh = fopen(path, "rb");
+    if (!fh) { set_error("cannot open '%s'", path); return B200_ERR_IO; }
+    uint32_t magic = 0;
+    MdefMaps m;
+    bool ok;
+    if (fread(&magic, 4, 1, fh) == 1 && (magic == 0x46444d42u || magic == 0x424d4446u)) {
+        ok = mdef_read_bin(fh, magic == 0x424d4446u, m);
+    } else {
+        rewind(fh);
+        ok = mdef_read_text(fh, m);
+    }
+    fclose(fh);
+    if (!ok) { if (g_last_error.empty() || g_last_error.find("mdef") == std::string::npos) set_error("%s: malformed model definition", path); return B200_ERR_IO; }
+    dims[0] = m.n_sen; dims[1] = m.n_ci_sen; dims[2] = m.n_ciphone; dims[3] = m.n_emit;
+    if (sen2cimap) std::copy(m.sen2ci.begin(), m.sen2ci.end(), sen2cimap);
+    if (cd2cisen) std::copy(m.cd2ci.begin(), m.cd2ci.end(), cd2cisen);
+    return B200_OK;
+}

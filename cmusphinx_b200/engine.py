@@ -139,6 +139,16 @@ def read_sendump(path: str, n_feat: int, n_density: int, n_sen: int):
                 mixw=mixw, mixw_cb=cb)
 
 
+def mdef_maps(path: str):
+    """Model definition (binary BMDF or text 0.3) -> dict(n_sen, n_ci_sen, n_ciphone, n_emit,
+    sen2cimap int16[n_sen], cd2cisen int16[n_sen]) as bin_mdef_read builds them (PS/bin_mdef.c:462-497)."""
+    dims = (C.c_int32 * 4)()
+    check(lib.b200_mdef_read_maps(path.encode(), dims, None, None), "mdef_maps")
+    a = np.zeros(dims[0], np.int16); c = np.zeros(dims[0], np.int16)
+    check(lib.b200_mdef_read_maps(path.encode(), dims, _p(a, C.c_int16), _p(c, C.c_int16)), "mdef_maps")
+    return dict(n_sen=dims[0], n_ci_sen=dims[1], n_ciphone=dims[2], n_emit=dims[3], sen2cimap=a, cd2cisen=c)
+
+
 def sen_write(path: str, scores: np.ndarray, logbase: float = LOGBASE, mdef_file: str = "(null)"):
     """Dense senone-score dump readable by `-senin yes` / ps_decode_senscr (PS/acmod.c:349-361,885-923)."""
     sc = _c(scores, np.int16)

@@ -97,6 +97,14 @@ int  b200_s3_read_tmat(const char *path, int32_t dims[4], float *data);
 int  b200_s3_read_sendump(const char *path, int32_t dims[5], uint8_t *mixw,
                           uint8_t cb[16]);
 
+/* Model-definition maps (PS/bin_mdef.c:330-507 binary "BMDF", PS/mdef.c:505-602
+ * text 0.3): dims = {n_sen, n_ci_sen, n_ciphone, n_emit_state};
+ * sen2cimap[n_sen] = CI phone owning each senone (the ptm senone -> codebook
+ * map, PS/ptm_mgau.c:836-848), cd2cisen[n_sen] = CI senone at the same state
+ * position (sphinx3's mdef_t.cd2cisen).  Either pointer may be NULL. */
+int  b200_mdef_read_maps(const char *path, int32_t dims[4], int16_t *sen2cimap,
+                         int16_t *cd2cisen);
+
 /* PS/acmod.c:349-361,885-982: senone-score dump files (`-senlogdir` output,
  * `-senin yes` / ps_decode_senscr input).  Write: scores [n_frames][n_sen]; with
  * active == NULL every frame is written dense, else frame t carries the

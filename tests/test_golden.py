@@ -200,3 +200,27 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".c")):
                 txt = open(os.path.join(dp, fn), errors="replace").read()
                 assert "liboracle" not in txt and "sphinx_oracle" not in txt and "libref_shim" not in txt, fn
+
+
+# ------------------------------------------------------------------- mdef maps
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("hmm", ["ptm", "hub4wsj_sc_8k", "cont"])
+def test_mdef_maps_match_reference(hmm):
+    """Native model-definition reader (binary BMDF: ptm, hub4wsj_sc_8k; text 0.3: the
+    sphinx3 continuous model) against the reference's bin_mdef (sen2cimap) and, for
+    the text file, sphinx3's mdef_init (cd2cisen)."""
+    d = os.path.join(orc.DATA_DIR, "hmm", hmm)
+    if not os.path.exists(os.path.join(d, "mdef")):
+        pytest.skip("model not bundled")
+    mm = b.mdef_maps(os.path.join(d, "mdef"))
+    r = orc.RefAcmod(d)
+    assert mm["n_sen"] == r.n_sen
+    np.testing.assert_array_equal(mm["sen2cimap"].astype(np.uint8), r.sen2cimap())
+    r.close()
+    assert (mm["cd2cisen"][:mm["n_ci_sen"]] == np.arange(mm["n_ci_sen"])).all()
+    assert (mm["cd2cisen"] >= 0).all() and (mm["cd2cisen"] < mm["n_ci_sen"]).all()
+    if hmm == "cont" and orc.have_ref_s3():
+        r3 = orc.RefS3(*(os.path.join(d, n) for n in ("means", "variances", "mixture_weights", "mdef")))
+        np.testing.assert_array_equal(mm["cd2cisen"], r3.cd2cisen())
+        assert mm["n_ci_sen"] == r3.n_ci_sen
+        r3.free()

@@ -146,9 +146,10 @@ def test_s3_gpu_real_model():
         pytest.skip("continuous model not bundled")
     mean, var, mixw = b.read_s3_cont_arrays(mf, vf, wf)
     S = mean.shape[0]
-    n_ci = 144                                   # 48 CI phones x 3 states
+    mm = b.mdef_maps(os.path.join(d, "mdef"))     # the model's own CD -> CI senone map (text mdef 0.3)
+    n_ci, cd2ci = mm["n_ci_sen"], mm["cd2cisen"].astype(np.int32)
+    assert n_ci == 144 and mm["n_sen"] == S      # 48 CI phones x 3 states
     rng = np.random.default_rng(4)
-    cd2ci = np.arange(S, dtype=np.int32); cd2ci[n_ci:] = rng.integers(0, n_ci, S - n_ci)
     m = b.S3Mgau.from_files(mf, vf, wf, cd2ci, n_ci)
     p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
     T = 40
