@@ -111,7 +111,10 @@ def batch_pipeline(replicas, procs):
         res["speech_s"] = speech_s
         for hmm, kind in (("ptm", 1), ("hub4wsj_sc_8k", 2)):
             w_cpu, h_cpu = run_sharded(tmp, f"cpu_{hmm}", hmm, names, cepdir, ".mfc", [], False, procs)
-            w_plg, h_plg = run_sharded(tmp, f"plg_{hmm}", hmm, names, cepdir, ".mfc", [], True, procs)
+            # one GPU is time-sliced between processes (no MPS here): the plug-in is a one-process-per-GPU
+            # binding, so its arm runs with 2 decoder processes; 16 contexts on one GPU cost 35 s on this batch
+            plg_procs = min(2, procs)
+            w_plg, h_plg = run_sharded(tmp, f"plg_{hmm}", hmm, names, cepdir, ".mfc", [], True, plg_procs)
             # ---- GPU stage for the whole batch
             t0 = time.perf_counter()
             mm = b.mdef_maps(os.path.join(D, "hmm", hmm, "mdef"))
@@ -138,7 +141,7 @@ def batch_pipeline(replicas, procs):
             res["models"].append({
                 "model": hmm, "frames": int(off[-1]),
                 "cpu": {"wall_s": w_cpu, "xrt_wall": w_cpu / speech_s},
-                "plugin": {"wall_s": w_plg, "xrt_wall": w_plg / speech_s, "identical_hyp_lines": h_plg == h_cpu,
+                "plugin": {"decoder_processes": plg_procs, "wall_s": w_plg, "xrt_wall": w_plg / speech_s, "identical_hyp_lines": h_plg == h_cpu,
                            "identical_words": words(h_plg) == words(h_cpu)},
                 "senin_pipeline": {"gpu_stage_s": t_score, "sen_write_s": t_write, "search_wall_s": w_sen,
                                    "wall_s": t_score + t_write + w_sen, "xrt_wall": (t_score + t_write + w_sen) / speech_s,
