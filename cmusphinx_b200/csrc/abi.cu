@@ -64,7 +64,8 @@ struct b200_mgau {
     int utt_T = 0;
     uint8_t *d_active = nullptr; size_t active_cap = 0;
     int16_t *d_row = nullptr;
-    int16_t *h_row = nullptr;   // pinned
+    int16_t *h_row = nullptr;   // pinned; kernels write it directly (UVA), no per-frame D2H call
+    uint8_t *h_active = nullptr; size_t h_active_cap = 0;   // pinned copy of the caller's active list, read by kernels directly
     float *h_frame = nullptr;   // pinned, one frame of features
 };
 
@@ -344,6 +345,7 @@ void b200_mgau_free(b200_mgau_t *m) {
         for (int i = 0; i < 4; ++i) if (m->ring[r][i]) cudaEventDestroy(m->ring[r][i]);
     cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_active); cudaFree(m->d_row);
     if (m->h_row) cudaFreeHost(m->h_row);
+    if (m->h_active) cudaFreeHost(m->h_active);
     if (m->h_frame) cudaFreeHost(m->h_frame);
     delete m;
 }
@@ -513,31 +515,39 @@ static int serve_frame(b200_mgau_t *m, int frame, int16_t *senscr, const uint8_t
     const GmmDev &g = m->g;
     cudaStream_t st = m->st[0];
     const bool use_active = !compallsen;
+    // Per-frame serving is latency bound (one call per frame of the decoder's
+    // search): the active list and the result row live in pinned host memory
+    // that the kernels read / write directly, so a frame costs one or two
+    // launches and one stream synchronisation, no copy calls.
+    const uint8_t *act = nullptr;
     if (use_active) {
         if (n_active < 0 || (n_active > 0 && !senone_active)) { set_error("bad active list"); return B200_ERR_ARG; }
-        int rc = ensure((void **)&m->d_active, &m->active_cap, (size_t)std::max(n_active, 1));
-        if (rc) return rc;
-        if (n_active > 0)
-            B200_CUDA_OK(cudaMemcpyAsync(m->d_active, senone_active, (size_t)n_active, cudaMemcpyHostToDevice, st));
+        if (m->h_active_cap < (size_t)std::max(n_active, 1)) {
+            if (m->h_active) cudaFreeHost(m->h_active);
+            m->h_active = nullptr; m->h_active_cap = 0;
+            const size_t cap = (size_t)std::max(n_active, g.n_sen + g.n_sen / 255 + 64);
+            B200_CUDA_OK(cudaMallocHost((void **)&m->h_active, cap));
+            m->h_active_cap = cap;
+        }
+        if (n_active > 0) memcpy(m->h_active, senone_active, (size_t)n_active);
+        act = m->h_active;
     }
     int rc;
     if (m->kind == 0) {
         const int16_t *raw = m->d_uraw + (size_t)frame * g.n_sen;
         if (use_active) {
             if (n_active == 0) return B200_OK;
-            B200_CUDA_OK(cudaMemcpyAsync(m->d_row, raw, (size_t)g.n_sen * 2, cudaMemcpyDeviceToDevice, st));
-            if ((rc = gmm_launch_ms_active_normalize(raw, m->d_active, n_active, m->d_row, st))) return rc;
+            if ((rc = gmm_launch_ms_active_normalize(raw, act, n_active, m->h_row, st))) return rc;   // writes active entries only
         } else {
             B200_CUDA_OK(cudaMemcpyAsync(m->d_row, raw, (size_t)g.n_sen * 2, cudaMemcpyDeviceToDevice, st));
             if ((rc = gmm_launch_normalize(m->d_row, 1, g.n_sen, st))) return rc;
+            B200_CUDA_OK(cudaMemcpyAsync(m->h_row, m->d_row, (size_t)g.n_sen * 2, cudaMemcpyDeviceToHost, st));
         }
     } else {
         const int2 *l = m->d_ulists + (size_t)frame * g.n_mgau * g.n_feat * g.topn;
-        // out row index is t - t0 with T=1,t0=0 -> write straight into d_row
-        if ((rc = gmm_launch_tied_senone(g, l, 1, 0, 1, m->kind == 2, use_active ? m->d_active : nullptr,
-                                         use_active ? n_active : 0, m->d_row, st))) return rc;
+        // out row index is t - t0 with T=1,t0=0 -> write straight into the pinned row
+        if ((rc = gmm_launch_tied_senone(g, l, 1, 0, 1, m->kind == 2, act, use_active ? n_active : 0, m->h_row, st))) return rc;
     }
-    B200_CUDA_OK(cudaMemcpyAsync(m->h_row, m->d_row, (size_t)g.n_sen * 2, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     if (m->kind == 0 && use_active) {
         // the reference writes only the active entries of the caller's array

@@ -841,8 +841,9 @@ int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cu
 //      conditions prove that the result equals the reference's full scan:
 //        (a) the 5 best candidates have pairwise different (int32) scores
 //            (then no tie / same-integer-bucket rule of eval_cb can matter), and
-//        (b) the 5th best exact distance beats  d~(8th candidate) + eps, an
-//            upper bound on every density that is not a candidate.
+//        (b) the 5th best exact distance beats  max(d~(8th candidate), best d~ any
+//            64-column group may have dropped) + eps, an upper bound on every
+//            density that is not a candidate.
 //   3. tied_fallback_kernel: the few pairs where (a) or (b) fails (~1e-3) get
 //      the reference's literal scan over the whole codebook.
 // ====================================================================
@@ -863,6 +864,10 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     int32_t k8[kCand]; int p8[kCand];
 #pragma unroll
     for (int j = 0; j < kCand; ++j) { k8[j] = 0x7fffffff; p8[j] = 0; }
+    // Values a 64-column group dropped (its 5th best and worse) never reach this
+    // kernel; each of them is >= the group's 4th kept key, so the smallest such
+    // key over all groups bounds them all.
+    int32_t gmin = 0x7fffffff;
 #pragma unroll 4
     for (int j = 0; j < tpc; ++j) {
         const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
@@ -872,6 +877,7 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
 #pragma unroll
         for (int cg = 0; cg < 4; ++cg) {
             const int32_t key[4] = {(int32_t)q4[cg].x, (int32_t)q4[cg].y, (int32_t)q4[cg].z, (int32_t)q4[cg].w};
+            gmin = min(gmin, key[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
@@ -894,8 +900,9 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     }
     lo = make_int4(idx[0], idx[1], idx[2], idx[3]); hi = make_int4(idx[4], idx[5], idx[6], idx[7]);
     reinterpret_cast<int4 *>(o)[0] = lo; reinterpret_cast<int4 *>(o)[1] = hi;
-    // every density that is not a candidate has approximate distance <= -k8[7]/32
-    bound[((size_t)mg * tn + tl) * 2] = -(float)k8[kCand - 1] * (1.0f / kAccScale);
+    // every density that is not a candidate -- kept by its group but not among the
+    // 8 best, or dropped inside its group -- has approximate distance <= this
+    bound[((size_t)mg * tn + tl) * 2] = -(float)min(k8[kCand - 1], gmin) * (1.0f / kAccScale);
     bound[((size_t)mg * tn + tl) * 2 + 1] = -(float)k8[0] * (1.0f / kAccScale);   // approximate best, for the error statistic
 }
 
