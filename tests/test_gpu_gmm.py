@@ -369,6 +369,11 @@ def test_tied_tensor_core_path_identical_to_exact(C, Mden, streams, S, T, kind):
     # duplicated Gaussians (identical distance for every frame) in codebook 0, stream 0
     mean[0, 0, 700 % Mden] = mean[0, 0, 3]; var[0, 0, 700 % Mden] = var[0, 0, 3]
     mean[0, 0, 200] = mean[0, 0, 100]; var[0, 0, 200] = var[0, 0, 100]
+    # six near-identical Gaussians inside ONE 64-column group of the GEMM tile: the group keeps only
+    # its 4 best keys, so the 5th/6th never reach the merge stage -- the bound must notice
+    for k in range(1, 6):
+        mean[0, 0, 64 + k] = mean[0, 0, 64] + rng.standard_normal(mean.shape[3]).astype(np.float32) * 1e-3
+        var[0, 0, 64 + k] = var[0, 0, 64]
     flat_m = np.concatenate([mean[:, f, :, :L].reshape(C, -1) for f, L in enumerate(streams)], 1)
     flat_v = np.concatenate([var[:, f, :, :L].reshape(C, -1) for f, L in enumerate(streams)], 1)
     pv_parts, pd_parts = [], []
@@ -385,6 +390,8 @@ def test_tied_tensor_core_path_identical_to_exact(C, Mden, streams, S, T, kind):
     # frames sitting on the duplicated Gaussians: exact ties inside the top 4
     feat[5, :streams[0]] = mean[0, 0, 3, :streams[0]]
     feat[6, :streams[0]] = mean[0, 0, 100, :streams[0]] + 0.01
+    feat[7, :streams[0]] = mean[0, 0, 64, :streams[0]]
+    feat[8, :streams[0]] = mean[0, 0, 66, :streams[0]] + 0.003
     got_tc = m.score(feat)
     n_lists, n_fallback = m.tied_stats()
     assert n_lists == T * C * F
