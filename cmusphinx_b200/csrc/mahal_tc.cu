@@ -48,6 +48,8 @@
 // running CTAs stream the same A tiles (L2 reuse) against different B tiles.
 #include "gmm_dev.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -81,6 +83,8 @@ struct TcParams {
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
     int m31;                // the constant 31 (63 for tied lists), kept opaque to the compiler (see make_key)
+    const float *scaleA;    // fp16 operands: per-column power-of-two scale of the A operand [8 * 2 * ksteps]
+    const int *flag;        // fp16 operands: != 0 when a feature would overflow fp16 -> the TF32 kernel runs instead
     uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
     int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
     uint8_t logadd[256];
@@ -142,6 +146,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -165,6 +177,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // (2<<7, 2<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                             ((uint32_t)(kTileM >> 4) << 24);
+// same with a = b = F16 (format code 0): kind::f16, K = 16 per instruction
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
@@ -231,13 +245,20 @@ __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], con
 // gX[m_tile][dim 0..Dp)[128 rows].  20 KB per tile for D = 39; the x^2 / hi / lo
 // expansion (4x the bytes) happens inside the SM so it never crosses L2.
 __global__ void __launch_bounds__(kTileM)
-tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D, int Dp, float *__restrict__ gX) {
+tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D, int Dp, float *__restrict__ gX,
+               const float *__restrict__ lim /* [D] or null */, int *__restrict__ flag) {
     __shared__ float tile[kTileM][41];
     const int mt = blockIdx.x, r = threadIdx.x;
     const int t0 = mt * kTileM;
     // coalesced read of the tile's rows (stream `off`..`off+D` of each frame vector)
     const int nrow = min(kTileM, T - t0);
-    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)(t0 + e / D) * stride + off + e % D];
+    bool over = false;
+    for (int e = r; e < nrow * D; e += kTileM) {
+        const float v = feat[(size_t)(t0 + e / D) * stride + off + e % D];
+        tile[e / D][e % D] = v;
+        if (lim) over |= !(fabsf(v) <= lim[e % D]);     // also catches NaN
+    }
+    if (over) atomicOr(flag, 1);
     __syncthreads();
     for (int i = 0; i < Dp; ++i)
         gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
@@ -256,20 +277,30 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
 //         reduces its 64 accumulator columns to their 4 best keys and stores
 //         them; tied_select_kernel merges the groups of a codebook and rescores
 //         the survivors exactly.
-template <int M, int KS, int MODE>
+// HALF 1: the operands are fp16 hi/lo pairs (22 significant bits, the same
+//         three-product scheme) issued as kind::f16 MMAs with K = 16: half the
+//         MMA instructions of the TF32 form.  fp16's 5-bit exponent is handled by
+//         per-column power-of-two scales (A column k times 2^e_k, B column k
+//         times 2^-e_k, chosen at load so that B fills the fp16 range); a frame
+//         whose scaled features would overflow sets *p.flag in the prep kernel
+//         and the batch is scored by the TF32 kernel instead (each kernel checks
+//         the flag first).  KS counts 16-column steps then.
+template <int M, int KS, int MODE, int HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (p.flag != nullptr && ((*p.flag != 0) == (HALF != 0))) return;   // the other operand format handles this batch
     constexpr int SPT = kTileN / M;       // senones per tile
     constexpr int kStages = ring_depth(KS);
-    constexpr int DP = 4 * KS;            // padded dims per frame in the X tile
+    constexpr int DP = (HALF ? 8 : 4) * KS;   // padded dims per frame in the X tile
     constexpr int kXBytes = DP * kTileM * 4;
     uint8_t *sB = smem;                                         // KS * 16 KB
     uint8_t *sA = sB + KS * kBStageBytes;                       // kStages * 8 KB
     uint8_t *sX = sA + kStages * kAStageBytes;                  // DP * 128 * 4
     uint8_t *sMixw = sX + kXBytes;                              // 256 B
     uint8_t *sTab = sMixw + 256;                                // 256 B
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256);
+    float *sScale = reinterpret_cast<float *>(sTab + 256);      // 16 * KS floats (HALF only; <= 320 B reserved)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256 + 320);
     // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2]
     constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kStages,
                   T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
@@ -294,6 +325,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) sTab[i] = p.logadd[i];
+    if (HALF) for (int i = threadIdx.x; i < 16 * KS; i += kThreads) sScale[i] = p.scaleA[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -356,10 +388,18 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                         const uint64_t dAlo = dAhi + (uint64_t)((kAStageBytes / 2) >> 4);
                         const uint64_t dBhi = dB0 + (uint64_t)((j * kBStageBytes) >> 4);
                         const uint64_t dBlo = dBhi + (uint64_t)((kBStageBytes / 2) >> 4);
-                        tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
-                        if (!(p.dbg & 2)) {
-                            tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
-                            tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
+                        if (HALF) {
+                            tc_mma_f16(d_tmem, dAhi, dBhi, kIdescF16, j > 0 ? 1u : 0u);
+                            if (!(p.dbg & 2)) {
+                                tc_mma_f16(d_tmem, dAhi, dBlo, kIdescF16, 1u);
+                                tc_mma_f16(d_tmem, dAlo, dBhi, kIdescF16, 1u);
+                            }
+                        } else {
+                            tc_mma_tf32(d_tmem, dAhi, dBhi, kIdesc, j > 0 ? 1u : 0u);
+                            if (!(p.dbg & 2)) {
+                                tc_mma_tf32(d_tmem, dAhi, dBlo, kIdesc, 1u);
+                                tc_mma_tf32(d_tmem, dAlo, dBhi, kIdesc, 1u);
+                            }
                         }
                         tc_commit(BAR(A_EMPTY + stage));
                         if (j == KS - 1) tc_commit(BAR(T_FULL + acc));
@@ -393,6 +433,34 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 if (lane == 0) mbar_arrive(BAR(X_EMPTY));     // staging buffer may be refilled
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
+                    if (HALF) {
+                        // 16 columns: scaled value -> fp16 hi + fp16 lo (exact remainder, rounded once)
+                        uint32_t hp[8], lp[8];
+#pragma unroll
+                        for (int kk = 0; kk < 16; kk += 2) {
+                            float a[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int k = j * 16 + kk + e;
+                                if (k < 2) a[e] = sScale[k];
+                                else {
+                                    const int i = (k - 2) >> 1;
+                                    a[e] = ((k - 2) & 1) ? __fmul_rn(x[i], sScale[k]) : __fmul_rn(__fmul_rn(x[i], sScale[k]), x[i]);
+                                }
+                            }
+                            const __half2 h = __floats2half2_rn(a[0], a[1]);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(__fsub_rn(a[0], hf.x), __fsub_rn(a[1], hf.y));
+                            hp[kk >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                            lp[kk >> 1] = *reinterpret_cast<const uint32_t *>(&l);
+                        }
+                        mbar_wait(BAR(A_EMPTY + stage), phase ^ 1);
+                        uint4 *dsth = reinterpret_cast<uint4 *>(sA + stage * kAStageBytes);
+                        dsth[0 * kTileM + r] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                        dsth[1 * kTileM + r] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                        dsth[2 * kTileM + r] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                        dsth[3 * kTileM + r] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+                    } else {
                     float hi[8], lo[8];
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
@@ -410,6 +478,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     dst[1 * kTileM + r] = make_float4(hi[4], hi[5], hi[6], hi[7]);
                     dst[2 * kTileM + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     dst[3 * kTileM + r] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(BAR(A_FULL + stage));
@@ -622,39 +691,137 @@ float tf32_round(float x) {
     return r;
 }
 
-// One row (= one Gaussian) of a B tile: K columns [c_hi, c_lo, -v_0, 2 mu_0 v_0, ...]
-// times -32, each split into TF32 hi/lo, in the [kstep][hi|lo][chunk][256 rows][4]
-// layout.  mu == nullptr: a padding Gaussian far below anything real.
+// Columns of one Gaussian's B row, times -32 (see make_key), in double:
+// col[0] = the whole constant det - sum mu^2 v, col[2+2i] = -v_i, col[3+2i] = 2 mu_i v_i.
+// mu == nullptr: a padding Gaussian far below anything real.
+void b_row_cols(std::vector<double> &col, int KP, int D, const float *mu, const float *v, float det) {
+    col.assign(KP, 0.0);
+    if (!mu) { col[0] = 3.0e7 * kAccScale; return; }
+    double c = (double)det;
+    for (int i = 0; i < D; ++i) {
+        c -= (double)mu[i] * (double)mu[i] * (double)v[i];
+        col[2 + 2 * i] = -(double)v[i];
+        col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
+    }
+    for (int k = 0; k < KP; ++k) col[k] *= -(double)kAccScale;
+    col[0] = c * -(double)kAccScale;
+}
+
+// TF32 hi/lo row in the [kstep(8 cols)][hi|lo][chunk][256 rows][4 f32] layout;
+// the constant is spread over columns 0 and 1 (4 x 11 bits).
 void build_b_row(float *tile, int r, int ksteps, int D, const float *mu, const float *v, float det) {
     const int KP = ksteps * 8;
-    std::vector<double> col(KP, 0.0);
-    double hi1 = 0, lo1 = 0, hi2 = 0, lo2 = 0;
-    if (mu) {
-        double c = (double)det;
-        for (int i = 0; i < D; ++i) {
-            c -= (double)mu[i] * (double)mu[i] * (double)v[i];
-            col[2 + 2 * i] = -(double)v[i];
-            col[3 + 2 * i] = 2.0 * (double)mu[i] * (double)v[i];
-        }
-        // everything is stored times -32 (see make_key)
-        c *= -(double)kAccScale;
-        for (int k = 2; k < KP; ++k) col[k] *= -(double)kAccScale;
-        hi1 = tf32_round((float)c); lo1 = tf32_round((float)(c - hi1));
-        const double c2 = c - hi1 - lo1;
-        hi2 = tf32_round((float)c2); lo2 = tf32_round((float)(c2 - hi2));
-    } else {
-        hi1 = 3.0e7 * kAccScale;
-    }
+    std::vector<double> col;
+    b_row_cols(col, KP, D, mu, v, det);
+    const double c = col[0];
+    const double hi1 = tf32_round((float)c), lo1 = mu ? tf32_round((float)(c - hi1)) : 0.0;
+    const double c2 = mu ? c - hi1 - lo1 : 0.0;
+    const double hi2 = tf32_round((float)c2), lo2 = tf32_round((float)(c2 - hi2));
     for (int k = 0; k < KP; ++k) {
         float hi, lo;
         if (k == 0) { hi = (float)hi1; lo = (float)lo1; }
         else if (k == 1) { hi = (float)hi2; lo = (float)lo2; }
         else { hi = tf32_round((float)col[k]); lo = tf32_round((float)(col[k] - (double)hi)); }
-        const int j = k / 8, c = (k % 8) / 4, e = k % 4;
+        const int j = k / 8, c4 = (k % 8) / 4, e = k % 4;
         float *st = tile + (size_t)j * (kBStageBytes / 4);
-        st[((0 * 2 + c) * kTileN + r) * 4 + e] = hi;
-        st[((1 * 2 + c) * kTileN + r) * 4 + e] = lo;
+        st[((0 * 2 + c4) * kTileN + r) * 4 + e] = hi;
+        st[((1 * 2 + c4) * kTileN + r) * 4 + e] = lo;
     }
+}
+
+// fp16 hi/lo row in the [kstep(16 cols)][hi|lo][chunk][256 rows][8 f16] layout
+// (the same bytes per stage); column k is stored times 2^-e[k].
+void build_b_row_half(__half *tile, int r, int ksteps, int D, const float *mu, const float *v, float det,
+                      const int *e) {
+    const int KP = ksteps * 16;
+    std::vector<double> col;
+    b_row_cols(col, KP, D, mu, v, det);
+    auto put = [&](int k, double val) {
+        const __half hi = __float2half_rn((float)val);
+        const __half lo = __float2half_rn((float)(val - (double)__half2float(hi)));
+        const int j = k / 16, c8 = (k % 16) / 8, el = k % 8;
+        __half *st = tile + (size_t)j * (kBStageBytes / 2);
+        st[((0 * 2 + c8) * kTileN + r) * 8 + el] = hi;
+        st[((1 * 2 + c8) * kTileN + r) * 8 + el] = lo;
+        return val - (double)__half2float(hi) - (double)__half2float(lo);
+    };
+    // constant: columns 0 and 1 share the scale e[0]; column 1 takes what column 0 left over
+    const double c = std::ldexp(col[0], -e[0]);
+    const double rest = put(0, c);
+    put(1, rest);
+    for (int k = 2; k < KP; ++k) put(k, std::ldexp(col[k], -e[k]));
+}
+
+// Per-column scales of the fp16 form and the feature limits that go with them.
+struct HalfOperand {
+    __half *dB = nullptr;
+    float *dScale = nullptr;     // [16 * ksteps] A-column factors 2^e
+    float *dLim = nullptr;       // [D] largest |x_i| the scaled A operand can hold
+    int *dFlag = nullptr;
+    int ksteps = 0;
+    void release() { cudaFree(dB); cudaFree(dScale); cudaFree(dLim); cudaFree(dFlag); dB = nullptr; dScale = dLim = nullptr; dFlag = nullptr; ksteps = 0; }
+};
+
+int half_ksteps(int D) {
+    const int need = (2 * D + 2 + 15) / 16;
+    return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 5 ? 5 : 0));
+}
+
+bool half_enabled() {
+    const char *e = getenv("B200_TC_F16");
+    return !(e && atoi(e) == 0);
+}
+
+// rows(tile, r, mu, v, det) -> false for a padding row.
+template <typename RowFn>
+bool build_half_operand(HalfOperand &h, int n_tiles_n, int D, RowFn rows) {
+    h.ksteps = half_ksteps(D);
+    if (!h.ksteps || !half_enabled()) { h.ksteps = 0; return false; }
+    const int KP = h.ksteps * 16;
+    std::vector<double> colmax(KP, 0.0), col;
+    for (int nt = 0; nt < n_tiles_n; ++nt)
+        for (int r = 0; r < kTileN; ++r) {
+            const float *mu, *v; float det;
+            const bool real = rows(nt, r, mu, v, det);
+            b_row_cols(col, KP, D, real ? mu : nullptr, v, det);
+            for (int k = 0; k < KP; ++k) colmax[k] = std::max(colmax[k], std::fabs(col[k]));
+        }
+    // B column k times 2^-e[k] peaks in (2^14, 2^15]; the A column carries 2^e[k]
+    std::vector<int> e(KP, 0);
+    for (int k = 0; k < KP; ++k) {
+        if (colmax[k] > 0.0) { int ex; std::frexp(colmax[k], &ex); e[k] = ex - 15; }
+        e[k] = std::max(-14, std::min(15, e[k]));     // the factor itself must be an fp16-representable power of two
+    }
+    e[1] = e[0];
+    std::vector<float> scale(KP), lim(D);
+    for (int k = 0; k < KP; ++k) scale[k] = std::ldexp(1.0f, e[k]);
+    bool usable = true;
+    for (int k = 0; k < KP; ++k) if (std::ldexp(colmax[k], -e[k]) > 60000.0) usable = false;   // model range beyond fp16 even when scaled
+    for (int i = 0; i < D; ++i) {
+        // x^2 * 2^e[2+2i] and |x| * 2^e[3+2i] must stay below the fp16 maximum (with margin)
+        const double l2 = std::sqrt(60000.0 / std::ldexp(1.0, e[2 + 2 * i])), l1 = 60000.0 / std::ldexp(1.0, e[3 + 2 * i]);
+        lim[i] = (float)std::min(l1, l2);
+        if (lim[i] < 4.0f) usable = false;            // would send ordinary features to the TF32 kernel all the time
+    }
+    if (!usable) { h.ksteps = 0; return false; }
+    const size_t tile_halves = (size_t)h.ksteps * (kBStageBytes / 2);
+    std::vector<__half> B((size_t)n_tiles_n * tile_halves);
+    std::fill(B.begin(), B.end(), __float2half_rn(0.f));
+    for (int nt = 0; nt < n_tiles_n; ++nt)
+        for (int r = 0; r < kTileN; ++r) {
+            const float *mu, *v; float det;
+            const bool real = rows(nt, r, mu, v, det);
+            build_b_row_half(B.data() + (size_t)nt * tile_halves, r, h.ksteps, D, real ? mu : nullptr, v, det, e.data());
+        }
+    const bool ok = cudaMalloc((void **)&h.dB, B.size() * 2) == cudaSuccess &&
+                    cudaMemcpy(h.dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaMalloc((void **)&h.dScale, KP * 4) == cudaSuccess &&
+                    cudaMemcpy(h.dScale, scale.data(), KP * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaMalloc((void **)&h.dLim, D * 4) == cudaSuccess &&
+                    cudaMemcpy(h.dLim, lim.data(), D * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaMalloc((void **)&h.dFlag, 4) == cudaSuccess && cudaMemset(h.dFlag, 0, 4) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); h.release(); return false; }
+    return true;
 }
 
 }  // namespace
@@ -665,6 +832,8 @@ struct TcPlan {
     float *dB = nullptr;
     uint8_t *dMixw = nullptr;
     float *dA = nullptr; size_t a_cap = 0;       // tiled/transposed features (bytes)
+    float *dAh = nullptr; size_t ah_cap = 0;     // same in the fp16 kernel's padding, when it differs
+    HalfOperand half;                            // fp16 hi/lo form of the B operand (ksteps == 0: not available)
     int16_t *dRaw = nullptr; size_t raw_cap = 0; // bytes
     int n_sm = 148;
     int aw = 1;
@@ -682,7 +851,8 @@ bool tc_shape_supported(const GmmDev &g) {
 void tc_plan_free(TcPlan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dRaw);
+    cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dAh); cudaFree(p->dRaw);
+    p->half.release();
     delete p;
 }
 
@@ -728,19 +898,25 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
         tc_plan_free(p);
         return nullptr;
     }
+    build_half_operand(p->half, p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det) {
+        const int s = nt * p->spt + r / M, dens = r % M;
+        if (s >= p->S) { mu = v = nullptr; det = 0.f; return false; }
+        mu = h_mean + ((size_t)s * M + dens) * D; v = h_var + ((size_t)s * M + dens) * D; det = h_det[(size_t)s * M + dens];
+        return true;
+    });
     return p;
 }
 
-template <int M, int KS, int MODE>
+template <int M, int KS, int MODE, int HALF>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
     const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
-                        (size_t)4 * KS * kTileM * 4 + 512 + 32 * 8 + 16;
+                        (size_t)(HALF ? 8 : 4) * KS * kTileM * 4 + 512 + 320 + 32 * 8 + 16;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    tc_score_kernel<M, KS, MODE><<<grid, kThreads, smem, st>>>(prm);
+    tc_score_kernel<M, KS, MODE, HALF><<<grid, kThreads, smem, st>>>(prm);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -748,32 +924,67 @@ static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
 template <int M, int MODE>
 static int launch_score_ks(const TcParams &prm, int ks, int grid, cudaStream_t st) {
     switch (ks) {
-        case 4: return launch_score<M, 4, MODE>(prm, grid, st);
-        case 7: return launch_score<M, 7, MODE>(prm, grid, st);
-        case 10: return launch_score<M, 10, MODE>(prm, grid, st);
+        case 4: return launch_score<M, 4, MODE, 0>(prm, grid, st);
+        case 7: return launch_score<M, 7, MODE, 0>(prm, grid, st);
+        case 10: return launch_score<M, 10, MODE, 0>(prm, grid, st);
     }
     set_error("tensor-core path: %d k-steps unsupported", ks);
     return B200_ERR_UNSUP;
 }
 
+template <int M, int MODE>
+static int launch_score_ks_half(const TcParams &prm, int ks, int grid, cudaStream_t st) {
+    switch (ks) {
+        case 2: return launch_score<M, 2, MODE, 1>(prm, grid, st);
+        case 4: return launch_score<M, 4, MODE, 1>(prm, grid, st);
+        case 5: return launch_score<M, 5, MODE, 1>(prm, grid, st);
+    }
+    set_error("tensor-core path (fp16 operands): %d k-steps unsupported", ks);
+    return B200_ERR_UNSUP;
+}
+
+// Feature tiles for one launch pair: the TF32 layout always, the fp16 layout
+// too when its padded dimension count differs; resets and fills the overflow flag.
+static int prep_features(const float *d_feat, int T, int stride, int off, int D, int ks_tf32, const HalfOperand &h,
+                         float **dX, size_t *x_cap, float **dXh, size_t *xh_cap, const float **gx_half, cudaStream_t st) {
+    const int n_tiles_m = (T + kTileM - 1) / kTileM;
+    const int Dp = 4 * ks_tf32, Dph = 8 * h.ksteps;
+    const size_t bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
+    if (*x_cap < bytes) {
+        cudaFree(*dX); *dX = nullptr; *x_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)dX, bytes));
+        *x_cap = bytes;
+    }
+    if (h.ksteps) B200_CUDA_OK(cudaMemsetAsync(h.dFlag, 0, 4, st));
+    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dp, *dX, h.ksteps ? h.dLim : nullptr, h.dFlag);
+    B200_LAUNCH_CHECK();
+    *gx_half = *dX;
+    if (h.ksteps && Dph != Dp) {
+        const size_t hb = (size_t)n_tiles_m * Dph * kTileM * sizeof(float);
+        if (*xh_cap < hb) {
+            cudaFree(*dXh); *dXh = nullptr; *xh_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)dXh, hb));
+            *xh_cap = hb;
+        }
+        tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dph, *dXh, nullptr, nullptr);
+        B200_LAUNCH_CHECK();
+        *gx_half = *dXh;
+    }
+    return B200_OK;
+}
+
 int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out) {
     const int n_tiles_m = (T + kTileM - 1) / kTileM;
     const int T_pad = n_tiles_m * kTileM;
-    const int Dp = 4 * p->ksteps;
-    const size_t a_bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
     const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->spt * sizeof(int16_t);
-    if (p->a_cap < a_bytes) {
-        cudaFree(p->dA); p->dA = nullptr; p->a_cap = 0;
-        B200_CUDA_OK(cudaMalloc((void **)&p->dA, a_bytes));
-        p->a_cap = a_bytes;
-    }
     if (p->raw_cap < raw_bytes) {
         cudaFree(p->dRaw); p->dRaw = nullptr; p->raw_cap = 0;
         B200_CUDA_OK(cudaMalloc((void **)&p->dRaw, raw_bytes));
         p->raw_cap = raw_bytes;
     }
-    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, p->D, 0, p->D, Dp, p->dA);
-    B200_LAUNCH_CHECK();
+    const float *gx_half = nullptr;
+    int rc0 = prep_features(d_feat, T, p->D, 0, p->D, p->ksteps, p->half, &p->dA, &p->a_cap, &p->dAh, &p->ah_cap, &gx_half, st);
+    if (rc0) return rc0;
     if (ev_prep) cudaEventRecord(*ev_prep, st);
 
     TcParams prm;
@@ -781,7 +992,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.m31 = 31; prm.part = nullptr;
+    prm.m31 = 31; prm.part = nullptr; prm.scaleA = nullptr; prm.flag = nullptr;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -793,6 +1004,20 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     memcpy(prm.logadd, p->logadd, 256);
     const int grid = std::min(prm.n_units, p->n_sm);
     *T_pad_out = T_pad;
+    int rc = B200_OK;
+    if (p->half.ksteps) {
+        // fp16 operands first; the TF32 kernel below returns at once unless a feature overflowed fp16
+        TcParams ph = prm;
+        ph.gB = reinterpret_cast<const float *>(p->half.dB); ph.gX = gx_half; ph.ksteps = p->half.ksteps;
+        ph.scaleA = p->half.dScale; ph.flag = p->half.dFlag;
+        switch (p->M) {
+            case 8: rc = launch_score_ks_half<8, 0>(ph, ph.ksteps, grid, st); break;
+            case 16: rc = launch_score_ks_half<16, 0>(ph, ph.ksteps, grid, st); break;
+            case 32: rc = launch_score_ks_half<32, 0>(ph, ph.ksteps, grid, st); break;
+        }
+        if (rc) return rc;
+        prm.flag = p->half.dFlag;
+    }
     switch (p->M) {
         case 8: return launch_score_ks<8, 0>(prm, p->ksteps, grid, st);
         case 16: return launch_score_ks<16, 0>(prm, p->ksteps, grid, st);
@@ -1056,6 +1281,8 @@ struct TcTied {
     int ksteps[B200_MAX_STREAMS] = {0, 0, 0, 0};
     float *dB[B200_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
     float4 *dRows[B200_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [mgau][density][mean lenp | var lenp]
+    HalfOperand half[B200_MAX_STREAMS];
+    float *dXh = nullptr; size_t xh_cap = 0;
     int lenp[B200_MAX_STREAMS] = {0, 0, 0, 0};
     float *dX = nullptr; size_t x_cap = 0;
     uint4 *dPart = nullptr; size_t part_cap = 0;
@@ -1071,6 +1298,8 @@ void tc_tied_free(TcTied *p) {
     cudaSetDevice(p->device);
     for (auto b : p->dB) cudaFree(b);
     for (auto b : p->dRows) cudaFree(b);
+    for (auto &h : p->half) h.release();
+    cudaFree(p->dXh);
     cudaFree(p->dX); cudaFree(p->dPart); cudaFree(p->dFlag); cudaFree(p->dCount); cudaFree(p->dCand); cudaFree(p->dBound);
     delete p;
 }
@@ -1116,6 +1345,14 @@ TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const flo
         }
         ok = ok && cudaMalloc((void **)&p->dRows[f], R.size() * 4) == cudaSuccess &&
              cudaMemcpy(p->dRows[f], R.data(), R.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok)
+            build_half_operand(p->half[f], p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det) {
+                const int mg = nt / p->tpc, c = (nt % p->tpc) * kTileN + r;
+                const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+                mu = h_mean + pbase + (size_t)c * D; v = h_var + pbase + (size_t)c * D;
+                det = h_det[((size_t)mg * g.n_feat + f) * g.n_density + c];
+                return true;
+            });
     }
     ok = ok && cudaMalloc((void **)&p->dCount, 16 * sizeof(int)) == cudaSuccess;
     if (!ok) {
@@ -1189,20 +1426,14 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
         }
         int2 *lc = lists + (size_t)c0 * g.n_mgau * g.n_feat * g.topn;
         for (int f = 0; f < g.n_feat; ++f) {
-            const int Dp = 4 * p->ksteps[f];
-            const size_t x_bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
-            if (p->x_cap < x_bytes) {
-                cudaFree(p->dX); p->dX = nullptr; p->x_cap = 0;
-                B200_CUDA_OK(cudaMalloc((void **)&p->dX, x_bytes));
-                p->x_cap = x_bytes;
-            }
-            tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat + (size_t)(t0 + c0) * g.veclen, cn, g.veclen, g.featoff[f],
-                                                        g.featlen[f], Dp, p->dX);
-            B200_LAUNCH_CHECK();
+            const float *gx_half = nullptr;
+            int rc = prep_features(d_feat + (size_t)(t0 + c0) * g.veclen, cn, g.veclen, g.featoff[f], g.featlen[f], p->ksteps[f],
+                                   p->half[f], &p->dX, &p->x_cap, &p->dXh, &p->xh_cap, &gx_half, st);
+            if (rc) return rc;
             TcParams prm;
             prm.gB = p->dB[f]; prm.gX = p->dX; prm.gMixw = nullptr; prm.raw = nullptr; prm.part = p->dPart;
             prm.T = cn; prm.T_pad = T_pad; prm.n_sen = 0; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
-            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63;
+            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.scaleA = nullptr; prm.flag = nullptr;
             int m_chunks = 1;
             while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
             prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
@@ -1210,7 +1441,14 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             prm.n_units = p->n_tiles_n * prm.m_chunks;
             memset(prm.logadd, 0, 256);
             const int grid = std::min(prm.n_units, p->n_sm);
-            int rc = launch_score_ks<32, 1>(prm, p->ksteps[f], grid, st);
+            if (p->half[f].ksteps) {
+                TcParams ph = prm;
+                ph.gB = reinterpret_cast<const float *>(p->half[f].dB); ph.gX = gx_half; ph.ksteps = p->half[f].ksteps;
+                ph.scaleA = p->half[f].dScale; ph.flag = p->half[f].dFlag;
+                if ((rc = launch_score_ks_half<32, 1>(ph, ph.ksteps, grid, st))) return rc;
+                prm.flag = p->half[f].dFlag;
+            }
+            rc = launch_score_ks<32, 1>(prm, p->ksteps[f], grid, st);
             if (rc) return rc;
             // flagged pairs of this launch: reset the per-launch counter, keep a running total in dCount[1]
             switch (g.topn) {
