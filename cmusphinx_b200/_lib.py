@@ -75,6 +75,7 @@ _sig("b200_mgau_featdim", C.c_int, vp)
 _sig("b200_mgau_update_params", C.c_int, vp, c_f32p, c_f32p, c_f32p)
 _sig("b200_mgau_set_path", C.c_int, vp, C.c_int)
 _sig("b200_mgau_get_path", C.c_int, vp)
+_sig("b200_mgau_tc_last_format", C.c_int, vp)
 _sig("b200_mgau_tied_stats", C.c_int, vp, C.POINTER(C.c_longlong))
 _sig("b200_mgau_score_host", C.c_int, vp, vp, C.c_int, vp)
 _sig("b200_mgau_score_dev", C.c_int, vp, vp, C.c_int, vp, vp)

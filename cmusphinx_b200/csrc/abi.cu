@@ -409,6 +409,13 @@ int b200_mgau_set_path(b200_mgau_t *m, int path) {
 }
 int b200_mgau_get_path(const b200_mgau_t *m) { return m ? m->path : -1; }
 
+int b200_mgau_tc_last_format(b200_mgau_t *m) {
+    if (!m || !m->tc) return -1;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    return tc_last_format(m->tc);
+}
+
 // ------------------------------------------------------------ dense scoring
 int b200_mgau_score_dev(b200_mgau_t *m, const float *d_feat, int T, int16_t *d_out, void *stream) {
     if (!m || (T > 0 && (!d_feat || !d_out))) { set_error("null argument"); return B200_ERR_ARG; }

@@ -1027,6 +1027,15 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     return B200_ERR_UNSUP;
 }
 
+// 1: the last tc_score_raw ran on fp16 operands, 0: on TF32 operands (none built, or a feature overflowed)
+int tc_last_format(TcPlan *p) {
+    if (!p || !p->half.ksteps) return 0;
+    int f = 1;
+    cudaSetDevice(p->device);
+    if (cudaMemcpy(&f, p->half.dFlag, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return f ? 0 : 1;
+}
+
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
     const size_t stride = (size_t)p->n_tiles_n * p->spt;
     static bool attr = false;

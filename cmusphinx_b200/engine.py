@@ -214,6 +214,10 @@ class Mgau:
     def set_path(self, path: int):
         check(lib.b200_mgau_set_path(self._h, path), "set_path")
 
+    def tc_last_format(self) -> int:
+        """1 = the last tensor-core call used fp16 operands, 0 = TF32 operands, -1 = no plan."""
+        return lib.b200_mgau_tc_last_format(self._h)
+
     def tied_stats(self):
         """(lists produced, lists re-done by the exact-scan fallback) of the last
         tensor-core scoring call of a ptm / s2_semi back-end."""

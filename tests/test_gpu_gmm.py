@@ -435,3 +435,29 @@ def test_config2_tolerance_at_scale():
     assert (d != 0).mean() < 5e-3 and d.max() <= 2
     assert len(beyond) <= 1 and all((t, s) == (3770, 3943) for t, s in beyond)
     m.free()
+
+
+def test_tensor_core_fp16_operands_and_tf32_fallback():
+    """The default operand format is fp16 hi/lo (kind::f16); a batch with a
+    feature outside the scaled fp16 range must be detected by the prep kernel
+    and scored by the TF32 kernel instead -- same tolerance either way."""
+    S, M, D, T = 300, 32, 39, 400
+    mean, var, mixw = synth.cont_model(S, M, D, 41)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+    feat = synth.cont_features(mean, var, T, 42)
+    got = m.score(feat)
+    assert m.tc_last_format() == 1
+    big = feat.copy()
+    big[123, 7] = 3.0e4                     # x^2 = 9e8: far beyond what fp16 can hold at this model's scale
+    got_big = m.score(big)
+    assert m.tc_last_format() == 0
+    m.set_path(0)
+    want, want_big = m.score(feat), m.score(big)
+    assert np.abs(got.astype(np.int32) - want).max() <= 1
+    assert np.abs(got_big.astype(np.int32) - want_big).max() <= 1
+    m.set_path(1)
+    assert np.array_equal(m.score(feat), got) and m.tc_last_format() == 1     # back on fp16 for clean batches
+    m.free()
