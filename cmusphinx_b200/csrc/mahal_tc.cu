@@ -602,7 +602,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
 // a fixed (frame, 16-byte column group) and walks the n-tiles, so reads are
 // contiguous runs of kFinFrames*spt int16 and all traffic is 16-byte vectors.
 // Requires spt % 8 == 0 and n_sen % 8 == 0 (else the generic kernel below).
-constexpr int kFinFrames = 4;
+constexpr int kFinFrames = 2;
 __global__ void __launch_bounds__(256)
 tc_finish_vec_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, int spt, int n_tiles_n,
                      int subtract_best, int16_t *__restrict__ out) {

@@ -19,6 +19,9 @@ __global__ void __launch_bounds__(256) probe(int *out, int iters, int seed) {
         if (OP == 1) { REP8(CHAIN_F) }
         if (OP == 2) { REP8(CHAIN_I3) }
         if (OP == 3) { REP8(CHAIN_F3) }
+        if (OP == 4) { CHAIN_I(0) CHAIN_F(0) CHAIN_I(1) CHAIN_F(1) CHAIN_I(2) CHAIN_F(2) CHAIN_I(3) CHAIN_F(3) }   // 8 int + 8 float ops
+        if (OP == 5) { asm volatile("lop3.b32 %0, %0, %1, 31, 0x36;" : "+r"(a[0]) : "r"(b[0])); CHAIN_I(1) CHAIN_I(2) CHAIN_I(3)
+                       asm volatile("lop3.b32 %0, %0, %1, 31, 0x36;" : "+r"(a[4]) : "r"(b[4])); CHAIN_I(5) CHAIN_I(6) CHAIN_I(7) }
     }
     int r = 0;
     for (int k = 0; k < 8; ++k) r += a[k] + b[k] + __float_as_int(x[k]) + __float_as_int(y[k]);
@@ -43,4 +46,4 @@ void run(const char *name) {
     cudaFree(d);
 }
 
-int main() { run<0>("min.s32"); run<1>("min.f32"); run<2>("min3.s32"); run<3>("min3.f32"); return 0; }
+int main() { run<0>("min.s32"); run<1>("min.f32"); run<2>("min3.s32"); run<3>("min3.f32"); run<4>("mix s32+f32"); return 0; }
