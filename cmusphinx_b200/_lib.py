@@ -94,6 +94,10 @@ _sig("b200_hmm_step_dev", C.c_int, vp, vp, C.c_int32, vp)
 _sig("b200_hmm_step_results", C.c_int, vp, c_i32p, c_i32p, c_i32p, c_u32p)
 _sig("b200_hmm_step_host", C.c_int, vp, c_i16p, C.c_int32)
 _sig("b200_hmm_last_ms", C.c_float, vp)
+_sig("b200_hmm_normalize_dev", C.c_int, vp, vp, vp)
+_sig("b200_hmm_clear_pruned_dev", C.c_int, vp, vp)
+_sig("b200_hmm_enter_dev", C.c_int, vp, vp, vp, vp, C.c_int, vp)
+_sig("b200_hmm_enter_host", C.c_int, vp, c_i32p, c_i32p, c_i32p, C.c_int)
 _sig("b200_s3_create", vp, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, C.c_double, C.c_double, C.c_double,
      c_i32p, C.c_int, C.c_int)
 _sig("b200_s3_load", vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_double, c_i32p, C.c_int,

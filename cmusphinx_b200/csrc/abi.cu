@@ -605,6 +605,8 @@ struct b200_hmmctx {
     int32_t *d_total = nullptr;
     std::vector<int32_t> h_utt_off;
     int16_t *d_senscr = nullptr; size_t senscr_cap = 0;
+    int32_t *d_winner = nullptr; size_t winner_cap = 0;      // hmm_enter scratch [n_hmm]
+    int32_t *d_enter = nullptr; size_t enter_cap = 0;        // hmm_enter scratch: idx | score | hist | old0, n each
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
@@ -716,7 +718,7 @@ void b200_hmm_ctx_free(b200_hmmctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     pop_free(c);
-    cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr);
+    cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr); cudaFree(c->d_winner); cudaFree(c->d_enter);
     cudaFree(c->d_block_count); cudaFree(c->d_utt_off); cudaFree(c->d_total);
     if (c->st) cudaStreamDestroy(c->st);
     for (int i = 0; i < 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -832,6 +834,46 @@ int b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h, const int16_t *sensc
 }
 
 float b200_hmm_last_ms(const b200_hmmctx_t *c) { return c ? c->last_ms : -1.f; }
+
+int b200_hmm_normalize_dev(b200_hmmctx_t *c, const int32_t *d_best_per_utt, void *stream) {
+    if (!c) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    return hmm_launch_normalize(c->p, c->c.n_emit, d_best_per_utt, c->d_fr, stream ? (cudaStream_t)stream : c->st);
+}
+
+int b200_hmm_clear_pruned_dev(b200_hmmctx_t *c, void *stream) {
+    if (!c || !c->d_keep) { set_error("no beam step has run on this population"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    return hmm_launch_clear_pruned(c->p, c->c.n_emit, c->d_keep, stream ? (cudaStream_t)stream : c->st);
+}
+
+int b200_hmm_enter_dev(b200_hmmctx_t *c, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,
+                       void *stream) {
+    if (!c || n < 0 || (n > 0 && (!d_idx || !d_score || !d_hist))) { set_error("b200_hmm_enter_dev: bad argument"); return B200_ERR_ARG; }
+    if (n == 0 || c->p.n_hmm == 0) return B200_OK;
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    int rc = ensure((void **)&c->d_winner, &c->winner_cap, (size_t)c->p.n_hmm * 4);
+    if (rc) return rc;
+    if ((rc = ensure((void **)&c->d_enter, &c->enter_cap, (size_t)n * 16))) return rc;
+    return hmm_launch_enter(c->p, d_idx, d_score, d_hist, n, c->d_winner, c->d_enter + (size_t)3 * n, nullptr,
+                            stream ? (cudaStream_t)stream : c->st);
+}
+
+int b200_hmm_enter_host(b200_hmmctx_t *c, const int32_t *idx, const int32_t *score, const int32_t *hist, int n) {
+    if (!c || n < 0 || (n > 0 && (!idx || !score || !hist))) { set_error("b200_hmm_enter_host: bad argument"); return B200_ERR_ARG; }
+    if (n == 0) return B200_OK;
+    for (int k = 0; k < n; ++k)
+        if (idx[k] < 0 || idx[k] >= c->p.n_hmm) { set_error("hmm_enter: HMM index %d out of range", idx[k]); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    int rc = ensure((void **)&c->d_enter, &c->enter_cap, (size_t)n * 16);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_enter, idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_enter + n, score, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_enter + 2 * (size_t)n, hist, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    if ((rc = b200_hmm_enter_dev(c, c->d_enter, c->d_enter + n, c->d_enter + 2 * (size_t)n, n, c->st))) return rc;
+    B200_CUDA_OK(cudaStreamSynchronize(c->st));
+    return B200_OK;
+}
 
 // ------------------------------------------------------------ memory helpers
 void *b200_dev_alloc(size_t bytes, int device) {

@@ -26,4 +26,9 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
                     HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
                     uint32_t *mask, int32_t *total, int do_beam, cudaStream_t st);
 
+int hmm_launch_normalize(const HmmPop &p, int n_emit, const int32_t *d_best_per_utt, const HmmFrame *fr, cudaStream_t st);
+int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const uint8_t *keep, cudaStream_t st);
+int hmm_launch_enter(const HmmPop &p, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,
+                     int32_t *d_winner, int32_t *d_old0, uint8_t *d_entered, cudaStream_t st);
+
 }  // namespace b200

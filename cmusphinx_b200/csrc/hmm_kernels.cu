@@ -441,4 +441,98 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
     return B200_OK;
 }
 
+
+// ------------------------------------------------------------ maintenance
+// hmm_normalize (PS/hmm.c:207-218) for the whole population: every state score
+// and exit score that is BETTER_THAN WORST_SCORE loses its utterance's value.
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_normalize_kernel(HmmPop p, int n_emit, const int32_t *__restrict__ best_per_utt, const HmmFrame *__restrict__ fr) {
+    const int u = blockIdx.y;
+    const int i = p.utt_off[u] + blockIdx.x * kHmmBlock + threadIdx.x;
+    if (i >= p.utt_off[u + 1]) return;
+    const int32_t b = best_per_utt ? best_per_utt[u] : fr[u].best;
+    for (int s = 0; s < n_emit; ++s) {
+        const int32_t v = p.score[(size_t)s * p.n_hmm + i];
+        if (BT(v, kWorstScore)) p.score[(size_t)s * p.n_hmm + i] = v - b;
+    }
+    const int32_t o = p.out_score[i];
+    if (BT(o, kWorstScore)) p.out_score[i] = o - b;
+}
+
+// hmm_clear_scores (PS/hmm.c:169-180) for the HMMs the beam step dropped
+// (keep == 0): the `else` arm of prune_nonroot_chan, PS/ngram_search_fwdtree.c:864-866.
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_clear_pruned_kernel(HmmPop p, int n_emit, const uint8_t *__restrict__ keep) {
+    const int i = blockIdx.x * kHmmBlock + threadIdx.x;
+    if (i >= p.n_hmm || keep[i]) return;
+    for (int s = 0; s < n_emit; ++s) p.score[(size_t)s * p.n_hmm + i] = kWorstScore;
+    p.out_score[i] = kWorstScore;
+    p.bestscore[i] = kWorstScore;
+}
+
+// Batched hmm_enter (PS/hmm.c:199-205) with the test its callers make first
+// (`score BETTER_THAN hmm_in_score`, PS/ngram_search_fwdtree.c:757,846): entry k
+// wants to put (score[k], hist[k]) into state 0 of HMM idx[k].  Sequential
+// semantics over the list: the best score wins, the FIRST entry among equal
+// scores keeps its history, an entry that does not beat the resident score
+// changes nothing.  Three passes: atomicMax on the score, atomicMin of the list
+// position among the winners, history write.
+__global__ void hmm_enter_max_kernel(HmmPop p, const int32_t *__restrict__ idx, const int32_t *__restrict__ score,
+                                     int n, int32_t *__restrict__ winner) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    winner[i] = 0x7fffffff;
+    if (BT(score[k], p.score[i])) atomicMax(&p.score[i], score[k]);   // state 0 row
+}
+__global__ void hmm_enter_pick_kernel(HmmPop p, const int32_t *__restrict__ idx, const int32_t *__restrict__ score,
+                                      const int32_t *__restrict__ old0, int n, int32_t *__restrict__ winner) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    if (score[k] == p.score[i] && BT(score[k], old0[k])) atomicMin(&winner[i], k);
+}
+__global__ void hmm_enter_hist_kernel(HmmPop p, const int32_t *__restrict__ idx, const int32_t *__restrict__ hist,
+                                      int n, const int32_t *__restrict__ winner, uint8_t *__restrict__ entered) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    if (winner[i] == k) { p.history[i] = hist[k]; if (entered) entered[i] = 1; }
+}
+__global__ void hmm_enter_snapshot_kernel(HmmPop p, const int32_t *__restrict__ idx, int n, int32_t *__restrict__ old0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) old0[k] = p.score[idx[k]];
+}
+
+int hmm_launch_normalize(const HmmPop &p, int n_emit, const int32_t *d_best_per_utt, const HmmFrame *fr, cudaStream_t st) {
+    if (p.n_hmm <= 0) return B200_OK;
+    const int bpu = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock;
+    hmm_normalize_kernel<<<dim3(bpu, p.n_utt), kHmmBlock, 0, st>>>(p, n_emit, d_best_per_utt, fr);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const uint8_t *keep, cudaStream_t st) {
+    if (p.n_hmm <= 0) return B200_OK;
+    hmm_clear_pruned_kernel<<<(p.n_hmm + kHmmBlock - 1) / kHmmBlock, kHmmBlock, 0, st>>>(p, n_emit, keep);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int hmm_launch_enter(const HmmPop &p, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,
+                     int32_t *d_winner /* [n_hmm] scratch */, int32_t *d_old0 /* [n] scratch */, uint8_t *d_entered,
+                     cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    const int g = (n + 255) / 256;
+    hmm_enter_snapshot_kernel<<<g, 256, 0, st>>>(p, d_idx, n, d_old0);
+    B200_LAUNCH_CHECK();
+    hmm_enter_max_kernel<<<g, 256, 0, st>>>(p, d_idx, d_score, n, d_winner);
+    B200_LAUNCH_CHECK();
+    hmm_enter_pick_kernel<<<g, 256, 0, st>>>(p, d_idx, d_score, d_old0, n, d_winner);
+    B200_LAUNCH_CHECK();
+    hmm_enter_hist_kernel<<<g, 256, 0, st>>>(p, d_idx, d_hist, n, d_winner, d_entered);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 }  // namespace b200

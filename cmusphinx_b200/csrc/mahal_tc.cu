@@ -1102,24 +1102,33 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     // kernel; each of them is >= the group's 4th kept key, so the smallest such
     // key over all groups bounds them all.
     int32_t gmin = 0x7fffffff;
-#pragma unroll 4
-    for (int j = 0; j < tpc; ++j) {
-        const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
-        uint4 q4[4];
+    // four tiles (16 independent 16-byte loads) are in flight before any of them is consumed
+    for (int j0 = 0; j0 < tpc; j0 += 4) {
+        uint4 q4[4][4];
 #pragma unroll
-        for (int cg = 0; cg < 4; ++cg) q4[cg] = src[cg];
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = min(j0 + jj, tpc - 1);
+            const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
 #pragma unroll
-        for (int cg = 0; cg < 4; ++cg) {
-            const int32_t key[4] = {(int32_t)q4[cg].x, (int32_t)q4[cg].y, (int32_t)q4[cg].z, (int32_t)q4[cg].w};
-            gmin = min(gmin, key[3]);
+            for (int cg = 0; cg < 4; ++cg) q4[jj][cg] = src[cg];
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
-                const int pos = j * 4 + cg;
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj;
+            if (j >= tpc) break;
 #pragma unroll
-                for (int r = kCand - 1; r >= 0; --r) {
-                    if (r > 0 && key[e] < k8[r - 1]) { k8[r] = k8[r - 1]; p8[r] = p8[r - 1]; }
-                    else { k8[r] = key[e]; p8[r] = pos; break; }
+            for (int cg = 0; cg < 4; ++cg) {
+                const int32_t key[4] = {(int32_t)q4[jj][cg].x, (int32_t)q4[jj][cg].y, (int32_t)q4[jj][cg].z, (int32_t)q4[jj][cg].w};
+                gmin = min(gmin, key[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
+                    const int pos = j * 4 + cg;
+#pragma unroll
+                    for (int r = kCand - 1; r >= 0; --r) {
+                        if (r > 0 && key[e] < k8[r - 1]) { k8[r] = k8[r - 1]; p8[r] = p8[r - 1]; }
+                        else { k8[r] = key[e]; p8[r] = pos; break; }
+                    }
                 }
             }
         }

@@ -485,6 +485,32 @@ class HmmContext:
             return int(best[0]), (idx[:nk[0]] if want_idx else int(nk[0])), mask[0]
         return best, (idx[:nk.sum()] if want_idx else nk), mask
 
+    def normalize(self, best_per_utt=None):
+        """hmm_normalize over the resident population (PS/hmm.c:207-218); None = the
+        per-utterance best of the last step()."""
+        if best_per_utt is None:
+            check(lib.b200_hmm_normalize_dev(self._h, None, None), "hmm_normalize")
+            check(lib.b200_dev_sync(0), "sync")
+            return
+        b = _c(best_per_utt, np.int32)
+        d = lib.b200_dev_alloc(b.nbytes, 0)
+        try:
+            check(lib.b200_dev_upload(d, b.ctypes.data, b.nbytes), "upload")
+            check(lib.b200_hmm_normalize_dev(self._h, d, None), "hmm_normalize")
+            check(lib.b200_dev_sync(0), "sync")
+        finally:
+            lib.b200_dev_free(d)
+
+    def clear_pruned(self):
+        """hmm_clear_scores for every HMM the last step()'s beam dropped."""
+        check(lib.b200_hmm_clear_pruned_dev(self._h, None), "hmm_clear_pruned")
+        check(lib.b200_dev_sync(0), "sync")
+
+    def enter(self, idx, score, hist):
+        """Batched hmm_enter with the callers' `only if better` test, list-order semantics."""
+        i, s, h = _c(idx, np.int32), _c(score, np.int32), _c(hist, np.int32)
+        check(lib.b200_hmm_enter_host(self._h, _p(i, C.c_int32), _p(s, C.c_int32), _p(h, C.c_int32), i.size), "hmm_enter")
+
     def step_dev_async(self, d_senscr: int, beam: int):
         check(lib.b200_hmm_step_dev(self._h, d_senscr, int(beam), None), "hmm_step_dev")
 

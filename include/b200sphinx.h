@@ -303,6 +303,24 @@ int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best /* [n_utt] */, int32_
 int  b200_hmm_step_host(b200_hmmctx_t *c, const int16_t *senscr, int32_t beam);
 float b200_hmm_last_ms(const b200_hmmctx_t *c);
 
+/* Maintenance of the resident population (PS/hmm.c:169-218), batched:
+ *  - hmm_normalize: every state / exit score BETTER_THAN WORST_SCORE loses its
+ *    utterance's value d_best_per_utt[u] (NULL: the best score of the last step),
+ *    as renormalize_scores does (PS/ngram_search_fwdtree.c:560-594);
+ *  - hmm_clear_scores for the HMMs the last beam step dropped (the `else` arm of
+ *    prune_nonroot_chan, PS/ngram_search_fwdtree.c:864-866);
+ *  - hmm_enter for a list of (HMM index, score, history id) with the test its
+ *    callers make first (`score BETTER_THAN hmm_in_score`, :757, :846): same
+ *    result as walking the list in order -- the best score wins, the first of
+ *    equal scores keeps its history, nothing changes if the resident in-score
+ *    is not beaten. */
+int  b200_hmm_normalize_dev(b200_hmmctx_t *c, const int32_t *d_best_per_utt, void *stream);
+int  b200_hmm_clear_pruned_dev(b200_hmmctx_t *c, void *stream);
+int  b200_hmm_enter_dev(b200_hmmctx_t *c, const int32_t *d_idx, const int32_t *d_score,
+                        const int32_t *d_hist, int n, void *stream);
+int  b200_hmm_enter_host(b200_hmmctx_t *c, const int32_t *idx, const int32_t *score,
+                         const int32_t *hist, int n);
+
 /* acmod_flags2list (PS/acmod.c:1219-1271): bitmask -> uint8 delta list with
  * the reference's lossy >255 bridging.  Host utility; returns n written. */
 int  b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_out);

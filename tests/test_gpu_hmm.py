@@ -170,3 +170,54 @@ def test_batched_utterances_match_independent_decoders():
         np.testing.assert_array_equal(idx, np.concatenate(want_idx).astype(np.int32))
         np.testing.assert_array_equal(mask, np.array(want_mask))
     ctx.free()
+
+
+def test_hmm_maintenance_ops_match_sequential_reference():
+    """hmm_normalize, hmm_clear_scores on pruned HMMs and batched hmm_enter
+    (PS/hmm.c:169-218 + the callers' `if better` test) against the literal
+    sequential loops."""
+    ne, n_hmm, n_sen = 3, 6000, 400
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(8, ne, 3), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n_hmm, ne, n_sen, 8, 200, seed=5)
+    sen = synth.senscr_frames(1, n_sen, 6)
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    pop = b.HmmPopulation(n_hmm, ne)
+    pop.score[:], pop.history[:], pop.senid[:] = d["score"].T, d["history"].T, d["senid"].T
+    pop.out_score[:], pop.out_history[:], pop.tmatid[:], pop.mpx[:] = d["out_score"], d["out_history"], d["tmatid"], d["mpx"]
+    ctx.upload(pop)
+    ctx.set_utts(np.array([0, 2500, n_hmm], np.int32))
+    best, idx, mask = ctx.step(np.stack([sen[0], sen[0]]), -60000, n_hmm)
+    after = b.HmmPopulation(n_hmm, ne)
+    ctx.download(after)
+    W = int(b.engine.WORST_SCORE)
+    keep = np.zeros(n_hmm, bool); keep[idx] = True
+    # --- hmm_clear_scores for the pruned ones
+    want_s, want_o, want_b = after.score.copy(), after.out_score.copy(), after.bestscore.copy()
+    want_s[:, ~keep] = W; want_o[~keep] = W; want_b[~keep] = W
+    ctx.clear_pruned()
+    got = b.HmmPopulation(n_hmm, ne); ctx.download(got)
+    np.testing.assert_array_equal(got.score, want_s); np.testing.assert_array_equal(got.out_score, want_o)
+    np.testing.assert_array_equal(got.bestscore, want_b); np.testing.assert_array_equal(got.history, after.history)
+    # --- hmm_normalize with the per-utterance best of the step
+    per = np.where(np.arange(n_hmm) < 2500, best[0], best[1]).astype(np.int64)
+    ws = want_s.astype(np.int64); wo = want_o.astype(np.int64)
+    ws = np.where(ws > W, ws - per[None, :], ws); wo = np.where(wo > W, wo - per, wo)
+    ctx.normalize()
+    ctx.download(got)
+    np.testing.assert_array_equal(got.score, ws.astype(np.int32)); np.testing.assert_array_equal(got.out_score, wo.astype(np.int32))
+    # --- batched hmm_enter: duplicates, ties, entries that do not beat the resident score
+    rng = np.random.default_rng(7)
+    n = 5000
+    eidx = rng.integers(0, 900, n).astype(np.int32)           # many duplicates
+    escore = (rng.integers(-40, 5, n) * 1000).astype(np.int32)  # many ties
+    escore[::7] = W
+    ehist = np.arange(n, dtype=np.int32) + 100000
+    s0, h0 = got.score[0].copy(), got.history[0].copy()
+    for k in range(n):                                           # the reference's order
+        if escore[k] > s0[eidx[k]]:
+            s0[eidx[k]] = escore[k]; h0[eidx[k]] = ehist[k]
+    ctx.enter(eidx, escore, ehist)
+    fin = b.HmmPopulation(n_hmm, ne); ctx.download(fin)
+    np.testing.assert_array_equal(fin.score[0], s0); np.testing.assert_array_equal(fin.history[0], h0)
+    np.testing.assert_array_equal(fin.score[1:], got.score[1:]); np.testing.assert_array_equal(fin.history[1:], got.history[1:])
+    ctx.free()
