@@ -83,6 +83,7 @@ struct TcParams {
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
     int m31;                // the constant 31 (63 for tied lists), kept opaque to the compiler (see make_key)
+    int khi, kmul;          // 2^(32-L) and 2^L (L = 5, or 6 for tied lists), opaque too: see make_key_fma
     const float *scaleA;    // fp16 operands: per-column power-of-two scale of the A operand [8 * 2 * ksteps]
     const int *flag;        // fp16 operands: != 0 when a feature would overflow fp16 -> the TF32 kernel runs instead
     uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
@@ -220,6 +221,19 @@ __device__ __forceinline__ int32_t make_key(uint32_t bits, int id, int32_t m31) 
 __device__ __forceinline__ int32_t logadd_fast(const uint8_t *tab, int32_t x, int32_t y) {
     const int32_t d = min(abs(x - y), 255);
     return max(x, y) + (int32_t)tab[d];
+}
+
+// The same key built on the FMA pipe: floor(J / 2^L) as the high word of
+// J * 2^(32-L) (IMAD.HI), then times 2^L plus (2^L - 1 - id) (IMAD with an
+// immediate); khi / kmul arrive as run-time values so that the compiler keeps
+// the multiplies.  Bit-identical to make_key, one ALU-pipe op less per value --
+// and MEASURED SLOWER (score kernel 8.2 -> 8.95 ms, config 3 7.0 -> 7.5 ms): the
+// two integer multiplies cost more issue/FMA-heavy time than the LOP3 saves.
+// Kept for the record; not used.
+template <int LOW>
+__device__ __forceinline__ int32_t make_key_fma(uint32_t bits, int id, int32_t khi, int32_t kmul) {
+    const int32_t q = __mulhi(__float2int_rz(__uint_as_float(bits)), khi);
+    return q * kmul + (LOW - id);
 }
 
 // senone_eval for one senone from its 4 best keys; mixw_rev[j] = mixw[31 - j].
@@ -992,7 +1006,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.m31 = 31; prm.part = nullptr; prm.scaleA = nullptr; prm.flag = nullptr;
+    prm.m31 = 31; prm.khi = 1 << 27; prm.kmul = 32; prm.part = nullptr; prm.scaleA = nullptr; prm.flag = nullptr;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -1451,7 +1465,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             TcParams prm;
             prm.gB = p->dB[f]; prm.gX = p->dX; prm.gMixw = nullptr; prm.raw = nullptr; prm.part = p->dPart;
             prm.T = cn; prm.T_pad = T_pad; prm.n_sen = 0; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
-            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.scaleA = nullptr; prm.flag = nullptr;
+            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.khi = 1 << 26; prm.kmul = 64; prm.scaleA = nullptr; prm.flag = nullptr;
             int m_chunks = 1;
             while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
             prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
