@@ -461,3 +461,21 @@ def test_tensor_core_fp16_operands_and_tf32_fallback():
     m.set_path(1)
     assert np.array_equal(m.score(feat), got) and m.tc_last_format() == 1     # back on fp16 for clean batches
     m.free()
+
+
+def test_tensor_core_tf32_operands_when_fp16_is_disabled(monkeypatch):
+    """B200_TC_F16=0 at model creation keeps the TF32 hi/lo kernels as the only
+    operand format (they are also the overflow fallback): same tolerance."""
+    monkeypatch.setenv("B200_TC_F16", "0")
+    S, M, D, T = 200, 16, 39, 300
+    mean, var, mixw = synth.cont_model(S, M, D, 51)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+    feat = synth.cont_features(mean, var, T, 52)
+    got = m.score(feat)
+    assert m.path == 1 and m.tc_last_format() == 0
+    m.set_path(0)
+    assert np.abs(got.astype(np.int32) - m.score(feat)).max() <= 1
+    m.free()
