@@ -1106,7 +1106,7 @@ constexpr float kTiedEps = 32.f;      // bound on |approximate - exact| distance
 // tile, contiguous across the warp.
 __global__ void __launch_bounds__(128)
 tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__restrict__ part,
-                  int32_t *__restrict__ cand /* [n_mgau][tn][8] */, float *__restrict__ bound /* [n_mgau][tn][2] */) {
+                  int32_t *__restrict__ cand /* [n_mgau][tn][8] */, float *__restrict__ bound /* [n_mgau][tn][3]: bound, approximate best, lane mask */) {
     const int tl = blockIdx.x * 128 + threadIdx.x, mg = blockIdx.y;
     if (tl >= tn) return;
     int32_t k8[kCand]; int p8[kCand];
@@ -1116,33 +1116,42 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     // kernel; each of them is >= the group's 4th kept key, so the smallest such
     // key over all groups bounds them all.
     int32_t gmin = 0x7fffffff;
-    // four tiles (16 independent 16-byte loads) are in flight before any of them is consumed
-    for (int j0 = 0; j0 < tpc; j0 += 4) {
-        uint4 q4[4][4];
+    // two tiles (8 independent 16-byte loads) in flight; the insertion is branch-free
+    // inside (static register indices) and compiled once per key slot, not once per tile
+#pragma unroll 1
+    for (int j0 = 0; j0 < tpc; j0 += 2) {
+        uint4 q4[2][4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 2; ++jj) {
             const int j = min(j0 + jj, tpc - 1);
             const uint4 *src = part + ((size_t)(mg * tpc + j) * T_pad + tl) * 4;
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) q4[jj][cg] = src[cg];
         }
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+            const int jj = u >> 2, cg = u & 3;
+            if (j0 + jj >= tpc) break;
+            uint4 q = q4[0][0];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = j0 + jj;
-            if (j >= tpc) break;
+            for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
-            for (int cg = 0; cg < 4; ++cg) {
-                const int32_t key[4] = {(int32_t)q4[jj][cg].x, (int32_t)q4[jj][cg].y, (int32_t)q4[jj][cg].z, (int32_t)q4[jj][cg].w};
-                gmin = min(gmin, key[3]);
+                for (int c2 = 0; c2 < 4; ++c2) if (a2 == jj && c2 == cg) q = q4[a2][c2];
+            const int32_t key[4] = {(int32_t)q.x, (int32_t)q.y, (int32_t)q.z, (int32_t)q.w};
+            gmin = min(gmin, key[3]);
+            const int pos = (j0 + jj) * 4 + cg;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (key[e] >= k8[kCand - 1]) break;      // ascending: the rest is worse too
-                    const int pos = j * 4 + cg;
+            for (int e = 0; e < 4; ++e) {
+                const int32_t kv = key[e];
+                if (kv < k8[kCand - 1]) {
 #pragma unroll
-                    for (int r = kCand - 1; r >= 0; --r) {
-                        if (r > 0 && key[e] < k8[r - 1]) { k8[r] = k8[r - 1]; p8[r] = p8[r - 1]; }
-                        else { k8[r] = key[e]; p8[r] = pos; break; }
+                    for (int r = kCand - 1; r >= 1; --r) {
+                        const bool sh = kv < k8[r - 1];
+                        const bool here = !sh && kv < k8[r];
+                        k8[r] = sh ? k8[r - 1] : (here ? kv : k8[r]);
+                        p8[r] = sh ? p8[r - 1] : (here ? pos : p8[r]);
                     }
+                    if (kv < k8[0]) { k8[0] = kv; p8[0] = pos; }
                 }
             }
         }
@@ -1159,8 +1168,16 @@ tied_merge_kernel(int n_density, int tn, int T_pad, int tpc, const uint4 *__rest
     reinterpret_cast<int4 *>(o)[0] = lo; reinterpret_cast<int4 *>(o)[1] = hi;
     // every density that is not a candidate -- kept by its group but not among the
     // 8 best, or dropped inside its group -- has approximate distance <= this
-    bound[((size_t)mg * tn + tl) * 2] = -(float)min(k8[kCand - 1], gmin) * (1.0f / kAccScale);
-    bound[((size_t)mg * tn + tl) * 2 + 1] = -(float)k8[0] * (1.0f / kAccScale);   // approximate best, for the error statistic
+    bound[((size_t)mg * tn + tl) * 3] = -(float)min(k8[kCand - 1], gmin) * (1.0f / kAccScale);
+    bound[((size_t)mg * tn + tl) * 3 + 1] = -(float)k8[0] * (1.0f / kAccScale);   // approximate best, for the error statistic
+    // Candidates 6..8 only have to be re-scored when they could still reach the 5 best:
+    // one whose approximate distance is more than 3 eps below the 5th candidate's cannot
+    // (|approximate - exact| <= eps on both), so its lane skips the gather.
+    const float thr = (float)k8[4] + 3.f * kAccScale * (kTiedEps + 1.5e-5f * fabsf((float)k8[4]) * (1.0f / kAccScale));
+    int need = 0x1f;
+#pragma unroll
+    for (int c = 5; c < kCand; ++c) need |= ((float)k8[c] <= thr) ? (1 << c) : 0;
+    bound[((size_t)mg * tn + tl) * 3 + 2] = __int_as_float(need);
 }
 
 // Stage 2b: 8 lanes per (frame, codebook), one candidate each: exact sequential
@@ -1181,10 +1198,12 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
     const int len = g.featlen[f], q = lenp >> 2;
     const int idx0 = cand[((size_t)mg * tn + tl) * kCand + c];
     const int idx = idx0 >= 0 ? idx0 : 0;
+    const bool need = (__float_as_int(bound[((size_t)mg * tn + tl) * 3 + 2]) >> c) & 1;
     const float4 *rp = rows + ((size_t)mg * g.n_density + idx) * (2 * q);
     const float *x = feat + (size_t)(t0 + tl) * g.veclen + g.featoff[f];
     float d = __ldg(g.det + ((size_t)mg * g.n_feat + f) * g.n_density + idx);
-#pragma unroll 2
+    if (need)
+#pragma unroll 5
     for (int i4 = 0; i4 < q; ++i4) {
         const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4);
         const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -1196,7 +1215,7 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
             }
         }
     }
-    if (idx0 < 0) d = -3.0e38f;
+    if (idx0 < 0 || !need) d = -3.0e38f;      // a skipped candidate is provably outside the N+1 best
     // rank among the 8 (descending, earlier candidate first on equal distances)
     int rank = 0;
 #pragma unroll
@@ -1216,10 +1235,10 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
         clash |= (rank <= N && orank <= N && odi == di);
     }
     // (b): the (N+1)-th best beats everything that is not a candidate
-    const float bd = bound[((size_t)mg * tn + tl) * 2] + kTiedEps + 1.5e-5f * fabsf(d);
+    const float bd = bound[((size_t)mg * tn + tl) * 3] + kTiedEps + 1.5e-5f * fabsf(d);
     // statistic: largest |GEMM distance - exact distance| seen on a best candidate (+2 for the id bits)
     if (c == 0 && idx0 >= 0) {
-        const float err = fabsf(bound[((size_t)mg * tn + tl) * 2 + 1] - d);
+        const float err = fabsf(bound[((size_t)mg * tn + tl) * 3 + 1] - d);
         if (err > 4.f) atomicMax(n_flagged + 2, (int)fminf(err, 1.0e9f));
     }
     const bool bad = clash || idx0 < 0 || (rank == N && !(d > bd));
@@ -1448,7 +1467,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
         if (p->cand_cap < (size_t)cn * g.n_mgau) {
             cudaFree(p->dCand); cudaFree(p->dBound); p->dCand = nullptr; p->dBound = nullptr; p->cand_cap = 0;
             B200_CUDA_OK(cudaMalloc((void **)&p->dCand, (size_t)cn * g.n_mgau * kCand * sizeof(int32_t)));
-            B200_CUDA_OK(cudaMalloc((void **)&p->dBound, (size_t)cn * g.n_mgau * 2 * sizeof(float)));
+            B200_CUDA_OK(cudaMalloc((void **)&p->dBound, (size_t)cn * g.n_mgau * 3 * sizeof(float)));
             p->cand_cap = (size_t)cn * g.n_mgau;
         }
         if (p->flag_cap < flag_bytes) {
