@@ -44,3 +44,9 @@ def test_feature_kernel_bit_exact():
     for cmn in (True, False):
         want = np.concatenate([orc.port_feat_1s_c_d_dd(cep[off[u]:off[u + 1]], cmn) for u in range(len(lens))])
         np.testing.assert_array_equal(b.feat_1s_c_d_dd(cep, off, cmn), want)
+
+
+@pytest.mark.gpu
+def test_feature_kernel_empty_batch():
+    out = b.feat_1s_c_d_dd(np.zeros((0, 13), np.float32), np.array([0, 0], np.int32))
+    assert out.shape == (0, 39)

@@ -161,3 +161,25 @@ def test_s3_gpu_real_model():
         a, c = p.eval_utt(feat, act), m.eval_utt(feat, act)
         np.testing.assert_array_equal(c[1], a[1]); np.testing.assert_array_equal(c[0], a[0])
     p.free(); m.free()
+
+
+@pytest.mark.gpu
+def test_s3_gpu_edge_sizes():
+    """Empty and single-frame utterances, a chunk boundary (2048 frames), all senones inactive."""
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=90, n_ci_sen=6, n_density=8, dim=13, seed=12)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    for mdl in (p, m):
+        mdl.set_fast(ci_pbeam=1e-30, ds_ratio=2)
+    out = m.eval_utt(np.zeros((0, 13), np.float32), np.zeros((0, 90), np.uint8))
+    assert out[0].shape == (0, 90) and out[1].shape == (0,)
+    assert m.eval_dense(np.zeros((0, 13), np.float32)).shape == (0, 90)
+    feat = synth.s3_features(mean, var, 2100, seed=13)           # crosses the internal 2048-frame chunk
+    act = synth.s3_active(90, n_ci, 2100, seed=14)
+    act[5] = 0; act[2047] = 0; act[2048] = 0                     # frames with no active CD senone
+    for T in (1, 2100):
+        p.utt_reset(); m.utt_reset()
+        a, c = p.eval_utt(feat[:T], act[:T]), m.eval_utt(feat[:T], act[:T])
+        np.testing.assert_array_equal(c[0], a[0]); np.testing.assert_array_equal(c[1], a[1])
+        np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()))
+    p.free(); m.free()
