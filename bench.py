@@ -325,10 +325,10 @@ def run_ours(args):
         achieved = T * N_SEN * FLOP_PER_UNIT / (kern_ms / 1e3) / 1e12 if kern_ms and kern_ms > 0 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": ("f16x3" if fmt == 1 else "tf32x3") if path == 1 else "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": ({1: "f16x3", 2: "f16x3+tf32x3"}.get(fmt, "tf32x3")) if path == 1 else "f32", "data": "synthetic",
                 "config": workload_config({
                     "parallelism": f"frame shards over {world} GPU(s), no collective on the scoring path",
-                    "kernel_path": ("tcgen05 Mahalanobis GEMM (" + ("fp16" if fmt == 1 else "TF32") + " hi/lo operands x 3 products, "
+                    "kernel_path": ("tcgen05 Mahalanobis GEMM (" + {1: "fp16", 2: "fp16/TF32 per tile"}.get(fmt, "TF32") + " hi/lo operands x 3 products, "
                                     "fp32 accumulate in TMEM) + fused top-N/log-add epilogue") if path == 1
                     else "exact CUDA-core path",
                     "l2": f"inputs rotate over {N_FEAT_SETS} feature batches and every step streams a 1.0 GB score "

@@ -94,7 +94,7 @@ bool tc_shape_supported(const GmmDev &g);
 // plan (ev_prep, if given, is recorded between the two kernels).  Stage 2:
 // transpose to row-major d_out[T][n_sen], minus the frame best if asked.
 int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out);
-int tc_last_format(TcPlan *p);   // 1 fp16 operands, 0 TF32 operands (synchronises)
+int tc_last_format(TcPlan *p);   // 1 all tiles fp16, 0 all TF32, 2 mixed (synchronises)
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st);
 
 }  // namespace b200

@@ -84,8 +84,8 @@ struct TcParams {
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
     int m31;                // the constant 31 (63 for tied lists), kept opaque to the compiler (see make_key)
     int khi, kmul;          // 2^(32-L) and 2^L (L = 5, or 6 for tied lists), opaque too: see make_key_fma
-    const float *scaleA;    // fp16 operands: per-column power-of-two scale of the A operand [8 * 2 * ksteps]
-    const int *flag;        // fp16 operands: != 0 when a feature would overflow fp16 -> the TF32 kernel runs instead
+    const float *scaleA;    // fp16 operands: per-tile, per-column power-of-two scale of the A operand [n_tiles_n][16 * ksteps]
+    const uint8_t *fmt;     // [n_tiles_n] operand format of every n-tile for THIS batch (1 fp16, 0 TF32); null: TF32 everywhere
     uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
     int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
     uint8_t logadd[256];
@@ -260,22 +260,36 @@ __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], con
 // expansion (4x the bytes) happens inside the SM so it never crosses L2.
 __global__ void __launch_bounds__(kTileM)
 tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D, int Dp, float *__restrict__ gX,
-               const float *__restrict__ lim /* [D] or null */, int *__restrict__ flag) {
+               unsigned int *__restrict__ xmax /* [D] max |x| as float bits, or null */) {
     __shared__ float tile[kTileM][41];
     const int mt = blockIdx.x, r = threadIdx.x;
     const int t0 = mt * kTileM;
     // coalesced read of the tile's rows (stream `off`..`off+D` of each frame vector)
     const int nrow = min(kTileM, T - t0);
-    bool over = false;
-    for (int e = r; e < nrow * D; e += kTileM) {
-        const float v = feat[(size_t)(t0 + e / D) * stride + off + e % D];
-        tile[e / D][e % D] = v;
-        if (lim) over |= !(fabsf(v) <= lim[e % D]);     // also catches NaN
-    }
-    if (over) atomicOr(flag, 1);
+    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)(t0 + e / D) * stride + off + e % D];
     __syncthreads();
     for (int i = 0; i < Dp; ++i)
         gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
+    if (xmax) {
+        // thread i < D: largest |x_i| of this tile (NaN counts as +inf)
+        if (r < D) {
+            float m = 0.f;
+            for (int q = 0; q < nrow; ++q) { const float a = fabsf(tile[q][r]); m = (a <= m) ? m : ((a == a) ? a : __int_as_float(0x7f800000)); }
+            atomicMax(xmax + r, __float_as_uint(m));
+        }
+    }
+}
+
+// Operand format of every n-tile for this batch: fp16 iff no feature exceeds the
+// tile's limits (and the tile's own range fits at all: lim > 0).
+__global__ void tc_tile_format_kernel(const unsigned int *__restrict__ xmax, const float *__restrict__ lim, int D,
+                                      int n_tiles_n, uint8_t *__restrict__ fmt, int *__restrict__ n_half) {
+    const int nt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nt >= n_tiles_n) return;
+    bool ok = true;
+    for (int i = 0; i < D; ++i) ok = ok && (__uint_as_float(xmax[i]) <= lim[(size_t)nt * D + i]);
+    fmt[nt] = ok ? 1 : 0;
+    if (ok) atomicAdd(n_half, 1);
 }
 
 // Veltkamp split on the FMA pipe: hi carries the top 11 significant bits of a
@@ -294,16 +308,17 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
 // HALF 1: the operands are fp16 hi/lo pairs (22 significant bits, the same
 //         three-product scheme) issued as kind::f16 MMAs with K = 16: half the
 //         MMA instructions of the TF32 form.  fp16's 5-bit exponent is handled by
-//         per-column power-of-two scales (A column k times 2^e_k, B column k
-//         times 2^-e_k, chosen at load so that B fills the fp16 range); a frame
-//         whose scaled features would overflow sets *p.flag in the prep kernel
-//         and the batch is scored by the TF32 kernel instead (each kernel checks
-//         the flag first).  KS counts 16-column steps then.
+//         power-of-two scales per n-tile and K column (A column k times 2^e,
+//         B column k times 2^-e, chosen at load so that the tile's B fills the
+//         fp16 range).  Per batch, tc_tile_format_kernel compares the largest
+//         |feature| of every dimension with each tile's limits and writes
+//         p.fmt[n_tile]; both kernels are launched and each takes the units of
+//         its own format, so one sharp Gaussian or one large feature only moves
+//         the affected tiles to TF32.  KS counts 16-column steps then.
 template <int M, int KS, int MODE, int HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    if (p.flag != nullptr && ((*p.flag != 0) == (HALF != 0))) return;   // the other operand format handles this batch
     constexpr int SPT = kTileN / M;       // senones per tile
     constexpr int kStages = ring_depth(KS);
     constexpr int DP = (HALF ? 8 : 4) * KS;   // padded dims per frame in the X tile
@@ -339,13 +354,14 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) sTab[i] = p.logadd[i];
-    if (HALF) for (int i = threadIdx.x; i < 16 * KS; i += kThreads) sScale[i] = p.scaleA[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     constexpr int ksteps = KS;
+    // a unit is skipped by the kernel of the other operand format
+#define OTHER_FORMAT(nt_) ((p.fmt ? (int)p.fmt[(nt_)] : 0) != HALF)
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -355,6 +371,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
             uint32_t xphase = 0, bphase = 0;
             for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
                 const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
+                if (OTHER_FORMAT(nt)) continue;
                 const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
                 mbar_wait(BAR(B_EMPTY), bphase ^ 1);
                 mbar_expect_tx(BAR(B_FULL), (uint32_t)ksteps * kBStageBytes);
@@ -382,6 +399,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         const uint64_t dB0 = make_desc(smem_u32(sB), kTileN * 16, 128);
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int mc = u / p.n_tiles_n;
+            if (OTHER_FORMAT(u % p.n_tiles_n)) continue;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
             mbar_wait(BAR(B_FULL), bphase);
             bphase ^= 1;
@@ -436,7 +454,14 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         int stage = 0; uint32_t phase = 0, xphase = 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int mc = u / p.n_tiles_n;
+            if (OTHER_FORMAT(u % p.n_tiles_n)) continue;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+            if (HALF) {
+                // this tile's scale table: everybody is done with the previous one, then refill
+                asm volatile("bar.sync 2, %0;" ::"n"(kBuildWarps * 32) : "memory");
+                for (int k = r; k < 16 * KS; k += kBuildWarps * 32) sScale[k] = p.scaleA[(size_t)(u % p.n_tiles_n) * (16 * KS) + k];
+                asm volatile("bar.sync 2, %0;" ::"n"(kBuildWarps * 32) : "memory");
+            }
             for (int mt = mt0; mt < mt1; ++mt) {
                 mbar_wait(BAR(X_FULL), xphase);
                 xphase ^= 1;
@@ -517,6 +542,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         const int32_t m31 = p.m31;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
+            if (OTHER_FORMAT(nt)) continue;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
             if (MODE == 0) {
                 epi_bar();
@@ -603,6 +629,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         }
     }
 
+#undef OTHER_FORMAT
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -766,14 +793,20 @@ void build_b_row_half(__half *tile, int r, int ksteps, int D, const float *mu, c
     for (int k = 2; k < KP; ++k) put(k, std::ldexp(col[k], -e[k]));
 }
 
-// Per-column scales of the fp16 form and the feature limits that go with them.
+// fp16 form of the B operand: scales per n-tile and K column, the feature limits
+// that go with them, and the per-batch format decision.
 struct HalfOperand {
     __half *dB = nullptr;
-    float *dScale = nullptr;     // [16 * ksteps] A-column factors 2^e
-    float *dLim = nullptr;       // [D] largest |x_i| the scaled A operand can hold
-    int *dFlag = nullptr;
-    int ksteps = 0;
-    void release() { cudaFree(dB); cudaFree(dScale); cudaFree(dLim); cudaFree(dFlag); dB = nullptr; dScale = dLim = nullptr; dFlag = nullptr; ksteps = 0; }
+    float *dScale = nullptr;     // [n_tiles_n][16 * ksteps] A-column factors 2^e
+    float *dLim = nullptr;       // [n_tiles_n][D] largest |x_i| the tile's scaled A operand can hold (0: tile never fp16)
+    unsigned int *dXmax = nullptr;   // [D] per batch
+    uint8_t *dFmt = nullptr;     // [n_tiles_n] per batch
+    int *dNHalf = nullptr;       // tiles on fp16 in the last batch
+    int ksteps = 0, n_tiles = 0, D = 0;
+    void release() {
+        cudaFree(dB); cudaFree(dScale); cudaFree(dLim); cudaFree(dXmax); cudaFree(dFmt); cudaFree(dNHalf);
+        dB = nullptr; dScale = dLim = nullptr; dXmax = nullptr; dFmt = nullptr; dNHalf = nullptr; ksteps = 0;
+    }
 };
 
 int half_ksteps(int D) {
@@ -791,49 +824,54 @@ template <typename RowFn>
 bool build_half_operand(HalfOperand &h, int n_tiles_n, int D, RowFn rows) {
     h.ksteps = half_ksteps(D);
     if (!h.ksteps || !half_enabled()) { h.ksteps = 0; return false; }
+    h.n_tiles = n_tiles_n; h.D = D;
     const int KP = h.ksteps * 16;
-    std::vector<double> colmax(KP, 0.0), col;
-    for (int nt = 0; nt < n_tiles_n; ++nt)
+    const size_t tile_halves = (size_t)h.ksteps * (kBStageBytes / 2);
+    std::vector<__half> B((size_t)n_tiles_n * tile_halves);
+    std::fill(B.begin(), B.end(), __float2half_rn(0.f));
+    std::vector<float> scale((size_t)n_tiles_n * KP), lim((size_t)n_tiles_n * D);
+    std::vector<double> colmax(KP), col;
+    std::vector<int> e(KP);
+    int n_usable = 0;
+    for (int nt = 0; nt < n_tiles_n; ++nt) {
+        std::fill(colmax.begin(), colmax.end(), 0.0);
         for (int r = 0; r < kTileN; ++r) {
             const float *mu, *v; float det;
             const bool real = rows(nt, r, mu, v, det);
             b_row_cols(col, KP, D, real ? mu : nullptr, v, det);
             for (int k = 0; k < KP; ++k) colmax[k] = std::max(colmax[k], std::fabs(col[k]));
         }
-    // B column k times 2^-e[k] peaks in (2^14, 2^15]; the A column carries 2^e[k]
-    std::vector<int> e(KP, 0);
-    for (int k = 0; k < KP; ++k) {
-        if (colmax[k] > 0.0) { int ex; std::frexp(colmax[k], &ex); e[k] = ex - 15; }
-        e[k] = std::max(-14, std::min(15, e[k]));     // the factor itself must be an fp16-representable power of two
-    }
-    e[1] = e[0];
-    std::vector<float> scale(KP), lim(D);
-    for (int k = 0; k < KP; ++k) scale[k] = std::ldexp(1.0f, e[k]);
-    bool usable = true;
-    for (int k = 0; k < KP; ++k) if (std::ldexp(colmax[k], -e[k]) > 60000.0) usable = false;   // model range beyond fp16 even when scaled
-    for (int i = 0; i < D; ++i) {
-        // x^2 * 2^e[2+2i] and |x| * 2^e[3+2i] must stay below the fp16 maximum (with margin)
-        const double l2 = std::sqrt(60000.0 / std::ldexp(1.0, e[2 + 2 * i])), l1 = 60000.0 / std::ldexp(1.0, e[3 + 2 * i]);
-        lim[i] = (float)std::min(l1, l2);
-        if (lim[i] < 4.0f) usable = false;            // would send ordinary features to the TF32 kernel all the time
-    }
-    if (!usable) { h.ksteps = 0; return false; }
-    const size_t tile_halves = (size_t)h.ksteps * (kBStageBytes / 2);
-    std::vector<__half> B((size_t)n_tiles_n * tile_halves);
-    std::fill(B.begin(), B.end(), __float2half_rn(0.f));
-    for (int nt = 0; nt < n_tiles_n; ++nt)
+        // B column k times 2^-e[k] peaks in (2^14, 2^15]; the A column carries 2^e[k],
+        // itself an fp16-representable power of two
+        bool fits = true;
+        for (int k = 0; k < KP; ++k) {
+            e[k] = 0;
+            if (colmax[k] > 0.0) { int ex; std::frexp(colmax[k], &ex); e[k] = ex - 15; }
+            e[k] = std::max(-14, std::min(15, e[k]));
+        }
+        e[1] = e[0];
+        for (int k = 0; k < KP; ++k) if (std::ldexp(colmax[k], -e[k]) > 60000.0) fits = false;   // beyond fp16 even when scaled
+        for (int k = 0; k < KP; ++k) scale[(size_t)nt * KP + k] = std::ldexp(1.0f, e[k]);
+        for (int i = 0; i < D; ++i) {
+            // x^2 * 2^e[2+2i] and |x| * 2^e[3+2i] must stay below the fp16 maximum (with margin)
+            const double l2 = std::sqrt(60000.0 / std::ldexp(1.0, e[2 + 2 * i])), l1 = 60000.0 / std::ldexp(1.0, e[3 + 2 * i]);
+            lim[(size_t)nt * D + i] = fits ? (float)std::min(l1, l2) : 0.f;
+        }
+        n_usable += fits ? 1 : 0;
         for (int r = 0; r < kTileN; ++r) {
             const float *mu, *v; float det;
             const bool real = rows(nt, r, mu, v, det);
-            build_b_row_half(B.data() + (size_t)nt * tile_halves, r, h.ksteps, D, real ? mu : nullptr, v, det, e.data());
+            if (fits) build_b_row_half(B.data() + (size_t)nt * tile_halves, r, h.ksteps, D, real ? mu : nullptr, v, det, e.data());
         }
-    const bool ok = cudaMalloc((void **)&h.dB, B.size() * 2) == cudaSuccess &&
-                    cudaMemcpy(h.dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
-                    cudaMalloc((void **)&h.dScale, KP * 4) == cudaSuccess &&
-                    cudaMemcpy(h.dScale, scale.data(), KP * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-                    cudaMalloc((void **)&h.dLim, D * 4) == cudaSuccess &&
-                    cudaMemcpy(h.dLim, lim.data(), D * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-                    cudaMalloc((void **)&h.dFlag, 4) == cudaSuccess && cudaMemset(h.dFlag, 0, 4) == cudaSuccess;
+    }
+    if (n_usable == 0) { h.ksteps = 0; return false; }
+    auto up = [](void **dst, const void *src, size_t bytes) {
+        return cudaMalloc(dst, bytes) == cudaSuccess && (!src || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess);
+    };
+    const bool ok = up((void **)&h.dB, B.data(), B.size() * 2) && up((void **)&h.dScale, scale.data(), scale.size() * 4) &&
+                    up((void **)&h.dLim, lim.data(), lim.size() * 4) && up((void **)&h.dXmax, nullptr, (size_t)D * 4) &&
+                    up((void **)&h.dFmt, nullptr, (size_t)n_tiles_n) && up((void **)&h.dNHalf, nullptr, 4) &&
+                    cudaMemset(h.dNHalf, 0, 4) == cudaSuccess;
     if (!ok) { cudaGetLastError(); h.release(); return false; }
     return true;
 }
@@ -969,9 +1007,16 @@ static int prep_features(const float *d_feat, int T, int stride, int off, int D,
         B200_CUDA_OK(cudaMalloc((void **)dX, bytes));
         *x_cap = bytes;
     }
-    if (h.ksteps) B200_CUDA_OK(cudaMemsetAsync(h.dFlag, 0, 4, st));
-    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dp, *dX, h.ksteps ? h.dLim : nullptr, h.dFlag);
+    if (h.ksteps) {
+        B200_CUDA_OK(cudaMemsetAsync(h.dXmax, 0, (size_t)D * 4, st));
+        B200_CUDA_OK(cudaMemsetAsync(h.dNHalf, 0, 4, st));
+    }
+    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dp, *dX, h.ksteps ? h.dXmax : nullptr);
     B200_LAUNCH_CHECK();
+    if (h.ksteps) {
+        tc_tile_format_kernel<<<(h.n_tiles + 255) / 256, 256, 0, st>>>(h.dXmax, h.dLim, D, h.n_tiles, h.dFmt, h.dNHalf);
+        B200_LAUNCH_CHECK();
+    }
     *gx_half = *dX;
     if (h.ksteps && Dph != Dp) {
         const size_t hb = (size_t)n_tiles_m * Dph * kTileM * sizeof(float);
@@ -980,7 +1025,7 @@ static int prep_features(const float *d_feat, int T, int stride, int off, int D,
             B200_CUDA_OK(cudaMalloc((void **)dXh, hb));
             *xh_cap = hb;
         }
-        tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dph, *dXh, nullptr, nullptr);
+        tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dph, *dXh, nullptr);
         B200_LAUNCH_CHECK();
         *gx_half = *dXh;
     }
@@ -1006,7 +1051,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.m31 = 31; prm.khi = 1 << 27; prm.kmul = 32; prm.part = nullptr; prm.scaleA = nullptr; prm.flag = nullptr;
+    prm.m31 = 31; prm.khi = 1 << 27; prm.kmul = 32; prm.part = nullptr; prm.scaleA = nullptr; prm.fmt = nullptr;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -1023,14 +1068,14 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
         // fp16 operands first; the TF32 kernel below returns at once unless a feature overflowed fp16
         TcParams ph = prm;
         ph.gB = reinterpret_cast<const float *>(p->half.dB); ph.gX = gx_half; ph.ksteps = p->half.ksteps;
-        ph.scaleA = p->half.dScale; ph.flag = p->half.dFlag;
+        ph.scaleA = p->half.dScale; ph.fmt = p->half.dFmt;
         switch (p->M) {
             case 8: rc = launch_score_ks_half<8, 0>(ph, ph.ksteps, grid, st); break;
             case 16: rc = launch_score_ks_half<16, 0>(ph, ph.ksteps, grid, st); break;
             case 32: rc = launch_score_ks_half<32, 0>(ph, ph.ksteps, grid, st); break;
         }
         if (rc) return rc;
-        prm.flag = p->half.dFlag;
+        prm.fmt = p->half.dFmt;
     }
     switch (p->M) {
         case 8: return launch_score_ks<8, 0>(prm, p->ksteps, grid, st);
@@ -1041,13 +1086,14 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     return B200_ERR_UNSUP;
 }
 
-// 1: the last tc_score_raw ran on fp16 operands, 0: on TF32 operands (none built, or a feature overflowed)
+// 1: every n-tile of the last tc_score_raw ran on fp16 operands, 0: none did (no fp16
+// operand, or the batch's features exceed every tile's range), 2: some did
 int tc_last_format(TcPlan *p) {
     if (!p || !p->half.ksteps) return 0;
-    int f = 1;
+    int n = 0;
     cudaSetDevice(p->device);
-    if (cudaMemcpy(&f, p->half.dFlag, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return f ? 0 : 1;
+    if (cudaMemcpy(&n, p->half.dNHalf, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n == 0 ? 0 : (n == p->n_tiles_n ? 1 : 2);
 }
 
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
@@ -1484,7 +1530,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             TcParams prm;
             prm.gB = p->dB[f]; prm.gX = p->dX; prm.gMixw = nullptr; prm.raw = nullptr; prm.part = p->dPart;
             prm.T = cn; prm.T_pad = T_pad; prm.n_sen = 0; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
-            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.khi = 1 << 26; prm.kmul = 64; prm.scaleA = nullptr; prm.flag = nullptr;
+            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.khi = 1 << 26; prm.kmul = 64; prm.scaleA = nullptr; prm.fmt = nullptr;
             int m_chunks = 1;
             while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
             prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
@@ -1495,9 +1541,9 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             if (p->half[f].ksteps) {
                 TcParams ph = prm;
                 ph.gB = reinterpret_cast<const float *>(p->half[f].dB); ph.gX = gx_half; ph.ksteps = p->half[f].ksteps;
-                ph.scaleA = p->half[f].dScale; ph.flag = p->half[f].dFlag;
+                ph.scaleA = p->half[f].dScale; ph.fmt = p->half[f].dFmt;
                 if ((rc = launch_score_ks_half<32, 1>(ph, ph.ksteps, grid, st))) return rc;
-                prm.flag = p->half[f].dFlag;
+                prm.fmt = p->half[f].dFmt;
             }
             rc = launch_score_ks<32, 1>(prm, p->ksteps[f], grid, st);
             if (rc) return rc;

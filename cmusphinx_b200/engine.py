@@ -215,7 +215,7 @@ class Mgau:
         check(lib.b200_mgau_set_path(self._h, path), "set_path")
 
     def tc_last_format(self) -> int:
-        """1 = the last tensor-core call used fp16 operands, 0 = TF32 operands, -1 = no plan."""
+        """1 = the last tensor-core call ran every tile on fp16 operands, 0 = on TF32, 2 = mixed, -1 = no plan."""
         return lib.b200_mgau_tc_last_format(self._h)
 
     def tied_stats(self):

@@ -191,10 +191,13 @@ int  b200_mgau_update_params(b200_mgau_t *m, const float *mean,
  * n_density % 256 == 0 and topn <= 4; default 1 when available. */
 int  b200_mgau_set_path(b200_mgau_t *m, int path);
 int  b200_mgau_get_path(const b200_mgau_t *m);
-/* ms tensor-core path: operand format of the last scoring call -- 1 = fp16
- * hi/lo pairs (kind::f16, the default), 0 = TF32 hi/lo pairs (no fp16 operand
- * for this model, B200_TC_F16=0, or a feature of the batch exceeded the fp16
- * range of the scaled operand), -1 = no tensor-core plan.  Synchronises. */
+/* ms tensor-core path: operand format of the last scoring call, decided per
+ * n-tile (256 Gaussians) and per batch -- 1 = every tile on fp16 hi/lo pairs
+ * (kind::f16, the default), 0 = every tile on TF32 hi/lo pairs (no fp16 operand
+ * for this model, B200_TC_F16=0, or the batch's features exceed every tile's
+ * scaled fp16 range), 2 = mixed (tiles with very sharp Gaussians, or whose
+ * limits this batch exceeds, ran on TF32), -1 = no tensor-core plan.
+ * Synchronises. */
 int  b200_mgau_tc_last_format(b200_mgau_t *m);
 /* Tied back-ends, tensor-core path: {(frame, codebook, stream) lists produced,
  * lists that went through the exact-scan fallback, largest |GEMM - exact|

@@ -451,7 +451,7 @@ def test_tensor_core_fp16_operands_and_tf32_fallback():
     got = m.score(feat)
     assert m.tc_last_format() == 1
     big = feat.copy()
-    big[123, 7] = 3.0e4                     # x^2 = 9e8: far beyond what fp16 can hold at this model's scale
+    big[123, 7] = 3.0e4                     # x^2 = 9e8: far beyond what fp16 can hold at any tile's scale
     got_big = m.score(big)
     assert m.tc_last_format() == 0
     m.set_path(0)
@@ -478,4 +478,29 @@ def test_tensor_core_tf32_operands_when_fp16_is_disabled(monkeypatch):
     assert m.path == 1 and m.tc_last_format() == 0
     m.set_path(0)
     assert np.abs(got.astype(np.int32) - m.score(feat)).max() <= 1
+    m.free()
+
+
+def test_tensor_core_mixed_operand_formats_per_tile():
+    """The operand format is decided per n-tile (8 senones) and per batch: senones
+    with very sharp Gaussians (variances at the floor, as real models have for
+    untrained densities) leave their tiles to the TF32 kernel while the rest of
+    the model runs on fp16 -- both kernels write one consistent score matrix."""
+    S, M, D, T = 400, 32, 39, 300
+    mean, var, mixw = synth.cont_model(S, M, D, 61)
+    sharp = [5, 6, 130, 390]                       # senones in 4 different tiles
+    for s_ in sharp:
+        var[s_, 3] = 1e-6                           # floored to 1e-4 -> 1/(2 var ln b) = 5e7
+        mean[s_, 3] = 0.0
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE)
+    m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+    feat = synth.cont_features(mean, var, T, 62)
+    got = m.score(feat)
+    assert m.tc_last_format() == 2, "expected some tiles on fp16 and some on TF32"
+    m.set_path(0)
+    want = m.score(feat)
+    d = np.abs(got.astype(np.int32) - want)
+    assert d.max() <= 1 and (d != 0).mean() < 1e-2
     m.free()
