@@ -266,18 +266,21 @@ tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D
     const int t0 = mt * kTileM;
     // coalesced read of the tile's rows (stream `off`..`off+D` of each frame vector)
     const int nrow = min(kTileM, T - t0);
-    for (int e = r; e < nrow * D; e += kTileM) tile[e / D][e % D] = feat[(size_t)(t0 + e / D) * stride + off + e % D];
+    __shared__ unsigned int s_max[41];
+    if (xmax && r < D) s_max[r] = 0u;
+    if (xmax) __syncthreads();
+    for (int e = r; e < nrow * D; e += kTileM) {
+        const float v = feat[(size_t)(t0 + e / D) * stride + off + e % D];
+        tile[e / D][e % D] = v;
+        if (xmax) {
+            // |x| as float bits orders like an unsigned int; NaN (exponent 255, mantissa != 0) sorts above +inf
+            atomicMax(&s_max[e % D], __float_as_uint(fabsf(v)));
+        }
+    }
     __syncthreads();
     for (int i = 0; i < Dp; ++i)
         gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
-    if (xmax) {
-        // thread i < D: largest |x_i| of this tile (NaN counts as +inf)
-        if (r < D) {
-            float m = 0.f;
-            for (int q = 0; q < nrow; ++q) { const float a = fabsf(tile[q][r]); m = (a <= m) ? m : ((a == a) ? a : __int_as_float(0x7f800000)); }
-            atomicMax(xmax + r, __float_as_uint(m));
-        }
-    }
+    if (xmax && r < D) atomicMax(xmax + r, s_max[r]);
 }
 
 // Operand format of every n-tile for this batch: fp16 iff no feature exceeds the
@@ -287,7 +290,7 @@ __global__ void tc_tile_format_kernel(const unsigned int *__restrict__ xmax, con
     const int nt = blockIdx.x * blockDim.x + threadIdx.x;
     if (nt >= n_tiles_n) return;
     bool ok = true;
-    for (int i = 0; i < D; ++i) ok = ok && (__uint_as_float(xmax[i]) <= lim[(size_t)nt * D + i]);
+    for (int i = 0; i < D; ++i) ok = ok && (__uint_as_float(xmax[i]) <= lim[(size_t)nt * D + i]);   // false for NaN
     fmt[nt] = ok ? 1 : 0;
     if (ok) atomicAdd(n_half, 1);
 }
