@@ -185,3 +185,50 @@ def test_gpu_scores_via_sen_file_drive_the_unmodified_decoder(tmp_path):
     # frame 0 identical; later frames up to the documented rank-N tie deviation of the seed-free lists
     np.testing.assert_array_equal(scores[0], ref_sc[0])
     assert (scores != ref_sc[:scores.shape[0]]).mean() < 1e-4
+
+
+TIDIGITS = os.path.join(D, "test", "tidigits")
+
+
+def _tidigits(tmp_path, tag, env_extra):
+    ctl = [l.strip() for l in open(os.path.join(TIDIGITS, "tidigits.ctl")) if l.strip()]
+    hyp = tmp_path / f"{tag}.hyp"
+    cmd = [BATCH, "-hmm", os.path.join(D, "hmm", "tidigits"), "-lm", os.path.join(D, "lm", "tidigits.DMP"), "-dict",
+           os.path.join(D, "lm", "tidigits.dic"), "-ctl", os.path.join(TIDIGITS, "tidigits.ctl"), "-cepdir", TIDIGITS,
+           "-hyp", str(hyp), "-logfn", str(tmp_path / f"{tag}.log")]
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.update(env_extra)
+    subprocess.run(cmd, env=env, check=True, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return hyp.read_text().strip().splitlines(), len(ctl), (tmp_path / f"{tag}.log").read_text(errors="replace")
+
+
+@needs
+def test_reference_build_reproduces_the_bundled_tidigits_goldens(tmp_path):
+    """The reference's own regression (test/regression/test-tidigits-simple.sh): the
+    decoder built by oracle/Makefile must give the word strings of the bundled
+    test-tidigits-simple.match on all utterances (its path scores differ by about 1 %
+    across compilers, which the reference's own compare_table tolerates)."""
+    if not os.path.exists(os.path.join(TIDIGITS, "tidigits.ctl")):
+        pytest.skip("tidigits fixtures not copied (make -C oracle ref)")
+    got, n, _ = _tidigits(tmp_path, "cpu", {})
+    want = open(os.path.join(TIDIGITS, "test-tidigits-simple.match")).read().strip().splitlines()
+    assert len(got) == len(want) == n
+    assert [l.rsplit("(", 1)[0] for l in got] == [l.rsplit("(", 1)[0] for l in want]
+    for g, w in zip(got, want):
+        sg, sw = int(g.rsplit(" ", 1)[1].rstrip(")")), int(w.rsplit(" ", 1)[1].rstrip(")"))
+        assert abs(sg - sw) <= 0.03 * abs(sw)
+
+
+@needs
+@pytest.mark.gpu
+def test_identical_hypotheses_tidigits_four_stream_model(tmp_path):
+    """hmm/en/tidigits: s2_4x features (4 streams of 12/24/3/12 dims), semi-continuous,
+    through the plug-in: every hypothesis line (words and path score) identical to
+    the reference's, and the words equal to the bundled goldens."""
+    if not os.path.exists(os.path.join(TIDIGITS, "tidigits.ctl")):
+        pytest.skip("tidigits fixtures not copied (make -C oracle ref)")
+    cpu, n, _ = _tidigits(tmp_path, "cpu", {})
+    gpu, _, log = _tidigits(tmp_path, "gpu", {"LD_PRELOAD": PLUGIN})
+    assert "b200" in log.lower()
+    assert gpu == cpu and len(gpu) == n
