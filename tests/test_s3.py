@@ -183,3 +183,30 @@ def test_s3_gpu_edge_sizes():
         np.testing.assert_array_equal(c[0], a[0]); np.testing.assert_array_equal(c[1], a[1])
         np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()))
     p.free(); m.free()
+
+
+@pytest.mark.gpu
+def test_s3_gpu_fuzz_against_oracle():
+    """25 random model shapes / beams / down-sampling ratios / active-set densities."""
+    for seed in range(25):
+        rng = np.random.default_rng(1000 + seed)
+        n_sen = int(rng.integers(40, 260)); n_ci = int(rng.integers(3, 24))
+        M = int(rng.choice([1, 2, 3, 5, 8, 11, 16, 33])); D = int(rng.choice([5, 13, 39]))
+        mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen, n_ci, M, D, seed)
+        p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+        m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+        T = int(rng.integers(3, 70))
+        feat = synth.s3_features(mean, var, T, seed + 1)
+        act = synth.s3_active(n_sen, n_ci, T, seed + 2, p_on=float(rng.uniform(0.02, 0.5)))
+        dense = m.eval_dense(feat)
+        ci = dense[:, :n_ci]
+        spread = float(np.median(ci.max(1) - np.median(ci, 1))) + 1
+        cfg = dict(ci_pbeam=float(np.float32(1.0003)) ** (-spread * float(rng.uniform(0.3, 2))),
+                   max_cd=int(rng.integers(1, n_sen)), ds_ratio=int(rng.integers(1, 5)), tighten=float(rng.uniform(0.1, 1.0)))
+        f0 = int(rng.integers(0, 7))
+        p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+        a, c = p.eval_utt(feat, act, f0), m.eval_utt(feat, act, f0)
+        np.testing.assert_array_equal(c[1], a[1], err_msg=f"seed {seed} {cfg}")
+        np.testing.assert_array_equal(c[0], a[0], err_msg=f"seed {seed} {cfg}")
+        np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()), err_msg=f"seed {seed}")
+        p.free(); m.free()
