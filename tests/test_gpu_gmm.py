@@ -504,3 +504,61 @@ def test_tensor_core_mixed_operand_formats_per_tile():
     d = np.abs(got.astype(np.int32) - want)
     assert d.max() <= 1 and (d != 0).mean() < 1e-2
     m.free()
+
+
+def test_tied_tensor_core_fuzz_identical_to_exact():
+    """Random tied models: 1-3 streams of 3..39 dims, 256/512/768 densities, topn 1..4,
+    ptm and s2_semi -- tensor-core lists must reproduce the exact scan bit for bit."""
+    for seed in range(12):
+        rng = np.random.default_rng(500 + seed)
+        kind = int(rng.choice([1, 2]))
+        C = 1 if kind == 2 else int(rng.integers(1, 6))
+        Mden = int(rng.choice([256, 512, 768]))
+        streams = [int(rng.integers(3, 40)) for _ in range(int(rng.integers(1, 4)))]
+        topn = int(rng.integers(1, 5))
+        S, T = int(rng.integers(20, 150)), int(rng.integers(1, 400))
+        F, V = len(streams), sum(streams)
+        mean = rng.standard_normal((C, F, Mden, max(streams))).astype(np.float32) * float(rng.uniform(0.5, 3))
+        var = np.exp(rng.uniform(np.log(0.02), np.log(8.0), mean.shape)).astype(np.float32)
+        flat_m = np.concatenate([mean[:, f, :, :L].reshape(C, -1) for f, L in enumerate(streams)], 1)
+        pv_parts, pd_parts = [], []
+        for f, L in enumerate(streams):
+            a, d = orc.port_precompute(var[:, f, :, :L].reshape(-1, L), L, 1e-4, orc.LOGBASE)
+            pv_parts.append(a.reshape(C, -1)); pd_parts.append(d.reshape(C, 1, Mden))
+        pv = np.concatenate(pv_parts, 1); pd = np.concatenate(pd_parts, 1)
+        mixw = rng.integers(0, 160, (F, Mden, S)).astype(np.uint8)
+        s2c = (np.arange(S) * C // S).astype(np.uint8)
+        cfg = b.MgauConfig(C, F, Mden, S, streams, topn=topn, logbase=orc.LOGBASE)
+        m = (b.ptm_from_arrays(cfg, flat_m, pv, pd, mixw, s2c) if kind == 1 else b.semi_from_arrays(cfg, flat_m, pv, pd, mixw))
+        assert m.path == 1
+        feat = (rng.standard_normal((T, V)) * float(rng.uniform(0.5, 2.5))).astype(np.float32)
+        got = m.score(feat)
+        m.set_path(0)
+        np.testing.assert_array_equal(got, m.score(feat), err_msg=f"seed {seed}: kind {kind} C {C} M {Mden} streams {streams} topn {topn}")
+        m.free()
+
+
+def test_tensor_core_ms_fuzz_within_one_of_exact():
+    """Random fully-continuous shapes (8/16/32 densities, 3..39 dims, variance spread up to
+    4 decades, feature scale 0.3..6): the tensor-core path stays within +-1 of the exact path."""
+    for seed in range(10):
+        rng = np.random.default_rng(900 + seed)
+        S, M, D, T = int(rng.integers(9, 700)), int(rng.choice([8, 16, 32])), int(rng.integers(3, 40)), int(rng.integers(1, 600))
+        mean = (rng.standard_normal((S, M, D)) * float(rng.uniform(0.3, 4))).astype(np.float32)
+        var = np.exp(rng.uniform(np.log(1e-3), np.log(10.0), (S, M, D))).astype(np.float32)
+        mixw = rng.dirichlet(np.ones(M), (S, 1)).astype(np.float32)
+        pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+        q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+        cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE)
+        m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+        assert m.path == 1
+        feat = (mean[rng.integers(0, S, T), rng.integers(0, M, T)] +
+                rng.standard_normal((T, D)) * float(rng.uniform(0.3, 6))).astype(np.float32)
+        got = m.score(feat).astype(np.int32)
+        fmt = m.tc_last_format()
+        m.set_path(0)
+        d = np.abs(got - m.score(feat))
+        assert d.max() <= 1, f"seed {seed}: S {S} M {M} D {D} T {T} format {fmt}: max |d| {d.max()}"
+        # the disagreement rate grows with |d| (relative GEMM error 2^-22): sharp models + far features reach a few %
+        assert (d != 0).mean() < 6e-2, f"seed {seed}: mismatch rate {(d != 0).mean():.3f}"
+        m.free()
