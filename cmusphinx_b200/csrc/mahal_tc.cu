@@ -17,16 +17,19 @@
 //     k = 2+2i     : A = x_i^2         B = -v_i
 //     k = 3+2i     : A = x_i           B = 2 mu_i v_i
 // padded to a multiple of 8.  Scores must be right to about one raw log unit
-// in 10^5..10^6, i.e. fp32-class operands: every operand is split into two
-// TF32 numbers (hi + lo, 2 x 11 significant bits) and the product is formed as
-//     Ahi*Bhi + Ahi*Blo + Alo*Bhi          ("TF32x3")
-// with fp32 accumulation in TMEM.  The constant comes first in K so partial
-// sums stay near the final magnitude.
+// in 10^5..10^6, i.e. fp32-class operands: every operand is split into a
+// hi + lo pair (2 x 11 significant bits) and the product is formed as
+//     Ahi*Bhi + Ahi*Blo + Alo*Bhi          
+// with fp32 accumulation in TMEM.  The pairs are fp16 numbers with a
+// power-of-two scale per n-tile and K column (kind::f16, K = 16 per MMA, the
+// default) or TF32 numbers (kind::tf32, K = 8; the tiles fp16 cannot hold) --
+// see tc_score_kernel.  The constant comes first in K so partial sums stay
+// near the final magnitude.
 //
 // Data layout in HBM (all pre-tiled so that every shared-memory stage is ONE
 // contiguous bulk copy, in the UMMA K-major no-swizzle canonical layout:
 // 16-byte K-chunks, 8-row core matrices, SBO = 128 B, LBO = rows*16 B):
-//   B  [n_tile][kstep][hi|lo][chunk 0|1][256 rows][4 f32]   16 KB / kstep, static
+//   B  [n_tile][kstep][hi|lo][chunk 0|1][256 rows][4 f32 | 8 f16]   16 KB / kstep, static
 //   X  [m_tile][40 dims][128 rows] f32 -- the RAW features, tiled + transposed
 //      (20 KB / frame tile).  The 4x larger [1,1,x^2,x..] hi/lo A operand is
 //      built inside the SM: streaming it pre-expanded made the kernel L2-bound
@@ -34,12 +37,13 @@
 //   raw scores, tile-major [n_tile][T_pad][256/M] int16  (coalesced 16 B stores)
 //
 // Kernel (persistent, 1 CTA / SM, 704 threads):
-//   warp 0      bulk-TMA producer: the unit's B tile once (resident, 160 KB),
-//               then one raw feature tile per frame tile
-//   warps 2..5  A builders: thread = frame row; x^2, Veltkamp hi/lo split (all
-//               FMA-pipe ops) written k-step by k-step into a 5-deep A ring
-//   warp 1      single-thread tcgen05.mma issuer, 128x256x8 kind::tf32,
-//               3 MMAs per k-step, two 256-column TMEM accumulators
+//   warp 0      bulk-TMA producer: the unit's B tile once (resident, 80 KB fp16 /
+//               160 KB TF32), then one raw feature tile per frame tile
+//   warps 2..5  A builders: thread = frame row; x^2, scale, hi/lo split
+//               written k-step by k-step into a 5-deep A ring
+//   warp 1      single-thread tcgen05.mma issuer, 128x256x16 kind::f16 (or
+//               128x256x8 kind::tf32), 3 MMAs per k-step, two 256-column TMEM
+//               accumulators
 //   warps 6..21 epilogue: tcgen05.ld of 64 columns (= two 32-density senones)
 //               per thread, accumulator released immediately, integer keys (trunc(d) << log2 M | density id), top-4 by
 //               a sort4 + bitonic-merge network in registers, table log-add
@@ -999,7 +1003,8 @@ static int launch_score_ks_half(const TcParams &prm, int ks, int grid, cudaStrea
 }
 
 // Feature tiles for one launch pair: the TF32 layout always, the fp16 layout
-// too when its padded dimension count differs; resets and fills the overflow flag.
+// too when its padded dimension count differs; reduces max |x_i| per dimension and
+// decides every n-tile's operand format for this batch.
 static int prep_features(const float *d_feat, int T, int stride, int off, int D, int ks_tf32, const HalfOperand &h,
                          float **dX, size_t *x_cap, float **dXh, size_t *xh_cap, const float **gx_half, cudaStream_t st) {
     const int n_tiles_m = (T + kTileM - 1) / kTileM;
