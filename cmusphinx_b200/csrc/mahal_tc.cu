@@ -87,7 +87,6 @@ struct TcParams {
     int16_t *raw;           // [n_tiles_n][T_pad][spt]
     int T, T_pad, n_sen, n_tiles_m, n_tiles_n, ksteps, m_chunks, tiles_per_chunk, n_units, aw;
     int m31;                // the constant 31 (63 for tied lists), kept opaque to the compiler (see make_key)
-    int khi, kmul;          // 2^(32-L) and 2^L (L = 5, or 6 for tied lists), opaque too: see make_key_fma
     const float *scaleA;    // fp16 operands: per-tile, per-column power-of-two scale of the A operand [n_tiles_n][16 * ksteps]
     const uint8_t *fmt;     // [n_tiles_n] operand format of every n-tile for THIS batch (1 fp16, 0 TF32); null: TF32 everywhere
     uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
@@ -227,18 +226,8 @@ __device__ __forceinline__ int32_t logadd_fast(const uint8_t *tab, int32_t x, in
     return max(x, y) + (int32_t)tab[d];
 }
 
-// The same key built on the FMA pipe: floor(J / 2^L) as the high word of
-// J * 2^(32-L) (IMAD.HI), then times 2^L plus (2^L - 1 - id) (IMAD with an
-// immediate); khi / kmul arrive as run-time values so that the compiler keeps
-// the multiplies.  Bit-identical to make_key, one ALU-pipe op less per value --
-// and MEASURED SLOWER (score kernel 8.2 -> 8.95 ms, config 3 7.0 -> 7.5 ms): the
-// two integer multiplies cost more issue/FMA-heavy time than the LOP3 saves.
-// Kept for the record; not used.
-template <int LOW>
-__device__ __forceinline__ int32_t make_key_fma(uint32_t bits, int id, int32_t khi, int32_t kmul) {
-    const int32_t q = __mulhi(__float2int_rz(__uint_as_float(bits)), khi);
-    return q * kmul + (LOW - id);
-}
+// (Building the key on the FMA pipe instead -- IMAD.HI + IMAD -- saves one ALU op per
+// value and was measured slower: 8.95 vs 8.2 ms, see profiles/README.md.)
 
 // senone_eval for one senone from its 4 best keys; mixw_rev[j] = mixw[31 - j].
 __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], const uint8_t *mixw_rev,
@@ -1059,7 +1048,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.T = T; prm.T_pad = T_pad; prm.n_sen = p->S; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
     prm.ksteps = p->ksteps; prm.aw = p->aw;
     { const char *e = getenv("B200_TC_DBG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.m31 = 31; prm.khi = 1 << 27; prm.kmul = 32; prm.part = nullptr; prm.scaleA = nullptr; prm.fmt = nullptr;
+    prm.m31 = 31; prm.part = nullptr; prm.scaleA = nullptr; prm.fmt = nullptr;
     // split the frame axis so that there are >= ~16 units per CTA, but never
     // less than 8 frame tiles per unit (B reload amortisation)
     int m_chunks = 1;
@@ -1538,7 +1527,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
             TcParams prm;
             prm.gB = p->dB[f]; prm.gX = p->dX; prm.gMixw = nullptr; prm.raw = nullptr; prm.part = p->dPart;
             prm.T = cn; prm.T_pad = T_pad; prm.n_sen = 0; prm.n_tiles_m = n_tiles_m; prm.n_tiles_n = p->n_tiles_n;
-            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.khi = 1 << 26; prm.kmul = 64; prm.scaleA = nullptr; prm.fmt = nullptr;
+            prm.ksteps = p->ksteps[f]; prm.aw = 1; prm.dbg = 0; prm.m31 = 63; prm.scaleA = nullptr; prm.fmt = nullptr;
             int m_chunks = 1;
             while ((long long)p->n_tiles_n * m_chunks < 16LL * p->n_sm && (n_tiles_m + m_chunks) / (m_chunks + 1) >= 8) ++m_chunks;
             prm.tiles_per_chunk = (n_tiles_m + m_chunks - 1) / m_chunks;
