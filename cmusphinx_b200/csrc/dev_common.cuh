@@ -25,6 +25,20 @@ extern std::atomic<long long> g_launches;
         B200_CUDA_OK(cudaGetLastError());                                       \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: call
+// sites remember it per device, so a process that drives several GPUs sets it
+// on each of them.
+struct AttrOnce {
+    unsigned long long done = 0;
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if ((done >> d) & 1ull) return false;
+        done |= 1ull << d;
+        return true;
+    }
+};
+
 constexpr int32_t kWorstScore = (int32_t)0xE0000000;
 constexpr int32_t kWorstDistI = (int32_t)0x80000000;
 constexpr int kShift = B200_SENSCR_SHIFT;

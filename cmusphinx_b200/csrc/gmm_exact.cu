@@ -425,10 +425,9 @@ int gmm_launch_normalize(int16_t *scr, int T, int n_sen, cudaStream_t st) {
     if (T <= 0) return B200_OK;
     size_t sh = ((size_t)n_sen * sizeof(int16_t) + 15) & ~(size_t)15;
     if (sh > 200 * 1024) { set_error("n_sen %d too large for the normalise kernel", n_sen); return B200_ERR_UNSUP; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static AttrOnce attr_set;
+    if (attr_set.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(ms_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     int blocks = std::min(T, 148 * 32);
     ms_normalize_kernel<<<blocks, 256, sh, st>>>(scr, T, n_sen);
@@ -446,10 +445,9 @@ int gmm_launch_tied_senone(const GmmDev &g, const int2 *lists, int T, int t0, in
                            const uint8_t *d_active, int n_active, int16_t *out, cudaStream_t st) {
     size_t sh = gmm_tied_smem(g, d_active ? n_active : 0);
     if (sh > 200 * 1024) { set_error("tied senone kernel needs %zu B of shared memory", sh); return B200_ERR_UNSUP; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static AttrOnce attr_set;
+    if (attr_set.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(tied_senone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     tied_senone_kernel<<<tn, 256, sh, st>>>(g, lists, min(T, t0 + tn), t0, g.topn, semi, d_active, n_active, out);
     B200_LAUNCH_CHECK();

@@ -416,11 +416,10 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
     B200_LAUNCH_CHECK();
     const size_t sh = step_smem(c);
     if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
-    static bool attr = false;
-    if (!attr) {
+    static AttrOnce attr;
+    if (attr.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     // a few CTAs per SM in total; each strides its utterance's range
     int gx = std::max(1, std::min(bpu, (148 * 8 + p.n_utt - 1) / p.n_utt));

@@ -959,10 +959,9 @@ template <int M, int KS, int MODE, int HALF>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
     const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
                         (size_t)(HALF ? 8 : 4) * KS * kTileM * 4 + 512 + 320 + 32 * 8 + 16;
-    static bool attr = false;
-    if (!attr) {
+    static AttrOnce attr;
+    if (attr.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
     }
     tc_score_kernel<M, KS, MODE, HALF><<<grid, kThreads, smem, st>>>(prm);
     B200_LAUNCH_CHECK();
@@ -1095,11 +1094,10 @@ int tc_last_format(TcPlan *p) {
 
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st) {
     const size_t stride = (size_t)p->n_tiles_n * p->spt;
-    static bool attr = false;
-    if (!attr) {
+    static AttrOnce attr;
+    if (attr.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc_finish_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     const bool vec = (p->spt % 8 == 0) && (p->S % 8 == 0) && ((reinterpret_cast<size_t>(d_out) & 15) == 0) &&
                      (256 % (kFinFrames * (p->spt / 8)) == 0);
@@ -1483,10 +1481,9 @@ static int tied_select_launch(TcTied *p, const GmmDev &g, int f, const float *d_
     const size_t sh = ((size_t)p->lenp[f] + g.n_density) * 4;
     if (sh > 200 * 1024) { set_error("codebook too large for the fallback kernel"); return B200_ERR_UNSUP; }
     auto kern = p->mode == 1 ? tied_fallback_kernel<N, 1> : tied_fallback_kernel<N, 2>;
-    static bool attr[2] = {false, false};
-    if (!attr[p->mode - 1]) {
+    static AttrOnce attr[2];
+    if (attr[p->mode - 1].need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr[p->mode - 1] = true;
     }
     kern<<<p->n_sm * 2, 256, sh, st>>>(g, f, d_feat, t0, p->dFlag, p->dCount, p->dRows[f], p->lenp[f], lists);
     B200_LAUNCH_CHECK();

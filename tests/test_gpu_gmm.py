@@ -562,3 +562,27 @@ def test_tensor_core_ms_fuzz_within_one_of_exact():
         # the disagreement rate grows with |d| (relative GEMM error 2^-22): sharp models + far features reach a few %
         assert (d != 0).mean() < 6e-2, f"seed {seed}: mismatch rate {(d != 0).mean():.3f}"
         m.free()
+
+
+def test_two_devices_in_one_process():
+    """One process driving two GPUs (skipped on a single-GPU box): every handle carries its
+    device, per-device kernel attributes are set on both."""
+    if b.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    S, M, D, T = 120, 32, 39, 260
+    mean, var, mixw = synth.cont_model(S, M, D, 71)
+    pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
+    q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
+    feat = synth.cont_features(mean, var, T, 72)
+    outs = []
+    for dev in (0, 1):
+        cfg = b.MgauConfig(S, 1, M, S, [D], topn=4, logbase=orc.LOGBASE, device=dev)
+        m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(S))
+        a = m.score(feat)
+        m.set_path(0)
+        e = m.score(feat)
+        assert np.abs(a.astype(np.int32) - e).max() <= 1
+        outs.append((a, e))
+        m.free()
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
