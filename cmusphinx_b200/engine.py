@@ -532,6 +532,50 @@ def feat_1s_c_d_dd(cep, utt_off=None, cmn: bool = True, device: int = 0) -> np.n
     return out
 
 
+FEAT_TYPES = ["1s_c_d_dd", "s3_1x39", "s2_4x", "1s_c_d_ld_dd", "1s_c", "1s_c_d"]
+
+
+class _FeatCfg(C.Structure):
+    _fields_ = [("type", C.c_int32), ("cepsize", C.c_int32), ("cmn", C.c_int32), ("varnorm", C.c_int32),
+                ("agc", C.c_int32), ("lda_rows", C.c_int32), ("lda_cols", C.c_int32), ("lda_dim", C.c_int32),
+                ("lda", C.POINTER(C.c_float)), ("n_subvec", C.c_int32), ("subvec", C.POINTER(C.c_int32))]
+
+
+lib.b200_feat_dims.argtypes = [C.POINTER(_FeatCfg), C.POINTER(C.c_int32)]
+lib.b200_feat_compute_host.argtypes = [C.POINTER(_FeatCfg), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int,
+                                       C.POINTER(C.c_float), C.c_int]
+
+
+def feat_compute(cep, utt_off=None, ftype: str = "1s_c_d_dd", cmn: bool = True, varnorm: bool = False,
+                 agc: bool = False, lda=None, lda_dim: int = 0, subvec=None, device: int = 0) -> np.ndarray:
+    """feat_s2mfc2feat_block_utt / feat_compute_utt for a batch of utterances
+    (SB/feat/feat.c:1110-1135, 1241-1265): `-feat ftype`, `-cmn current|none`,
+    `-varnorm`, `-agc max|none`, `-lda` ([rows][stream_len] matrix, `-ldadim`),
+    `-svspec` (flat index list).  Returns [T][out_len] float32."""
+    cep = _c(cep, np.float32)
+    T, cs = cep.shape
+    off = np.array([0, T], np.int32) if utt_off is None else _c(utt_off, np.int32)
+    cfg = _FeatCfg()
+    if ftype not in FEAT_TYPES:
+        raise ValueError(f"unknown -feat type {ftype}")
+    cfg.type, cfg.cepsize, cfg.cmn, cfg.varnorm, cfg.agc = FEAT_TYPES.index(ftype), cs, int(cmn), int(varnorm), int(agc)
+    keep = []
+    if lda is not None:
+        lda = _c(lda, np.float32)
+        keep.append(lda)
+        cfg.lda_rows, cfg.lda_cols, cfg.lda_dim, cfg.lda = lda.shape[0], lda.shape[1], lda_dim, _p(lda, C.c_float)
+    if subvec is not None and len(subvec):
+        sv = _c(np.asarray(subvec), np.int32)
+        keep.append(sv)
+        cfg.n_subvec, cfg.subvec = sv.size, _p(sv, C.c_int32)
+    dims = (C.c_int32 * 3)()
+    check(lib.b200_feat_dims(C.byref(cfg), dims), "feat_dims")
+    out = np.zeros((T, dims[2]), np.float32)
+    check(lib.b200_feat_compute_host(C.byref(cfg), _p(cep, C.c_float), _p(off, C.c_int32), off.size - 1,
+                                     _p(out, C.c_float), device), "feat_compute")
+    return out
+
+
 # ------------------------------------------------------------ sphinx3 GMM
 S3_LOGBASE = float(np.float32(1.0003))   # sphinx3 -logbase default (float32 option, cmdln_macro.h:246)
 

@@ -423,6 +423,47 @@ int  b200_feat_1s_c_d_dd_dev(const float *d_cep, const int32_t *d_utt_off, int n
 int  b200_feat_1s_c_d_dd_host(const float *cep, const int32_t *utt_off, int n_utt,
                               int cepsize, int cmn, float *feat, int device);
 
+/* General form of the same stage: every `-feat` type the reference computes
+ * from cepstra, with its whole-utterance normalisations and the two linear
+ * post-steps.  Replaces feat_s2mfc2feat_block_utt -> feat_compute_utt
+ * (SB/feat/feat.c:1110-1135, 1241-1265) for a batch of utterances:
+ *   cmn      0 = none, 1 = current           (feat_cmn feat.c:1060-1081; cmn.c:150-213)
+ *   varnorm  unit variance per dimension      (cmn.c:186-212; needs cmn == 1)
+ *   agc      0 = none, 1 = max on c0, applied after cmn (feat_agc feat.c:1084-1108; agc.c:108-126)
+ *   type     the compute_feat function        (feat.c:559-849)
+ *   lda      [lda_rows][lda_cols] float32, lda_cols == the type's stream length, rows used =
+ *            lda_dim (0: all) -- feat_lda_transform (SB/feat/lda.c:141-160), single stream only
+ *   subvec   n_subvec indices into the (LDA'd) vector -- feat_subvec_project (feat.c:334-355);
+ *            the -svspec stream boundaries do not change the memory layout
+ * `prior` CMN and `emax`/`noise` AGC are live-mode running estimates that the
+ * reference does not use in whole-utterance mode (feat.c:1064-1066, 1088-1090)
+ * and are refused.  Bit-exact: each float operation is the reference's, in its order. */
+enum {
+    B200_FEAT_1S_C_D_DD = 0,    /* c | d | dd, window 3                     feat.c:726-769 */
+    B200_FEAT_S3_1X39 = 1,      /* c1-12 | d1-12 | c0 d0 dd0 | dd1-12, w 3  feat.c:622-672 */
+    B200_FEAT_S2_4X = 2,        /* 4 streams 12|24|3|12, window 4           feat.c:559-618 */
+    B200_FEAT_1S_C_D_LD_DD = 3, /* c | d | long d | dd, window 4            feat.c:772-825 */
+    B200_FEAT_1S_C = 4,         /* cepstra only, window 0                   feat.c:676-683 */
+    B200_FEAT_1S_C_D = 5        /* c | d, window 2                          feat.c:700-723 */
+};
+typedef struct b200_feat_cfg {
+    int32_t type, cepsize, cmn, varnorm, agc;
+    int32_t lda_rows, lda_cols, lda_dim;   /* lda_rows == 0: no LDA */
+    const float *lda;                      /* host pointer (both entry points) */
+    int32_t n_subvec;                      /* 0: no projection */
+    const int32_t *subvec;                 /* host pointer */
+} b200_feat_cfg_t;
+/* dims = {window, stream-concatenated length before LDA, output length per frame};
+ * B200_ERR_ARG / B200_ERR_UNSUP for a configuration the reference would reject. */
+int  b200_feat_dims(const b200_feat_cfg_t *cfg, int32_t dims[3]);
+/* d_cep [T_total][cepsize] -> d_feat [T_total][dims[2]], both on the device.
+ * d_scratch: b200_feat_scratch_bytes(cfg, n_utt, T_total) bytes. */
+size_t b200_feat_scratch_bytes(const b200_feat_cfg_t *cfg, int n_utt, int T_total);
+int  b200_feat_compute_dev(const b200_feat_cfg_t *cfg, const float *d_cep, const int32_t *d_utt_off,
+                           int n_utt, int T_total, void *d_scratch, float *d_feat, void *stream);
+int  b200_feat_compute_host(const b200_feat_cfg_t *cfg, const float *cep, const int32_t *utt_off,
+                            int n_utt, float *feat, int device);
+
 /* -------------------------------------------------- device memory helpers
  * (so a non-torch host can keep buffers resident) */
 void *b200_dev_alloc(size_t bytes, int device);

@@ -405,6 +405,56 @@ ref_acmod_cep2feat(void *vh, const float *cep, int n_frames, int ceplen,
     return nfr;
 }
 
+/* The reference's own feat_t, built directly (no model directory): feat_init
+ * (feat.c:851-1037) for `type` / cmn / varnorm / agc, an LDA matrix installed
+ * the way feat_read_lda leaves it (lda.c:104-134), -svspec through
+ * parse_subvecs + feat_set_subvecs, then one whole utterance through
+ * feat_s2mfc2feat_live(beginutt = endutt = TRUE).  out receives rows of
+ * *row_len floats (the pre-LDA vector length, as feat_array_alloc lays them
+ * out); returns the number of frames, -1 on a configuration error. */
+int
+ref_feat_compute(const char *type, const char *cmn, int varnorm, const char *agc, int cepsize,
+                 const float *lda, int lda_m, int lda_n, int lda_dim, const char *svspec,
+                 const float *cep_in, int n_frames, float *out, int *row_len, int *out_dim)
+{
+    feat_t *fcb;
+    mfcc_t **cepp, ***fb;
+    float *cep;
+    int32 ncep = n_frames;
+    int f, tot = 0, t, nfr;
+    err_set_logfp(NULL);
+    fcb = feat_init(type, cmn_type_from_str(cmn), varnorm, agc_type_from_str(agc), 0, cepsize);
+    if (fcb == NULL) return -1;
+    if (lda) {
+        if (fcb->n_stream != 1 || lda_n != (int)fcb->stream_len[0]) { feat_free(fcb); return -1; }
+        fcb->lda = (mfcc_t ***)ckd_calloc_3d(1, lda_m, lda_n, sizeof(float));
+        memcpy(fcb->lda[0][0], lda, sizeof(float) * lda_m * lda_n);
+        fcb->n_lda = 1;
+        if (lda_dim > lda_m || lda_dim <= 0) lda_dim = lda_m;
+        fcb->out_dim = lda_dim;
+    }
+    if (svspec && *svspec) {
+        int32 **sv = parse_subvecs(svspec);
+        if (sv == NULL || feat_set_subvecs(fcb, sv) < 0) { feat_free(fcb); return -1; }
+    }
+    for (f = 0; f < fcb->n_stream; ++f) tot += fcb->stream_len[f];
+    *row_len = tot;
+    *out_dim = fcb->sv_dim ? fcb->sv_dim : feat_dimension(fcb);
+    if (n_frames <= 0) { feat_free(fcb); return 0; }
+    cep = ckd_calloc((size_t)n_frames * cepsize, sizeof(float));   /* normalised IN PLACE */
+    memcpy(cep, cep_in, sizeof(float) * (size_t)n_frames * cepsize);
+    cepp = ckd_calloc(n_frames, sizeof(*cepp));
+    for (t = 0; t < n_frames; ++t) cepp[t] = (mfcc_t *)(cep + (size_t)t * cepsize);
+    fb = feat_array_alloc(fcb, n_frames + 16);
+    nfr = feat_s2mfc2feat_live(fcb, cepp, &ncep, TRUE, TRUE, fb);
+    for (t = 0; t < nfr; ++t) memcpy(out + (size_t)t * tot, fb[t][0], tot * sizeof(float));
+    feat_array_free(fb);
+    ckd_free(cepp);
+    ckd_free(cep);
+    feat_free(fcb);
+    return nfr;
+}
+
 /* Copy out tmat->tp as [n_tmat][n_state][n_state+1] uint8 and the mdef's
  * sseq table as [n_sseq][n_emit] uint16.  Pass NULL to query sizes only.
  * sizes[0..2] = n_tmat, n_emit_state, n_sseq. */

@@ -1212,3 +1212,127 @@ orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *feat)
     }
     free(buf); free(mean);
 }
+
+
+/* ---- general feature stage ------------------------------------------------
+ * The same walk as the reference: pad (feat.c:1253-1259), cmn [+varnorm]
+ * (cmn.c:150-213), agc max (agc.c:108-126), the type's compute_feat on every
+ * frame (feat.c:559-849), lda (lda.c:141-160), subvectors (feat.c:334-355). */
+static int
+orc_feat_window(int type, int cs, int *k)
+{
+    switch (type) {
+    case 0: *k = 3 * cs; return 3;
+    case 1: *k = 39; return cs == 13 ? 3 : -1;
+    case 2: *k = 51; return cs == 13 ? 4 : -1;
+    case 3: *k = 4 * cs; return 4;
+    case 4: *k = cs; return 0;
+    case 5: *k = 2 * cs; return 2;
+    }
+    return -1;
+}
+
+int
+orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
+                 const float *lda, int lda_dim, const int *subvec, int n_subvec,
+                 const float *cep, int T, float *out)
+{
+    int k, t, i, j, n, out_len;
+    const int cs = cepsize, win = orc_feat_window(type, cepsize, &k);
+    float *buf, *row, *tmp;
+    if (win < 0) return -1;
+    out_len = n_subvec > 0 ? n_subvec : (lda ? lda_dim : k);
+    if (T <= 0) return out_len;
+    n = T + 2 * win;
+    buf = malloc(sizeof(float) * (size_t)n * cs);
+    row = calloc(k, sizeof(float));
+    tmp = calloc(k, sizeof(float));
+    for (t = 0; t < n; ++t) {
+        int src = t - win;
+        if (src < 0) src = 0;
+        if (src > T - 1) src = T - 1;
+        memcpy(buf + (size_t)t * cs, cep + (size_t)src * cs, sizeof(float) * cs);
+    }
+    if (cmn) {
+        float *mean = calloc(cs, sizeof(float)), *var = calloc(cs, sizeof(float));
+        for (t = 0; t < n; ++t)
+            for (i = 0; i < cs; ++i) mean[i] += buf[(size_t)t * cs + i];
+        for (i = 0; i < cs; ++i) mean[i] /= n;
+        if (!varnorm) {
+            for (t = 0; t < n; ++t)
+                for (i = 0; i < cs; ++i) buf[(size_t)t * cs + i] -= mean[i];
+        }
+        else {
+            for (t = 0; t < n; ++t)
+                for (i = 0; i < cs; ++i) {
+                    float d = buf[(size_t)t * cs + i] - mean[i];
+                    var[i] += d * d;
+                }
+            for (i = 0; i < cs; ++i) var[i] = (float)sqrt((double)n / var[i]);
+            for (t = 0; t < n; ++t)
+                for (i = 0; i < cs; ++i)
+                    buf[(size_t)t * cs + i] = (buf[(size_t)t * cs + i] - mean[i]) * var[i];
+        }
+        free(mean); free(var);
+    }
+    if (agc) {
+        float m = buf[0];
+        for (t = 1; t < n; ++t)
+            if (buf[(size_t)t * cs] > m) m = buf[(size_t)t * cs];
+        for (t = 0; t < n; ++t) buf[(size_t)t * cs] -= m;
+    }
+#define C_(off, d) (c[(off) * cs + (d)])
+#define DD_(d) ((C_(3, d) - C_(-1, d)) - (C_(1, d) - C_(-3, d)))
+    for (t = 0; t < T; ++t) {
+        const float *c = buf + (size_t)(t + win) * cs;
+        float *f = row;
+        switch (type) {
+        case 0:
+            for (i = 0; i < cs; ++i) *f++ = C_(0, i);
+            for (i = 0; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
+            for (i = 0; i < cs; ++i) *f++ = DD_(i);
+            break;
+        case 1:
+            for (i = 1; i < cs; ++i) *f++ = C_(0, i);
+            for (i = 1; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
+            *f++ = C_(0, 0); *f++ = C_(2, 0) - C_(-2, 0); *f++ = DD_(0);
+            for (i = 1; i < cs; ++i) *f++ = DD_(i);
+            break;
+        case 2:
+            for (i = 1; i < cs; ++i) *f++ = C_(0, i);
+            for (i = 1; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
+            for (i = 1; i < cs; ++i) *f++ = C_(4, i) - C_(-4, i);
+            *f++ = C_(0, 0); *f++ = C_(2, 0) - C_(-2, 0); *f++ = DD_(0);
+            for (i = 1; i < cs; ++i) *f++ = DD_(i);
+            break;
+        case 3:
+            for (i = 0; i < cs; ++i) *f++ = C_(0, i);
+            for (i = 0; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
+            for (i = 0; i < cs; ++i) *f++ = C_(4, i) - C_(-4, i);
+            for (i = 0; i < cs; ++i) *f++ = DD_(i);
+            break;
+        case 4:
+            for (i = 0; i < cs; ++i) *f++ = C_(0, i);
+            break;
+        case 5:
+            for (i = 0; i < cs; ++i) *f++ = C_(0, i);
+            for (i = 0; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
+            break;
+        }
+        if (lda) {
+            memset(tmp, 0, sizeof(float) * k);
+            for (j = 0; j < lda_dim; ++j)
+                for (i = 0; i < k; ++i) tmp[j] += row[i] * lda[(size_t)j * k + i];
+            memcpy(row, tmp, sizeof(float) * k);
+        }
+        if (n_subvec > 0) {
+            for (j = 0; j < n_subvec; ++j) tmp[j] = row[subvec[j]];
+            memcpy(row, tmp, sizeof(float) * n_subvec);
+        }
+        memcpy(out + (size_t)t * out_len, row, sizeof(float) * out_len);
+    }
+#undef C_
+#undef DD_
+    free(buf); free(row); free(tmp);
+    return out_len;
+}

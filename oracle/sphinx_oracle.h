@@ -158,6 +158,15 @@ void orc_s3_counts(const orc_s3_model_t *m, int64_t *c);
  * (feat.c:726-769, 1241-1265; cmn.c:150-186).  cep [T][cepsize], feat [T][3*cepsize]. */
 void orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *feat);
 
+/* General form (feat.c:1110-1135 feat_compute_utt on the padded utterance of
+ * feat.c:1241-1265): type 0 1s_c_d_dd, 1 s3_1x39, 2 s2_4x, 3 1s_c_d_ld_dd, 4 1s_c,
+ * 5 1s_c_d (feat.c:559-849); cmn 0/1 (+ varnorm, cmn.c:150-213); agc 0 none, 1 max
+ * (agc.c:108-126); lda [lda_dim][k] or NULL (lda.c:141-160); subvec indices or NULL
+ * (feat.c:334-355).  out [T][out_len]; returns out_len (<0: bad configuration). */
+int orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
+                     const float *lda, int lda_dim, const int *subvec, int n_subvec,
+                     const float *cep, int T, float *out);
+
 #ifdef __cplusplus
 }
 #endif

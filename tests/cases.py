@@ -63,3 +63,22 @@ def tied_arrays(name, g):
     n_sen = int(g["n_sen"])
     sd = engine.read_sendump(d + "/sendump", gm["n_feat"], gm["n_density"], n_sen)
     return gm, gv, sd, n_sen
+
+
+# (ftype, cmn, varnorm, agc, use_lda, lda_dim, svspec) of tests/golden/feat_general.npz
+# (outputs of the reference's own feat_t; tests/golden/make_golden.py feat_general)
+FEAT_GOLDEN_CASES = [
+    ("1s_c_d_dd", 1, 0, 0, False, 0, None),
+    ("1s_c_d_dd", 1, 1, 1, False, 0, None),
+    ("1s_c_d_dd", 1, 0, 0, True, 29, None),
+    ("1s_c_d_dd", 1, 0, 0, True, 0, "0-9/10-19/20-28"),
+    ("1s_c_d_dd", 0, 0, 1, False, 0, "0-12/13-25/26-38"),
+    ("s3_1x39", 1, 0, 1, False, 0, None),
+    ("s3_1x39", 1, 1, 0, True, 32, "3,1,5/0"),
+    ("s2_4x", 1, 0, 0, False, 0, None),
+    ("s2_4x", 0, 0, 1, False, 0, None),
+    ("1s_c_d_ld_dd", 1, 1, 0, False, 0, None),
+    ("1s_c_d_ld_dd", 1, 0, 0, True, 40, None),
+    ("1s_c", 1, 0, 0, False, 0, None),
+    ("1s_c_d", 1, 0, 1, True, 0, None),
+]

@@ -187,8 +187,25 @@ def s3_case(name="s3_synth.npz", T=40):
     r.free()
 
 
+def feat_general():
+    """General feature stage: the reference's own feat_t (ref_feat_compute in oracle/ref_shim.c)
+    on 80 frames of test/data/wsj/442c0201.mfc for the configurations of cases.FEAT_GOLDEN_CASES."""
+    import cases
+    cep = orc.read_mfc(os.path.join(orc.DATA_DIR, "test", "wsj", "442c0201.mfc"))[40:120].copy()
+    lda = np.random.default_rng(77).standard_normal((52, 52)).astype(np.float32)
+    klen = {"1s_c_d_dd": 39, "s3_1x39": 39, "s2_4x": 51, "1s_c_d_ld_dd": 52, "1s_c": 13, "1s_c_d": 26}
+    outs = {}
+    for i, (ftype, cmn, vn, agc, use_lda, dim, sv) in enumerate(cases.FEAT_GOLDEN_CASES):
+        outs[f"out{i}"] = orc.ref_feat_compute(cep, ftype, cmn, vn, agc, lda[:klen[ftype], :klen[ftype]] if use_lda else None, dim, sv)
+    save("feat_general.npz", cep=cep, lda=lda, **outs)
+
+
 if __name__ == "__main__":
     assert orc.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    if len(sys.argv) > 1:      # regenerate only the named fixtures, e.g. `make_golden.py feat_general`
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     logmath()
     ms_case("ms_small.npz", 48, 8, 13, 1, 4, 33, 11)
     ms_case("ms_3stream.npz", 40, 16, 7, 3, 4, 21, 12)

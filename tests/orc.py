@@ -104,6 +104,8 @@ def ref():
         L.ref_acmod_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, C.c_int, i16p]
         L.ref_acmod_sen2cimap.argtypes = [vp, u8p]
         L.ref_acmod_cep2feat.argtypes = [vp, f32p, C.c_int, C.c_int, f32p, C.c_int]
+        L.ref_feat_compute.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, f32p, C.c_int, C.c_int,
+                                       C.c_int, C.c_char_p, f32p, C.c_int, f32p, i32p, i32p]
         L.ref_acmod_tables.argtypes = [vp, i32p, u8p, u16p]
         L.ref_tmat_load.argtypes = [C.c_char_p, C.c_double, C.c_double, u8p, C.c_int, i32p]
         L.ref_hmm_eval_batch.restype = C.c_int32
@@ -451,3 +453,62 @@ def port_feat_1s_c_d_dd(cep, cmn=True):
     out = np.zeros((cep.shape[0], 3 * cep.shape[1]), np.float32)
     port.orc_feat_1s_c_d_dd(_p(cep, C.c_float), cep.shape[0], cep.shape[1], 1 if cmn else 0, _p(out, C.c_float))
     return out
+
+
+FEAT_TYPES = ["1s_c_d_dd", "s3_1x39", "s2_4x", "1s_c_d_ld_dd", "1s_c", "1s_c_d"]
+port.orc_feat_compute.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int, i32p, C.c_int,
+                                  f32p, C.c_int, f32p]
+
+
+def parse_svspec(spec):
+    """'0-12/13-25/26-38' or '0,2,4/1,3' -> flat index list (sphinxbase parse_subvecs; the
+    stream boundaries do not change the memory layout)."""
+    idx = []
+    for part in spec.split("/"):
+        for piece in part.split(","):
+            if "-" in piece:
+                a, b = piece.split("-")
+                idx.extend(range(int(a), int(b) + 1))
+            else:
+                idx.append(int(piece))
+    return idx
+
+
+def port_feat_compute(cep, ftype="1s_c_d_dd", cmn=True, varnorm=False, agc=False, lda=None, lda_dim=0, svspec=None):
+    cep = _c(cep, np.float32)
+    T, cs = cep.shape
+    sv = np.array(parse_svspec(svspec) if svspec else [], np.int32)
+    if lda is not None:
+        lda = _c(lda, np.float32)
+        if lda_dim <= 0 or lda_dim > lda.shape[0]:
+            lda_dim = lda.shape[0]
+        lda = np.ascontiguousarray(lda[:lda_dim])
+    out = np.zeros((T, 4 * max(cs, 13)), np.float32)
+    n = port.orc_feat_compute(FEAT_TYPES.index(ftype), cs, int(cmn), int(varnorm), int(agc),
+                              _p(lda, C.c_float) if lda is not None else None, lda_dim,
+                              _p(sv, C.c_int32) if sv.size else None, sv.size, _p(cep, C.c_float), T,
+                              _p(out, C.c_float))
+    if n < 0:
+        raise ValueError("bad feature configuration")
+    flat = out.reshape(-1)[:T * n]
+    return flat.reshape(T, n).copy()
+
+
+def ref_feat_compute(cep, ftype="1s_c_d_dd", cmn=True, varnorm=False, agc=False, lda=None, lda_dim=0, svspec=None):
+    """The reference's feat_t on one utterance -> [T][out_dim] (the valid prefix of its rows)."""
+    cep = _c(cep, np.float32)
+    T, cs = cep.shape
+    out = np.zeros((T + 16, 4 * max(cs, 13)), np.float32)
+    row = (C.c_int32 * 1)()
+    od = (C.c_int32 * 1)()
+    if lda is not None:
+        lda = _c(lda, np.float32)
+    n = ref().ref_feat_compute(ftype.encode(), b"current" if cmn else b"none", int(varnorm),
+                               b"max" if agc else b"none", cs,
+                               _p(lda, C.c_float) if lda is not None else None,
+                               lda.shape[0] if lda is not None else 0, lda.shape[1] if lda is not None else 0, lda_dim,
+                               svspec.encode() if svspec else None, _p(cep, C.c_float), T, _p(out, C.c_float), row, od)
+    if n < 0:
+        raise ValueError("reference rejected the feature configuration")
+    rows = out.reshape(-1)[:n * row[0]].reshape(n, row[0])
+    return rows[:, :od[0]].copy()

@@ -50,3 +50,104 @@ def test_feature_kernel_bit_exact():
 def test_feature_kernel_empty_batch():
     out = b.feat_1s_c_d_dd(np.zeros((0, 13), np.float32), np.array([0, 0], np.int32))
     assert out.shape == (0, 39)
+
+
+# ------------------------------------------------------------------ general form
+_CFGS = [(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 0, 1)]   # (cmn, varnorm, agc)
+
+
+def _cep(T, seed=0):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((T, 13)) * 4 + rng.standard_normal(13) * 10).astype(np.float32)
+
+
+def _same(a, b):
+    # 1-frame utterances with -varnorm divide by a zero variance: NaN in the reference too
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ftype", orc.FEAT_TYPES)
+def test_general_feature_port_matches_reference(ftype):
+    """Every -feat type x cmn/varnorm/agc against the reference's own feat_t (feat_init +
+    feat_s2mfc2feat_live(full utterance)), including 1- and 2-frame utterances."""
+    cep = _cep(60)
+    for cmn, vn, agc in _CFGS:
+        for T in (60, 9, 2, 1):
+            assert _same(orc.port_feat_compute(cep[:T], ftype, cmn, vn, agc),
+                         orc.ref_feat_compute(cep[:T], ftype, cmn, vn, agc)), (ftype, cmn, vn, agc, T)
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+def test_lda_and_subvector_port_matches_reference():
+    """feat_lda_transform (-lda / -ldadim) and feat_subvec_project (-svspec), alone and chained."""
+    cep = _cep(40, 1)
+    rng = np.random.default_rng(2)
+    for ftype in ("1s_c_d_dd", "s3_1x39", "1s_c_d_ld_dd", "1s_c_d"):
+        k = orc.port_feat_compute(cep, ftype).shape[1]
+        lda = rng.standard_normal((k, k)).astype(np.float32)
+        for dim in (0, 20, k):
+            for sv in (None, "0-9/10-19", "3,1,5/0"):
+                assert _same(orc.port_feat_compute(cep, ftype, True, False, False, lda, dim, sv),
+                             orc.ref_feat_compute(cep, ftype, True, False, False, lda, dim, sv)), (ftype, dim, sv)
+        assert _same(orc.port_feat_compute(cep, ftype, svspec="0-12/13-25"),
+                     orc.ref_feat_compute(cep, ftype, svspec="0-12/13-25"))
+
+
+def test_general_feature_port_matches_golden():
+    g = cases.load("feat_general.npz")
+    lda = g["lda"]
+    for i, (ftype, cmn, vn, agc, use_lda, dim, sv) in enumerate(cases.FEAT_GOLDEN_CASES):
+        got = orc.port_feat_compute(g["cep"], ftype, cmn, vn, agc, lda[:_klen(ftype), :_klen(ftype)] if use_lda else None, dim, sv)
+        assert _same(got, g[f"out{i}"]), (ftype, cmn, vn, agc, use_lda, dim, sv)
+    # and the special case is the general one
+    np.testing.assert_array_equal(orc.port_feat_compute(g["cep"]), orc.port_feat_1s_c_d_dd(g["cep"], True))
+
+
+def _klen(ftype):
+    return {"1s_c_d_dd": 39, "s3_1x39": 39, "s2_4x": 51, "1s_c_d_ld_dd": 52, "1s_c": 13, "1s_c_d": 26}[ftype]
+
+
+@pytest.mark.gpu
+def test_general_feature_kernels_match_golden():
+    g = cases.load("feat_general.npz")
+    lda = g["lda"]
+    for i, (ftype, cmn, vn, agc, use_lda, dim, sv) in enumerate(cases.FEAT_GOLDEN_CASES):
+        got = b.feat_compute(g["cep"], None, ftype, cmn, vn, agc, lda[:_klen(ftype), :_klen(ftype)] if use_lda else None, dim,
+                             orc.parse_svspec(sv) if sv else None)
+        assert _same(got, g[f"out{i}"]), (ftype, cmn, vn, agc, use_lda, dim, sv)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ftype", orc.FEAT_TYPES)
+def test_general_feature_kernels_bit_exact_ragged_batch(ftype):
+    """A ragged batch (1-, 2-frame and long utterances) in one call == the port per utterance."""
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 5, 300, 7, 1, 64, 129, 9]
+    cep = _cep(sum(lens), 7)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    k = _klen(ftype)
+    lda = rng.standard_normal((k, k)).astype(np.float32)
+    for cmn, vn, agc in _CFGS:
+        for use_lda, dim, sv in ((False, 0, None), (True, 0, None), (True, k - 7, "0-3/9,8"), (False, 0, "2,0/5-7")):
+            if ftype == "s2_4x" and (use_lda or sv):
+                continue
+            want = np.concatenate([orc.port_feat_compute(cep[off[u]:off[u + 1]], ftype, cmn, vn, agc,
+                                                         lda if use_lda else None, dim, sv) for u in range(len(lens))])
+            got = b.feat_compute(cep, off, ftype, cmn, vn, agc, lda if use_lda else None, dim,
+                                 orc.parse_svspec(sv) if sv else None)
+            assert _same(got, want), (ftype, cmn, vn, agc, use_lda, dim, sv)
+
+
+@pytest.mark.gpu
+def test_general_feature_stage_refuses_what_the_reference_rejects():
+    cep = _cep(10)
+    with pytest.raises(b.B200Error):
+        b.feat_compute(cep, None, "s2_4x", lda=np.eye(51, dtype=np.float32))          # lda.c:69-73
+    with pytest.raises(b.B200Error):
+        b.feat_compute(cep, None, "1s_c_d_dd", lda=np.eye(38, dtype=np.float32))      # lda.c:127-128
+    with pytest.raises(b.B200Error):
+        b.feat_compute(cep[:, :12], None, "s3_1x39")                                  # feat.c: cepsize must be 13
+    with pytest.raises(b.B200Error):
+        b.feat_compute(cep, None, "1s_c", subvec=list(range(14)))                     # feat.c:309-313
+    assert b.feat_compute(np.zeros((0, 13), np.float32), np.array([0, 0], np.int32), "s2_4x").shape == (0, 51)
