@@ -28,7 +28,7 @@ class MgauCfg(C.Structure):
     _fields_ = [("n_mgau", C.c_int32), ("n_feat", C.c_int32), ("n_density", C.c_int32),
                 ("n_sen", C.c_int32), ("featlen", C.c_int32 * 4), ("topn", C.c_int32),
                 ("aw", C.c_int32), ("ds_ratio", C.c_int32), ("logbase", C.c_double),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("topn_beam", C.c_int32 * 4)]
 
 
 class HmmSoa(C.Structure):

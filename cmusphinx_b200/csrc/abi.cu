@@ -116,6 +116,7 @@ b200_mgau *mgau_common(int kind, const b200_mgau_cfg_t *cfg, const float *mean, 
     for (int f = 0; f < cfg->n_feat; ++f) {
         g.featlen[f] = cfg->featlen[f]; g.featoff[f] = g.veclen;
         g.veclen += cfg->featlen[f]; g.maxlen = std::max(g.maxlen, cfg->featlen[f]);
+        g.topn_beam[f] = kind == 2 ? cfg->topn_beam[f] : 0;   // only s2_semi_mgau_init reads -topn_beam
     }
     m->n_param = (size_t)g.n_mgau * g.n_density * g.veclen;
     m->n_det = (size_t)g.n_mgau * g.n_feat * g.n_density;

@@ -21,6 +21,7 @@ struct GmmDev {
     int n_clust, row_bytes;
     uint8_t mixw_cb[16];
     uint8_t logadd[256];        // logmath_init(base, 10, 1) byte table
+    int topn_beam[B200_MAX_STREAMS];   // s2_semi -topn_beam per stream, 0 = off
 };
 
 // Integer top-N list of the tied back-ends (shared by the exact kernel and the

@@ -314,6 +314,7 @@ tied_senone_kernel(GmmDev g, const int2 *__restrict__ lists, int T, int t0, int 
     __shared__ uint8_t s_tab[256];
     __shared__ uint8_t s_cb16[16];
     __shared__ int s_best;
+    __shared__ int s_neff[B200_MAX_STREAMS];   // mgau_norm's return value per stream (s2_semi -topn_beam)
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += blockDim.x) s_tab[i] = g.logadd[i];
     if (tid < 16) s_cb16[tid] = g.mixw_cb[tid];
@@ -346,6 +347,16 @@ tied_senone_kernel(GmmDev g, const int2 *__restrict__ lists, int T, int t0, int 
         l_sc[i] = v;
     }
     __syncthreads();
+    if (tid < F) {
+        // s2_semi_mgau.c:199-206: the list ends at the first score above the stream's beam
+        int n = N;
+        const int beam = semi ? g.topn_beam[tid] : 0;
+        if (beam)
+            for (int j = 0; j < N; ++j)
+                if (l_sc[tid * N + j] > beam) { n = j; break; }
+        s_neff[tid] = n;
+    }
+    __syncthreads();
 
     int32_t mybest = 0x7fffffff;
     const int rb = g.row_bytes;
@@ -356,7 +367,8 @@ tied_senone_kernel(GmmDev g, const int2 *__restrict__ lists, int T, int t0, int 
             const int32_t *cw = l_cw + (c * F + f) * N;
             const int32_t *sc = l_sc + (c * F + f) * N;
             int32_t fden = 0;
-            for (int j = 0; j < N; ++j) {
+            const int nf = s_neff[f];
+            for (int j = 0; j < nf; ++j) {
                 int32_t mw;
                 const uint8_t *r = g.mixw_t + ((size_t)f * g.n_density + cw[j]) * rb;
                 if (g.n_clust) {

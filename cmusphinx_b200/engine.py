@@ -180,6 +180,7 @@ class MgauConfig:
     ds_ratio: int = 1
     logbase: float = LOGBASE
     device: int = 0
+    topn_beam: Sequence[int] = ()   # -topn_beam per stream (s2_semi only)
 
     def to_c(self) -> MgauCfg:
         c = MgauCfg()
@@ -187,6 +188,8 @@ class MgauConfig:
         for i, l in enumerate(self.featlen):
             c.featlen[i] = int(l)
         c.topn, c.aw, c.ds_ratio, c.logbase, c.device = self.topn, self.aw, self.ds_ratio, self.logbase, self.device
+        for i, v in enumerate(self.topn_beam):
+            c.topn_beam[i] = int(v)
         return c
 
 
@@ -351,7 +354,7 @@ def semi_from_arrays(cfg, mean, var_pre, det, mixw_rows, n_clust=0, mixw_cb=None
 
 
 def tied_from_model_dir(hmmdir: str, n_sen: int, sen2cb=None, topn=4, varfloor=1e-4, mixwfloor=1e-7,
-                        logbase=LOGBASE, device=0) -> Mgau:
+                        logbase=LOGBASE, device=0, topn_beam=()) -> Mgau:
     """Back-end selection of acmod_init_am (PS/acmod.c:110-127) for a model
     directory holding means / variances / sendump|mixture_weights: one codebook
     -> s2_semi, otherwise ptm (sen2cb = bin_mdef sen2cimap must be given)."""
@@ -379,7 +382,8 @@ def tied_from_model_dir(hmmdir: str, n_sen: int, sen2cb=None, topn=4, varfloor=1
     else:
         mw = read_mixw(os.path.join(hmmdir, "mixture_weights"))
         rows, n_clust, cb = mixw_quantize_tied(mw, mixwfloor, logbase), 0, None
-    cfg = MgauConfig(n_mgau, n_feat, n_density, n_sen, veclen, topn=topn, logbase=logbase, device=device)
+    cfg = MgauConfig(n_mgau, n_feat, n_density, n_sen, veclen, topn=topn, logbase=logbase, device=device,
+                     topn_beam=tuple(topn_beam))
     if n_mgau == 1:
         return semi_from_arrays(cfg, mean, var, det, rows, n_clust, cb)
     return ptm_from_arrays(cfg, mean, var, det, rows, sen2cb, n_clust, cb)

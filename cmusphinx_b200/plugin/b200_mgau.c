@@ -179,6 +179,20 @@ static void fill_cfg(b200_mgau_cfg_t *c, cmd_ln_t *config, const gau_t *g, int n
     c->aw = cmd_ln_int32_r(config, "-aw");
     c->ds_ratio = cmd_ln_int32_r(config, "-ds");
     c->logbase = logbase;
+    {   /* -topn_beam as split_topn reads it (s2_semi_mgau.c:1204-1231): comma list of uint8,
+         * streams past the end of the list get the largest value given */
+        const char *str = cmd_ln_str_r(config, "-topn_beam");
+        int i = 0, maxn = 0;
+        while (str && *str && i < c->n_feat) {
+            int v = (uint8)atoi(str);
+            const char *comma = strchr(str, ',');
+            c->topn_beam[i++] = v;
+            if (v > maxn) maxn = v;
+            if (!comma) break;
+            str = comma + 1;
+        }
+        while (i < c->n_feat) c->topn_beam[i++] = maxn;
+    }
     c->device = getenv("B200_DEVICE") ? atoi(getenv("B200_DEVICE")) : 0;
 }
 

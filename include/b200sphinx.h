@@ -132,6 +132,10 @@ typedef struct {
     int32_t ds_ratio;   /* -ds    (:347); only 1 is supported on device */
     double  logbase;    /* -logbase (:371) */
     int32_t device;     /* CUDA device ordinal */
+    /* -topn_beam (PS cmdln_macro.h:355), s2_semi only: per stream, the list is cut at the
+     * first normalised score above the beam (mgau_norm, PS/s2_semi_mgau.c:189-207); 0 = off.
+     * Values as split_topn leaves them (uint8 range; PS/s2_semi_mgau.c:1204-1231). */
+    int32_t topn_beam[B200_MAX_STREAMS];
 } b200_mgau_cfg_t;
 
 /* ms back-end: PS/ms_mgau.c:79-141 ms_mgau_init.  mean/var/det are the

@@ -236,7 +236,8 @@ typedef struct {
  * NULL/"" (auto: s2_semi -> ptm -> ms) or ".semi."/".ptm."/".cont." to force
  * the generic ms back-end. */
 void *
-ref_acmod_open(const char *hmmdir, const char *senmgau, int topn, int ds, double logbase)
+ref_acmod_open_ex(const char *hmmdir, const char *senmgau, int topn, int ds, double logbase,
+                  const char *topn_beam)
 {
     ref_acmod_t *h = ckd_calloc(1, sizeof(*h));
     char tn[32], dsb[32], lb[64];
@@ -254,6 +255,8 @@ ref_acmod_open(const char *hmmdir, const char *senmgau, int topn, int ds, double
                                 "-logbase", lb, "-compallsen", "yes", NULL);
     if (h->config == NULL)
         return NULL;
+    if (topn_beam && topn_beam[0])
+        cmd_ln_set_str_r(h->config, "-topn_beam", topn_beam);
     /* Mirror ps_init_defaults (pocketsphinx.c:146-158): expand -hmm. */
     {
         static const char *const files[][2] = {
@@ -453,6 +456,12 @@ ref_feat_compute(const char *type, const char *cmn, int varnorm, const char *agc
     ckd_free(cep);
     feat_free(fcb);
     return nfr;
+}
+
+void *
+ref_acmod_open(const char *hmmdir, const char *senmgau, int topn, int ds, double logbase)
+{
+    return ref_acmod_open_ex(hmmdir, senmgau, topn, ds, logbase, NULL);
 }
 
 /* Copy out tmat->tp as [n_tmat][n_state][n_state+1] uint8 and the mdef's

@@ -423,6 +423,8 @@ struct orc_tied_model {
     topn_t *f;                /* current slot */
     char *cb_active;
     int frame_idx;
+    int topn_beam[8];         /* s2_semi -topn_beam per stream, 0 = off */
+    int hist_n[2][8];         /* mgau_norm's return value per slot and stream (topn_hist_n) */
 };
 
 orc_tied_model_t *
@@ -455,6 +457,14 @@ orc_tied_free(orc_tied_model_t *m)
     if (!m) return;
     orc_logmath_free(m->lm8);
     free(m->hist[0]); free(m->hist[1]); free(m->cb_active); free(m);
+}
+
+/* s2_semi_mgau.c:1300-1303: -topn_beam per stream (ignored by ptm, which never reads it) */
+void
+orc_tied_set_topn_beam(orc_tied_model_t *m, const int *beam)
+{
+    int f;
+    for (f = 0; f < m->n_feat; ++f) m->topn_beam[f] = m->kind == 1 ? 0 : beam[f];
 }
 
 /* ptm_mgau.c:846-865, s2_semi_mgau.c:1313-1324 */
@@ -637,7 +647,10 @@ orc_tied_frame_eval(orc_tied_model_t *m, const float *feat, const uint8_t *senon
                     t[k].score = -((t[k].score >> SHIFT) - norm);
                     if (t[k].score > 96)
                         t[k].score = 96;
+                    if (m->topn_beam[j] && t[k].score > m->topn_beam[j])   /* s2_semi_mgau.c:203-204 */
+                        break;
                 }
+                m->hist_n[frame % 2][j] = k;
             }
         }
         m->frame_idx = frame + 1;   /* what acmod_advance does (acmod.c:880) */
@@ -660,7 +673,8 @@ orc_tied_frame_eval(orc_tied_model_t *m, const float *feat, const uint8_t *senon
             for (f = 0; f < F; ++f) {
                 const topn_t *t = m->f + ((long)cb * F + f) * N;
                 int fden = 0;
-                for (k = 0; k < N; ++k) {
+                const int nf = m->kind == 1 ? N : m->hist_n[frame % 2][f];
+                for (k = 0; k < nf; ++k) {
                     int w = tied_mixw(m, f, t[k].cw, sen) + t[k].score;
                     fden = (k == 0) ? w : fast_add(m->lm8, fden, w);
                 }

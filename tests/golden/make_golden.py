@@ -187,6 +187,18 @@ def s3_case(name="s3_synth.npz", T=40):
     r.free()
 
 
+def semi_beam():
+    """s2_semi with -topn_beam (mgau_norm's list cut, s2_semi_mgau.c:189-207): the reference's
+    dense scores on the frames of semi_hub4wsj.npz for two beam settings."""
+    g = np.load(os.path.join(HERE, "semi_hub4wsj.npz"))
+    out = {}
+    for i, beam in enumerate(("20", "10,40")):
+        r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k"), topn_beam=beam)
+        out[f"dense{i}"] = r.score(g["feat"])
+        r.close()
+    save("semi_hub4wsj_beam.npz", beams=np.array([[20, 20, 20], [10, 40, 40]], np.int32), **out)
+
+
 def feat_general():
     """General feature stage: the reference's own feat_t (ref_feat_compute in oracle/ref_shim.c)
     on 80 frames of test/data/wsj/442c0201.mfc for the configurations of cases.FEAT_GOLDEN_CASES."""

@@ -59,6 +59,7 @@ def _load_port():
                                C.c_int, C.c_int, u8p, u8p, C.c_double]
     L.orc_tied_free.argtypes = [vp]
     L.orc_tied_reset.argtypes = [vp]
+    L.orc_tied_set_topn_beam.argtypes = [vp, i32p]
     L.orc_tied_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, C.c_int, i16p]
     L.orc_tied_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
     L.orc_tied_lists.argtypes = [vp, i32p, i32p]
@@ -94,6 +95,8 @@ def ref():
         L.ref_ms_params.argtypes = [vp, f32p, f32p, f32p, u8p]
         L.ref_ms_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
         L.ref_ms_eval_active.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, i16p]
+        L.ref_acmod_open_ex.restype = vp
+        L.ref_acmod_open_ex.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_char_p]
         L.ref_acmod_open.restype = vp
         L.ref_acmod_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double]
         L.ref_acmod_close.argtypes = [vp]
@@ -212,6 +215,10 @@ class PortTied:
     def reset(self):
         port.orc_tied_reset(self.h)
 
+    def set_topn_beam(self, beam):
+        bm = _c(list(beam) + [0] * 8, np.int32)
+        port.orc_tied_set_topn_beam(self.h, _p(bm, C.c_int32))
+
     def eval_all(self, feat):
         feat = _c(feat, np.float32).reshape(-1, self.veclen)
         out = np.zeros((feat.shape[0], self.n_sen), np.int16)
@@ -252,8 +259,8 @@ def hmm_eval(fn, n_emit, tp, sseq, senscr, score, history, out_score, out_histor
 class RefAcmod:
     """The reference's acmod + whichever back-end it selects, on a model directory."""
 
-    def __init__(self, hmmdir, senmgau="", topn=4, ds=1, logbase=LOGBASE):
-        self.h = ref().ref_acmod_open(hmmdir.encode(), senmgau.encode(), topn, ds, logbase)
+    def __init__(self, hmmdir, senmgau="", topn=4, ds=1, logbase=LOGBASE, topn_beam=""):
+        self.h = ref().ref_acmod_open_ex(hmmdir.encode(), senmgau.encode(), topn, ds, logbase, topn_beam.encode())
         if not self.h:
             raise RuntimeError(f"reference acmod_init failed for {hmmdir}")
         info = (C.c_int32 * 4)()

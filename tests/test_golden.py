@@ -156,6 +156,23 @@ def test_oracle_tied_golden(name, kind):
         np.testing.assert_array_equal(got, g["act_scores"][i])
 
 
+def test_oracle_semi_topn_beam_golden():
+    """-topn_beam (s2_semi_mgau.c:189-207) against the reference's scores for two beam settings."""
+    name = "semi_hub4wsj.npz"
+    if not cases.have_model(name):
+        pytest.skip("model files (oracle/_ref/data) not present")
+    g, gb = cases.load(name), cases.load("semi_hub4wsj_beam.npz")
+    gm, gv, sd, n_sen = cases.tied_arrays(name, g)
+    pv, pd = orc.port_precompute(gv["data"].reshape(-1, 13), 13, 1e-4, orc.LOGBASE)
+    pt = orc.PortTied(2, 1, 3, gm["veclen"], gm["n_density"], n_sen, 4, gm["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], None, orc.LOGBASE)
+    for i, beam in enumerate(gb["beams"]):
+        pt.reset()
+        pt.set_topn_beam([int(v) for v in beam])
+        np.testing.assert_array_equal(pt.eval_all(g["feat"]), gb[f"dense{i}"])
+        assert (gb[f"dense{i}"] != g["dense"]).mean() > 0.3   # the beam really changes the scores
+
+
 @pytest.mark.parametrize("name", ["cont_hub4_topn4.npz", "cont_hub4_topn8.npz"])
 def test_oracle_real_cont_golden(name):
     if not cases.have_model(name):

@@ -184,6 +184,45 @@ def test_tied_backends_vs_reference_golden(name, kind):
     m.free()
 
 
+def test_semi_topn_beam_vs_reference_golden_and_port():
+    """s2_semi -topn_beam on the device (exact scan and tensor-core codebook stage): frame 0
+    identical to the reference, the rest within the seed-free tolerance of the test above;
+    and identical to the port on single frames (fresh lists on both sides)."""
+    name = "semi_hub4wsj.npz"
+    if not cases.have_model(name):
+        pytest.skip("model files (oracle/_ref/data) not present")
+    g, gb = cases.load(name), cases.load("semi_hub4wsj_beam.npz")
+    gm, gv, sd, n_sen = cases.tied_arrays(name, g)
+    pv, pd = orc.port_precompute(gv["data"].reshape(-1, 13), 13, 1e-4, orc.LOGBASE)
+    pt = orc.PortTied(2, 1, 3, gm["veclen"], gm["n_density"], n_sen, 4, gm["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], None, orc.LOGBASE)
+    for i, beam in enumerate(gb["beams"]):
+        beam = [int(v) for v in beam]
+        m = b.tied_from_model_dir(cases.model_dir(name), n_sen, topn=4, logbase=orc.LOGBASE, topn_beam=beam)
+        want = gb[f"dense{i}"]
+        for path in (0, 1):
+            m.set_path(path)
+            got = m.score(g["feat"])
+            np.testing.assert_array_equal(got[0], want[0])
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert float((diff != 0).mean()) <= 1e-4 and diff.max() <= 2, (beam, path)
+        pt.set_topn_beam(beam)
+        for t in (3, 11, 17):
+            pt.reset()
+            np.testing.assert_array_equal(m.score(g["feat"][t:t + 1])[0], pt.frame_eval(g["feat"][t], None, True, 0))
+        m.free()
+    # ptm never reads -topn_beam: the setting must not change its scores
+    name = "ptm_hub4wsj.npz"
+    if cases.have_model(name):
+        g = cases.load(name)
+        n_sen = int(g["n_sen"])
+        m0 = b.tied_from_model_dir(cases.model_dir(name), n_sen, sen2cb=g["sen2cb"], topn=4, logbase=orc.LOGBASE)
+        m1 = b.tied_from_model_dir(cases.model_dir(name), n_sen, sen2cb=g["sen2cb"], topn=4, logbase=orc.LOGBASE,
+                                   topn_beam=[5, 5, 5])
+        np.testing.assert_array_equal(m0.score(g["feat"][:6]), m1.score(g["feat"][:6]))
+        m0.free(); m1.free()
+
+
 def test_config2_shape_subset_exact():
     """BASELINE config 2 shape (5000 senones x 32 Gaussians x 39 dims) on a frame
     subset the oracle finishes in seconds."""

@@ -230,3 +230,22 @@ def test_reference_ptm_reads_past_its_logadd_table():
     # AND inside its table it still equals the oracle on most rows
     if not same_rows.all():
         print(f"reference self-disagreement on {int((~same_rows).sum())} of {len(same_rows)} frames")
+
+
+@pytest.mark.parametrize("beam,per_stream", [("20", [20, 20, 20]), ("10,40", [10, 40, 40]), ("5,0,60", [5, 0, 60]), ("1", [1, 1, 1])])
+def test_s2_semi_topn_beam_matches_reference(beam, per_stream):
+    """-topn_beam: mgau_norm cuts each stream's list at the first normalised score above the
+    beam (s2_semi_mgau.c:189-207); split_topn fills missing streams with the largest value."""
+    hmm = os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k")
+    r = orc.RefAcmod(hmm, topn_beam=beam)
+    feat = _real_feats(r, "wsj/440c0201.mfc", 60)
+    want = r.score(feat)
+    from cmusphinx_b200 import engine
+    g, v = engine.read_gauden(hmm + "/means"), engine.read_gauden(hmm + "/variances")
+    pv, pd = orc.port_precompute(v["data"].reshape(-1, 13), 13)
+    sd = engine.read_sendump(hmm + "/sendump", 3, 256, r.n_sen)
+    pt = orc.PortTied(2, 1, 3, [13, 13, 13], 256, r.n_sen, 4, g["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], None)
+    pt.set_topn_beam(per_stream)
+    np.testing.assert_array_equal(pt.eval_all(feat), want)
+    r.close()
