@@ -81,6 +81,7 @@ _sig("b200_mgau_score_host", C.c_int, vp, vp, C.c_int, vp)
 _sig("b200_mgau_score_dev", C.c_int, vp, vp, C.c_int, vp, vp)
 _sig("b200_mgau_frame_eval", C.c_int, vp, c_i16p, c_u8p, C.c_int32, C.POINTER(c_f32p), C.c_int32, C.c_int32)
 _sig("b200_mgau_utt_begin", C.c_int, vp, vp, C.c_int)
+_sig("b200_mgau_utt_begin_at", C.c_int, vp, vp, C.c_int, C.c_int)
 _sig("b200_mgau_utt_frame", C.c_int, vp, c_i16p, c_u8p, C.c_int32, C.c_int32, C.c_int32)
 _sig("b200_mgau_last_ms", C.c_float, vp, C.c_int)
 _sig("b200_mgau_timing_avg", C.c_float, vp, C.c_int, C.c_int)

@@ -61,6 +61,7 @@ struct b200_mgau {
     float *d_ufeat = nullptr; size_t ufeat_cap = 0;
     int16_t *d_uraw = nullptr; size_t uraw_cap = 0;
     int2 *d_ulists = nullptr; size_t ulists_cap = 0;
+    int2 *d_carry = nullptr; int carry_frame = -2;   // s2_semi -ds: finished list of the last frame scored
     int utt_T = 0;
     uint8_t *d_active = nullptr; size_t active_cap = 0;
     int16_t *d_row = nullptr;
@@ -98,7 +99,11 @@ b200_mgau *mgau_common(int kind, const b200_mgau_cfg_t *cfg, const float *mean, 
     if (cfg->n_feat < 1 || cfg->n_feat > B200_MAX_STREAMS) { set_error("n_feat %d unsupported (1..%d)", cfg->n_feat, B200_MAX_STREAMS); return nullptr; }
     if (cfg->topn < 1 || cfg->topn > B200_MAX_TOPN) { set_error("topn %d unsupported (1..%d)", cfg->topn, B200_MAX_TOPN); return nullptr; }
     if (cfg->topn > cfg->n_density) { set_error("topn %d > n_density %d", cfg->topn, cfg->n_density); return nullptr; }
-    if (cfg->ds_ratio > 1) { set_error("-ds %d: frame down-sampling is not supported on the device path", cfg->ds_ratio); return nullptr; }
+    // -ds: ms_mgau never reads it (ignored, as in the reference); s2_semi re-scores the previous
+    // frame's codewords on the skipped frames (tied_ds_kernel); the reference's ptm path leaves
+    // RAW un-normalised scores in its lists on skipped frames (ptm_mgau.c:247-248 returns before
+    // the normalisation) and then indexes its 256-byte log-add table with them: undefined, refused.
+    if (cfg->ds_ratio > 1 && kind == 1) { set_error("-ds %d: the reference's ptm back-end is undefined for -ds > 1 (un-normalised list scores, ptm_mgau.c:247-248)", cfg->ds_ratio); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         set_error("no CUDA device: libb200sphinx has no CPU fallback");
@@ -169,13 +174,16 @@ int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cu
             if ((rc = gmm_launch_topn(g, 0, d_feat, T, t0, tn, nullptr, d_out, 1, st))) return rc;
         }
     } else {
-        const int chunk = frames_per_list_chunk(m);
+        int chunk = frames_per_list_chunk(m);
+        const int ds = m->kind == 2 ? std::max(1, m->cfg.ds_ratio) : 1;
+        if (ds > 1) chunk = std::max(ds, chunk - chunk % ds);   // every chunk starts on a fully evaluated frame
         if ((rc = ensure((void **)&m->d_lists, &m->lists_cap, (size_t)chunk * list_bytes_per_frame(m)))) return rc;
         for (int t0 = 0; t0 < T; t0 += chunk) {
             int tn = std::min(T - t0, chunk);
             if (m->kind != 0 && m->path == 1 && m->tct) rc = tc_tied_lists(m->tct, g, d_feat, t0, tn, m->d_lists, st);
             else rc = gmm_launch_topn(g, m->kind, d_feat, T, t0, tn, m->d_lists, nullptr, 0, st);
             if (rc) return rc;
+            if (ds > 1 && (rc = gmm_launch_tied_ds(g, d_feat, t0, tn, 0, ds, m->d_lists, nullptr, st))) return rc;
             if (m->kind == 0) rc = gmm_launch_ms_senone(g, m->d_lists, T, t0, tn, d_out, st);
             else rc = gmm_launch_tied_senone(g, m->d_lists, T, t0, tn, m->kind == 2, nullptr, 0, d_out, st);
             if (rc) return rc;
@@ -344,7 +352,7 @@ void b200_mgau_free(b200_mgau_t *m) {
     for (int i = 0; i < 2; ++i) { cudaFree(m->d_feat[i]); cudaFree(m->d_out[i]); if (m->st[i]) cudaStreamDestroy(m->st[i]); }
     for (int r = 0; r < b200_mgau::kRing; ++r)
         for (int i = 0; i < 4; ++i) if (m->ring[r][i]) cudaEventDestroy(m->ring[r][i]);
-    cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_active); cudaFree(m->d_row);
+    cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_carry); cudaFree(m->d_active); cudaFree(m->d_row);
     if (m->h_row) cudaFreeHost(m->h_row);
     if (m->h_active) cudaFreeHost(m->h_active);
     if (m->h_frame) cudaFreeHost(m->h_frame);
@@ -435,8 +443,10 @@ int b200_mgau_score_host(b200_mgau_t *m, const float *feat, int T, int16_t *out)
     if (!m || (T > 0 && (!feat || !out))) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(m->device));
     const GmmDev &g = m->g;
-    const int chunk = std::min(T, kHostChunkFrames);
+    int chunk = std::min(T, kHostChunkFrames);
     if (chunk <= 0) return B200_OK;
+    if (m->kind == 2 && m->cfg.ds_ratio > 1 && chunk < T)   // chunks are scored as frames 0.. : keep them aligned to -ds
+        chunk = std::max(m->cfg.ds_ratio, chunk - chunk % m->cfg.ds_ratio);
     const size_t fb = (size_t)chunk * g.veclen * 4, ob = (size_t)chunk * g.n_sen * 2;
     for (int i = 0; i < 2; ++i) {
         int rc = ensure((void **)&m->d_feat[i], &m->feat_cap[i], fb); if (rc) return rc;
@@ -489,8 +499,10 @@ float b200_mgau_timing_avg(b200_mgau_t *m, int n_calls, int which) {
 }
 
 // ------------------------------------------------- utterance / frame serving
-int b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T) {
-    if (!m || T < 0 || (T > 0 && !feat)) { set_error("null argument"); return B200_ERR_ARG; }
+int b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T) { return b200_mgau_utt_begin_at(m, feat, T, 0); }
+
+int b200_mgau_utt_begin_at(b200_mgau_t *m, const float *feat, int T, int frame0) {
+    if (!m || T < 0 || frame0 < 0 || (T > 0 && !feat)) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(m->device));
     const GmmDev &g = m->g;
     m->utt_T = 0;
@@ -511,6 +523,19 @@ int b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T) {
             if (m->path == 1 && m->tct) rc = tc_tied_lists(m->tct, g, m->d_ufeat, t0, tn, dst, st);
             else rc = gmm_launch_topn(g, m->kind, m->d_ufeat, T, t0, tn, dst, nullptr, 0, st);
             if (rc) return rc;
+        }
+        const int ds = m->kind == 2 ? std::max(1, m->cfg.ds_ratio) : 1;
+        if (ds > 1) {
+            const size_t lb = list_bytes_per_frame(m);
+            const bool need = frame0 % ds != 0;
+            if (need && m->carry_frame != frame0 - 1) {
+                set_error("-ds %d: frame %d needs the list of frame %d, which was not the last frame scored", ds, frame0, frame0 - 1);
+                return B200_ERR_ARG;
+            }
+            if (!m->d_carry) B200_CUDA_OK(cudaMalloc((void **)&m->d_carry, lb));
+            if ((rc = gmm_launch_tied_ds(g, m->d_ufeat, 0, T, frame0, ds, m->d_ulists, need ? m->d_carry : nullptr, st))) return rc;
+            B200_CUDA_OK(cudaMemcpyAsync(m->d_carry, (const char *)m->d_ulists + (size_t)(T - 1) * lb, lb, cudaMemcpyDeviceToDevice, st));
+            m->carry_frame = frame0 + T - 1;
         }
     }
     B200_CUDA_OK(cudaStreamSynchronize(st));
@@ -578,13 +603,12 @@ int b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr, const uint8_t *senone_a
 int b200_mgau_frame_eval(b200_mgau_t *m, int16_t *senscr, const uint8_t *senone_active, int32_t n_senone_active,
                          const float *const *feat, int32_t frame, int32_t compallsen) {
     if (!m || !senscr || !feat) { set_error("null argument"); return B200_ERR_ARG; }
-    (void)frame;
     const GmmDev &g = m->g;
     for (int f = 0; f < g.n_feat; ++f) {
         if (!feat[f]) { set_error("null stream pointer"); return B200_ERR_ARG; }
         memcpy(m->h_frame + g.featoff[f], feat[f], (size_t)g.featlen[f] * 4);
     }
-    int rc = b200_mgau_utt_begin(m, m->h_frame, 1);
+    int rc = b200_mgau_utt_begin_at(m, m->h_frame, 1, frame < 0 ? 0 : frame);   // the frame number matters to -ds only
     if (rc) return rc;
     return serve_frame(m, 0, senscr, senone_active, n_senone_active, compallsen);
 }

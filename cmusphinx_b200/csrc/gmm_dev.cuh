@@ -63,6 +63,8 @@ struct TopI {  // ptm / s2_semi: int32 scores, codewords
 
 int gmm_launch_topn(const GmmDev &g, int mode, const float *d_feat, int T, int t0, int tn, int2 *lists,
                     int16_t *raw, int fused, cudaStream_t st);
+int gmm_launch_tied_ds(const GmmDev &g, const float *d_feat, int t0, int tn, int frame0, int ds_ratio, int2 *lists,
+                       const int2 *carry, cudaStream_t st);
 int gmm_launch_ms_senone(const GmmDev &g, const int2 *lists, int T, int t0, int tn, int16_t *raw,
                          cudaStream_t st);
 int gmm_launch_normalize(int16_t *scr, int T, int n_sen, cudaStream_t st);

@@ -397,7 +397,61 @@ tied_senone_kernel(GmmDev g, const int2 *__restrict__ lists, int T, int t0, int 
         out[(size_t)t * g.n_sen + i] = (int16_t)(row[i] - sub);
 }
 
+// s2_semi -ds (s2_semi_mgau.c:176-186): on a frame whose number is not a multiple
+// of ds_ratio mgau_dist stops after eval_topn (:80-118) -- the previous frame's N
+// codewords re-scored on this frame, each bubbling up past strictly smaller scores.
+// The chain back to the last fully evaluated frame is at most ds_ratio - 1 frames
+// long, so every down-sampled frame replays it on its own: one thread per (frame,
+// codebook, stream).  lists[] holds the batch's frames [t0, t0 + tn); frame t of
+// the batch has number frame0 + t.  `carry` is the finished list of frame
+// frame0 - 1 for chains that start before the batch.
+__global__ void tied_ds_kernel(GmmDev g, const float *__restrict__ feat, int t0, int tn, int frame0, int R,
+                               int2 *__restrict__ lists, const int2 *__restrict__ carry) {
+    const int CF = g.n_mgau * g.n_feat, N = g.topn;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)tn * CF) return;
+    const int t = t0 + (int)(id / CF), cf = (int)(id % CF);
+    const int r = (frame0 + t) % R;
+    if (r == 0) return;
+    const int c = cf / g.n_feat, f = cf % g.n_feat, len = g.featlen[f];
+    const int base = t - r;   // batch index of the last full frame (may precede the batch)
+    int2 L[B200_MAX_TOPN];
+    const int2 *src = base >= t0 ? lists + ((size_t)(base - t0) * CF + cf) * N : carry + (size_t)cf * N;
+    for (int i = 0; i < N; ++i) L[i] = src[i];
+    const size_t pbase = (size_t)c * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
+    const size_t dbase = ((size_t)c * g.n_feat + f) * g.n_density;
+    for (int u = (base >= t0 ? base + 1 : t0); u <= t; ++u) {
+        const float *x = feat + (size_t)u * g.veclen + g.featoff[f];
+        for (int i = 0; i < N; ++i) {
+            const int cw = L[i].x;
+            const float *m = g.mean + pbase + (size_t)cw * len, *v = g.var + pbase + (size_t)cw * len;
+            float d = g.det[dbase + cw];
+            for (int k = 0; k < len; ++k) {
+                const float diff = __fsub_rn(x[k], m[k]);
+                d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), v[k]));
+            }
+            const int2 e = make_int2(cw, (int32_t)d);
+            int j = i - 1;
+            for (; j >= 0 && e.y > L[j].y; --j) L[j + 1] = L[j];
+            L[j + 1] = e;
+        }
+    }
+    int2 *dst = lists + ((size_t)(t - t0) * CF + cf) * N;
+    for (int i = 0; i < N; ++i) dst[i] = L[i];
+}
+
 // ------------------------------------------------------------ host launchers
+int gmm_launch_tied_ds(const GmmDev &g, const float *d_feat, int t0, int tn, int frame0, int ds_ratio, int2 *lists,
+                       const int2 *carry, cudaStream_t st) {
+    if (ds_ratio <= 1 || tn <= 0) return B200_OK;
+    if (t0 != 0 && (frame0 + t0) % ds_ratio != 0) { set_error("-ds: list chunk does not start on a fully evaluated frame"); return B200_ERR_ARG; }
+    if (t0 == 0 && frame0 % ds_ratio != 0 && !carry) { set_error("-ds %d: frame %d needs the list of frame %d, which was not scored by this back-end", ds_ratio, frame0, frame0 - 1); return B200_ERR_ARG; }
+    const long long n = (long long)tn * g.n_mgau * g.n_feat;
+    tied_ds_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, d_feat, t0, tn, frame0, ds_ratio, lists, carry);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 template <int MODE>
 static int launch_topn(const GmmDev &g, const float *d_feat, int T, int t0, int tn, int2 *lists,
                        int16_t *raw, int fused, cudaStream_t st) {

@@ -288,10 +288,11 @@ class Mgau:
         return lib.b200_mgau_timing_avg(self._h, n_calls, which)
 
     # utterance-batched serving (what the plug-in does)
-    def utt_begin(self, feat: np.ndarray):
+    def utt_begin(self, feat: np.ndarray, frame0: int = 0):
+        """Score a block of frames that starts at utterance frame `frame0` (only s2_semi -ds looks at it)."""
         feat = _c(feat, np.float32)
         T = feat.shape[0]
-        check(lib.b200_mgau_utt_begin(self._h, feat.ctypes.data, T), "utt_begin")
+        check(lib.b200_mgau_utt_begin_at(self._h, feat.ctypes.data, T, int(frame0)), "utt_begin")
 
     def utt_frame(self, senscr: np.ndarray, senone_active: Optional[np.ndarray], n_senone_active: int,
                   frame: int, compallsen: bool):
@@ -354,7 +355,7 @@ def semi_from_arrays(cfg, mean, var_pre, det, mixw_rows, n_clust=0, mixw_cb=None
 
 
 def tied_from_model_dir(hmmdir: str, n_sen: int, sen2cb=None, topn=4, varfloor=1e-4, mixwfloor=1e-7,
-                        logbase=LOGBASE, device=0, topn_beam=()) -> Mgau:
+                        logbase=LOGBASE, device=0, topn_beam=(), ds_ratio=1) -> Mgau:
     """Back-end selection of acmod_init_am (PS/acmod.c:110-127) for a model
     directory holding means / variances / sendump|mixture_weights: one codebook
     -> s2_semi, otherwise ptm (sen2cb = bin_mdef sen2cimap must be given)."""
@@ -383,7 +384,7 @@ def tied_from_model_dir(hmmdir: str, n_sen: int, sen2cb=None, topn=4, varfloor=1
         mw = read_mixw(os.path.join(hmmdir, "mixture_weights"))
         rows, n_clust, cb = mixw_quantize_tied(mw, mixwfloor, logbase), 0, None
     cfg = MgauConfig(n_mgau, n_feat, n_density, n_sen, veclen, topn=topn, logbase=logbase, device=device,
-                     topn_beam=tuple(topn_beam))
+                     topn_beam=tuple(topn_beam), ds_ratio=ds_ratio)
     if n_mgau == 1:
         return semi_from_arrays(cfg, mean, var, det, rows, n_clust, cb)
     return ptm_from_arrays(cfg, mean, var, det, rows, sen2cb, n_clust, cb)

@@ -383,7 +383,7 @@ b200_frame_eval(ps_mgau_t *mg, int16 *senscr, uint8 *senone_active, int32 n_seno
             for (f = 0; f < s->n_feat; ++f) { memcpy(s->stage + off, feat[f], s->veclen[f] * sizeof(float)); off += s->veclen[f]; }
             src = s->stage;
         }
-        rc = b200_mgau_utt_begin(s->gpu, src, n);
+        rc = b200_mgau_utt_begin_at(s->gpu, src, n, frame);
         if (rc) { E_ERROR("b200: utt_begin failed: %s\n", b200_last_error()); return -1; }
         s->cache_first = frame;
         s->cache_n = n;

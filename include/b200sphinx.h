@@ -129,7 +129,7 @@ typedef struct {
     int32_t featlen[B200_MAX_STREAMS];
     int32_t topn;       /* -topn  (PS cmdln_macro.h:351) */
     int32_t aw;         /* -aw    (:331), ms only */
-    int32_t ds_ratio;   /* -ds    (:347); only 1 is supported on device */
+    int32_t ds_ratio;   /* -ds    (:347): s2_semi implements it, ms ignores it (as the reference), ptm refuses > 1 */
     double  logbase;    /* -logbase (:371) */
     int32_t device;     /* CUDA device ordinal */
     /* -topn_beam (PS cmdln_macro.h:355), s2_semi only: per stream, the list is cut at the
@@ -236,6 +236,13 @@ int  b200_mgau_frame_eval(b200_mgau_t *m, int16_t *senscr,
  * normalisation (ms: PS/ms_mgau.c:226-248; ptm: PS/ptm_mgau.c:267-288,390-397)
  * on the host with the caller's active list. */
 int  b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T);
+/* Same, for a block of frames that starts at utterance frame `frame0` (live
+ * mode hands the decoder's buffered frames over piecewise).  Only s2_semi with
+ * -ds > 1 looks at the number: frames that are not a multiple of ds_ratio
+ * re-score the previous frame's codewords (PS/s2_semi_mgau.c:176-186), so a
+ * block starting on such a frame continues from the last frame of the block
+ * before it. */
+int  b200_mgau_utt_begin_at(b200_mgau_t *m, const float *feat, int T, int frame0);
 int  b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr,
                          const uint8_t *senone_active, int32_t n_senone_active,
                          int32_t frame, int32_t compallsen);

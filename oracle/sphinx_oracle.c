@@ -425,6 +425,7 @@ struct orc_tied_model {
     int frame_idx;
     int topn_beam[8];         /* s2_semi -topn_beam per stream, 0 = off */
     int hist_n[2][8];         /* mgau_norm's return value per slot and stream (topn_hist_n) */
+    int ds_ratio;             /* s2_semi -ds (0/1 = every frame) */
 };
 
 orc_tied_model_t *
@@ -465,6 +466,13 @@ orc_tied_set_topn_beam(orc_tied_model_t *m, const int *beam)
 {
     int f;
     for (f = 0; f < m->n_feat; ++f) m->topn_beam[f] = m->kind == 1 ? 0 : beam[f];
+}
+
+/* s2_semi_mgau.c:1298: -ds (the ptm flavour of -ds is undefined in the reference and not restated) */
+void
+orc_tied_set_ds(orc_tied_model_t *m, int ds_ratio)
+{
+    m->ds_ratio = m->kind == 1 ? 1 : ds_ratio;
 }
 
 /* ptm_mgau.c:846-865, s2_semi_mgau.c:1313-1324 */
@@ -641,7 +649,8 @@ orc_tied_frame_eval(orc_tied_model_t *m, const float *feat, const uint8_t *senon
                 topn_t *t = m->f + (long)j * N;
                 int32_t norm;
                 tied_eval_topn(m, 0, j, feat + m->featoff[j]);
-                tied_eval_cb(m, 0, j, feat + m->featoff[j]);
+                if (m->ds_ratio <= 1 || frame % m->ds_ratio == 0)   /* s2_semi_mgau.c:182-183 */
+                    tied_eval_cb(m, 0, j, feat + m->featoff[j]);
                 norm = t[0].score >> SHIFT;
                 for (k = 0; k < N; ++k) {
                     t[k].score = -((t[k].score >> SHIFT) - norm);

@@ -99,6 +99,7 @@ orc_tied_model_t *orc_tied_new(int kind, int n_mgau, int n_feat, const int *feat
 void orc_tied_free(orc_tied_model_t *m);
 void orc_tied_reset(orc_tied_model_t *m);   /* fresh history, as after *_init */
 /* One frame_eval call; frames must be fed in increasing order. */
+void orc_tied_set_ds(orc_tied_model_t *m, int ds_ratio);                 /* -ds, s2_semi only */
 void orc_tied_set_topn_beam(orc_tied_model_t *m, const int *beam);   /* -topn_beam, s2_semi only */
 int orc_tied_frame_eval(orc_tied_model_t *m, const float *feat,
                         const uint8_t *senone_active, int n_senone_active,

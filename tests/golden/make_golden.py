@@ -196,7 +196,13 @@ def semi_beam():
         r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k"), topn_beam=beam)
         out[f"dense{i}"] = r.score(g["feat"])
         r.close()
-    save("semi_hub4wsj_beam.npz", beams=np.array([[20, 20, 20], [10, 40, 40]], np.int32), **out)
+    # -ds 2 and -ds 3 (+ a beam): skipped frames re-score the previous frame's codewords (s2_semi_mgau.c:176-186)
+    for i, (ds, beam) in enumerate(((2, ""), (3, "15"))):
+        r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k"), ds=ds, topn_beam=beam)
+        out[f"ds_dense{i}"] = r.score(g["feat"])
+        r.close()
+    save("semi_hub4wsj_beam.npz", beams=np.array([[20, 20, 20], [10, 40, 40]], np.int32),
+         ds_cfg=np.array([[2, 0], [3, 15]], np.int32), **out)
 
 
 def feat_general():

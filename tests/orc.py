@@ -60,6 +60,7 @@ def _load_port():
     L.orc_tied_free.argtypes = [vp]
     L.orc_tied_reset.argtypes = [vp]
     L.orc_tied_set_topn_beam.argtypes = [vp, i32p]
+    L.orc_tied_set_ds.argtypes = [vp, C.c_int]
     L.orc_tied_frame_eval.argtypes = [vp, f32p, u8p, C.c_int, C.c_int, C.c_int, i16p]
     L.orc_tied_eval_all.argtypes = [vp, f32p, C.c_int, i16p]
     L.orc_tied_lists.argtypes = [vp, i32p, i32p]
@@ -214,6 +215,9 @@ class PortTied:
 
     def reset(self):
         port.orc_tied_reset(self.h)
+
+    def set_ds(self, ds):
+        port.orc_tied_set_ds(self.h, int(ds))
 
     def set_topn_beam(self, beam):
         bm = _c(list(beam) + [0] * 8, np.int32)

@@ -171,6 +171,12 @@ def test_oracle_semi_topn_beam_golden():
         pt.set_topn_beam([int(v) for v in beam])
         np.testing.assert_array_equal(pt.eval_all(g["feat"]), gb[f"dense{i}"])
         assert (gb[f"dense{i}"] != g["dense"]).mean() > 0.3   # the beam really changes the scores
+    for i, (ds, beam) in enumerate(gb["ds_cfg"]):
+        pt.reset()
+        pt.set_topn_beam([int(beam)] * 3)
+        pt.set_ds(int(ds))
+        np.testing.assert_array_equal(pt.eval_all(g["feat"]), gb[f"ds_dense{i}"])
+        assert (gb[f"ds_dense{i}"] != g["dense"]).mean() > 0.3
 
 
 @pytest.mark.parametrize("name", ["cont_hub4_topn4.npz", "cont_hub4_topn8.npz"])

@@ -211,6 +211,46 @@ def test_semi_topn_beam_vs_reference_golden_and_port():
             pt.reset()
             np.testing.assert_array_equal(m.score(g["feat"][t:t + 1])[0], pt.frame_eval(g["feat"][t], None, True, 0))
         m.free()
+    # -ds: dense batch, a batch that crosses the internal list chunking, piecewise utterance
+    # serving (blocks that start on a skipped frame continue from the block before) and
+    # frame-by-frame calls all give the reference's scores
+    for i, (ds, beam) in enumerate(gb["ds_cfg"]):
+        ds, beam = int(ds), int(beam)
+        want = gb[f"ds_dense{i}"]
+        m = b.tied_from_model_dir(cases.model_dir(name), n_sen, topn=4, logbase=orc.LOGBASE, topn_beam=[beam] * 3,
+                                  ds_ratio=ds)
+        for path in (0, 1):
+            m.set_path(path)
+            got = m.score(g["feat"])
+            np.testing.assert_array_equal(got[0], want[0])
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert float((diff != 0).mean()) <= 1e-4 and diff.max() <= 2, (ds, beam, path)
+        dense = m.score(g["feat"])
+        T = g["feat"].shape[0]
+        out = np.zeros(n_sen, np.int16)
+        for t0, t1 in ((0, 5), (5, 6), (6, 13), (13, T)):
+            m.utt_begin(g["feat"][t0:t1], frame0=t0)
+            for t in range(t0, t1):
+                m.utt_frame(out, None, 0, t - t0, True)
+                np.testing.assert_array_equal(out, dense[t])
+        for t in range(T):   # ps_mgaufuncs_t.frame_eval, one frame per call
+            streams = [g["feat"][t, 13 * k:13 * k + 13].copy() for k in range(3)]
+            m.frame_eval(out, None, 0, streams, t, True)
+            np.testing.assert_array_equal(out, dense[t])
+        with pytest.raises(b.B200Error):   # a skipped frame whose predecessor was never scored
+            m.utt_begin(g["feat"][3:5], frame0=ds * 5 + 1)
+        m.free()
+        # a long batch (list chunking inside the library) == the port on the same frames
+        pt.reset(); pt.set_topn_beam([beam] * 3); pt.set_ds(ds)
+        long_feat = np.tile(g["feat"], (9, 1))
+        m = b.tied_from_model_dir(cases.model_dir(name), n_sen, topn=4, logbase=orc.LOGBASE, topn_beam=[beam] * 3,
+                                  ds_ratio=ds)
+        got, want = m.score(long_feat), pt.eval_all(long_feat)
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert float((diff != 0).mean()) <= 1e-4 and diff.max() <= 2
+        m.free()
+    pt.set_ds(1)
+    # ms ignores -ds, as ms_mgau.c does (it never reads the option)
     # ptm never reads -topn_beam: the setting must not change its scores
     name = "ptm_hub4wsj.npz"
     if cases.have_model(name):

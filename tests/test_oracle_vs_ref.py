@@ -249,3 +249,22 @@ def test_s2_semi_topn_beam_matches_reference(beam, per_stream):
     pt.set_topn_beam(per_stream)
     np.testing.assert_array_equal(pt.eval_all(feat), want)
     r.close()
+
+
+@pytest.mark.parametrize("ds,beam", [(2, 0), (3, 0), (4, 15), (7, 0)])
+def test_s2_semi_frame_downsampling_matches_reference(ds, beam):
+    """-ds: frames that are not a multiple of ds_ratio stop after eval_topn (s2_semi_mgau.c:176-186)."""
+    hmm = os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k")
+    r = orc.RefAcmod(hmm, ds=ds, topn_beam=str(beam) if beam else "")
+    feat = _real_feats(r, "wsj/440c0201.mfc", 60)
+    want = r.score(feat)
+    from cmusphinx_b200 import engine
+    g, v = engine.read_gauden(hmm + "/means"), engine.read_gauden(hmm + "/variances")
+    pv, pd = orc.port_precompute(v["data"].reshape(-1, 13), 13)
+    sd = engine.read_sendump(hmm + "/sendump", 3, 256, r.n_sen)
+    pt = orc.PortTied(2, 1, 3, [13, 13, 13], 256, r.n_sen, 4, g["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], None)
+    pt.set_topn_beam([beam] * 3)
+    pt.set_ds(ds)
+    np.testing.assert_array_equal(pt.eval_all(feat), want)
+    r.close()

@@ -64,6 +64,21 @@ def test_identical_hypotheses_semi_continuous(tmp_path, passes, inp):
 
 @pytest.mark.gpu
 @needs
+@pytest.mark.parametrize("opts", [["-ds", "2"], ["-topn_beam", "20"], ["-ds", "3", "-topn_beam", "30,20,40"]],
+                         ids=["ds2", "beam20", "ds3+beams"])
+def test_identical_hypotheses_semi_with_ds_and_topn_beam(tmp_path, opts):
+    """The s2_semi fast-evaluation options reach the device back-end through the plug-in:
+    -ds (s2_semi_mgau.c:176-186) and -topn_beam (:189-207); default 3-pass decode, so the
+    second pass re-scores from frame 0 after acmod_rewind."""
+    utts, cepdir, ext, extra = MFC
+    ref, _ = _decode(tmp_path, "ref", utts, cepdir, ext, extra + opts, {})
+    got, log = _decode(tmp_path, "gpu", utts, cepdir, ext, extra + opts, {"LD_PRELOAD": PLUGIN})
+    assert "b200_semi back-end on GPU" in log
+    assert got == ref
+
+
+@pytest.mark.gpu
+@needs
 def test_identical_hypotheses_ptm_and_compallsen(tmp_path):
     utts, cepdir, ext, extra = MFC
     for more in ([], ["-compallsen", "yes"]):
