@@ -399,6 +399,15 @@ b200_transform(ps_mgau_t *mg, ps_mllr_t *mllr)
     b200_ps_mgau_t *s = (b200_ps_mgau_t *)mg;
     gau_t g;
     int rc = -1;
+    if (s->base.vt == &b200_funcs[2] && !getenv("B200_SEMI_MLLR")) {
+        /* The reference's s2_semi back-end transforms s->g (s2_semi_mgau.c:1338-1343) but scores
+         * with the aliases s->means / s->vars / s->dets taken at init (:1267-1269), which
+         * gauden_mllr_transform leaves pointing at the untransformed arrays: -mllr has no
+         * effect on its scores.  Same here, so that results stay identical; B200_SEMI_MLLR=1
+         * applies the transform that was intended. */
+        E_INFO("b200: s2_semi ignores the MLLR transform, as the reference does\n");
+        return 0;
+    }
     if (load_gauden(s->config, s->logbase, &g, mllr) == 0)
         rc = b200_mgau_update_params(s->gpu, g.mean, g.var, g.det);
     if (rc) E_ERROR("b200: transform failed: %s\n", b200_last_error());

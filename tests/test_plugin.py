@@ -127,6 +127,96 @@ def test_identical_hypotheses_fully_continuous(tmp_path, passes):
     assert w_tc == w_cpu and abs(s_tc - s_cpu) <= 40, (s_tc, s_cpu)
 
 
+def _write_mllr(path, veclens, seed):
+    """An MLLR file in the text format ps_mllr_read parses (ps_mllr.c:55-125): one class,
+    A = I + small rotation, a bias and a variance scale per stream."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as fh:
+        fh.write(f"1\n{len(veclens)}\n")
+        for n in veclens:
+            A = np.eye(n) + 0.03 * rng.standard_normal((n, n))
+            fh.write(f"{n}\n")
+            for row in A:
+                fh.write(" ".join(f"{v:.6f}" for v in row) + " \n")
+            fh.write(" ".join(f"{v:.6f}" for v in 0.2 * rng.standard_normal(n)) + " \n")
+            fh.write(" ".join(f"{v:.6f}" for v in 1.0 + 0.1 * rng.random(n)) + " \n")
+
+
+@pytest.mark.gpu
+@needs
+def test_mllr_transform_through_the_vtable(tmp_path):
+    """ps_mgaufuncs_t.transform (acmod_update_mllr, acmod.c:337-346 -> gauden_mllr_transform,
+    ms_gauden.c:551-605): with -mllr the plug-in re-reads, transforms, re-precomputes and
+    re-uploads the Gaussians.  ptm: identical words (and the transform does change the
+    scores); fully continuous on the exact kernels: identical path score."""
+    utts, cepdir, ext, extra = MFC
+    mllr = tmp_path / "ptm.mllr"
+    _write_mllr(mllr, [13, 13, 13], 1)
+    opts = extra + ["-mllr", str(mllr)]
+    plain, _ = _decode(tmp_path, "plain", utts[1:], cepdir, ext, extra, {}, hmm="ptm")
+    ref, _ = _decode(tmp_path, "ref", utts[1:], cepdir, ext, opts, {}, hmm="ptm")
+    got, log = _decode(tmp_path, "gpu", utts[1:], cepdir, ext, opts, {"LD_PRELOAD": PLUGIN}, hmm="ptm")
+    assert "b200_ptm back-end on GPU" in log
+    assert ref != plain                                   # the transform is not a no-op
+    assert [l.rsplit("(", 1)[0] for l in got] == [l.rsplit("(", 1)[0] for l in ref]
+
+    an4 = os.path.join(D, "lm", "an4")
+    if not os.path.exists(os.path.join(an4, "an4.dict")):
+        pytest.skip("an4 LM/dictionary not copied (make -C oracle ref)")
+    mllr = tmp_path / "cont.mllr"
+    _write_mllr(mllr, [39], 2)
+    ctl = tmp_path / "c.ctl"
+    ctl.write_text("pittsburgh.littleendian\n")
+
+    def run(tag, env_extra, more):
+        hyp = tmp_path / f"{tag}.hyp"
+        cmd = [BATCH, "-hmm", os.path.join(D, "hmm", "cont"), "-lm", os.path.join(an4, "an4.ug.lm.DMP"), "-dict",
+               os.path.join(an4, "an4.dict"), "-fdict", os.path.join(an4, "filler.dict"), "-ctl", str(ctl), "-cepdir",
+               os.path.join(D, "test"), "-cepext", ".mfc", "-hyp", str(hyp), "-logfn", str(tmp_path / f"{tag}.log")] + more
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+        env.update(env_extra)
+        subprocess.run(cmd, env=env, check=True, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return hyp.read_text().strip()
+
+    base = run("c0", {}, [])
+    want = run("c1", {}, ["-mllr", str(mllr)])
+    got = run("c2", {"LD_PRELOAD": PLUGIN, "B200_MS_PATH": "0"}, ["-mllr", str(mllr)])
+    assert want != base
+    assert got == want
+
+
+@pytest.mark.gpu
+@needs
+def test_s2_semi_mllr_is_the_references_no_op(tmp_path):
+    """The reference's s2_semi back-end transforms s->g but keeps scoring with the aliases
+    taken at init (s2_semi_mgau.c:1267-1269, 1338-1343): -mllr does not change its scores.
+    The plug-in mirrors that (B200_SEMI_MLLR=1 applies the intended transform instead)."""
+    if not os.path.exists(os.path.join(TIDIGITS, "tidigits.ctl")):
+        pytest.skip("tidigits fixtures not copied (make -C oracle ref)")
+    mllr = os.path.join(D, "test", "wsj", "s1.mllr")      # the bundled 4-stream (12/24/3/12) transform
+
+    def run(tag, env_extra, more):
+        hyp = tmp_path / f"{tag}.hyp"
+        cmd = [BATCH, "-hmm", os.path.join(D, "hmm", "tidigits"), "-lm", os.path.join(D, "lm", "tidigits.DMP"), "-dict",
+               os.path.join(D, "lm", "tidigits.dic"), "-ctl", os.path.join(TIDIGITS, "tidigits.ctl"), "-ctlcount", "8",
+               "-cepdir", TIDIGITS, "-hyp", str(hyp), "-logfn", str(tmp_path / f"{tag}.log")] + more
+        env = dict(os.environ)
+        env["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+        env.update(env_extra)
+        subprocess.run(cmd, env=env, check=True, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return hyp.read_text().strip().splitlines()
+
+    plain = run("p", {}, [])
+    ref = run("r", {}, ["-mllr", mllr])
+    assert ref == plain                                    # the reference's own behaviour
+    got = run("g", {"LD_PRELOAD": PLUGIN}, ["-mllr", mllr])
+    assert got == ref
+    forced = run("f", {"LD_PRELOAD": PLUGIN, "B200_SEMI_MLLR": "1"}, ["-mllr", mllr])
+    assert [l.rsplit(" ", 1)[1] for l in forced] != [l.rsplit(" ", 1)[1] for l in ref]   # scores move when applied
+
+
 @needs
 def test_sen_dump_roundtrip_against_the_reference(tmp_path):
     """CPU-only: the reference writes a senone dump (-senlogdir); our reader
