@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--utts", type=int, default=64)
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--cpu-frames", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=80)
+    ap.add_argument("--single-steps", action="store_true", help="one b200_hmm_step_dev call per frame (no graph)")
     args = ap.parse_args()
     import torch
     import cmusphinx_b200 as b
@@ -49,17 +51,27 @@ def main():
     ctx.set_utts(np.arange(B + 1, dtype=np.int32) * N_HMM)
     n_sets = 8
     sen = torch.from_numpy(synth.senscr_frames(n_sets * B, N_SEN, 99).reshape(n_sets, B, N_SEN)).cuda()
-    stream = torch.cuda.current_stream().cuda_stream
-    for f in range(5):
-        b.lib.b200_hmm_step_dev(ctx._h, sen[f % n_sets].data_ptr(), BEAM, stream)
+    # The frames of a run are issued by b200_hmm_run_dev: replays of one instantiated CUDA graph of
+    # 32 frames (5 kernels each) -- per-frame launch latency is what bounds the single-utterance case.
+    # --single-steps times the same frames as individual b200_hmm_step_dev calls.
+    side = torch.cuda.Stream()          # the legacy default stream cannot be captured
+    stream = side.cuda_stream
+    torch.cuda.synchronize()
+
+    def run(n):
+        if args.single_steps:
+            for f in range(n):
+                b.lib.b200_hmm_step_dev(ctx._h, sen[f % n_sets].data_ptr(), BEAM, stream)
+        else:
+            ctx.run_dev(sen.data_ptr(), B * N_SEN, n_sets, n, BEAM, stream)
+
+    run(args.warmup)                    # warm-up; >= 72 frames builds the graph
     torch.cuda.synchronize()
     l0 = b.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for f in range(args.frames):
-        # scores are re-normalised by nobody here: periodically re-upload to keep them in range
-        b.lib.b200_hmm_step_dev(ctx._h, sen[f % n_sets].data_ptr(), BEAM, stream)
-    e1.record()
+    e0.record(side)
+    run(args.frames)
+    e1.record(side)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.frames
     launches = b.launch_count() - l0
@@ -92,6 +104,7 @@ def main():
         "config": {"workload": f"hmm_vit_eval_3st + beam + compaction + active-senone gather, {B} utterances x {N_HMM} "
                                "HMMs per frame (BASELINE configs[3])", "n_sen": N_SEN, "mpx_fraction": 0.1},
         "gpu_launches": int(launches),
+        "issue": "b200_hmm_step_dev per frame" if args.single_steps else "b200_hmm_run_dev (CUDA-graph replays of 32 frames)",
         "survivor_fraction": float(np.sum(nk)) / units,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "traffic": None},

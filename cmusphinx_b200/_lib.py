@@ -92,6 +92,7 @@ _sig("b200_hmm_pop_upload", C.c_int, vp, C.POINTER(HmmSoa))
 _sig("b200_hmm_pop_download", C.c_int, vp, C.POINTER(HmmSoa))
 _sig("b200_hmm_pop_set_utts", C.c_int, vp, C.c_int, c_i32p)
 _sig("b200_hmm_step_dev", C.c_int, vp, vp, C.c_int32, vp)
+_sig("b200_hmm_run_dev", C.c_int, vp, vp, C.c_long, C.c_int, C.c_int, C.c_int32, vp)
 _sig("b200_hmm_step_results", C.c_int, vp, c_i32p, c_i32p, c_i32p, c_u32p)
 _sig("b200_hmm_step_host", C.c_int, vp, c_i16p, C.c_int32)
 _sig("b200_hmm_last_ms", C.c_float, vp)

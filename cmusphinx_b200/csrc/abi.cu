@@ -635,6 +635,10 @@ struct b200_hmmctx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
+    // b200_hmm_run_dev: one instantiated CUDA graph of `g_frames` steps, valid for this key
+    cudaGraphExec_t g_exec = nullptr;
+    int g_frames = 0;
+    struct GKey { const void *sen, *score; long stride; int cycle, n_hmm, n_utt, max_per_utt; int32_t beam; } g_key{};
 };
 
 namespace {
@@ -745,6 +749,7 @@ void b200_hmm_ctx_free(b200_hmmctx_t *c) {
     pop_free(c);
     cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr); cudaFree(c->d_winner); cudaFree(c->d_enter);
     cudaFree(c->d_block_count); cudaFree(c->d_utt_off); cudaFree(c->d_total);
+    if (c->g_exec) cudaGraphExecDestroy(c->g_exec);
     if (c->st) cudaStreamDestroy(c->st);
     for (int i = 0; i < 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -799,6 +804,63 @@ int b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam, v
                              c->d_mask, c->d_total, 1, st);
     cudaEventRecord(c->ev[1], st);
     return rc;
+}
+
+// A run of frames is launch-latency bound when the population is one utterance
+// (5 small kernels per frame): replay an instantiated CUDA graph of >= 32 frames
+// instead of launching them one by one.
+int b200_hmm_run_dev(b200_hmmctx_t *c, const int16_t *d_senscr, long frame_stride, int n_cycle, int n_frames,
+                     int32_t beam, void *stream) {
+    if (!c || !d_senscr || n_cycle < 1 || n_frames < 0 || frame_stride < 0) { set_error("bad argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->st;
+    auto step = [&](int f) {
+        return hmm_launch_step(c->c, c->p, d_senscr + (size_t)(f % n_cycle) * frame_stride, beam, c->d_fr, c->d_keep,
+                               c->d_block_count, c->d_keep_idx, c->d_mask, c->d_total, 1, st);
+    };
+    const int G = n_cycle * ((32 + n_cycle - 1) / n_cycle);   // frames per graph: whole cycles, >= 32
+    int rc = B200_OK;
+    cudaEventRecord(c->ev[0], st);
+    int f = 0;
+    if (n_frames >= 2 * G + n_cycle && c->p.n_hmm > 0) {
+        const b200_hmmctx::GKey &k = c->g_key;
+        const bool same = c->g_exec && c->g_frames == G && k.sen == d_senscr && k.score == c->p.score &&
+                          k.stride == frame_stride && k.cycle == n_cycle && k.n_hmm == c->p.n_hmm &&
+                          k.n_utt == c->p.n_utt && k.max_per_utt == c->p.max_per_utt && k.beam == beam;
+        if (!same) {
+            if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
+            // one cycle launched directly (this also sets the kernels' attributes on this device) ...
+            for (; f < n_cycle; ++f)
+                if ((rc = step(f))) return rc;
+            // ... then G frames recorded, not executed; captured launches are counted when replayed
+            const long long before = g_launches.load();
+            cudaGraph_t graph = nullptr;
+            B200_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            for (int i = 0; i < G && !rc; ++i) rc = step(i);
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            g_launches.store(before);
+            if (rc || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) { set_error("graph capture failed: %s", cudaGetErrorString(e)); rc = B200_ERR_CUDA; }
+                cudaGetLastError();
+                return rc;
+            }
+            const cudaError_t e2 = cudaGraphInstantiate(&c->g_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) { c->g_exec = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(e2)); return B200_ERR_CUDA; }
+            c->g_key = b200_hmmctx::GKey{d_senscr, c->p.score, frame_stride, n_cycle, c->p.n_hmm, c->p.n_utt, c->p.max_per_utt, beam};
+            c->g_frames = G;
+        }
+        // f is a multiple of n_cycle here, and so is G: the replays stay in phase with the cycle
+        for (; f + G <= n_frames; f += G) {
+            B200_CUDA_OK(cudaGraphLaunch(c->g_exec, st));
+            g_launches.fetch_add(5LL * G, std::memory_order_relaxed);
+        }
+    }
+    for (; f < n_frames; ++f)
+        if ((rc = step(f))) return rc;
+    cudaEventRecord(c->ev[1], st);
+    return B200_OK;
 }
 
 int b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off) {

@@ -480,6 +480,11 @@ class HmmContext:
             check(lib.b200_hmm_step_host(self._h, _p(s, C.c_int16), int(beam)), "hmm_step_host")
         else:
             check(lib.b200_hmm_step_dev(self._h, senscr, int(beam), None), "hmm_step_dev")
+        return self.step_results(n_hmm, want_idx)
+
+    def step_results(self, n_hmm: int, want_idx=True):
+        """(best, survivors, mask) of the last step / the last frame of run_dev."""
+        nu = getattr(self, "n_utt", 1)
         best, nk = np.zeros(nu, np.int32), np.zeros(nu, np.int32)
         idx = np.zeros(n_hmm, np.int32) if want_idx else None
         mask = np.zeros((nu, (self.n_sen + 31) // 32), np.uint32)
@@ -515,6 +520,12 @@ class HmmContext:
         """Batched hmm_enter with the callers' `only if better` test, list-order semantics."""
         i, s, h = _c(idx, np.int32), _c(score, np.int32), _c(hist, np.int32)
         check(lib.b200_hmm_enter_host(self._h, _p(i, C.c_int32), _p(s, C.c_int32), _p(h, C.c_int32), i.size), "hmm_enter")
+
+    def run_dev(self, d_senscr: int, frame_stride: int, n_cycle: int, n_frames: int, beam: int, stream=None):
+        """n_frames steps on device-resident senone scores (frame f at d_senscr + (f % n_cycle) * frame_stride
+        int16 elements); long runs replay a CUDA graph.  Read the last frame with step_results()."""
+        check(lib.b200_hmm_run_dev(self._h, d_senscr, int(frame_stride), int(n_cycle), int(n_frames), int(beam), stream),
+              "hmm_run_dev")
 
     def step_dev_async(self, d_senscr: int, beam: int):
         check(lib.b200_hmm_step_dev(self._h, d_senscr, int(beam), None), "hmm_step_dev")

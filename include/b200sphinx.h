@@ -308,6 +308,14 @@ int  b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off);
  * survivors (acmod_activate_hmm) -> mask[(n_sen+31)/32].
  * d_senscr: device int16[n_sen].  Results stay on the device; fetch with
  * b200_hmm_step_results. */
+/* n_frames consecutive b200_hmm_step_dev calls; frame f reads the senone scores at
+ * d_senscr + (f % n_cycle) * frame_stride (int16 elements).  Same results as the
+ * single steps; long runs are issued as replays of one instantiated CUDA graph of
+ * >= 32 frames (a single-utterance population is launch-latency bound: 5 small
+ * kernels per frame).  The results of the LAST frame are read with
+ * b200_hmm_step_results. */
+int  b200_hmm_run_dev(b200_hmmctx_t *c, const int16_t *d_senscr, long frame_stride,
+                      int n_cycle, int n_frames, int32_t beam, void *stream);
 int  b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam,
                        void *stream);
 int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best /* [n_utt] */, int32_t *n_keep /* [n_utt] */,

@@ -221,3 +221,41 @@ def test_hmm_maintenance_ops_match_sequential_reference():
     np.testing.assert_array_equal(fin.score[0], s0); np.testing.assert_array_equal(fin.history[0], h0)
     np.testing.assert_array_equal(fin.score[1:], got.score[1:]); np.testing.assert_array_equal(fin.history[1:], got.history[1:])
     ctx.free()
+
+
+@pytest.mark.parametrize("n_utt", [1, 3])
+def test_run_of_frames_as_graph_replays_equals_single_steps(n_utt):
+    """b200_hmm_run_dev (a CUDA graph of >= 32 frames replayed, plus directly launched head and
+    tail frames) leaves exactly the population and the last-frame results of the same number of
+    b200_hmm_step_dev calls; a second run reuses the instantiated graph."""
+    ne, n_sen, n_tmat, n_sseq, n, cyc, beam = 3, 800, 10, 2000, 4000, 8, -60000
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n, ne, n_sen, n_tmat, n_sseq, seed=21, mpx_fraction=0.15)
+    off = np.linspace(0, n, n_utt + 1).astype(np.int32)
+    sen = np.ascontiguousarray(synth.senscr_frames(cyc * n_utt, n_sen, 31).reshape(cyc, n_utt, n_sen))
+    d_sen = b.lib.b200_dev_alloc(sen.nbytes, 0)
+    assert d_sen
+    b.engine.check(b.lib.b200_dev_upload(d_sen, sen.ctypes.data, sen.nbytes), "upload")
+    stride = n_utt * n_sen
+    ctxs = []
+    for _ in range(2):
+        c = b.HmmContext(ne, tp, d["sseq"], n_sen)
+        c.upload(_to_pop(d, ne))
+        c.set_utts(off)
+        ctxs.append(c)
+    a, g = ctxs
+    done = 0
+    for n_frames in (100, 75, 3):           # graph built, graph reused (with a tail), too short for a graph
+        for f in range(n_frames):
+            a.step_dev_async(d_sen + ((f % cyc) * stride) * 2, beam)
+        g.run_dev(d_sen, stride, cyc, n_frames, beam)
+        ra, rg = a.step_results(n), g.step_results(n)
+        for x, y in zip(ra, rg):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+        pa, pg = b.HmmPopulation(n, ne), b.HmmPopulation(n, ne)
+        a.download(pa); g.download(pg)
+        for k in ("score", "history", "out_score", "out_history", "bestscore", "senid"):
+            np.testing.assert_array_equal(getattr(pa, k), getattr(pg, k), err_msg=k)
+        done += n_frames
+    a.free(); g.free()
+    b.lib.b200_dev_free(d_sen)
