@@ -236,7 +236,7 @@ __device__ __forceinline__ void eval5_mpx(HmmRegs &h, const uint8_t *tp, const i
 constexpr int kHmmBlock = 256;
 
 template <int NE>
-__global__ void __launch_bounds__(kHmmBlock)
+__global__ void __launch_bounds__(kHmmBlock, NE == 3 ? 6 : 4)
 hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr_all, HmmFrame *fr) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
@@ -304,100 +304,141 @@ __global__ void hmm_frame_init_kernel(HmmFrame *fr, int n_utt, uint32_t *mask, i
     for (int i = i0; i < n_utt; i += stride) { fr[i].best = kWorstScore; fr[i].n_keep = 0; }
 }
 
-// Pass 1 of the order-preserving compaction: keep flag + per-block count.
+// Pass 1 of the order-preserving compaction: keep flag + per-tile count.  A
+// tile is kTileIters * kHmmBlock consecutive HMMs of one utterance (few, fat
+// CTAs: the scan below and the mask merge of pass 3 scale with the tile count).
+// kTileIters = 8 for big populations, 1 when that would leave most SMs idle.
+template <int kTileIters>
 __global__ void __launch_bounds__(kHmmBlock)
 hmm_beam_flag_kernel(HmmPop p, const HmmFrame *fr, int32_t beam, uint8_t *keep, int32_t *block_count) {
-    const int u = blockIdx.y;
-    const int i = p.utt_off[u] + blockIdx.x * kHmmBlock + threadIdx.x;
+    __shared__ int32_t s_cnt[kHmmBlock / 32];
+    constexpr int kTile = kTileIters * kHmmBlock;
+    const int u = blockIdx.y, tid = threadIdx.x;
+    const int hi = p.utt_off[u + 1];
+    const int base = p.utt_off[u] + blockIdx.x * kTile + tid;
     const int32_t thresh = fr[u].best + beam;
-    bool k = false;
-    if (i < p.utt_off[u + 1]) {
-        k = BT(p.bestscore[i], thresh);
-        keep[i] = k ? 1 : 0;
+    int32_t bs[kTileIters];
+#pragma unroll
+    for (int j = 0; j < kTileIters; ++j) {
+        const int i = base + j * kHmmBlock;
+        bs[j] = i < hi ? p.bestscore[i] : (int32_t)0x80000000;
     }
-    const int cnt = __syncthreads_count(k);
-    if (threadIdx.x == 0) block_count[u * gridDim.x + blockIdx.x] = cnt;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kTileIters; ++j) {
+        const int i = base + j * kHmmBlock;
+        const bool k = i < hi && BT(bs[j], thresh);
+        if (i < hi) keep[i] = k ? 1 : 0;
+        cnt += k ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kHmmBlock / 32; ++w) t += s_cnt[w];
+        block_count[u * gridDim.x + blockIdx.x] = t;
+    }
 }
 
-// Pass 2: exclusive scan of the block counts by one block; per-utterance
-// survivor counts land in fr[u].n_keep, the total in *total.
+// Pass 2: exclusive scan of the block counts by one block (every thread owns a
+// contiguous run of counts: one pass, three barriers); per-utterance survivor
+// counts land in fr[u].n_keep, the total in *total.
 __global__ void __launch_bounds__(1024)
 hmm_scan_kernel(int32_t *block_count, int n_blocks, int blocks_per_utt, HmmFrame *fr, int n_utt, int32_t *total) {
     __shared__ int32_t s_warp[32];
-    __shared__ int32_t s_carry;
+    __shared__ int32_t s_total;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    const int per = (n_blocks + 1023) / 1024;
+    const int b0 = min(n_blocks, tid * per), b1 = min(n_blocks, b0 + per);
+    int32_t sum = 0;
+    for (int i = b0; i < b1; ++i) sum += block_count[i];
+    int32_t x = sum;
+    for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
     __syncthreads();
-    for (int base = 0; base < n_blocks; base += 1024) {
-        const int i = base + tid;
-        int32_t v = i < n_blocks ? block_count[i] : 0;
-        int32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int32_t ws = s_warp[lane];
-            for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
-            s_warp[lane] = ws;
-        }
-        __syncthreads();
-        const int32_t incl = x + (w ? s_warp[w - 1] : 0) + s_carry;
-        if (i < n_blocks) block_count[i] = incl - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = incl;
-        __syncthreads();
+    if (w == 0) {
+        int32_t ws = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
+        s_warp[lane] = ws;
     }
-    if (tid == 0) *total = s_carry;
+    __syncthreads();
+    const int32_t incl = x + (w ? s_warp[w - 1] : 0);
+    int32_t run = incl - sum;
+    for (int i = b0; i < b1; ++i) { const int32_t v = block_count[i]; block_count[i] = run; run += v; }
+    if (tid == 1023) { s_total = incl; *total = incl; }
     __syncthreads();
     for (int u = tid; u < n_utt; u += 1024) {
         const int32_t b = block_count[u * blocks_per_utt];
-        const int32_t e = (u + 1 < n_utt) ? block_count[(u + 1) * blocks_per_utt] : s_carry;
+        const int32_t e = (u + 1 < n_utt) ? block_count[(u + 1) * blocks_per_utt] : s_total;
         fr[u].n_keep = e - b;
     }
 }
 
 // Pass 3: scatter survivors (order preserved) and OR their senones into the
-// utterance's active mask (acmod_activate_hmm).
-template <int NE>
+// utterance's active mask (acmod_activate_hmm).  One tile per CTA: the mask is
+// accumulated in shared memory and merged into the utterance's mask once.
+template <int NE, int kTileIters>
 __global__ void __launch_bounds__(kHmmBlock)
 hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block_off,
                    int32_t *keep_idx, uint32_t *mask_all) {
-    extern __shared__ uint32_t s_mask[];
-    __shared__ int32_t s_wsum[kHmmBlock / 32];
+    // one flag BYTE per senone, set with plain stores (every writer stores the same 1, so no
+    // atomics and no serialisation of the many survivors that share a mask word), packed
+    // into words by ballots at the end
+    extern __shared__ uint32_t s_flag_w[];
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
+    constexpr int kTile = kTileIters * kHmmBlock;
+    __shared__ int32_t s_wsum[2][kHmmBlock / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int u = blockIdx.y;
     const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-    if (lo + (int)blockIdx.x * kHmmBlock >= hi) return;
+    if (lo + (int)blockIdx.x * kTile >= hi) return;
     const int n_words = (c.n_sen + 31) / 32;
     uint32_t *mask = mask_all + (size_t)u * n_words;
-    for (int k = tid; k < n_words; k += kHmmBlock) s_mask[k] = 0u;
-    __syncthreads();
-    const int i = lo + blockIdx.x * kHmmBlock + tid;
-    const bool k = (i < hi) && keep[i];
-    const unsigned bal = __ballot_sync(0xffffffffu, k);
-    if (lane == 0) s_wsum[w] = __popc(bal);
-    if (k) {
-        const int n = p.n_hmm;
-        const bool mpx = p.mpx[i] != 0;
+    for (int k = tid; k < n_words * 8; k += kHmmBlock) s_flag_w[k] = 0u;
+    int off = block_off[u * gridDim.x + blockIdx.x];
+    const int n = p.n_hmm;
+    uint8_t kp[kTileIters];
 #pragma unroll
-        for (int s = 0; s < NE; ++s) {
-            uint32_t id = p.senid[(size_t)s * n + i];
-            if (mpx) {
-                if (id == B200_BAD_SSID) continue;
-                id = c.sseq[(size_t)id * NE + s];
-            }
-            atomicOr(&s_mask[id >> 5], 1u << (id & 31));
-        }
+    for (int j = 0; j < kTileIters; ++j) {
+        const int i = lo + blockIdx.x * kTile + j * kHmmBlock + tid;
+        kp[j] = i < hi ? keep[i] : 0;
     }
     __syncthreads();
-    if (k) {
-        int off = block_off[u * gridDim.x + blockIdx.x];
-        for (int ww = 0; ww < w; ++ww) off += s_wsum[ww];
-        off += __popc(bal & ((1u << lane) - 1u));
-        keep_idx[off] = i;
+#pragma unroll
+    for (int j = 0; j < kTileIters; ++j) {
+        const int i = lo + blockIdx.x * kTile + j * kHmmBlock + tid;
+        const bool k = kp[j] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_wsum[j & 1][w] = __popc(bal);
+        if (k) {
+            const bool mpx = p.mpx[i] != 0;
+#pragma unroll
+            for (int s = 0; s < NE; ++s) {
+                uint32_t id = p.senid[(size_t)s * n + i];
+                if (mpx) {
+                    if (id == B200_BAD_SSID) continue;
+                    id = c.sseq[(size_t)id * NE + s];
+                }
+                s_flag[id] = 1;
+            }
+        }
+        __syncthreads();      // s_wsum[j & 1] complete (and not rewritten before iteration j + 2's barrier)
+        int before = 0, all = 0;
+#pragma unroll
+        for (int ww = 0; ww < kHmmBlock / 32; ++ww) {
+            const int v = s_wsum[j & 1][ww];
+            all += v;
+            if (ww < w) before += v;
+        }
+        if (k) keep_idx[off + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        off += all;
     }
-    for (int kk = tid; kk < n_words; kk += kHmmBlock)
-        if (s_mask[kk]) atomicOr(&mask[kk], s_mask[kk]);
+    __syncthreads();
+    for (int kk = w; kk < n_words; kk += kHmmBlock / 32) {      // warp-uniform loop
+        const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
+        if (lane == 0 && word) atomicOr(&mask[kk], word);
+    }
 }
 
 // ------------------------------------------------------------ host launchers
@@ -421,21 +462,51 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
         B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    // a few CTAs per SM in total; each strides its utterance's range
-    int gx = std::max(1, std::min(bpu, (148 * 8 + p.n_utt - 1) / p.n_utt));
+    // exactly one resident wave of CTAs (occupancy x SM count), split evenly over the
+    // utterances; each CTA strides its utterance's range
+    static size_t occ_sh[2] = {0, 0};
+    static int occ_wave[2] = {0, 0};          // CTAs in one resident wave, per kernel flavour
+    const int fl = c.n_emit == 3 ? 0 : 1;
+    if (occ_sh[fl] != sh || occ_wave[fl] == 0) {
+        int per_sm = 0, n_sm = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (fl == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<3>, kHmmBlock, sh);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<5>, kHmmBlock, sh);
+        occ_wave[fl] = std::max(1, per_sm) * n_sm;
+        occ_sh[fl] = sh;
+    }
+    int gx = std::max(1, std::min(bpu, occ_wave[fl] / p.n_utt));
     dim3 grid(gx, p.n_utt);
     if (c.n_emit == 3) hmm_step_kernel<3><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
     else hmm_step_kernel<5><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
     B200_LAUNCH_CHECK();
     if (!do_beam) return B200_OK;
-    dim3 g2(bpu, p.n_utt);
-    hmm_beam_flag_kernel<<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
+    // fat tiles (8 x 256 HMMs per CTA) when that still fills the machine twice over, else one HMM per thread
+    const bool fat = (long long)((p.max_per_utt + 8 * kHmmBlock - 1) / (8 * kHmmBlock)) * p.n_utt >= 2 * 148;
+    const int tile = (fat ? 8 : 1) * kHmmBlock;
+    const int tpu = (p.max_per_utt + tile - 1) / tile;            // tiles per utterance (<= bpu)
+    dim3 g2(tpu, p.n_utt);
+    if (fat) hmm_beam_flag_kernel<8><<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
+    else hmm_beam_flag_kernel<1><<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
     B200_LAUNCH_CHECK();
-    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, bpu * p.n_utt, bpu, fr, p.n_utt, total);
+    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, tpu * p.n_utt, tpu, fr, p.n_utt, total);
     B200_LAUNCH_CHECK();
-    const size_t msh = (size_t)n_words * 4;
-    if (c.n_emit == 3) hmm_scatter_kernel<3><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-    else hmm_scatter_kernel<5><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    const size_t msh = (size_t)n_words * 32;     // one flag byte per senone (<= 64 KB)
+    static AttrOnce attr2;
+    if (attr2.need()) {
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+    }
+    if (c.n_emit == 3) {
+        if (fat) hmm_scatter_kernel<3, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+        else hmm_scatter_kernel<3, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    } else {
+        if (fat) hmm_scatter_kernel<5, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+        else hmm_scatter_kernel<5, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
+    }
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
