@@ -388,7 +388,9 @@ hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block
     extern __shared__ uint32_t s_flag_w[];
     uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
     constexpr int kTile = kTileIters * kHmmBlock;
-    __shared__ int32_t s_wsum[2][kHmmBlock / 32];
+    constexpr int kWarps = kHmmBlock / 32, kCnt = kTileIters * kWarps;   // (row, warp) survivor counts
+    static_assert(kCnt <= 64, "offset scan handles two entries per lane");
+    __shared__ int32_t s_off[64];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int u = blockIdx.y;
     const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
@@ -396,46 +398,54 @@ hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block
     const int n_words = (c.n_sen + 31) / 32;
     uint32_t *mask = mask_all + (size_t)u * n_words;
     for (int k = tid; k < n_words * 8; k += kHmmBlock) s_flag_w[k] = 0u;
-    int off = block_off[u * gridDim.x + blockIdx.x];
+    const int off = block_off[u * gridDim.x + blockIdx.x];
     const int n = p.n_hmm;
+    const int base = lo + blockIdx.x * kTile + tid;
+    // all keep flags of the tile first, then ONE exclusive scan over the (row, warp)
+    // counts: the rows below need no barrier between them and their loads overlap
     uint8_t kp[kTileIters];
+    unsigned bal[kTileIters];
 #pragma unroll
     for (int j = 0; j < kTileIters; ++j) {
-        const int i = lo + blockIdx.x * kTile + j * kHmmBlock + tid;
+        const int i = base + j * kHmmBlock;
         kp[j] = i < hi ? keep[i] : 0;
     }
+#pragma unroll
+    for (int j = 0; j < kTileIters; ++j) {
+        bal[j] = __ballot_sync(0xffffffffu, kp[j] != 0);
+        if (lane == 0) s_off[j * kWarps + w] = __popc(bal[j]);
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int32_t v0 = lane < kCnt ? s_off[lane] : 0, v1 = lane + 32 < kCnt ? s_off[lane + 32] : 0;
+        int32_t x0 = v0, x1 = v1;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+            if (lane >= o) { x0 += y0; x1 += y1; }
+        }
+        const int32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
+        if (lane < kCnt) s_off[lane] = x0 - v0;
+        if (lane + 32 < kCnt) s_off[lane + 32] = tot0 + x1 - v1;
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kTileIters; ++j) {
-        const int i = lo + blockIdx.x * kTile + j * kHmmBlock + tid;
-        const bool k = kp[j] != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, k);
-        if (lane == 0) s_wsum[j & 1][w] = __popc(bal);
-        if (k) {
-            const bool mpx = p.mpx[i] != 0;
+        if (!kp[j]) continue;
+        const int i = base + j * kHmmBlock;
+        keep_idx[off + s_off[j * kWarps + w] + __popc(bal[j] & ((1u << lane) - 1u))] = i;
+        const bool mpx = p.mpx[i] != 0;
 #pragma unroll
-            for (int s = 0; s < NE; ++s) {
-                uint32_t id = p.senid[(size_t)s * n + i];
-                if (mpx) {
-                    if (id == B200_BAD_SSID) continue;
-                    id = c.sseq[(size_t)id * NE + s];
-                }
-                s_flag[id] = 1;
+        for (int s = 0; s < NE; ++s) {
+            uint32_t id = p.senid[(size_t)s * n + i];
+            if (mpx) {
+                if (id == B200_BAD_SSID) continue;
+                id = c.sseq[(size_t)id * NE + s];
             }
+            s_flag[id] = 1;
         }
-        __syncthreads();      // s_wsum[j & 1] complete (and not rewritten before iteration j + 2's barrier)
-        int before = 0, all = 0;
-#pragma unroll
-        for (int ww = 0; ww < kHmmBlock / 32; ++ww) {
-            const int v = s_wsum[j & 1][ww];
-            all += v;
-            if (ww < w) before += v;
-        }
-        if (k) keep_idx[off + before + __popc(bal & ((1u << lane) - 1u))] = i;
-        off += all;
     }
     __syncthreads();
-    for (int kk = w; kk < n_words; kk += kHmmBlock / 32) {      // warp-uniform loop
+    for (int kk = w; kk < n_words; kk += kWarps) {      // warp-uniform loop
         const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
         if (lane == 0 && word) atomicOr(&mask[kk], word);
     }
