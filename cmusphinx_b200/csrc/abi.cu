@@ -722,7 +722,7 @@ extern "C" {
 
 b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat, const uint16_t *sseq, int n_sseq,
                                    int n_sen, int device) {
-    if (n_emit != 3 && n_emit != 5) { set_error("n_emit_state %d unsupported (3 or 5; hmm_vit_eval_anytopo is host-only)", n_emit); return nullptr; }
+    if (n_emit < 1 || n_emit > 5) { set_error("n_emit_state %d unsupported (1..5 = HMM_MAX_NSTATE, PS/hmm.h:90)", n_emit); return nullptr; }
     if (!tp || n_tmat <= 0 || n_sen <= 0 || n_sen > 65535 || (n_sseq > 0 && !sseq)) { set_error("bad hmm context arguments"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libb200sphinx has no CPU fallback"); return nullptr; }

@@ -235,6 +235,53 @@ __device__ __forceinline__ void eval5_mpx(HmmRegs &h, const uint8_t *tp, const i
 // (utterance, HMM index).  n_utt == 1 is the reference's per-decoder case.
 constexpr int kHmmBlock = 256;
 
+// hmm_vit_eval_anytopo (hmm.c:711-786): what hmm_vit_eval dispatches to when
+// n_emit_state is neither 3 nor 5 (1, 2 or 4 -- HMM_MAX_NSTATE is 5).  Generic
+// upper-triangular topology: every transition that is not "zero" competes, ties
+// keep the earlier candidate (self loop, then from = to-1, to-2, ...).  As in the
+// reference, state 0's sum is not clamped, new scores are stored unclamped, and
+// a missing senone scores WORST_SCORE (hmm_senscr, hmm.h:198-200).
+template <int NE>
+__device__ __forceinline__ void eval_any(HmmRegs &h, const uint8_t *tp, const int16_t *sen, const uint16_t *sseq,
+                                         bool mpx) {
+    int32_t st[NE];
+#pragma unroll
+    for (int s = 0; s < NE; ++s) {
+        uint32_t id = h.sid[s];
+        if (mpx && id != B200_BAD_SSID) id = sseq[(size_t)id * NE + s];
+        const int32_t ss = id == 0xffffu ? kWorstScore : -(int32_t)sen[id];
+        int32_t v = h.sc[s] + ss;
+        if (s > 0 && WT(v, kWorstScore)) v = kWorstScore;
+        st[s] = v;
+    }
+    int32_t scr = kWorstScore, bh = 0;
+    uint16_t bsid = 0;
+    bool found = false;
+#pragma unroll
+    for (int f = NE - 1; f >= 0; --f) {
+        const int32_t t = tpv<NE>(tp, f, NE);
+        if (BT(t, B200_TMAT_WORST) && BT(st[f] + t, scr)) { scr = st[f] + t; bh = h.hi[f]; found = true; }
+    }
+    h.out_sc = scr;
+    if (found) h.out_hi = bh;
+    int32_t best = scr;
+#pragma unroll
+    for (int to = NE - 1; to >= 0; --to) {
+        const int32_t tt = tpv<NE>(tp, to, to);
+        scr = BT(tt, B200_TMAT_WORST) ? st[to] + tt : kWorstScore;
+        found = false;
+#pragma unroll
+        for (int f = to - 1; f >= 0; --f) {
+            const int32_t t = tpv<NE>(tp, f, to);
+            if (BT(t, B200_TMAT_WORST) && BT(st[f] + t, scr)) { scr = st[f] + t; bh = h.hi[f]; bsid = h.sid[f]; found = true; }
+        }
+        h.sc[to] = scr;
+        if (found) { h.hi[to] = bh; if (mpx) h.sid[to] = bsid; }
+        if (WT(best, scr)) best = scr;
+    }
+    h.best = best;
+}
+
 template <int NE>
 __global__ void __launch_bounds__(kHmmBlock, NE == 3 ? 6 : 4)
 hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr_all, HmmFrame *fr) {
@@ -272,7 +319,8 @@ hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr_all, HmmF
         const uint8_t *tp = s_tp + (int)p.tmatid[i] * NE * (NE + 1);
         const bool mpx = p.mpx[i] != 0;
         if (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
-        else { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
+        else if (NE == 5) { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
+        else eval_any<NE>(h, tp, s_sen, c.sseq, mpx);
 #pragma unroll
         for (int s = 0; s < NE; ++s) {
             p.score[(size_t)s * n + i] = h.sc[s];
@@ -468,28 +516,44 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
     const size_t sh = step_smem(c);
     if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
     static AttrOnce attr;
+    if (c.n_emit < 1 || c.n_emit > 5) { set_error("n_emit_state %d outside 1..5 (HMM_MAX_NSTATE)", c.n_emit); return B200_ERR_UNSUP; }
+#define B200_HMM_NE(...)                                   \
+    switch (c.n_emit) {                                    \
+    case 1: { constexpr int NE = 1; __VA_ARGS__; } break;  \
+    case 2: { constexpr int NE = 2; __VA_ARGS__; } break;  \
+    case 3: { constexpr int NE = 3; __VA_ARGS__; } break;  \
+    case 4: { constexpr int NE = 4; __VA_ARGS__; } break;  \
+    default: { constexpr int NE = 5; __VA_ARGS__; } break; \
+    }
     if (attr.need()) {
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int ne = 1; ne <= 5; ++ne) {
+            cudaError_t e = cudaSuccess;
+            switch (ne) {
+            case 1: e = cudaFuncSetAttribute(hmm_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+            case 2: e = cudaFuncSetAttribute(hmm_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+            case 3: e = cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+            case 4: e = cudaFuncSetAttribute(hmm_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+            default: e = cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
+            }
+            B200_CUDA_OK(e);
+        }
     }
     // exactly one resident wave of CTAs (occupancy x SM count), split evenly over the
     // utterances; each CTA strides its utterance's range
-    static size_t occ_sh[2] = {0, 0};
-    static int occ_wave[2] = {0, 0};          // CTAs in one resident wave, per kernel flavour
-    const int fl = c.n_emit == 3 ? 0 : 1;
+    static size_t occ_sh[6] = {0, 0, 0, 0, 0, 0};
+    static int occ_wave[6] = {0, 0, 0, 0, 0, 0};   // CTAs in one resident wave, per kernel flavour
+    const int fl = c.n_emit;
     if (occ_sh[fl] != sh || occ_wave[fl] == 0) {
         int per_sm = 0, n_sm = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (fl == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<3>, kHmmBlock, sh);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<5>, kHmmBlock, sh);
+        B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<NE>, kHmmBlock, sh));
         occ_wave[fl] = std::max(1, per_sm) * n_sm;
         occ_sh[fl] = sh;
     }
     int gx = std::max(1, std::min(bpu, occ_wave[fl] / p.n_utt));
     dim3 grid(gx, p.n_utt);
-    if (c.n_emit == 3) hmm_step_kernel<3><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
-    else hmm_step_kernel<5><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr);
+    B200_HMM_NE(hmm_step_kernel<NE><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr));
     B200_LAUNCH_CHECK();
     if (!do_beam) return B200_OK;
     // fat tiles (8 x 256 HMMs per CTA) when that still fills the machine twice over, else one HMM per thread
@@ -503,20 +567,15 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
     hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, tpu * p.n_utt, tpu, fr, p.n_utt, total);
     B200_LAUNCH_CHECK();
     const size_t msh = (size_t)n_words * 32;     // one flag byte per senone (<= 64 KB)
-    static AttrOnce attr2;
-    if (attr2.need()) {
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(hmm_scatter_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+    if (msh > 48 * 1024) {   // more than 12 288 senones: the flag bytes need the opt-in shared-memory size
+        cudaError_t e = cudaSuccess;
+        B200_HMM_NE(e = fat ? cudaFuncSetAttribute(hmm_scatter_kernel<NE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024)
+                            : cudaFuncSetAttribute(hmm_scatter_kernel<NE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
+        B200_CUDA_OK(e);
     }
-    if (c.n_emit == 3) {
-        if (fat) hmm_scatter_kernel<3, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-        else hmm_scatter_kernel<3, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-    } else {
-        if (fat) hmm_scatter_kernel<5, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-        else hmm_scatter_kernel<5, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask);
-    }
+    if (fat) { B200_HMM_NE(hmm_scatter_kernel<NE, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask)); }
+    else { B200_HMM_NE(hmm_scatter_kernel<NE, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask)); }
+#undef B200_HMM_NE
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

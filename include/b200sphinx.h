@@ -316,6 +316,8 @@ int  b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off);
  * b200_hmm_step_results. */
 int  b200_hmm_run_dev(b200_hmmctx_t *c, const int16_t *d_senscr, long frame_stride,
                       int n_cycle, int n_frames, int32_t beam, void *stream);
+/* (n_emit_state may be 1..5 = HMM_MAX_NSTATE: 3 and 5 run the reference's unrolled
+ * specialisations, 1, 2 and 4 hmm_vit_eval_anytopo, PS/hmm.c:711-786.) */
 int  b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam,
                        void *stream);
 int  b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best /* [n_utt] */, int32_t *n_keep /* [n_utt] */,

@@ -751,6 +751,34 @@ hmm_eval_one(int ne, const uint8_t *tp, const uint16_t *sseq, const int16_t *sen
 #define TP(i, j) (-(int32_t)tp[(i) * nc + (j)])
 #define SEN(st) (mpx ? senscr[sseq[(long)sid[st] * ne + (st)]] : senscr[sid[st]])
 
+    if (ne != 3 && ne != 5) {   /* hmm_vit_eval_anytopo, hmm.c:711-786 (n_emit_state 1, 2 or 4) */
+        int to, from, bestfrom;
+        int32_t newscr, scr;
+        for (st = 0; st < ne; ++st) {
+            /* hmm_senscr (hmm.h:198-200): WORST_SCORE for a missing senone */
+            int32_t ss;
+            if (mpx) ss = (sid[st] == ORC_BAD_SSID || sseq[(long)sid[st] * ne + st] == 0xffff) ? W : -(int32_t)SEN(st);
+            else ss = sid[st] == 0xffff ? W : -(int32_t)SEN(st);
+            s[st] = sc[st] + ss;
+            if (st > 0 && s[st] < W) s[st] = W;      /* state 0 is not clamped (:720) */
+        }
+        scr = W; bestfrom = -1;
+        for (from = ne - 1; from >= 0; --from)
+            if (TP(from, ne) > ORC_TMAT_WORST && (newscr = s[from] + TP(from, ne)) > scr) { scr = newscr; bestfrom = from; }
+        *out_sc = scr;
+        if (bestfrom >= 0) *out_hi = hi[bestfrom];
+        best = scr;
+        for (to = ne - 1; to >= 0; --to) {
+            scr = TP(to, to) > ORC_TMAT_WORST ? s[to] + TP(to, to) : W;
+            bestfrom = -1;
+            for (from = to - 1; from >= 0; --from)
+                if (TP(from, to) > ORC_TMAT_WORST && (newscr = s[from] + TP(from, to)) > scr) { scr = newscr; bestfrom = from; }
+            sc[to] = scr;                              /* stored unclamped (:766-774) */
+            if (bestfrom >= 0) { hi[to] = hi[bestfrom]; if (mpx) sid[to] = sid[bestfrom]; }
+            if (best < scr) best = scr;
+        }
+        return best;
+    }
     if (ne == 3 && !mpx) {   /* hmm.c:531-609 */
         s[2] = sc[2] - SEN(2); s[1] = sc[1] - SEN(1); s[0] = sc[0] - SEN(0);
         best = W;
@@ -869,7 +897,7 @@ orc_hmm_eval_batch(int n_emit, int n_hmm, const uint8_t *tp, int n_tmat, const u
     int32_t best = W;
     int i, r;
     (void)n_tmat; (void)n_sseq; (void)ssid;
-    if (n_emit != 3 && n_emit != 5)
+    if (n_emit < 1 || n_emit > 5)   /* HMM_MAX_NSTATE = 5 (hmm.h:90) */
         return W;
     for (r = 0; r < (n_frames_repeat > 0 ? n_frames_repeat : 1); ++r) {
         best = W;

@@ -116,6 +116,31 @@ def tmat_hmm():
     save("tmat_hmm.npz", **keep)
 
 
+def hmm_anytopo():
+    """hmm_vit_eval for n_emit_state 1, 2 and 4, i.e. hmm_vit_eval_anytopo (hmm.c:711-786), run by
+    the reference on synthetic populations (30 % multiplex HMMs, some with BAD_SSID states)."""
+    keep = {}
+    for ne in (1, 2, 4):
+        n_sen, n_tmat, n_sseq, n_hmm, nfr = 400, 13, 200, 1500, 4
+        tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 3))
+        pop = synth.hmm_population(n_hmm, ne, n_sen, n_tmat, n_sseq, seed=ne, mpx_fraction=0.3)
+        sen = synth.senscr_frames(nfr, n_sen, ne + 10)
+        a = {k: v.copy() for k, v in pop.items()}
+        bests = []
+        for f in range(nfr):
+            bests.append(orc.hmm_eval(R.ref_hmm_eval_batch, ne, tp, pop["sseq"], sen[f], a["score"], a["history"],
+                                      a["out_score"], a["out_history"], a["senid"], a["tmatid"], a["mpx"],
+                                      a["bestscore"]))
+        for k, v in pop.items():
+            keep[f"h{ne}_in_{k}"] = v
+        for k in ("score", "history", "out_score", "out_history", "senid", "bestscore"):
+            keep[f"h{ne}_out_{k}"] = a[k]
+        keep[f"h{ne}_tp"] = tp
+        keep[f"h{ne}_senscr"] = sen
+        keep[f"h{ne}_best"] = np.array(bests, np.int32)
+    save("hmm_anytopo.npz", **keep)
+
+
 def real_model(name, hmmdir, mfc, n_frames, senmgau="", topn=4):
     r = orc.RefAcmod(os.path.join(orc.DATA_DIR, "hmm", hmmdir), senmgau, topn)
     cep = orc.read_mfc(os.path.join(orc.DATA_DIR, "test", mfc))

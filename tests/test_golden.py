@@ -124,9 +124,9 @@ def test_oracle_ms_golden(name):
         np.testing.assert_array_equal(out, g["act_scores"][i])
 
 
-@pytest.mark.parametrize("ne", [3, 5])
+@pytest.mark.parametrize("ne", [3, 5, 1, 2, 4])   # 1, 2, 4: hmm_vit_eval_anytopo
 def test_oracle_hmm_golden(ne):
-    g = cases.load("tmat_hmm.npz")
+    g = cases.load("tmat_hmm.npz" if ne in (3, 5) else "hmm_anytopo.npz")
     a = {k: g[f"h{ne}_in_{k}"].copy() for k in ("score", "history", "out_score", "out_history", "senid", "tmatid",
                                                 "mpx", "bestscore", "sseq")}
     for f in range(g[f"h{ne}_senscr"].shape[0]):

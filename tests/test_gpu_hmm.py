@@ -37,9 +37,9 @@ def _assert_pop(p, d):
     np.testing.assert_array_equal(p.bestscore, d["bestscore"])
 
 
-@pytest.mark.parametrize("ne", [3, 5])
+@pytest.mark.parametrize("ne", [3, 5, 1, 2, 4])   # 1, 2, 4: hmm_vit_eval_anytopo
 def test_hmm_vit_eval_golden(ne):
-    g = cases.load("tmat_hmm.npz")
+    g = cases.load("tmat_hmm.npz" if ne in (3, 5) else "hmm_anytopo.npz")
     src = {k: g[f"h{ne}_in_{k}"] for k in ("score", "history", "out_score", "out_history", "senid", "tmatid", "mpx",
                                            "bestscore")}
     sen = g[f"h{ne}_senscr"]
@@ -51,7 +51,8 @@ def test_hmm_vit_eval_golden(ne):
     ctx.free()
 
 
-@pytest.mark.parametrize("ne,n_hmm", [(3, 50000), (5, 20011), (3, 1), (3, 255), (5, 257)])
+@pytest.mark.parametrize("ne,n_hmm", [(3, 50000), (5, 20011), (3, 1), (3, 255), (5, 257),
+                                      (1, 3001), (2, 4099), (4, 20000)])   # 1, 2, 4: hmm_vit_eval_anytopo
 def test_hmm_vit_eval_vs_oracle_config4(ne, n_hmm):
     """BASELINE config 4 population (50k HMMs, 10 % mpx, both skip / no-skip
     transition matrices) over several frames."""
@@ -82,11 +83,11 @@ def test_empty_population_and_bad_arguments():
     with pytest.raises(b.B200Error, match="tmatid"):
         ctx.vit_eval(pop, np.zeros((1, 100), np.int16))
     with pytest.raises(b.B200Error):
-        b.HmmContext(4, np.zeros((1, 4, 5), np.uint8), None, 10)
+        b.HmmContext(6, np.zeros((1, 6, 7), np.uint8), None, 10)   # HMM_MAX_NSTATE is 5 (PS/hmm.h:90)
     ctx.free()
 
 
-@pytest.mark.parametrize("ne", [3, 5])
+@pytest.mark.parametrize("ne", [3, 5, 4])
 def test_step_beam_compaction_and_active_senones(ne):
     n_sen, n_tmat, n_sseq, n_hmm = 5000, 50, 27000, 50000
     tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)

@@ -115,7 +115,7 @@ def test_tmat_quantiser_matches_reference(tmp_path):
     np.testing.assert_array_equal(orc.port_tmat_quantize(tp).reshape(-1), out)
 
 
-@pytest.mark.parametrize("n_emit", [3, 5])
+@pytest.mark.parametrize("n_emit", [3, 5, 1, 2, 4])   # 1, 2, 4 -> hmm_vit_eval_anytopo (hmm.c:711-786)
 def test_hmm_eval_matches_reference(n_emit):
     n_sen, n_tmat, n_sseq, n_hmm = 500, 17, 300, 4000
     tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, n_emit, 3))
