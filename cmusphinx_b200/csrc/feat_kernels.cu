@@ -156,6 +156,7 @@ __global__ void feat_map_kernel(const float *__restrict__ cep, const int32_t *__
     };
     float r;
     if (kind == 0) r = at(0);
+    else if (kind == 3) r = at(a - 8);            // plain copy of a neighbouring frame (offset biased by 8)
     else if (kind == 1) r = __fsub_rn(at(a), at(-a));
     else r = __fsub_rn(__fsub_rn(at(3), at(-1)), __fsub_rn(at(1), at(-3)));
     out[id] = r;
@@ -188,7 +189,8 @@ inline uint16_t fm(int kind, int a, int i) { return (uint16_t)(kind << 12 | a <<
 
 // window, map and pre-LDA length of a -feat type; false if the reference's
 // feat_init would reject it
-bool feat_layout(int type, int cs, int &win, FeatMap &m) {
+bool feat_layout(const b200_feat_cfg_t *cfg, int &win, FeatMap &m) {
+    const int type = cfg->type, cs = cfg->cepsize;
     m.n = 0;
     if (cs < 1 || cs > 64) return false;
     auto add = [&](int kind, int a, int i) { m.e[m.n++] = fm(kind, a, i); };
@@ -227,6 +229,24 @@ bool feat_layout(int type, int cs, int &win, FeatMap &m) {
         win = 0;
         for (int i = 0; i < cs; ++i) add(0, 0, i);
         return true;
+    case B200_FEAT_COPY: {
+        // feat_copy (feat.c:828-849): per stream, the window's frames one after the other
+        const int w = cfg->copy_window, ns = cfg->copy_streams;
+        if (w < 0 || w > 7 || ns < 0 || ns > B200_MAX_STREAMS) return false;
+        int tot = 0;
+        for (int j = 0; j < ns; ++j) { if (cfg->copy_len[j] < 1) return false; tot += cfg->copy_len[j]; }
+        if (ns && tot > cs) return false;
+        if ((ns ? tot : cs) * (2 * w + 1) > kMaxFeatLen) return false;
+        win = w;
+        int spos = 0;
+        for (int j = 0; j < (ns ? ns : 1); ++j) {
+            const int len = ns ? cfg->copy_len[j] : cs;
+            for (int i = -w; i <= w; ++i)
+                for (int d = 0; d < len; ++d) add(3, i + 8, spos + d);
+            spos += len;
+        }
+        return true;
+    }
     case B200_FEAT_1S_C_D:
         win = 2;
         for (int i = 0; i < cs; ++i) add(0, 0, i);
@@ -243,7 +263,7 @@ struct FeatPlan {
 
 int feat_plan(const b200_feat_cfg_t *c, FeatPlan &p) {
     if (!c) { set_error("feature stage: null configuration"); return B200_ERR_ARG; }
-    if (!feat_layout(c->type, c->cepsize, p.win, p.map)) {
+    if (!feat_layout(c, p.win, p.map)) {
         set_error("feature stage: unknown -feat type %d or cepsize %d not valid for it", c->type, c->cepsize);
         return B200_ERR_ARG;
     }
@@ -253,7 +273,7 @@ int feat_plan(const b200_feat_cfg_t *c, FeatPlan &p) {
     p.lda_dim = 0;
     p.out_len = p.k;
     if (c->lda_rows > 0) {
-        if (c->type == B200_FEAT_S2_4X) { set_error("LDA incompatible with multi-stream features (lda.c:69-73)"); return B200_ERR_ARG; }
+        if (c->type == B200_FEAT_S2_4X || (c->type == B200_FEAT_COPY && c->copy_streams > 1)) { set_error("LDA incompatible with multi-stream features (lda.c:69-73)"); return B200_ERR_ARG; }
         if (!c->lda || c->lda_cols != p.k) {
             set_error("LDA matrix dimension %d doesn't match feature stream size %d (lda.c:127-128)", c->lda_cols, p.k);
             return B200_ERR_ARG;
@@ -263,7 +283,7 @@ int feat_plan(const b200_feat_cfg_t *c, FeatPlan &p) {
         p.out_len = p.lda_dim;
     }
     if (c->n_subvec > 0) {
-        if (c->type == B200_FEAT_S2_4X) { set_error("subvector specifications require single-stream features (feat.c:294-297)"); return B200_ERR_ARG; }
+        if (c->type == B200_FEAT_S2_4X || (c->type == B200_FEAT_COPY && c->copy_streams > 1)) { set_error("subvector specifications require single-stream features (feat.c:294-297)"); return B200_ERR_ARG; }
         if (!c->subvec || c->n_subvec > p.out_len) {
             set_error("total dimensionality of subvector specification %d > feature dimensionality %d (feat.c:309-313)",
                       c->n_subvec, p.out_len);

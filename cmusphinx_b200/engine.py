@@ -551,10 +551,28 @@ def feat_1s_c_d_dd(cep, utt_off=None, cmn: bool = True, device: int = 0) -> np.n
 FEAT_TYPES = ["1s_c_d_dd", "s3_1x39", "s2_4x", "1s_c_d_ld_dd", "1s_c", "1s_c_d"]
 
 
+def parse_feat_type(ftype: str):
+    """-feat string -> (type id, copy window, copy stream lengths): the named types of feat_init
+    (SB/feat/feat.c:866-951) or its numeric form "n[,n..][:w]" (feat.c:952-1000)."""
+    if ftype in FEAT_TYPES:
+        return FEAT_TYPES.index(ftype), 0, []
+    if ftype in ("1s_3c", "1s_4c"):
+        # feat_s3_cepwin (feat.c:687-696) copies (2w+1)*cepsize CONTIGUOUS floats starting at frame t-w,
+        # but the padded utterance is not contiguous (feat.c:1248-1259): its first and last w output
+        # frames read stale / out-of-bounds memory in the reference.  Nothing to be identical to.
+        raise ValueError(f"-feat {ftype}: undefined at the utterance edges in the reference (feat_s3_cepwin); "
+                         f"use the numeric form '13:{ftype[3]}'")
+    if ftype and ftype[0].isdigit():
+        body, _, w = ftype.partition(":")
+        return 6, int(w) if w else 0, [int(x) for x in body.split(",")]
+    raise ValueError(f"unknown -feat type {ftype}")
+
+
 class _FeatCfg(C.Structure):
     _fields_ = [("type", C.c_int32), ("cepsize", C.c_int32), ("cmn", C.c_int32), ("varnorm", C.c_int32),
                 ("agc", C.c_int32), ("lda_rows", C.c_int32), ("lda_cols", C.c_int32), ("lda_dim", C.c_int32),
-                ("lda", C.POINTER(C.c_float)), ("n_subvec", C.c_int32), ("subvec", C.POINTER(C.c_int32))]
+                ("lda", C.POINTER(C.c_float)), ("n_subvec", C.c_int32), ("subvec", C.POINTER(C.c_int32)),
+                ("copy_window", C.c_int32), ("copy_streams", C.c_int32), ("copy_len", C.c_int32 * 4)]
 
 
 lib.b200_feat_dims.argtypes = [C.POINTER(_FeatCfg), C.POINTER(C.c_int32)]
@@ -572,9 +590,11 @@ def feat_compute(cep, utt_off=None, ftype: str = "1s_c_d_dd", cmn: bool = True, 
     T, cs = cep.shape
     off = np.array([0, T], np.int32) if utt_off is None else _c(utt_off, np.int32)
     cfg = _FeatCfg()
-    if ftype not in FEAT_TYPES:
-        raise ValueError(f"unknown -feat type {ftype}")
-    cfg.type, cfg.cepsize, cfg.cmn, cfg.varnorm, cfg.agc = FEAT_TYPES.index(ftype), cs, int(cmn), int(varnorm), int(agc)
+    tid, cw, clen = parse_feat_type(ftype)
+    cfg.type, cfg.cepsize, cfg.cmn, cfg.varnorm, cfg.agc = tid, cs, int(cmn), int(varnorm), int(agc)
+    cfg.copy_window, cfg.copy_streams = cw, len(clen)
+    for j, l in enumerate(clen):
+        cfg.copy_len[j] = l
     keep = []
     if lda is not None:
         lda = _c(lda, np.float32)

@@ -465,7 +465,12 @@ enum {
     B200_FEAT_S2_4X = 2,        /* 4 streams 12|24|3|12, window 4           feat.c:559-618 */
     B200_FEAT_1S_C_D_LD_DD = 3, /* c | d | long d | dd, window 4            feat.c:772-825 */
     B200_FEAT_1S_C = 4,         /* cepstra only, window 0                   feat.c:676-683 */
-    B200_FEAT_1S_C_D = 5        /* c | d, window 2                          feat.c:700-723 */
+    B200_FEAT_1S_C_D = 5,       /* c | d, window 2                          feat.c:700-723 */
+    B200_FEAT_COPY = 6          /* the numeric types "n[,n..][:w]": frames t-w..t+w concatenated per stream,
+                                 * feat_copy feat.c:828-849, 952-1000 (copy_window, copy_streams, copy_len).
+                                 * (`1s_3c` / `1s_4c`, feat_s3_cepwin feat.c:687-696, copy contiguous memory
+                                 * across the non-contiguous padded utterance: their edge frames are
+                                 * undefined in the reference and the types are not offered.) */
 };
 typedef struct b200_feat_cfg {
     int32_t type, cepsize, cmn, varnorm, agc;
@@ -473,6 +478,10 @@ typedef struct b200_feat_cfg {
     const float *lda;                      /* host pointer (both entry points) */
     int32_t n_subvec;                      /* 0: no projection */
     const int32_t *subvec;                 /* host pointer */
+    /* B200_FEAT_COPY only: window w (0..7); copy_streams == 0 means one stream of cepsize
+     * values, else the cepstral vector is cut into copy_streams pieces of copy_len[] values */
+    int32_t copy_window, copy_streams;
+    int32_t copy_len[B200_MAX_STREAMS];
 } b200_feat_cfg_t;
 /* dims = {window, stream-concatenated length before LDA, output length per frame};
  * B200_ERR_ARG / B200_ERR_UNSUP for a configuration the reference would reject. */

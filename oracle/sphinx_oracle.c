@@ -1269,10 +1269,28 @@ orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *feat)
  * The same walk as the reference: pad (feat.c:1253-1259), cmn [+varnorm]
  * (cmn.c:150-213), agc max (agc.c:108-126), the type's compute_feat on every
  * frame (feat.c:559-849), lda (lda.c:141-160), subvectors (feat.c:334-355). */
+static int orc_copy_window, orc_copy_streams, orc_copy_len[8];   /* type 6, set by orc_feat_set_copy */
+
+/* feat_copy types "n[,n..][:w]" (feat.c:828-849, 952-1000) */
+void
+orc_feat_set_copy(int window, int n_streams, const int *len)
+{
+    int j;
+    orc_copy_window = window; orc_copy_streams = n_streams;
+    for (j = 0; j < n_streams && j < 8; ++j) orc_copy_len[j] = len[j];
+}
+
 static int
 orc_feat_window(int type, int cs, int *k)
 {
     switch (type) {
+    case 6: {
+        int j, tot = 0;
+        for (j = 0; j < orc_copy_streams; ++j) tot += orc_copy_len[j];
+        if (orc_copy_streams == 0) tot = cs;
+        *k = tot * (2 * orc_copy_window + 1);
+        return tot <= cs ? orc_copy_window : -1;
+    }
     case 0: *k = 3 * cs; return 3;
     case 1: *k = 39; return cs == 13 ? 3 : -1;
     case 2: *k = 51; return cs == 13 ? 4 : -1;
@@ -1369,6 +1387,16 @@ orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
             for (i = 0; i < cs; ++i) *f++ = C_(0, i);
             for (i = 0; i < cs; ++i) *f++ = C_(2, i) - C_(-2, i);
             break;
+        case 6: {
+            int spos = 0, w;
+            for (j = 0; j < (orc_copy_streams ? orc_copy_streams : 1); ++j) {
+                const int len = orc_copy_streams ? orc_copy_len[j] : cs;
+                for (w = -win; w <= win; ++w)
+                    for (i = 0; i < len; ++i) *f++ = C_(w, spos + i);
+                spos += len;
+            }
+            break;
+        }
         }
         if (lda) {
             memset(tmp, 0, sizeof(float) * k);

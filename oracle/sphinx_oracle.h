@@ -165,6 +165,7 @@ void orc_feat_1s_c_d_dd(const float *cep, int T, int cepsize, int cmn, float *fe
  * 5 1s_c_d (feat.c:559-849); cmn 0/1 (+ varnorm, cmn.c:150-213); agc 0 none, 1 max
  * (agc.c:108-126); lda [lda_dim][k] or NULL (lda.c:141-160); subvec indices or NULL
  * (feat.c:334-355).  out [T][out_len]; returns out_len (<0: bad configuration). */
+void orc_feat_set_copy(int window, int n_streams, const int *len);   /* parameters of type 6 (feat_copy types) */
 int orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
                      const float *lda, int lda_dim, const int *subvec, int n_subvec,
                      const float *cep, int T, float *out);

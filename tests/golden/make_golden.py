@@ -230,6 +230,22 @@ def semi_beam():
          ds_cfg=np.array([[2, 0], [3, 15]], np.int32), **out)
 
 
+def feat_unit_test():
+    """The reference's own feature unit test (sphinxbase/test/unit/test_feat/test_feat.c): its 6 x 13
+    input cepstra (parsed out of the C source) and the expected printout _test_feat.res, 6 lines each
+    for -feat "13", "13:1" and "1s_c_d_dd" (cmn none, agc none), values printed with %.3f."""
+    import re
+    d = "/root/reference/sphinxbase/test/unit/test_feat"
+    src = open(os.path.join(d, "test_feat.c")).read()
+    body = src[src.index("const mfcc_t data[6][13]"):src.index("};") + 2]
+    vals = [float(v) for v in re.findall(r"FLOAT2MFCC\(([-0-9.]+)\)", body)]
+    cep = np.array(vals, np.float32).reshape(6, 13)
+    lines = [l.split() for l in open(os.path.join(d, "_test_feat.res")).read().strip().splitlines()]
+    assert len(lines) == 18
+    save("feat_unit_test.npz", cep=cep, res_13=np.array(lines[0:6], np.float64), res_13_1=np.array(lines[6:12], np.float64),
+         res_1s_c_d_dd=np.array(lines[12:18], np.float64))
+
+
 def feat_general():
     """General feature stage: the reference's own feat_t (ref_feat_compute in oracle/ref_shim.c)
     on 80 frames of test/data/wsj/442c0201.mfc for the configurations of cases.FEAT_GOLDEN_CASES."""

@@ -467,6 +467,7 @@ def port_feat_1s_c_d_dd(cep, cmn=True):
 
 
 FEAT_TYPES = ["1s_c_d_dd", "s3_1x39", "s2_4x", "1s_c_d_ld_dd", "1s_c", "1s_c_d"]
+port.orc_feat_set_copy.argtypes = [C.c_int, C.c_int, i32p]
 port.orc_feat_compute.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int, i32p, C.c_int,
                                   f32p, C.c_int, f32p]
 
@@ -494,8 +495,12 @@ def port_feat_compute(cep, ftype="1s_c_d_dd", cmn=True, varnorm=False, agc=False
         if lda_dim <= 0 or lda_dim > lda.shape[0]:
             lda_dim = lda.shape[0]
         lda = np.ascontiguousarray(lda[:lda_dim])
-    out = np.zeros((T, 4 * max(cs, 13)), np.float32)
-    n = port.orc_feat_compute(FEAT_TYPES.index(ftype), cs, int(cmn), int(varnorm), int(agc),
+    from cmusphinx_b200.engine import parse_feat_type
+    tid, cw, clen = parse_feat_type(ftype)
+    cl = np.array(clen + [0] * 8, np.int32)
+    port.orc_feat_set_copy(cw, len(clen), _p(cl, C.c_int32))
+    out = np.zeros((T, max(4 * max(cs, 13), 15 * cs)), np.float32)
+    n = port.orc_feat_compute(tid, cs, int(cmn), int(varnorm), int(agc),
                               _p(lda, C.c_float) if lda is not None else None, lda_dim,
                               _p(sv, C.c_int32) if sv.size else None, sv.size, _p(cep, C.c_float), T,
                               _p(out, C.c_float))
@@ -509,7 +514,7 @@ def ref_feat_compute(cep, ftype="1s_c_d_dd", cmn=True, varnorm=False, agc=False,
     """The reference's feat_t on one utterance -> [T][out_dim] (the valid prefix of its rows)."""
     cep = _c(cep, np.float32)
     T, cs = cep.shape
-    out = np.zeros((T + 16, 4 * max(cs, 13)), np.float32)
+    out = np.zeros((T + 16, max(4 * max(cs, 13), 15 * cs)), np.float32)
     row = (C.c_int32 * 1)()
     od = (C.c_int32 * 1)()
     if lda is not None:

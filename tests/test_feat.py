@@ -151,3 +151,58 @@ def test_general_feature_stage_refuses_what_the_reference_rejects():
     with pytest.raises(b.B200Error):
         b.feat_compute(cep, None, "1s_c", subvec=list(range(14)))                     # feat.c:309-313
     assert b.feat_compute(np.zeros((0, 13), np.float32), np.array([0, 0], np.int32), "s2_4x").shape == (0, 51)
+
+
+# ------------------------------------------------- the reference's own feature unit test
+_UNIT = [("13", "res_13"), ("13:1", "res_13_1"), ("1s_c_d_dd", "res_1s_c_d_dd")]
+
+
+def _as_printed(x):
+    """what test_feat.c prints: "%.3f" of every value"""
+    return np.array([[float("%.3f" % v) for v in row] for row in x])
+
+
+@pytest.mark.parametrize("ftype,key", _UNIT)
+def test_port_reproduces_the_references_feature_unit_test(ftype, key):
+    """sphinxbase/test/unit/test_feat/test_feat.c + _test_feat.res (cmn none, agc none)."""
+    g = cases.load("feat_unit_test.npz")
+    np.testing.assert_array_equal(_as_printed(orc.port_feat_compute(g["cep"], ftype, False)), g[key])
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ftype", ["13", "13:1", "13:3", "5,8:2", "4,4,5", "12"])
+def test_numeric_feature_types_match_reference(ftype):
+    """feat_copy types "n[,n..][:w]" (feat.c:828-849, 952-1000), with and without normalisation."""
+    cep = _cep(40, 3)
+    for cmn, vn, agc in ((0, 0, 0), (1, 0, 0), (1, 1, 1)):
+        for T in (40, 2, 1):
+            assert _same(orc.port_feat_compute(cep[:T], ftype, cmn, vn, agc),
+                         orc.ref_feat_compute(cep[:T], ftype, cmn, vn, agc)), (ftype, cmn, vn, agc, T)
+
+
+def test_window_copy_types_with_undefined_edges_are_not_offered():
+    """`1s_3c` / `1s_4c`: feat_s3_cepwin copies contiguous memory across the non-contiguous padded
+    utterance -- the reference's first and last w frames are undefined (checked against it below)."""
+    with pytest.raises(ValueError, match="feat_s3_cepwin"):
+        b.engine.parse_feat_type("1s_3c")
+    if orc.have_ref():
+        cep = _cep(30, 4)
+        r, a = orc.ref_feat_compute(cep, "1s_3c", False), orc.port_feat_compute(cep, "13:3", False)
+        assert np.array_equal(r[3:-3], a[3:-3])          # interior frames: the plain window copy
+
+
+@pytest.mark.gpu
+def test_feature_kernels_reproduce_the_references_unit_test_and_numeric_types():
+    g = cases.load("feat_unit_test.npz")
+    for ftype, key in _UNIT:
+        np.testing.assert_array_equal(_as_printed(b.feat_compute(g["cep"], None, ftype, False)), g[key])
+    lens = [1, 2, 40, 7, 130]
+    cep = _cep(sum(lens), 9)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    for ftype in ("13", "13:1", "13:3", "5,8:2", "4,4,5", "12", "13:7"):
+        for cmn, vn, agc in ((0, 0, 0), (1, 0, 0), (1, 1, 1)):
+            want = np.concatenate([orc.port_feat_compute(cep[off[u]:off[u + 1]], ftype, cmn, vn, agc)
+                                   for u in range(len(lens))])
+            assert _same(b.feat_compute(cep, off, ftype, cmn, vn, agc), want), (ftype, cmn, vn, agc)
+    with pytest.raises(b.B200Error):
+        b.feat_compute(cep, off, "7,7")           # streams longer than the cepstral vector

@@ -25,6 +25,34 @@ def test_logadd_table_golden():
     assert g["table10"].size == 256
 
 
+# The reference's own logmath unit tests (sphinxbase/test/unit/test_logmath/): literal
+# expected values and tolerance (LOG_EPSILON = 1500 raw units, compared after the shift).
+_LOGMATH_KATS = [
+    # (base, shift, [(p, expected log)])                      source
+    (1.0001, 8, [(1e-150, -13493), (42.0, 146)]),          # test_log_shifted.c:13-24
+    (1.003, 0, [(1e-48, -36896), (42.0, 1247)]),           # test_log_int8.c:13-20
+    (1.0001, 0, [(1e-150, -3454050), (42.0, 37378)]),      # test_log_int16.c:13-23
+]
+
+
+@pytest.mark.parametrize("base,shift,kats", _LOGMATH_KATS)
+def test_reference_logmath_unit_test_known_answers(base, shift, kats):
+    """logmath_log / logmath_add of the oracle and of the product's host code reproduce the
+    known answers the reference's unit tests assert, within the reference's own tolerance,
+    and the two add identities those tests check (1e-48 + 5e-48 = 6e-48; 1e-48 + 42 = 42)."""
+    eps = 1500
+    lm = orc.port.orc_logmath_init(base, shift, 1)
+    for p, want in kats:
+        for got in (orc.port.orc_logmath_log(lm, p), b.lib.b200_logmath_log(base, shift, p)):
+            assert abs(got - want) < eps, (base, shift, p, got, want)
+    for log, add in ((lambda p: orc.port.orc_logmath_log(lm, p), lambda x, y: orc.port.orc_logmath_add(lm, x, y)),
+                     (lambda p: b.lib.b200_logmath_log(base, shift, p),
+                      lambda x, y: b.lib.b200_logmath_add(base, shift, x, y))):
+        assert abs(add(log(1e-48), log(5e-48)) - log(6e-48)) < eps
+        assert abs(add(log(1e-48), log(42.0)) - log(42.0)) < eps
+    orc.port.orc_logmath_free(lm)
+
+
 def test_logmath_log_add_golden():
     g = cases.load("logmath.npz")
     base = float(g["base"])
