@@ -2,11 +2,18 @@
 // (no helper arithmetic), s32 vs f32, 2-input vs 3-input.  ops/clk/SM.
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 #define CHAIN_I(k) asm volatile("min.s32 %0, %0, %1; max.s32 %1, %1, %0;" : "+r"(a[k]), "+r"(b[k]));
 #define CHAIN_F(k) asm volatile("min.f32 %0, %0, %1; max.f32 %1, %1, %0;" : "+f"(x[k]), "+f"(y[k]));
 #define CHAIN_I3(k) a[k] = __vimin3_s32(a[k], b[k], c3 + it); b[k] = __vimax3_s32(b[k], a[k], c3 - it);
 #define CHAIN_F3(k) asm volatile("min.f32 %0, %0, %1, %2; max.f32 %1, %1, %0, %2;" : "+f"(x[k]), "+f"(y[k]) : "f"(f3));
+// packed 16-bit forms: two values per instruction (candidates for an exact pre-filter in the epilogue)
+#define CHAIN_S16X2(k) a[k] = (int)__vmins2((unsigned)a[k], (unsigned)b[k]); b[k] = (int)__vmaxs2((unsigned)b[k], (unsigned)a[k]);
+#define CHAIN_S16X2_3(k) a[k] = (int)__vimin3_s16x2((unsigned)a[k], (unsigned)b[k], (unsigned)(c3 + it)); b[k] = (int)__vimax3_s16x2((unsigned)b[k], (unsigned)a[k], (unsigned)(c3 - it));
+#define CHAIN_H2(k) { __half2 p = *reinterpret_cast<__half2 *>(&a[k]), q = *reinterpret_cast<__half2 *>(&b[k]); p = __hmin2(p, q); q = __hmax2(q, p); a[k] = *reinterpret_cast<int *>(&p); b[k] = *reinterpret_cast<int *>(&q); }
+#define CHAIN_BF2(k) { __nv_bfloat162 p = *reinterpret_cast<__nv_bfloat162 *>(&a[k]), q = *reinterpret_cast<__nv_bfloat162 *>(&b[k]); p = __hmin2(p, q); q = __hmax2(q, p); a[k] = *reinterpret_cast<int *>(&p); b[k] = *reinterpret_cast<int *>(&q); }
 #define REP8(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
 template <int OP>
@@ -19,6 +26,11 @@ __global__ void __launch_bounds__(256) probe(int *out, int iters, int seed) {
         if (OP == 1) { REP8(CHAIN_F) }
         if (OP == 2) { REP8(CHAIN_I3) }
         if (OP == 3) { REP8(CHAIN_F3) }
+        if (OP == 6) { REP8(CHAIN_S16X2) }
+        if (OP == 7) { REP8(CHAIN_S16X2_3) }
+        if (OP == 8) { REP8(CHAIN_H2) }
+        if (OP == 9) { REP8(CHAIN_BF2) }
+        if (OP == 10) { CHAIN_I(0) CHAIN_H2(1) CHAIN_I(2) CHAIN_H2(3) CHAIN_I(4) CHAIN_H2(5) CHAIN_I(6) CHAIN_H2(7) }   // do s32 and f16x2 min/max share a pipe?
         if (OP == 4) { CHAIN_I(0) CHAIN_F(0) CHAIN_I(1) CHAIN_F(1) CHAIN_I(2) CHAIN_F(2) CHAIN_I(3) CHAIN_F(3) }   // 8 int + 8 float ops
         if (OP == 5) { asm volatile("lop3.b32 %0, %0, %1, 31, 0x36;" : "+r"(a[0]) : "r"(b[0])); CHAIN_I(1) CHAIN_I(2) CHAIN_I(3)
                        asm volatile("lop3.b32 %0, %0, %1, 31, 0x36;" : "+r"(a[4]) : "r"(b[4])); CHAIN_I(5) CHAIN_I(6) CHAIN_I(7) }
@@ -46,4 +58,7 @@ void run(const char *name) {
     cudaFree(d);
 }
 
-int main() { run<0>("min.s32"); run<1>("min.f32"); run<2>("min3.s32"); run<3>("min3.f32"); run<4>("mix s32+f32"); return 0; }
+int main() { run<0>("min.s32"); run<1>("min.f32"); run<2>("min3.s32"); run<3>("min3.f32"); run<4>("mix s32+f32");
+    // instructions/clk/SM; every packed instruction handles 2 values
+    run<6>("vmin.s16x2"); run<7>("vmin3.s16x2"); run<8>("hmin2.f16"); run<9>("hmin2.bf16"); run<10>("mix s32+f16x2");
+    return 0; }
