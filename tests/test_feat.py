@@ -206,3 +206,49 @@ def test_feature_kernels_reproduce_the_references_unit_test_and_numeric_types():
             assert _same(b.feat_compute(cep, off, ftype, cmn, vn, agc), want), (ftype, cmn, vn, agc)
     with pytest.raises(b.B200Error):
         b.feat_compute(cep, off, "7,7")           # streams longer than the cepstral vector
+
+
+def test_feature_plan_dims_and_refusals_host_only():
+    """b200_feat_dims is host code (no device needed): window / stream length / output length of
+    every type, and the configurations feat_init / feat_read_lda / feat_set_subvecs reject."""
+    import ctypes as C
+    from cmusphinx_b200.engine import _FeatCfg, parse_feat_type
+
+    def dims(ftype, cs=13, lda=None, lda_dim=0, sv=None, **kw):
+        cfg = _FeatCfg()
+        tid, cw, clen = parse_feat_type(ftype)
+        cfg.type, cfg.cepsize, cfg.cmn = tid, cs, kw.get("cmn", 1)
+        cfg.agc = kw.get("agc", 0)
+        cfg.copy_window, cfg.copy_streams = cw, len(clen)
+        for j, l in enumerate(clen):
+            cfg.copy_len[j] = l
+        keep = []
+        if lda is not None:
+            lda = np.ascontiguousarray(lda, np.float32); keep.append(lda)
+            cfg.lda_rows, cfg.lda_cols, cfg.lda_dim = lda.shape[0], lda.shape[1], lda_dim
+            cfg.lda = lda.ctypes.data_as(C.POINTER(C.c_float))
+        if sv is not None:
+            sv = np.ascontiguousarray(sv, np.int32); keep.append(sv)
+            cfg.n_subvec, cfg.subvec = sv.size, sv.ctypes.data_as(C.POINTER(C.c_int32))
+        d = (C.c_int32 * 3)()
+        rc = b.lib.b200_feat_dims(C.byref(cfg), d)
+        return rc, list(d)
+
+    assert dims("1s_c_d_dd") == (0, [3, 39, 39])
+    assert dims("s3_1x39") == (0, [3, 39, 39])
+    assert dims("s2_4x") == (0, [4, 51, 51])
+    assert dims("1s_c_d_ld_dd") == (0, [4, 52, 52])
+    assert dims("1s_c") == (0, [0, 13, 13])
+    assert dims("1s_c_d") == (0, [2, 26, 26])
+    assert dims("13:1") == (0, [1, 39, 39])
+    assert dims("5,8:2") == (0, [2, 65, 65])
+    assert dims("1s_c_d_dd", lda=np.eye(39), lda_dim=29) == (0, [3, 39, 29])
+    assert dims("1s_c_d_dd", lda=np.eye(39), lda_dim=99) == (0, [3, 39, 39])      # lda.c:131-134
+    assert dims("1s_c_d_dd", lda=np.eye(39), lda_dim=29, sv=[0, 5, 7]) == (0, [3, 39, 3])
+    assert dims("s3_1x39", cs=12)[0] < 0                    # feat.c: s3_1x39 needs 13 cepstra
+    assert dims("s2_4x", lda=np.eye(51))[0] < 0             # lda.c:69-73
+    assert dims("1s_c_d_dd", lda=np.eye(38))[0] < 0         # lda.c:127-128
+    assert dims("1s_c", sv=list(range(14)))[0] < 0          # feat.c:309-313
+    assert dims("7,7")[0] < 0                               # more stream values than cepstra
+    assert dims("1s_c_d_dd", cmn=2)[0] < 0                  # prior CMN: live mode only
+    assert dims("1s_c_d_dd", agc=2)[0] < 0                  # emax AGC: live mode only
