@@ -268,3 +268,30 @@ def test_s2_semi_frame_downsampling_matches_reference(ds, beam):
     pt.set_ds(ds)
     np.testing.assert_array_equal(pt.eval_all(feat), want)
     r.close()
+
+
+@pytest.mark.parametrize("topn", [1, 2, 3, 6, 8])
+def test_tied_backends_other_topn_match_reference(topn):
+    """-topn other than the default 4: the reference runs different unrolled scorers
+    (get_scores_{4b,8b}_feat_1 .. _6 and _any, s2_semi_mgau.c:209-700; ptm loops over max_topn)."""
+    from cmusphinx_b200 import engine
+    hmm = os.path.join(orc.DATA_DIR, "hmm", "hub4wsj_sc_8k")
+    r = orc.RefAcmod(hmm, topn=topn)
+    feat = _real_feats(r, "wsj/440c0201.mfc", 30)
+    g, v = engine.read_gauden(hmm + "/means"), engine.read_gauden(hmm + "/variances")
+    pv, pd = orc.port_precompute(v["data"].reshape(-1, 13), 13)
+    sd = engine.read_sendump(hmm + "/sendump", 3, 256, r.n_sen)
+    pt = orc.PortTied(2, 1, 3, [13, 13, 13], 256, r.n_sen, topn, g["data"], pv, pd, sd["mixw"], sd["n_clust"],
+                      sd["mixw_cb"], None)
+    np.testing.assert_array_equal(pt.eval_all(feat), r.score(feat))
+    r.close()
+    hmm = os.path.join(orc.DATA_DIR, "hmm", "ptm")
+    r = orc.RefAcmod(hmm, topn=topn)
+    feat = _real_feats(r, "wsj/442c0201.mfc", 10)
+    g, v = engine.read_gauden(hmm + "/means"), engine.read_gauden(hmm + "/variances")
+    pv, pd = orc.port_precompute(v["data"].reshape(-1, 13), 13)
+    sd = engine.read_sendump(hmm + "/sendump", 3, g["n_density"], r.n_sen)
+    pt = orc.PortTied(1, 50, 3, [13, 13, 13], g["n_density"], r.n_sen, topn, g["data"], pv, pd, sd["mixw"],
+                      sd["n_clust"], sd["mixw_cb"], r.sen2cimap())
+    np.testing.assert_array_equal(pt.eval_all(feat), r.score(feat))
+    r.close()
