@@ -295,3 +295,24 @@ def test_tied_backends_other_topn_match_reference(topn):
                       sd["n_clust"], sd["mixw_cb"], r.sen2cimap())
     np.testing.assert_array_equal(pt.eval_all(feat), r.score(feat))
     r.close()
+
+
+@pytest.mark.parametrize("aw", [2, 3])
+def test_ms_backend_acoustic_weight_matches_reference(tmp_path, aw):
+    """-aw (ms_mgau.c:105, senone_eval's `scr /= aw`, ms_senone.c:408-409) on a 2-stream model."""
+    n_sen, n_density, dim, n_feat, topn = 40, 16, 7, 2, 3
+    mean, var, mixw, mfile, vfile, wfile, vl = _ms_files(tmp_path, n_sen, n_density, dim, n_feat, 23)
+    h = orc.ref().ref_ms_init(mfile.encode(), vfile.encode(), wfile.encode(), b".cont.", 1e-4, 1e-7, topn, aw, orc.LOGBASE)
+    assert h
+    tot = n_sen * n_density * dim * n_feat
+    rmean, rvar = np.zeros(tot, np.float32), np.zeros(tot, np.float32)
+    rdet = np.zeros(n_sen * n_feat * n_density, np.float32)
+    rmixw = np.zeros(n_sen * n_feat * n_density, np.uint8)
+    orc.ref().ref_ms_params(h, orc._p(rmean, C.c_float), orc._p(rvar, C.c_float), orc._p(rdet, C.c_float),
+                            orc._p(rmixw, C.c_uint8))
+    feat = synth.cont_features(mean, var, 25, 6)
+    out_ref = np.zeros((25, n_sen), np.int16)
+    orc.ref().ref_ms_eval_all(h, orc._p(feat, C.c_float), 25, orc._p(out_ref, C.c_int16))
+    pm = orc.PortMs(n_sen, n_feat, vl, n_density, n_sen, topn, aw, rmean, rvar, rdet, rmixw, np.arange(n_sen))
+    np.testing.assert_array_equal(pm.eval_all(feat), out_ref)
+    orc.ref().ref_ms_free(h)
