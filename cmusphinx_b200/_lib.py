@@ -77,6 +77,7 @@ _sig("b200_mgau_set_path", C.c_int, vp, C.c_int)
 _sig("b200_mgau_get_path", C.c_int, vp)
 _sig("b200_mgau_tc_last_format", C.c_int, vp)
 _sig("b200_mgau_tied_stats", C.c_int, vp, C.POINTER(C.c_longlong))
+_sig("b200_mgau_cont_stats", C.c_int, vp, C.POINTER(C.c_longlong))
 _sig("b200_mgau_score_host", C.c_int, vp, vp, C.c_int, vp)
 _sig("b200_mgau_score_dev", C.c_int, vp, vp, C.c_int, vp, vp)
 _sig("b200_mgau_frame_eval", C.c_int, vp, c_i16p, c_u8p, C.c_int32, C.POINTER(c_f32p), C.c_int32, C.c_int32)

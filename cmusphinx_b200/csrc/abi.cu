@@ -402,6 +402,16 @@ int b200_mgau_tied_stats(b200_mgau_t *m, long long out[3]) {
     return B200_OK;
 }
 
+int b200_mgau_cont_stats(b200_mgau_t *m, long long out[7]) {
+    if (!m || !out) { set_error("null argument"); return B200_ERR_ARG; }
+    for (int i = 0; i < 7; ++i) out[i] = 0;
+    if (!m->tc) return B200_OK;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (tc_last_stats(m->tc, out)) { set_error("tc_last_stats: %s", cudaGetErrorString(cudaGetLastError())); return B200_ERR_CUDA; }
+    return B200_OK;
+}
+
 int b200_mgau_set_path(b200_mgau_t *m, int path) {
     if (!m) return B200_ERR_ARG;
     if (path == 0) { m->path = 0; return B200_OK; }

@@ -98,6 +98,9 @@ bool tc_shape_supported(const GmmDev &g);
 // transpose to row-major d_out[T][n_sen], minus the frame best if asked.
 int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out);
 int tc_last_format(TcPlan *p);   // 1 all tiles fp16, 0 all TF32, 2 mixed (synchronises)
+// {pairs scored, pairs on the hard path, queue A items, queue B items, overflow flag,
+//  largest |GEMM - reference| distance seen} of the last tc_score_raw (synchronises)
+int tc_last_stats(TcPlan *p, long long out[7]);
 int tc_finish(TcPlan *p, int T, int T_pad, int subtract_best, int16_t *d_out, cudaStream_t st);
 
 }  // namespace b200

@@ -79,6 +79,22 @@ constexpr int kFirstEpiWarp = 2 + kBuildWarps;
 constexpr int kThreads = (2 + kBuildWarps) * 32 + kEpiThreads;
 constexpr int kColsPerEpiThread = kTileN / (kEpiWarps / 4);   // 64
 constexpr uint32_t kTmemCols = 512;
+// MODE 0 (fully continuous) epilogue, round 2: the GEMM delivers w = -32 (d - 1024 mixw)
+// and most (frame, senone) pairs are decided by one cheap certificate (see
+// tc_score_kernel); the rest go through a shared-memory queue to kHardWarps
+// dedicated warps that run the full top-4 network on compacted lanes.
+constexpr int kHardWarps = 8;
+// with hard-path warps the certificate needs only 8 epilogue warps (2 per TMEM lane quarter, 128 columns each)
+constexpr int epi_warps(int HW) { return HW ? 8 : kEpiWarps; }
+constexpr int score_threads(int HW) { return (2 + kBuildWarps + epi_warps(HW) + HW) * 32; }
+constexpr int kQueueBytes = 41 * 1024;          // per buffer, two buffers
+constexpr int kWinFden = 42;                    // 29 (log-add table reach) + 11 (three other terms can add up to that) + 2
+constexpr float kWinV = (float)kWinFden * 1024.f * 32.f;     // the same window on the -32-scaled accumulator
+constexpr float kBig = 1099511627776.f;         // 2^40: sat((th - x) * 2^40) is a crisp 0/1 indicator on the FMA pipe
+constexpr float kDeltaV = 64.f * 32.f;          // slack of the "at most 3 better densities" count (64 raw units)
+constexpr int kFixRegionsMax = 160;             // one fix-up queue region per CTA
+constexpr int kEpsCap = 400;                    // beyond this bound a pair goes to the literal scan
+constexpr int kFixChunk = 64;                   // queue A slots a hard-path warp reserves at a time
 
 struct TcParams {
     const float *gB;        // pre-tiled B operand
@@ -90,7 +106,14 @@ struct TcParams {
     const float *scaleA;    // fp16 operands: per-tile, per-column power-of-two scale of the A operand [n_tiles_n][16 * ksteps]
     const uint8_t *fmt;     // [n_tiles_n] operand format of every n-tile for THIS batch (1 fp16, 0 TF32); null: TF32 everywhere
     uint4 *part;            // tied mode: [n_tiles_n][T_pad][4] sorted top-4 keys of each 64-column group
-    int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step
+    int dbg;                // development knobs (B200_TC_DBG): 1 = skip epilogue math, 2 = one MMA per k-step, 4 = every pair takes the hard path
+    // MODE 0, round 2
+    const float *gCw;       // [n_tiles_n][256] 32*1024*mixw of every tile row (the offset folded into the B constant)
+    uint4 *qa;              // fix-up queue A: [regions][capA] {t, senone, slots 0|1, slots 2|3}
+    uint2 *qb;              // fix-up queue B: [capB] {t, senone}
+    unsigned *qcnt;         // [1] n_B, [2] overflow, [3] max |GEMM - exact| seen, [4] hard pairs, [5] of those finished in place (tile queue full), [8 + region] n_A
+    unsigned capA, capB;
+    int eps0, eps_shift;    // bound on |GEMM distance - reference distance|: eps0 + (|d| >> eps_shift) raw units
     uint8_t logadd[256];
 };
 
@@ -122,6 +145,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
         if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s
+    }
+}
+// The same for waits off the critical path (a consumer that is ahead of its
+// producer): back off between polls so the spinning warp does not take issue
+// slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(200);
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -247,6 +282,141 @@ __device__ __forceinline__ int32_t senone_from_keys(const int32_t (&top)[4], con
     return clamp16(scr);
 }
 
+// ------------------------------------------------ MODE 0 round-2 epilogue parts
+// Exactness contract.  The GEMM distance d~ differs from the reference's
+// sequentially rounded float32 d (ms_gauden.c:417-523) by at most
+// eps(d) = eps0 + (|d| >> eps_shift) raw units (measured, and monitored at run
+// time: TcParams::qcnt[3]).  A score is emitted by this kernel only when every
+// decision it rests on holds for ALL d within eps of d~:
+//   * the set and the order of the top 4 densities (gaps > 2 eps),
+//   * fden = ((int32)d + 1023) >> 10 of every density that can change the
+//     log-add chain: the chain is evaluated at the lower and at the upper end
+//     of every density's interval -- it is monotone in each term, so equal ends
+//     pin the true value between them.
+// Everything else is queued for tc_fix_a_kernel (re-scores the uncertain
+// densities with the reference's float32 arithmetic) or tc_fix_b_kernel
+// (near-ties: the literal scan of the senone's M densities).
+// slots: 16 bits per top-4 density -- 0|fden - mixw (15 bits) when settled, 1|10 low bits of floor(-d~)|5-bit id when open
+struct FixOut { uint32_t kind, s01, s23; };   // kind 0 settled, 1 queue A, 2 queue B
+
+__device__ __forceinline__ void fix_append(const TcParams &p, const FixOut &fx, uint32_t t, uint32_t sen) {
+    if (fx.kind == 1) {
+        const unsigned region = blockIdx.x < kFixRegionsMax ? blockIdx.x : 0;
+        const unsigned i = atomicAdd(p.qcnt + 8 + region, 1u);
+        if (i < p.capA) p.qa[(size_t)region * p.capA + i] = make_uint4(t, sen, fx.s01, fx.s23);
+        else p.qcnt[2] = 1u;
+    } else if (fx.kind == 2) {
+        const unsigned i = atomicAdd(p.qcnt + 1, 1u);
+        if (i < p.capB) p.qb[i] = make_uint2(t, sen);
+        else p.qcnt[2] = 1u;
+    }
+}
+
+__device__ __forceinline__ int32_t chain4(const uint8_t *tab, const int32_t (&f)[4]) {
+    int32_t r = logadd_fast(tab, f[0], f[1]);
+    r = logadd_fast(tab, r, f[2]);
+    return logadd_fast(tab, r, f[3]);
+}
+
+// The full selection for one (frame, senone): w[j] = accumulator bits of density
+// j (= -32 (d - 1024 mixw)), cw[j] = 32*1024*mixw_j (16-byte aligned), mixw_rev as
+// in senone_from_keys.  Returns the score and what (if anything) must be re-done
+// exactly.
+template <int M>
+__device__ __forceinline__ int32_t hard_eval(const uint32_t (&w)[M], const float *cw, const uint8_t *mixw_rev,
+                                             const uint8_t *tab, int aw, int eps0, int eps_shift, int32_t m31,
+                                             FixOut &fx) {
+    int32_t k[M];
+#pragma unroll
+    for (int j = 0; j < M; j += 4) {
+        const float4 c = *reinterpret_cast<const float4 *>(cw + j);
+        k[j] = make_key(__float_as_uint(__fadd_rn(__uint_as_float(w[j]), -c.x)), j, m31);
+        k[j + 1] = make_key(__float_as_uint(__fadd_rn(__uint_as_float(w[j + 1]), -c.y)), j + 1, m31);
+        k[j + 2] = make_key(__float_as_uint(__fadd_rn(__uint_as_float(w[j + 2]), -c.z)), j + 2, m31);
+        k[j + 3] = make_key(__float_as_uint(__fadd_rn(__uint_as_float(w[j + 3]), -c.w)), j + 3, m31);
+    }
+    int32_t top[4] = {k[0], k[1], k[2], k[3]};
+    sort4(top[0], top[1], top[2], top[3]);
+#pragma unroll
+    for (int g = 4; g < M; g += 4) merge4(top, k[g], k[g + 1], k[g + 2], k[g + 3]);
+    // the smallest key above the fourth: keys below it wrap to the top of the unsigned range
+    const uint32_t base = (uint32_t)top[3] + 1u;
+    uint32_t r5 = min(min((uint32_t)k[0] - base, (uint32_t)k[1] - base), (uint32_t)k[2] - base);
+#pragma unroll
+    for (int j = 3; j + 1 < M; j += 2) r5 = min(min(r5, (uint32_t)k[j] - base), (uint32_t)k[j + 1] - base);
+    if ((M & 1) == 0) r5 = min(r5, (uint32_t)k[M - 1] - base);
+    int32_t J[4], lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) J[j] = top[j] >> 5;            // floor(-d~): (int32)d = -J for d <= 0
+    // one bound for the four (they are sorted: the largest |d| is at one of the ends)
+    const int32_t ep_raw = eps0 + (max(abs(J[0]), abs(J[3])) >> eps_shift);
+    const int32_t ep = min(ep_raw, kEpsCap);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int32_t mw = (int32_t)mixw_rev[top[j] & 31];
+        lo[j] = ((((1 << kShift) - 1) - J[j] - ep) >> kShift) - mw;
+        hi[j] = ((((1 << kShift) - 1) - J[j] + ep) >> kShift) - mw;
+    }
+    // the chain at both ends of every density's fden interval; equal ends pin the true value
+    const int32_t Flo = chain4(tab, lo), Fhi = chain4(tab, hi);
+    const int32_t gap = 2 * ep + 2;
+    bool close = (J[1] - J[0]) <= gap || (J[2] - J[1]) <= gap || (J[3] - J[2]) <= gap;
+    close |= r5 < (uint32_t)((gap + 2) << 5);                   // a fifth density within reach of the fourth
+    close |= ep_raw > kEpsCap;                                  // too far out for the interval logic: literal scan
+    fx.kind = close ? 2u : (Flo != Fhi ? 1u : 0u);
+    uint32_t sl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool sure = lo[j] == hi[j] && lo[j] > -16000 && lo[j] < 16000;
+        const uint32_t id = 31u - (uint32_t)(top[j] & 31);
+        sl[j] = sure ? ((uint32_t)lo[j] & 0x7fffu) : (0x8000u | (((uint32_t)J[j] & 0x3ffu) << 5) | id);
+    }
+    fx.s01 = sl[0] | (sl[1] << 16); fx.s23 = sl[2] | (sl[3] << 16);
+    int32_t scr = -Fhi;
+    if (__builtin_expect(aw != 1, 0)) scr /= aw;
+    return clamp16(scr);
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// The cheap certificate.  w[j] as above; c2[j] = max(kWinV, 32*1024*mixw_j + kDeltaV) * 2^40.
+// Let j* be the density with the smallest w (the largest d - 1024 mixw) and
+// t_j = w_j - w_j*.  If for every other density
+//   (1) t_j >= kWinV: it sits > 40 log-add units below j*; whichever of them are
+//       in the top 4, their chain cannot reach the table's 29-unit window of j*
+//       even when three of them add up (x + 7 + 4), and
+//   (2) t_j >= 32*1024*mixw_j + kDeltaV, i.e. its distance stays kDeltaV short of
+//       j*'s score, let alone j*'s distance: j* is the top-1 density by distance
+//       (an exact tie in w fails this test too), and
+//   (3) fden of j* is the same over the whole eps interval,
+// the senone score is exactly -(fden(j*) - mixw(j*)) -- read off w(j*) alone.
+// (1) and (2) are one comparison per density against a per-row constant, done
+// as sat((c_j - t_j) * 2^40) on the FMA pipe and summed: the sum must be 1 (j*).
+template <int M>
+__device__ __forceinline__ bool easy_eval(const uint32_t *w /* M registers */, const float *c2, int aw, int eps0,
+                                          int eps_shift, int32_t &score) {
+    float W1 = fmin3(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]));
+#pragma unroll
+    for (int j = 3; j + 1 < M; j += 2) W1 = fmin3(W1, __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
+    if ((M & 1) == 0) W1 = fminf(W1, __uint_as_float(w[M - 1]));
+    // the next float above W1, so that j* itself (and an exact tie) gives a negative difference
+    const float W1n = __uint_as_float(__float_as_uint(W1) + 1u);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        const float t = __fadd_rn(__uint_as_float(w[j]), -W1n);
+        acc[j & 3] += __saturatef(fmaf(t, -kBig, c2[j]));
+    }
+    const float N = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    const int32_t q = __float2int_rd(W1 * (1.0f / kAccScale));          // floor(-(d - 1024 mixw))
+    const int32_t e = min(eps0 + (abs(q) >> eps_shift), kEpsCap + 1);
+    const bool bnd = ((((1 << kShift) - 1) - q + e) & ((1 << kShift) - 1)) <= 2 * e || e > kEpsCap;
+    int32_t scr = -((((1 << kShift) - 1) - q) >> kShift);
+    if (__builtin_expect(aw != 1, 0)) scr /= aw;
+    score = clamp16(scr);
+    return W1 > 0.f && N == 1.0f && !bnd;
+}
+
 // ------------------------------------------------------------------- kernels
 // Feature rows [T][D] -> per frame tile, transposed and zero padded:
 // gX[m_tile][dim 0..Dp)[128 rows].  20 KB per tile for D = 39; the x^2 / hi / lo
@@ -311,14 +481,26 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
 //         p.fmt[n_tile]; both kernels are launched and each takes the units of
 //         its own format, so one sharp Gaussian or one large feature only moves
 //         the affected tiles to TF32.  KS counts 16-column steps then.
-template <int M, int KS, int MODE, int HALF>
-__global__ void __launch_bounds__(kThreads, 1)
+// smem bytes of one instantiation (host and device agree on it)
+constexpr int score_smem_bytes(int KS, int HALF, int HW) {
+    return KS * kBStageBytes + ring_depth(KS) * kAStageBytes + (HALF ? 8 : 4) * KS * kTileM * 4 + 512 + 320 +
+           40 * 8 + 16 + (kTileN + 128) * 4 + kTileN * 4 + (HW ? 2 * kQueueBytes + 128 : 0);
+}
+
+// HW: number of dedicated hard-path warps (MODE 0 only; 0 = uncertain pairs are
+// finished in place by the epilogue lane that found them, e.g. the 160 KB-B TF32
+// instantiation that has no room for the queue).
+template <int M, int KS, int MODE, int HALF, int HW>
+__global__ void __launch_bounds__(score_threads(HW), 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int SPT = kTileN / M;       // senones per tile
     constexpr int kStages = ring_depth(KS);
     constexpr int DP = (HALF ? 8 : 4) * KS;   // padded dims per frame in the X tile
     constexpr int kXBytes = DP * kTileM * 4;
+    constexpr int NT = score_threads(HW);
+    constexpr int EW = epi_warps(HW);             // epilogue warps
+    constexpr int kFirstHardWarp = kFirstEpiWarp + EW;
     uint8_t *sB = smem;                                         // KS * 16 KB
     uint8_t *sA = sB + KS * kBStageBytes;                       // kStages * 8 KB
     uint8_t *sX = sA + kStages * kAStageBytes;                  // DP * 128 * 4
@@ -326,10 +508,20 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     uint8_t *sTab = sMixw + 256;                                // 256 B
     float *sScale = reinterpret_cast<float *>(sTab + 256);      // 16 * KS floats (HALF only; <= 320 B reserved)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256 + 320);
-    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2]
+    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2], q_full[2], q_empty[2]
     constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kStages,
-                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, Q_FULL = T_EMPTY + 2, Q_EMPTY = Q_FULL + 2,
+                  N_BARS = Q_EMPTY + 2;
+    static_assert(N_BARS <= 40, "barrier area");
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
+    // 32*1024*mixw per tile row, senone stride M + 4 (16-byte rows; the hard-path lanes of a warp read different senones)
+    float *sCw = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(tmem_slot) + 16);
+    float *sC2 = sCw + kTileN + 128;                                                        // [256] certificate constants
+    uint32_t *sQ = reinterpret_cast<uint32_t *>(sC2 + kTileN);                              // HW: two item buffers
+    uint32_t *sQn = sQ + 2 * (kQueueBytes / 4);                                             // HW: items in each buffer
+    constexpr int QS = M + 4;                     // item stride in words: M accumulators + header, 16-byte aligned, conflict-free
+    constexpr int QCAP = kQueueBytes / (QS * 4);
+    constexpr int QSL = QCAP / EW;                // slots of one epilogue warp's slice
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -341,7 +533,8 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         mbar_init(BAR(X_FULL), 1);
         mbar_init(BAR(X_EMPTY), kBuildWarps);
         for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), kBuildWarps); mbar_init(BAR(A_EMPTY + s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), kEpiThreads / 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), EW); }
+        for (int a = 0; a < 2; ++a) { mbar_init(BAR(Q_FULL + a), EW); mbar_init(BAR(Q_EMPTY + a), HW ? HW : 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -349,7 +542,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                      ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 256; i += kThreads) sTab[i] = p.logadd[i];
+    for (int i = threadIdx.x; i < 256; i += NT) sTab[i] = p.logadd[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -521,6 +714,80 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 }
             }
         }
+    } else if (HW && warp >= kFirstHardWarp) {
+        // ===================== hard-path warps (MODE 0) =====================
+        // Consumers of the per-tile item queue: 32 items per pass, one per lane, the
+        // full top-4 network + the interval check of hard_eval.
+        const int hw = warp - kFirstHardWarp;
+        uint32_t qt = 0;                                  // tiles seen by this CTA
+        const unsigned region = blockIdx.x < kFixRegionsMax ? blockIdx.x : 0;
+        unsigned fbase = 0; int fleft = 0;                // this warp's reserved run of queue A slots
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
+            if (OTHER_FORMAT(nt)) continue;
+            const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");   // previous unit's tables are free
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");   // this unit's tables are loaded
+            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
+            for (int mt = mt0; mt < mt1; ++mt, ++qt) {
+                const int buf = qt & 1;
+                mbar_wait_idle(BAR(Q_FULL + buf), (qt >> 1) & 1);
+                // every epilogue warp filled its own slice of the buffer; items are numbered across the slices
+                int pre[EW + 1];
+                pre[0] = 0;
+#pragma unroll
+                for (int e = 0; e < EW; ++e) pre[e + 1] = pre[e] + (int)sQn[buf * EW + e];
+                const int n = (p.dbg & 16) ? 0 : pre[EW];
+                const uint32_t *qb = sQ + buf * (kQueueBytes / 4);
+                for (int i0 = hw * 32; i0 < n; i0 += HW * 32) {
+                    const int i = i0 + lane;
+                    const int ii = min(i, n - 1);
+                    int sidx = ii;                                   // slot = slice * QSL + offset inside the slice
+#pragma unroll
+                    for (int e = 1; e < EW; ++e) sidx += (ii >= pre[e]) ? (QSL - (pre[e] - pre[e - 1])) : 0;
+                    const uint32_t *it = qb + (size_t)sidx * QS;
+                    uint32_t w[M];
+#pragma unroll
+                    for (int j = 0; j < M; j += 4) {
+                        const uint4 x = *reinterpret_cast<const uint4 *>(it + j);
+                        w[j] = x.x; w[j + 1] = x.y; w[j + 2] = x.z; w[j + 3] = x.w;
+                    }
+                    const uint32_t hdr = it[M];
+                    const int rw = hdr & 127, sl = hdr >> 8;          // frame row in the tile, senone in the tile
+                    FixOut fx;
+                    const int32_t sc = hard_eval<M>(w, sCw + sl * (M + 4), sMixw + sl * M - (32 - M), sTab, p.aw, p.eps0,
+                                                    p.eps_shift, p.m31, fx);
+                    const int t = mt * kTileM + rw;
+                    const bool live = i < n && t < p.T;
+                    if (live) rawt[(size_t)t * SPT + sl] = (int16_t)sc;
+                    // queue A appends: slots are reserved kFixChunk at a time (one global atomic per
+                    // chunk instead of one round trip per pass)
+                    const unsigned ma = __ballot_sync(0xffffffffu, live && fx.kind == 1);
+                    if (ma) {
+                        const int cnt = __popc(ma), rank = __popc(ma & ((1u << lane) - 1u));
+                        unsigned nbase = 0;
+                        if (cnt > fleft) {
+                            if (lane == 0) nbase = atomicAdd(p.qcnt + 8 + region, (unsigned)kFixChunk);
+                            nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                        }
+                        if (live && fx.kind == 1) {
+                            const unsigned idx = rank < fleft ? fbase + rank : nbase + (rank - fleft);
+                            if (idx < p.capA) p.qa[(size_t)region * p.capA + idx] = make_uint4((uint32_t)t, (uint32_t)(nt * SPT + sl), fx.s01, fx.s23);
+                            else p.qcnt[2] = 1u;
+                        }
+                        if (cnt > fleft) { fbase = nbase + (cnt - fleft); fleft = kFixChunk - (cnt - fleft); }
+                        else { fbase += cnt; fleft -= cnt; }
+                    }
+                    if (live && fx.kind == 2) fix_append(p, fx, (uint32_t)t, (uint32_t)(nt * SPT + sl));
+                }
+                if (hw == 0 && lane == 0 && n) atomicAdd(p.qcnt + 4, (unsigned)n);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(Q_EMPTY + buf));
+            }
+        }
+        // the unused rest of the last reservation: null items (tc_fix_a_kernel skips them)
+        for (int k = lane; k < fleft; k += 32)
+            if (fbase + k < p.capA) p.qa[(size_t)region * p.capA + fbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);
     } else {
         // ===================== epilogue (16 warps) =====================
         // Warp w may read TMEM lanes 32*(w%4)..+31 only; the four warps of a lane
@@ -528,43 +795,46 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         // thread pulls its 64 columns into registers, releases the accumulator
         // at once (the MMA warp can start the tile after next) and only then
         // does the selection / log-add arithmetic.
-        constexpr int CPT = kColsPerEpiThread;           // columns per thread
+        constexpr int CPT = kTileN / (EW / 4);           // columns per thread (64, or 128 with hard-path warps)
         constexpr int SPE = CPT / M;                     // senones per thread
         const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..511
         const int q = warp & 3;
         const int cg = (warp - kFirstEpiWarp) >> 2;      // column group 0..3
+        const int ew = warp - kFirstEpiWarp;
         const int row = q * 32 + lane;                   // frame row in the tile
         int acc = 0; uint32_t accphase = 0;
+        uint32_t qt = 0;
         const int32_t m31 = p.m31;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
             if (OTHER_FORMAT(nt)) continue;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
             if (MODE == 0) {
-                epi_bar();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");
                 if (et < kTileN) {
                     // stored reversed inside each senone so that key & 31 indexes it directly
                     const int sl = et / M, dens = et % M;
                     sMixw[sl * M + (M - 1 - dens)] = p.gMixw[(size_t)nt * kTileN + et];
+                    const float c = p.gCw[(size_t)nt * kTileN + et];
+                    sCw[sl * (M + 4) + dens] = c;
+                    sC2[et] = fmaxf(kWinV, c + kDeltaV) * kBig;
                 }
-                epi_bar();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");
             }
             int16_t *rawt = MODE == 0 ? p.raw + (size_t)nt * p.T_pad * SPT : nullptr;
             uint4 *partt = MODE == 1 ? p.part + (size_t)nt * p.T_pad * 4 : nullptr;
-            // key & 31 = 31 - id = (32 - M) + (M - 1 - id): bias the table pointer for M < 32
-            const uint8_t *mixw_t = sMixw + cg * CPT - (32 - M);
-            for (int mt = mt0; mt < mt1; ++mt) {
+            for (int mt = mt0; mt < mt1; ++mt, ++qt) {
                 mbar_wait(BAR(T_FULL + acc), accphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + cg * CPT);
-                uint32_t v0[32], v1[32];
-                tmem_ld32(taddr, v0);
-                tmem_ld32(taddr + 32, v1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
                 if (MODE == 1) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr, v0);
+                    tmem_ld32(taddr + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
                     // keys carry a 6-bit id (63 - column within the thread's 64)
                     int32_t ta[4], tb[4];
 #pragma unroll
@@ -585,39 +855,90 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     if (++acc == 2) { acc = 0; accphase ^= 1; }
                     continue;
                 }
-                int16_t res[SPE];
-                if (p.dbg & 1) {
-#pragma unroll
-                    for (int k = 0; k < SPE; ++k) res[k] = (int16_t)(v0[k] ^ v1[k]);
-                } else
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const uint32_t (&v)[32] = c ? v1 : v0;
-#pragma unroll
-                    for (int s = 0; s < 32 / M; ++s) {   // senones inside the 32-column chunk
-                        int32_t top[4];
-                        top[0] = make_key(v[s * M + 0], 0, m31); top[1] = make_key(v[s * M + 1], 1, m31);
-                        top[2] = make_key(v[s * M + 2], 2, m31); top[3] = make_key(v[s * M + 3], 3, m31);
-                        sort4(top[0], top[1], top[2], top[3]);
-#pragma unroll
-                        for (int g = 4; g < M; g += 4)
-                            merge4(top, make_key(v[s * M + g], g, m31), make_key(v[s * M + g + 1], g + 1, m31),
-                                   make_key(v[s * M + g + 2], g + 2, m31), make_key(v[s * M + g + 3], g + 3, m31));
-                        const int sl = c * (32 / M) + s;                  // senone within this thread's columns
-                        res[sl] = (int16_t)senone_from_keys(top, mixw_t + sl * M, sTab, p.aw);
-                    }
-                }
+                // ---- MODE 0: certificate per senone; the rest is queued (or finished in place)
+                const int buf = qt & 1;
+                if (HW) mbar_wait(BAR(Q_EMPTY + buf), ((qt >> 1) & 1) ^ 1);     // the buffer's previous tile has been consumed
+                uint32_t *qbuf = sQ + buf * (kQueueBytes / 4);
                 const int t = mt * kTileM + row;
-                if (t < p.T) {
-                    int16_t *dst = rawt + (size_t)t * SPT + cg * SPE;
-                    if (SPE == 2) {
-                        *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(res);
-                    } else if (SPE == 4) {
-                        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(res);
-                    } else {
+                // One 32-column chunk per iteration, NOT unrolled: the loop body must stay in the
+                // instruction cache next to the other warp roles' code.
+                constexpr int SPC = 32 / M;                                     // senones per chunk
+                unsigned long long pack = 0;                                    // M == 32: the thread's scores, 16 bits each
+                int qn = 0;                                                     // hard pairs of this warp in this tile
+                auto chunk = [&](const int c, const uint32_t (&v)[32]) {
+                    int16_t res[SPC];
 #pragma unroll
-                        for (int k = 0; k < SPE; k += 8)
-                            *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(res + k);
+                    for (int s = 0; s < SPC; ++s) {      // senones inside the 32-column chunk
+                        const int st = cg * SPE + c * SPC + s;            // senone within the tile
+                        int32_t sc;
+                        bool easy = easy_eval<M>(&v[s * M], sC2 + st * M, p.aw, p.eps0, p.eps_shift, sc);
+                        if (p.dbg & 4) easy = false;
+                        if ((p.dbg & 1) || nt * SPT + st >= p.n_sen) easy = true;     // (padding senones of the last tile)
+                        const unsigned hm = __ballot_sync(0xffffffffu, !easy);
+                        if (hm) {
+                            // the warp's own slice of the tile's buffer: no atomics, a register counter
+                            const int slot = HW ? qn + __popc(hm & ((1u << lane) - 1u)) : QSL;
+                            qn += __popc(hm);
+                            if (!easy) {
+                                if (slot < QSL) {
+                                    uint32_t *it = qbuf + (size_t)(ew * QSL + slot) * QS;
+#pragma unroll
+                                    for (int j = 0; j < M; j += 4)
+                                        *reinterpret_cast<uint4 *>(it + j) = make_uint4(v[s * M + j], v[s * M + j + 1], v[s * M + j + 2], v[s * M + j + 3]);
+                                    it[M] = (uint32_t)row | ((uint32_t)st << 8);
+                                } else {
+                                    // no queue (or it is full): finish here
+                                    uint32_t w[M];
+#pragma unroll
+                                    for (int j = 0; j < M; ++j) w[j] = v[s * M + j];
+                                    FixOut fx;
+                                    sc = hard_eval<M>(w, sCw + st * (M + 4), sMixw + st * M - (32 - M), sTab, p.aw, p.eps0,
+                                                      p.eps_shift, m31, fx);
+                                    if (fx.kind && t < p.T) fix_append(p, fx, (uint32_t)t, (uint32_t)(nt * SPT + st));
+                                    if (HW) atomicAdd(p.qcnt + 5, 1u);      // statistic: the tile's queue was full
+                                    easy = true;
+                                }
+                            }
+                        }
+                        res[s] = (int16_t)sc;
+                    }
+                    if (M == 32) {
+                        pack |= (unsigned long long)(uint16_t)res[0] << (16 * c);
+                    } else if (t < p.T) {
+                        // chunk-wise stores; the hard-path warps write what is not final here
+                        // (queued pairs: placeholders, overwritten by the hard-path warps after the hand-over)
+                        int16_t *dst = rawt + (size_t)t * SPT + cg * SPE + c * SPC;
+                        if (SPC == 2) *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(res);
+                        else *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(res);
+                    }
+                };
+                // (prefetching the next chunk into a second register set spills at 80 registers: measured slower)
+#pragma unroll 1
+                for (int c = 0; c < CPT / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32 * c, v);
+                    tmem_ld_wait();
+                    if (c == CPT / 32 - 1) {
+                        // last load done: the accumulator may be overwritten
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+                    }
+                    chunk(c, v);
+                }
+                if (M == 32 && t < p.T) {
+                    // One vector store of the thread's scores, BEFORE the queue hand-over: the entries
+                    // of queued pairs are placeholders that the hard-path warps overwrite afterwards
+                    // (ordered by the mbarrier's release / acquire).
+                    int16_t *dst = rawt + (size_t)t * SPT + cg * SPE;
+                    if (CPT == 64) *reinterpret_cast<uint32_t *>(dst) = (uint32_t)pack;
+                    else *reinterpret_cast<unsigned long long *>(dst) = pack;
+                }
+                if (HW) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        sQn[buf * EW + ew] = (uint32_t)min(qn, QSL);
+                        mbar_arrive(BAR(Q_FULL + buf));
                     }
                 }
                 if (++acc == 2) { acc = 0; accphase ^= 1; }
@@ -717,6 +1038,164 @@ tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, i
     }
 }
 
+
+// ------------------------------------------------------------- exact fix-ups
+// The reference's float32 distance of density `id` of codebook `s` (single stream):
+// ms_gauden.c:417-445, sequential in i, every operation rounded separately.
+// `rows`: 16-byte aligned copy of the parameters, [codebook * n_density + id][mean Dp | scaled 1/(2 var) Dp]
+// with Dp = D rounded up to 4 (one 16-byte gather per 4 dimensions).
+template <int DC>
+__device__ __forceinline__ float exact_dist_n(const GmmDev &g, const float4 *__restrict__ rows, const float *__restrict__ x,
+                                              int s, int id, int D) {
+    const int q = (D + 3) >> 2;
+    const float4 *__restrict__ rp = rows + ((size_t)s * g.n_density + id) * (2 * q);
+    float d = __ldg(g.det + (size_t)s * g.n_density + id);
+    constexpr int QC = (DC + 3) / 4;
+    if (DC > 0) {
+#pragma unroll
+        for (int i4 = 0; i4 < QC; ++i4) {
+            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + QC + i4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i4 * 4 + e < DC) {
+                    const float diff = __fsub_rn(__ldg(x + i4 * 4 + e), mm[e]);
+                    d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
+                }
+        }
+    } else {
+        for (int i4 = 0; i4 < q; ++i4) {
+            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i4 * 4 + e < D) {
+                    const float diff = __fsub_rn(__ldg(x + i4 * 4 + e), mm[e]);
+                    d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
+                }
+        }
+    }
+    return d;
+}
+__device__ __forceinline__ float exact_dist(const GmmDev &g, const float4 *rows, const float *x, int s, int id) {
+    const int D = g.featlen[0];
+    if (D == 39) return exact_dist_n<39>(g, rows, x, s, id, D);
+    return exact_dist_n<0>(g, rows, x, s, id, D);
+}
+
+__device__ __forceinline__ int32_t exact_chain(const GmmDev &g, const int32_t (&fw)[4], int n) {
+    int32_t f = fw[0];
+    for (int j = 1; j < n; ++j) f = logadd_tab(g.logadd, f, fw[j]);
+    int32_t scr = -f;
+    if (g.aw != 1) scr /= g.aw;
+    return clamp16(scr);
+}
+
+// Queue A: the set and the order of the top 4 are certain, but some density's
+// fden = ((int32)d + 1023) >> 10 is not.  A settled slot carries fden - mixw, an
+// open one the density id.  One item per lane; the open slots of the warp's 32
+// items (about one per item) are compacted through shared memory so that every
+// lane of the exact-distance loop has work.
+__global__ void __launch_bounds__(256)
+tc_fix_a_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ rows, const float *__restrict__ feat, int T_pad, int spt,
+                const uint4 *__restrict__ qa, unsigned capA, unsigned *__restrict__ qcnt, int16_t *__restrict__ raw,
+                int eps0, int eps_shift) {
+    if (qcnt[2]) return;                                   // overflow: queue B's kernel redoes everything
+    __shared__ uint16_t s_work[8][128];                    // per warp: (lane << 2) | slot of every open slot
+    __shared__ int32_t s_fw[8][32][4];
+    const int region = blockIdx.y;
+    const unsigned n = min(qcnt[8 + region], capA);
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    unsigned maxerr = 0;
+    // 28 items per warp and round: their open slots (about 1.1 per item) then mostly fit one 32-lane pass
+    constexpr unsigned kBatch = 28;
+    for (unsigned i0 = (blockIdx.x * 8 + wp) * kBatch; i0 < n; i0 += gridDim.x * 8 * kBatch) {
+        const unsigned i = i0 + lane;
+        uint4 it = (lane < kBatch && i < n) ? qa[(size_t)region * capA + i] : make_uint4(0xffffffffu, 0, 0, 0);
+        const bool live = it.x != 0xffffffffu;          // (null items pad the warps' reservations)
+        // compact the open slots
+        int n_open = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t slot = ((c < 2 ? it.z : it.w) >> (16 * (c & 1))) & 0xffffu;
+            const bool open = live && (slot & 0x8000u);
+            const unsigned m = __ballot_sync(0xffffffffu, open);
+            if (open) s_work[wp][n_open + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((lane << 2) | c);
+            if (!open) s_fw[wp][lane][c] = (int32_t)(slot << 17) >> 17;                // 15-bit two's complement
+            n_open += __popc(m);
+        }
+        __syncwarp();
+        for (int k0 = 0; k0 < n_open; k0 += 32) {
+            const int k = k0 + lane;
+            const int wk = s_work[wp][min(k, n_open - 1)];
+            const int src = wk >> 2, c = wk & 3;
+            const int t = (int)__shfl_sync(0xffffffffu, it.x, src), sn = (int)__shfl_sync(0xffffffffu, it.y, src);
+            const uint32_t z = __shfl_sync(0xffffffffu, it.z, src), w = __shfl_sync(0xffffffffu, it.w, src);
+            if (k < n_open) {
+                const uint32_t slot = ((c < 2 ? z : w) >> (16 * (c & 1))) & 0xffffu;
+                const int id = slot & 31;
+                const float d = exact_dist(g, rows, feat + (size_t)t * g.veclen, sn, id);
+                const int32_t di = (int32_t)d;
+                s_fw[wp][src][c] = ((di + ((1 << kShift) - 1)) >> kShift) - (int32_t)g.mixw_t[(size_t)id * g.n_sen + sn];
+                // |GEMM - reference| on this density, from the 10 low bits the item kept of floor(-d~)
+                const int32_t err = abs(((((-di) - (int32_t)((slot >> 5) & 0x3ff) + 512) & 1023) - 512));
+                maxerr = max(maxerr, (unsigned)err);
+                // Safety net: the certificates assumed |error| <= eps0 + (|d| >> eps_shift).  These
+                // re-scored densities are a 1-2 % sample of all; when one of them uses more than
+                // half of that bound the whole batch is redone by the literal scan.
+                if (2 * err > eps0 + (abs(di) >> eps_shift)) qcnt[2] = 1u;
+            }
+        }
+        __syncwarp();
+        if (live) {
+            int32_t f4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f4[j] = s_fw[wp][lane][j];
+            const int t = (int)it.x, sn = (int)it.y;
+            raw[((size_t)(sn / spt) * T_pad + t) * spt + sn % spt] = (int16_t)exact_chain(g, f4, 4);
+        }
+        __syncwarp();
+    }
+    maxerr = __reduce_max_sync(0xffffffffu, maxerr);
+    if (lane == 0 && maxerr > 2 && maxerr > qcnt[3]) atomicMax(qcnt + 3, maxerr);
+}
+
+// Queue B: near-ties among the top 5 (or a duplicated density): the literal
+// evaluation of the senone -- every density exactly, the top N in the reference's
+// order (descending d, the later density first on equal d: ms_gauden.c:505-520).
+// One warp per item, lane = density.  After a queue overflow: every (frame, senone).
+__global__ void __launch_bounds__(256)
+tc_fix_b_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ rows, const float *__restrict__ feat, int T, int T_pad, int spt,
+                const uint2 *__restrict__ qb, unsigned capB, const unsigned *__restrict__ qcnt,
+                int16_t *__restrict__ raw) {
+    const bool all = qcnt[2] != 0;
+    const unsigned long long n = all ? (unsigned long long)T * g.n_sen : min(qcnt[1], capB);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) {
+        int t, s;
+        if (all) { t = (int)(i / g.n_sen); s = (int)(i % g.n_sen); }
+        else { const uint2 it = qb[i]; t = (int)it.x; s = (int)it.y; }
+        if (s >= g.n_sen || t >= T) continue;
+        float d = lane < g.n_density ? exact_dist(g, rows, feat + (size_t)t * g.veclen, s, lane) : 0.f;
+        bool in = lane < g.n_density;
+        int32_t fw[4];
+        for (int r = 0; r < 4; ++r) {
+            // warp arg-max over (d, id): larger d, then larger id
+            float bd = d; int bi = in ? lane : -1;
+            for (int o = 16; o; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || od > bd || (od == bd && oi > bi))) { bd = od; bi = oi; }
+            }
+            const int32_t di = (int32_t)bd;
+            fw[r] = ((di + ((1 << kShift) - 1)) >> kShift) - (int32_t)g.mixw_t[(size_t)max(bi, 0) * g.n_sen + s];
+            if (lane == bi) in = false;
+        }
+        if (lane == 0) raw[((size_t)(s / spt) * T_pad + t) * spt + s % spt] = (int16_t)exact_chain(g, fw, 4);
+    }
+}
+
 // host-side TF32 rounding (round to nearest, ties away, like cvt.rna.tf32.f32)
 float tf32_round(float x) {
     uint32_t u;
@@ -729,12 +1208,13 @@ float tf32_round(float x) {
 }
 
 // Columns of one Gaussian's B row, times -32 (see make_key), in double:
-// col[0] = the whole constant det - sum mu^2 v, col[2+2i] = -v_i, col[3+2i] = 2 mu_i v_i.
-// mu == nullptr: a padding Gaussian far below anything real.
-void b_row_cols(std::vector<double> &col, int KP, int D, const float *mu, const float *v, float det) {
+// col[0] = the whole constant det - sum mu^2 v (- 1024 mixw for the fully
+// continuous path, whose accumulator is w = -32 (d - 1024 mixw)), col[2+2i] = -v_i,
+// col[3+2i] = 2 mu_i v_i.  mu == nullptr: a padding Gaussian far below anything real.
+void b_row_cols(std::vector<double> &col, int KP, int D, const float *mu, const float *v, float det, int mixw = 0) {
     col.assign(KP, 0.0);
     if (!mu) { col[0] = 3.0e7 * kAccScale; return; }
-    double c = (double)det;
+    double c = (double)det - 1024.0 * (double)mixw;
     for (int i = 0; i < D; ++i) {
         c -= (double)mu[i] * (double)mu[i] * (double)v[i];
         col[2 + 2 * i] = -(double)v[i];
@@ -746,10 +1226,10 @@ void b_row_cols(std::vector<double> &col, int KP, int D, const float *mu, const 
 
 // TF32 hi/lo row in the [kstep(8 cols)][hi|lo][chunk][256 rows][4 f32] layout;
 // the constant is spread over columns 0 and 1 (4 x 11 bits).
-void build_b_row(float *tile, int r, int ksteps, int D, const float *mu, const float *v, float det) {
+void build_b_row(float *tile, int r, int ksteps, int D, const float *mu, const float *v, float det, int mixw = 0) {
     const int KP = ksteps * 8;
     std::vector<double> col;
-    b_row_cols(col, KP, D, mu, v, det);
+    b_row_cols(col, KP, D, mu, v, det, mixw);
     const double c = col[0];
     const double hi1 = tf32_round((float)c), lo1 = mu ? tf32_round((float)(c - hi1)) : 0.0;
     const double c2 = mu ? c - hi1 - lo1 : 0.0;
@@ -769,10 +1249,10 @@ void build_b_row(float *tile, int r, int ksteps, int D, const float *mu, const f
 // fp16 hi/lo row in the [kstep(16 cols)][hi|lo][chunk][256 rows][8 f16] layout
 // (the same bytes per stage); column k is stored times 2^-e[k].
 void build_b_row_half(__half *tile, int r, int ksteps, int D, const float *mu, const float *v, float det,
-                      const int *e) {
+                      const int *e, int mixw = 0) {
     const int KP = ksteps * 16;
     std::vector<double> col;
-    b_row_cols(col, KP, D, mu, v, det);
+    b_row_cols(col, KP, D, mu, v, det, mixw);
     auto put = [&](int k, double val) {
         const __half hi = __float2half_rn((float)val);
         const __half lo = __float2half_rn((float)(val - (double)__half2float(hi)));
@@ -815,7 +1295,7 @@ bool half_enabled() {
     return !(e && atoi(e) == 0);
 }
 
-// rows(tile, r, mu, v, det) -> false for a padding row.
+// rows(tile, r, mu, v, det, mixw) -> false for a padding row.
 template <typename RowFn>
 bool build_half_operand(HalfOperand &h, int n_tiles_n, int D, RowFn rows) {
     h.ksteps = half_ksteps(D);
@@ -832,9 +1312,9 @@ bool build_half_operand(HalfOperand &h, int n_tiles_n, int D, RowFn rows) {
     for (int nt = 0; nt < n_tiles_n; ++nt) {
         std::fill(colmax.begin(), colmax.end(), 0.0);
         for (int r = 0; r < kTileN; ++r) {
-            const float *mu, *v; float det;
-            const bool real = rows(nt, r, mu, v, det);
-            b_row_cols(col, KP, D, real ? mu : nullptr, v, det);
+            const float *mu, *v; float det; int mw = 0;
+            const bool real = rows(nt, r, mu, v, det, mw);
+            b_row_cols(col, KP, D, real ? mu : nullptr, v, det, mw);
             for (int k = 0; k < KP; ++k) colmax[k] = std::max(colmax[k], std::fabs(col[k]));
         }
         // B column k times 2^-e[k] peaks in (2^14, 2^15]; the A column carries 2^e[k],
@@ -855,9 +1335,9 @@ bool build_half_operand(HalfOperand &h, int n_tiles_n, int D, RowFn rows) {
         }
         n_usable += fits ? 1 : 0;
         for (int r = 0; r < kTileN; ++r) {
-            const float *mu, *v; float det;
-            const bool real = rows(nt, r, mu, v, det);
-            if (fits) build_b_row_half(B.data() + (size_t)nt * tile_halves, r, h.ksteps, D, real ? mu : nullptr, v, det, e.data());
+            const float *mu, *v; float det; int mw = 0;
+            const bool real = rows(nt, r, mu, v, det, mw);
+            if (fits) build_b_row_half(B.data() + (size_t)nt * tile_halves, r, h.ksteps, D, real ? mu : nullptr, v, det, e.data(), mw);
         }
     }
     if (n_usable == 0) { h.ksteps = 0; return false; }
@@ -886,6 +1366,15 @@ struct TcPlan {
     int n_sm = 148;
     int aw = 1;
     uint8_t logadd[256];
+    // round 2: exact fix-up of the pairs the score kernel could not settle
+    GmmDev g{};                                  // device pointers of the reference-layout parameters
+    float *dCw = nullptr;                        // [n_tiles_n][256] 32*1024*mixw per tile row
+    float4 *dRows = nullptr;                     // [S*M][mean Dp | var Dp] 16-byte aligned rows for the exact re-scoring gathers
+    uint4 *dQa = nullptr; size_t qa_cap = 0;     // items per region
+    uint2 *dQb = nullptr; size_t qb_cap = 0;     // items
+    unsigned *dQcnt = nullptr;                   // [8 + kFixRegionsMax]
+    int eps0 = 5, eps_shift = 18;
+    long long last_T = 0;
 };
 
 bool tc_shape_supported(const GmmDev &g) {
@@ -900,6 +1389,7 @@ void tc_plan_free(TcPlan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dAh); cudaFree(p->dRaw);
+    cudaFree(p->dCw); cudaFree(p->dRows); cudaFree(p->dQa); cudaFree(p->dQb); cudaFree(p->dQcnt);
     p->half.release();
     delete p;
 }
@@ -922,17 +1412,23 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     p->n_tiles_n = (p->S + p->spt - 1) / p->spt;
     memcpy(p->logadd, g.logadd, 256);
     const int M = p->M, D = p->D;
+    p->g = g;
+    { const char *e = getenv("B200_TC_EPS0"); if (e) p->eps0 = std::max(2, atoi(e)); }
+    { const char *e = getenv("B200_TC_EPS_SHIFT"); if (e) p->eps_shift = std::max(8, std::min(30, atoi(e))); }
     const size_t tile_floats = (size_t)p->ksteps * (kBStageBytes / 4);
     std::vector<float> B((size_t)p->n_tiles_n * tile_floats, 0.f);
     std::vector<uint8_t> mw((size_t)p->n_tiles_n * kTileN, 0);
+    std::vector<float> cw((size_t)p->n_tiles_n * kTileN, 0.f);
     for (int nt = 0; nt < p->n_tiles_n; ++nt)
         for (int r = 0; r < kTileN; ++r) {
             const int s = nt * p->spt + r / M, dens = r % M;
             float *tile = B.data() + (size_t)nt * tile_floats;
             if (s < p->S) {
+                const int q = h_mixw[(size_t)s * M + dens];
                 build_b_row(tile, r, p->ksteps, D, h_mean + ((size_t)s * M + dens) * D, h_var + ((size_t)s * M + dens) * D,
-                            h_det[(size_t)s * M + dens]);
-                mw[(size_t)nt * kTileN + r] = h_mixw[(size_t)s * M + dens];
+                            h_det[(size_t)s * M + dens], q);
+                mw[(size_t)nt * kTileN + r] = (uint8_t)q;
+                cw[(size_t)nt * kTileN + r] = kAccScale * 1024.f * (float)q;
             } else {
                 build_b_row(tile, r, p->ksteps, D, nullptr, nullptr, 0.f);
             }
@@ -940,16 +1436,35 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaMalloc((void **)&p->dB, B.size() * 4) != cudaSuccess ||
         cudaMalloc((void **)&p->dMixw, mw.size()) != cudaSuccess ||
+        cudaMalloc((void **)&p->dCw, cw.size() * 4) != cudaSuccess ||
+        cudaMalloc((void **)&p->dQcnt, (8 + kFixRegionsMax) * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(p->dQcnt, 0, (8 + kFixRegionsMax) * sizeof(unsigned)) != cudaSuccess ||
         cudaMemcpy(p->dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->dCw, cw.data(), cw.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(p->dMixw, mw.data(), mw.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("tensor-core plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         tc_plan_free(p);
         return nullptr;
     }
-    build_half_operand(p->half, p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det) {
+    {
+        const int Dp = (D + 3) & ~3;
+        std::vector<float> R((size_t)p->S * M * 2 * Dp, 0.f);
+        for (size_t r = 0; r < (size_t)p->S * M; ++r) {
+            memcpy(R.data() + r * 2 * Dp, h_mean + r * D, D * sizeof(float));
+            memcpy(R.data() + r * 2 * Dp + Dp, h_var + r * D, D * sizeof(float));
+        }
+        if (cudaMalloc((void **)&p->dRows, R.size() * 4) != cudaSuccess ||
+            cudaMemcpy(p->dRows, R.data(), R.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("tensor-core plan allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            tc_plan_free(p);
+            return nullptr;
+        }
+    }
+    build_half_operand(p->half, p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det, int &q) {
         const int s = nt * p->spt + r / M, dens = r % M;
-        if (s >= p->S) { mu = v = nullptr; det = 0.f; return false; }
+        if (s >= p->S) { mu = v = nullptr; det = 0.f; q = 0; return false; }
         mu = h_mean + ((size_t)s * M + dens) * D; v = h_var + ((size_t)s * M + dens) * D; det = h_det[(size_t)s * M + dens];
+        q = h_mixw[(size_t)s * M + dens];
         return true;
     });
     return p;
@@ -957,13 +1472,14 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
 
 template <int M, int KS, int MODE, int HALF>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
-    const size_t smem = (size_t)KS * kBStageBytes + (size_t)ring_depth(KS) * kAStageBytes +
-                        (size_t)(HALF ? 8 : 4) * KS * kTileM * 4 + 512 + 320 + 32 * 8 + 16;
+    // the hard-path warps and their queue where the B tile leaves room for them
+    constexpr int HW = (MODE == 0 && score_smem_bytes(KS, HALF, kHardWarps) <= 227 * 1024) ? kHardWarps : 0;
+    constexpr size_t smem = score_smem_bytes(KS, HALF, HW);
     static AttrOnce attr;
     if (attr.need()) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE, HALF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    tc_score_kernel<M, KS, MODE, HALF><<<grid, kThreads, smem, st>>>(prm);
+    tc_score_kernel<M, KS, MODE, HALF, HW><<<grid, score_threads(HW), smem, st>>>(prm);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -1059,6 +1575,24 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     memcpy(prm.logadd, p->logadd, 256);
     const int grid = std::min(prm.n_units, p->n_sm);
     *T_pad_out = T_pad;
+    // fix-up queues: A holds up to 1/8 of all pairs (split into one region per CTA), B 1/64
+    const size_t pairs = (size_t)T_pad * p->S;
+    const size_t capA = std::max<size_t>(4096, pairs / 8 / grid), capB = std::max<size_t>(65536, pairs / 64);
+    if (p->qa_cap < capA) {
+        cudaFree(p->dQa); p->dQa = nullptr; p->qa_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&p->dQa, capA * kFixRegionsMax * sizeof(uint4)));
+        p->qa_cap = capA;
+    }
+    if (p->qb_cap < capB) {
+        cudaFree(p->dQb); p->dQb = nullptr; p->qb_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&p->dQb, capB * sizeof(uint2)));
+        p->qb_cap = capB;
+    }
+    B200_CUDA_OK(cudaMemsetAsync(p->dQcnt, 0, (8 + kFixRegionsMax) * sizeof(unsigned), st));
+    prm.gCw = p->dCw; prm.qa = p->dQa; prm.qb = p->dQb; prm.qcnt = p->dQcnt;
+    prm.capA = (unsigned)p->qa_cap; prm.capB = (unsigned)p->qb_cap;
+    prm.eps0 = p->eps0; prm.eps_shift = p->eps_shift;
+    p->last_T = T;
     int rc = B200_OK;
     if (p->half.ksteps) {
         // fp16 operands first; the TF32 kernel below returns at once unless a feature overflowed fp16
@@ -1074,12 +1608,32 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
         prm.fmt = p->half.dFmt;
     }
     switch (p->M) {
-        case 8: return launch_score_ks<8, 0>(prm, p->ksteps, grid, st);
-        case 16: return launch_score_ks<16, 0>(prm, p->ksteps, grid, st);
-        case 32: return launch_score_ks<32, 0>(prm, p->ksteps, grid, st);
+        case 8: rc = launch_score_ks<8, 0>(prm, p->ksteps, grid, st); break;
+        case 16: rc = launch_score_ks<16, 0>(prm, p->ksteps, grid, st); break;
+        case 32: rc = launch_score_ks<32, 0>(prm, p->ksteps, grid, st); break;
+        default: set_error("tensor-core path: n_density %d unsupported", p->M); return B200_ERR_UNSUP;
     }
-    set_error("tensor-core path: n_density %d unsupported", p->M);
-    return B200_ERR_UNSUP;
+    if (rc) return rc;
+    if (prm.dbg & 8) return B200_OK;      // development: leave the queued pairs un-fixed
+    tc_fix_a_kernel<<<dim3(8, grid), 256, 0, st>>>(p->g, p->dRows, d_feat, T_pad, p->spt, p->dQa, prm.capA, p->dQcnt, p->dRaw, p->eps0, p->eps_shift);
+    B200_LAUNCH_CHECK();
+    tc_fix_b_kernel<<<p->n_sm * 4, 256, 0, st>>>(p->g, p->dRows, d_feat, T, T_pad, p->spt, p->dQb, prm.capB, p->dQcnt, p->dRaw);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// {frames x senones of the last call, pairs that took the hard path, queue A items,
+//  queue B items, queue overflow (everything redone exactly), largest |GEMM - reference|
+//  distance seen on a re-scored density (raw log units; 0 if <= 2)}   (synchronises)
+int tc_last_stats(TcPlan *p, long long out[7]) {
+    for (int i = 0; i < 7; ++i) out[i] = 0;
+    if (!p) return 0;
+    std::vector<unsigned> c(8 + kFixRegionsMax);
+    cudaSetDevice(p->device);
+    if (cudaMemcpy(c.data(), p->dQcnt, c.size() * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    out[0] = p->last_T * p->S; out[1] = c[4] + c[5]; out[3] = c[1]; out[4] = c[2]; out[5] = c[3]; out[6] = c[5];
+    for (int r = 0; r < kFixRegionsMax; ++r) out[2] += c[8 + r];
+    return 0;
 }
 
 // 1: every n-tile of the last tc_score_raw ran on fp16 operands, 0: none did (no fp16
@@ -1438,7 +1992,7 @@ TcTied *tc_tied_create(const GmmDev &g, int mode, const float *h_mean, const flo
         ok = ok && cudaMalloc((void **)&p->dRows[f], R.size() * 4) == cudaSuccess &&
              cudaMemcpy(p->dRows[f], R.data(), R.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
         if (ok)
-            build_half_operand(p->half[f], p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det) {
+            build_half_operand(p->half[f], p->n_tiles_n, D, [&](int nt, int r, const float *&mu, const float *&v, float &det, int &) {
                 const int mg = nt / p->tpc, c = (nt % p->tpc) * kTileN + r;
                 const size_t pbase = (size_t)mg * g.n_density * g.veclen + (size_t)g.n_density * g.featoff[f];
                 mu = h_mean + pbase + (size_t)c * D; v = h_var + pbase + (size_t)c * D;

@@ -229,6 +229,14 @@ class Mgau:
         self.tied_max_err = int(out[2])
         return int(out[0]), int(out[1])
 
+    def cont_stats(self) -> dict:
+        """Last tensor-core scoring call of a fully continuous ms back-end
+        (include/b200sphinx.h: b200_mgau_cont_stats)."""
+        out = (C.c_longlong * 7)()
+        check(lib.b200_mgau_cont_stats(self._h, out), "cont_stats")
+        k = ("pairs", "hard_pairs", "rescored_pairs", "rescanned_pairs", "overflow", "max_gemm_err", "hard_pairs_in_place")
+        return dict(zip(k, (int(v) for v in out)))
+
     # vt->free
     def free(self):
         if self._h:

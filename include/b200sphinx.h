@@ -208,6 +208,19 @@ int  b200_mgau_tc_last_format(b200_mgau_t *m);
  * distance observed on a best candidate in raw log units (0 if <= 4)} of the
  * last scoring call. */
 int  b200_mgau_tied_stats(b200_mgau_t *m, long long out[3]);
+/* ms tensor-core path (fully continuous models), last scoring call:
+ * {frame x senone pairs scored, pairs that took the full top-N network (the
+ * rest were settled by the single-density certificate), pairs whose fden had to
+ * be re-derived from the reference's float32 distance (queue A), pairs whose
+ * top-N set or order was re-derived by the literal scan (queue B), 1 if a queue
+ * overflowed and every pair was redone by the literal scan, largest
+ * |GEMM - reference| distance seen on a re-scored density in raw log units (0
+ * if <= 2; the certificates assume eps0 + (|d| >> eps_shift), see
+ * B200_TC_EPS0 / B200_TC_EPS_SHIFT), hard pairs finished by the finding lane
+ * because the tile's queue was full}.  Every score of this path is bit-identical
+ * to ms_cont_mgau_frame_eval's as long as the last entry stays below that
+ * bound.  Synchronises. */
+int  b200_mgau_cont_stats(b200_mgau_t *m, long long out[7]);
 
 /* Batched dense scoring == ps_mgau_frame_eval(..., compallsen=1) for frames
  * 0..T-1 (PS/ms_mgau.c:162-205, PS/ptm_mgau.c:405-450,

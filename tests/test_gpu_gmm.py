@@ -130,6 +130,11 @@ def test_real_continuous_model_exact(name):
     d = cases.model_dir(name)
     m = b.ms_from_files(d + "/means", d + "/variances", d + "/mixture_weights", ".cont.", topn=int(g["topn"]),
                         logbase=orc.LOGBASE)
+    if int(g["topn"]) == 4:
+        # the default (tcgen05) path on real speech frames against the reference's own scores
+        assert m.path == 1
+        np.testing.assert_array_equal(m.score(g["feat"]), g["dense"])
+        assert m.cont_stats()["max_gemm_err"] <= 16
     m.set_path(0)
     np.testing.assert_array_equal(m.score(g["feat"]), g["dense"])
     for i in range(g["act_scores"].shape[0]):
@@ -286,8 +291,7 @@ def test_config2_shape_subset_exact():
         got = m.score(feat)
         diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
         print(f"tensor-core path: mismatch fraction {(diff != 0).mean():.2e}, max |d| {diff.max()}")
-        assert diff.max() <= 1
-        assert (diff != 0).mean() < 2e-2
+        assert diff.max() == 0
     m.free()
 
 
@@ -317,12 +321,12 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("S,M,D,T", [(64, 32, 39, 300), (250, 8, 39, 515), (100, 16, 13, 129), (37, 32, 20, 77),
                                      (4999, 32, 39, 130)])
-def test_tensor_core_path_within_one_of_exact(S, M, D, T):
-    """tcgen05 path (TF32x3 + integer-key epilogue) against the exact path, which is
-    itself bit-exact against the oracle: max |d| <= 1 (north_star tolerance), and
-    the disagreement rate stays at the log-add quantisation noise floor.  Shapes
-    cover all template instantiations (M = 8/16/32, 4/8/10 k-steps), padded
-    tiles, ragged frame counts and an n_sen that forces the generic finish pass."""
+def test_tensor_core_path_identical_to_exact(S, M, D, T):
+    """tcgen05 path (GEMM + certificate / top-4 network + exact fix-ups, round 2)
+    against the exact path, which is itself bit-exact against the oracle:
+    IDENTICAL scores.  Shapes cover all template instantiations (M = 8/16/32,
+    2/4/5 fp16 and 4/7/10 TF32 k-steps), padded tiles, ragged frame counts and an
+    n_sen that forces the generic finish pass."""
     mean, var, mixw = synth.cont_model(S, M, D, 31)
     pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
     q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
@@ -335,7 +339,7 @@ def test_tensor_core_path_within_one_of_exact(S, M, D, T):
     want = m.score(feat)
     diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
     print(f"S={S} M={M} D={D} T={T}: mismatch {float((diff != 0).mean()):.2e} max {diff.max()}")
-    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2
+    assert diff.max() == 0
     if S <= 250:
         pm = orc.PortMs(S, 1, [D], M, S, 4, 1, mean, pv, pd, q, np.arange(S), orc.LOGBASE)
         np.testing.assert_array_equal(want, pm.eval_all(feat))
@@ -344,7 +348,7 @@ def test_tensor_core_path_within_one_of_exact(S, M, D, T):
     m.utt_begin(feat[:40])
     row = np.zeros(S, np.int16)
     m.utt_frame(row, None, 0, 7, True)
-    assert np.abs(row.astype(np.int32) - want[7].astype(np.int32)).max() <= 1
+    np.testing.assert_array_equal(row, want[7])
     m.free()
 
 
@@ -489,30 +493,30 @@ def test_tied_tensor_core_path_identical_to_exact(C, Mden, streams, S, T, kind):
     m.free()
 
 
-def test_config2_tolerance_at_scale():
-    """1e8 scores of BASELINE config 2 (frames 40000..59999 of the sweep in
-    tools/tc_fullscale_check.py): tcgen05 path vs the exact path.  The
-    north_star tolerance (+-1) must hold everywhere except for rank-4/rank-5
-    Gaussian pairs that the reference's OWN float32 rounding orders -- the
-    full 5e8-score sweep has exactly one (frame 43770, senone 3943: two
-    densities 0.4 raw log units apart in the reference's arithmetic, in the
-    other order in exact arithmetic, mixture weights 24 vs 52 -> |d| = 2;
-    profiles/r1_tc_fullscale_parity.json)."""
+def test_config2_identical_at_scale():
+    """1e8 scores of BASELINE config 2 (frames 40000..79999 of the sweep in
+    tools/tc_fullscale_check.py, which includes both pairs the round-1 kernel got
+    wrong by more than 1: frame 43770 / senone 3943 and frame 64372): tcgen05
+    path vs the exact path -- identical, no tolerance, no whitelist.  The
+    run-time monitor of the GEMM error must stay inside the bound the
+    certificates assume (eps0 = 5 raw units at |d| = 0)."""
     n_sen, M, D = 5000, 32, 39
     mean, var, mixw = synth.cont_model(n_sen, M, D, 1234)
     pv, pd = orc.port_precompute(var.reshape(-1, D), D, 1e-4, orc.LOGBASE)
     q = orc.port_mixw_quantize(mixw, 1e-7, orc.LOGBASE)
     cfg = b.MgauConfig(n_sen, 1, M, n_sen, [D], topn=4, logbase=orc.LOGBASE)
     m = b.ms_from_arrays(cfg, mean, pv, pd, q, np.arange(n_sen))
-    feat = synth.cont_features(mean, var, 20000, 5678 + 40000)
-    got = m.score(feat).astype(np.int32)
-    m.set_path(0)
-    want = m.score(feat).astype(np.int32)
-    d = np.abs(got - want)
-    beyond = np.argwhere(d > 1)
-    print(f"mismatch {float((d != 0).mean()):.3e}, beyond tolerance {len(beyond)}, max {d.max()}")
-    assert (d != 0).mean() < 5e-3 and d.max() <= 2
-    assert len(beyond) <= 1 and all((t, s) == (3770, 3943) for t, s in beyond)
+    for t0 in (40000, 60000):
+        feat = synth.cont_features(mean, var, 20000, 5678 + t0)
+        m.set_path(1)
+        got = m.score(feat)
+        st = m.cont_stats()
+        m.set_path(0)
+        want = m.score(feat)
+        print(f"t0 {t0}: differing scores {int((got != want).sum())}; last chunk {st}")
+        np.testing.assert_array_equal(got, want)
+        assert st["overflow"] == 0 and st["max_gemm_err"] <= 6, st
+        assert 0 < st["hard_pairs"] < 0.3 * st["pairs"] and st["rescored_pairs"] < 0.04 * st["pairs"], st
     m.free()
 
 
@@ -535,8 +539,8 @@ def test_tensor_core_fp16_operands_and_tf32_fallback():
     assert m.tc_last_format() == 0
     m.set_path(0)
     want, want_big = m.score(feat), m.score(big)
-    assert np.abs(got.astype(np.int32) - want).max() <= 1
-    assert np.abs(got_big.astype(np.int32) - want_big).max() <= 1
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got_big, want_big)
     m.set_path(1)
     assert np.array_equal(m.score(feat), got) and m.tc_last_format() == 1     # back on fp16 for clean batches
     m.free()
@@ -556,7 +560,7 @@ def test_tensor_core_tf32_operands_when_fp16_is_disabled(monkeypatch):
     got = m.score(feat)
     assert m.path == 1 and m.tc_last_format() == 0
     m.set_path(0)
-    assert np.abs(got.astype(np.int32) - m.score(feat)).max() <= 1
+    np.testing.assert_array_equal(got, m.score(feat))
     m.free()
 
 
@@ -580,8 +584,7 @@ def test_tensor_core_mixed_operand_formats_per_tile():
     assert m.tc_last_format() == 2, "expected some tiles on fp16 and some on TF32"
     m.set_path(0)
     want = m.score(feat)
-    d = np.abs(got.astype(np.int32) - want)
-    assert d.max() <= 1 and (d != 0).mean() < 1e-2
+    np.testing.assert_array_equal(got, want)
     m.free()
 
 
@@ -617,9 +620,11 @@ def test_tied_tensor_core_fuzz_identical_to_exact():
         m.free()
 
 
-def test_tensor_core_ms_fuzz_within_one_of_exact():
+def test_tensor_core_ms_fuzz_identical_to_exact():
     """Random fully-continuous shapes (8/16/32 densities, 3..39 dims, variance spread up to
-    4 decades, feature scale 0.3..6): the tensor-core path stays within +-1 of the exact path."""
+    4 decades, feature scale 0.3..6 -- sharp Gaussians far from the features, where the GEMM
+    error is large): the tensor-core path stays IDENTICAL to the exact path; several of
+    these models trip the error monitor / queue limits and are redone by the literal scan."""
     for seed in range(10):
         rng = np.random.default_rng(900 + seed)
         S, M, D, T = int(rng.integers(9, 700)), int(rng.choice([8, 16, 32])), int(rng.integers(3, 40)), int(rng.integers(1, 600))
@@ -633,13 +638,10 @@ def test_tensor_core_ms_fuzz_within_one_of_exact():
         assert m.path == 1
         feat = (mean[rng.integers(0, S, T), rng.integers(0, M, T)] +
                 rng.standard_normal((T, D)) * float(rng.uniform(0.3, 6))).astype(np.float32)
-        got = m.score(feat).astype(np.int32)
-        fmt = m.tc_last_format()
+        got = m.score(feat)
+        fmt, st = m.tc_last_format(), m.cont_stats()
         m.set_path(0)
-        d = np.abs(got - m.score(feat))
-        assert d.max() <= 1, f"seed {seed}: S {S} M {M} D {D} T {T} format {fmt}: max |d| {d.max()}"
-        # the disagreement rate grows with |d| (relative GEMM error 2^-22): sharp models + far features reach a few %
-        assert (d != 0).mean() < 6e-2, f"seed {seed}: mismatch rate {(d != 0).mean():.3f}"
+        np.testing.assert_array_equal(got, m.score(feat), err_msg=f"seed {seed}: S {S} M {M} D {D} T {T} format {fmt} {st}")
         m.free()
 
 
@@ -660,7 +662,7 @@ def test_two_devices_in_one_process():
         a = m.score(feat)
         m.set_path(0)
         e = m.score(feat)
-        assert np.abs(a.astype(np.int32) - e).max() <= 1
+        np.testing.assert_array_equal(a, e)
         outs.append((a, e))
         m.free()
     np.testing.assert_array_equal(outs[0][1], outs[1][1])

@@ -95,9 +95,9 @@ def test_identical_hypotheses_ptm_and_compallsen(tmp_path):
 def test_identical_hypotheses_fully_continuous(tmp_path, passes):
     """hub4_cd_continuous_8gau_1s_c_d_dd (6144 senones x 8 Gaussians x 39 dims) goes
     through the reference's generic ms back-end; the plug-in serves it from the
-    exact kernels (path 0: identical path score required) and from the tcgen05
-    Mahalanobis GEMM (path 1, scores within +-1: identical words required, and
-    the path score may move by at most a few units)."""
+    exact kernels (path 0) and from the tcgen05 Mahalanobis GEMM (path 1, the
+    default; bit-identical senone scores since round 2): identical words AND
+    identical path score on both."""
     an4 = os.path.join(D, "lm", "an4")
     if not os.path.exists(os.path.join(an4, "an4.dict")):
         pytest.skip("an4 LM/dictionary not copied (make -C oracle ref)")
@@ -124,7 +124,9 @@ def test_identical_hypotheses_fully_continuous(tmp_path, passes):
     if not passes:
         assert w_cpu.split() == "P I T T S B U R G H".split()
     assert (w_ex, s_ex) == (w_cpu, s_cpu)
-    assert w_tc == w_cpu and abs(s_tc - s_cpu) <= 40, (s_tc, s_cpu)
+    assert (w_tc, s_tc) == (w_cpu, s_cpu)
+    w_def, s_def, _ = run("default", {"LD_PRELOAD": PLUGIN})
+    assert (w_def, s_def) == (w_cpu, s_cpu)
 
 
 def _write_mllr(path, veclens, seed):

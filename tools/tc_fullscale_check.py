@@ -23,9 +23,12 @@ cfg = b.MgauConfig(n_sen, 1, M, n_sen, [D], topn=4, logbase=LOGBASE)
 m = b.ms_from_arrays(cfg, mean, pv.reshape(mean.shape), pd.reshape(n_sen, 1, M), q, np.arange(n_sen))
 hist = np.zeros(8, np.int64)
 worst = []
+stats = {}
 for t0 in range(0, T, 20000):
     feat = synth.cont_features(mean, var, min(20000, T - t0), 5678 + t0)
     m.set_path(1); a = m.score(feat).astype(np.int32)
+    for k, v in m.cont_stats().items():
+        stats[k] = max(stats.get(k, 0), v) if k in ("overflow", "max_gemm_err") else stats.get(k, 0) + v
     m.set_path(0); e = m.score(feat).astype(np.int32)
     d = np.abs(a - e)
     hist += np.bincount(np.minimum(d, 7).ravel(), minlength=8)
@@ -34,4 +37,5 @@ for t0 in range(0, T, 20000):
         worst += [(int(t0 + i), int(j), int(a[i, j]), int(e[i, j])) for i, j in idx]
 print(json.dumps({"frames": T, "scores": int(hist.sum()), "abs_diff_histogram_0_to_7plus": hist.tolist(),
                   "mismatch_fraction": float(hist[1:].sum() / hist.sum()), "beyond_tolerance": int(hist[2:].sum()),
-                  "examples_frame_senone_tc_exact": worst[:10]}))
+                  "examples_frame_senone_tc_exact": worst[:10], "tensor_core_path_stats": stats,
+                  "eps": [os.environ.get("B200_TC_EPS0", "default"), os.environ.get("B200_TC_EPS_SHIFT", "default")]}))
