@@ -1142,8 +1142,8 @@ tc_fix_a_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ row
                 maxerr = max(maxerr, (unsigned)err);
                 // Safety net: the certificates assumed |error| <= eps0 + (|d| >> eps_shift).  These
                 // re-scored densities are a 1-2 % sample of all; when one of them uses more than
-                // half of that bound the whole batch is redone by the literal scan.
-                if (2 * err > eps0 + (abs(di) >> eps_shift)) qcnt[2] = 1u;
+                // three quarters of that bound the whole batch is redone by the literal scan.
+                if (4 * err > 3 * (eps0 + (abs(di) >> eps_shift))) qcnt[2] = 1u;
             }
         }
         __syncwarp();
