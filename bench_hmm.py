@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """bench_hmm.py -- BASELINE.json configs[3]: hmm_vit_eval (3-state) over 50 000
 active HMMs per frame with the fwdtree beam test and the active-senone gather,
-on one B200.  Secondary benchmark (bench.py carries the headline metric); prints
-one JSON line with the HBM roofline of the step (SURVEY.md section 8(d):
-76 algorithmic bytes per HMM*frame).
+on one B200.  Secondary benchmark: `python bench.py` runs it after the headline
+(the literal 1 x 50 000 configuration and the batched 64 x 50 000 one) and
+attaches the results under `secondary.hmm_single` / `secondary.hmm`; stand-alone
+it prints one JSON line with the HBM roofline of the step (SURVEY.md section
+8(d): 76 algorithmic bytes per HMM*frame).
 
   python bench_hmm.py [--utts B] [--frames F]
 
-B > 1 batches B utterances x 50k HMMs in one resident population
-(b200_hmm_pop_set_utts): per-frame launch latency, not bandwidth, bounds the
-single-utterance case.
+The beam is chosen so that about half of the population survives every frame
+of the timed region (the synthetic state scores are uniform over 2^20, so the
+spread is stationary): the order-preserving compaction and the active-senone
+gather are exercised at the survivor rate the launch list was profiled at.
 """
 import argparse
 import json
@@ -24,23 +27,33 @@ sys.path.insert(0, ROOT)
 
 N_HMM, N_SEN, N_TMAT, N_SSEQ, NE = 50_000, 5000, 50, 27_000, 3
 BYTES_PER_UNIT = 76
-BEAM = -1080 * 40      # synthetic scores are far more spread than real ones: keep ~half
+BEAM = -(1 << 19)      # state scores are spread uniformly over 2^20: about half of the HMMs stay inside
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--utts", type=int, default=64)
-    ap.add_argument("--frames", type=int, default=200)
-    ap.add_argument("--cpu-frames", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=80)
-    ap.add_argument("--single-steps", action="store_true", help="one b200_hmm_step_dev call per frame (no graph)")
-    args = ap.parse_args()
+def cpu_reference(d, tp, cpu_frames):
+    """The reference's own hmm_vit_eval (oracle/_ref) on one utterance's population, one core."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from cmusphinx_b200 import synth
+    fn = orc.ref().ref_hmm_eval_batch if orc.have_ref() else orc.port.orc_hmm_eval_batch
+    one = {k: (v[:N_HMM].copy() if k != "sseq" else v) for k, v in d.items()}
+    s0 = synth.senscr_frames(1, N_SEN, 99)[0]
+    t0 = time.perf_counter()
+    orc.hmm_eval(fn, NE, tp, d["sseq"], s0, one["score"], one["history"], one["out_score"], one["out_history"],
+                 one["senid"], one["tmatid"], one["mpx"], one["bestscore"], repeat=cpu_frames)
+    dt = time.perf_counter() - t0
+    return {"value": N_HMM * cpu_frames / dt, "unit": "HMM*frames/s", "cores": 1,
+            "kind": "reference" if orc.have_ref() else "port",
+            "sample": f"{cpu_frames} frames x {N_HMM} HMMs ({dt:.1f} s), hmm_vit_eval only (no beam / gather), one core"}
+
+
+def run(utts=64, frames=200, warmup=80, single_steps=False, cpu=True, cpu_frames=200):
     import torch
     import cmusphinx_b200 as b
     from cmusphinx_b200 import synth
     from cmusphinx_b200.engine import LOGBASE
     assert b.device_count() > 0
-    B = args.utts
+    B = utts
     tp = b.tmat_quantize(synth.bakis_tmat(N_TMAT, NE, 7), 1e-4, LOGBASE)
     d = synth.hmm_population(N_HMM * B, NE, N_SEN, N_TMAT, N_SSEQ, seed=42, mpx_fraction=0.1)
     pop = b.HmmPopulation(N_HMM * B, NE)
@@ -51,65 +64,67 @@ def main():
     ctx.set_utts(np.arange(B + 1, dtype=np.int32) * N_HMM)
     n_sets = 8
     sen = torch.from_numpy(synth.senscr_frames(n_sets * B, N_SEN, 99).reshape(n_sets, B, N_SEN)).cuda()
-    # The frames of a run are issued by b200_hmm_run_dev: replays of one instantiated CUDA graph of
-    # 32 frames (5 kernels each) -- per-frame launch latency is what bounds the single-utterance case.
-    # --single-steps times the same frames as individual b200_hmm_step_dev calls.
     side = torch.cuda.Stream()          # the legacy default stream cannot be captured
     stream = side.cuda_stream
     torch.cuda.synchronize()
 
-    def run(n):
-        if args.single_steps:
+    def go(n):
+        if single_steps:
             for f in range(n):
                 b.lib.b200_hmm_step_dev(ctx._h, sen[f % n_sets].data_ptr(), BEAM, stream)
         else:
             ctx.run_dev(sen.data_ptr(), B * N_SEN, n_sets, n, BEAM, stream)
 
-    run(args.warmup)                    # warm-up; >= 72 frames builds the graph
+    go(warmup)
     torch.cuda.synchronize()
+    _, nk0, _ = ctx.step_results(N_HMM * B, want_idx=False)
     l0 = b.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(side)
-    run(args.frames)
+    go(frames)
     e1.record(side)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.frames
+    ms = e0.elapsed_time(e1) / frames
     launches = b.launch_count() - l0
     units = N_HMM * B
     value = units / (ms / 1e3)
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
     achieved = units * BYTES_PER_UNIT / (ms / 1e3) / 1e9
-    best, nk, _ = ctx.step(sen[0].cpu().numpy(), BEAM, units, want_idx=False)
-    # CPU: the reference's own hmm_vit_eval on one utterance's population
-    cpu = None
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import orc
-        fn = orc.ref().ref_hmm_eval_batch if orc.have_ref() else orc.port.orc_hmm_eval_batch
-        one = {k: (v[:N_HMM].copy() if k != "sseq" else v) for k, v in d.items()}
-        s0 = synth.senscr_frames(1, N_SEN, 99)[0]
-        t0 = time.perf_counter()
-        orc.hmm_eval(fn, NE, tp, d["sseq"], s0, one["score"], one["history"], one["out_score"], one["out_history"],
-                     one["senid"], one["tmatid"], one["mpx"], one["bestscore"], repeat=args.cpu_frames)
-        dt = time.perf_counter() - t0
-        cpu = {"value": N_HMM * args.cpu_frames / dt, "unit": "HMM*frames/s", "cores": 1,
-               "kind": "reference" if orc.have_ref() else "port",
-               "sample": f"{args.cpu_frames} frames x {N_HMM} HMMs, hmm_vit_eval only (no beam / gather), includes AoS marshalling"}
-    except Exception as ex:
-        cpu = {"value": None, "sample": f"failed: {ex!r}"}
-    print(json.dumps({
+    _, nk1, _ = ctx.step_results(N_HMM * B, want_idx=False)
+    res = {
         "metric": "hmm_frames_evaluated_per_sec", "value": value, "unit": "HMM*frames/s", "n_gpus": 1,
-        "steps": args.frames, "ms_per_step": ms, "higher_is_better": True, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"hmm_vit_eval_3st + beam + compaction + active-senone gather, {B} utterances x {N_HMM} "
-                               "HMMs per frame (BASELINE configs[3])", "n_sen": N_SEN, "mpx_fraction": 0.1},
+        "steps": frames, "ms_per_step": ms, "us_per_frame": ms * 1e3, "higher_is_better": True, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": f"hmm_vit_eval_3st + beam + compaction + active-senone gather, {B} utterance(s) x {N_HMM} "
+                               "HMMs per frame (BASELINE configs[3])", "n_sen": N_SEN, "mpx_fraction": 0.1, "beam": BEAM},
         "gpu_launches": int(launches),
-        "issue": "b200_hmm_step_dev per frame" if args.single_steps else "b200_hmm_run_dev (CUDA-graph replays of 32 frames)",
-        "survivor_fraction": float(np.sum(nk)) / units,
+        "issue": "b200_hmm_step_dev per frame" if single_steps else "b200_hmm_run_dev",
+        "survivor_fraction": {"first_timed_frame": float(np.sum(nk0)) / units, "last_timed_frame": float(np.sum(nk1)) / units},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "traffic": None},
-        "cpu_baseline": cpu}))
+                     "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(pk) else "fallback"}}
     ctx.free()
+    del sen
+    torch.cuda.empty_cache()
+    if cpu:
+        try:
+            res["cpu_baseline"] = cpu_reference(d, tp, cpu_frames)
+        except Exception as ex:
+            res["cpu_baseline"] = {"value": None, "kind": "reference", "cores": 0, "sample": f"failed: {ex!r}"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--utts", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--cpu-frames", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=80)
+    ap.add_argument("--single-steps", action="store_true", help="one b200_hmm_step_dev call per frame")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    print(json.dumps(run(args.utts, args.frames, args.warmup, args.single_steps, not args.no_cpu_baseline, args.cpu_frames)))
 
 
 if __name__ == "__main__":

@@ -1,15 +1,29 @@
 #!/usr/bin/env python
 """bench_ptm.py -- BASELINE.json configs[2]: ptm_mgau, 256 phonetic codebooks x
 4096 densities x 39 dims, 5000 senone mixture-weight rows, top-4 fast-eval, one
-B200.  Secondary benchmark; one JSON line.  The codebook stage runs on the
-tensor cores (the TF32x3 GEMM of bench.py producing candidate keys, exact
-float32 re-scoring of the 8 best per (frame, codebook), exact-scan fallback for
-unprovable ties) and is checked here against the exact CUDA-core scan: scores
-must be identical."""
+B200, T = 100 000 frames per step.  Secondary
+benchmark: `python bench.py` runs it after the headline and attaches the result
+under `secondary.ptm`; stand-alone it prints one JSON line.
+
+The codebook stage runs on the tensor cores (the hi/lo GEMM of bench.py
+producing candidate keys, exact float32 re-scoring of the 8 best per (frame,
+codebook), exact-scan fallback for unprovable ties) and is checked here against
+the exact CUDA-core scan: scores must be identical.
+
+CPU baseline: the reference's own C code on one host core.  ptm_mgau_init needs
+a 256-phone model definition, which the tree does not have; the same parameters
+and senone->codebook map run through the reference's generic multi-codebook
+back-end instead (ms_mgau_init with a -senmgau map file: gauden_dist over the
+256 x 4096 densities + senone_eval, ms_mgau.c:162-252) -- the reference's
+implementation of exactly this Gaussian work, stated in `sample`.
+"""
 import argparse
 import json
 import os
+import struct
 import sys
+import tempfile
+import time
 
 import numpy as np
 
@@ -18,12 +32,53 @@ sys.path.insert(0, ROOT)
 C, M, D, S = 256, 4096, 39, 5000
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=8192)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--cpu-frames", type=int, default=48)
-    args = ap.parse_args()
+def _write_senmgau(path, s2c, n_mgau):
+    """senone -> codebook map file (ms_senone.c:64-147, version 1.2)."""
+    with open(path, "wb") as fp:
+        fp.write(b"s3\nversion 1.2\nendhdr\n")
+        fp.write(struct.pack("<I", 0x11223344))
+        fp.write(struct.pack("<i", n_mgau))
+        fp.write(struct.pack("<i", len(s2c)))
+        fp.write(np.asarray(s2c, "<u4").tobytes())
+
+
+def cpu_reference(mean, var, mixw_q, s2c, feat, budget_s=12.0):
+    """The reference's ms back-end on the same parameters, one core, a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as Ct
+    import orc
+    from cmusphinx_b200 import s3io
+    from cmusphinx_b200.engine import LOGBASE
+    if not orc.have_ref():
+        return {"value": None, "unit": "frame*senones/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    with tempfile.TemporaryDirectory(prefix="b200ptm_") as tmp:
+        f = [os.path.join(tmp, n) for n in ("means", "variances", "mixture_weights", "senmgau")]
+        s3io.write_gauden(f[0], mean.reshape(C, M, D), [D])
+        s3io.write_gauden(f[1], var.reshape(C, M, D), [D])
+        # weights whose quantised form is the benchmark's uint8 table: w = b^-(q << 10)
+        w = np.exp(-(mixw_q[0].T.astype(np.float64) * 1024.0) * np.log(LOGBASE)).astype(np.float32)
+        s3io.write_mixw(f[2], w.reshape(S, 1, M))
+        _write_senmgau(f[3], s2c, C)
+        h = orc.ref().ref_ms_init(f[0].encode(), f[1].encode(), f[2].encode(), f[3].encode(), 1e-4, 1e-7, 4, 1, LOGBASE)
+        assert h, "reference ms_mgau_init failed"
+        out = np.zeros((1, S), np.int16)
+        one = np.ascontiguousarray(feat[:1])
+        t0 = time.perf_counter()
+        orc.ref().ref_ms_eval_all(h, orc._p(one, Ct.c_float), 1, orc._p(out, Ct.c_int16))
+        per = time.perf_counter() - t0
+        n = int(max(3, min(len(feat), budget_s / max(per, 1e-3))))
+        fs = np.ascontiguousarray(feat[:n])
+        out = np.zeros((n, S), np.int16)
+        t0 = time.perf_counter()
+        orc.ref().ref_ms_eval_all(h, orc._p(fs, Ct.c_float), n, orc._p(out, Ct.c_int16))
+        dt = time.perf_counter() - t0
+        orc.ref().ref_ms_free(h)
+    return {"value": n * S / dt, "unit": "frame*senones/s", "cores": 1, "kind": "reference",
+            "sample": f"{n} frames of the same workload on one core ({dt:.1f} s) through the reference's ms_mgau back-end "
+                      "(-senmgau map file; ptm_mgau_init itself needs a 256-phone mdef the tree does not have)"}
+
+
+def run(frames=100_000, steps=2, cpu=True, cpu_budget_s=12.0):
     import torch
     import cmusphinx_b200 as b
     from cmusphinx_b200.engine import LOGBASE
@@ -35,14 +90,17 @@ def main():
     s2c = (np.arange(S) * C // S).astype(np.uint8)
     cfg = b.MgauConfig(C, 1, M, S, [D], topn=4, logbase=LOGBASE)
     m = b.ptm_from_arrays(cfg, mean, pv.reshape(C, -1), pd.reshape(C, 1, M), mixw, s2c)
-    T = args.frames
-    feat = torch.from_numpy((rng.standard_normal((T, D)) * 1.5).astype(np.float32)).cuda()
+    T = frames
+    feat_h = (rng.standard_normal((T, D)) * 1.5).astype(np.float32)
+    feat = torch.from_numpy(feat_h).cuda()
     out = torch.empty((T, S), dtype=torch.int16, device="cuda")
+    l0 = b.launch_count()
     m.score_dev(feat.data_ptr(), T, out.data_ptr())
     ms = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         m.score_dev(feat.data_ptr(), T, out.data_ptr())
         ms.append(m.last_ms(0))
+    launches = (b.launch_count() - l0) // (steps + 1)
     t = float(np.mean(ms))
     path = m.path
     stats = m.tied_stats() if path == 1 else (0, 0)
@@ -55,35 +113,41 @@ def main():
     t_exact = m.last_ms(0) * T / n_chk
     assert np.array_equal(chk_tc, out0.cpu().numpy()), "tensor-core path != exact path"
     flop = 4.0 * D * C * M       # per frame
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1325.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(pk))["bf16_tflops_sustained"] if os.path.exists(pk) else 1400.0
     ach = flop * T / (t / 1e3) / 1e12
-    # CPU baseline: the oracle port (checker only), one core, a bounded sample of the same workload
-    import time
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    n_cpu = args.cpu_frames
-    pt = orc.PortTied(1, C, 1, [D], M, S, 4, mean, pv.reshape(C, -1), pd.reshape(C, 1, M), mixw, 0, None, s2c, LOGBASE)
-    fh = feat[:n_cpu].cpu().numpy()
-    t0c = time.perf_counter()
-    want = pt.eval_all(fh)
-    dtc = time.perf_counter() - t0c
-    first = chk_tc[0]
-    cpu_same_frame0 = bool(np.array_equal(first, want[0]))   # later frames: the oracle seeds with the previous frame's list
-    print(json.dumps({"metric": "frames_x_senones_scored_per_sec", "value": T * S / (t / 1e3), "unit": "frame*senones/s",
-                      "n_gpus": 1, "steps": args.steps, "ms_per_step": t, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"ptm_mgau {C} codebooks x {M} densities x {D} dims, {S} senones, topn 4, "
-                                             f"{T} frames/step (BASELINE configs[2])",
-                                 "kernel_path": "tcgen05 GEMM candidates + exact re-scoring (bit-identical to the exact scan)" if path == 1 else "exact CUDA-core",
-                                 "lists": stats[0], "lists_via_exact_fallback": stats[1], "max_gemm_vs_exact_raw_units": getattr(m, "tied_max_err", 0),
-                                 "exact_path_ms_per_step_extrapolated": t_exact},
-                      "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                                   "algorithmic_flop_per_unit": flop / S, "traffic": None},
-                      "cpu_baseline": {"value": n_cpu * S / dtc, "unit": "frame*senones/s", "cores": 1, "kind": "port",
-                                       "sample": f"{n_cpu} frames of the same workload ({dtc:.1f} s); frame 0 identical to the GPU: {cpu_same_frame0}"},
-                      "gpu_launches": int(b.launch_count()),
-                      "checksum": int(out[:8].to(torch.int64).sum().item())}))
+    res = {"metric": "frames_x_senones_scored_per_sec", "value": T * S / (t / 1e3), "unit": "frame*senones/s",
+           "n_gpus": 1, "steps": steps, "ms_per_step": t, "dtype": "f16x3", "data": "synthetic",
+           "config": {"workload": f"ptm_mgau {C} codebooks x {M} densities x {D} dims, {S} senones, topn 4, "
+                                  f"{T} frames/step (BASELINE configs[2])",
+                      "kernel_path": "tcgen05 GEMM candidates + exact re-scoring (bit-identical to the exact scan)" if path == 1 else "exact CUDA-core",
+                      "lists": stats[0], "lists_via_exact_fallback": stats[1],
+                      "max_gemm_vs_exact_raw_units": getattr(m, "tied_max_err", 0),
+                      "exact_path_ms_per_step_extrapolated": t_exact,
+                      "parity": f"first {n_chk} frames identical to the exact CUDA-core scan"},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "algorithmic_flop_per_unit": flop / S, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if os.path.exists(pk) else "fallback"},
+           "gpu_launches": int(launches),
+           "checksum": int(out[:8].to(torch.int64).sum().item())}
     m.free()
+    del out, feat
+    torch.cuda.empty_cache()
+    if cpu:
+        try:
+            res["cpu_baseline"] = cpu_reference(mean, var, mixw, s2c, feat_h[:64], cpu_budget_s)
+        except Exception as ex:
+            res["cpu_baseline"] = {"value": None, "kind": "reference", "cores": 0, "sample": f"failed: {ex!r}"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=100_000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    print(json.dumps(run(args.frames, args.steps, not args.no_cpu_baseline)))
 
 
 if __name__ == "__main__":

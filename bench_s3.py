@@ -39,6 +39,39 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=2000)
     args = ap.parse_args()
+    print(json.dumps(run(args)))
+
+
+def cpu_reference(mean, var, mixw, cd2ci, n_ci, feat_h, act_h, beam, n):
+    """The reference's own mgau_eval / approx_cont_mgau_frame_eval (oracle/_ref/libs3am.so) on one
+    core, model handed over as S3 files; falls back to the oracle port when _ref is not built."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from cmusphinx_b200 import s3io
+    have = os.path.exists(os.path.join(orc.REF_DIR, "libref_shim_s3.so"))
+    tmp = tempfile.TemporaryDirectory(prefix="b200s3_")
+    if have:
+        f = [os.path.join(tmp.name, k) for k in ("means", "variances", "mixture_weights")]
+        s3io.write_gauden(f[0], mean, [D]); s3io.write_gauden(f[1], var, [D]); s3io.write_mixw(f[2], mixw.reshape(S, 1, M))
+        p = orc.RefS3(f[0], f[1], f[2], None, cd2ci, n_ci)
+    else:
+        p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    t0 = time.perf_counter()
+    p.eval_utt(feat_h[:n], None)
+    dt = time.perf_counter() - t0
+    p.set_fast(ci_pbeam=beam); p.utt_reset()
+    t0 = time.perf_counter()
+    o = p.eval_utt(feat_h[:4 * n], act_h[:4 * n])
+    dt2 = time.perf_counter() - t0
+    p.free()
+    tmp.cleanup()
+    return o, {"value": n * S / dt, "unit": "frame*senones/s", "cores": 1, "kind": "reference" if have else "port",
+               "sample": f"{n} frames dense ({dt:.1f} s), {4 * n} frames approx ({dt2:.1f} s), one core; GPU == this on the sample",
+               "approx_frames_per_s": 4 * n / dt2}
+
+
+def run(args):
     import torch
     import cmusphinx_b200 as b
     from cmusphinx_b200 import synth
@@ -53,6 +86,7 @@ def main():
     act = torch.from_numpy(act_h).cuda()
     out = torch.empty((T, S), dtype=torch.int32, device="cuda")
     best = torch.empty(T, dtype=torch.int32, device="cuda")
+    prev_stream = torch.cuda.current_stream()
     torch.cuda.set_stream(torch.cuda.Stream())     # time and launch on the same non-default stream
     st = torch.cuda.current_stream().cuda_stream
     fp64_rate = b.lib.b200_fp64_issue_rate(0)
@@ -93,24 +127,15 @@ def main():
                      "active_frame_senones_per_s": n_active / (ms_approx * 1e-3),
                      "active_fraction": n_active / (T * S), "ci_pbeam": beam}
     launches = b.launch_count() - l0
-    # CPU baseline: the oracle port (checker only) on a bounded sample, one core
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
-    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    # CPU baseline: the reference itself on a bounded sample, one core; parity on the sample while we are here
     n = args.cpu_frames
-    t0 = time.perf_counter()
-    p.eval_utt(feat_h[:n], None)
-    dt = time.perf_counter() - t0
-    cpu_dense = n * S / dt
-    p.set_fast(ci_pbeam=beam); p.utt_reset()
-    t0 = time.perf_counter()
-    o = p.eval_utt(feat_h[:4 * n], act_h[:4 * n])
-    dt2 = time.perf_counter() - t0
-    # parity on the sample while we are here
+    o, cpu = cpu_reference(mean, var, mixw, cd2ci, n_ci, feat_h, act_h, beam, n)
     m.utt_reset()
     got = m.eval_utt(feat_h[:4 * n], act_h[:4 * n])
-    assert np.array_equal(got[0], o[0]) and np.array_equal(got[1], o[1]), "GPU != oracle on the bench sample"
-    print(json.dumps({
+    assert np.array_equal(got[0], o[0]) and np.array_equal(got[1], o[1]), "GPU != reference on the bench sample"
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(prev_stream)
+    return ({
         "metric": "frames_x_senones_scored_per_sec (sphinx3 mgau_eval, float64)", "value": dense_rate,
         "unit": "frame*senones/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dense,
         "higher_is_better": True, "dtype": "f64", "data": "synthetic",
@@ -121,10 +146,8 @@ def main():
                      "algorithmic_f64_instr_per_unit": flop_unit,
                      "peak_source": "b200_fp64_issue_rate(): DMUL/DADD chains measured on this device"},
         "paths": res, "gpu_launches": int(launches),
-        "cpu_baseline": {"value": cpu_dense, "unit": "frame*senones/s", "cores": 1, "kind": "port",
-                         "sample": f"{n} frames dense ({dt:.1f} s), {4 * n} frames approx ({dt2:.1f} s); GPU == oracle on the sample",
-                         "approx_frames_per_s": 4 * n / dt2},
-    }))
+        "cpu_baseline": cpu,
+    })
 
 
 if __name__ == "__main__":
