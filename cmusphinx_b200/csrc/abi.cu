@@ -632,10 +632,15 @@ struct b200_hmmctx {
     uint8_t *d_tp = nullptr; uint16_t *d_sseq = nullptr;
     HmmPop p{};
     size_t pop_cap = 0;  // in HMMs
-    HmmFrame *d_fr = nullptr; int fr_cap = 0;          // [n_utt]
-    uint8_t *d_keep = nullptr; int32_t *d_block_count = nullptr, *d_keep_idx = nullptr;
+    HmmFrame *d_fr = nullptr; int fr_cap = 0;          // [3][n_utt] rotating frame records
+    int fr_slot = 0;                                   // slot of the last frame that ran
+    int32_t *d_block_count = nullptr, *d_keep_idx = nullptr;   // survivors per tile; survivor list
     size_t bc_cap = 0;
-    uint32_t *d_mask = nullptr; size_t mask_cap = 0;   // [n_utt][n_words]
+    uint32_t *d_mask = nullptr; size_t mask_cap = 0;   // [2][n_utt][n_words]
+    uint32_t *d_mask_part = nullptr; size_t mask_part_cap = 0;   // words: [2][n_utt][CTAs per utterance][n_words]
+    int mask_par = 0;                                  // parity of the last frame's mask
+    unsigned *d_bar = nullptr;                         // grid barrier of the persistent step kernel
+    bool stepped = false;
     int32_t *d_utt_off = nullptr; int utt_cap = 0;
     int32_t *d_total = nullptr;
     std::vector<int32_t> h_utt_off;
@@ -645,10 +650,6 @@ struct b200_hmmctx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
-    // b200_hmm_run_dev: one instantiated CUDA graph of `g_frames` steps, valid for this key
-    cudaGraphExec_t g_exec = nullptr;
-    int g_frames = 0;
-    struct GKey { const void *sen, *score; long stride; int cycle, n_hmm, n_utt, max_per_utt; int32_t beam; } g_key{};
 };
 
 namespace {
@@ -656,8 +657,8 @@ namespace {
 void pop_free(b200_hmmctx *c) {
     cudaFree(c->p.score); cudaFree(c->p.history); cudaFree(c->p.out_score); cudaFree(c->p.out_history);
     cudaFree(c->p.bestscore); cudaFree(c->p.senid); cudaFree(c->p.tmatid); cudaFree(c->p.mpx);
-    cudaFree(c->d_keep); cudaFree(c->d_keep_idx);
-    c->p = HmmPop{}; c->d_keep = nullptr; c->d_keep_idx = nullptr; c->pop_cap = 0;
+    cudaFree(c->d_keep_idx);
+    c->p = HmmPop{}; c->d_keep_idx = nullptr; c->pop_cap = 0;
 }
 
 int pop_reserve(b200_hmmctx *c, int n) {
@@ -673,7 +674,6 @@ int pop_reserve(b200_hmmctx *c, int n) {
     B200_CUDA_OK(cudaMalloc((void **)&c->p.senid, N * ne * 2));
     B200_CUDA_OK(cudaMalloc((void **)&c->p.tmatid, N * 2));
     B200_CUDA_OK(cudaMalloc((void **)&c->p.mpx, N));
-    B200_CUDA_OK(cudaMalloc((void **)&c->d_keep, N));
     B200_CUDA_OK(cudaMalloc((void **)&c->d_keep_idx, N * 4));
     c->pop_cap = N; c->p.n_hmm = n;
     return B200_OK;
@@ -696,13 +696,24 @@ int set_utts(b200_hmmctx *c, int n_utt, const int32_t *off) {
     }
     if (n_utt > c->fr_cap) {
         cudaFree(c->d_fr); c->d_fr = nullptr; c->fr_cap = 0;
-        B200_CUDA_OK(cudaMalloc((void **)&c->d_fr, (size_t)n_utt * sizeof(HmmFrame)));
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_fr, (size_t)3 * n_utt * sizeof(HmmFrame)));
         c->fr_cap = n_utt;
     }
     if ((size_t)n_utt * n_words > c->mask_cap) {
         cudaFree(c->d_mask); c->d_mask = nullptr; c->mask_cap = 0;
-        B200_CUDA_OK(cudaMalloc((void **)&c->d_mask, (size_t)n_utt * n_words * 4));
+        B200_CUDA_OK(cudaMalloc((void **)&c->d_mask, (size_t)2 * n_utt * n_words * 4));
         c->mask_cap = (size_t)n_utt * n_words;
+    }
+    {   // partial masks: at most one resident wave of CTAs (<= 8 per SM) is split over the utterances
+        const int wave = 8 * 148;
+        const int gy = std::max(1, std::min(n_utt, wave));
+        const size_t gx_max = (size_t)std::max(1, std::min((mx + 255) / 256, wave / gy));
+        const size_t need = (size_t)2 * n_utt * gx_max * n_words;
+        if (need > c->mask_part_cap) {
+            cudaFree(c->d_mask_part); c->d_mask_part = nullptr; c->mask_part_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&c->d_mask_part, need * 4));
+            c->mask_part_cap = need;
+        }
     }
     const size_t nb = (size_t)((mx + 255) / 256) * n_utt + 1;
     if (nb > c->bc_cap) {
@@ -713,6 +724,7 @@ int set_utts(b200_hmmctx *c, int n_utt, const int32_t *off) {
     B200_CUDA_OK(cudaMemcpy(c->d_utt_off, off, (size_t)(n_utt + 1) * 4, cudaMemcpyHostToDevice));
     c->h_utt_off.assign(off, off + n_utt + 1);
     c->p.n_utt = n_utt; c->p.max_per_utt = mx; c->p.utt_off = c->d_utt_off;
+    c->fr_slot = 0; c->mask_par = 0; c->stepped = false;
     return B200_OK;
 }
 
@@ -744,7 +756,7 @@ b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat, co
     const int n_words = (n_sen + 31) / 32;
     if (dev_alloc_copy(&c->d_tp, tp, (size_t)n_tmat * n_emit * (n_emit + 1)) ||
         dev_alloc_copy(&c->d_sseq, sseq, (size_t)std::max(n_sseq, 1) * n_emit * (n_sseq > 0 ? 1 : 0)) ||
-        cudaMalloc((void **)&c->d_total, 4) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_total, 4) != cudaSuccess || cudaMalloc((void **)&c->d_bar, 4) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess) {
         set_error("hmm context allocation failed"); b200_hmm_ctx_free(c); return nullptr;
@@ -757,9 +769,8 @@ void b200_hmm_ctx_free(b200_hmmctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     pop_free(c);
-    cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_senscr); cudaFree(c->d_winner); cudaFree(c->d_enter);
-    cudaFree(c->d_block_count); cudaFree(c->d_utt_off); cudaFree(c->d_total);
-    if (c->g_exec) cudaGraphExecDestroy(c->g_exec);
+    cudaFree(c->d_tp); cudaFree(c->d_sseq); cudaFree(c->d_fr); cudaFree(c->d_mask); cudaFree(c->d_mask_part); cudaFree(c->d_senscr); cudaFree(c->d_winner); cudaFree(c->d_enter);
+    cudaFree(c->d_block_count); cudaFree(c->d_utt_off); cudaFree(c->d_total); cudaFree(c->d_bar);
     if (c->st) cudaStreamDestroy(c->st);
     for (int i = 0; i < 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -805,72 +816,58 @@ int b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h) {
     return B200_OK;
 }
 
+// One launch of the persistent step kernel: n_frames frames, frame f on the scores at
+// d_senscr + ((frame0 + f) % n_cycle) * frame_stride.
+static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, int n_cycle, int n_frames, int32_t beam,
+                   int do_beam, cudaStream_t st) {
+    if (c->p.n_hmm <= 0 || n_frames <= 0) return B200_OK;
+    HmmRun r{};
+    r.sen_base = d_senscr; r.frame_stride = frame_stride; r.n_cycle = n_cycle; r.frame0 = 0; r.n_frames = n_frames;
+    r.beam = beam; r.do_beam = do_beam;
+    r.fr3 = c->d_fr; r.slot0 = (c->fr_slot + 1) % 3;
+    r.tile_count = c->d_block_count; r.tpu = (c->p.max_per_utt + 255) / 256;
+    r.keep_idx = c->d_keep_idx;
+    r.mask2 = c->d_mask; r.mask0 = (c->mask_par + 1) & 1;
+    r.mask_part = c->d_mask_part; r.mask_part_words = c->mask_part_cap;
+    r.total = c->d_total; r.bar = c->d_bar;
+    static long long *d_probe = nullptr;
+    if (getenv("B200_HMM_PROBE") && !d_probe) cudaMalloc((void **)&d_probe, 64);
+    r.probe = d_probe;
+    const int rc = hmm_launch_run(c->c, c->p, r, st);
+    if (rc) return rc;
+    c->fr_slot = (r.slot0 + n_frames - 1) % 3;
+    c->mask_par = (r.mask0 + n_frames - 1) & 1;
+    c->stepped = do_beam != 0;
+    if (d_probe) {
+        long long h[6];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_probe, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "hmm probe (cycles): A %lld  bar1 %lld  B %lld  bar2 %lld  C %lld\n", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+    }
+    return B200_OK;
+}
+
 int b200_hmm_step_dev(b200_hmmctx_t *c, const int16_t *d_senscr, int32_t beam, void *stream) {
     if (!c || !d_senscr) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->st;
     cudaEventRecord(c->ev[0], st);
-    int rc = hmm_launch_step(c->c, c->p, d_senscr, beam, c->d_fr, c->d_keep, c->d_block_count, c->d_keep_idx,
-                             c->d_mask, c->d_total, 1, st);
+    const int rc = hmm_run(c, d_senscr, 0, 1, 1, beam, 1, st);
     cudaEventRecord(c->ev[1], st);
     return rc;
 }
 
-// A run of frames is launch-latency bound when the population is one utterance
-// (5 small kernels per frame): replay an instantiated CUDA graph of >= 32 frames
-// instead of launching them one by one.
+// A run of frames is ONE launch of the persistent kernel (two grid barriers per
+// frame instead of five kernel launches).
 int b200_hmm_run_dev(b200_hmmctx_t *c, const int16_t *d_senscr, long frame_stride, int n_cycle, int n_frames,
                      int32_t beam, void *stream) {
     if (!c || !d_senscr || n_cycle < 1 || n_frames < 0 || frame_stride < 0) { set_error("bad argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->st;
-    auto step = [&](int f) {
-        return hmm_launch_step(c->c, c->p, d_senscr + (size_t)(f % n_cycle) * frame_stride, beam, c->d_fr, c->d_keep,
-                               c->d_block_count, c->d_keep_idx, c->d_mask, c->d_total, 1, st);
-    };
-    const int G = n_cycle * ((32 + n_cycle - 1) / n_cycle);   // frames per graph: whole cycles, >= 32
-    int rc = B200_OK;
     cudaEventRecord(c->ev[0], st);
-    int f = 0;
-    if (n_frames >= 2 * G + n_cycle && c->p.n_hmm > 0) {
-        const b200_hmmctx::GKey &k = c->g_key;
-        const bool same = c->g_exec && c->g_frames == G && k.sen == d_senscr && k.score == c->p.score &&
-                          k.stride == frame_stride && k.cycle == n_cycle && k.n_hmm == c->p.n_hmm &&
-                          k.n_utt == c->p.n_utt && k.max_per_utt == c->p.max_per_utt && k.beam == beam;
-        if (!same) {
-            if (c->g_exec) { cudaGraphExecDestroy(c->g_exec); c->g_exec = nullptr; }
-            // one cycle launched directly (this also sets the kernels' attributes on this device) ...
-            for (; f < n_cycle; ++f)
-                if ((rc = step(f))) return rc;
-            // ... then G frames recorded, not executed; captured launches are counted when replayed
-            const long long before = g_launches.load();
-            cudaGraph_t graph = nullptr;
-            B200_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            for (int i = 0; i < G && !rc; ++i) rc = step(i);
-            const cudaError_t e = cudaStreamEndCapture(st, &graph);
-            g_launches.store(before);
-            if (rc || e != cudaSuccess) {
-                if (graph) cudaGraphDestroy(graph);
-                if (!rc) { set_error("graph capture failed: %s", cudaGetErrorString(e)); rc = B200_ERR_CUDA; }
-                cudaGetLastError();
-                return rc;
-            }
-            const cudaError_t e2 = cudaGraphInstantiate(&c->g_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e2 != cudaSuccess) { c->g_exec = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(e2)); return B200_ERR_CUDA; }
-            c->g_key = b200_hmmctx::GKey{d_senscr, c->p.score, frame_stride, n_cycle, c->p.n_hmm, c->p.n_utt, c->p.max_per_utt, beam};
-            c->g_frames = G;
-        }
-        // f is a multiple of n_cycle here, and so is G: the replays stay in phase with the cycle
-        for (; f + G <= n_frames; f += G) {
-            B200_CUDA_OK(cudaGraphLaunch(c->g_exec, st));
-            g_launches.fetch_add(5LL * G, std::memory_order_relaxed);
-        }
-    }
-    for (; f < n_frames; ++f)
-        if ((rc = step(f))) return rc;
+    const int rc = hmm_run(c, d_senscr, frame_stride, n_cycle, n_frames, beam, 1, st);
     cudaEventRecord(c->ev[1], st);
-    return B200_OK;
+    return rc;
 }
 
 int b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off) {
@@ -887,7 +884,7 @@ int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int3
     std::vector<HmmFrame> fr(nu);
     int32_t total = 0;
     if (c->p.n_hmm > 0) {
-        B200_CUDA_OK(cudaMemcpy(fr.data(), c->d_fr, sizeof(HmmFrame) * nu, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(fr.data(), c->d_fr + (size_t)c->fr_slot * nu, sizeof(HmmFrame) * nu, cudaMemcpyDeviceToHost));
         B200_CUDA_OK(cudaMemcpy(&total, c->d_total, 4, cudaMemcpyDeviceToHost));
     } else {
         for (auto &f : fr) { f.best = B200_WORST_SCORE; f.n_keep = 0; }
@@ -898,7 +895,8 @@ int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int3
     }
     if (keep_idx && total > 0) B200_CUDA_OK(cudaMemcpy(keep_idx, c->d_keep_idx, (size_t)total * 4, cudaMemcpyDeviceToHost));
     if (sen_mask && c->p.n_hmm > 0)
-        B200_CUDA_OK(cudaMemcpy(sen_mask, c->d_mask, (size_t)nu * ((c->c.n_sen + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+        B200_CUDA_OK(cudaMemcpy(sen_mask, c->d_mask + (size_t)c->mask_par * nu * ((c->c.n_sen + 31) / 32),
+                                (size_t)nu * ((c->c.n_sen + 31) / 32) * 4, cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&c->last_ms, c->ev[0], c->ev[1]);
     return B200_OK;
 }
@@ -921,10 +919,10 @@ int b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h, const int16_t *sensc
     if ((rc = ensure((void **)&c->d_senscr, &c->senscr_cap, (size_t)c->c.n_sen * 2 * std::max(n_frames, 1)))) return rc;
     B200_CUDA_OK(cudaMemcpyAsync(c->d_senscr, senscr, (size_t)c->c.n_sen * 2 * n_frames, cudaMemcpyHostToDevice, c->st));
     for (int f = 0; f < n_frames; ++f) {
-        rc = hmm_launch_step(c->c, c->p, c->d_senscr + (size_t)f * c->c.n_sen, 0, c->d_fr, c->d_keep,
-                             c->d_block_count, c->d_keep_idx, c->d_mask, c->d_total, 0, c->st);
+        rc = hmm_run(c, c->d_senscr + (size_t)f * c->c.n_sen, 0, 1, 1, 0, 0, c->st);
         if (rc) return rc;
-        if (best_out) B200_CUDA_OK(cudaMemcpyAsync(&best_out[f], (const int32_t *)c->d_fr, 4, cudaMemcpyDeviceToHost, c->st));
+        if (best_out) B200_CUDA_OK(cudaMemcpyAsync(&best_out[f], (const int32_t *)(c->d_fr + (size_t)c->fr_slot * std::max(c->p.n_utt, 1)), 4,
+                                                   cudaMemcpyDeviceToHost, c->st));
     }
     B200_CUDA_OK(cudaStreamSynchronize(c->st));
     return b200_hmm_pop_download(c, h);
@@ -935,13 +933,15 @@ float b200_hmm_last_ms(const b200_hmmctx_t *c) { return c ? c->last_ms : -1.f; }
 int b200_hmm_normalize_dev(b200_hmmctx_t *c, const int32_t *d_best_per_utt, void *stream) {
     if (!c) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
-    return hmm_launch_normalize(c->p, c->c.n_emit, d_best_per_utt, c->d_fr, stream ? (cudaStream_t)stream : c->st);
+    return hmm_launch_normalize(c->p, c->c.n_emit, d_best_per_utt, c->d_fr + (size_t)c->fr_slot * std::max(c->p.n_utt, 1),
+                                stream ? (cudaStream_t)stream : c->st);
 }
 
 int b200_hmm_clear_pruned_dev(b200_hmmctx_t *c, void *stream) {
-    if (!c || !c->d_keep) { set_error("no beam step has run on this population"); return B200_ERR_ARG; }
+    if (!c || !c->stepped) { set_error("no beam step has run on this population"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
-    return hmm_launch_clear_pruned(c->p, c->c.n_emit, c->d_keep, stream ? (cudaStream_t)stream : c->st);
+    return hmm_launch_clear_pruned(c->p, c->c.n_emit, c->d_fr + (size_t)c->fr_slot * std::max(c->p.n_utt, 1),
+                                   stream ? (cudaStream_t)stream : c->st);
 }
 
 int b200_hmm_enter_dev(b200_hmmctx_t *c, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,

@@ -20,14 +20,27 @@ struct HmmPop {               // SoA mirror of hmm_t (PS/hmm.h:156-173), state-m
     uint8_t *mpx;
 };
 
-struct HmmFrame { int32_t best; int32_t n_keep; };
+// per utterance and frame: best score, survivors, the beam threshold they were tested against
+struct HmmFrame { int32_t best; int32_t n_keep; int32_t thresh; int32_t pad; };
 
-int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, int32_t beam,
-                    HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
-                    uint32_t *mask, int32_t *total, int do_beam, cudaStream_t st);
+// one launch = a run of frames (see hmm_run_kernel)
+struct HmmRun {
+    const int16_t *sen_base; long frame_stride; int n_cycle, frame0, n_frames;   // frame f scores: sen_base + ((frame0 + f) % n_cycle) * frame_stride + utt * n_sen
+    int32_t beam; int do_beam;
+    HmmFrame *fr3; int slot0;            // [3][n_utt] frame records, frame f uses slot (slot0 + f) % 3
+    int32_t *tile_count;                 // [n_utt][tpu] survivors per 256-HMM tile
+    int tpu;                             // tiles per utterance (largest)
+    int32_t *keep_idx;
+    uint32_t *mask2; int mask0;          // [2][n_utt][n_words], frame f uses (mask0 + f) & 1
+    uint32_t *mask_part; size_t mask_part_words;   // [2][n_utt][gx][n_words] per-CTA partial masks
+    int32_t *total;
+    unsigned *bar;                       // grid barrier counter
+    long long *probe;                    // development: phase time stamps of CTA 0 on the last frame (or null)
+};
+int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run, cudaStream_t st);
 
 int hmm_launch_normalize(const HmmPop &p, int n_emit, const int32_t *d_best_per_utt, const HmmFrame *fr, cudaStream_t st);
-int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const uint8_t *keep, cudaStream_t st);
+int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const HmmFrame *fr, cudaStream_t st);
 int hmm_launch_enter(const HmmPop &p, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,
                      int32_t *d_winner, int32_t *d_old0, uint8_t *d_entered, cudaStream_t st);
 

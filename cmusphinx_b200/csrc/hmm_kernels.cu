@@ -282,240 +282,312 @@ __device__ __forceinline__ void eval_any(HmmRegs &h, const uint8_t *tp, const in
     h.best = best;
 }
 
+// ------------------------------------------------------------------ the step
+// One persistent cooperative kernel runs a whole RUN of search frames (round 2;
+// it replaces five launches per frame: init, step, beam flag, scan, scatter).
+// The grid is exactly one resident wave: gx CTAs stride the tiles (256 HMMs) of
+// an utterance, gy CTA rows stride the utterances.  Per frame:
+//   A  hmm_vit_eval of every HMM (state in registers, senone scores and the
+//      transition table in shared memory), bestscore stored, the utterance's
+//      frame best by atomicMax                              -- grid barrier --
+//   B  beam test against best + beam, survivors counted per tile and per
+//      utterance                                            -- grid barrier --
+//   C  order-preserving scatter of the survivors' indices (offsets from the
+//      tile counts: no keep-byte array, no separate scan kernel) and their
+//      senones into the utterance's active mask (acmod_activate_hmm)
+// Frame records rotate over three slots and the masks over two, so phase A of
+// the next frame needs no third barrier.
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned n_cta, unsigned &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        const unsigned target = epoch * n_cta;
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned *>(ctr) < target)
+            if (clock64() - t0 > 4000000000LL) __trap();        // a protocol bug must trap, not hang the box
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// sum over the block of (a, b); every thread gets both totals
+__device__ __forceinline__ int2 block_sum2(int a, int b, int32_t *s_red /* [2 * warps] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    __syncthreads();
+    if (lane == 0) { s_red[2 * w] = a; s_red[2 * w + 1] = b; }
+    __syncthreads();
+    int ta = 0, tb = 0;
+    for (int k = 0; k < kHmmBlock / 32; ++k) { ta += s_red[2 * k]; tb += s_red[2 * k + 1]; }
+    return make_int2(ta, tb);
+}
+
+// The active-senone mask of one utterance and frame: the OR of the partial masks its gx CTAs
+// stored with plain stores (merging them with atomicOr made every CTA of an utterance hammer
+// the same n_words addresses: 17 us per frame on 196 CTAs).  One thread per mask word.
+__device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_words] */, int gx, int n_words, uint32_t *mask_u,
+                                           int w0, int wstep) {
+    // L lanes share a word (each ORs every L-th partial), 256 / L words per pass; this CTA owns
+    // the words w0, w0 + wstep, ...
+    int L = 1;
+    while (L < 32 && L < gx) L <<= 1;
+    const int per_pass = kHmmBlock / L, sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const int n_mine = w0 < n_words ? (n_words - w0 + wstep - 1) / wstep : 0;
+    for (int j0 = 0; j0 < n_mine; j0 += per_pass) {
+        const int j = j0 + slot;
+        const int kk = w0 + j * wstep;
+        uint32_t v = 0;
+        if (j < n_mine)
+            for (int b = sub; b < gx; b += L) v |= part_u[(size_t)b * n_words + kk];
+        for (int o = L >> 1; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if (j < n_mine && sub == 0) mask_u[kk] = v;
+    }
+}
+
 template <int NE>
-__global__ void __launch_bounds__(kHmmBlock, NE == 3 ? 6 : 4)
-hmm_step_kernel(HmmDev c, HmmPop p, const int16_t *__restrict__ senscr_all, HmmFrame *fr) {
+__global__ void __launch_bounds__(kHmmBlock, NE == 3 ? 5 : 4)
+hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
-    uint8_t *s_tp = sm_raw + (((size_t)c.n_sen * 2 + 15) & ~(size_t)15);
-    const int tid = threadIdx.x;
-    const int u = blockIdx.y;
-    const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-    if (lo + (int)blockIdx.x * kHmmBlock >= hi) return;   // uniform per block
-    const int16_t *senscr = senscr_all + (size_t)u * c.n_sen;
-    // stage the frame's senone scores (vectorised) and the transition table
-    {
-        const int n16 = ((reinterpret_cast<size_t>(senscr) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
-        const int4 *src = reinterpret_cast<const int4 *>(senscr);
-        int4 *dst = reinterpret_cast<int4 *>(s_sen);
-        for (int i = tid; i < n16; i += kHmmBlock) dst[i] = src[i];
-        for (int i = n16 * 8 + tid; i < c.n_sen; i += kHmmBlock) s_sen[i] = senscr[i];
+    const size_t sen_bytes = ((size_t)c.n_sen * 2 + 15) & ~(size_t)15;
+    const size_t tp_bytes = ((size_t)c.n_tmat * NE * (NE + 1) + 15) & ~(size_t)15;
+    uint8_t *s_tp = sm_raw + sen_bytes;
+    uint32_t *s_flag_w = reinterpret_cast<uint32_t *>(sm_raw + sen_bytes + tp_bytes);   // one flag byte per senone
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
+    // tile counts of one utterance | offsets of my tiles | keep ballots of my tiles (all my utterances)
+    const int rows = (r.tpu + (int)gridDim.x - 1) / (int)gridDim.x + 3;                 // my tiles per utterance (+ the 4-tile batch overrun)
+    int32_t *s_tc = reinterpret_cast<int32_t *>(s_flag + (size_t)((c.n_sen + 31) / 32) * 32);
+    int32_t *s_off = s_tc + r.tpu;
+    uint32_t *s_bal = reinterpret_cast<uint32_t *>(s_off + rows);
+    __shared__ int32_t s_red[2 * (kHmmBlock / 32)];
+    __shared__ int32_t s_wcnt[kHmmBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gx = gridDim.x, gy = gridDim.y, bx = blockIdx.x, by = blockIdx.y;
+    const unsigned n_cta = (unsigned)gx * gy;
+    const int n = p.n_hmm, n_utt = p.n_utt;
+    const int n_words = (c.n_sen + 31) / 32;
+    unsigned epoch = 0;
+
+    {   // transition table once; frame records and the first mask
         const int ntp = c.n_tmat * NE * (NE + 1);
         for (int i = tid; i < ntp; i += kHmmBlock) s_tp[i] = c.tp[i];
-    }
-    __syncthreads();
-    int32_t blockbest = kWorstScore;
-    const int n = p.n_hmm;
-    for (int i = lo + blockIdx.x * kHmmBlock + tid; i < hi; i += gridDim.x * kHmmBlock) {
-        HmmRegs h;
-#pragma unroll
-        for (int s = 0; s < NE; ++s) {
-            h.sc[s] = p.score[(size_t)s * n + i];
-            h.hi[s] = p.history[(size_t)s * n + i];
-            h.sid[s] = p.senid[(size_t)s * n + i];
-        }
-        h.out_sc = p.out_score[i];
-        h.out_hi = p.out_history[i];
-        const uint8_t *tp = s_tp + (int)p.tmatid[i] * NE * (NE + 1);
-        const bool mpx = p.mpx[i] != 0;
-        if (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
-        else if (NE == 5) { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
-        else eval_any<NE>(h, tp, s_sen, c.sseq, mpx);
-#pragma unroll
-        for (int s = 0; s < NE; ++s) {
-            p.score[(size_t)s * n + i] = h.sc[s];
-            p.history[(size_t)s * n + i] = h.hi[s];
-        }
-        if (mpx) {
-#pragma unroll
-            for (int s = 1; s < NE; ++s) p.senid[(size_t)s * n + i] = h.sid[s];
-        }
-        p.out_score[i] = h.out_sc;
-        p.out_history[i] = h.out_hi;
-        p.bestscore[i] = h.best;
-        blockbest = max(blockbest, h.best);
-    }
-    for (int o = 16; o > 0; o >>= 1) blockbest = max(blockbest, __shfl_xor_sync(0xffffffffu, blockbest, o));
-    __shared__ int32_t s_best[kHmmBlock / 32];
-    if ((tid & 31) == 0) s_best[tid >> 5] = blockbest;
-    __syncthreads();
-    if (tid == 0) {
-        int32_t b = s_best[0];
-        for (int w = 1; w < kHmmBlock / 32; ++w) b = max(b, s_best[w]);
-        atomicMax(&fr[u].best, b);
-    }
-}
-
-__global__ void hmm_frame_init_kernel(HmmFrame *fr, int n_utt, uint32_t *mask, int n_mask_words) {
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int i = i0; i < n_mask_words; i += stride) mask[i] = 0u;
-    for (int i = i0; i < n_utt; i += stride) { fr[i].best = kWorstScore; fr[i].n_keep = 0; }
-}
-
-// Pass 1 of the order-preserving compaction: keep flag + per-tile count.  A
-// tile is kTileIters * kHmmBlock consecutive HMMs of one utterance (few, fat
-// CTAs: the scan below and the mask merge of pass 3 scale with the tile count).
-// kTileIters = 8 for big populations, 1 when that would leave most SMs idle.
-template <int kTileIters>
-__global__ void __launch_bounds__(kHmmBlock)
-hmm_beam_flag_kernel(HmmPop p, const HmmFrame *fr, int32_t beam, uint8_t *keep, int32_t *block_count) {
-    __shared__ int32_t s_cnt[kHmmBlock / 32];
-    constexpr int kTile = kTileIters * kHmmBlock;
-    const int u = blockIdx.y, tid = threadIdx.x;
-    const int hi = p.utt_off[u + 1];
-    const int base = p.utt_off[u] + blockIdx.x * kTile + tid;
-    const int32_t thresh = fr[u].best + beam;
-    int32_t bs[kTileIters];
-#pragma unroll
-    for (int j = 0; j < kTileIters; ++j) {
-        const int i = base + j * kHmmBlock;
-        bs[j] = i < hi ? p.bestscore[i] : (int32_t)0x80000000;
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < kTileIters; ++j) {
-        const int i = base + j * kHmmBlock;
-        const bool k = i < hi && BT(bs[j], thresh);
-        if (i < hi) keep[i] = k ? 1 : 0;
-        cnt += k ? 1 : 0;
-    }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-        int t = 0;
-        for (int w = 0; w < kHmmBlock / 32; ++w) t += s_cnt[w];
-        block_count[u * gridDim.x + blockIdx.x] = t;
-    }
-}
-
-// Pass 2: exclusive scan of the block counts by one block (every thread owns a
-// contiguous run of counts: one pass, three barriers); per-utterance survivor
-// counts land in fr[u].n_keep, the total in *total.
-__global__ void __launch_bounds__(1024)
-hmm_scan_kernel(int32_t *block_count, int n_blocks, int blocks_per_utt, HmmFrame *fr, int n_utt, int32_t *total) {
-    __shared__ int32_t s_warp[32];
-    __shared__ int32_t s_total;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int per = (n_blocks + 1023) / 1024;
-    const int b0 = min(n_blocks, tid * per), b1 = min(n_blocks, b0 + per);
-    int32_t sum = 0;
-    for (int i = b0; i < b1; ++i) sum += block_count[i];
-    int32_t x = sum;
-    for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[w] = x;
-    __syncthreads();
-    if (w == 0) {
-        int32_t ws = s_warp[lane];
-        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
-        s_warp[lane] = ws;
-    }
-    __syncthreads();
-    const int32_t incl = x + (w ? s_warp[w - 1] : 0);
-    int32_t run = incl - sum;
-    for (int i = b0; i < b1; ++i) { const int32_t v = block_count[i]; block_count[i] = run; run += v; }
-    if (tid == 1023) { s_total = incl; *total = incl; }
-    __syncthreads();
-    for (int u = tid; u < n_utt; u += 1024) {
-        const int32_t b = block_count[u * blocks_per_utt];
-        const int32_t e = (u + 1 < n_utt) ? block_count[(u + 1) * blocks_per_utt] : s_total;
-        fr[u].n_keep = e - b;
-    }
-}
-
-// Pass 3: scatter survivors (order preserved) and OR their senones into the
-// utterance's active mask (acmod_activate_hmm).  One tile per CTA: the mask is
-// accumulated in shared memory and merged into the utterance's mask once.
-template <int NE, int kTileIters>
-__global__ void __launch_bounds__(kHmmBlock)
-hmm_scatter_kernel(HmmDev c, HmmPop p, const uint8_t *keep, const int32_t *block_off,
-                   int32_t *keep_idx, uint32_t *mask_all) {
-    // one flag BYTE per senone, set with plain stores (every writer stores the same 1, so no
-    // atomics and no serialisation of the many survivors that share a mask word), packed
-    // into words by ballots at the end
-    extern __shared__ uint32_t s_flag_w[];
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
-    constexpr int kTile = kTileIters * kHmmBlock;
-    constexpr int kWarps = kHmmBlock / 32, kCnt = kTileIters * kWarps;   // (row, warp) survivor counts
-    static_assert(kCnt <= 64, "offset scan handles two entries per lane");
-    __shared__ int32_t s_off[64];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int u = blockIdx.y;
-    const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-    if (lo + (int)blockIdx.x * kTile >= hi) return;
-    const int n_words = (c.n_sen + 31) / 32;
-    uint32_t *mask = mask_all + (size_t)u * n_words;
-    for (int k = tid; k < n_words * 8; k += kHmmBlock) s_flag_w[k] = 0u;
-    const int off = block_off[u * gridDim.x + blockIdx.x];
-    const int n = p.n_hmm;
-    const int base = lo + blockIdx.x * kTile + tid;
-    // all keep flags of the tile first, then ONE exclusive scan over the (row, warp)
-    // counts: the rows below need no barrier between them and their loads overlap
-    uint8_t kp[kTileIters];
-    unsigned bal[kTileIters];
-#pragma unroll
-    for (int j = 0; j < kTileIters; ++j) {
-        const int i = base + j * kHmmBlock;
-        kp[j] = i < hi ? keep[i] : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < kTileIters; ++j) {
-        bal[j] = __ballot_sync(0xffffffffu, kp[j] != 0);
-        if (lane == 0) s_off[j * kWarps + w] = __popc(bal[j]);
-    }
-    __syncthreads();
-    if (w == 0) {
-        const int32_t v0 = lane < kCnt ? s_off[lane] : 0, v1 = lane + 32 < kCnt ? s_off[lane + 32] : 0;
-        int32_t x0 = v0, x1 = v1;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int32_t y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
-            if (lane >= o) { x0 += y0; x1 += y1; }
-        }
-        const int32_t tot0 = __shfl_sync(0xffffffffu, x0, 31);
-        if (lane < kCnt) s_off[lane] = x0 - v0;
-        if (lane + 32 < kCnt) s_off[lane + 32] = tot0 + x1 - v1;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kTileIters; ++j) {
-        if (!kp[j]) continue;
-        const int i = base + j * kHmmBlock;
-        keep_idx[off + s_off[j * kWarps + w] + __popc(bal[j] & ((1u << lane) - 1u))] = i;
-        const bool mpx = p.mpx[i] != 0;
-#pragma unroll
-        for (int s = 0; s < NE; ++s) {
-            uint32_t id = p.senid[(size_t)s * n + i];
-            if (mpx) {
-                if (id == B200_BAD_SSID) continue;
-                id = c.sseq[(size_t)id * NE + s];
+        if (bx == 0)
+            for (int u = by; u < n_utt; u += gy) {
+                if (tid < 3) { HmmFrame f; f.best = kWorstScore; f.n_keep = 0; f.thresh = kWorstScore; f.pad = 0; r.fr3[(size_t)tid * n_utt + u] = f; }
             }
-            s_flag[id] = 1;
+    }
+    grid_barrier(r.bar, n_cta, epoch);
+
+    for (int f = 0; f < r.n_frames; ++f) {
+        const bool probe = r.probe && f == r.n_frames - 1 && bx == 0 && by == 0 && tid == 0;
+        if (probe) r.probe[0] = clock64();
+        HmmFrame *fr = r.fr3 + (size_t)((r.slot0 + f) % 3) * n_utt;
+        const int16_t *sen_frame = r.sen_base + (size_t)((r.frame0 + f) % r.n_cycle) * r.frame_stride;
+        // ------------------------------------------------ A: hmm_vit_eval
+        for (int u = by; u < n_utt; u += gy) {
+            const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+            if (lo + bx * kHmmBlock >= hi) continue;            // uniform per block
+            const int16_t *senscr = sen_frame + (size_t)u * c.n_sen;
+            __syncthreads();                                    // the previous row's readers are done
+            {
+                const int n16 = ((reinterpret_cast<size_t>(senscr) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
+                const int4 *src = reinterpret_cast<const int4 *>(senscr);
+                int4 *dst = reinterpret_cast<int4 *>(s_sen);
+                for (int i = tid; i < n16; i += kHmmBlock) dst[i] = src[i];
+                for (int i = n16 * 8 + tid; i < c.n_sen; i += kHmmBlock) s_sen[i] = senscr[i];
+            }
+            __syncthreads();
+            int32_t blockbest = kWorstScore;
+            for (int i = lo + bx * kHmmBlock + tid; i < hi; i += gx * kHmmBlock) {
+                HmmRegs h;
+#pragma unroll
+                for (int s = 0; s < NE; ++s) {
+                    h.sc[s] = p.score[(size_t)s * n + i];
+                    h.hi[s] = p.history[(size_t)s * n + i];
+                    h.sid[s] = p.senid[(size_t)s * n + i];
+                }
+                h.out_sc = p.out_score[i];
+                h.out_hi = p.out_history[i];
+                const uint8_t *tp = s_tp + (int)p.tmatid[i] * NE * (NE + 1);
+                const bool mpx = p.mpx[i] != 0;
+                if (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
+                else if (NE == 5) { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
+                else eval_any<NE>(h, tp, s_sen, c.sseq, mpx);
+#pragma unroll
+                for (int s = 0; s < NE; ++s) {
+                    p.score[(size_t)s * n + i] = h.sc[s];
+                    p.history[(size_t)s * n + i] = h.hi[s];
+                }
+                if (mpx) {
+#pragma unroll
+                    for (int s = 1; s < NE; ++s) p.senid[(size_t)s * n + i] = h.sid[s];
+                }
+                p.out_score[i] = h.out_sc;
+                p.out_history[i] = h.out_hi;
+                p.bestscore[i] = h.best;
+                blockbest = max(blockbest, h.best);
+            }
+            for (int o = 16; o > 0; o >>= 1) blockbest = max(blockbest, __shfl_xor_sync(0xffffffffu, blockbest, o));
+            if (lane == 0) s_wcnt[w] = blockbest;
+            __syncthreads();
+            if (tid == 0) {
+                int32_t b = s_wcnt[0];
+                for (int k = 1; k < kHmmBlock / 32; ++k) b = max(b, s_wcnt[k]);
+                atomicMax(&fr[u].best, b);
+            }
         }
+        if (!r.do_beam) continue;                               // (eval only: one frame per launch)
+        if (probe) r.probe[1] = clock64();
+        grid_barrier(r.bar, n_cta, epoch);
+        if (probe) r.probe[2] = clock64();
+
+        // ------------------------------------------------ B: beam test, counts
+        // All loads of the CTA's tiles of an utterance are issued before the first vote; the keep
+        // ballots stay in shared memory for phase C (no keep-byte array, no second read).
+        for (int u = by; u < n_utt; u += gy) {
+            const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+            if (f > 0)                                          // the previous frame's partial masks are complete (barrier 1)
+                merge_mask(r.mask_part + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx * n_words, gx, n_words,
+                           r.mask2 + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * n_words, bx, gx);
+            const int32_t thresh = fr[u].best + r.beam;
+            const int n_tiles = (hi - lo + kHmmBlock - 1) / kHmmBlock;
+            uint32_t *bal_u = s_bal + (size_t)((u - by) / gy) * rows * (kHmmBlock / 32);
+            int row = 0;
+            for (int t0 = bx; t0 < n_tiles; t0 += 4 * gx, row += 4) {
+                int32_t bs[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = lo + (t0 + j * gx) * kHmmBlock + tid;
+                    bs[j] = (t0 + j * gx < n_tiles && i < hi) ? p.bestscore[i] : (int32_t)0x80000000;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, BT(bs[j], thresh));
+                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * (kHmmBlock / 32) + w] = bal;
+                }
+            }
+            __syncthreads();
+            int cta_cnt = 0;
+            for (int rr = tid; bx + rr * gx < n_tiles; rr += kHmmBlock) {
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < kHmmBlock / 32; ++k) cnt += __popc(bal_u[rr * (kHmmBlock / 32) + k]);
+                r.tile_count[(size_t)u * r.tpu + bx + rr * gx] = cnt;
+                cta_cnt += cnt;
+            }
+            cta_cnt = block_sum2(cta_cnt, 0, s_red).x;
+            if (tid == 0) {
+                if (cta_cnt) atomicAdd(&fr[u].n_keep, cta_cnt);
+                if (bx == 0) fr[u].thresh = thresh;
+            }
+        }
+        if (probe) r.probe[3] = clock64();
+        grid_barrier(r.bar, n_cta, epoch);
+        if (probe) r.probe[4] = clock64();
+
+        // ------------------------------------------------ C: scatter + active senones
+        uint32_t *part_f = r.mask_part + (size_t)((r.mask0 + f) & 1) * n_utt * gx * n_words;
+        HmmFrame *fr_n2 = r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt;
+        for (int u = by; u < n_utt; u += gy) {
+            const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+            const int n_tiles = (hi - lo + kHmmBlock - 1) / kHmmBlock;
+            const uint32_t *bal_u = s_bal + (size_t)((u - by) / gy) * rows * (kHmmBlock / 32);
+            // survivors of the utterances before this one; the utterance's tile counts
+            int part = 0;
+            for (int k = tid; k < u; k += kHmmBlock) part += fr[k].n_keep;
+            for (int k = tid; k < n_tiles; k += kHmmBlock) s_tc[k] = r.tile_count[(size_t)u * r.tpu + k];
+            const int base = block_sum2(part, 0, s_red).x;      // (its barriers also publish s_tc)
+            if (bx == 0 && tid == 0) {
+                if (u == n_utt - 1) *r.total = base + fr[u].n_keep;
+                HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
+                fr_n2[u] = z;                                   // the record of the frame after next
+            }
+            uint32_t *part_u = part_f + ((size_t)u * gx + bx) * n_words;
+            if (bx >= n_tiles) {                                // (uniform) no tile of this utterance: an empty partial mask
+                for (int k = tid; k < n_words; k += kHmmBlock) part_u[k] = 0u;
+                continue;
+            }
+            for (int k = tid; k < n_words * 8; k += kHmmBlock) s_flag_w[k] = 0u;
+            // exclusive scan of the utterance's tile counts, in place (one pass: a chunk per thread,
+            // then a scan of the 256 chunk sums)
+            __syncthreads();
+            {
+                const int per = (n_tiles + kHmmBlock - 1) / kHmmBlock;
+                const int k0 = min(n_tiles, tid * per), k1 = min(n_tiles, k0 + per);
+                int sum = 0;
+                for (int k = k0; k < k1; ++k) sum += s_tc[k];
+                int x = sum;
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (lane == 31) s_wcnt[w] = x;
+                __syncthreads();
+                int wbase = 0;
+                for (int k = 0; k < w; ++k) wbase += s_wcnt[k];
+                int run = base + wbase + x - sum;
+                for (int k = k0; k < k1; ++k) { const int v = s_tc[k]; s_tc[k] = run; run += v; }
+            }
+            __syncthreads();
+            // four of my tiles at a time: every load of the batch is issued (unconditionally, on a
+            // clamped index) before the first use
+            for (int row0 = 0; bx + row0 * gx < n_tiles; row0 += 4) {
+                bool act[4]; int idx[4]; uint32_t sid[4][NE]; bool mp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = bx + (row0 + j) * gx;
+                    idx[j] = lo + t * kHmmBlock + tid;
+                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * (kHmmBlock / 32) + w] >> lane) & 1u);
+                    const int ii = min(idx[j], hi - 1);
+                    mp[j] = p.mpx[ii] != 0;
+#pragma unroll
+                    for (int s = 0; s < NE; ++s) sid[j][s] = p.senid[(size_t)s * n + ii];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int s = 0; s < NE; ++s)
+                        if (mp[j]) sid[j][s] = (act[j] && sid[j][s] != B200_BAD_SSID) ? c.sseq[(size_t)sid[j][s] * NE + s] : 0xffffffffu;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!act[j]) continue;
+                    const int row = row0 + j;
+                    const unsigned bal = bal_u[row * (kHmmBlock / 32) + w];
+                    int woff = 0;
+                    for (int k = 0; k < w; ++k) woff += __popc(bal_u[row * (kHmmBlock / 32) + k]);
+                    r.keep_idx[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = idx[j];
+#pragma unroll
+                    for (int s = 0; s < NE; ++s)
+                        if (sid[j][s] != 0xffffffffu) s_flag[sid[j][s]] = 1;
+                }
+            }
+            __syncthreads();
+            for (int kk = w; kk < n_words; kk += kHmmBlock / 32) {      // warp-uniform loop
+                const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
+                if (lane == 0) part_u[kk] = word;
+            }
+            __syncthreads();
+        }
+        if (probe) r.probe[5] = clock64();
     }
-    __syncthreads();
-    for (int kk = w; kk < n_words; kk += kWarps) {      // warp-uniform loop
-        const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
-        if (lane == 0 && word) atomicOr(&mask[kk], word);
+    if (r.do_beam && r.n_frames > 0) {                          // the last frame's mask
+        grid_barrier(r.bar, n_cta, epoch);
+        const int f = r.n_frames - 1;
+        for (int u = by; u < n_utt; u += gy)
+            merge_mask(r.mask_part + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx * n_words, gx, n_words,
+                       r.mask2 + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * n_words, bx, gx);
     }
 }
 
-// ------------------------------------------------------------ host launchers
-static size_t step_smem(const HmmDev &c) {
-    return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * c.n_emit * (c.n_emit + 1) + 16;
+// ------------------------------------------------------------ host launcher
+static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta) {
+    const int rows = (tpu + gx - 1) / gx + 3;
+    return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (((size_t)c.n_tmat * c.n_emit * (c.n_emit + 1) + 15) & ~(size_t)15) +
+           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (kHmmBlock / 32)) * 4 + 16;
 }
 
-int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, int32_t beam,
-                    HmmFrame *fr, uint8_t *keep, int32_t *block_count, int32_t *keep_idx,
-                    uint32_t *mask, int32_t *total, int do_beam, cudaStream_t st) {
-    const int n_words = (c.n_sen + 31) / 32;
-    if (p.n_hmm <= 0 || p.n_utt <= 0) return B200_OK;
-    const int bpu = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock;   // blocks per utterance
-    const int n_mask = n_words * p.n_utt;
-    hmm_frame_init_kernel<<<std::max(1, std::min(148, (n_mask + 255) / 256)), 256, 0, st>>>(fr, p.n_utt, mask, n_mask);
-    B200_LAUNCH_CHECK();
-    const size_t sh = step_smem(c);
-    if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
-    static AttrOnce attr;
+int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
+    if (p.n_hmm <= 0 || p.n_utt <= 0 || run_in.n_frames <= 0) return B200_OK;
     if (c.n_emit < 1 || c.n_emit > 5) { set_error("n_emit_state %d outside 1..5 (HMM_MAX_NSTATE)", c.n_emit); return B200_ERR_UNSUP; }
 #define B200_HMM_NE(...)                                   \
     switch (c.n_emit) {                                    \
@@ -525,58 +597,48 @@ int hmm_launch_step(const HmmDev &c, const HmmPop &p, const int16_t *d_senscr, i
     case 4: { constexpr int NE = 4; __VA_ARGS__; } break;  \
     default: { constexpr int NE = 5; __VA_ARGS__; } break; \
     }
+    static AttrOnce attr;
     if (attr.need()) {
-        for (int ne = 1; ne <= 5; ++ne) {
-            cudaError_t e = cudaSuccess;
-            switch (ne) {
-            case 1: e = cudaFuncSetAttribute(hmm_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
-            case 2: e = cudaFuncSetAttribute(hmm_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
-            case 3: e = cudaFuncSetAttribute(hmm_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
-            case 4: e = cudaFuncSetAttribute(hmm_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
-            default: e = cudaFuncSetAttribute(hmm_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); break;
-            }
-            B200_CUDA_OK(e);
-        }
-    }
-    // exactly one resident wave of CTAs (occupancy x SM count), split evenly over the
-    // utterances; each CTA strides its utterance's range
-    static size_t occ_sh[6] = {0, 0, 0, 0, 0, 0};
-    static int occ_wave[6] = {0, 0, 0, 0, 0, 0};   // CTAs in one resident wave, per kernel flavour
-    const int fl = c.n_emit;
-    if (occ_sh[fl] != sh || occ_wave[fl] == 0) {
-        int per_sm = 0, n_sm = 148, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_step_kernel<NE>, kHmmBlock, sh));
-        occ_wave[fl] = std::max(1, per_sm) * n_sm;
-        occ_sh[fl] = sh;
-    }
-    int gx = std::max(1, std::min(bpu, occ_wave[fl] / p.n_utt));
-    dim3 grid(gx, p.n_utt);
-    B200_HMM_NE(hmm_step_kernel<NE><<<grid, kHmmBlock, sh, st>>>(c, p, d_senscr, fr));
-    B200_LAUNCH_CHECK();
-    if (!do_beam) return B200_OK;
-    // fat tiles (8 x 256 HMMs per CTA) when that still fills the machine twice over, else one HMM per thread
-    const bool fat = (long long)((p.max_per_utt + 8 * kHmmBlock - 1) / (8 * kHmmBlock)) * p.n_utt >= 2 * 148;
-    const int tile = (fat ? 8 : 1) * kHmmBlock;
-    const int tpu = (p.max_per_utt + tile - 1) / tile;            // tiles per utterance (<= bpu)
-    dim3 g2(tpu, p.n_utt);
-    if (fat) hmm_beam_flag_kernel<8><<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
-    else hmm_beam_flag_kernel<1><<<g2, kHmmBlock, 0, st>>>(p, fr, beam, keep, block_count);
-    B200_LAUNCH_CHECK();
-    hmm_scan_kernel<<<1, 1024, 0, st>>>(block_count, tpu * p.n_utt, tpu, fr, p.n_utt, total);
-    B200_LAUNCH_CHECK();
-    const size_t msh = (size_t)n_words * 32;     // one flag byte per senone (<= 64 KB)
-    if (msh > 48 * 1024) {   // more than 12 288 senones: the flag bytes need the opt-in shared-memory size
         cudaError_t e = cudaSuccess;
-        B200_HMM_NE(e = fat ? cudaFuncSetAttribute(hmm_scatter_kernel<NE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024)
-                            : cudaFuncSetAttribute(hmm_scatter_kernel<NE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
-        B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
     }
-    if (fat) { B200_HMM_NE(hmm_scatter_kernel<NE, 8><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask)); }
-    else { B200_HMM_NE(hmm_scatter_kernel<NE, 1><<<g2, kHmmBlock, msh, st>>>(c, p, keep, block_count, keep_idx, mask)); }
+    // exactly one resident wave of CTAs (occupancy x SM count); the shared-memory need depends on
+    // the grid shape (tiles per CTA), so: shape from the occupancy at the base need, then re-check
+    const int bpu = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock;
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int gx = 1, gy = 1;
+    size_t sh = 0;
+    for (int per_sm_try = (c.n_emit == 3 ? 5 : 4); per_sm_try >= 1; --per_sm_try) {
+        const int wave = per_sm_try * n_sm;
+        gy = std::max(1, std::min(p.n_utt, wave));
+        gx = std::max(1, std::min(bpu, wave / gy));
+        sh = run_smem(c, bpu, gx, (p.n_utt + gy - 1) / gy);
+        if (sh > 200 * 1024) continue;
+        int per_sm = 0;
+        B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_run_kernel<NE>, kHmmBlock, sh));
+        if (per_sm >= per_sm_try) break;
+        if (per_sm_try == 1) { set_error("hmm step: population does not fit one resident wave (%zu B shared memory per CTA)", sh); return B200_ERR_UNSUP; }
+    }
+    if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
+    HmmRun r = run_in;
+    if ((size_t)2 * p.n_utt * gx * ((c.n_sen + 31) / 32) > run_in.mask_part_words) {
+        set_error("hmm step: partial-mask buffer too small (%zu words)", run_in.mask_part_words);
+        return B200_ERR_ARG;
+    }
+    HmmDev cc = c; HmmPop pp = p;
+    B200_CUDA_OK(cudaMemsetAsync(r.bar, 0, sizeof(unsigned), st));
+    void *args[] = {(void *)&cc, (void *)&pp, (void *)&r};
+    cudaError_t e = cudaSuccess;
+    B200_HMM_NE(e = cudaLaunchCooperativeKernel((const void *)hmm_run_kernel<NE>, dim3(gx, gy), dim3(kHmmBlock), args, sh, st));
 #undef B200_HMM_NE
-    B200_LAUNCH_CHECK();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    B200_CUDA_OK(e);
     return B200_OK;
 }
 
@@ -601,9 +663,11 @@ hmm_normalize_kernel(HmmPop p, int n_emit, const int32_t *__restrict__ best_per_
 // hmm_clear_scores (PS/hmm.c:169-180) for the HMMs the beam step dropped
 // (keep == 0): the `else` arm of prune_nonroot_chan, PS/ngram_search_fwdtree.c:864-866.
 __global__ void __launch_bounds__(kHmmBlock)
-hmm_clear_pruned_kernel(HmmPop p, int n_emit, const uint8_t *__restrict__ keep) {
-    const int i = blockIdx.x * kHmmBlock + threadIdx.x;
-    if (i >= p.n_hmm || keep[i]) return;
+hmm_clear_pruned_kernel(HmmPop p, int n_emit, const HmmFrame *__restrict__ fr) {
+    const int u = blockIdx.y;
+    const int i = p.utt_off[u] + blockIdx.x * kHmmBlock + threadIdx.x;
+    if (i >= p.utt_off[u + 1]) return;
+    if (BT(p.bestscore[i], fr[u].thresh)) return;         // kept by the last beam step
     for (int s = 0; s < n_emit; ++s) p.score[(size_t)s * p.n_hmm + i] = kWorstScore;
     p.out_score[i] = kWorstScore;
     p.bestscore[i] = kWorstScore;
@@ -651,9 +715,10 @@ int hmm_launch_normalize(const HmmPop &p, int n_emit, const int32_t *d_best_per_
     return B200_OK;
 }
 
-int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const uint8_t *keep, cudaStream_t st) {
+int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const HmmFrame *fr, cudaStream_t st) {
     if (p.n_hmm <= 0) return B200_OK;
-    hmm_clear_pruned_kernel<<<(p.n_hmm + kHmmBlock - 1) / kHmmBlock, kHmmBlock, 0, st>>>(p, n_emit, keep);
+    const int bpu = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock;
+    hmm_clear_pruned_kernel<<<dim3(bpu, p.n_utt), kHmmBlock, 0, st>>>(p, n_emit, fr);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
