@@ -111,10 +111,16 @@ def batch_pipeline(replicas, procs):
         res["speech_s"] = speech_s
         for hmm, kind in (("ptm", 1), ("hub4wsj_sc_8k", 2)):
             w_cpu, h_cpu = run_sharded(tmp, f"cpu_{hmm}", hmm, names, cepdir, ".mfc", [], False, procs)
-            # one GPU is time-sliced between processes (no MPS here): the plug-in is a one-process-per-GPU
-            # binding, so its arm runs with 2 decoder processes; 16 contexts on one GPU cost 35 s on this batch
-            plg_procs = min(2, procs)
+            # Every decoder process creates its own CUDA context on the one GPU; since round 2 a frame_eval
+            # of the ms / s2_semi back-ends costs no GPU work (the utterance's rows are on the host), so
+            # what the plug-in arm pays per process is that start-up.  Two shapes: one process per core,
+            # and 4 processes (fewer contexts, longer queues).
+            plg_procs = procs
             w_plg, h_plg = run_sharded(tmp, f"plg_{hmm}", hmm, names, cepdir, ".mfc", [], True, plg_procs)
+            w_plg4, h_plg4 = run_sharded(tmp, f"plg4_{hmm}", hmm, names, cepdir, ".mfc", [], True, min(4, procs))
+            # start-up alone: one process, one utterance, both arms
+            w_one_cpu, _ = run_sharded(tmp, f"one_cpu_{hmm}", hmm, names[:1], cepdir, ".mfc", [], False, 1)
+            w_one_plg, _ = run_sharded(tmp, f"one_plg_{hmm}", hmm, names[:1], cepdir, ".mfc", [], True, 1)
             # ---- GPU stage for the whole batch
             t0 = time.perf_counter()
             mm = b.mdef_maps(os.path.join(D, "hmm", hmm, "mdef"))
@@ -142,7 +148,10 @@ def batch_pipeline(replicas, procs):
                 "model": hmm, "frames": int(off[-1]),
                 "cpu": {"wall_s": w_cpu, "xrt_wall": w_cpu / speech_s},
                 "plugin": {"decoder_processes": plg_procs, "wall_s": w_plg, "xrt_wall": w_plg / speech_s, "identical_hyp_lines": h_plg == h_cpu,
-                           "identical_words": words(h_plg) == words(h_cpu)},
+                           "identical_words": words(h_plg) == words(h_cpu),
+                           "with_4_processes": {"wall_s": w_plg4, "identical_words": words(h_plg4) == words(h_cpu)},
+                           "one_process_one_utterance_wall_s": {"cpu": w_one_cpu, "plugin": w_one_plg,
+                                                                "note": "the difference is CUDA context creation + parameter upload"}},
                 "senin_pipeline": {"gpu_stage_s": t_score, "sen_write_s": t_write, "search_wall_s": w_sen,
                                    "wall_s": t_score + t_write + w_sen, "xrt_wall": (t_score + t_write + w_sen) / speech_s,
                                    "model_load_s_excluded": t_load, "identical_words": words(h_sen) == words(h_cpu),

@@ -68,6 +68,9 @@ struct b200_mgau {
     int16_t *h_row = nullptr;   // pinned; kernels write it directly (UVA), no per-frame D2H call
     uint8_t *h_active = nullptr; size_t h_active_cap = 0;   // pinned copy of the caller's active list, read by kernels directly
     float *h_frame = nullptr;   // pinned, one frame of features
+    // ms / s2_semi: the utterance's score rows on the host (pinned), copied once at utt_begin --
+    // frame_eval calls are then served without touching the GPU
+    int16_t *h_uraw = nullptr; size_t h_uraw_cap = 0;
 };
 
 namespace {
@@ -345,6 +348,7 @@ b200_mgau_t *b200_ms_load(const char *meanfile, const char *varfile, const char 
 void b200_mgau_free(b200_mgau_t *m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    if (m->h_uraw) cudaFreeHost(m->h_uraw);
     if (m->tc) tc_plan_free(m->tc);
     if (m->tct) tc_tied_free(m->tct);
     cudaFree(m->d_mean); cudaFree(m->d_var); cudaFree(m->d_det); cudaFree(m->d_mixw);
@@ -548,16 +552,72 @@ int b200_mgau_utt_begin_at(b200_mgau_t *m, const float *feat, int T, int frame0)
             m->carry_frame = frame0 + T - 1;
         }
     }
+    if (m->kind != 1) {
+        // ms: un-normalised rows (the normalisation depends on the caller's active set,
+        // PS/ms_mgau.c:226-248, and is applied by serve_frame on the host); s2_semi: final
+        // scores (normalised by each stream's own best codeword, independent of the active set)
+        if (m->kind == 2) {
+            if ((rc = ensure((void **)&m->d_uraw, &m->uraw_cap, (size_t)T * g.n_sen * 2))) return rc;
+            if ((rc = gmm_launch_tied_senone(g, m->d_ulists, T, 0, T, 1, nullptr, 0, m->d_uraw, st))) return rc;
+        }
+        const size_t bytes = (size_t)T * g.n_sen * 2;
+        if (m->h_uraw_cap < bytes) {
+            if (m->h_uraw) cudaFreeHost(m->h_uraw);
+            m->h_uraw = nullptr; m->h_uraw_cap = 0;
+            B200_CUDA_OK(cudaMallocHost((void **)&m->h_uraw, bytes));
+            m->h_uraw_cap = bytes;
+        }
+        B200_CUDA_OK(cudaMemcpyAsync(m->h_uraw, m->d_uraw, bytes, cudaMemcpyDeviceToHost, st));
+    }
     B200_CUDA_OK(cudaStreamSynchronize(st));
     m->utt_T = T;
+    return B200_OK;
+}
+
+// ms / s2_semi: one frame_eval from the host copy of the utterance's rows (no GPU work).
+static int serve_frame_host(b200_mgau_t *m, int frame, int16_t *senscr, const uint8_t *senone_active,
+                            int32_t n_active, int32_t compallsen) {
+    const int n_sen = m->g.n_sen;
+    const int16_t *row = m->h_uraw + (size_t)frame * n_sen;
+    if (!compallsen && (n_active < 0 || (n_active > 0 && !senone_active))) { set_error("bad active list"); return B200_ERR_ARG; }
+    if (m->kind == 2) {
+        // s2_semi_mgau_frame_eval: memset 0, then the active senones (s2_semi_mgau.c:840-886)
+        if (compallsen) { memcpy(senscr, row, (size_t)n_sen * 2); return B200_OK; }
+        memset(senscr, 0, (size_t)n_sen * 2);
+        int s = 0;
+        for (int i = 0; i < n_active; ++i) { s += senone_active[i]; if (s >= n_sen) break; senscr[s] = row[s]; }
+        return B200_OK;
+    }
+    // ms_cont_mgau_frame_eval: subtract the best of the scored (all / active) senones (ms_mgau.c:188-248)
+    int32_t best = 0x7fffffff;
+    if (compallsen) {
+        for (int i = 0; i < n_sen; ++i) best = std::min(best, (int32_t)row[i]);
+        for (int i = 0; i < n_sen; ++i) {
+            const int32_t v = (int32_t)row[i] - best;
+            senscr[i] = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+        }
+        return B200_OK;
+    }
+    int s = 0;
+    for (int i = 0; i < n_active; ++i) { s += senone_active[i]; if (s >= n_sen) break; best = std::min(best, (int32_t)row[s]); }
+    s = 0;
+    for (int i = 0; i < n_active; ++i) {
+        s += senone_active[i];
+        if (s >= n_sen) break;
+        const int32_t v = (int32_t)row[s] - best;
+        senscr[s] = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+    }
     return B200_OK;
 }
 
 static int serve_frame(b200_mgau_t *m, int frame, int16_t *senscr, const uint8_t *senone_active,
                        int32_t n_active, int32_t compallsen) {
     const GmmDev &g = m->g;
+    if (m->kind != 1) return serve_frame_host(m, frame, senscr, senone_active, n_active, compallsen);
     cudaStream_t st = m->st[0];
     const bool use_active = !compallsen;
+    // ptm: the normalisation depends on which CODEBOOKS the active senones touch
+    // (PS/ptm_mgau.c:267-288), so the mixing stage runs on the device per frame.
     // Per-frame serving is latency bound (one call per frame of the decoder's
     // search): the active list and the result row live in pinned host memory
     // that the kernels read / write directly, so a frame costs one or two

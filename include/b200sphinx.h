@@ -244,10 +244,18 @@ int  b200_mgau_frame_eval(b200_mgau_t *m, int16_t *senscr,
                           int32_t compallsen);
 
 /* Utterance-batched variant used by the plug-in: score all T frames of an
- * utterance once (dense, un-normalised pieces kept on the host), then serve
- * frame_eval calls from the cache applying the active-set-dependent
- * normalisation (ms: PS/ms_mgau.c:226-248; ptm: PS/ptm_mgau.c:267-288,390-397)
- * on the host with the caller's active list. */
+ * utterance once, then serve frame_eval calls from the cache with the caller's
+ * active list.
+ *   ms      : the dense un-normalised rows are copied to pinned host memory at
+ *             utt_begin; utt_frame applies the active-set-dependent
+ *             normalisation (PS/ms_mgau.c:226-248) on the host -- no GPU work
+ *             per frame;
+ *   s2_semi : the final scores (normalised per stream, independent of the active
+ *             set) are copied to the host at utt_begin; utt_frame copies / masks
+ *             a row -- no GPU work per frame;
+ *   ptm     : the top-N lists stay on the device; utt_frame runs the mixing stage
+ *             there, because its normalisation depends on which codebooks the
+ *             active senones touch (PS/ptm_mgau.c:267-288,390-397). */
 int  b200_mgau_utt_begin(b200_mgau_t *m, const float *feat, int T);
 /* Same, for a block of frames that starts at utterance frame `frame0` (live
  * mode hands the decoder's buffered frames over piecewise).  Only s2_semi with
