@@ -37,6 +37,12 @@ class HmmSoa(C.Structure):
                 ("tmatid", c_i16p), ("mpx", c_u8p), ("bestscore", c_i32p)]
 
 
+class S3HmmSoa(C.Structure):
+    _fields_ = [("n_hmm", C.c_int32), ("score", c_i32p), ("history", c_i32p), ("ssid", c_i32p),
+                ("out_score", c_i32p), ("out_history", c_i32p), ("bestscore", c_i32p),
+                ("tmatid", c_i32p), ("mpx", c_u8p)]
+
+
 def _sig(name, restype, *argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -89,6 +95,8 @@ _sig("b200_mgau_timing_avg", C.c_float, vp, C.c_int, C.c_int)
 _sig("b200_hmm_ctx_create", vp, C.c_int, c_u8p, C.c_int, c_u16p, C.c_int, C.c_int, C.c_int)
 _sig("b200_hmm_ctx_free", None, vp)
 _sig("b200_hmm_eval_host", C.c_int, vp, C.POINTER(HmmSoa), c_i16p, C.c_int, c_i32p)
+_sig("b200_s3hmm_eval_host", C.c_int, C.c_int, c_i32p, C.c_int, c_i16p, C.c_int, C.c_int, C.POINTER(S3HmmSoa), c_i32p,
+     C.c_int, c_i32p, C.c_int)
 _sig("b200_hmm_pop_upload", C.c_int, vp, C.POINTER(HmmSoa))
 _sig("b200_hmm_pop_download", C.c_int, vp, C.POINTER(HmmSoa))
 _sig("b200_hmm_pop_set_utts", C.c_int, vp, C.c_int, c_i32p)

@@ -426,6 +426,29 @@ class HmmPopulation:
         return s
 
 
+def s3hmm_vit_eval(n_emit: int, tp, sseq, n_sen: int, senscr, score, history, out_score, out_history, ssid, tmatid, mpx,
+                   bestscore, device: int = 0):
+    """sphinx3's hmm_vit_eval (libs3decoder/libam/hmm.c:852-873) for every HMM, once per row of
+    senscr ([n_frames][n_sen] int32).  State-major int32 arrays [n_emit][n_hmm] (score, history,
+    ssid), updated in place; tp int32 [n_tmat][n_emit][n_emit + 1]; sseq int16 [n_sseq][n_emit].
+    Returns the per-frame best scores."""
+    tp, sseq = _c(tp, np.int32), _c(sseq, np.int16)
+    senscr = _c(senscr, np.int32).reshape(-1, n_sen)
+    for a in (score, history, ssid, out_score, out_history, bestscore):
+        assert a.dtype == np.int32 and a.flags.c_contiguous
+    tm, mp = _c(tmatid, np.int32), _c(mpx, np.uint8)
+    soa = _lib.S3HmmSoa()
+    soa.n_hmm = out_score.shape[0]
+    soa.score, soa.history, soa.ssid = _p(score, C.c_int32), _p(history, C.c_int32), _p(ssid, C.c_int32)
+    soa.out_score, soa.out_history, soa.bestscore = _p(out_score, C.c_int32), _p(out_history, C.c_int32), _p(bestscore, C.c_int32)
+    soa.tmatid, soa.mpx = _p(tm, C.c_int32), _p(mp, C.c_uint8)
+    best = np.zeros(senscr.shape[0], np.int32)
+    check(lib.b200_s3hmm_eval_host(n_emit, _p(tp, C.c_int32), tp.shape[0], _p(sseq, C.c_int16), sseq.shape[0], n_sen,
+                                   C.byref(soa), _p(senscr, C.c_int32), senscr.shape[0], _p(best, C.c_int32), device),
+          "s3hmm_eval_host")
+    return best
+
+
 class HmmContext:
     """hmm_context_t on the GPU: hmm_context_init(n_emit, tp, senscore, sseq)."""
 

@@ -525,6 +525,29 @@ void *b200_host_alloc_pinned(size_t bytes);
 void  b200_host_free_pinned(void *p);
 int   b200_dev_sync(int device);
 
+/* ------------------------------------------------------------------------
+ * sphinx3's flavour of hmm_vit_eval (sphinx3/src/libs3decoder/libam/hmm.c:285-873,
+ * dispatcher :852-873): int32 transition log-probabilities and int32 senone scores
+ * that are ADDED, WORST_SCORE = S3_LOGPROB_ZERO = 0xc8000000 (s3types.h:192),
+ * int32 senone-sequence ids (-1 = none), senone ids through sseq[ssid][state] for
+ * mpx and non-mpx HMMs alike (hmm.h:218-226).  State-major SoA mirror of
+ * sphinx3's hmm_t (hmm.h:184-197):
+ *   score/history/ssid [n_emit][n_hmm] (non-mpx HMMs use ssid row 0 only),
+ *   out_score/out_history/bestscore [n_hmm], tmatid [n_hmm], mpx [n_hmm].
+ * tp: [n_tmat][n_emit][n_emit + 1] (what ctx->tp[tmatid][0] points at, row stride
+ * n_emit + 1: hmm_tprob_3st(i, j) = tp[i * 4 + j]); sseq: s3senid_t
+ * [n_sseq][n_emit]; senscr: [n_frames][n_sen].  Evaluates every HMM once per
+ * frame (the population is updated in place), best_out[f] = best score of frame f. */
+typedef struct {
+    int32_t n_hmm;
+    int32_t *score, *history, *ssid;
+    int32_t *out_score, *out_history, *bestscore;
+    const int32_t *tmatid;
+    const uint8_t *mpx;
+} b200_s3hmm_soa_t;
+int  b200_s3hmm_eval_host(int n_emit, const int32_t *tp, int n_tmat, const int16_t *sseq, int n_sseq, int n_sen,
+                          b200_s3hmm_soa_t *h, const int32_t *senscr, int n_frames, int32_t *best_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -582,3 +582,46 @@ ref_hmm_eval_batch(int n_emit, int n_hmm, const uint8 *tp, int n_tmat,
     ckd_free_3d(tpp);
     return best;
 }
+
+/* hmm_clear_scores / hmm_normalize / hmm_enter (hmm.c:169-218) on SoA arrays
+ * [n_hmm][n_emit] (score, history) + out_score, out_history, bestscore:
+ *   op 0: hmm_clear_scores(h) for every HMM with sel[i] != 0
+ *   op 1: hmm_normalize(h, arg[i]) for every HMM
+ *   op 2: the callers' entry loop (ngram_search_fwdtree.c:757,846): for k in
+ *         0..n_list-1: if (lscore[k] BETTER_THAN hmm_in_score(h[lidx[k]]))
+ *         hmm_enter(h[lidx[k]], lscore[k], lhist[k], frame) */
+int
+ref_hmm_maint(int op, int n_emit, int n_hmm, int32 *score, int32 *history, int32 *out_score,
+              int32 *out_history, int32 *bestscore, const uint8 *sel, const int32 *arg,
+              int n_list, const int32 *lidx, const int32 *lscore, const int32 *lhist)
+{
+    static uint8 tp1[HMM_MAX_NSTATE * (HMM_MAX_NSTATE + 1)];
+    uint8 ***tpp = (uint8 ***)ckd_calloc_3d(1, n_emit, n_emit + 1, sizeof(uint8));
+    hmm_context_t *ctx = hmm_context_init(n_emit, (uint8 ** const *)tpp, NULL, NULL);
+    hmm_t *hm = ckd_calloc(n_hmm, sizeof(*hm));
+    int i, j, k;
+    (void)tp1;
+    for (i = 0; i < n_hmm; ++i) {
+        hmm_t *h = &hm[i];
+        h->ctx = ctx; h->mpx = 0; h->n_emit_state = n_emit; h->frame = -1;
+        for (j = 0; j < n_emit; ++j) { h->score[j] = score[i * n_emit + j]; h->history[j] = history[i * n_emit + j]; }
+        h->out_score = out_score[i]; h->out_history = out_history[i]; h->bestscore = bestscore[i];
+    }
+    if (op == 0) { for (i = 0; i < n_hmm; ++i) if (sel[i]) hmm_clear_scores(&hm[i]); }
+    else if (op == 1) { for (i = 0; i < n_hmm; ++i) hmm_normalize(&hm[i], arg[i]); }
+    else if (op == 2) {
+        for (k = 0; k < n_list; ++k) {
+            hmm_t *h = &hm[lidx[k]];
+            if (lscore[k] BETTER_THAN hmm_in_score(h)) hmm_enter(h, lscore[k], lhist[k], 1);
+        }
+    }
+    for (i = 0; i < n_hmm; ++i) {
+        hmm_t *h = &hm[i];
+        for (j = 0; j < n_emit; ++j) { score[i * n_emit + j] = h->score[j]; history[i * n_emit + j] = h->history[j]; }
+        out_score[i] = h->out_score; out_history[i] = h->out_history; bestscore[i] = h->bestscore;
+    }
+    hmm_context_free(ctx);
+    ckd_free(hm);
+    ckd_free_3d(tpp);
+    return 0;
+}

@@ -177,3 +177,63 @@ ref_s3_close(void *vh)
     logmath_free(h->lmath);
     ckd_free(h);
 }
+
+/* ------------------------------------------------- sphinx3 hmm_vit_eval
+ * Batched over HMM-major arrays (score/history/ssid [n_hmm][n_emit]); tp is
+ * [n_tmat][n_emit][n_emit + 1] int32 (the hmm_tprob_3st / _5st macros index
+ * ctx->tp[tmatid][0] with a row stride of n_emit + 1), sseq [n_sseq][n_emit]. */
+#include "hmm.h"
+int32
+ref_s3hmm_eval_batch(int n_emit, int n_hmm, const int32 *tp, int n_tmat, const int16 *sseq, int n_sseq,
+                     const int32 *senscr, int32 *score, int32 *history, int32 *out_score, int32 *out_history,
+                     int32 *ssid, const int32 *tmatid, const uint8 *mpx, int32 *bestscore, int repeat)
+{
+    int32 ***tpp = (int32 ***)ckd_calloc_3d(n_tmat, n_emit + 1, n_emit + 1, sizeof(int32));
+    s3senid_t **ss = ckd_calloc(n_sseq, sizeof(*ss));
+    hmm_context_t *ctx;
+    hmm_t *hm = ckd_calloc(n_hmm, sizeof(*hm));
+    int32 best = S3_LOGPROB_ZERO;
+    int i, j, k, r;
+    for (i = 0; i < n_tmat; ++i)
+        for (j = 0; j < n_emit; ++j)
+            for (k = 0; k <= n_emit; ++k)
+                tpp[i][j][k] = tp[((size_t)i * n_emit + j) * (n_emit + 1) + k];
+    for (i = 0; i < n_sseq; ++i) ss[i] = (s3senid_t *)(sseq + (size_t)i * n_emit);
+    ctx = hmm_context_init(n_emit, tpp, (int32 *)senscr, ss);
+    for (i = 0; i < n_hmm; ++i) {
+        hmm_t *h = &hm[i];
+        hmm_init(ctx, h, mpx[i], ssid[(size_t)i * n_emit], tmatid[i]);
+        for (j = 0; j < n_emit; ++j) {
+            hmm_score(h, j) = score[(size_t)i * n_emit + j];
+            hmm_history(h, j) = history[(size_t)i * n_emit + j];
+            if (mpx[i]) hmm_mpx_ssid(h, j) = ssid[(size_t)i * n_emit + j];
+        }
+        hmm_out_score(h) = out_score[i];
+        hmm_out_history(h) = out_history[i];
+        hmm_bestscore(h) = bestscore[i];
+    }
+    for (r = 0; r < (repeat > 0 ? repeat : 1); ++r) {
+        best = S3_LOGPROB_ZERO;
+        for (i = 0; i < n_hmm; ++i) {
+            int32 b = hmm_vit_eval(&hm[i]);
+            if (b > best) best = b;
+        }
+    }
+    for (i = 0; i < n_hmm; ++i) {
+        hmm_t *h = &hm[i];
+        for (j = 0; j < n_emit; ++j) {
+            score[(size_t)i * n_emit + j] = hmm_score(h, j);
+            history[(size_t)i * n_emit + j] = (int32)hmm_history(h, j);
+            if (mpx[i]) ssid[(size_t)i * n_emit + j] = hmm_mpx_ssid(h, j);
+        }
+        out_score[i] = hmm_out_score(h);
+        out_history[i] = (int32)hmm_out_history(h);
+        bestscore[i] = hmm_bestscore(h);
+        hmm_deinit(h);
+    }
+    hmm_context_free(ctx);
+    ckd_free(hm);
+    ckd_free(ss);
+    ckd_free_3d((void ***)tpp);
+    return best;
+}

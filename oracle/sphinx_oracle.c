@@ -1415,3 +1415,231 @@ orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
     free(buf); free(row); free(tmp);
     return out_len;
 }
+
+/* ======================================================================
+ * sphinx3's hmm_vit_eval flavour (sphinx3/src/libs3decoder/libam/hmm.c:285-873):
+ * int32 tp and senone scores that are added, WORST = S3_LOGPROB_ZERO
+ * (s3types.h:192), int32 ssids (-1 = none), senone ids via sseq[ssid][state].
+ * HMM-major arrays [n_hmm][n_emit]; non-mpx HMMs use ssid[i][0].
+ * TEST INFRASTRUCTURE ONLY.
+ * ====================================================================== */
+#define S3W ((int32_t)0xc8000000)
+#define S3TP(i, j) tp[(i) * (ne + 1) + (j)]
+#define S3SEN(id, st) sen[sseq[(size_t)(id) * ne + (st)]]
+/* new score of a state with a self loop (a), a one-step (b, from state fb) and a two-step
+ * (c2, from state fc) entry: the reference's nested comparison -- on a == b the one-step path
+ * wins, c2 must beat the winner strictly */
+#define S3_PICK3(dst, a, b, c2, fb, fc)                                              \
+    do {                                                                             \
+        if ((a) > (b)) { if ((c2) > (a)) { dst = (c2); from = (fc); } else { dst = (a); from = -1; } } \
+        else { if ((c2) > (b)) { dst = (c2); from = (fc); } else { dst = (b); from = (fb); } }          \
+    } while (0)
+
+static int32_t s3hmm_one(int ne, const int32_t *tp, const int16_t *sseq, const int32_t *sen, int32_t *sc, int32_t *hi,
+                         int32_t *ssid, int mpx, int32_t *out_sc, int32_t *out_hi)
+{
+    int32_t best = S3W, from = -1;
+    if (ne != 3 && ne != 5) {           /* hmm_vit_eval_anytopo, hmm.c:776-850 */
+        int32_t st[5], nsc[5], nhi[5], nss[5], scr, bf;
+        int s, f, to;
+        for (s = 0; s < ne; ++s) {
+            int32_t id = mpx ? ssid[s] : ssid[0];
+            st[s] = sc[s] + (id == -1 ? S3W : S3SEN(id, s));
+            if (s > 0 && st[s] < S3W) st[s] = S3W;
+            nhi[s] = hi[s]; nss[s] = ssid[s];
+        }
+        scr = S3W; bf = -1;
+        for (f = ne - 1; f >= 0; --f)
+            if (S3TP(f, ne) > S3W && st[f] + S3TP(f, ne) > scr) { scr = st[f] + S3TP(f, ne); bf = f; }
+        *out_sc = scr;
+        if (bf >= 0) *out_hi = hi[bf];
+        best = scr;
+        for (to = ne - 1; to >= 0; --to) {
+            scr = S3TP(to, to) > S3W ? st[to] + S3TP(to, to) : S3W;
+            bf = -1;
+            for (f = to - 1; f >= 0; --f)
+                if (S3TP(f, to) > S3W && st[f] + S3TP(f, to) > scr) { scr = st[f] + S3TP(f, to); bf = f; }
+            nsc[to] = scr;
+            if (bf >= 0) { nhi[to] = hi[bf]; if (mpx) nss[to] = ssid[bf]; }
+            if (best < scr) best = scr;
+        }
+        for (s = 0; s < ne; ++s) { sc[s] = nsc[s]; hi[s] = nhi[s]; if (mpx) ssid[s] = nss[s]; }
+        return best;
+    }
+    if (ne == 3 && !mpx) {              /* hmm.c:592-671 */
+        int32_t s3, s2, s1, s0, t0, t1, t2;
+        s2 = sc[2] + S3SEN(ssid[0], 2); s1 = sc[1] + S3SEN(ssid[0], 1); s0 = sc[0] + S3SEN(ssid[0], 0);
+        t0 = t1 = S3W; t2 = INT32_MIN;
+        if (s2 > S3W) { t1 = s2 + S3TP(2, 3); t0 = s2 + S3TP(2, 2); }
+        if (s1 > S3W && S3TP(1, 3) > S3W) t2 = s1 + S3TP(1, 3);
+        if (t1 > t2) { s3 = t1; *out_hi = hi[2]; } else { s3 = t2; *out_hi = hi[1]; }
+        if (s3 < S3W) s3 = S3W;
+        *out_sc = s3; best = s3;
+        t1 = t2 = S3W;
+        if (s1 > S3W) t1 = s1 + S3TP(1, 2);
+        if (S3TP(0, 2) > S3W) t2 = s0 + S3TP(0, 2);
+        S3_PICK3(s2, t0, t1, t2, 1, 0);
+        if (from >= 0) hi[2] = hi[from];
+        if (s2 < S3W) s2 = S3W;
+        if (s2 > best) best = s2;
+        sc[2] = s2;
+        t0 = t1 = S3W;
+        if (s1 > S3W) t0 = s1 + S3TP(1, 1);
+        if (s0 > S3W) t1 = s0 + S3TP(0, 1);
+        if (t0 > t1) s1 = t0; else { s1 = t1; hi[1] = hi[0]; }
+        if (s1 < S3W) s1 = S3W;
+        if (s1 > best) best = s1;
+        sc[1] = s1;
+        s0 += S3TP(0, 0);
+        if (s0 < S3W) s0 = S3W;
+        if (s0 > best) best = s0;
+        sc[0] = s0;
+        return best;
+    }
+    if (ne == 3) {                      /* mpx, hmm.c:673-774 */
+        int32_t s3, s2, s1, s0, t0, t1, t2 = INT32_MIN;
+        if (ssid[2] == -1) s2 = t1 = S3W;
+        else { s2 = sc[2] + S3SEN(ssid[2], 2); if (s2 < S3W) s2 = S3W; t1 = s2 + S3TP(2, 3); }
+        if (ssid[1] == -1) s1 = S3W;
+        else { s1 = sc[1] + S3SEN(ssid[1], 1); if (s1 < S3W) s1 = S3W; t2 = s1 + S3TP(1, 3); }
+        if (t1 > t2) { s3 = t1; *out_hi = hi[2]; } else { s3 = t2; *out_hi = hi[1]; }
+        if (s3 < S3W) s3 = S3W;
+        *out_sc = s3; best = s3;
+        s0 = sc[0] + S3SEN(ssid[0], 0);
+        if (s0 < S3W) s0 = S3W;
+        t0 = t1 = S3W;
+        if (s2 != S3W) t0 = s2 + S3TP(2, 2);
+        if (s1 != S3W) t1 = s1 + S3TP(1, 2);
+        if (S3TP(0, 2) > S3W) t2 = s0 + S3TP(0, 2);
+        S3_PICK3(s2, t0, t1, t2, 1, 0);
+        if (from >= 0) { hi[2] = hi[from]; ssid[2] = ssid[from]; }
+        if (s2 < S3W) s2 = S3W;
+        if (s2 > best) best = s2;
+        sc[2] = s2;
+        t0 = S3W;
+        if (s1 != S3W) t0 = s1 + S3TP(1, 1);
+        t1 = s0 + S3TP(0, 1);
+        if (t0 > t1) s1 = t0; else { s1 = t1; hi[1] = hi[0]; ssid[1] = ssid[0]; }
+        if (s1 < S3W) s1 = S3W;
+        if (s1 > best) best = s1;
+        sc[1] = s1;
+        s0 += S3TP(0, 0);
+        if (s0 < S3W) s0 = S3W;
+        if (s0 > best) best = s0;
+        sc[0] = s0;
+        return best;
+    }
+    if (!mpx) {                         /* 5 states, hmm.c:285-414 */
+        int32_t s5, s4, s3, s2, s1, s0, t0, t1, t2;
+        s4 = sc[4] + S3SEN(ssid[0], 4); s3 = sc[3] + S3SEN(ssid[0], 3);
+        if (s3 > S3W) {
+            t1 = s4 + S3TP(4, 5); t2 = s3 + S3TP(3, 5);
+            if (t1 > t2) { s5 = t1; *out_hi = hi[4]; } else { s5 = t2; *out_hi = hi[3]; }
+            if (s5 < S3W) s5 = S3W;
+            *out_sc = s5; best = s5;
+        }
+        s2 = sc[2] + S3SEN(ssid[0], 2);
+        if (s2 > S3W) {
+            t0 = s4 + S3TP(4, 4); t1 = s3 + S3TP(3, 4); t2 = s2 + S3TP(2, 4);
+            S3_PICK3(s4, t0, t1, t2, 3, 2);
+            if (from >= 0) hi[4] = hi[from];
+            if (s4 < S3W) s4 = S3W;
+            if (s4 > best) best = s4;
+            sc[4] = s4;
+        }
+        s1 = sc[1] + S3SEN(ssid[0], 1);
+        if (s1 > S3W) {
+            t0 = s3 + S3TP(3, 3); t1 = s2 + S3TP(2, 3); t2 = s1 + S3TP(1, 3);
+            S3_PICK3(s3, t0, t1, t2, 2, 1);
+            if (from >= 0) hi[3] = hi[from];
+            if (s3 < S3W) s3 = S3W;
+            if (s3 > best) best = s3;
+            sc[3] = s3;
+        }
+        s0 = sc[0] + S3SEN(ssid[0], 0);
+        t0 = s2 + S3TP(2, 2); t1 = s1 + S3TP(1, 2); t2 = s0 + S3TP(0, 2);
+        S3_PICK3(s2, t0, t1, t2, 1, 0);
+        if (from >= 0) hi[2] = hi[from];
+        if (s2 < S3W) s2 = S3W;
+        if (s2 > best) best = s2;
+        sc[2] = s2;
+        t0 = s1 + S3TP(1, 1); t1 = s0 + S3TP(0, 1);
+        if (t0 > t1) s1 = t0; else { s1 = t1; hi[1] = hi[0]; }
+        if (s1 < S3W) s1 = S3W;
+        if (s1 > best) best = s1;
+        sc[1] = s1;
+        s0 += S3TP(0, 0);
+        if (s0 < S3W) s0 = S3W;
+        if (s0 > best) best = s0;
+        sc[0] = s0;
+        return best;
+    }
+    {                                   /* 5 states, mpx, hmm.c:416-586 */
+        int32_t s5, s4, s3, s2, s1, s0, t0, t1, t2;
+        if (ssid[4] == -1) s4 = t1 = S3W; else { s4 = sc[4] + S3SEN(ssid[4], 4); t1 = s4 + S3TP(4, 5); }
+        if (ssid[3] == -1) s3 = t2 = S3W; else { s3 = sc[3] + S3SEN(ssid[3], 3); t2 = s3 + S3TP(3, 5); }
+        if (t1 > t2) { s5 = t1; *out_hi = hi[4]; } else { s5 = t2; *out_hi = hi[3]; }
+        if (s5 < S3W) s5 = S3W;
+        *out_sc = s5; best = s5;
+        if (ssid[2] == -1) s2 = t2 = S3W; else { s2 = sc[2] + S3SEN(ssid[2], 2); t2 = s2 + S3TP(2, 4); }
+        t0 = t1 = S3W;
+        if (s4 != S3W) t0 = s4 + S3TP(4, 4);
+        if (s3 != S3W) t1 = s3 + S3TP(3, 4);
+        S3_PICK3(s4, t0, t1, t2, 3, 2);
+        if (from >= 0) { hi[4] = hi[from]; ssid[4] = ssid[from]; }
+        if (s4 < S3W) s4 = S3W;
+        if (s4 > best) best = s4;
+        sc[4] = s4;
+        if (ssid[1] == -1) s1 = t2 = S3W; else { s1 = sc[1] + S3SEN(ssid[1], 1); t2 = s1 + S3TP(1, 3); }
+        t0 = t1 = S3W;
+        if (s3 != S3W) t0 = s3 + S3TP(3, 3);
+        if (s2 != S3W) t1 = s2 + S3TP(2, 3);
+        S3_PICK3(s3, t0, t1, t2, 2, 1);
+        if (from >= 0) { hi[3] = hi[from]; ssid[3] = ssid[from]; }
+        if (s3 < S3W) s3 = S3W;
+        if (s3 > best) best = s3;
+        sc[3] = s3;
+        s0 = sc[0] + S3SEN(ssid[0], 0);
+        t0 = t1 = S3W;
+        if (s2 != S3W) t0 = s2 + S3TP(2, 2);
+        if (s1 != S3W) t1 = s1 + S3TP(1, 2);
+        t2 = s0 + S3TP(0, 2);
+        S3_PICK3(s2, t0, t1, t2, 1, 0);
+        if (from >= 0) { hi[2] = hi[from]; ssid[2] = ssid[from]; }
+        if (s2 < S3W) s2 = S3W;
+        if (s2 > best) best = s2;
+        sc[2] = s2;
+        t0 = S3W;
+        if (s1 != S3W) t0 = s1 + S3TP(1, 1);
+        t1 = s0 + S3TP(0, 1);
+        if (t0 > t1) s1 = t0; else { s1 = t1; hi[1] = hi[0]; ssid[1] = ssid[0]; }
+        if (s1 < S3W) s1 = S3W;
+        if (s1 > best) best = s1;
+        sc[1] = s1;
+        s0 += S3TP(0, 0);
+        if (s0 < S3W) s0 = S3W;
+        if (s0 > best) best = s0;
+        sc[0] = s0;
+        return best;
+    }
+}
+
+int32_t orc_s3hmm_eval_batch(int ne, int n_hmm, const int32_t *tp, int n_tmat, const int16_t *sseq, int n_sseq,
+                             const int32_t *sen, int32_t *score, int32_t *history, int32_t *out_score,
+                             int32_t *out_history, int32_t *ssid, const int32_t *tmatid, const uint8_t *mpx,
+                             int32_t *bestscore, int repeat)
+{
+    int32_t best = S3W;
+    int r, i;
+    (void)n_tmat; (void)n_sseq;
+    for (r = 0; r < (repeat > 0 ? repeat : 1); ++r) {
+        best = S3W;
+        for (i = 0; i < n_hmm; ++i) {
+            int32_t b = s3hmm_one(ne, tp + (size_t)tmatid[i] * ne * (ne + 1), sseq, sen, score + (size_t)i * ne,
+                                  history + (size_t)i * ne, ssid + (size_t)i * ne, mpx[i], &out_score[i], &out_history[i]);
+            bestscore[i] = b;
+            if (b > best) best = b;
+        }
+    }
+    return best;
+}

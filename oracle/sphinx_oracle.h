@@ -173,4 +173,10 @@ int orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
 #ifdef __cplusplus
 }
 #endif
+/* sphinx3's hmm_vit_eval flavour (libs3decoder/libam/hmm.c:285-873), HMM-major arrays */
+int32_t orc_s3hmm_eval_batch(int ne, int n_hmm, const int32_t *tp, int n_tmat, const int16_t *sseq, int n_sseq,
+                             const int32_t *sen, int32_t *score, int32_t *history, int32_t *out_score,
+                             int32_t *out_history, int32_t *ssid, const int32_t *tmatid, const uint8_t *mpx,
+                             int32_t *bestscore, int repeat);
+
 #endif

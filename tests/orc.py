@@ -115,8 +115,30 @@ def ref():
         L.ref_hmm_eval_batch.restype = C.c_int32
         L.ref_hmm_eval_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_int, u16p, C.c_int, i16p, i32p, i32p, i32p,
                                          i32p, u16p, u16p, i16p, u8p, i32p, C.c_int]
+        L.ref_hmm_maint.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, u8p, i32p, C.c_int, i32p,
+                                    i32p, i32p]
         _ref = L
     return _ref
+
+
+def ref_hmm_maint(op, score, history, out_score, out_history, bestscore, sel=None, arg=None, lidx=None, lscore=None,
+                  lhist=None):
+    """The reference's hmm_clear_scores (op 0, on sel) / hmm_normalize (op 1, by arg) / entry loop with
+    hmm_enter (op 2, list order) on HMM-major arrays [n_hmm][n_emit]; returns the updated copies."""
+    sc, hi = _c(score, np.int32).copy(), _c(history, np.int32).copy()
+    os_, oh, bs = _c(out_score, np.int32).copy(), _c(out_history, np.int32).copy(), _c(bestscore, np.int32).copy()
+    n_hmm, n_emit = sc.shape
+    z8, z32 = np.zeros(1, np.uint8), np.zeros(1, np.int32)
+    sel = z8 if sel is None else _c(sel, np.uint8)
+    arg = z32 if arg is None else _c(arg, np.int32)
+    n_list = 0 if lidx is None else len(lidx)
+    li = z32 if lidx is None else _c(lidx, np.int32)
+    ls = z32 if lscore is None else _c(lscore, np.int32)
+    lh = z32 if lhist is None else _c(lhist, np.int32)
+    ref().ref_hmm_maint(op, n_emit, n_hmm, _p(sc, C.c_int32), _p(hi, C.c_int32), _p(os_, C.c_int32), _p(oh, C.c_int32),
+                        _p(bs, C.c_int32), _p(sel, C.c_uint8), _p(arg, C.c_int32), n_list, _p(li, C.c_int32),
+                        _p(ls, C.c_int32), _p(lh, C.c_int32))
+    return sc, hi, os_, oh, bs
 
 
 # ------------------------------------------------------------------ wrappers
@@ -453,6 +475,33 @@ class RefS3(_S3Common):
 
     def free(self):
         ref_s3().ref_s3_close(self.h)
+
+
+# ------------------------------------------------------- sphinx3 hmm_vit_eval
+port.orc_s3hmm_eval_batch.restype = C.c_int32
+port.orc_s3hmm_eval_batch.argtypes = [C.c_int, C.c_int, i32p, C.c_int, i16p, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p,
+                                      i32p, u8p, i32p, C.c_int]
+
+
+def s3hmm_eval(which, n_emit, tp, sseq, senscr, score, history, out_score, out_history, ssid, tmatid, mpx, bestscore,
+               repeat=1):
+    """which = "port" (oracle/sphinx_oracle.c) or "ref" (sphinx3's own libam/hmm.c via oracle/_ref).
+    HMM-major int32 arrays [n_hmm][n_emit], updated in place; returns the best score of the last pass."""
+    if which == "ref":
+        fn = ref_s3().ref_s3hmm_eval_batch
+        fn.restype = C.c_int32
+        fn.argtypes = port.orc_s3hmm_eval_batch.argtypes
+    else:
+        fn = port.orc_s3hmm_eval_batch
+    tp, sseq, senscr = _c(tp, np.int32), _c(sseq, np.int16), _c(senscr, np.int32)
+    return fn(n_emit, out_score.shape[0], _p(tp, C.c_int32), tp.shape[0], _p(sseq, C.c_int16), sseq.shape[0],
+              _p(senscr, C.c_int32), _p(score, C.c_int32), _p(history, C.c_int32), _p(out_score, C.c_int32),
+              _p(out_history, C.c_int32), _p(ssid, C.c_int32), _p(_c(tmatid, np.int32), C.c_int32),
+              _p(_c(mpx, np.uint8), C.c_uint8), _p(bestscore, C.c_int32), repeat)
+
+
+def have_ref_s3():
+    return os.path.exists(os.path.join(REF_DIR, "libref_shim_s3.so"))
 
 
 # ------------------------------------------------------- feature stage

@@ -222,6 +222,17 @@ def test_hmm_maintenance_ops_match_sequential_reference():
     np.testing.assert_array_equal(fin.score[0], s0); np.testing.assert_array_equal(fin.history[0], h0)
     np.testing.assert_array_equal(fin.score[1:], got.score[1:]); np.testing.assert_array_equal(fin.history[1:], got.history[1:])
     ctx.free()
+    if orc.have_ref():
+        # the same three operations by the reference's own hmm.c (oracle/_ref), HMM-major
+        r0 = orc.ref_hmm_maint(0, after.score.T, after.history.T, after.out_score, after.out_history, after.bestscore,
+                               sel=(~keep).astype(np.uint8))
+        np.testing.assert_array_equal(r0[0].T, want_s); np.testing.assert_array_equal(r0[2], want_o)
+        np.testing.assert_array_equal(r0[4], want_b); np.testing.assert_array_equal(r0[1].T, after.history)
+        r1 = orc.ref_hmm_maint(1, r0[0], r0[1], r0[2], r0[3], r0[4], arg=per.astype(np.int32))
+        np.testing.assert_array_equal(r1[0].T, got.score); np.testing.assert_array_equal(r1[2], got.out_score)
+        r2 = orc.ref_hmm_maint(2, r1[0], r1[1], r1[2], r1[3], r1[4], lidx=eidx, lscore=escore, lhist=ehist)
+        np.testing.assert_array_equal(r2[0].T, fin.score); np.testing.assert_array_equal(r2[1].T, fin.history)
+        np.testing.assert_array_equal(r2[2], fin.out_score)
 
 
 @pytest.mark.parametrize("n_utt", [1, 3])
