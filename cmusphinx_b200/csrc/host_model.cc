@@ -625,3 +625,49 @@ extern "C" int b200_mdef_read_maps(const char *path, int32_t dims[4], int16_t *s
     if (cd2cisen) std::copy(m.cd2ci.begin(), m.cd2ci.end(), cd2cisen);
     return B200_OK;
 }
+
+
+// ---------------------------------------------------------------- hmm_t AoS <-> SoA
+extern "C" int b200_hmm_pack(const void *const *hmms, int n, int n_emit, b200_hmm_soa_t *soa) {
+    if (n < 0 || n_emit < 1 || n_emit > 5 || !soa || (n > 0 && (!hmms || !soa->score || !soa->history || !soa->out_score ||
+        !soa->out_history || !soa->senid || !soa->tmatid || !soa->mpx || !soa->bestscore))) {
+        b200::set_error("b200_hmm_pack: bad argument");
+        return B200_ERR_ARG;
+    }
+    const size_t N = (size_t)n;
+    for (int i = 0; i < n; ++i) {
+        const b200_ps_hmm_t *h = static_cast<const b200_ps_hmm_t *>(hmms[i]);
+        if (!h || h->n_emit_state != n_emit) { b200::set_error("b200_hmm_pack: hmm %d has %d emitting states, context has %d", i, h ? h->n_emit_state : -1, n_emit); return B200_ERR_ARG; }
+        for (int s = 0; s < n_emit; ++s) {
+            soa->score[s * N + i] = h->score[s];
+            soa->history[s * N + i] = h->history[s];
+            soa->senid[s * N + i] = h->senid[s];
+        }
+        soa->out_score[i] = h->out_score;
+        soa->out_history[i] = h->out_history;
+        soa->tmatid[i] = h->tmatid;
+        soa->mpx[i] = h->mpx;
+        soa->bestscore[i] = h->bestscore;
+    }
+    soa->n_hmm = n;
+    return B200_OK;
+}
+
+extern "C" void b200_hmm_unpack_one(const b200_hmm_soa_t *soa, int n_emit, int i, void *hmm) {
+    b200_ps_hmm_t *h = static_cast<b200_ps_hmm_t *>(hmm);
+    const size_t N = (size_t)soa->n_hmm;
+    for (int s = 0; s < n_emit; ++s) {
+        h->score[s] = soa->score[s * N + i];
+        h->history[s] = soa->history[s * N + i];
+        if (h->mpx) h->senid[s] = soa->senid[s * N + i];
+    }
+    h->out_score = soa->out_score[i];
+    h->out_history = soa->out_history[i];
+    h->bestscore = soa->bestscore[i];
+}
+
+extern "C" int b200_hmm_unpack(const b200_hmm_soa_t *soa, int n_emit, void *const *hmms) {
+    if (!soa || n_emit < 1 || n_emit > 5 || (soa->n_hmm > 0 && !hmms)) { b200::set_error("b200_hmm_unpack: bad argument"); return B200_ERR_ARG; }
+    for (int i = 0; i < soa->n_hmm; ++i) b200_hmm_unpack_one(soa, n_emit, i, hmms[i]);
+    return B200_OK;
+}

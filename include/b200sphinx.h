@@ -306,6 +306,34 @@ typedef struct {
     int32_t *bestscore;    /* [n_hmm] out */
 } b200_hmm_soa_t;
 
+/* AoS <-> SoA: the reference's hmm_t (PS/hmm.h:156-173; 80 bytes on LP64,
+ * embedded as the first member of chan_t / root_chan_t, PS/ngram_search.h:64-104)
+ * as this library reads it.  The binding checks sizeof / offsetof against the
+ * real header at compile time (plugin/b200_hmm.c). */
+typedef struct {
+    void    *ctx;
+    int32_t  score[5];
+    int32_t  history[5];
+    int32_t  out_score;
+    int32_t  out_history;
+    uint16_t ssid;
+    uint16_t senid[5];
+    int32_t  bestscore;
+    int16_t  tmatid;
+    int16_t  frame;
+    uint8_t  mpx;
+    uint8_t  n_emit_state;
+} b200_ps_hmm_t;
+/* Gather n HMMs (an array of hmm_t pointers, e.g. the channels evaluate_channels
+ * walks, PS/ngram_search_fwdtree.c:598-691) into a caller-allocated SoA with
+ * room for n HMMs (arrays of n_emit * n resp. n entries); sets soa->n_hmm. */
+int  b200_hmm_pack(const void *const *hmms, int n, int n_emit, b200_hmm_soa_t *soa);
+/* Scatter the fields hmm_vit_eval writes (score, history, out_score, out_history,
+ * bestscore, and the per-state ssids of mpx HMMs) of SoA entry i back into the
+ * hmm_t. */
+void b200_hmm_unpack_one(const b200_hmm_soa_t *soa, int n_emit, int i, void *hmm);
+int  b200_hmm_unpack(const b200_hmm_soa_t *soa, int n_emit, void *const *hmms);
+
 /* Host round trip: upload SoA, run n_frames steps with senscr[f] =
  * senscr + f*n_sen (hmm_context_set_senscore per frame), download.
  * best_out[n_frames] gets max bestscore per frame. */

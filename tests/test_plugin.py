@@ -339,3 +339,36 @@ def test_identical_hypotheses_tidigits_four_stream_model(tmp_path):
     gpu, _, log = _tidigits(tmp_path, "gpu", {"LD_PRELOAD": PLUGIN})
     assert "b200" in log.lower()
     assert gpu == cpu and len(gpu) == n
+
+
+@needs
+@pytest.mark.gpu
+@pytest.mark.parametrize("inp", [RAW, MFC], ids=["raw", "wsj_mfc"])
+def test_hmm_boundary_evaluate_channels_on_the_gpu(tmp_path, inp):
+    """SURVEY.md section 8(b), HMM boundary: with B200_HMM_PLUGIN=1 the binding evaluates every
+    frame's active channels -- what eval_root_chan / eval_nonroot_chan / eval_word_chan
+    (ngram_search_fwdtree.c:598-691) would pass to hmm_vit_eval one by one -- in one batched
+    b200_hmm_eval_host call through b200_hmm_pack / b200_hmm_unpack_one.  The unmodified decoder
+    must produce the same hypothesis lines (words and path scores), with the reference's own GMM
+    back-end and with the GPU one."""
+    utts, cepdir, ext, extra = inp
+    passes = ["-fwdflat", "no", "-bestpath", "no"]
+    ref, _ = _decode(tmp_path, "ref", utts, cepdir, ext, extra + passes, {})
+    for tag, env in (("hmm", {"LD_PRELOAD": PLUGIN, "B200_HMM_PLUGIN": "1", "B200_PLUGIN_DISABLE": "1"}),
+                     ("hmm_gmm", {"LD_PRELOAD": PLUGIN, "B200_HMM_PLUGIN": "1"})):
+        ctl = tmp_path / f"{tag}.ctl"
+        ctl.write_text("\n".join(utts) + "\n")
+        hyp = tmp_path / f"{tag}.hyp"
+        cmd = [BATCH, "-hmm", os.path.join(D, "hmm", "hub4wsj_sc_8k"), "-lm", os.path.join(D, "lm", "wsj0vp.5000.DMP"),
+               "-dict", os.path.join(D, "lm", "cmu07a.dic"), "-ctl", str(ctl), "-cepdir", cepdir, "-cepext", ext,
+               "-hyp", str(hyp), "-logfn", str(tmp_path / f"{tag}.log")] + extra + passes
+        e = dict(os.environ)
+        e["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + e.get("LD_LIBRARY_PATH", "")
+        e.update(env)
+        p = subprocess.run(cmd, env=e, check=True, timeout=1800, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        got = hyp.read_text().strip().splitlines()
+        assert got == ref, tag
+        rep = [l for l in p.stderr.splitlines() if l.startswith("b200 hmm:")]
+        assert rep, "the HMM binding did not run"
+        frames, evals, fell = (int(x) for x in __import__("re").findall(r"(\d+) frames, (\d+) HMM evaluations on the GPU, (\d+) calls", rep[-1])[0])
+        assert frames > 100 and evals > 20 * frames and fell == 0, rep[-1]

@@ -79,7 +79,7 @@ def test_gpu_matches_port_and_reference(ne):
     import cmusphinx_b200 as b
     c = _case(ne, 30000, 200 + ne)
     want, bw = _run("port", ne, c)
-    g = {k: np.ascontiguousarray(c[k].T) if c[k].ndim == 2 else c[k].copy()
+    g = {k: c[k].T.copy(order="C") if c[k].ndim == 2 else c[k].copy()
          for k in ("score", "history", "ssid", "out_score", "out_history", "bestscore")}
     best = b.s3hmm_vit_eval(ne, c["tp"], c["sseq"], c["n_sen"], c["sen"], g["score"], g["history"], g["out_score"],
                             g["out_history"], g["ssid"], c["tmatid"], c["mpx"], g["bestscore"])
@@ -101,7 +101,7 @@ def test_gpu_matches_port_and_reference(ne):
 def test_gpu_rejects_bad_ids():
     import cmusphinx_b200 as b
     c = _case(3, 64, 9)
-    g = {k: np.ascontiguousarray(c[k].T) if c[k].ndim == 2 else c[k].copy()
+    g = {k: c[k].T.copy(order="C") if c[k].ndim == 2 else c[k].copy()
          for k in ("score", "history", "ssid", "out_score", "out_history", "bestscore")}
     g["ssid"][0, 5] = 10 ** 6
     with pytest.raises(b.B200Error):
