@@ -497,11 +497,13 @@ def main():
     ap.add_argument("--workload", default="ms_cont", choices=["ms_cont", "ptm", "hmm", "s3", "e2e_decode"],
                     help="ms_cont = the headline (BASELINE configs[1]); the others run the secondary benches "
                          "(bench_ptm.py configs[2], bench_hmm.py configs[3], bench_s3.py sphinx3 flavour, "
-                         "bench_e2e.py configs[0]/[4] subset) on one GPU")
+                         "bench_e2e_decode.py configs[4]: sharded batch decode, runs under torchrun too) on one GPU")
     args, rest = ap.parse_known_args()
     if args.workload != "ms_cont":
         import runpy
-        script = {"ptm": "bench_ptm.py", "hmm": "bench_hmm.py", "s3": "bench_s3.py", "e2e_decode": "bench_e2e.py"}[args.workload]
+        script = {"ptm": "bench_ptm.py", "hmm": "bench_hmm.py", "s3": "bench_s3.py", "e2e_decode": "bench_e2e_decode.py"}[args.workload]
+        if args.workload == "e2e_decode":
+            rest = rest + ["--gpus", str(args.gpus)]
         sys.argv = [script] + rest
         runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), script), run_name="__main__")
         return
