@@ -700,6 +700,7 @@ struct b200_hmmctx {
     uint32_t *d_mask_part = nullptr; size_t mask_part_cap = 0;   // words: [2][n_utt][CTAs per utterance][n_words]
     int mask_par = 0;                                  // parity of the last frame's mask
     unsigned *d_bar = nullptr;                         // grid barrier of the persistent step kernel
+    cudaStream_t last_st = nullptr;                    // stream of the last step (a caller may pass its own)
     bool stepped = false;
     int32_t *d_utt_off = nullptr; int utt_cap = 0;
     int32_t *d_total = nullptr;
@@ -793,8 +794,18 @@ int check_soa(const b200_hmmctx *c, const b200_hmm_soa_t *h) {
     if (h->n_hmm < 0) { set_error("negative n_hmm"); return B200_ERR_ARG; }
     if (h->n_hmm > 0 && (!h->score || !h->history || !h->out_score || !h->out_history || !h->senid ||
                          !h->tmatid || !h->mpx || !h->bestscore)) { set_error("null SoA field"); return B200_ERR_ARG; }
-    for (int i = 0; i < h->n_hmm; ++i)
+    const size_t N = (size_t)h->n_hmm;
+    for (int i = 0; i < h->n_hmm; ++i) {
         if (h->tmatid[i] < 0 || h->tmatid[i] >= c->c.n_tmat) { set_error("tmatid[%d]=%d out of range", i, h->tmatid[i]); return B200_ERR_ARG; }
+        // the kernels index shared-memory tables with these ids: senone ids (or, for mpx HMMs,
+        // senone-sequence ids with BAD_SSID = 0xffff meaning "no state")
+        for (int s = 0; s < c->c.n_emit; ++s) {
+            const unsigned id = h->senid[(size_t)s * N + i];
+            if (h->mpx[i]) {
+                if (id != B200_BAD_SSID && (int)id >= c->c.n_sseq) { set_error("ssid[%d][%d]=%u out of range (%d senone sequences)", s, i, id, c->c.n_sseq); return B200_ERR_ARG; }
+            } else if ((int)id >= c->c.n_sen) { set_error("senid[%d][%d]=%u out of range (%d senones)", s, i, id, c->c.n_sen); return B200_ERR_ARG; }
+        }
+    }
     return B200_OK;
 }
 
@@ -896,6 +907,7 @@ static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, i
     const int rc = hmm_launch_run(c->c, c->p, r, st);
     if (rc) return rc;
     c->fr_slot = (r.slot0 + n_frames - 1) % 3;
+    c->last_st = st;
     c->mask_par = (r.mask0 + n_frames - 1) & 1;
     c->stepped = do_beam != 0;
     if (d_probe) {
@@ -940,6 +952,7 @@ int b200_hmm_step_results(b200_hmmctx_t *c, int32_t *best, int32_t *n_keep, int3
     if (!c) { set_error("null argument"); return B200_ERR_ARG; }
     B200_CUDA_OK(cudaSetDevice(c->device));
     B200_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (c->last_st && c->last_st != c->st) B200_CUDA_OK(cudaStreamSynchronize(c->last_st));   // the step ran on the caller's stream
     const int nu = std::max(c->p.n_utt, 1);
     std::vector<HmmFrame> fr(nu);
     int32_t total = 0;

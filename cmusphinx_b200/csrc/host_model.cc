@@ -362,6 +362,8 @@ int b200_s3_read_sendump(const char *path, int32_t dims[5], uint8_t *mixw, uint8
     if (n_clust == 15) n_clust = 16;
     if (!(n_bits == 8 || n_bits == 4)) { set_error("%s: cluster bits must be 4 or 8", path); return B200_ERR_IO; }
     if (r != n_density) { set_error("%s: padded row count %d != %d unsupported", path, r, n_density); return B200_ERR_UNSUP; }
+    // (the mixing kernels index rows with a stride of n_sen: a padded column count would misalign every row)
+    if (c != n_sen) { set_error("%s: padded column count %d != %d senones unsupported", path, c, n_sen); return B200_ERR_UNSUP; }
     int row_bytes = (n_bits == 4) ? (c + 1) / 2 : c;
     dims[0] = n_feat; dims[1] = n_density; dims[2] = n_sen; dims[3] = n_clust; dims[4] = row_bytes;
     if (!mixw) return B200_OK;

@@ -1835,6 +1835,10 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
     if (c == 0 && idx0 >= 0) {
         const float err = fabsf(bound[((size_t)mg * tn + tl) * 3 + 1] - d);
         if (err > 4.f) atomicMax(n_flagged + 2, (int)fminf(err, 1.0e9f));
+        // Safety net: the completeness proof (b) assumes |GEMM - exact| <= eps for the densities that
+        // were NOT re-scored.  The best candidates are the sample we can check; when one of them uses
+        // more than half of the bound, the whole launch is redone by the literal scan.
+        if (err > 0.5f * (kTiedEps + 1.5e-5f * fabsf(d))) n_flagged[3] = 1;
     }
     const bool bad = clash || idx0 < 0 || (rank == N && !(d > bd));
     const bool ok = (__ballot_sync(gm, bad) & gm) == 0;
@@ -1851,15 +1855,16 @@ tied_rescore_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int
 // eval_cb in index order (same code as gmm_topn_kernel).
 template <int N, int MODE>
 __global__ void __launch_bounds__(256)
-tied_fallback_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, const int2 *__restrict__ flagged,
+tied_fallback_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, int tn, const int2 *__restrict__ flagged,
                      const int *__restrict__ n_flagged, const float4 *__restrict__ rows, int lenp,
                      int2 *__restrict__ lists) {
     extern __shared__ float sh[];   // x[lenp] | d[n_density]
     const int len = g.featlen[f], q = lenp >> 2;
     float *x = sh, *dd = sh + lenp;
-    const int n = *n_flagged;
+    const bool all = n_flagged[3] != 0;                    // the error monitor tripped: every (frame, codebook) pair
+    const int n = all ? tn * g.n_mgau : *n_flagged;
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
-        const int tl = flagged[w].x, mg = flagged[w].y;
+        const int tl = all ? w / g.n_mgau : flagged[w].x, mg = all ? w % g.n_mgau : flagged[w].y;
         __syncthreads();
         for (int i = threadIdx.x; i < lenp; i += blockDim.x)
             x[i] = i < len ? feat[(size_t)(t0 + tl) * g.veclen + g.featoff[f] + i] : 0.f;
@@ -1918,7 +1923,7 @@ tied_fallback_kernel(GmmDev g, int f, const float *__restrict__ feat, int t0, co
     }
 }
 
-__global__ void tied_count_roll(int *c) { c[1] += c[0]; c[0] = 0; }
+__global__ void tied_count_roll(int *c, int pairs) { c[1] += c[3] ? pairs : c[0]; c[0] = 0; c[3] = 0; }
 
 }  // namespace
 
@@ -2039,7 +2044,7 @@ static int tied_select_launch(TcTied *p, const GmmDev &g, int f, const float *d_
     if (attr[p->mode - 1].need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    kern<<<p->n_sm * 2, 256, sh, st>>>(g, f, d_feat, t0, p->dFlag, p->dCount, p->dRows[f], p->lenp[f], lists);
+    kern<<<p->n_sm * 2, 256, sh, st>>>(g, f, d_feat, t0, tn, p->dFlag, p->dCount, p->dRows[f], p->lenp[f], lists);
     B200_LAUNCH_CHECK();
     (void)len;
     return B200_OK;
@@ -2103,7 +2108,7 @@ int tc_tied_lists(TcTied *p, const GmmDev &g, const float *d_feat, int t0, int t
                 default: rc = tied_select_launch<4>(p, g, f, d_feat, t0 + c0, cn, T_pad, lc, st); break;
             }
             if (rc) return rc;
-            tied_count_roll<<<1, 1, 0, st>>>(p->dCount);
+            tied_count_roll<<<1, 1, 0, st>>>(p->dCount, cn * g.n_mgau);
             B200_LAUNCH_CHECK();
             p->pairs += (long long)cn * g.n_mgau;
         }

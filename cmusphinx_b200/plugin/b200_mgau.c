@@ -163,7 +163,11 @@ static b200_ps_mgau_t *wrap(b200_mgau_t *gpu, int kind, cmd_ln_t *config, acmod_
     s->n_mgau = g->dims[0]; s->n_feat = g->dims[1]; s->n_density = g->dims[2];
     for (f = 0; f < s->n_feat; ++f) { s->veclen[f] = g->veclen[f]; s->featdim += g->veclen[f]; }
     s->cache_first = 0; s->cache_n = 0;
-    if (g_nreg < MAX_REG) g_reg[g_nreg++] = s;
+    /* the registry is how acmod_start_utt finds the back-end to invalidate its utterance cache:
+     * a back-end that is not in it would re-serve the previous utterance's scores */
+    if (g_nreg >= MAX_REG)
+        E_FATAL("b200: more than %d live back-ends in one process; raise MAX_REG in plugin/b200_mgau.c\n", MAX_REG);
+    g_reg[g_nreg++] = s;
     E_INFO("b200: %s back-end on GPU %d: %d codebooks x %d streams x %d densities, %d senones\n",
            s->base.vt->name, 0, s->n_mgau, s->n_feat, s->n_density, b200_mgau_n_sen(gpu));
     return s;
@@ -282,6 +286,12 @@ ptm_mgau_init(acmod_t *acmod)
     }
     if (load_gauden(acmod->config, lb, &g, NULL) < 0) goto out;
     if (g.dims[0] > 256) { E_INFO("Number of codebooks exceeds 256: %d\n", g.dims[0]); goto out; }   /* ptm_mgau.c:799 */
+    /* Returning NULL here would make acmod_init_am fall through to the ms back-end (other scoring
+     * semantics, or a failure when only a sendump exists): refuse loudly instead. */
+    if (cmd_ln_int32_r(acmod->config, "-ds") > 1)
+        E_FATAL("b200: -ds %d with a ptm model: the reference's ptm back-end leaves un-normalised scores in its "
+                "lists on skipped frames (ptm_mgau.c:247-248) and indexes its log-add table with them -- undefined "
+                "output, not reproduced; use -ds 1 or B200_PLUGIN_DISABLE=1\n", (int)cmd_ln_int32_r(acmod->config, "-ds"));
     if (g.dims[1] != feat_dimension1(acmod->fcb)) { E_ERROR("Number of streams does not match\n"); goto out; }
     for (f = 0; f < g.dims[1]; ++f)
         if (g.veclen[f] != (int32)feat_dimension2(acmod->fcb, f)) { E_ERROR("Stream dimension mismatch\n"); goto out; }
