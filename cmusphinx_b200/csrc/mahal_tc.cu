@@ -75,26 +75,37 @@ constexpr int kMaxKSteps = 10;        // K <= 80  (D <= 39)
 constexpr int kBuildWarps = 4;        // A-operand builders: one thread per frame row
 constexpr int kEpiWarps = 16;         // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kFirstEpiWarp = 2 + kBuildWarps;
+// Warp roles.  The SM's issue arbiter prefers the HIGHEST warp id among the eligible warps of a
+// scheduler, so the latency-critical roles (A builders -> MMA issuer -> producer) get the top
+// ids and the throughput work (epilogue) the low ones.  TMEM lane quarter of a warp = id % 4.
+constexpr int kFirstEpiWarp = 0;
+constexpr int kFirstBuildWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + kBuildWarps;
+constexpr int kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = (2 + kBuildWarps) * 32 + kEpiThreads;
 constexpr int kColsPerEpiThread = kTileN / (kEpiWarps / 4);   // 64
 constexpr uint32_t kTmemCols = 512;
 // MODE 0 (fully continuous) epilogue, round 2: the GEMM delivers w = -32 (d - 1024 mixw)
 // and most (frame, senone) pairs are decided by one cheap certificate (see
-// tc_score_kernel); the rest go through a shared-memory queue to kHardWarps
-// dedicated warps that run the full top-4 network on compacted lanes.
-constexpr int kHardWarps = 8;
-// with hard-path warps the certificate needs only 8 epilogue warps (2 per TMEM lane quarter, 128 columns each)
-constexpr int epi_warps(int HW) { return HW ? 8 : kEpiWarps; }
-constexpr int score_threads(int HW) { return (2 + kBuildWarps + epi_warps(HW) + HW) * 32; }
-constexpr int kQueueBytes = 41 * 1024;          // per buffer, two buffers
+// tc_score_kernel).  The rest are compacted: every epilogue warp appends the
+// accumulator rows of its undecided pairs to a PRIVATE ring in shared memory and,
+// whenever the ring holds a warp's worth, runs the full top-4 network on 32 of
+// them at once (one item per lane).  No warp waits for another one: the 16 epilogue
+// warps are symmetric (an earlier version with 8 dedicated hard-path warps was bound
+// by the latency of those few warps: 11.0 ms against 6.2 ms with every pair easy).
+constexpr int kQCap = 40;                       // items per warp ring
+constexpr int kQPass = 26;                      // run a pass when the ring holds this many (a pass takes up to 32)
+constexpr int kQIdle = 12;                      // ... or this many when the warp would otherwise wait for the next accumulator
+constexpr int epi_warps(int) { return kEpiWarps; }
+constexpr int score_threads(int) { return (2 + kBuildWarps + kEpiWarps) * 32; }
+constexpr int queue_bytes(int M) { return kEpiWarps * kQCap * (M * 4 + 4) + 128; }
 constexpr int kWinFden = 42;                    // 29 (log-add table reach) + 11 (three other terms can add up to that) + 2
 constexpr float kWinV = (float)kWinFden * 1024.f * 32.f;     // the same window on the -32-scaled accumulator
 constexpr float kBig = 1099511627776.f;         // 2^40: sat((th - x) * 2^40) is a crisp 0/1 indicator on the FMA pipe
 constexpr float kDeltaV = 64.f * 32.f;          // slack of the "at most 3 better densities" count (64 raw units)
 constexpr int kFixRegionsMax = 160;             // one fix-up queue region per CTA
 constexpr int kEpsCap = 400;                    // beyond this bound a pair goes to the literal scan
-constexpr int kFixChunk = 64;                   // queue A slots a hard-path warp reserves at a time
+constexpr int kFixChunk = 64;                   // queue A slots a warp reserves at a time
 
 struct TcParams {
     const float *gB;        // pre-tiled B operand
@@ -114,11 +125,16 @@ struct TcParams {
     unsigned *qcnt;         // [1] n_B, [2] overflow, [3] max |GEMM - exact| seen, [4] hard pairs, [5] of those finished in place (tile queue full), [8 + region] n_A
     unsigned capA, capB;
     int eps0, eps_shift;    // bound on |GEMM distance - reference distance|: eps0 + (|d| >> eps_shift) raw units
+    float epsA, epsB;       // the same bound for cert_eval, as a fraction of one fden step (1024 raw units)
     uint8_t logadd[256];
 };
 
 // ------------------------------------------------------------------ PTX glue
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Makes a value opaque to the compiler: it then stays in its register instead of being
+// re-derived (shared-window base + offset, three instructions) at every use in a hot loop.
+__device__ __forceinline__ uint32_t keep(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -138,25 +154,22 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Spin with a watchdog: a protocol bug must trap, not hang the GPU box.
+// Spin with a watchdog: a protocol bug must trap, not hang the GPU box.  The loop is three
+// instructions (poll, count, branch): polling warps share the issue slots of the warps they wait for.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();   // ~3 s
+        if (++spins > (1u << 24)) __trap();             // > 1 s
     }
 }
-// The same for waits off the critical path (a consumer that is ahead of its
-// producer): back off between polls so the spinning warp does not take issue
-// slots from the warps it is waiting for.
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
+// The same for waits that can be long (an epilogue warp that is ahead of the MMA pipeline):
+// back off between polls.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        __nanosleep(200);
-        if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) __trap();
+        __nanosleep(64);
+        if (++spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -379,42 +392,76 @@ __device__ __forceinline__ int32_t hard_eval(const uint32_t (&w)[M], const float
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-// The cheap certificate.  w[j] as above; c2[j] = max(kWinV, 32*1024*mixw_j + kDeltaV) * 2^40.
-// Let j* be the density with the smallest w (the largest d - 1024 mixw) and
-// t_j = w_j - w_j*.  If for every other density
-//   (1) t_j >= kWinV: it sits > 40 log-add units below j*; whichever of them are
-//       in the top 4, their chain cannot reach the table's 29-unit window of j*
-//       even when three of them add up (x + 7 + 4), and
-//   (2) t_j >= 32*1024*mixw_j + kDeltaV, i.e. its distance stays kDeltaV short of
-//       j*'s score, let alone j*'s distance: j* is the top-1 density by distance
-//       (an exact tie in w fails this test too), and
-//   (3) fden of j* is the same over the whole eps interval,
-// the senone score is exactly -(fden(j*) - mixw(j*)) -- read off w(j*) alone.
-// (1) and (2) are one comparison per density against a per-row constant, done
-// as sat((c_j - t_j) * 2^40) on the FMA pipe and summed: the sum must be 1 (j*).
-template <int M>
-__device__ __forceinline__ bool easy_eval(const uint32_t *w /* M registers */, const float *c2, int aw, int eps0,
-                                          int eps_shift, int32_t &score) {
-    float W1 = fmin3(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]));
+// The cheap certificate.  w[j] as above; c2[j] = c_j * 2^40 with
+// c_j = max(kWinV, 32*1024*(mixw_j - min mixw of the senone) + kDeltaV).
+// Let j* be the density with the smallest w (the largest d - 1024 mixw), W1 = w_j*.  If for
+// every other density w_j >= W1 + c_j, then
+//   (1) it sits > 40 log-add units below j*; whichever of them are in the top 4,
+//       their chain cannot reach the table's 29-unit window of j* even when three
+//       of them add up (x + 7 + 4), and
+//   (2) d_j = S_j + 1024 mixw_j <= S_j* - 1024 (mixw_j - min mixw) - delta + 1024 mixw_j
+//       <= d_j* - delta: j* is the top-1 density by distance (an exact tie in w fails
+//       the test too), so it is in the top 4 whatever the others are, and
+//   (3) when fden of j* is the same over the whole eps interval,
+// the senone score is exactly -(fden(j*) - mixw(j*)) = floor(W1 / 32768) -- read off W1 alone
+// (fden = ((int32)d + 1023) >> 10 with (int32)d = -floor(W1 / 32) for d <= 0).
+// Instruction budget per density: FMNMX3 (two per instruction), one FFMA for the row's
+// threshold K_j = (W1 + c_j) 2^40, one FFMA.SAT for the crisp 0/1 indicator
+// sat(K_j - w_j 2^40) (both with an immediate operand), and one IADD3 per two indicators
+// on their float bit patterns (N * 0x3f800000 cannot alias 0x3f800000 for N <= 512).
+// epsA = (eps0 + 1.5) / 1024, epsB = 2^-(15 + eps_shift): the eps interval as a fraction of one
+// fden step.
+// UNI: every c_j of the senone is kWinV (at most three densities could violate (2), so j* is
+// among the top 4 by distance whatever they do): one threshold for the whole row.
+template <int M, bool UNI>
+__device__ __forceinline__ bool cert_eval(const uint32_t *w /* M registers */, const float *c2, int aw, float epsA,
+                                          float epsB, int32_t &score) {
+    // four independent min chains (the whole certificate hangs on this value)
+    float W1;
+    {
+        float m[4];
 #pragma unroll
-    for (int j = 3; j + 1 < M; j += 2) W1 = fmin3(W1, __uint_as_float(w[j]), __uint_as_float(w[j + 1]));
-    if ((M & 1) == 0) W1 = fminf(W1, __uint_as_float(w[M - 1]));
-    // the next float above W1, so that j* itself (and an exact tie) gives a negative difference
-    const float W1n = __uint_as_float(__float_as_uint(W1) + 1u);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 4; ++k) {
+            constexpr int Q = M / 4;
+            m[k] = __uint_as_float(w[k * Q]);
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-        const float t = __fadd_rn(__uint_as_float(w[j]), -W1n);
-        acc[j & 3] += __saturatef(fmaf(t, -kBig, c2[j]));
+            for (int j = 1; j + 1 < Q; j += 2) m[k] = fmin3(m[k], __uint_as_float(w[k * Q + j]), __uint_as_float(w[k * Q + j + 1]));
+            if ((Q & 1) == 0) m[k] = fminf(m[k], __uint_as_float(w[k * Q + Q - 1]));
+        }
+        W1 = fminf(fmin3(m[0], m[1], m[2]), m[3]);
     }
-    const float N = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    const int32_t q = __float2int_rd(W1 * (1.0f / kAccScale));          // floor(-(d - 1024 mixw))
-    const int32_t e = min(eps0 + (abs(q) >> eps_shift), kEpsCap + 1);
-    const bool bnd = ((((1 << kShift) - 1) - q + e) & ((1 << kShift) - 1)) <= 2 * e || e > kEpsCap;
-    int32_t scr = -((((1 << kShift) - 1) - q) >> kShift);
+    uint32_t n0 = 0, n1 = 0;
+    if (UNI) {
+        const float Ku = fmaf(W1, kBig, kWinV * kBig);
+#pragma unroll
+        for (int j = 0; j < M; j += 4) {
+            const float i0 = __saturatef(fmaf(__uint_as_float(w[j]), -kBig, Ku));
+            const float i1 = __saturatef(fmaf(__uint_as_float(w[j + 1]), -kBig, Ku));
+            const float i2 = __saturatef(fmaf(__uint_as_float(w[j + 2]), -kBig, Ku));
+            const float i3 = __saturatef(fmaf(__uint_as_float(w[j + 3]), -kBig, Ku));
+            n0 += __float_as_uint(i0) + __float_as_uint(i1);
+            n1 += __float_as_uint(i2) + __float_as_uint(i3);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < M; j += 4) {
+            const float4 c = *reinterpret_cast<const float4 *>(c2 + j);
+            const float i0 = __saturatef(fmaf(__uint_as_float(w[j]), -kBig, fmaf(W1, kBig, c.x)));
+            const float i1 = __saturatef(fmaf(__uint_as_float(w[j + 1]), -kBig, fmaf(W1, kBig, c.y)));
+            const float i2 = __saturatef(fmaf(__uint_as_float(w[j + 2]), -kBig, fmaf(W1, kBig, c.z)));
+            const float i3 = __saturatef(fmaf(__uint_as_float(w[j + 3]), -kBig, fmaf(W1, kBig, c.w)));
+            n0 += __float_as_uint(i0) + __float_as_uint(i1);
+            n1 += __float_as_uint(i2) + __float_as_uint(i3);
+        }
+    }
+    const float u = W1 * (1.0f / (kAccScale * 1024.f));                 // exact (power of two)
+    const float fl = floorf(u);
+    const float g = fabsf((u - fl) - 0.5f);                             // exact; 0.5 = the middle of a fden step
+    const float lim = fmaf(W1, -epsB, 0.5f - epsA);                     // <= 0 far out: never certain there
+    int32_t scr = __float2int_rd(u);
     if (__builtin_expect(aw != 1, 0)) scr /= aw;
     score = clamp16(scr);
-    return W1 > 0.f && N == 1.0f && !bnd;
+    return W1 > 0.f && (n0 + n1) == 0x3f800000u && g < lim;
 }
 
 // ------------------------------------------------------------------- kernels
@@ -482,14 +529,14 @@ __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
 //         its own format, so one sharp Gaussian or one large feature only moves
 //         the affected tiles to TF32.  KS counts 16-column steps then.
 // smem bytes of one instantiation (host and device agree on it)
-constexpr int score_smem_bytes(int KS, int HALF, int HW) {
+constexpr int score_smem_bytes(int KS, int HALF, int HW, int M = 32) {
     return KS * kBStageBytes + ring_depth(KS) * kAStageBytes + (HALF ? 8 : 4) * KS * kTileM * 4 + 512 + 320 +
-           40 * 8 + 16 + (kTileN + 128) * 4 + kTileN * 4 + (HW ? 2 * kQueueBytes + 128 : 0);
+           40 * 8 + 16 + (kTileN + 128) * 4 + kTileN * 4 + 128 + (HW ? queue_bytes(M) : 0);
 }
 
-// HW: number of dedicated hard-path warps (MODE 0 only; 0 = uncertain pairs are
-// finished in place by the epilogue lane that found them, e.g. the 160 KB-B TF32
-// instantiation that has no room for the queue).
+// HW: 1 = every epilogue warp keeps a ring of undecided pairs in shared memory (MODE 0
+// only); 0 = undecided pairs are finished in place by the lane that found them, e.g. the
+// 160 KB-B TF32 instantiation that has no room for the rings.
 template <int M, int KS, int MODE, int HALF, int HW>
 __global__ void __launch_bounds__(score_threads(HW), 1)
 tc_score_kernel(const __grid_constant__ TcParams p) {
@@ -500,7 +547,6 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     constexpr int kXBytes = DP * kTileM * 4;
     constexpr int NT = score_threads(HW);
     constexpr int EW = epi_warps(HW);             // epilogue warps
-    constexpr int kFirstHardWarp = kFirstEpiWarp + EW;
     uint8_t *sB = smem;                                         // KS * 16 KB
     uint8_t *sA = sB + KS * kBStageBytes;                       // kStages * 8 KB
     uint8_t *sX = sA + kStages * kAStageBytes;                  // DP * 128 * 4
@@ -508,20 +554,19 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     uint8_t *sTab = sMixw + 256;                                // 256 B
     float *sScale = reinterpret_cast<float *>(sTab + 256);      // 16 * KS floats (HALF only; <= 320 B reserved)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sTab + 256 + 320);
-    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2], q_full[2], q_empty[2]
+    // barrier map: b_full, b_empty, x_full, x_empty, a_full[S], a_empty[S], tmem_full[2], tmem_empty[2]
     constexpr int B_FULL = 0, B_EMPTY = 1, X_FULL = 2, X_EMPTY = 3, A_FULL = 4, A_EMPTY = 4 + kStages,
-                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, Q_FULL = T_EMPTY + 2, Q_EMPTY = Q_FULL + 2,
-                  N_BARS = Q_EMPTY + 2;
-    static_assert(N_BARS <= 40, "barrier area");
+                  T_FULL = 4 + 2 * kStages, T_EMPTY = T_FULL + 2, N_BARS = T_EMPTY + 2;
+    static_assert(N_BARS <= 36, "barrier area");
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 40);
     // 32*1024*mixw per tile row, senone stride M + 4 (16-byte rows; the hard-path lanes of a warp read different senones)
     float *sCw = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(tmem_slot) + 16);
     float *sC2 = sCw + kTileN + 128;                                                        // [256] certificate constants
-    uint32_t *sQ = reinterpret_cast<uint32_t *>(sC2 + kTileN);                              // HW: two item buffers
-    uint32_t *sQn = sQ + 2 * (kQueueBytes / 4);                                             // HW: items in each buffer
-    constexpr int QS = M + 4;                     // item stride in words: M accumulators + header, 16-byte aligned, conflict-free
-    constexpr int QCAP = kQueueBytes / (QS * 4);
-    constexpr int QSL = QCAP / EW;                // slots of one epilogue warp's slice
+    // HW: per epilogue warp a ring of [kQCap][M] accumulator rows (128-byte aligned), then all the headers
+    uint32_t *sUni = reinterpret_cast<uint32_t *>(sC2 + kTileN);   // [SPT <= 32] uniform-window flag per senone of the tile
+    unsigned *sTick = reinterpret_cast<unsigned *>(bars + 36);     // chunk ticket counter per lane quarter (the barrier area's spare 32 bytes)
+    uint32_t *sQ = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(sUni + 32) + 127) & ~(uintptr_t)127);
+    uint32_t *sQh = sQ + kEpiWarps * kQCap * M;
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
@@ -533,11 +578,12 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
         mbar_init(BAR(X_FULL), 1);
         mbar_init(BAR(X_EMPTY), kBuildWarps);
         for (int s = 0; s < kStages; ++s) { mbar_init(BAR(A_FULL + s), kBuildWarps); mbar_init(BAR(A_EMPTY + s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), EW); }
-        for (int a = 0; a < 2; ++a) { mbar_init(BAR(Q_FULL + a), EW); mbar_init(BAR(Q_EMPTY + a), HW ? HW : 1); }
+        // accumulator releases: one per epilogue warp (MODE 1) or one per 32-column chunk and lane quarter (MODE 0)
+        for (int a = 0; a < 2; ++a) { mbar_init(BAR(T_FULL + a), 1); mbar_init(BAR(T_EMPTY + a), MODE == 0 ? 4 * (kTileN / 32) : EW); }
+        for (int a = 0; a < 4; ++a) sTick[a] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -552,7 +598,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
     // a unit is skipped by the kernel of the other operand format
 #define OTHER_FORMAT(nt_) ((p.fmt ? (int)p.fmt[(nt_)] : 0) != HALF)
 
-    if (warp == 0) {
+    if (warp == kProdWarp) {
         // ===================== producer =====================
         // Bulk-TMA: the unit's B tile (resident for the whole unit), then one raw
         // feature tile (DP x 128 fp32) per frame tile.
@@ -577,7 +623,7 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         // The whole warp walks the (fully unrolled) loop so control flow stays
         // uniform; one elected lane issues.  Ring slot and barrier parity of
@@ -633,12 +679,12 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
             if (elect_one()) tc_commit(BAR(B_EMPTY));
             __syncwarp();
         }
-    } else if (warp < kFirstEpiWarp) {
+    } else if (warp >= kFirstBuildWarp) {
         // ===================== A-operand builders (4 warps) =====================
         // Thread r owns frame row r of the tile: it keeps the row's DP features in
         // registers and, k-step by k-step, writes [1,1,x^2,x,...] split into TF32
         // hi/lo straight into the UMMA K-major layout of the A ring.
-        const int r = threadIdx.x - 64;                  // 0..127
+        const int r = threadIdx.x - kFirstBuildWarp * 32; // 0..127
         const float *xs = reinterpret_cast<const float *>(sX);
         int stage = 0; uint32_t phase = 0, xphase = 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -664,16 +710,22 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     if (HALF) {
                         // 16 columns: scaled value -> fp16 hi + fp16 lo (exact remainder, rounded once)
                         uint32_t hp[8], lp[8];
+                        float sc[16];                     // this k-step's 16 column scales: four 16-byte broadcast loads
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 q4 = *reinterpret_cast<const float4 *>(sScale + j * 16 + k4 * 4);
+                            sc[k4 * 4] = q4.x; sc[k4 * 4 + 1] = q4.y; sc[k4 * 4 + 2] = q4.z; sc[k4 * 4 + 3] = q4.w;
+                        }
 #pragma unroll
                         for (int kk = 0; kk < 16; kk += 2) {
                             float a[2];
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int k = j * 16 + kk + e;
-                                if (k < 2) a[e] = sScale[k];
+                                if (k < 2) a[e] = sc[kk + e];
                                 else {
                                     const int i = (k - 2) >> 1;
-                                    a[e] = ((k - 2) & 1) ? __fmul_rn(x[i], sScale[k]) : __fmul_rn(__fmul_rn(x[i], sScale[k]), x[i]);
+                                    a[e] = ((k - 2) & 1) ? __fmul_rn(x[i], sc[kk + e]) : __fmul_rn(__fmul_rn(x[i], sc[kk + e]), x[i]);
                                 }
                             }
                             const __half2 h = __floats2half2_rn(a[0], a[1]);
@@ -714,120 +766,74 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                 }
             }
         }
-    } else if (HW && warp >= kFirstHardWarp) {
-        // ===================== hard-path warps (MODE 0) =====================
-        // Consumers of the per-tile item queue: 32 items per pass, one per lane, the
-        // full top-4 network + the interval check of hard_eval.
-        const int hw = warp - kFirstHardWarp;
-        uint32_t qt = 0;                                  // tiles seen by this CTA
-        const unsigned region = blockIdx.x < kFixRegionsMax ? blockIdx.x : 0;
-        unsigned fbase = 0; int fleft = 0;                // this warp's reserved run of queue A slots
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-            const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
-            if (OTHER_FORMAT(nt)) continue;
-            const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");   // previous unit's tables are free
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");   // this unit's tables are loaded
-            int16_t *rawt = p.raw + (size_t)nt * p.T_pad * SPT;
-            for (int mt = mt0; mt < mt1; ++mt, ++qt) {
-                const int buf = qt & 1;
-                mbar_wait_idle(BAR(Q_FULL + buf), (qt >> 1) & 1);
-                // every epilogue warp filled its own slice of the buffer; items are numbered across the slices
-                int pre[EW + 1];
-                pre[0] = 0;
-#pragma unroll
-                for (int e = 0; e < EW; ++e) pre[e + 1] = pre[e] + (int)sQn[buf * EW + e];
-                const int n = (p.dbg & 16) ? 0 : pre[EW];
-                const uint32_t *qb = sQ + buf * (kQueueBytes / 4);
-                for (int i0 = hw * 32; i0 < n; i0 += HW * 32) {
-                    const int i = i0 + lane;
-                    const int ii = min(i, n - 1);
-                    int sidx = ii;                                   // slot = slice * QSL + offset inside the slice
-#pragma unroll
-                    for (int e = 1; e < EW; ++e) sidx += (ii >= pre[e]) ? (QSL - (pre[e] - pre[e - 1])) : 0;
-                    const uint32_t *it = qb + (size_t)sidx * QS;
-                    uint32_t w[M];
-#pragma unroll
-                    for (int j = 0; j < M; j += 4) {
-                        const uint4 x = *reinterpret_cast<const uint4 *>(it + j);
-                        w[j] = x.x; w[j + 1] = x.y; w[j + 2] = x.z; w[j + 3] = x.w;
-                    }
-                    const uint32_t hdr = it[M];
-                    const int rw = hdr & 127, sl = hdr >> 8;          // frame row in the tile, senone in the tile
-                    FixOut fx;
-                    const int32_t sc = hard_eval<M>(w, sCw + sl * (M + 4), sMixw + sl * M - (32 - M), sTab, p.aw, p.eps0,
-                                                    p.eps_shift, p.m31, fx);
-                    const int t = mt * kTileM + rw;
-                    const bool live = i < n && t < p.T;
-                    if (live) rawt[(size_t)t * SPT + sl] = (int16_t)sc;
-                    // queue A appends: slots are reserved kFixChunk at a time (one global atomic per
-                    // chunk instead of one round trip per pass)
-                    const unsigned ma = __ballot_sync(0xffffffffu, live && fx.kind == 1);
-                    if (ma) {
-                        const int cnt = __popc(ma), rank = __popc(ma & ((1u << lane) - 1u));
-                        unsigned nbase = 0;
-                        if (cnt > fleft) {
-                            if (lane == 0) nbase = atomicAdd(p.qcnt + 8 + region, (unsigned)kFixChunk);
-                            nbase = __shfl_sync(0xffffffffu, nbase, 0);
-                        }
-                        if (live && fx.kind == 1) {
-                            const unsigned idx = rank < fleft ? fbase + rank : nbase + (rank - fleft);
-                            if (idx < p.capA) p.qa[(size_t)region * p.capA + idx] = make_uint4((uint32_t)t, (uint32_t)(nt * SPT + sl), fx.s01, fx.s23);
-                            else p.qcnt[2] = 1u;
-                        }
-                        if (cnt > fleft) { fbase = nbase + (cnt - fleft); fleft = kFixChunk - (cnt - fleft); }
-                        else { fbase += cnt; fleft -= cnt; }
-                    }
-                    if (live && fx.kind == 2) fix_append(p, fx, (uint32_t)t, (uint32_t)(nt * SPT + sl));
-                }
-                if (hw == 0 && lane == 0 && n) atomicAdd(p.qcnt + 4, (unsigned)n);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(Q_EMPTY + buf));
-            }
-        }
-        // the unused rest of the last reservation: null items (tc_fix_a_kernel skips them)
-        for (int k = lane; k < fleft; k += 32)
-            if (fbase + k < p.capA) p.qa[(size_t)region * p.capA + fbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);
     } else {
         // ===================== epilogue (16 warps) =====================
         // Warp w may read TMEM lanes 32*(w%4)..+31 only; the four warps of a lane
         // quarter split the 256 accumulator columns into 64-column groups.  Each
-        // thread pulls its 64 columns into registers, releases the accumulator
-        // at once (the MMA warp can start the tile after next) and only then
-        // does the selection / log-add arithmetic.
-        constexpr int CPT = kTileN / (EW / 4);           // columns per thread (64, or 128 with hard-path warps)
+        // thread pulls 32 columns at a time into registers; after the last load the
+        // accumulator is released (the MMA warp can start the tile after next).
+        constexpr int CPT = kTileN / (EW / 4);           // columns per thread (64)
         constexpr int SPE = CPT / M;                     // senones per thread
-        const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..511
         const int q = warp & 3;
         const int cg = (warp - kFirstEpiWarp) >> 2;      // column group 0..3
         const int ew = warp - kFirstEpiWarp;
+        const int et = threadIdx.x - kFirstEpiWarp * 32; // 0..511
         const int row = q * 32 + lane;                   // frame row in the tile
         int acc = 0; uint32_t accphase = 0;
-        uint32_t qt = 0;
         const int32_t m31 = p.m31;
+        // MODE 0: this warp's ring of undecided pairs and its reserved run of queue A slots
+        // [kQCap][M] accumulator rows; 16-byte chunk c of slot s sits at chunk c ^ swz(s) of the item, so that
+        // eight lanes with consecutive slots touch eight different 16-byte bank groups
+        const uint32_t wq = keep(smem_u32(sQ + ew * (kQCap * M)));
+        const uint32_t wqh = keep(smem_u32(sQh + ew * kQCap)); // [kQCap] headers: (frame - first frame of the unit) << 5 | senone in the tile
+        const uint32_t bT = keep(BAR(T_FULL));           // T_FULL[a] = bT + 8 a, T_EMPTY[a] = bT + 16 + 8 a
+        const uint32_t tmq = keep(tmem_base + ((uint32_t)(q * 32) << 16));
+        const uint32_t tkq = keep(smem_u32(sTick + q));
+        auto item_addr = [&](int slot) {                 // address of chunk 0 of the slot, swizzle bits folded in
+            const int swz = M == 32 ? (slot & 7) : (M == 16 ? ((slot >> 1) & 3) : ((slot >> 2) & 1));
+            return wq + (uint32_t)slot * (M * 4) + ((uint32_t)swz << 4);
+        };
+        int qhead = 0, qpend = 0;
+        unsigned n_hard = 0, n_inplace = 0;
+        uint32_t tick = 0; bool have_tick = false;       // chunk ticket of this warp's lane quarter (MODE 0)
+        int tile_base = 0;                               // running tile number of the current unit's first tile
+        const unsigned region = blockIdx.x < kFixRegionsMax ? blockIdx.x : 0;
+        unsigned fbase = 0; int fleft = 0;
+        const bool all_hard = (p.dbg & 4) != 0, all_easy = (p.dbg & 1) != 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
             const int nt = u % p.n_tiles_n, mc = u / p.n_tiles_n;
             if (OTHER_FORMAT(nt)) continue;
             const int mt0 = mc * p.tiles_per_chunk, mt1 = min(p.n_tiles_m, mt0 + p.tiles_per_chunk);
             if (MODE == 0) {
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");      // every ring is empty: the previous unit's tables are free
                 if (et < kTileN) {
                     // stored reversed inside each senone so that key & 31 indexes it directly
                     const int sl = et / M, dens = et % M;
                     sMixw[sl * M + (M - 1 - dens)] = p.gMixw[(size_t)nt * kTileN + et];
                     const float c = p.gCw[(size_t)nt * kTileN + et];
                     sCw[sl * (M + 4) + dens] = c;
-                    sC2[et] = fmaxf(kWinV, c + kDeltaV) * kBig;
+                    // the senone's smallest mixw offset (its M rows are M consecutive lanes)
+                    float cmin = c;
+#pragma unroll
+                    for (int o = M / 2; o; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+                    // condition (2) asks for more than the window only from a density whose mixw offset exceeds
+                    // the senone's smallest by ~42 units; with at most three of those nobody has to ask (cert_eval)
+                    const float cd = (c - cmin) + kDeltaV;
+                    const unsigned bm = __ballot_sync(0xffffffffu, cd > kWinV);
+                    const unsigned gmask = M == 32 ? 0xffffffffu : (((1u << (M & 31)) - 1u) << ((lane / M) * M));
+                    const bool uni = __popc(bm & gmask) <= 3;
+                    sC2[et] = (uni ? kWinV : fmaxf(kWinV, cd)) * kBig;
+                    if (dens == 0) sUni[sl] = uni ? 1u : 0u;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * (EW + HW)) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
             }
             int16_t *rawt = MODE == 0 ? p.raw + (size_t)nt * p.T_pad * SPT : nullptr;
             uint4 *partt = MODE == 1 ? p.part + (size_t)nt * p.T_pad * 4 : nullptr;
-            for (int mt = mt0; mt < mt1; ++mt, ++qt) {
-                mbar_wait(BAR(T_FULL + acc), accphase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + cg * CPT);
-                if (MODE == 1) {
+            if (MODE == 1) {
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    mbar_wait(BAR(T_FULL + acc), accphase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTileN + cg * CPT);
                     uint32_t v0[32], v1[32];
                     tmem_ld32(taddr, v0);
                     tmem_ld32(taddr + 32, v1);
@@ -853,103 +859,157 @@ tc_score_kernel(const __grid_constant__ TcParams p) {
                     ce(m0, m2); ce(m1, m3); ce(m0, m1); ce(m2, m3);
                     partt[(size_t)(mt * kTileM + row) * 4 + cg] = make_uint4((uint32_t)m0, (uint32_t)m1, (uint32_t)m2, (uint32_t)m3);
                     if (++acc == 2) { acc = 0; accphase ^= 1; }
-                    continue;
                 }
-                // ---- MODE 0: certificate per senone; the rest is queued (or finished in place)
-                const int buf = qt & 1;
-                if (HW) mbar_wait(BAR(Q_EMPTY + buf), ((qt >> 1) & 1) ^ 1);     // the buffer's previous tile has been consumed
-                uint32_t *qbuf = sQ + buf * (kQueueBytes / 4);
-                const int t = mt * kTileM + row;
-                // One 32-column chunk per iteration, NOT unrolled: the loop body must stay in the
-                // instruction cache next to the other warp roles' code.
-                constexpr int SPC = 32 / M;                                     // senones per chunk
-                unsigned long long pack = 0;                                    // M == 32: the thread's scores, 16 bits each
-                int qn = 0;                                                     // hard pairs of this warp in this tile
-                auto chunk = [&](const int c, const uint32_t (&v)[32]) {
-                    int16_t res[SPC];
-#pragma unroll
-                    for (int s = 0; s < SPC; ++s) {      // senones inside the 32-column chunk
-                        const int st = cg * SPE + c * SPC + s;            // senone within the tile
-                        int32_t sc;
-                        bool easy = easy_eval<M>(&v[s * M], sC2 + st * M, p.aw, p.eps0, p.eps_shift, sc);
-                        if (p.dbg & 4) easy = false;
-                        if ((p.dbg & 1) || nt * SPT + st >= p.n_sen) easy = true;     // (padding senones of the last tile)
-                        const unsigned hm = __ballot_sync(0xffffffffu, !easy);
-                        if (hm) {
-                            // the warp's own slice of the tile's buffer: no atomics, a register counter
-                            const int slot = HW ? qn + __popc(hm & ((1u << lane) - 1u)) : QSL;
-                            qn += __popc(hm);
-                            if (!easy) {
-                                if (slot < QSL) {
-                                    uint32_t *it = qbuf + (size_t)(ew * QSL + slot) * QS;
-#pragma unroll
-                                    for (int j = 0; j < M; j += 4)
-                                        *reinterpret_cast<uint4 *>(it + j) = make_uint4(v[s * M + j], v[s * M + j + 1], v[s * M + j + 2], v[s * M + j + 3]);
-                                    it[M] = (uint32_t)row | ((uint32_t)st << 8);
-                                } else {
-                                    // no queue (or it is full): finish here
-                                    uint32_t w[M];
-#pragma unroll
-                                    for (int j = 0; j < M; ++j) w[j] = v[s * M + j];
-                                    FixOut fx;
-                                    sc = hard_eval<M>(w, sCw + st * (M + 4), sMixw + st * M - (32 - M), sTab, p.aw, p.eps0,
-                                                      p.eps_shift, m31, fx);
-                                    if (fx.kind && t < p.T) fix_append(p, fx, (uint32_t)t, (uint32_t)(nt * SPT + st));
-                                    if (HW) atomicAdd(p.qcnt + 5, 1u);      // statistic: the tile's queue was full
-                                    easy = true;
-                                }
-                            }
-                        }
-                        res[s] = (int16_t)sc;
-                    }
-                    if (M == 32) {
-                        pack |= (unsigned long long)(uint16_t)res[0] << (16 * c);
-                    } else if (t < p.T) {
-                        // chunk-wise stores; the hard-path warps write what is not final here
-                        // (queued pairs: placeholders, overwritten by the hard-path warps after the hand-over)
-                        int16_t *dst = rawt + (size_t)t * SPT + cg * SPE + c * SPC;
-                        if (SPC == 2) *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(res);
-                        else *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(res);
-                    }
-                };
-                // (prefetching the next chunk into a second register set spills at 80 registers: measured slower)
+                continue;
+            }
+            // ---- MODE 0: certificate per senone; undecided pairs go to the warp's ring (or are
+            // finished in place when there is no ring / it is full).
+            // Chunks (32 accumulator columns of one lane quarter) are handed out by a ticket counter
+            // per quarter: a warp that is busy with a pass simply takes fewer chunks and the other
+            // three warps of its quarter take more, so the accumulator is released at the AVERAGE
+            // pace of the quarter's warps, not at the pace of the slowest one (with a fixed
+            // warp -> column mapping one warp in a pass held up the release, the MMA warp and
+            // through it all other warps: 9.6 ms against 6.1 ms without undecided pairs).
+            constexpr int SPC = 32 / M;                                         // senones per chunk
+            constexpr int NCH = kTileN / 32;                                    // chunks per tile and quarter
+            const int ntile = mt1 - mt0;
+            const int n_valid = min(SPT, p.n_sen - nt * SPT);                   // real senones of this n-tile
+            // One chunk per iteration, NOT unrolled: the loop body (certificate, append, pass)
+            // exists once and must stay in the instruction cache next to the other warp roles' code.
 #pragma unroll 1
-                for (int c = 0; c < CPT / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + 32 * c, v);
-                    tmem_ld_wait();
-                    if (c == CPT / 32 - 1) {
-                        // last load done: the accumulator may be overwritten
+            while (true) {
+                if (!have_tick) {
+                    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(tick) : "r"(tkq) : "memory");
+                    tick = __shfl_sync(0xffffffffu, tick, 0);
+                    have_tick = true;
+                }
+                const int tseq = (int)(tick / NCH) - tile_base;                 // tile of this unit
+                bool drain = tseq >= ntile;                                     // the ticket belongs to the next unit: keep it
+                if (drain && !(HW && qpend)) break;
+                const int c = (int)(tick % NCH);
+                const int mt = mt0 + tseq;
+                const int t = mt * kTileM + row;
+                const uint32_t trel = (uint32_t)(tseq * kTileM + row);
+                {
+                    if (!drain) {
+                        const uint32_t gseq = tick / NCH;                       // running tile number of this CTA
+                        const uint32_t acc = gseq & 1u;
+                        mbar_wait(bT + 8u * acc, (gseq >> 1) & 1u);
+                        tc_fence_after();
+                        const uint32_t taddr = tmq + acc * kTileN + (uint32_t)(c * 32);
+                        uint32_t v[32];
+                        tmem_ld32(taddr, v);
+                        tmem_ld_wait();
+                        // the chunk is in registers: one of the accumulator's 4 * NCH releases
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(T_EMPTY + acc));
+                        if (lane == 0) mbar_arrive(bT + 16u + 8u * acc);
+                        have_tick = false;
+#pragma unroll
+                        for (int s = 0; s < SPC; ++s) {      // senones inside the 32-column chunk
+                            const int st = c * SPC + s;                       // senone within the tile
+                            int32_t sc;
+                            bool easy = sUni[st] ? cert_eval<M, true>(&v[s * M], sC2 + st * M, p.aw, p.epsA, p.epsB, sc)
+                                                 : cert_eval<M, false>(&v[s * M], sC2 + st * M, p.aw, p.epsA, p.epsB, sc);
+                            if (all_hard) easy = false;
+                            if (all_easy || st >= n_valid) easy = true;                  // (padding senones of the last tile)
+                            const unsigned hm = __ballot_sync(0xffffffffu, !easy);
+                            if (hm) {
+                                const int rank = __popc(hm & ((1u << lane) - 1u));
+                                const int pos = qpend + rank;                  // position in the ring, if it fits
+                                if (HW) qpend = min(qpend + __popc(hm), kQCap);
+                                n_hard += (unsigned)__popc(hm);
+                                if (!easy) {
+                                    if (HW && pos < kQCap) {
+                                        int slot = qhead + pos;
+                                        slot -= slot >= kQCap ? kQCap : 0;
+                                        const uint32_t it = item_addr(slot);
+#pragma unroll
+                                        for (int j = 0; j < M; j += 4)
+                                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(it ^ (uint32_t)(j << 2)),
+                                                         "r"(v[s * M + j]), "r"(v[s * M + j + 1]), "r"(v[s * M + j + 2]), "r"(v[s * M + j + 3]) : "memory");
+                                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(wqh + 4u * (uint32_t)slot), "r"((trel << 5) | (uint32_t)st) : "memory");
+                                    } else {
+                                        // no ring (or it is full): finish here
+                                        uint32_t w[M];
+#pragma unroll
+                                        for (int j = 0; j < M; ++j) w[j] = v[s * M + j];
+                                        FixOut fx;
+                                        sc = hard_eval<M>(w, sCw + st * (M + 4), sMixw + st * M - (32 - M), sTab, p.aw, p.eps0,
+                                                          p.eps_shift, m31, fx);
+                                        if (fx.kind && t < p.T) fix_append(p, fx, (uint32_t)t, (uint32_t)(nt * SPT + st));
+                                        ++n_inplace;
+                                        easy = true;
+                                    }
+                                }
+                            }
+                            if (easy && t < p.T) rawt[(size_t)t * SPT + st] = (int16_t)sc;
+                        }
                     }
-                    chunk(c, v);
-                }
-                if (M == 32 && t < p.T) {
-                    // One vector store of the thread's scores, BEFORE the queue hand-over: the entries
-                    // of queued pairs are placeholders that the hard-path warps overwrite afterwards
-                    // (ordered by the mbarrier's release / acquire).
-                    int16_t *dst = rawt + (size_t)t * SPT + cg * SPE;
-                    if (CPT == 64) *reinterpret_cast<uint32_t *>(dst) = (uint32_t)pack;
-                    else *reinterpret_cast<unsigned long long *>(dst) = pack;
-                }
-                if (HW) {
-                    __syncwarp();
-                    if (lane == 0) {
-                        sQn[buf * EW + ew] = (uint32_t)min(qn, QSL);
-                        mbar_arrive(BAR(Q_FULL + buf));
+                    // ---- the ring: 32 undecided pairs at a time, one per lane, through the full
+                    // top-4 network + the interval check of hard_eval
+                    while (HW && (qpend >= kQPass || (drain && qpend > 0))) {
+                        __syncwarp();                                          // the appends above are visible
+                        const int n = min(qpend, 32);
+                        int slot = qhead + min(lane, n - 1);
+                        slot -= slot >= kQCap ? kQCap : 0;
+                        const uint32_t it = item_addr(slot);
+                        uint32_t w[M];
+#pragma unroll
+                        for (int j = 0; j < M; j += 4)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[j]), "=r"(w[j + 1]), "=r"(w[j + 2]), "=r"(w[j + 3])
+                                         : "r"(it ^ (uint32_t)(j << 2)) : "memory");
+                        uint32_t hdr;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hdr) : "r"(wqh + 4u * (uint32_t)slot) : "memory");
+                        const int sl = (int)(hdr & 31u);                       // senone in the tile
+                        const int th = mt0 * kTileM + (int)(hdr >> 5);
+                        FixOut fx;
+                        const int32_t sc = hard_eval<M>(w, sCw + sl * (M + 4), sMixw + sl * M - (32 - M), sTab, p.aw, p.eps0,
+                                                        p.eps_shift, m31, fx);
+                        const bool live = lane < n && th < p.T;
+                        if (live) rawt[(size_t)th * SPT + sl] = (int16_t)sc;
+                        // queue A appends: slots are reserved kFixChunk at a time (one global atomic per
+                        // chunk instead of one round trip per pass)
+                        const unsigned ma = __ballot_sync(0xffffffffu, live && fx.kind == 1);
+                        if (ma) {
+                            const int cnt = __popc(ma), rank = __popc(ma & ((1u << lane) - 1u));
+                            unsigned nbase = 0;
+                            if (cnt > fleft) {
+                                if (lane == 0) nbase = atomicAdd(p.qcnt + 8 + region, (unsigned)kFixChunk);
+                                nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                            }
+                            if (live && fx.kind == 1) {
+                                const unsigned idx = rank < fleft ? fbase + rank : nbase + (rank - fleft);
+                                if (idx < p.capA) p.qa[(size_t)region * p.capA + idx] = make_uint4((uint32_t)th, (uint32_t)(nt * SPT + sl), fx.s01, fx.s23);
+                                else p.qcnt[2] = 1u;
+                            }
+                            if (cnt > fleft) { fbase = nbase + (cnt - fleft); fleft = kFixChunk - (cnt - fleft); }
+                            else { fbase += cnt; fleft -= cnt; }
+                        }
+                        if (live && fx.kind == 2) fix_append(p, fx, (uint32_t)th, (uint32_t)(nt * SPT + sl));
+                        qhead += n; qhead -= qhead >= kQCap ? kQCap : 0;
+                        qpend -= n;
+                        __syncwarp();                                          // the slots may be overwritten
                     }
                 }
-                if (++acc == 2) { acc = 0; accphase ^= 1; }
             }
+            tile_base += ntile;
+        }
+        if (MODE == 0) {
+            // the unused rest of the last reservation: null items (tc_fix_a_kernel skips them)
+            for (int k = lane; k < fleft; k += 32)
+                if (fbase + k < p.capA) p.qa[(size_t)region * p.capA + fbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+            n_hard = __reduce_add_sync(0xffffffffu, lane == 0 ? n_hard : 0u);
+            n_inplace = __reduce_add_sync(0xffffffffu, n_inplace);
+            if (lane == 0 && n_hard) atomicAdd(p.qcnt + 4, n_hard);
+            if (lane == 0 && n_inplace) atomicAdd(p.qcnt + 5, n_inplace);
         }
     }
 
 #undef OTHER_FORMAT
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
@@ -1472,9 +1532,9 @@ TcPlan *tc_plan_create(const GmmDev &g, const float *h_mean, const float *h_var,
 
 template <int M, int KS, int MODE, int HALF>
 static int launch_score(const TcParams &prm, int grid, cudaStream_t st) {
-    // the hard-path warps and their queue where the B tile leaves room for them
-    constexpr int HW = (MODE == 0 && score_smem_bytes(KS, HALF, kHardWarps) <= 227 * 1024) ? kHardWarps : 0;
-    constexpr size_t smem = score_smem_bytes(KS, HALF, HW);
+    // the epilogue warps' rings of undecided pairs, where the B tile leaves room for them
+    constexpr int HW = (MODE == 0 && score_smem_bytes(KS, HALF, 1, M) <= 227 * 1024) ? 1 : 0;
+    constexpr size_t smem = score_smem_bytes(KS, HALF, HW, M);
     static AttrOnce attr;
     if (attr.need()) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc_score_kernel<M, KS, MODE, HALF, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1592,6 +1652,8 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     prm.gCw = p->dCw; prm.qa = p->dQa; prm.qb = p->dQb; prm.qcnt = p->dQcnt;
     prm.capA = (unsigned)p->qa_cap; prm.capB = (unsigned)p->qb_cap;
     prm.eps0 = p->eps0; prm.eps_shift = p->eps_shift;
+    prm.epsA = ((float)p->eps0 + 1.5f) / 1024.f;
+    prm.epsB = std::ldexp(1.0f, -(15 + p->eps_shift));
     p->last_T = T;
     int rc = B200_OK;
     if (p->half.ksteps) {
@@ -1631,7 +1693,7 @@ int tc_last_stats(TcPlan *p, long long out[7]) {
     std::vector<unsigned> c(8 + kFixRegionsMax);
     cudaSetDevice(p->device);
     if (cudaMemcpy(c.data(), p->dQcnt, c.size() * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    out[0] = p->last_T * p->S; out[1] = c[4] + c[5]; out[3] = c[1]; out[4] = c[2]; out[5] = c[3]; out[6] = c[5];
+    out[0] = p->last_T * p->S; out[1] = c[4]; out[3] = c[1]; out[4] = c[2]; out[5] = c[3]; out[6] = c[5];
     for (int r = 0; r < kFixRegionsMax; ++r) out[2] += c[8 + r];
     return 0;
 }
