@@ -95,7 +95,6 @@ constexpr uint32_t kTmemCols = 512;
 // by the latency of those few warps: 11.0 ms against 6.2 ms with every pair easy).
 constexpr int kQCap = 40;                       // items per warp ring
 constexpr int kQPass = 26;                      // run a pass when the ring holds this many (a pass takes up to 32)
-constexpr int kQIdle = 12;                      // ... or this many when the warp would otherwise wait for the next accumulator
 constexpr int epi_warps(int) { return kEpiWarps; }
 constexpr int score_threads(int) { return (2 + kBuildWarps + kEpiWarps) * 32; }
 constexpr int queue_bytes(int M) { return kEpiWarps * kQCap * (M * 4 + 4) + 128; }
@@ -470,7 +469,8 @@ __device__ __forceinline__ bool cert_eval(const uint32_t *w /* M registers */, c
 // expansion (4x the bytes) happens inside the SM so it never crosses L2.
 __global__ void __launch_bounds__(kTileM)
 tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D, int Dp, float *__restrict__ gX,
-               unsigned int *__restrict__ xmax /* [D] max |x| as float bits, or null */) {
+               unsigned int *__restrict__ xmax /* [D] max |x| as float bits, or null */,
+               float *__restrict__ xrow /* [T_pad][(D+3)&~3] 16-byte aligned zero-padded rows for the exact fix-ups, or null */) {
     __shared__ float tile[kTileM][41];
     const int mt = blockIdx.x, r = threadIdx.x;
     const int t0 = mt * kTileM;
@@ -490,6 +490,13 @@ tc_prep_kernel(const float *__restrict__ feat, int T, int stride, int off, int D
     __syncthreads();
     for (int i = 0; i < Dp; ++i)
         gX[((size_t)mt * Dp + i) * kTileM + r] = (r < nrow && i < D) ? tile[r][i] : 0.f;
+    if (xrow) {
+        const int D4 = (D + 3) & ~3;
+        for (int e = r; e < kTileM * D4; e += kTileM) {
+            const int rr = e / D4, i = e % D4;
+            xrow[(size_t)t0 * D4 + e] = (rr < nrow && i < D) ? tile[rr][i] : 0.f;
+        }
+    }
     if (xmax && r < D) atomicMax(xmax + r, s_max[r]);
 }
 
@@ -1105,7 +1112,7 @@ tc_finish_kernel(const int16_t *__restrict__ raw, int T, int T_pad, int n_sen, i
 // `rows`: 16-byte aligned copy of the parameters, [codebook * n_density + id][mean Dp | scaled 1/(2 var) Dp]
 // with Dp = D rounded up to 4 (one 16-byte gather per 4 dimensions).
 template <int DC>
-__device__ __forceinline__ float exact_dist_n(const GmmDev &g, const float4 *__restrict__ rows, const float *__restrict__ x,
+__device__ __forceinline__ float exact_dist_n(const GmmDev &g, const float4 *__restrict__ rows, const float4 *__restrict__ x4,
                                               int s, int id, int D) {
     const int q = (D + 3) >> 2;
     const float4 *__restrict__ rp = rows + ((size_t)s * g.n_density + id) * (2 * q);
@@ -1114,33 +1121,35 @@ __device__ __forceinline__ float exact_dist_n(const GmmDev &g, const float4 *__r
     if (DC > 0) {
 #pragma unroll
         for (int i4 = 0; i4 < QC; ++i4) {
-            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + QC + i4);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + QC + i4), xx = __ldg(x4 + i4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, xs[4] = {xx.x, xx.y, xx.z, xx.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (i4 * 4 + e < DC) {
-                    const float diff = __fsub_rn(__ldg(x + i4 * 4 + e), mm[e]);
+                    const float diff = __fsub_rn(xs[e], mm[e]);
                     d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
                 }
         }
     } else {
         for (int i4 = 0; i4 < q; ++i4) {
-            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4);
-            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float4 m4 = __ldg(rp + i4), v4 = __ldg(rp + q + i4), xx = __ldg(x4 + i4);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, xs[4] = {xx.x, xx.y, xx.z, xx.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (i4 * 4 + e < D) {
-                    const float diff = __fsub_rn(__ldg(x + i4 * 4 + e), mm[e]);
+                    const float diff = __fsub_rn(xs[e], mm[e]);
                     d = __fsub_rn(d, __fmul_rn(__fmul_rn(diff, diff), vv[e]));
                 }
         }
     }
     return d;
 }
-__device__ __forceinline__ float exact_dist(const GmmDev &g, const float4 *rows, const float *x, int s, int id) {
+// `xrow`: the batch's features as 16-byte aligned zero-padded rows [T_pad][(D+3)&~3] (tc_prep_kernel)
+__device__ __forceinline__ float exact_dist(const GmmDev &g, const float4 *rows, const float *xrow, int t, int s, int id) {
     const int D = g.featlen[0];
-    if (D == 39) return exact_dist_n<39>(g, rows, x, s, id, D);
-    return exact_dist_n<0>(g, rows, x, s, id, D);
+    const float4 *x4 = reinterpret_cast<const float4 *>(xrow) + (size_t)t * ((D + 3) >> 2);
+    if (D == 39) return exact_dist_n<39>(g, rows, x4, s, id, D);
+    return exact_dist_n<0>(g, rows, x4, s, id, D);
 }
 
 __device__ __forceinline__ int32_t exact_chain(const GmmDev &g, const int32_t (&fw)[4], int n) {
@@ -1194,7 +1203,7 @@ tc_fix_a_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ row
             if (k < n_open) {
                 const uint32_t slot = ((c < 2 ? z : w) >> (16 * (c & 1))) & 0xffffu;
                 const int id = slot & 31;
-                const float d = exact_dist(g, rows, feat + (size_t)t * g.veclen, sn, id);
+                const float d = exact_dist(g, rows, feat, t, sn, id);
                 const int32_t di = (int32_t)d;
                 s_fw[wp][src][c] = ((di + ((1 << kShift) - 1)) >> kShift) - (int32_t)g.mixw_t[(size_t)id * g.n_sen + sn];
                 // |GEMM - reference| on this density, from the 10 low bits the item kept of floor(-d~)
@@ -1237,7 +1246,7 @@ tc_fix_b_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ row
         if (all) { t = (int)(i / g.n_sen); s = (int)(i % g.n_sen); }
         else { const uint2 it = qb[i]; t = (int)it.x; s = (int)it.y; }
         if (s >= g.n_sen || t >= T) continue;
-        float d = lane < g.n_density ? exact_dist(g, rows, feat + (size_t)t * g.veclen, s, lane) : 0.f;
+        float d = lane < g.n_density ? exact_dist(g, rows, feat, t, s, lane) : 0.f;
         bool in = lane < g.n_density;
         int32_t fw[4];
         for (int r = 0; r < 4; ++r) {
@@ -1421,6 +1430,7 @@ struct TcPlan {
     uint8_t *dMixw = nullptr;
     float *dA = nullptr; size_t a_cap = 0;       // tiled/transposed features (bytes)
     float *dAh = nullptr; size_t ah_cap = 0;     // same in the fp16 kernel's padding, when it differs
+    float *dXrow = nullptr; size_t xrow_cap = 0; // 16-byte aligned zero-padded feature rows for the exact fix-up kernels
     HalfOperand half;                            // fp16 hi/lo form of the B operand (ksteps == 0: not available)
     int16_t *dRaw = nullptr; size_t raw_cap = 0; // bytes
     int n_sm = 148;
@@ -1448,7 +1458,7 @@ bool tc_shape_supported(const GmmDev &g) {
 void tc_plan_free(TcPlan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dAh); cudaFree(p->dRaw);
+    cudaFree(p->dB); cudaFree(p->dMixw); cudaFree(p->dA); cudaFree(p->dAh); cudaFree(p->dRaw); cudaFree(p->dXrow);
     cudaFree(p->dCw); cudaFree(p->dRows); cudaFree(p->dQa); cudaFree(p->dQb); cudaFree(p->dQcnt);
     p->half.release();
     delete p;
@@ -1570,7 +1580,8 @@ static int launch_score_ks_half(const TcParams &prm, int ks, int grid, cudaStrea
 // too when its padded dimension count differs; reduces max |x_i| per dimension and
 // decides every n-tile's operand format for this batch.
 static int prep_features(const float *d_feat, int T, int stride, int off, int D, int ks_tf32, const HalfOperand &h,
-                         float **dX, size_t *x_cap, float **dXh, size_t *xh_cap, const float **gx_half, cudaStream_t st) {
+                         float **dX, size_t *x_cap, float **dXh, size_t *xh_cap, const float **gx_half, cudaStream_t st,
+                         float *xrow = nullptr) {
     const int n_tiles_m = (T + kTileM - 1) / kTileM;
     const int Dp = 4 * ks_tf32, Dph = 8 * h.ksteps;
     const size_t bytes = (size_t)n_tiles_m * Dp * kTileM * sizeof(float);
@@ -1583,7 +1594,7 @@ static int prep_features(const float *d_feat, int T, int stride, int off, int D,
         B200_CUDA_OK(cudaMemsetAsync(h.dXmax, 0, (size_t)D * 4, st));
         B200_CUDA_OK(cudaMemsetAsync(h.dNHalf, 0, 4, st));
     }
-    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dp, *dX, h.ksteps ? h.dXmax : nullptr);
+    tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dp, *dX, h.ksteps ? h.dXmax : nullptr, xrow);
     B200_LAUNCH_CHECK();
     if (h.ksteps) {
         tc_tile_format_kernel<<<(h.n_tiles + 255) / 256, 256, 0, st>>>(h.dXmax, h.dLim, D, h.n_tiles, h.dFmt, h.dNHalf);
@@ -1597,7 +1608,7 @@ static int prep_features(const float *d_feat, int T, int stride, int off, int D,
             B200_CUDA_OK(cudaMalloc((void **)dXh, hb));
             *xh_cap = hb;
         }
-        tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dph, *dXh, nullptr);
+        tc_prep_kernel<<<n_tiles_m, kTileM, 0, st>>>(d_feat, T, stride, off, D, Dph, *dXh, nullptr, nullptr);
         B200_LAUNCH_CHECK();
         *gx_half = *dXh;
     }
@@ -1614,7 +1625,13 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
         p->raw_cap = raw_bytes;
     }
     const float *gx_half = nullptr;
-    int rc0 = prep_features(d_feat, T, p->D, 0, p->D, p->ksteps, p->half, &p->dA, &p->a_cap, &p->dAh, &p->ah_cap, &gx_half, st);
+    const size_t xrow_bytes = (size_t)T_pad * ((p->D + 3) & ~3) * sizeof(float);
+    if (p->xrow_cap < xrow_bytes) {
+        cudaFree(p->dXrow); p->dXrow = nullptr; p->xrow_cap = 0;
+        B200_CUDA_OK(cudaMalloc((void **)&p->dXrow, xrow_bytes));
+        p->xrow_cap = xrow_bytes;
+    }
+    int rc0 = prep_features(d_feat, T, p->D, 0, p->D, p->ksteps, p->half, &p->dA, &p->a_cap, &p->dAh, &p->ah_cap, &gx_half, st, p->dXrow);
     if (rc0) return rc0;
     if (ev_prep) cudaEventRecord(*ev_prep, st);
 
@@ -1677,9 +1694,9 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     }
     if (rc) return rc;
     if (prm.dbg & 8) return B200_OK;      // development: leave the queued pairs un-fixed
-    tc_fix_a_kernel<<<dim3(8, grid), 256, 0, st>>>(p->g, p->dRows, d_feat, T_pad, p->spt, p->dQa, prm.capA, p->dQcnt, p->dRaw, p->eps0, p->eps_shift);
+    tc_fix_a_kernel<<<dim3(8, grid), 256, 0, st>>>(p->g, p->dRows, p->dXrow, T_pad, p->spt, p->dQa, prm.capA, p->dQcnt, p->dRaw, p->eps0, p->eps_shift);
     B200_LAUNCH_CHECK();
-    tc_fix_b_kernel<<<p->n_sm * 4, 256, 0, st>>>(p->g, p->dRows, d_feat, T, T_pad, p->spt, p->dQb, prm.capB, p->dQcnt, p->dRaw);
+    tc_fix_b_kernel<<<p->n_sm * 4, 256, 0, st>>>(p->g, p->dRows, p->dXrow, T, T_pad, p->spt, p->dQb, prm.capB, p->dQcnt, p->dRaw);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
