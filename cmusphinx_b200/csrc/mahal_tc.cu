@@ -1194,16 +1194,43 @@ tc_fix_a_kernel(const __grid_constant__ GmmDev g, const float4 *__restrict__ row
             n_open += __popc(m);
         }
         __syncwarp();
-        for (int k0 = 0; k0 < n_open; k0 += 32) {
-            const int k = k0 + lane;
+        // Four lanes per open slot: lane ql of a quad loads 16-byte piece 4 i + ql of the density's
+        // mean / variance rows and of the frame's feature row (the quad reads 64 contiguous bytes,
+        // the warp 8 rows per instruction instead of 32) and forms its four terms
+        // (x - mean)^2 * v; the subtraction chain -- the reference's order, one rounding per step --
+        // runs over the terms in dimension order, handed round the quad by shuffles.
+        const int D = g.featlen[0], q4 = (D + 3) >> 2;
+        const int ql = lane & 3;
+        for (int k0 = 0; k0 < n_open; k0 += 8) {
+            const int k = k0 + (lane >> 2);
             const int wk = s_work[wp][min(k, n_open - 1)];
             const int src = wk >> 2, c = wk & 3;
             const int t = (int)__shfl_sync(0xffffffffu, it.x, src), sn = (int)__shfl_sync(0xffffffffu, it.y, src);
             const uint32_t z = __shfl_sync(0xffffffffu, it.z, src), w = __shfl_sync(0xffffffffu, it.w, src);
-            if (k < n_open) {
-                const uint32_t slot = ((c < 2 ? z : w) >> (16 * (c & 1))) & 0xffffu;
-                const int id = slot & 31;
-                const float d = exact_dist(g, rows, feat, t, sn, id);
+            const uint32_t slot = ((c < 2 ? z : w) >> (16 * (c & 1))) & 0xffffu;
+            const int id = slot & 31;
+            const float4 *__restrict__ rp = rows + ((size_t)sn * g.n_density + id) * (2 * q4);
+            const float4 *__restrict__ x4 = reinterpret_cast<const float4 *>(feat) + (size_t)t * q4;
+            float d = __ldg(g.det + (size_t)sn * g.n_density + id);
+            for (int i0 = 0; i0 < q4; i0 += 4) {
+                const int idx = i0 + ql;
+                float tm[4] = {0.f, 0.f, 0.f, 0.f};
+                if (idx < q4) {
+                    // (pad dimensions: mean, variance and feature are all 0 there -- the term is +0 and d - 0 == d)
+                    const float4 m4 = __ldg(rp + idx), v4 = __ldg(rp + q4 + idx), xx = __ldg(x4 + idx);
+                    float df;
+                    df = __fsub_rn(xx.x, m4.x); tm[0] = __fmul_rn(__fmul_rn(df, df), v4.x);
+                    df = __fsub_rn(xx.y, m4.y); tm[1] = __fmul_rn(__fmul_rn(df, df), v4.y);
+                    df = __fsub_rn(xx.z, m4.z); tm[2] = __fmul_rn(__fmul_rn(df, df), v4.z);
+                    df = __fsub_rn(xx.w, m4.w); tm[3] = __fmul_rn(__fmul_rn(df, df), v4.w);
+                }
+#pragma unroll
+                for (int sq = 0; sq < 4; ++sq)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        d = __fsub_rn(d, __shfl_sync(0xffffffffu, tm[e], sq, 4));
+            }
+            if (k < n_open && ql == 0) {
                 const int32_t di = (int32_t)d;
                 s_fw[wp][src][c] = ((di + ((1 << kShift) - 1)) >> kShift) - (int32_t)g.mixw_t[(size_t)id * g.n_sen + sn];
                 // |GEMM - reference| on this density, from the 10 low bits the item kept of floor(-d~)
