@@ -695,6 +695,7 @@ struct b200_hmmctx {
     HmmFrame *d_fr = nullptr; int fr_cap = 0;          // [3][n_utt] rotating frame records
     int fr_slot = 0;                                   // slot of the last frame that ran
     int32_t *d_block_count = nullptr, *d_keep_idx = nullptr;   // survivors per tile; survivor list
+    int32_t *d_keep_tmp = nullptr;                             // per-utterance lists of the cluster kernel
     size_t bc_cap = 0;
     uint32_t *d_mask = nullptr; size_t mask_cap = 0;   // [2][n_utt][n_words]
     uint32_t *d_mask_part = nullptr; size_t mask_part_cap = 0;   // words: [2][n_utt][CTAs per utterance][n_words]
@@ -718,8 +719,8 @@ namespace {
 void pop_free(b200_hmmctx *c) {
     cudaFree(c->p.score); cudaFree(c->p.history); cudaFree(c->p.out_score); cudaFree(c->p.out_history);
     cudaFree(c->p.bestscore); cudaFree(c->p.senid); cudaFree(c->p.tmatid); cudaFree(c->p.mpx);
-    cudaFree(c->d_keep_idx);
-    c->p = HmmPop{}; c->d_keep_idx = nullptr; c->pop_cap = 0;
+    cudaFree(c->d_keep_idx); cudaFree(c->d_keep_tmp);
+    c->p = HmmPop{}; c->d_keep_idx = nullptr; c->d_keep_tmp = nullptr; c->pop_cap = 0;
 }
 
 int pop_reserve(b200_hmmctx *c, int n) {
@@ -736,6 +737,7 @@ int pop_reserve(b200_hmmctx *c, int n) {
     B200_CUDA_OK(cudaMalloc((void **)&c->p.tmatid, N * 2));
     B200_CUDA_OK(cudaMalloc((void **)&c->p.mpx, N));
     B200_CUDA_OK(cudaMalloc((void **)&c->d_keep_idx, N * 4));
+    B200_CUDA_OK(cudaMalloc((void **)&c->d_keep_tmp, N * 4));
     c->pop_cap = N; c->p.n_hmm = n;
     return B200_OK;
 }
@@ -768,7 +770,7 @@ int set_utts(b200_hmmctx *c, int n_utt, const int32_t *off) {
     {   // partial masks: at most one resident wave of CTAs (<= 8 per SM) is split over the utterances
         const int wave = 8 * 148;
         const int gy = std::max(1, std::min(n_utt, wave));
-        const size_t gx_max = (size_t)std::max(1, std::min((mx + 255) / 256, wave / gy));
+        const size_t gx_max = (size_t)std::max(16, std::min((mx + 255) / 256, wave / gy));   // (>= the cluster kernel's 16 CTAs per utterance)
         const size_t need = (size_t)2 * n_utt * gx_max * n_words;
         if (need > c->mask_part_cap) {
             cudaFree(c->d_mask_part); c->d_mask_part = nullptr; c->mask_part_cap = 0;
@@ -897,7 +899,7 @@ static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, i
     r.beam = beam; r.do_beam = do_beam;
     r.fr3 = c->d_fr; r.slot0 = (c->fr_slot + 1) % 3;
     r.tile_count = c->d_block_count; r.tpu = (c->p.max_per_utt + 255) / 256;
-    r.keep_idx = c->d_keep_idx;
+    r.keep_idx = c->d_keep_idx; r.keep_tmp = c->d_keep_tmp;
     r.mask2 = c->d_mask; r.mask0 = (c->mask_par + 1) & 1;
     r.mask_part = c->d_mask_part; r.mask_part_words = c->mask_part_cap;
     r.total = c->d_total; r.bar = c->d_bar;

@@ -31,6 +31,7 @@ struct HmmRun {
     int32_t *tile_count;                 // [n_utt][tpu] survivors per 256-HMM tile
     int tpu;                             // tiles per utterance (largest)
     int32_t *keep_idx;
+    int32_t *keep_tmp;                   // [n_hmm] per-utterance survivor lists of the cluster form (packed into keep_idx after the run)
     uint32_t *mask2; int mask0;          // [2][n_utt][n_words], frame f uses (mask0 + f) & 1
     uint32_t *mask_part; size_t mask_part_words;   // [2][n_utt][gx][n_words] per-CTA partial masks
     int32_t *total;

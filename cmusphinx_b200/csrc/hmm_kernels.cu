@@ -312,7 +312,19 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned n_cta, unsi
     __syncthreads();
 }
 
+// all threads of all CTAs of the cluster; release / acquire at cluster scope orders the global-memory
+// hand-overs between the phases (per-utterance best, tile counts, partial masks)
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool CL>
+__device__ __forceinline__ void sync_ctas(unsigned *ctr, unsigned n_cta, unsigned &epoch) {
+    if (CL) cluster_barrier();
+    else grid_barrier(ctr, n_cta, epoch);
+}
+
 // sum over the block of (a, b); every thread gets both totals
+template <int BLK>
 __device__ __forceinline__ int2 block_sum2(int a, int b, int32_t *s_red /* [2 * warps] */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
@@ -320,20 +332,21 @@ __device__ __forceinline__ int2 block_sum2(int a, int b, int32_t *s_red /* [2 * 
     if (lane == 0) { s_red[2 * w] = a; s_red[2 * w + 1] = b; }
     __syncthreads();
     int ta = 0, tb = 0;
-    for (int k = 0; k < kHmmBlock / 32; ++k) { ta += s_red[2 * k]; tb += s_red[2 * k + 1]; }
+    for (int k = 0; k < BLK / 32; ++k) { ta += s_red[2 * k]; tb += s_red[2 * k + 1]; }
     return make_int2(ta, tb);
 }
 
 // The active-senone mask of one utterance and frame: the OR of the partial masks its gx CTAs
 // stored with plain stores (merging them with atomicOr made every CTA of an utterance hammer
 // the same n_words addresses: 17 us per frame on 196 CTAs).  One thread per mask word.
+template <int BLK>
 __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_words] */, int gx, int n_words, uint32_t *mask_u,
                                            int w0, int wstep) {
     // L lanes share a word (each ORs every L-th partial), 256 / L words per pass; this CTA owns
     // the words w0, w0 + wstep, ...
     int L = 1;
     while (L < 32 && L < gx) L <<= 1;
-    const int per_pass = kHmmBlock / L, sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const int per_pass = BLK / L, sub = threadIdx.x % L, slot = threadIdx.x / L;
     const int n_mine = w0 < n_words ? (n_words - w0 + wstep - 1) / wstep : 0;
     for (int j0 = 0; j0 < n_mine; j0 += per_pass) {
         const int j = j0 + slot;
@@ -346,8 +359,16 @@ __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_word
     }
 }
 
-template <int NE>
-__global__ void __launch_bounds__(kHmmBlock, NE == 3 ? 5 : 4)
+// BLK threads per CTA.  CL = false: cooperative launch, one resident wave of 256-thread CTAs, grid
+// barriers, every frame over all utterances.  CL = true: every grid row is a thread-block CLUSTER
+// (gridDim.x CTAs of 1024 threads) that takes ONE utterance at a time through ALL frames of the
+// run with cluster barriers only -- utterances are independent, so no grid-wide barrier is left,
+// and the utterance's state (76 B x 50 000 HMMs = 3.8 MB) stays in L2 from frame to frame instead
+// of streaming from HBM.  Only the last frame's survivor list has to be ordered across
+// utterances: the cluster form writes per-utterance lists (r.keep_tmp) and
+// hmm_compact_last_kernel packs them.
+template <int NE, int BLK, bool CL>
+__global__ void __launch_bounds__(BLK, BLK == 256 ? (NE == 3 ? 5 : 4) : 1)
 hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
@@ -361,8 +382,8 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     int32_t *s_tc = reinterpret_cast<int32_t *>(s_flag + (size_t)((c.n_sen + 31) / 32) * 32);
     int32_t *s_off = s_tc + r.tpu;
     uint32_t *s_bal = reinterpret_cast<uint32_t *>(s_off + rows);
-    __shared__ int32_t s_red[2 * (kHmmBlock / 32)];
-    __shared__ int32_t s_wcnt[kHmmBlock / 32];
+    __shared__ int32_t s_red[2 * (BLK / 32)];
+    __shared__ int32_t s_wcnt[BLK / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gx = gridDim.x, gy = gridDim.y, bx = blockIdx.x, by = blockIdx.y;
     const unsigned n_cta = (unsigned)gx * gy;
@@ -372,35 +393,37 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
 
     {   // transition table once; frame records and the first mask
         const int ntp = c.n_tmat * NE * (NE + 1);
-        for (int i = tid; i < ntp; i += kHmmBlock) s_tp[i] = c.tp[i];
+        for (int i = tid; i < ntp; i += BLK) s_tp[i] = c.tp[i];
         if (bx == 0)
             for (int u = by; u < n_utt; u += gy) {
                 if (tid < 3) { HmmFrame f; f.best = kWorstScore; f.n_keep = 0; f.thresh = kWorstScore; f.pad = 0; r.fr3[(size_t)tid * n_utt + u] = f; }
             }
     }
-    grid_barrier(r.bar, n_cta, epoch);
+    sync_ctas<CL>(r.bar, n_cta, epoch);
 
+    for (int u0 = by; u0 < (CL ? n_utt : by + 1); u0 += gy) {       // CL: one utterance at a time, all its frames
+    const int u_lo = CL ? u0 : by, u_hi = CL ? u0 + 1 : n_utt;
     for (int f = 0; f < r.n_frames; ++f) {
         const bool probe = r.probe && f == r.n_frames - 1 && bx == 0 && by == 0 && tid == 0;
         if (probe) r.probe[0] = clock64();
         HmmFrame *fr = r.fr3 + (size_t)((r.slot0 + f) % 3) * n_utt;
         const int16_t *sen_frame = r.sen_base + (size_t)((r.frame0 + f) % r.n_cycle) * r.frame_stride;
         // ------------------------------------------------ A: hmm_vit_eval
-        for (int u = by; u < n_utt; u += gy) {
+        for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-            if (lo + bx * kHmmBlock >= hi) continue;            // uniform per block
+            if (lo + bx * BLK >= hi) continue;            // uniform per block
             const int16_t *senscr = sen_frame + (size_t)u * c.n_sen;
             __syncthreads();                                    // the previous row's readers are done
             {
                 const int n16 = ((reinterpret_cast<size_t>(senscr) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
                 const int4 *src = reinterpret_cast<const int4 *>(senscr);
                 int4 *dst = reinterpret_cast<int4 *>(s_sen);
-                for (int i = tid; i < n16; i += kHmmBlock) dst[i] = src[i];
-                for (int i = n16 * 8 + tid; i < c.n_sen; i += kHmmBlock) s_sen[i] = senscr[i];
+                for (int i = tid; i < n16; i += BLK) dst[i] = src[i];
+                for (int i = n16 * 8 + tid; i < c.n_sen; i += BLK) s_sen[i] = senscr[i];
             }
             __syncthreads();
             int32_t blockbest = kWorstScore;
-            for (int i = lo + bx * kHmmBlock + tid; i < hi; i += gx * kHmmBlock) {
+            for (int i = lo + bx * BLK + tid; i < hi; i += gx * BLK) {
                 HmmRegs h;
 #pragma unroll
                 for (int s = 0; s < NE; ++s) {
@@ -434,87 +457,89 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             __syncthreads();
             if (tid == 0) {
                 int32_t b = s_wcnt[0];
-                for (int k = 1; k < kHmmBlock / 32; ++k) b = max(b, s_wcnt[k]);
+                for (int k = 1; k < BLK / 32; ++k) b = max(b, s_wcnt[k]);
                 atomicMax(&fr[u].best, b);
             }
         }
         if (!r.do_beam) continue;                               // (eval only: one frame per launch)
         if (probe) r.probe[1] = clock64();
-        grid_barrier(r.bar, n_cta, epoch);
+        sync_ctas<CL>(r.bar, n_cta, epoch);
         if (probe) r.probe[2] = clock64();
 
         // ------------------------------------------------ B: beam test, counts
         // All loads of the CTA's tiles of an utterance are issued before the first vote; the keep
         // ballots stay in shared memory for phase C (no keep-byte array, no second read).
-        for (int u = by; u < n_utt; u += gy) {
+        for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
             if (f > 0)                                          // the previous frame's partial masks are complete (barrier 1)
-                merge_mask(r.mask_part + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx * n_words, gx, n_words,
+                merge_mask<BLK>(r.mask_part + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx * n_words, gx, n_words,
                            r.mask2 + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * n_words, bx, gx);
             const int32_t thresh = fr[u].best + r.beam;
-            const int n_tiles = (hi - lo + kHmmBlock - 1) / kHmmBlock;
-            uint32_t *bal_u = s_bal + (size_t)((u - by) / gy) * rows * (kHmmBlock / 32);
+            const int n_tiles = (hi - lo + BLK - 1) / BLK;
+            uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
             int row = 0;
             for (int t0 = bx; t0 < n_tiles; t0 += 4 * gx, row += 4) {
                 int32_t bs[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int i = lo + (t0 + j * gx) * kHmmBlock + tid;
+                    const int i = lo + (t0 + j * gx) * BLK + tid;
                     bs[j] = (t0 + j * gx < n_tiles && i < hi) ? p.bestscore[i] : (int32_t)0x80000000;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const unsigned bal = __ballot_sync(0xffffffffu, BT(bs[j], thresh));
-                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * (kHmmBlock / 32) + w] = bal;
+                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * (BLK / 32) + w] = bal;
                 }
             }
             __syncthreads();
             int cta_cnt = 0;
-            for (int rr = tid; bx + rr * gx < n_tiles; rr += kHmmBlock) {
+            for (int rr = tid; bx + rr * gx < n_tiles; rr += BLK) {
                 int cnt = 0;
 #pragma unroll
-                for (int k = 0; k < kHmmBlock / 32; ++k) cnt += __popc(bal_u[rr * (kHmmBlock / 32) + k]);
+                for (int k = 0; k < BLK / 32; ++k) cnt += __popc(bal_u[rr * (BLK / 32) + k]);
                 r.tile_count[(size_t)u * r.tpu + bx + rr * gx] = cnt;
                 cta_cnt += cnt;
             }
-            cta_cnt = block_sum2(cta_cnt, 0, s_red).x;
+            cta_cnt = block_sum2<BLK>(cta_cnt, 0, s_red).x;
             if (tid == 0) {
                 if (cta_cnt) atomicAdd(&fr[u].n_keep, cta_cnt);
                 if (bx == 0) fr[u].thresh = thresh;
             }
         }
         if (probe) r.probe[3] = clock64();
-        grid_barrier(r.bar, n_cta, epoch);
+        sync_ctas<CL>(r.bar, n_cta, epoch);
         if (probe) r.probe[4] = clock64();
 
         // ------------------------------------------------ C: scatter + active senones
         uint32_t *part_f = r.mask_part + (size_t)((r.mask0 + f) & 1) * n_utt * gx * n_words;
         HmmFrame *fr_n2 = r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt;
-        for (int u = by; u < n_utt; u += gy) {
+        for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-            const int n_tiles = (hi - lo + kHmmBlock - 1) / kHmmBlock;
-            const uint32_t *bal_u = s_bal + (size_t)((u - by) / gy) * rows * (kHmmBlock / 32);
+            const int n_tiles = (hi - lo + BLK - 1) / BLK;
+            const uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
             // survivors of the utterances before this one; the utterance's tile counts
             int part = 0;
-            for (int k = tid; k < u; k += kHmmBlock) part += fr[k].n_keep;
-            for (int k = tid; k < n_tiles; k += kHmmBlock) s_tc[k] = r.tile_count[(size_t)u * r.tpu + k];
-            const int base = block_sum2(part, 0, s_red).x;      // (its barriers also publish s_tc)
+            if (!CL) for (int k = tid; k < u; k += BLK) part += fr[k].n_keep;
+            for (int k = tid; k < n_tiles; k += BLK) s_tc[k] = r.tile_count[(size_t)u * r.tpu + k];
+            const int base_all = block_sum2<BLK>(part, 0, s_red).x;  // (its barriers also publish s_tc)
+            const int base = CL ? lo : base_all;                     // CL: a list per utterance, packed after the run
+            int32_t *keep_dst = CL ? r.keep_tmp : r.keep_idx;
             if (bx == 0 && tid == 0) {
-                if (u == n_utt - 1) *r.total = base + fr[u].n_keep;
+                if (!CL && u == n_utt - 1) *r.total = base + fr[u].n_keep;
                 HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
                 fr_n2[u] = z;                                   // the record of the frame after next
             }
             uint32_t *part_u = part_f + ((size_t)u * gx + bx) * n_words;
             if (bx >= n_tiles) {                                // (uniform) no tile of this utterance: an empty partial mask
-                for (int k = tid; k < n_words; k += kHmmBlock) part_u[k] = 0u;
+                for (int k = tid; k < n_words; k += BLK) part_u[k] = 0u;
                 continue;
             }
-            for (int k = tid; k < n_words * 8; k += kHmmBlock) s_flag_w[k] = 0u;
+            for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
             // exclusive scan of the utterance's tile counts, in place (one pass: a chunk per thread,
             // then a scan of the 256 chunk sums)
             __syncthreads();
             {
-                const int per = (n_tiles + kHmmBlock - 1) / kHmmBlock;
+                const int per = (n_tiles + BLK - 1) / BLK;
                 const int k0 = min(n_tiles, tid * per), k1 = min(n_tiles, k0 + per);
                 int sum = 0;
                 for (int k = k0; k < k1; ++k) sum += s_tc[k];
@@ -535,8 +560,8 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int t = bx + (row0 + j) * gx;
-                    idx[j] = lo + t * kHmmBlock + tid;
-                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * (kHmmBlock / 32) + w] >> lane) & 1u);
+                    idx[j] = lo + t * BLK + tid;
+                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * (BLK / 32) + w] >> lane) & 1u);
                     const int ii = min(idx[j], hi - 1);
                     mp[j] = p.mpx[ii] != 0;
 #pragma unroll
@@ -552,17 +577,17 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 for (int j = 0; j < 4; ++j) {
                     if (!act[j]) continue;
                     const int row = row0 + j;
-                    const unsigned bal = bal_u[row * (kHmmBlock / 32) + w];
+                    const unsigned bal = bal_u[row * (BLK / 32) + w];
                     int woff = 0;
-                    for (int k = 0; k < w; ++k) woff += __popc(bal_u[row * (kHmmBlock / 32) + k]);
-                    r.keep_idx[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = idx[j];
+                    for (int k = 0; k < w; ++k) woff += __popc(bal_u[row * (BLK / 32) + k]);
+                    keep_dst[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = idx[j];
 #pragma unroll
                     for (int s = 0; s < NE; ++s)
                         if (sid[j][s] != 0xffffffffu) s_flag[sid[j][s]] = 1;
                 }
             }
             __syncthreads();
-            for (int kk = w; kk < n_words; kk += kHmmBlock / 32) {      // warp-uniform loop
+            for (int kk = w; kk < n_words; kk += BLK / 32) {      // warp-uniform loop
                 const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
                 if (lane == 0) part_u[kk] = word;
             }
@@ -571,24 +596,40 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
         if (probe) r.probe[5] = clock64();
     }
     if (r.do_beam && r.n_frames > 0) {                          // the last frame's mask
-        grid_barrier(r.bar, n_cta, epoch);
+        sync_ctas<CL>(r.bar, n_cta, epoch);
         const int f = r.n_frames - 1;
-        for (int u = by; u < n_utt; u += gy)
-            merge_mask(r.mask_part + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx * n_words, gx, n_words,
+        for (int u = u_lo; u < u_hi; u += gy)
+            merge_mask<BLK>(r.mask_part + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx * n_words, gx, n_words,
                        r.mask2 + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * n_words, bx, gx);
     }
+    }                                                           // next utterance of this cluster
+}
+
+// The cluster form leaves the last frame's survivors as one list per utterance at keep_tmp + utt_off[u];
+// pack them in (utterance, HMM index) order and publish the total.  One block per utterance.
+__global__ void __launch_bounds__(256)
+hmm_compact_last_kernel(HmmPop p, const HmmFrame *__restrict__ fr, const int32_t *__restrict__ keep_tmp,
+                        int32_t *__restrict__ keep_idx, int32_t *__restrict__ total) {
+    __shared__ int s_base;
+    const int u = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int k = 0; k < u; ++k) b += fr[k].n_keep;
+        s_base = b;
+        if (u == p.n_utt - 1) *total = b + fr[u].n_keep;
+    }
+    __syncthreads();
+    const int n = fr[u].n_keep, lo = p.utt_off[u], base = s_base;
+    for (int i = threadIdx.x; i < n; i += 256) keep_idx[base + i] = keep_tmp[lo + i];
 }
 
 // ------------------------------------------------------------ host launcher
-static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta) {
+static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
     const int rows = (tpu + gx - 1) / gx + 3;
     return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (((size_t)c.n_tmat * c.n_emit * (c.n_emit + 1) + 15) & ~(size_t)15) +
-           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (kHmmBlock / 32)) * 4 + 16;
+           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (blk / 32)) * 4 + 16;
 }
 
-int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
-    if (p.n_hmm <= 0 || p.n_utt <= 0 || run_in.n_frames <= 0) return B200_OK;
-    if (c.n_emit < 1 || c.n_emit > 5) { set_error("n_emit_state %d outside 1..5 (HMM_MAX_NSTATE)", c.n_emit); return B200_ERR_UNSUP; }
 #define B200_HMM_NE(...)                                   \
     switch (c.n_emit) {                                    \
     case 1: { constexpr int NE = 1; __VA_ARGS__; } break;  \
@@ -597,14 +638,76 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
     case 4: { constexpr int NE = 4; __VA_ARGS__; } break;  \
     default: { constexpr int NE = 5; __VA_ARGS__; } break; \
     }
+
+constexpr int kClusterBlock = 1024;
+
+// The cluster form (see hmm_run_kernel): grid rows = clusters of `cs` CTAs x 1024 threads, as many
+// rows as the device can keep resident, each taking utterances row, row + rows, ... through the
+// whole run.  Returns 1 when the form does not apply (then the cooperative form runs).
+static int hmm_launch_run_cluster(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
+    static int enabled = -1;
+    // Opt-in (B200_HMM_CLUSTER=1): measured SLOWER than the cooperative form on B200 -- 17.4 vs 14.5 us per
+    // frame for one utterance x 50 000 HMMs, 175 vs 95 us for 64 utterances.  The cluster barriers are
+    // cheaper (1.2-1.5 k cycles against 2.8-3.0 k for the grid barrier), but a frame's time is the chain of
+    // dependent global round trips INSIDE the phases, and 16 CTAs x 1024 threads walk it three times per
+    // phase where 196 CTAs x 256 threads walk it once (phase A 13.2 k cycles against 4.3 k; profiles/README.md).
+    if (enabled < 0) { const char *e = getenv("B200_HMM_CLUSTER"); enabled = (e && atoi(e) != 0) ? 1 : 0; }
+    if (!enabled || !run_in.do_beam) return 1;
+    HmmRun r = run_in;
+    r.tpu = (p.max_per_utt + kClusterBlock - 1) / kClusterBlock;
     static AttrOnce attr;
     if (attr.need()) {
         cudaError_t e = cudaSuccess;
-        e = cudaFuncSetAttribute(hmm_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
-        e = cudaFuncSetAttribute(hmm_run_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
-        e = cudaFuncSetAttribute(hmm_run_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
-        e = cudaFuncSetAttribute(hmm_run_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
-        e = cudaFuncSetAttribute(hmm_run_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+#define B200_SET(NE_)                                                                                                          \
+        e = cudaFuncSetAttribute(hmm_run_kernel<NE_, kClusterBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(hmm_run_kernel<NE_, kClusterBlock, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); \
+        if (e != cudaSuccess) { cudaGetLastError(); enabled = 0; return 1; }
+        B200_SET(1) B200_SET(2) B200_SET(3) B200_SET(4) B200_SET(5)
+#undef B200_SET
+    }
+    for (int cs = 16; cs >= 8; cs >>= 1) {
+        const size_t sh = run_smem(c, r.tpu, cs, 1, kClusterBlock);
+        if (sh > 200 * 1024) continue;
+        if ((size_t)2 * p.n_utt * cs * ((c.n_sen + 31) / 32) > run_in.mask_part_words) continue;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs, 1, 1); cfg.blockDim = dim3(kClusterBlock, 1, 1); cfg.dynamicSmemBytes = sh; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        cudaError_t e = cudaSuccess;
+        B200_HMM_NE(e = cudaOccupancyMaxActiveClusters(&n_clusters, hmm_run_kernel<NE, kClusterBlock, true>, &cfg));
+        if (e != cudaSuccess || n_clusters < 1) { cudaGetLastError(); continue; }
+        cfg.gridDim = dim3(cs, std::min(p.n_utt, n_clusters), 1);
+        HmmDev cc = c; HmmPop pp = p;
+        B200_HMM_NE(e = cudaLaunchKernelEx(&cfg, hmm_run_kernel<NE, kClusterBlock, true>, cc, pp, r));
+        if (e != cudaSuccess) { cudaGetLastError(); continue; }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        const HmmFrame *fr_last = r.fr3 + (size_t)((r.slot0 + r.n_frames - 1) % 3) * p.n_utt;
+        hmm_compact_last_kernel<<<p.n_utt, 256, 0, st>>>(pp, fr_last, r.keep_tmp, r.keep_idx, r.total);
+        B200_LAUNCH_CHECK();
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return B200_OK;
+    }
+    return 1;
+}
+
+int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
+    if (p.n_hmm <= 0 || p.n_utt <= 0 || run_in.n_frames <= 0) return B200_OK;
+    if (c.n_emit < 1 || c.n_emit > 5) { set_error("n_emit_state %d outside 1..5 (HMM_MAX_NSTATE)", c.n_emit); return B200_ERR_UNSUP; }
+    {
+        const int rc = hmm_launch_run_cluster(c, p, run_in, st);
+        if (rc != 1) return rc;
+    }
+    static AttrOnce attr;
+    if (attr.need()) {
+        cudaError_t e = cudaSuccess;
+        e = cudaFuncSetAttribute(hmm_run_kernel<1, kHmmBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<2, kHmmBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<3, kHmmBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<4, kHmmBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_run_kernel<5, kHmmBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
     }
     // exactly one resident wave of CTAs (occupancy x SM count); the shared-memory need depends on
     // the grid shape (tiles per CTA), so: shape from the occupancy at the base need, then re-check
@@ -618,10 +721,10 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
         const int wave = per_sm_try * n_sm;
         gy = std::max(1, std::min(p.n_utt, wave));
         gx = std::max(1, std::min(bpu, wave / gy));
-        sh = run_smem(c, bpu, gx, (p.n_utt + gy - 1) / gy);
+        sh = run_smem(c, bpu, gx, (p.n_utt + gy - 1) / gy, kHmmBlock);
         if (sh > 200 * 1024) continue;
         int per_sm = 0;
-        B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_run_kernel<NE>, kHmmBlock, sh));
+        B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_run_kernel<NE, kHmmBlock, false>, kHmmBlock, sh));
         if (per_sm >= per_sm_try) break;
         if (per_sm_try == 1) { set_error("hmm step: population does not fit one resident wave (%zu B shared memory per CTA)", sh); return B200_ERR_UNSUP; }
     }
@@ -635,12 +738,12 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
     B200_CUDA_OK(cudaMemsetAsync(r.bar, 0, sizeof(unsigned), st));
     void *args[] = {(void *)&cc, (void *)&pp, (void *)&r};
     cudaError_t e = cudaSuccess;
-    B200_HMM_NE(e = cudaLaunchCooperativeKernel((const void *)hmm_run_kernel<NE>, dim3(gx, gy), dim3(kHmmBlock), args, sh, st));
-#undef B200_HMM_NE
+    B200_HMM_NE(e = cudaLaunchCooperativeKernel((const void *)hmm_run_kernel<NE, kHmmBlock, false>, dim3(gx, gy), dim3(kHmmBlock), args, sh, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA_OK(e);
     return B200_OK;
 }
+#undef B200_HMM_NE
 
 
 // ------------------------------------------------------------ maintenance

@@ -272,3 +272,21 @@ def test_run_of_frames_as_graph_replays_equals_single_steps(n_utt):
     a.free(); g.free()
     b.lib.b200_dev_free(d_sen)
 
+
+
+def test_cluster_form_of_the_run_kernel_gives_the_same_results():
+    """hmm_run_kernel<NE, 1024, true> (thread-block clusters, one utterance at a time through the
+    whole run, B200_HMM_CLUSTER=1; opt-in because it measured slower) must pass the same
+    beam / compaction / batched-utterance / run-of-frames tests.  The switch is read once per
+    process, hence the sub-process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("B200_HMM_CLUSTER") == "1":
+        pytest.skip("already inside the cluster-form run")
+    env = dict(os.environ, B200_HMM_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "step_beam or batched_utterances or run_of_frames"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
