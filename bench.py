@@ -374,6 +374,7 @@ def run_ours(args):
     kern_ms = m.timing_avg(min(args.steps, 64), 2)
     prep_ms = m.timing_avg(min(args.steps, 64), 1)
     norm_ms = m.timing_avg(min(args.steps, 64), 3)
+    fix_ms = m.timing_avg(min(args.steps, 64), 4) if path == 1 else 0.0
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -434,7 +435,10 @@ def run_ours(args):
     fmt = m.tc_last_format() if path == 1 else -1
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = T * N_SEN * FLOP_PER_UNIT / (kern_ms / 1e3) / 1e12 if kern_ms and kern_ms > 0 else None
+        # the dominant kernel = the tcgen05 score kernel alone; its exact fix-up kernels are timed apart
+        dom_ms = kern_ms - fix_ms if (kern_ms and fix_ms and fix_ms > 0) else kern_ms
+        achieved = T * N_SEN * FLOP_PER_UNIT / (dom_ms / 1e3) / 1e12 if dom_ms and dom_ms > 0 else None
+        achieved_step = T * N_SEN * FLOP_PER_UNIT / (ms_per_step / 1e3) / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": ({1: "f16x3", 2: "f16x3+tf32x3"}.get(fmt, "tf32x3")) if path == 1 else "f32", "data": "synthetic",
@@ -460,7 +464,8 @@ def run_ours(args):
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic()[0],
                              "traffic_source": ncu_traffic()[1], "peak_source": peak_src,
-                             "kernel_ms": {"operand_prep": prep_ms, "score": kern_ms, "normalize": norm_ms},
+                             "frac_whole_step": achieved_step / peak,
+                             "kernel_ms": {"operand_prep": prep_ms, "score": dom_ms, "exact_fixups": fix_ms, "normalize": norm_ms},
                              "algorithmic_flop_per_unit": FLOP_PER_UNIT}}
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -53,7 +53,7 @@ struct b200_mgau {
     // ring of event quadruples: one per timed scoring call, so a caller can run
     // K asynchronous steps and read every step's kernel times afterwards
     static constexpr int kRing = 64;
-    cudaEvent_t ring[kRing][4] = {};
+    cudaEvent_t ring[kRing][5] = {};   // ev0 start, ev1 after prep, ev2 after scoring (+ fix-ups), ev3 end, ev4 between the score kernel and its fix-up kernels
     cudaEvent_t *ev = ring[0];
     long long n_timed = 0;
     float last_ms[4] = {0, 0, 0, 0};
@@ -139,7 +139,7 @@ b200_mgau *mgau_common(int kind, const b200_mgau_cfg_t *cfg, const float *mean, 
     for (int i = 0; i < 2; ++i)
         if (cudaStreamCreateWithFlags(&m->st[i], cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); b200_mgau_free(m); return nullptr; }
     for (int r = 0; r < b200_mgau::kRing; ++r)
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 5; ++i)
             if (cudaEventCreate(&m->ring[r][i]) != cudaSuccess) { set_error("event create failed"); b200_mgau_free(m); return nullptr; }
     if (cudaMalloc((void **)&m->d_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
         cudaMallocHost((void **)&m->h_row, (size_t)g.n_sen * 2 + 16) != cudaSuccess ||
@@ -164,7 +164,8 @@ int score_dense_dev(b200_mgau *m, const float *d_feat, int T, int16_t *d_out, cu
     }
     if (m->kind == 0 && m->path == 1 && m->tc) {
         int T_pad = 0;
-        if ((rc = tc_score_raw(m->tc, d_feat, T, st, timed ? &m->ev[1] : nullptr, &T_pad))) return rc;
+        if (timed) cudaEventRecord(m->ev[4], st);       // (re-recorded inside when the fix-up kernels run)
+        if ((rc = tc_score_raw(m->tc, d_feat, T, st, timed ? &m->ev[1] : nullptr, &T_pad, timed ? &m->ev[4] : nullptr))) return rc;
         if (timed) cudaEventRecord(m->ev[2], st);
         if ((rc = tc_finish(m->tc, T, T_pad, normalize ? 1 : 0, d_out, st))) return rc;
         if (timed) cudaEventRecord(m->ev[3], st);
@@ -355,7 +356,7 @@ void b200_mgau_free(b200_mgau_t *m) {
     cudaFree(m->d_sen2cb); cudaFree(m->d_sen2mgau); cudaFree(m->d_lists);
     for (int i = 0; i < 2; ++i) { cudaFree(m->d_feat[i]); cudaFree(m->d_out[i]); if (m->st[i]) cudaStreamDestroy(m->st[i]); }
     for (int r = 0; r < b200_mgau::kRing; ++r)
-        for (int i = 0; i < 4; ++i) if (m->ring[r][i]) cudaEventDestroy(m->ring[r][i]);
+        for (int i = 0; i < 5; ++i) if (m->ring[r][i]) cudaEventDestroy(m->ring[r][i]);
     cudaFree(m->d_ufeat); cudaFree(m->d_uraw); cudaFree(m->d_ulists); cudaFree(m->d_carry); cudaFree(m->d_active); cudaFree(m->d_row);
     if (m->h_row) cudaFreeHost(m->h_row);
     if (m->h_active) cudaFreeHost(m->h_active);
@@ -495,7 +496,7 @@ float b200_mgau_last_ms(const b200_mgau_t *m, int which) {
 }
 
 float b200_mgau_timing_avg(b200_mgau_t *m, int n_calls, int which) {
-    if (!m || which < 0 || which > 3 || n_calls < 1) return -1.f;
+    if (!m || which < 0 || which > 4 || n_calls < 1) return -1.f;
     if (n_calls > b200_mgau::kRing) n_calls = b200_mgau::kRing;
     if ((long long)n_calls > m->n_timed) n_calls = (int)m->n_timed;
     if (n_calls < 1) return -1.f;
@@ -505,6 +506,7 @@ float b200_mgau_timing_avg(b200_mgau_t *m, int n_calls, int which) {
         cudaEvent_t *e = m->ring[(m->n_timed - 1 - k) % b200_mgau::kRing];
         float ms = 0;
         cudaError_t rc = which == 0 ? cudaEventElapsedTime(&ms, e[0], e[3])
+                       : which == 4 ? cudaEventElapsedTime(&ms, e[4], e[2])
                                     : cudaEventElapsedTime(&ms, e[which - 1], e[which]);
         if (rc != cudaSuccess) { set_error("timing not available: %s", cudaGetErrorString(rc)); cudaGetLastError(); return -1.f; }
         sum += ms;

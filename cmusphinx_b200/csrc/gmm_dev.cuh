@@ -96,7 +96,7 @@ bool tc_shape_supported(const GmmDev &g);
 // Stage 1: operand prep + scoring kernel -> tile-major raw scores inside the
 // plan (ev_prep, if given, is recorded between the two kernels).  Stage 2:
 // transpose to row-major d_out[T][n_sen], minus the frame best if asked.
-int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out);
+int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out, cudaEvent_t *ev_fix = nullptr);
 int tc_last_format(TcPlan *p);   // 1 all tiles fp16, 0 all TF32, 2 mixed (synchronises)
 // {pairs scored, pairs on the hard path, queue A items, queue B items, overflow flag,
 //  largest |GEMM - reference| distance seen} of the last tc_score_raw (synchronises)

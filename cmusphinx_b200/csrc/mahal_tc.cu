@@ -1642,7 +1642,7 @@ static int prep_features(const float *d_feat, int T, int stride, int off, int D,
     return B200_OK;
 }
 
-int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out) {
+int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEvent_t *ev_prep, int *T_pad_out, cudaEvent_t *ev_fix) {
     const int n_tiles_m = (T + kTileM - 1) / kTileM;
     const int T_pad = n_tiles_m * kTileM;
     const size_t raw_bytes = (size_t)p->n_tiles_n * T_pad * p->spt * sizeof(int16_t);
@@ -1721,6 +1721,7 @@ int tc_score_raw(TcPlan *p, const float *d_feat, int T, cudaStream_t st, cudaEve
     }
     if (rc) return rc;
     if (prm.dbg & 8) return B200_OK;      // development: leave the queued pairs un-fixed
+    if (ev_fix) cudaEventRecord(*ev_fix, st);   // score kernel(s) | exact fix-up kernels
     tc_fix_a_kernel<<<dim3(8, grid), 256, 0, st>>>(p->g, p->dRows, p->dXrow, T_pad, p->spt, p->dQa, prm.capA, p->dQcnt, p->dRaw, p->eps0, p->eps_shift);
     B200_LAUNCH_CHECK();
     tc_fix_b_kernel<<<p->n_sm * 4, 256, 0, st>>>(p->g, p->dRows, p->dXrow, T, T_pad, p->spt, p->dQb, prm.capB, p->dQcnt, p->dRaw);

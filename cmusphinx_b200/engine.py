@@ -292,7 +292,8 @@ class Mgau:
 
     def timing_avg(self, n_calls: int, which: int = 2) -> float:
         """Mean device time (ms) of section `which` (0 total, 1 operand prep, 2
-        scoring kernels, 3 normalise) over the last n_calls score_dev calls."""
+        scoring kernels, 3 normalise, 4 the exact fix-up kernels inside 2) over the last
+        n_calls score_dev calls."""
         return lib.b200_mgau_timing_avg(self._h, n_calls, which)
 
     # utterance-batched serving (what the plug-in does)

@@ -270,7 +270,9 @@ int  b200_mgau_utt_frame(b200_mgau_t *m, int16_t *senscr,
 
 /* Timing of the last score_* call's dominant kernel(s) in milliseconds
  * (CUDA events on the launching stream). which: 0 = total device time,
- * 1 = operand-prep kernel, 2 = main scoring kernel, 3 = normalise kernel. */
+ * 1 = operand-prep kernel, 2 = main scoring kernel(s), 3 = normalise kernel;
+ * b200_mgau_timing_avg also takes 4 = the exact fix-up kernels of the tensor-core
+ * ms path (the tail of section 2; 2 minus 4 = the tcgen05 score kernel alone). */
 float b200_mgau_last_ms(const b200_mgau_t *m, int which);
 /* Average of the same quantity over the last n_calls (<= 64) score_dev calls,
  * including asynchronous ones on a caller's stream; the caller must have
