@@ -58,6 +58,9 @@ struct S3Dev {
     const uint16_t *tab16; const uint32_t *tab32; uint32_t tab_size;
     int32_t lzero;         // logmath zero (MIN_INT32 >> 2)
     double distfloor, f;
+    // sub-vector quantised shortlists (S3/libam/subvq.c); svq_n_sv == 0: none
+    int svq_n_sv, svq_size, svq_eval; int32_t svq_beam;
+    const int32_t *svq_map;    // [s][cpt][n_sv] compacted + linearised (sub-vector * size + codeword)
 };
 
 // logmath_add, SB/util/logmath.c:391-436 (shift 0 table, 16 or 32 bit wide)
@@ -95,7 +98,8 @@ __device__ __forceinline__ int32_t s3_gauscr(const S3Dev &g, int s, int c, doubl
 template <int CP, int KC>
 __global__ void __launch_bounds__(kEvalThreads, 8)
 s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_hi,
-               const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, int16_t *__restrict__ bst) {
+               const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, int16_t *__restrict__ bst,
+               const int32_t *__restrict__ vqd /* [T][n_sv * size] sub-VQ scores of every frame, or null */) {
     extern __shared__ float xs[];   // [kFB][veclen] | int32 stage[G][kFR][CP*KC]
     constexpr int G = kEvalThreads / CP;
     const int t0 = blockIdx.y * kFB;
@@ -160,19 +164,87 @@ s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_h
         // frame; with update_best_id == 1 the best component is the first
         // strict maximum
         for (int j = lc; j < nv; j += CP) {
-            int32_t score = kS3Zero, bscr = kS3Zero; int bidx = kNoBst;
             const int32_t *sj = stage + j * CP * KC;
-            for (int c = 0; c < nc; ++c) {
-                const int32_t v = sj[c];
-                score = s3_logadd(g, score, v);
-                if (v > bscr) { bscr = v; bidx = c; }
-            }
-            if (score <= kS3Zero) score = kS3Zero;
             const int kj = __fns(mask0, 0, j + 1);      // j-th flagged frame of this pass
+            // approx_mgau_eval (approx_cont_mgau.c:187-284) with a sub-VQ model: the components whose
+            // quantised score is within the beam of the senone's best one (subvq_mgau_shortlist,
+            // subvq.c:383-468) -- a mask over the dense result -- and the whole mixture again when
+            // the shortlist's score is hopeless (< S3_LOGPROB_ZERO + 100000, :256-281)
+            const int32_t *vq = vqd ? vqd + (size_t)(t0 + kj) * g.svq_n_sv * g.svq_size : nullptr;
+            const int32_t *mp0 = g.svq_map + (size_t)s * g.cpt * g.svq_n_sv;
+            auto quant = [&](int c) -> int32_t {
+                const int32_t *mp = mp0 + (size_t)c * g.svq_n_sv;
+                uint32_t v;                              // (the reference's int32 sums wrap)
+                if (g.svq_n_sv == 3) {
+                    if (g.svq_eval == 1) v = (uint32_t)vq[mp[0]];
+                    else if (g.svq_eval == 2) v = (uint32_t)vq[mp[0]] + 2u * (uint32_t)vq[mp[1]];
+                    else v = (uint32_t)vq[mp[0]] + (uint32_t)vq[mp[1]] + (uint32_t)vq[mp[2]];
+                } else {
+                    v = 0;
+                    for (int k2 = 0; k2 < g.svq_n_sv; ++k2) v += (uint32_t)vq[mp[k2]];
+                }
+                return (int32_t)v;
+            };
+            int32_t th = (int32_t)0x80000000;
+            bool shortlist = vq != nullptr;
+            if (shortlist) {
+                int32_t bv = (int32_t)0x80000000;
+                for (int c = 0; c < nc; ++c) bv = max(bv, quant(c));
+                th = (int32_t)((uint32_t)bv + (uint32_t)g.svq_beam);
+            }
+            int32_t score, bscr; int bidx;
+            while (true) {
+                score = kS3Zero; bscr = kS3Zero; bidx = kNoBst;
+                for (int c = 0; c < nc; ++c) {
+                    if (shortlist && quant(c) < th) continue;
+                    const int32_t v = sj[c];
+                    score = s3_logadd(g, score, v);
+                    if (v > bscr) { bscr = v; bidx = c; }
+                }
+                if (score <= kS3Zero) score = kS3Zero;
+                if (!(shortlist && score < kS3Zero + 100000)) break;
+                shortlist = false;
+            }
             raw[(size_t)(t0 + kj) * g.n_sen + s] = score;
             if (bst) bst[(size_t)(t0 + kj) * g.n_sen + s] = (int16_t)bidx;
         }
         __syncwarp(gmask);
+    }
+}
+
+// subvq_gautbl_eval_logs3 (subvq.c:488-506) / vector_gautbl_eval_logs3 (S3/libcommon/vector.c:590-650) for every
+// frame: one block per frame, one thread per (sub-vector, codeword); the same float32-difference /
+// float64-accumulate arithmetic as the densities.  Sub-vectors >= VQ_EVAL are never evaluated by the reference
+// and keep the 0 its calloc left there.
+struct S3Vq {
+    int n_sv, size, n_eval;
+    const int32_t *veclen, *off_dim, *off_par;   // [n_sv]: length, offset into featdim, offset into mean / var
+    const int32_t *featdim;
+    const float *mean, *lrd;                     // mean [off_par + r * L + i], lrd [sv * size + r]
+    const double *var;
+    double distfloor, f;
+};
+__global__ void __launch_bounds__(128)
+s3_vq_kernel(S3Vq q, const float *__restrict__ feat, int T, int veclen, int32_t *__restrict__ out) {
+    const int t = blockIdx.x;
+    const float *x = feat + (size_t)t * veclen;
+    for (int e = threadIdx.x; e < q.n_sv * q.size; e += blockDim.x) {
+        const int sv = e / q.size, r = e % q.size;
+        int32_t v = 0;
+        if (sv < q.n_eval) {
+            const int L = q.veclen[sv];
+            const int32_t *fd = q.featdim + q.off_dim[sv];
+            const float *mu = q.mean + q.off_par[sv] + (size_t)r * L;
+            const double *va = q.var + q.off_par[sv] + (size_t)r * L;
+            double dval = (double)q.lrd[e];
+            for (int i = 0; i < L; ++i) {
+                const double dd = (double)__fsub_rn(x[fd[i]], mu[i]);
+                dval = __dsub_rn(dval, __dmul_rn(__dmul_rn(dd, dd), va[i]));
+            }
+            if (dval < q.distfloor) dval = q.distfloor;
+            v = __double2int_rz(__dmul_rn(q.f, dval));
+        }
+        out[(size_t)t * q.n_sv * q.size + e] = v;
     }
 }
 
@@ -375,6 +447,11 @@ struct b200_s3mgau {
     size_t capT = 0;
     float *d_feat = nullptr; uint8_t *d_act = nullptr, *d_flags = nullptr;
     int32_t *d_raw = nullptr, *d_out = nullptr, *d_beam = nullptr, *d_best = nullptr; int16_t *d_bst = nullptr;
+    // sub-VQ model (b200_s3_set_subvq), optional
+    int svq_n_sv = 0, svq_size = 0, svq_eval = 0; int32_t svq_beam = 0;
+    int32_t *d_svq_map = nullptr, *d_svq_i = nullptr; float *d_svq_f = nullptr; double *d_svq_var = nullptr;
+    int32_t *d_vqd = nullptr; size_t vqd_cap = 0;
+    S3Vq vq{};
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0.f;
@@ -384,6 +461,7 @@ struct b200_s3mgau {
         g.mean = d_mean; g.var = d_var; g.lrd = d_lrd; g.mixw = d_mixw; g.ncomp = d_ncomp; g.cd2ci = d_cd2ci;
         g.tab16 = d_tab16; g.tab32 = d_tab32; g.tab_size = (uint32_t)lm->table.size();
         g.lzero = lm->zero; g.distfloor = distfloor; g.f = f;
+        g.svq_n_sv = svq_n_sv; g.svq_size = svq_size; g.svq_eval = svq_eval; g.svq_beam = svq_beam; g.svq_map = d_svq_map;
         return g;
     }
 };
@@ -413,27 +491,27 @@ int s3_reserve(b200_s3mgau *m, int T) {
 
 template <int CP, int KC>
 int launch_eval_t(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
-                  int32_t *raw, int16_t *bst, cudaStream_t st) {
+                  int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd) {
     if (s_hi <= s_lo || T <= 0) return B200_OK;
     constexpr int G = kEvalThreads / CP;
     dim3 grid((s_hi - s_lo + G - 1) / G, (T + kFB - 1) / kFB);
     size_t smem = (size_t)kFB * m->veclen * sizeof(float) + (size_t)kEvalThreads * KC * kFR * sizeof(int32_t);
-    s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst);
+    s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst, vqd);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
 int launch_eval(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
-                int32_t *raw, int16_t *bst, cudaStream_t st) {
+                int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd = nullptr) {
     switch (m->cp * 8 + m->kc) {
-    case 1 * 8 + 1: return launch_eval_t<1, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 2 * 8 + 1: return launch_eval_t<2, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 4 * 8 + 1: return launch_eval_t<4, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 8 * 8 + 1: return launch_eval_t<8, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 16 * 8 + 1: return launch_eval_t<16, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 32 * 8 + 1: return launch_eval_t<32, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 32 * 8 + 2: return launch_eval_t<32, 2>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
-    case 32 * 8 + 4: return launch_eval_t<32, 4>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st);
+    case 1 * 8 + 1: return launch_eval_t<1, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 2 * 8 + 1: return launch_eval_t<2, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 4 * 8 + 1: return launch_eval_t<4, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 8 * 8 + 1: return launch_eval_t<8, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 16 * 8 + 1: return launch_eval_t<16, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 32 * 8 + 1: return launch_eval_t<32, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 32 * 8 + 2: return launch_eval_t<32, 2>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 32 * 8 + 4: return launch_eval_t<32, 4>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
     }
     set_error("unsupported component count");
     return B200_ERR_UNSUP;
@@ -444,11 +522,23 @@ int s3_chunk_dev(b200_s3mgau *m, const float *d_feat, int T, int frame0, uint8_t
                  int32_t *d_best, cudaStream_t st) {
     const S3Dev g = m->dev();
     int rc;
-    if ((rc = launch_eval(m, d_feat, T, 0, m->n_ci, nullptr, m->d_raw, m->d_bst, st))) return rc;
+    const int32_t *vqd = nullptr;
+    if (m->svq_n_sv) {
+        const size_t need = (size_t)T * m->svq_n_sv * m->svq_size;
+        if (need > m->vqd_cap) {
+            cudaFree(m->d_vqd); m->d_vqd = nullptr; m->vqd_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&m->d_vqd, need * sizeof(int32_t)));
+            m->vqd_cap = need;
+        }
+        s3_vq_kernel<<<T, 128, 0, st>>>(m->vq, d_feat, T, m->veclen, m->d_vqd);
+        B200_LAUNCH_CHECK();
+        vqd = m->d_vqd;
+    }
+    if ((rc = launch_eval(m, d_feat, T, 0, m->n_ci, nullptr, m->d_raw, m->d_bst, st, vqd))) return rc;
     s3_decide_kernel<<<T, 256, (size_t)3 * std::max(m->n_ci, 1) * sizeof(int32_t), st>>>(
         g, T, frame0, m->ci_pbeam, m->max_cd, m->ds_ratio, m->tighten, m->d_raw, d_act, m->d_flags, m->d_beam);
     B200_LAUNCH_CHECK();
-    if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st))) return rc;
+    if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st, vqd))) return rc;
     const int n_cd = m->n_sen - m->n_ci;
     if (n_cd > 0) {
         s3_backoff_kernel<<<dim3((n_cd + 127) / 128, T), 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags,
@@ -602,7 +692,8 @@ void b200_s3_free(b200_s3mgau_t *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_mean, m->d_var, m->d_lrd, m->d_mixw, m->d_ncomp, m->d_cd2ci, m->d_tab16, m->d_tab32, m->d_bstidx,
-                    m->d_update, m->d_prev, m->d_feat, m->d_act, m->d_flags, m->d_raw, m->d_out, m->d_beam, m->d_best, m->d_bst};
+                    m->d_update, m->d_prev, m->d_feat, m->d_act, m->d_flags, m->d_raw, m->d_out, m->d_beam, m->d_best, m->d_bst,
+                    m->d_svq_map, m->d_svq_i, m->d_svq_f, m->d_svq_var, m->d_vqd};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (m->st) cudaStreamDestroy(m->st);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
@@ -620,6 +711,128 @@ int b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio
     if (!m || ds_ratio < 1) { set_error("b200_s3_set_fast: bad argument"); return B200_ERR_ARG; }
     m->ci_pbeam = ci_pbeam <= 0.0 ? kS3Zero : m->lm->log(ci_pbeam);   // logs3(), S3/libcommon/logs3.c:110-118
     m->max_cd = max_cd; m->ds_ratio = ds_ratio; m->tighten = tighten_factor;
+    return B200_OK;
+}
+
+// -subvq FILE, -svmax, -vqeval, -subvqbeam: subvq_init (S3/libam/subvq.c:206-373) -- the text file gausubvq
+// writes -- then subvq_maha_precomp (:106-123: variance floor, vector_maha_precomp), subvq_map_compact
+// (:127-181) and subvq_map_linearize (:191-203); the beam goes through logs3 as fast_gmm_init does
+// (fast_algo_struct.c:454).  file == NULL switches the layer off again.
+int b200_s3_set_subvq(b200_s3mgau_t *m, const char *file, double varfloor, int max_sv, int vqeval, double subvqbeam) {
+    if (!m) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    cudaFree(m->d_svq_map); cudaFree(m->d_svq_i); cudaFree(m->d_svq_f); cudaFree(m->d_svq_var);
+    m->d_svq_map = m->d_svq_i = nullptr; m->d_svq_f = nullptr; m->d_svq_var = nullptr; m->svq_n_sv = 0;
+    if (!file) return B200_OK;
+    FILE *fp = fopen(file, "r");
+    if (!fp) { set_error("cannot open sub-VQ file %s", file); return B200_ERR_IO; }
+    std::vector<char> line(1 << 20);
+    auto next = [&]() { return fgets(line.data(), (int)line.size(), fp) != nullptr; };
+    auto fail = [&](const char *what) { fclose(fp); set_error("sub-VQ file %s: %s", file, what); return B200_ERR_IO; };
+    int R = 0, Cc = 0, n_sv_file = 0, size = 0;
+    for (;;) {
+        if (!next()) return fail("no VQParam header");
+        if (sscanf(line.data(), "VQParam %d %d -> %d %d", &R, &Cc, &n_sv_file, &size) == 4) break;
+    }
+    if (R != m->n_sen || Cc != m->max_comp) { fclose(fp); set_error("Model size conflict: %d x %d (SubVQ) vs %d x %d (Original)", R, Cc, m->n_sen, m->max_comp); return B200_ERR_ARG; }
+    if (n_sv_file < 1 || size < 1) return fail("bad VQParam header");
+    int n_sv = (max_sv < 0 || max_sv > n_sv_file) ? n_sv_file : max_sv;
+    if (n_sv < 1) return fail("no sub-vector left (-svmax)");
+    std::vector<int32_t> veclen(n_sv_file), off_dim(n_sv_file + 1, 0), off_par(n_sv_file + 1, 0), featdim;
+    for (int sv = 0; sv < n_sv_file; ++sv) {
+        int k = -1, l = 0, n = 0;
+        if (!next() || sscanf(line.data(), "Subvector %d length %d%n", &k, &l, &n) != 2 || k != sv || l < 1) return fail("sub-vector header");
+        veclen[sv] = l;
+        const char *sp = line.data() + n;
+        for (int c = 0; c < l; ++c) {
+            int d = 0, adv = 0;
+            if (sscanf(sp, "%d%n", &d, &adv) != 1 || d < 0 || d >= m->veclen) return fail("sub-vector dimension");
+            featdim.push_back(d); sp += adv;
+        }
+        off_dim[sv + 1] = off_dim[sv] + l; off_par[sv + 1] = off_par[sv] + l * size;
+    }
+    std::vector<float> mean(off_par[n_sv_file]), lrd((size_t)n_sv_file * size);
+    std::vector<float> varf(off_par[n_sv_file]);
+    std::vector<int32_t> map((size_t)R * Cc * n_sv_file);
+    for (int sv = 0; sv < n_sv_file; ++sv) {
+        int k = -1;
+        if (!next() || sscanf(line.data(), "Codebook %d", &k) != 1 || k != sv) return fail("codebook header");
+        for (int r = 0; r < size; ++r) {
+            if (!next()) return fail("codebook row");
+            const char *sp = line.data();
+            for (int c = 0; c < veclen[sv]; ++c) {
+                int adv = 0;
+                if (sscanf(sp, "%f %f%n", &mean[off_par[sv] + (size_t)r * veclen[sv] + c], &varf[off_par[sv] + (size_t)r * veclen[sv] + c], &adv) != 2) return fail("codebook entry");
+                sp += adv;
+            }
+        }
+        if (!next() || sscanf(line.data(), "Map %d", &k) != 1 || k != sv) return fail("map header");
+        for (int r = 0; r < R; ++r) {
+            if (!next()) return fail("map row");
+            const char *sp = line.data();
+            for (int c = 0; c < Cc; ++c) {
+                int v = 0, adv = 0;
+                if (sscanf(sp, "%d%n", &v, &adv) != 1 || v >= size) return fail("map entry");
+                map[((size_t)r * Cc + c) * n_sv_file + sv] = v; sp += adv;
+            }
+        }
+    }
+    char tok[64] = "";
+    if (fscanf(fp, "%63s", tok) != 1 || strcmp(tok, "End") != 0) return fail("no End token");
+    fclose(fp);
+    // precompute (only the sub-vectors in use matter)
+    std::vector<double> var(off_par[n_sv]);
+    for (int sv = 0; sv < n_sv; ++sv)
+        for (int r = 0; r < size; ++r) {
+            float *v = &varf[off_par[sv] + (size_t)r * veclen[sv]];
+            double det = 0.0;
+            for (int i = 0; i < veclen[sv]; ++i) if (v[i] < varfloor) v[i] = (float)varfloor;
+            for (int i = 0; i < veclen[sv]; ++i) { det -= std::log((double)v[i]); v[i] = (float)(1.0 / (v[i] * 2.0)); }
+            det -= std::log(2.0 * M_PI) * veclen[sv];
+            lrd[(size_t)sv * size + r] = (float)(det * 0.5);
+            for (int i = 0; i < veclen[sv]; ++i) var[off_par[sv] + (size_t)r * veclen[sv] + i] = (double)v[i];
+        }
+    // compact + linearise, in the device layout [s][cpt][n_sv]
+    std::vector<int32_t> dmap((size_t)R * m->cpt * n_sv, -1);
+    for (int r = 0; r < R; ++r) {
+        int c2 = 0;
+        for (int c = 0; c < Cc; ++c) {
+            const int32_t *src = &map[((size_t)r * Cc + c) * n_sv_file];
+            if (src[0] < 0) {
+                for (int sv = 1; sv < n_sv; ++sv) if (src[sv] >= 0) { set_error("Partially undefined map[%d][%d]", r, c); return B200_ERR_ARG; }
+                continue;
+            }
+            for (int sv = 0; sv < n_sv; ++sv) {
+                if (src[sv] < 0) { set_error("Partially undefined map[%d][%d]", r, c); return B200_ERR_ARG; }
+                dmap[((size_t)r * m->cpt + c2) * n_sv + sv] = sv * size + src[sv];
+            }
+            ++c2;
+        }
+        if (c2 != m->h_ncomp[r]) { set_error("Mixture %d: #Valid components conflict: %d (SubVQ) vs %d (Original)", r, c2, m->h_ncomp[r]); return B200_ERR_ARG; }
+    }
+    std::vector<int32_t> ints;
+    ints.insert(ints.end(), veclen.begin(), veclen.begin() + n_sv);
+    ints.insert(ints.end(), off_dim.begin(), off_dim.begin() + n_sv);
+    ints.insert(ints.end(), off_par.begin(), off_par.begin() + n_sv);
+    ints.insert(ints.end(), featdim.begin(), featdim.begin() + off_dim[n_sv]);
+    std::vector<float> flt(mean.begin(), mean.begin() + off_par[n_sv]);
+    flt.insert(flt.end(), lrd.begin(), lrd.begin() + (size_t)n_sv * size);
+    auto up = [&](void **dst, const void *src, size_t bytes) {
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!(up((void **)&m->d_svq_map, dmap.data(), dmap.size() * 4) && up((void **)&m->d_svq_i, ints.data(), ints.size() * 4) &&
+          up((void **)&m->d_svq_f, flt.data(), flt.size() * 4) && up((void **)&m->d_svq_var, var.data(), var.size() * 8))) {
+        set_error("sub-VQ upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return B200_ERR_CUDA;
+    }
+    m->svq_n_sv = n_sv; m->svq_size = size; m->svq_eval = std::min(n_sv, vqeval);
+    m->svq_beam = subvqbeam <= 0.0 ? kS3Zero : m->lm->log(subvqbeam);
+    S3Vq &q = m->vq;
+    q.n_sv = n_sv; q.size = size; q.n_eval = m->svq_eval;
+    q.veclen = m->d_svq_i; q.off_dim = m->d_svq_i + n_sv; q.off_par = m->d_svq_i + 2 * n_sv; q.featdim = m->d_svq_i + 3 * n_sv;
+    q.mean = m->d_svq_f; q.lrd = m->d_svq_f + off_par[n_sv]; q.var = m->d_svq_var;
+    q.distfloor = m->distfloor; q.f = m->f;
     return B200_OK;
 }
 

@@ -682,6 +682,11 @@ class S3Mgau:
         lib.b200_s3_dims(self.h, d)
         self.ci_pbeam = int(d[4])
 
+    def set_subvq(self, path, varfloor=1e-4, max_sv=-1, vqeval=3, subvqbeam=1e-3):
+        """-subvq / -svmax / -vqeval / -subvqbeam (S3/libam/subvq.c); path None removes the layer."""
+        check(lib.b200_s3_set_subvq(self.h, None if path is None else path.encode(), varfloor, max_sv, vqeval, subvqbeam),
+              "s3_set_subvq")
+
     def utt_reset(self):
         check(lib.b200_s3_utt_reset(self.h), "s3_utt_reset")
 

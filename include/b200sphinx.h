@@ -434,6 +434,15 @@ int  b200_s3_dims(const b200_s3mgau_t *m, int32_t dims[5]);
  * probability), -maxcdsenpf, -ds, -tighten_factor. */
 int  b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio,
                       float tighten_factor);
+/* -subvq FILE -svmax N -vqeval N -subvqbeam P: sub-vector quantised Gaussian selection for the approx path --
+ * subvq_init, S3/libam/subvq.c:206-373 (file format, variance floor, vector_maha_precomp, map compaction and
+ * linearisation), subvq_gautbl_eval_logs3 :488-506, subvq_mgau_shortlist :383-468 and approx_mgau_eval's use of
+ * the shortlist incl. its full re-evaluation below S3_LOGPROB_ZERO + 100000 (approx_cont_mgau.c:187-284).  On the
+ * device the shortlist is a mask over the dense component scores.  -svq4svq (quantised scores AS the Gaussian
+ * scores) and the Gaussian selector (-gs, gs.c: no map file in the tree to pin it against) are not implemented.
+ * file == NULL removes the layer.  The model must have been created with the same component layout the file
+ * was made for (the reference's own check: #valid components per mixture). */
+int  b200_s3_set_subvq(b200_s3mgau_t *m, const char *file, double varfloor, int max_sv, int vqeval, double subvqbeam);
 /* per-utterance reset of bstidx / updatetime (S3/libsearch/srch_time_switch_tree.c:484-490) */
 int  b200_s3_utt_reset(b200_s3mgau_t *m);
 /* Host copies of the precomputed parameters in the reference's order, padded

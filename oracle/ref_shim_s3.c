@@ -21,6 +21,8 @@
 #include "ascr.h"
 #include "mdef.h"
 #include "logs3.h"
+#include "subvq.h"
+#include <sphinxbase/cmd_ln.h>
 
 typedef struct {
     logmath_t *lmath;
@@ -30,6 +32,9 @@ typedef struct {
     fast_gmm_t *fg;
     ascr_t a;           /* only senscr / sen_active / rec_sen_active used */
     ptmr_t tm;
+    subvq_t *svq;       /* -subvq: sub-vector quantised shortlists (S3/libam/subvq.c), or NULL */
+    double svqbeam;     /* -subvqbeam (probability) */
+    cmd_ln_t *config;   /* carries -vqeval for subvq_init */
 } s3h_t;
 
 void *
@@ -52,7 +57,8 @@ ref_s3_open(const char *mean, const char *var, const char *mixw, const char *mde
         for (i = 0; i < n_sen; ++i)
             h->mdef->cd2cisen[i] = (s3senid_t)cd2cisen[i];
     }
-    h->fg = fast_gmm_init(1, 0, 0, 1, 0, 1e-80, 1e-80, 0.5f, 100000, h->mdef->n_ci_sen, h->lmath);
+    h->svqbeam = 1e-80;
+    h->fg = fast_gmm_init(1, 0, 0, 1, 0, h->svqbeam, 1e-80, 0.5f, 100000, h->mdef->n_ci_sen, h->lmath);
     h->a.senscr = ckd_calloc(h->g->n_mgau, sizeof(int32));
     h->a.sen_active = ckd_calloc(h->g->n_mgau, 1);
     h->a.rec_sen_active = ckd_calloc(h->g->n_mgau, 1);
@@ -66,7 +72,90 @@ ref_s3_set_fast(void *vh, double ci_pbeam, int max_cd, int ds_ratio, float tight
     s3h_t *h = vh;
     int n_ci = h->mdef->n_ci_sen;
     fast_gmm_free(h->fg);
-    h->fg = fast_gmm_init(ds_ratio, 0, 0, 1, 0, 1e-80, ci_pbeam, tighten, max_cd, n_ci, h->lmath);
+    h->fg = fast_gmm_init(ds_ratio, 0, 0, 1, 0, h->svqbeam, ci_pbeam, tighten, max_cd, n_ci, h->lmath);
+}
+
+/* -subvq FILE -subvqbeam P -vqeval N: the reference's own subvq_init (subvq.c:206-373).
+ * Call before ref_s3_set_fast (which carries the beam into fast_gmm_init).  0 on success. */
+int
+ref_s3_open_svq(void *vh, const char *file, double varfloor, int max_sv, int vqeval, double subvqbeam)
+{
+    static const arg_t defs[] = {
+        { "-vqeval", ARG_INT32, "3", "sub-vectors used for the shortlist" },
+        { NULL, 0, NULL, NULL }
+    };
+    s3h_t *h = vh;
+    char buf[16];
+    snprintf(buf, sizeof buf, "%d", vqeval);
+    h->config = cmd_ln_init(NULL, defs, FALSE, "-vqeval", buf, NULL);
+    h->svq = subvq_init(file, varfloor, max_sv, h->g, h->config, h->lmath);
+    h->svqbeam = subvqbeam;
+    return h->svq ? 0 : -1;
+}
+
+/* d[0..4] = n_sv, vqsize, origsize.r, origsize.c, VQ_EVAL; d[5] = logs3(subvqbeam) as fast_gmm_init stores it */
+void
+ref_s3_svq_dims(void *vh, int32 *d)
+{
+    s3h_t *h = vh;
+    d[0] = h->svq->n_sv; d[1] = h->svq->vqsize; d[2] = h->svq->origsize.r; d[3] = h->svq->origsize.c;
+    d[4] = h->svq->VQ_EVAL; d[5] = h->fg->gaus->subvqbeam;
+}
+
+/* precomputed tables of sub-vector sv: featdim[veclen], mean / var [vqsize][veclen] (var = 1/(2 var)), lrd[vqsize];
+ * returns veclen; scal[0] = distfloor */
+int
+ref_s3_svq_tables(void *vh, int sv, int32 *featdim, float *mean, float *var, float *lrd, double *scal)
+{
+    s3h_t *h = vh;
+    vector_gautbl_t *t = &h->svq->gautbl[sv];
+    int r, L = t->veclen;
+    for (r = 0; r < L; ++r) featdim[r] = h->svq->featdim[sv][r];
+    for (r = 0; r < h->svq->vqsize; ++r) {
+        memcpy(mean + (size_t)r * L, t->mean[r], L * sizeof(float));
+        memcpy(var + (size_t)r * L, t->var[r], L * sizeof(float));
+        lrd[r] = t->lrd[r];
+    }
+    scal[0] = t->distfloor;
+    return L;
+}
+
+/* the compacted, linearised map [origsize.r][origsize.c][n_sv] */
+void
+ref_s3_svq_map(void *vh, int32 *out)
+{
+    s3h_t *h = vh;
+    subvq_t *v = h->svq;
+    int r, c, s;
+    for (r = 0; r < v->origsize.r; ++r)
+        for (c = 0; c < v->origsize.c; ++c)
+            for (s = 0; s < v->n_sv; ++s)
+                out[((size_t)r * v->origsize.c + c) * v->n_sv + s] = v->map[r][c][s];
+}
+
+/* subvq_gautbl_eval_logs3 for T frames: out [T][n_sv * vqsize] */
+void
+ref_s3_svq_vqdist(void *vh, const float *feat, int T, int32 *out)
+{
+    s3h_t *h = vh;
+    subvq_t *v = h->svq;
+    int t, n = v->n_sv * v->vqsize, L = h->g->veclen;
+    for (t = 0; t < T; ++t) {
+        subvq_gautbl_eval_logs3(v, (float32 *)feat + (size_t)t * L, h->lmath);
+        memcpy(out + (size_t)t * n, v->vqdist[0], n * sizeof(int32));
+    }
+}
+
+/* subvq_mgau_shortlist for one senone against the vqdist of the last evaluated frame: out[0..n) flags */
+int
+ref_s3_svq_shortlist(void *vh, int s, uint8 *out)
+{
+    s3h_t *h = vh;
+    int i, n = mgau_n_comp(h->g, s);
+    int ng = subvq_mgau_shortlist(h->svq, s, n, h->fg->gaus->subvqbeam);
+    memset(out, 0, n);
+    for (i = 0; h->svq->mgau_sl[i] >= 0; ++i) out[h->svq->mgau_sl[i]] = 1;
+    return ng;
 }
 
 void
@@ -154,8 +243,8 @@ ref_s3_eval_utt(void *vh, const float *feat, int T, int frame0, uint8 *sen_activ
         float32 *x = (float32 *)feat + (size_t)t * L;
         if (sen_active) memcpy(h->a.sen_active, sen_active + (size_t)t * S, S);
         else memset(h->a.sen_active, 1, S);
-        approx_cont_mgau_ci_eval(NULL, NULL, h->g, h->fg, h->mdef, x, ci, &cib, frame0 + t, h->lmath);
-        best[t] = approx_cont_mgau_frame_eval(h->mdef, NULL, NULL, h->g, h->fg, &h->a, x, frame0 + t,
+        approx_cont_mgau_ci_eval(h->svq, NULL, h->g, h->fg, h->mdef, x, ci, &cib, frame0 + t, h->lmath);
+        best[t] = approx_cont_mgau_frame_eval(h->mdef, h->svq, NULL, h->g, h->fg, &h->a, x, frame0 + t,
                                               ci, &h->tm, h->lmath);
         memcpy(out + (size_t)t * S, h->a.senscr, S * sizeof(int32));
         if (sen_active) memcpy(sen_active + (size_t)t * S, h->a.sen_active, S);
@@ -170,6 +259,8 @@ ref_s3_close(void *vh)
     s3h_t *h = vh;
     if (!h) return;
     fast_gmm_free(h->fg);
+    if (h->svq) subvq_free(h->svq);
+    if (h->config) cmd_ln_free_r(h->config);
     mgau_free(h->g);
     if (h->own_mdef) { ckd_free(h->mdef->cd2cisen); ckd_free(h->mdef); }
     else mdef_free(h->mdef);

@@ -934,6 +934,15 @@ struct orc_s3_model {
     int32_t *bstidx, *bstscr, *updatetime;
     int32_t *ci_occ, *idx;
     int64_t n_sen_eval, n_gau_eval;
+    /* sub-vector quantised shortlists (S3/libam/subvq.c), optional */
+    int svq_n_sv, svq_size, svq_eval;        /* #sub-vectors, codewords per sub-vector, VQ_EVAL */
+    int *svq_veclen, **svq_featdim;          /* [n_sv], [n_sv][veclen] */
+    float **svq_mean, **svq_var, **svq_lrd;  /* [n_sv] -> [size][veclen], [size][veclen] (1/(2 var)), [size] */
+    double svq_distfloor;
+    int32_t *svq_map;                        /* [n_sen][max_comp][n_sv] compacted + linearised, -1 = none */
+    int32_t *svq_dist;                       /* [n_sv * size] scores of the current frame */
+    int32_t svq_beam;
+    int32_t *svq_sl;                         /* [max_comp + 1] */
 };
 
 /* S3/libcommon/vector.c:181-204 */
@@ -1018,6 +1027,12 @@ orc_s3_new(int n_sen, int n_comp, int veclen, const float *mean, const float *va
 void
 orc_s3_free(orc_s3_model_t *m)
 {
+    if (m && m->svq_n_sv) {
+        int k;
+        for (k = 0; k < m->svq_n_sv; ++k) { free(m->svq_featdim[k]); free(m->svq_mean[k]); free(m->svq_var[k]); free(m->svq_lrd[k]); }
+        free(m->svq_veclen); free(m->svq_featdim); free(m->svq_mean); free(m->svq_var); free(m->svq_lrd);
+        free(m->svq_map); free(m->svq_dist); free(m->svq_sl);
+    }
     if (!m) return;
     free(m->n_comp); free(m->mean); free(m->var); free(m->lrd); free(m->mixw); free(m->cd2cisen);
     free(m->bstidx); free(m->bstscr); free(m->updatetime); free(m->ci_occ); free(m->idx);
@@ -1118,12 +1133,153 @@ orc_s3_mgau_eval(orc_s3_model_t *m, int s, const int32_t *active, const float *x
     return score;
 }
 
-/* approx_cont_mgau_ci_eval (S3/libam/approx_cont_mgau.c:368-431), no GS/SVQ */
+/* ---- sub-vector quantised Gaussian selection (S3/libam/subvq.c) ----
+ * orc_s3_set_svq = what subvq_init (:206-373) does after reading the file: variance floor +
+ * vector_maha_precomp per codeword (subvq_maha_precomp :106-123, S3/libcommon/vector.c:127-134,
+ * 327-339), map compaction (:127-181: entries < 0 mark unused components, the remaining ones move
+ * up) and linearisation (:191-203: index = sub-vector * vqsize + codeword).  The caller passes
+ * the file's contents: veclen[n_sv], featdim (concatenated), mean / var (concatenated
+ * [size][veclen] blocks, raw variances), map [n_sen][max_comp][n_sv_file] as in the file.
+ * n_sv_use = min(-svmax, n_sv_file) sub-vectors are kept (:228-243). */
+int
+orc_s3_set_svq(orc_s3_model_t *m, int n_sv_file, int n_sv_use, int vqsize, int vqeval, const int32_t *veclen,
+               const int32_t *featdim, const float *mean, const float *var, const int32_t *map, double varfloor,
+               double subvqbeam)
+{
+    int sv, r, c, c2, i, off_d = 0;
+    size_t off_p = 0;
+    if (n_sv_use < 0 || n_sv_use > n_sv_file) n_sv_use = n_sv_file;
+    m->svq_n_sv = n_sv_use; m->svq_size = vqsize;
+    m->svq_eval = n_sv_use < vqeval ? n_sv_use : vqeval;                 /* :240-241 */
+    m->svq_veclen = calloc(n_sv_use, sizeof(int)); m->svq_featdim = calloc(n_sv_use, sizeof(int *));
+    m->svq_mean = calloc(n_sv_use, sizeof(float *)); m->svq_var = calloc(n_sv_use, sizeof(float *));
+    m->svq_lrd = calloc(n_sv_use, sizeof(float *));
+    m->svq_distfloor = m->distfloor;                                    /* logmath_log_to_ln(S3_LOGPROB_ZERO), vector.c:549: the same value as mgau_init's */
+    for (sv = 0; sv < n_sv_file; ++sv) {
+        const int L = veclen[sv];
+        if (sv < n_sv_use) {
+            m->svq_veclen[sv] = L;
+            m->svq_featdim[sv] = malloc(sizeof(int) * L);
+            for (i = 0; i < L; ++i) m->svq_featdim[sv][i] = featdim[off_d + i];
+            m->svq_mean[sv] = malloc(sizeof(float) * vqsize * L);
+            m->svq_var[sv] = malloc(sizeof(float) * vqsize * L);
+            m->svq_lrd[sv] = malloc(sizeof(float) * vqsize);
+            memcpy(m->svq_mean[sv], mean + off_p, sizeof(float) * vqsize * L);
+            memcpy(m->svq_var[sv], var + off_p, sizeof(float) * vqsize * L);
+            for (r = 0; r < vqsize; ++r) {
+                float *v = m->svq_var[sv] + (size_t)r * L;
+                double det = 0.0;
+                for (i = 0; i < L; ++i) if (v[i] < varfloor) v[i] = (float)varfloor;
+                for (i = 0; i < L; ++i) { det -= (double)log(v[i]); v[i] = (float)(1.0 / (v[i] * 2.0)); }
+                det -= log(2.0 * M_PI) * L;
+                m->svq_lrd[sv][r] = (float)(det * 0.5);
+            }
+        }
+        off_d += L; off_p += (size_t)vqsize * L;
+    }
+    m->svq_map = malloc(sizeof(int32_t) * m->n_sen * m->max_comp * n_sv_use);
+    for (r = 0; r < m->n_sen; ++r) {
+        int32_t *dst = m->svq_map + (size_t)r * m->max_comp * n_sv_use;
+        const int32_t *src = map + (size_t)r * m->max_comp * n_sv_file;
+        for (c = 0, c2 = 0; c < m->max_comp; ++c) {
+            if (src[(size_t)c * n_sv_file] < 0) continue;
+            for (sv = 0; sv < n_sv_use; ++sv) dst[(size_t)c2 * n_sv_use + sv] = sv * vqsize + src[(size_t)c * n_sv_file + sv];
+            c2++;
+        }
+        if (c2 != m->n_comp[r]) return -1;                               /* :174-177 */
+        for (; c2 < m->max_comp; ++c2) for (sv = 0; sv < n_sv_use; ++sv) dst[(size_t)c2 * n_sv_use + sv] = -1;
+    }
+    m->svq_dist = calloc((size_t)n_sv_use * vqsize, sizeof(int32_t));    /* unevaluated sub-vectors stay 0 (ckd_calloc_2d, :366) */
+    m->svq_sl = malloc(sizeof(int32_t) * (m->max_comp + 1));
+    m->svq_beam = subvqbeam <= 0.0 ? S3_ZERO : orc_logmath_log(m->lmath, subvqbeam);   /* logs3(), fast_algo_struct.c:454 */
+    return 0;
+}
+
+void
+orc_s3_svq_tables(const orc_s3_model_t *m, int sv, float *mean, float *var, float *lrd, double *scal)
+{
+    const int L = m->svq_veclen[sv];
+    memcpy(mean, m->svq_mean[sv], sizeof(float) * m->svq_size * L);
+    memcpy(var, m->svq_var[sv], sizeof(float) * m->svq_size * L);
+    memcpy(lrd, m->svq_lrd[sv], sizeof(float) * m->svq_size);
+    scal[0] = m->svq_distfloor;
+}
+void orc_s3_svq_map(const orc_s3_model_t *m, int32_t *out) { memcpy(out, m->svq_map, sizeof(int32_t) * m->n_sen * m->max_comp * m->svq_n_sv); }
+int32_t orc_s3_svq_beam(const orc_s3_model_t *m) { return m->svq_beam; }
+
+/* subvq_gautbl_eval_logs3 (subvq.c:488-506) + vector_gautbl_eval_logs3 (vector.c:590-650): only the
+ * first VQ_EVAL sub-vectors are evaluated */
+void
+orc_s3_svq_eval(orc_s3_model_t *m, const float *x)
+{
+    int sv, r, i;
+    for (sv = 0; sv < m->svq_n_sv && sv < m->svq_eval; ++sv) {
+        const int L = m->svq_veclen[sv];
+        for (r = 0; r < m->svq_size; ++r) {
+            const float *mu = m->svq_mean[sv] + (size_t)r * L, *va = m->svq_var[sv] + (size_t)r * L;
+            double dval = m->svq_lrd[sv][r], diff;
+            for (i = 0; i < L; ++i) {
+                diff = x[m->svq_featdim[sv][i]] - mu[i];      /* float32 subtraction, then widened */
+                dval -= diff * diff * va[i];
+            }
+            if (dval < m->svq_distfloor) dval = m->svq_distfloor;
+            m->svq_dist[sv * m->svq_size + r] = (int32_t)(m->f * dval);
+        }
+    }
+}
+void orc_s3_svq_dist(const orc_s3_model_t *m, int32_t *out) { memcpy(out, m->svq_dist, sizeof(int32_t) * m->svq_n_sv * m->svq_size); }
+
+/* subvq_mgau_shortlist (subvq.c:383-468); returns the shortlist length, list in m->svq_sl */
+int
+orc_s3_svq_shortlist(orc_s3_model_t *m, int s)
+{
+    const int n = m->n_comp[s], nsv = m->svq_n_sv;
+    const int32_t *map = m->svq_map + (size_t)s * m->max_comp * nsv, *vq = m->svq_dist;
+    int32_t gs[256], v, bv = INT_MIN, th;
+    int i, k, nc = 0;
+    for (i = 0; i < n; ++i, map += nsv) {
+        if (nsv == 3) {
+            if (m->svq_eval == 1) v = vq[map[0]];
+            else if (m->svq_eval == 2) v = vq[map[0]] + 2 * vq[map[1]];
+            else v = vq[map[0]] + vq[map[1]] + vq[map[2]];
+        } else {
+            for (v = 0, k = 0; k < nsv; ++k) v += vq[map[k]];
+        }
+        gs[i] = v;
+        if (bv < v) bv = v;
+    }
+    th = bv + m->svq_beam;
+    for (i = 0; i < n; ++i) if (gs[i] >= th) m->svq_sl[nc++] = i;
+    m->svq_sl[nc] = -1;
+    return nc;
+}
+
+/* approx_mgau_eval (approx_cont_mgau.c:187-284) without a Gaussian selector and with svq4svq off */
+static int
+s3_approx_mgau_eval(orc_s3_model_t *m, int s, int32_t *senscr, const float *x, int fr)
+{
+    const int32_t *sl = NULL;
+    int ng = m->n_comp[s];
+    if (m->svq_n_sv) {
+        ng = orc_s3_svq_shortlist(m, s);
+        sl = m->svq_sl;
+        if (ng == 0) { sl = NULL; ng = m->n_comp[s]; }
+    }
+    senscr[s] = orc_s3_mgau_eval(m, s, sl, x, fr, 1);
+    if (senscr[s] < S3_ZERO + 100000 && sl) {            /* :256-281: recompute with every component */
+        ng += m->n_comp[s];
+        senscr[s] = orc_s3_mgau_eval(m, s, NULL, x, fr, 1);
+    }
+    return ng;
+}
+
+/* approx_cont_mgau_ci_eval (S3/libam/approx_cont_mgau.c:368-431), no Gaussian selector */
 void
 orc_s3_ci_eval(orc_s3_model_t *m, const float *x, int32_t *ci_senscr, int32_t *best, int fr)
 {
     int s;
-    for (s = 0; s < m->n_ci_sen; ++s) ci_senscr[s] = orc_s3_mgau_eval(m, s, NULL, x, fr, 1);
+    if (m->svq_n_sv) orc_s3_svq_eval(m, x);
+    for (s = 0; s < m->n_ci_sen; ++s) s3_approx_mgau_eval(m, s, ci_senscr, x, fr);
     *best = INT_MIN;
     for (s = 0; s < m->n_ci_sen; ++s) if (ci_senscr[s] > *best) *best = ci_senscr[s];
 }
@@ -1163,6 +1319,7 @@ orc_s3_frame_eval(orc_s3_model_t *m, const float *x, int frame, const int32_t *c
     int32_t best = INT_MIN, pbest = INT_MIN, dyn, single[2] = { -1, -1 };
     int s, is_skip;
     int64_t ns = 0, ng = 0;
+    if (m->svq_n_sv) orc_s3_svq_eval(m, x);
     if (m->max_cd < m->n_sen - m->n_ci_sen) dyn = s3_dyn_beam(m, sen_active, cache_ci_senscr);
     else dyn = m->ci_pbeam;
     is_skip = (frame % m->ds_ratio) != 0;
@@ -1175,8 +1332,8 @@ orc_s3_frame_eval(orc_s3_model_t *m, const float *x, int frame, const int32_t *c
             sen_active[s] = 1;
         } else if (sen_active[s]) {
             if (senscr[m->cd2cisen[s]] >= pbest + dyn) {
-                senscr[s] = orc_s3_mgau_eval(m, s, NULL, x, frame, 1);
-                ng += m->n_comp[s]; ns++;
+                ng += s3_approx_mgau_eval(m, s, senscr, x, frame);
+                ns++;
             } else if (m->bstidx[s] == S3_NO_BSTIDX || m->updatetime[s] != frame - 1) {
                 senscr[s] = senscr[m->cd2cisen[s]];
             } else {

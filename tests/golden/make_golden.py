@@ -212,6 +212,42 @@ def s3_case(name="s3_synth.npz", T=40):
     r.free()
 
 
+S3_SVQ_CFGS = [   # (n_sv, vqeval, subvqbeam, fast-GMM settings)
+    (3, 3, 1e-3, dict()),
+    (3, 2, 1e-2, dict(ci_pbeam=1e-40, max_cd=60)),
+    (1, 3, 1e-3, dict(ci_pbeam=1e-30, ds_ratio=3)),
+]
+
+
+def s3_svq_case(name="s3_svq.npz", T=30):
+    """sphinx3 sub-vector quantised shortlists: the reference's subvq_init / subvq_gautbl_eval_logs3 /
+    approx_cont_mgau_frame_eval(svq) on the synthetic model of s3_case with the synthetic sub-VQ
+    models of orc.synthetic_subvq (the .subvq text is regenerated from the seeds by the test)."""
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=160, n_ci_sen=16)
+    D = mean.shape[2]
+    feat = synth.s3_features(mean, var, T)
+    act = synth.s3_active(mean.shape[0], n_ci, T)
+    valid = ~np.all(var == 0, axis=2)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        mf, vf, wf = (os.path.join(d, n) for n in ("means", "variances", "mixture_weights"))
+        s3io.write_gauden(mf, mean, [D]); s3io.write_gauden(vf, var, [D]); s3io.write_mixw(wf, mixw[:, None, :])
+        for i, (n_sv, vqeval, beam, cfg) in enumerate(S3_SVQ_CFGS):
+            q = orc.synthetic_subvq(mean, var, valid, n_sv, 16)
+            path = os.path.join(d, "m%d.subvq" % i)
+            orc.write_subvq(path, q)
+            r = orc.RefS3(mf, vf, wf, None, cd2ci, n_ci)
+            orc.ref_set_svq(r, path, vqeval=vqeval, subvqbeam=beam)
+            r.set_fast(**cfg); r.utt_reset()
+            vq = np.zeros((T, r.svq_dims[0] * 16), np.int32)
+            orc.ref_s3().ref_s3_svq_vqdist(r.h, orc._p(feat, orc.C.c_float), T, orc._p(vq, orc.C.c_int32))
+            o, best, a = r.eval_utt(feat, act, 1)
+            bi, ut = r.state()
+            out.update({f"vq{i}": vq, f"scr{i}": o, f"best{i}": best, f"act{i}": a, f"bstidx{i}": bi, f"upd{i}": ut})
+            r.free()
+    save(name, n_sen=160, n_ci=n_ci, feat=feat, act=act, frame0=1, **out)
+
+
 def semi_beam():
     """s2_semi with -topn_beam (mgau_norm's list cut, s2_semi_mgau.c:189-207): the reference's
     dense scores on the frames of semi_hub4wsj.npz for two beam settings."""
@@ -276,3 +312,4 @@ if __name__ == "__main__":
     real_model("cont_hub4_topn4.npz", "cont", "pittsburgh.littleendian.mfc", 20, ".cont.", 4)
     real_model("cont_hub4_topn8.npz", "cont", "pittsburgh.littleendian.mfc", 12, ".cont.", 8)
     s3_case()
+    s3_svq_case()

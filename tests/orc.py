@@ -477,6 +477,118 @@ class RefS3(_S3Common):
         ref_s3().ref_s3_close(self.h)
 
 
+# ------------------------------------------------------- sphinx3 sub-vector quantised shortlists
+port.orc_s3_set_svq.restype = C.c_int
+port.orc_s3_set_svq.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, f32p, f32p, i32p, C.c_double, C.c_double]
+port.orc_s3_svq_tables.argtypes = [vp, C.c_int, f32p, f32p, f32p, f64p]
+port.orc_s3_svq_map.argtypes = [vp, i32p]
+port.orc_s3_svq_beam.restype = C.c_int32
+port.orc_s3_svq_beam.argtypes = [vp]
+port.orc_s3_svq_eval.argtypes = [vp, f32p]
+port.orc_s3_svq_dist.argtypes = [vp, i32p]
+port.orc_s3_svq_shortlist.restype = C.c_int
+port.orc_s3_svq_shortlist.argtypes = [vp, C.c_int]
+
+
+def read_subvq(path):
+    """Independent reader of the text format subvq_init parses (S3/libam/subvq.c:206-340):
+    -> dict(r, c, n_sv, vqsize, veclen [n_sv], featdim [list of arrays], mean / var [list of [vqsize][veclen]],
+    map [r][c][n_sv] int32 (entries < 0 = component not present))."""
+    lines = open(path).read().split("\n")
+    i = 0
+    while not lines[i].startswith("VQParam"):
+        i += 1
+    t = lines[i].split()
+    r, c, n_sv, vqsize = int(t[1]), int(t[2]), int(t[4]), int(t[5])
+    i += 1
+    veclen, featdim = [], []
+    for s in range(n_sv):
+        t = lines[i].split(); i += 1
+        assert t[0] == "Subvector" and int(t[1]) == s
+        L = int(t[3]); veclen.append(L); featdim.append(np.array([int(x) for x in t[4:4 + L]], np.int32))
+    mean, var = [], []
+    mp = np.zeros((r, c, n_sv), np.int32)
+    for s in range(n_sv):
+        assert lines[i].split()[:2] == ["Codebook", str(s)]; i += 1
+        mv = np.array([[float(x) for x in lines[i + k].split()] for k in range(vqsize)], np.float64); i += vqsize
+        mean.append(np.ascontiguousarray(mv[:, 0::2], np.float32)); var.append(np.ascontiguousarray(mv[:, 1::2], np.float32))
+        assert lines[i].split()[:2] == ["Map", str(s)]; i += 1
+        for k in range(r):
+            mp[k, :, s] = [int(x) for x in lines[i + k].split()]
+        i += r
+    assert lines[i].strip() == "End"
+    return dict(r=r, c=c, n_sv=n_sv, vqsize=vqsize, veclen=np.array(veclen, np.int32), featdim=featdim, mean=mean, var=var, map=mp)
+
+
+def write_subvq(path, q):
+    """The same format from arrays (synthetic sub-VQ models for the tests)."""
+    with open(path, "w") as f:
+        f.write("VQParam %d %d -> %d %d\n" % (q["r"], q["c"], q["n_sv"], q["vqsize"]))
+        for s in range(q["n_sv"]):
+            f.write("Subvector %d length %d " % (s, q["veclen"][s]) + " ".join("%2d" % d for d in q["featdim"][s]) + "\n")
+        for s in range(q["n_sv"]):
+            f.write("Codebook %d Sqerr 0.0\n" % s)
+            for k in range(q["vqsize"]):
+                f.write(" ".join("%.8e %.8e" % (q["mean"][s][k, i], q["var"][s][k, i]) for i in range(q["veclen"][s])) + "\n")
+            f.write("Map %d\n" % s)
+            for k in range(q["r"]):
+                f.write(" ".join("%d" % v for v in q["map"][k, :, s]) + "\n")
+        f.write("End\n")
+
+
+def synthetic_subvq(mean, var, n_comp_valid, n_sv, vqsize, seed=5):
+    """A sub-VQ model for a synthetic acoustic model: sub-vectors = contiguous slices of the
+    feature vector, codewords = randomly chosen (mean, variance) sub-vectors of the model's own
+    Gaussians, map = nearest codeword by Euclidean distance of the means; components the
+    acoustic model drops (mgau_uninit_compact) are marked -1 as gausubvq writes them."""
+    rng = np.random.default_rng(seed)
+    S, M, D = mean.shape
+    edges = np.linspace(0, D, n_sv + 1).astype(int)
+    q = dict(r=S, c=M, n_sv=n_sv, vqsize=vqsize, veclen=np.diff(edges).astype(np.int32), featdim=[], mean=[], var=[],
+             map=np.zeros((S, M, n_sv), np.int32))
+    flat_m, flat_v = mean.reshape(S * M, D), var.reshape(S * M, D)
+    for s in range(n_sv):
+        dims = np.arange(edges[s], edges[s + 1], dtype=np.int32)
+        pick = rng.choice(np.flatnonzero(n_comp_valid.ravel()), vqsize, replace=False)
+        cm, cv = flat_m[pick][:, dims].copy(), np.maximum(flat_v[pick][:, dims], 1e-3).copy()
+        q["featdim"].append(dims); q["mean"].append(cm.astype(np.float32)); q["var"].append(cv.astype(np.float32))
+        d2 = ((flat_m[:, None, dims] - cm[None]) ** 2).sum(-1)
+        q["map"][:, :, s] = d2.argmin(1).reshape(S, M)
+    q["map"][~n_comp_valid] = -1
+    return q
+
+
+def port_set_svq(p3, q, varfloor=1e-4, max_sv=-1, vqeval=3, subvqbeam=1e-3):
+    """Attach the sub-VQ model `q` (read_subvq) to a PortS3."""
+    veclen = _c(q["veclen"], np.int32)
+    fd = _c(np.concatenate(q["featdim"]), np.int32)
+    mean = _c(np.concatenate([m.ravel() for m in q["mean"]]), np.float32)
+    var = _c(np.concatenate([v.ravel() for v in q["var"]]), np.float32)
+    mp = _c(q["map"], np.int32)
+    rc = port.orc_s3_set_svq(p3.h, q["n_sv"], max_sv, q["vqsize"], vqeval, _p(veclen, C.c_int32), _p(fd, C.c_int32),
+                             _p(mean, C.c_float), _p(var, C.c_float), _p(mp, C.c_int32), varfloor, subvqbeam)
+    assert rc == 0, "sub-VQ map does not match the model's components"
+    p3.svq = q
+    p3.n_sv_use = q["n_sv"] if max_sv < 0 else min(max_sv, q["n_sv"])
+
+
+def ref_set_svq(r3, path, varfloor=1e-4, max_sv=-1, vqeval=3, subvqbeam=1e-3):
+    L = ref_s3()
+    L.ref_s3_open_svq.restype = C.c_int
+    L.ref_s3_open_svq.argtypes = [vp, C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double]
+    L.ref_s3_svq_dims.argtypes = [vp, i32p]
+    L.ref_s3_svq_tables.restype = C.c_int
+    L.ref_s3_svq_tables.argtypes = [vp, C.c_int, i32p, f32p, f32p, f32p, f64p]
+    L.ref_s3_svq_map.argtypes = [vp, i32p]
+    L.ref_s3_svq_vqdist.argtypes = [vp, f32p, C.c_int, i32p]
+    L.ref_s3_svq_shortlist.restype = C.c_int
+    L.ref_s3_svq_shortlist.argtypes = [vp, C.c_int, u8p]
+    assert L.ref_s3_open_svq(r3.h, path.encode(), varfloor, max_sv, vqeval, subvqbeam) == 0
+    d = np.zeros(6, np.int32)
+    L.ref_s3_svq_dims(r3.h, _p(d, C.c_int32))
+    r3.svq_dims = [int(v) for v in d]       # n_sv, vqsize, r, c, VQ_EVAL, (beam valid after set_fast)
+
+
 # ------------------------------------------------------- sphinx3 hmm_vit_eval
 port.orc_s3hmm_eval_batch.restype = C.c_int32
 port.orc_s3hmm_eval_batch.argtypes = [C.c_int, C.c_int, i32p, C.c_int, i16p, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p,

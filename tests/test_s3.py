@@ -210,3 +210,127 @@ def test_s3_gpu_fuzz_against_oracle():
         np.testing.assert_array_equal(c[0], a[0], err_msg=f"seed {seed} {cfg}")
         np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()), err_msg=f"seed {seed}")
         p.free(); m.free()
+
+
+# ---------------------------------------------------------------- sub-vector quantised shortlists (S3/libam/subvq.c)
+SVQ_GOLDEN_CFGS = [(3, 3, 1e-3, dict()), (3, 2, 1e-2, dict(ci_pbeam=1e-40, max_cd=60)), (1, 3, 1e-3, dict(ci_pbeam=1e-30, ds_ratio=3))]
+
+
+def _svq_golden_model(tmp_path, i):
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=160, n_ci_sen=16)
+    n_sv, vqeval, beam, cfg = SVQ_GOLDEN_CFGS[i]
+    q = orc.synthetic_subvq(mean, var, ~np.all(var == 0, axis=2), n_sv, 16)
+    path = str(tmp_path / ("m%d.subvq" % i))
+    orc.write_subvq(path, q)
+    return mean, var, mixw, cd2ci, n_ci, path, vqeval, beam, cfg
+
+
+@pytest.mark.parametrize("i", range(len(SVQ_GOLDEN_CFGS)))
+def test_s3_subvq_port_matches_golden(tmp_path, i):
+    """The port's sub-VQ layer against outputs of the reference itself (tests/golden/s3_svq.npz,
+    make_golden.py:s3_svq_case) -- holds where /root/reference is absent."""
+    g = cases.load("s3_svq.npz")
+    mean, var, mixw, cd2ci, n_ci, path, vqeval, beam, cfg = _svq_golden_model(tmp_path, i)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    orc.port_set_svq(p, orc.read_subvq(path), vqeval=vqeval, subvqbeam=beam)
+    p.set_fast(**cfg); p.utt_reset()
+    vq = np.zeros_like(g[f"vq{i}"])
+    for t in range(g["feat"].shape[0]):
+        row = np.ascontiguousarray(g["feat"][t])
+        orc.port.orc_s3_svq_eval(p.h, orc._p(row, orc.C.c_float))
+        orc.port.orc_s3_svq_dist(p.h, orc._p(vq[t], orc.C.c_int32))
+    np.testing.assert_array_equal(vq, g[f"vq{i}"])
+    o, best, a = p.eval_utt(g["feat"], g["act"], int(g["frame0"]))
+    np.testing.assert_array_equal(best, g[f"best{i}"]); np.testing.assert_array_equal(o, g[f"scr{i}"])
+    np.testing.assert_array_equal(a, g[f"act{i}"])
+    bi, ut = p.state()
+    np.testing.assert_array_equal(bi, g[f"bstidx{i}"]); np.testing.assert_array_equal(ut, g[f"upd{i}"])
+    p.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(SVQ_GOLDEN_CFGS)))
+def test_s3_subvq_gpu_matches_golden(tmp_path, i):
+    g = cases.load("s3_svq.npz")
+    mean, var, mixw, cd2ci, n_ci, path, vqeval, beam, cfg = _svq_golden_model(tmp_path, i)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    m.set_subvq(path, vqeval=vqeval, subvqbeam=beam)
+    m.set_fast(**cfg); m.utt_reset()
+    o, best, a = m.eval_utt(g["feat"], g["act"], int(g["frame0"]))
+    np.testing.assert_array_equal(best, g[f"best{i}"]); np.testing.assert_array_equal(o, g[f"scr{i}"])
+    np.testing.assert_array_equal(a, g[f"act{i}"])
+    bi, ut = m.state()
+    np.testing.assert_array_equal(bi, g[f"bstidx{i}"]); np.testing.assert_array_equal(ut, g[f"upd{i}"])
+    m.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_sv,vqsize,vqeval,max_sv,beam", [
+    (dict(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=1), 3, 32, 3, -1, 1e-3),
+    (dict(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=1), 3, 32, 2, -1, 1e-1),
+    (dict(n_sen=300, n_ci_sen=21, n_density=5, dim=13, seed=2), 3, 16, 1, -1, 1e-2),
+    (dict(n_sen=200, n_ci_sen=12, n_density=32, dim=39, seed=3), 4, 64, 3, -1, 1e-4),     # generic #sub-vectors
+    (dict(n_sen=150, n_ci_sen=9, n_density=40, dim=25, seed=4), 2, 24, 3, -1, 0.3),        # > 32 components
+    (dict(n_sen=200, n_ci_sen=12, n_density=8, dim=39, seed=6), 3, 16, 3, 2, 1e-3),        # -svmax 2 of 3
+    (dict(n_sen=97, n_ci_sen=7, n_density=1, dim=39, seed=5), 1, 8, 3, -1, 1e-3),
+])
+def test_s3_subvq_gpu_matches_oracle(tmp_path, shape, n_sv, vqsize, vqeval, max_sv, beam):
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(**shape)
+    q = orc.synthetic_subvq(mean, var, ~np.all(var == 0, axis=2), n_sv, vqsize, seed=shape["seed"])
+    path = str(tmp_path / "m.subvq")
+    orc.write_subvq(path, q)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    orc.port_set_svq(p, orc.read_subvq(path), max_sv=max_sv, vqeval=vqeval, subvqbeam=beam)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    m.set_subvq(path, max_sv=max_sv, vqeval=vqeval, subvqbeam=beam)
+    T = 70
+    feat = synth.s3_features(mean, var, T, seed=shape["seed"] + 100)
+    act = synth.s3_active(mean.shape[0], n_ci, T, seed=shape["seed"] + 200)
+    for cfg in (dict(), dict(ci_pbeam=1e-40), dict(ci_pbeam=1e-40, max_cd=max(4, mean.shape[0] // 12)),
+                dict(ci_pbeam=1e-30, ds_ratio=3)):
+        for active in (act, None):
+            p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+            a, c = p.eval_utt(feat, active, 2), m.eval_utt(feat, active, 2)
+            np.testing.assert_array_equal(c[1], a[1], err_msg=str(cfg))
+            np.testing.assert_array_equal(c[0], a[0], err_msg=str(cfg))
+            np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()))
+    # the dense call (mgau_eval on every senone) ignores the layer, and removing it restores the plain scores
+    plain = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    m.set_subvq(None); m.set_fast(); m.utt_reset(); plain.set_fast()
+    np.testing.assert_array_equal(m.eval_utt(feat, act, 0)[0], plain.eval_utt(feat, act, 0)[0])
+    p.free(); m.free(); plain.free()
+
+
+@pytest.mark.gpu
+def test_s3_subvq_gpu_real_model_and_per_frame_binding():
+    """hub4_cd_continuous_8gau_1s_c_d_dd with the tree's own test.subvq; also through the per-frame entry point."""
+    d = os.path.join(orc.DATA_DIR, "hmm", "cont")
+    mf, vf, wf, sv = (os.path.join(d, n) for n in ("means", "variances", "mixture_weights", "test.subvq"))
+    if not os.path.exists(sv):
+        pytest.skip("test.subvq not bundled")
+    mean, var, mixw = b.read_s3_cont_arrays(mf, vf, wf)
+    mm = b.mdef_maps(os.path.join(d, "mdef"))
+    n_ci, cd2ci = mm["n_ci_sen"], mm["cd2cisen"].astype(np.int32)
+    m = b.S3Mgau.from_files(mf, vf, wf, cd2ci, n_ci)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    m.set_subvq(sv, subvqbeam=3e-3); orc.port_set_svq(p, orc.read_subvq(sv), subvqbeam=3e-3)
+    rng = np.random.default_rng(4)
+    T = 24
+    idx = rng.integers(0, mean.shape[0], T)
+    feat = (mean[idx, 0] + rng.standard_normal((T, mean.shape[2])) * np.sqrt(var[idx, 0])).astype(np.float32)
+    act = synth.s3_active(mean.shape[0], n_ci, T, seed=6)
+    for cfg in (dict(), dict(ci_pbeam=1e-40, max_cd=400)):
+        p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+        a, c = p.eval_utt(feat, act), m.eval_utt(feat, act)
+        np.testing.assert_array_equal(c[1], a[1]); np.testing.assert_array_equal(c[0], a[0])
+    p.utt_reset(); m.utt_reset()
+    want, wbest, wact = p.eval_utt(feat, act)
+    senscr = np.zeros(mean.shape[0], np.int32)
+    for t in range(T):
+        a = act[t].copy()
+        assert m.frame_eval(feat[t], t, a, senscr) == wbest[t]
+        np.testing.assert_array_equal(senscr, want[t])
+    with pytest.raises(b.B200Error, match="Model size conflict"):
+        small = b.S3Mgau.from_arrays(*synth.s3_model(n_sen=97, n_ci_sen=7, n_density=1, dim=39, seed=5))
+        small.set_subvq(sv)
+    p.free(); m.free()
