@@ -61,6 +61,9 @@ struct S3Dev {
     // sub-vector quantised shortlists (S3/libam/subvq.c); svq_n_sv == 0: none
     int svq_n_sv, svq_size, svq_eval; int32_t svq_beam;
     const int32_t *svq_map;    // [s][cpt][n_sv] compacted + linearised (sub-vector * size + codeword)
+    // Gaussian selector (S3/libam/gs.c); gs_n_code == 0: none
+    int gs_n_code;
+    const uint32_t *gs_map;    // [s][n_code] bit c = component c is short-listed for that codeword
 };
 
 // logmath_add, SB/util/logmath.c:391-436 (shift 0 table, 16 or 32 bit wide)
@@ -99,7 +102,8 @@ template <int CP, int KC>
 __global__ void __launch_bounds__(kEvalThreads, 8)
 s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_hi,
                const uint8_t *__restrict__ flags, int32_t *__restrict__ raw, int16_t *__restrict__ bst,
-               const int32_t *__restrict__ vqd /* [T][n_sv * size] sub-VQ scores of every frame, or null */) {
+               const int32_t *__restrict__ vqd /* [T][n_sv * size] sub-VQ scores of every frame, or null */,
+               const int32_t *__restrict__ gscw /* [T] closest Gaussian-selector codeword of every frame, or null */) {
     extern __shared__ float xs[];   // [kFB][veclen] | int32 stage[G][kFR][CP*KC]
     constexpr int G = kEvalThreads / CP;
     const int t0 = blockIdx.y * kFB;
@@ -186,8 +190,17 @@ s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_h
                 return (int32_t)v;
             };
             int32_t th = (int32_t)0x80000000;
-            bool shortlist = vq != nullptr;
-            if (shortlist) {
+            // the Gaussian selector goes first (gs4gs): the bit map of (senone, closest codeword), every
+            // component when it is empty (gs_mgau_shortlist, gs.c:263-300)
+            uint32_t gsbits = 0xffffffffu;
+            if (gscw) {
+                gsbits = g.gs_map[(size_t)s * g.gs_n_code + gscw[t0 + kj]];
+                if (nc < 32) gsbits &= (1u << nc) - 1u;
+                if (gsbits == 0) gsbits = 0xffffffffu;
+                vq = nullptr;
+            }
+            bool shortlist = vq != nullptr || gscw != nullptr;
+            if (vq) {
                 int32_t bv = (int32_t)0x80000000;
                 for (int c = 0; c < nc; ++c) bv = max(bv, quant(c));
                 th = (int32_t)((uint32_t)bv + (uint32_t)g.svq_beam);
@@ -196,7 +209,7 @@ s3_eval_kernel(S3Dev g, const float *__restrict__ feat, int T, int s_lo, int s_h
             while (true) {
                 score = kS3Zero; bscr = kS3Zero; bidx = kNoBst;
                 for (int c = 0; c < nc; ++c) {
-                    if (shortlist && quant(c) < th) continue;
+                    if (shortlist && (vq ? quant(c) < th : !((gsbits >> (c & 31)) & 1u))) continue;
                     const int32_t v = sj[c];
                     score = s3_logadd(g, score, v);
                     if (v > bscr) { bscr = v; bidx = c; }
@@ -246,6 +259,35 @@ s3_vq_kernel(S3Vq q, const float *__restrict__ feat, int T, int veclen, int32_t 
         }
         out[(size_t)t * q.n_sv * q.size + e] = v;
     }
+}
+
+// gc_compute_closest_cw (gs.c:221-259) for every frame: squared Euclidean distance with float32 differences
+// summed in float64 in dimension order; the FIRST minimum wins.  One block per frame, one thread per codeword.
+__global__ void __launch_bounds__(128)
+s3_gs_kernel(const float *__restrict__ cw, int n_code, int L, const float *__restrict__ feat, int veclen, int32_t *__restrict__ out) {
+    __shared__ double s_d[128];
+    __shared__ int s_i[128];
+    const int t = blockIdx.x;
+    const float *x = feat + (size_t)t * veclen;
+    double best = 1.7976931348623157e308; int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < n_code; c += blockDim.x) {
+        double tmp = 0.0;
+        for (int i = 0; i < L; ++i) {
+            const double dd = (double)__fsub_rn(x[i], cw[(size_t)c * L + i]);
+            tmp = __dadd_rn(tmp, __dmul_rn(dd, dd));
+        }
+        if (tmp < best) { best = tmp; bi = c; }        // ascending c within the thread: first minimum
+    }
+    s_d[threadIdx.x] = best; s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double d2 = s_d[threadIdx.x + o]; const int i2 = s_i[threadIdx.x + o];
+            if (d2 < s_d[threadIdx.x] || (d2 == s_d[threadIdx.x] && i2 < s_i[threadIdx.x])) { s_d[threadIdx.x] = d2; s_i[threadIdx.x] = i2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[t] = s_i[0] == 0x7fffffff ? 0 : s_i[0];
 }
 
 // K2: one block per frame.
@@ -452,6 +494,9 @@ struct b200_s3mgau {
     int32_t *d_svq_map = nullptr, *d_svq_i = nullptr; float *d_svq_f = nullptr; double *d_svq_var = nullptr;
     int32_t *d_vqd = nullptr; size_t vqd_cap = 0;
     S3Vq vq{};
+    // Gaussian selector (b200_s3_set_gs), optional
+    int gs_n_code = 0, gs_featlen = 0;
+    float *d_gs_cw = nullptr; uint32_t *d_gs_map = nullptr; int32_t *d_gscw = nullptr; size_t gscw_cap = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0.f;
@@ -462,6 +507,7 @@ struct b200_s3mgau {
         g.tab16 = d_tab16; g.tab32 = d_tab32; g.tab_size = (uint32_t)lm->table.size();
         g.lzero = lm->zero; g.distfloor = distfloor; g.f = f;
         g.svq_n_sv = svq_n_sv; g.svq_size = svq_size; g.svq_eval = svq_eval; g.svq_beam = svq_beam; g.svq_map = d_svq_map;
+        g.gs_n_code = gs_n_code; g.gs_map = d_gs_map;
         return g;
     }
 };
@@ -491,27 +537,27 @@ int s3_reserve(b200_s3mgau *m, int T) {
 
 template <int CP, int KC>
 int launch_eval_t(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
-                  int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd) {
+                  int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd, const int32_t *gscw) {
     if (s_hi <= s_lo || T <= 0) return B200_OK;
     constexpr int G = kEvalThreads / CP;
     dim3 grid((s_hi - s_lo + G - 1) / G, (T + kFB - 1) / kFB);
     size_t smem = (size_t)kFB * m->veclen * sizeof(float) + (size_t)kEvalThreads * KC * kFR * sizeof(int32_t);
-    s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst, vqd);
+    s3_eval_kernel<CP, KC><<<grid, kEvalThreads, smem, st>>>(m->dev(), d_feat, T, s_lo, s_hi, flags, raw, bst, vqd, gscw);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
 int launch_eval(const b200_s3mgau *m, const float *d_feat, int T, int s_lo, int s_hi, const uint8_t *flags,
-                int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd = nullptr) {
+                int32_t *raw, int16_t *bst, cudaStream_t st, const int32_t *vqd = nullptr, const int32_t *gscw = nullptr) {
     switch (m->cp * 8 + m->kc) {
-    case 1 * 8 + 1: return launch_eval_t<1, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 2 * 8 + 1: return launch_eval_t<2, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 4 * 8 + 1: return launch_eval_t<4, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 8 * 8 + 1: return launch_eval_t<8, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 16 * 8 + 1: return launch_eval_t<16, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 32 * 8 + 1: return launch_eval_t<32, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 32 * 8 + 2: return launch_eval_t<32, 2>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
-    case 32 * 8 + 4: return launch_eval_t<32, 4>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd);
+    case 1 * 8 + 1: return launch_eval_t<1, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 2 * 8 + 1: return launch_eval_t<2, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 4 * 8 + 1: return launch_eval_t<4, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 8 * 8 + 1: return launch_eval_t<8, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 16 * 8 + 1: return launch_eval_t<16, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 32 * 8 + 1: return launch_eval_t<32, 1>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 32 * 8 + 2: return launch_eval_t<32, 2>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
+    case 32 * 8 + 4: return launch_eval_t<32, 4>(m, d_feat, T, s_lo, s_hi, flags, raw, bst, st, vqd, gscw);
     }
     set_error("unsupported component count");
     return B200_ERR_UNSUP;
@@ -534,11 +580,22 @@ int s3_chunk_dev(b200_s3mgau *m, const float *d_feat, int T, int frame0, uint8_t
         B200_LAUNCH_CHECK();
         vqd = m->d_vqd;
     }
-    if ((rc = launch_eval(m, d_feat, T, 0, m->n_ci, nullptr, m->d_raw, m->d_bst, st, vqd))) return rc;
+    const int32_t *gscw = nullptr;
+    if (m->gs_n_code) {
+        if ((size_t)T > m->gscw_cap) {
+            cudaFree(m->d_gscw); m->d_gscw = nullptr; m->gscw_cap = 0;
+            B200_CUDA_OK(cudaMalloc((void **)&m->d_gscw, (size_t)T * sizeof(int32_t)));
+            m->gscw_cap = T;
+        }
+        s3_gs_kernel<<<T, 128, 0, st>>>(m->d_gs_cw, m->gs_n_code, m->gs_featlen, d_feat, m->veclen, m->d_gscw);
+        B200_LAUNCH_CHECK();
+        gscw = m->d_gscw;
+    }
+    if ((rc = launch_eval(m, d_feat, T, 0, m->n_ci, nullptr, m->d_raw, m->d_bst, st, vqd, gscw))) return rc;
     s3_decide_kernel<<<T, 256, (size_t)3 * std::max(m->n_ci, 1) * sizeof(int32_t), st>>>(
         g, T, frame0, m->ci_pbeam, m->max_cd, m->ds_ratio, m->tighten, m->d_raw, d_act, m->d_flags, m->d_beam);
     B200_LAUNCH_CHECK();
-    if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st, vqd))) return rc;
+    if ((rc = launch_eval(m, d_feat, T, m->n_ci, m->n_sen, m->d_flags, m->d_raw, m->d_bst, st, vqd, gscw))) return rc;
     const int n_cd = m->n_sen - m->n_ci;
     if (n_cd > 0) {
         s3_backoff_kernel<<<dim3((n_cd + 127) / 128, T), 128, 0, st>>>(g, d_feat, T, frame0, m->ds_ratio, m->d_flags,
@@ -693,7 +750,7 @@ void b200_s3_free(b200_s3mgau_t *m) {
     cudaSetDevice(m->device);
     void *ptrs[] = {m->d_mean, m->d_var, m->d_lrd, m->d_mixw, m->d_ncomp, m->d_cd2ci, m->d_tab16, m->d_tab32, m->d_bstidx,
                     m->d_update, m->d_prev, m->d_feat, m->d_act, m->d_flags, m->d_raw, m->d_out, m->d_beam, m->d_best, m->d_bst,
-                    m->d_svq_map, m->d_svq_i, m->d_svq_f, m->d_svq_var, m->d_vqd};
+                    m->d_svq_map, m->d_svq_i, m->d_svq_f, m->d_svq_var, m->d_vqd, m->d_gs_cw, m->d_gs_map, m->d_gscw};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (m->st) cudaStreamDestroy(m->st);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
@@ -833,6 +890,47 @@ int b200_s3_set_subvq(b200_s3mgau_t *m, const char *file, double varfloor, int m
     q.veclen = m->d_svq_i; q.off_dim = m->d_svq_i + n_sv; q.off_par = m->d_svq_i + 2 * n_sv; q.featdim = m->d_svq_i + 3 * n_sv;
     q.mean = m->d_svq_f; q.lrd = m->d_svq_f + off_par[n_sv]; q.var = m->d_svq_var;
     q.distfloor = m->distfloor; q.f = m->f;
+    return B200_OK;
+}
+
+// -gs FILE: gs_read (S3/libam/gs.c:156-218) -- five int32 (n_mgau, n_feat, n_density, n_code, featlen), then per
+// codeword its featlen float32 and one bit vector per mixture, of which the reference keeps the first 32-bit word.
+// file == NULL switches the layer off.  With both layers set the selector wins (approx_mgau_eval, gs4gs).
+int b200_s3_set_gs(b200_s3mgau_t *m, const char *file) {
+    if (!m) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(m->device));
+    B200_CUDA_OK(cudaStreamSynchronize(m->st));
+    cudaFree(m->d_gs_cw); cudaFree(m->d_gs_map); m->d_gs_cw = nullptr; m->d_gs_map = nullptr; m->gs_n_code = 0;
+    if (!file) return B200_OK;
+    FILE *fp = fopen(file, "rb");
+    if (!fp) { set_error("cannot open Gaussian-selector map %s", file); return B200_ERR_IO; }
+    int32_t hd[5];
+    if (fread(hd, 4, 5, fp) != 5) { fclose(fp); set_error("%s: short header", file); return B200_ERR_IO; }
+    const int n_mgau = hd[0], n_feat = hd[1], n_density = hd[2], n_code = hd[3], featlen = hd[4];
+    if (n_mgau != m->n_sen || n_feat != 1 || n_density != m->max_comp || featlen != m->veclen || n_code < 1) {
+        fclose(fp);
+        set_error("%s: %d mixtures x %d streams x %d densities, feature length %d do not match the model", file, n_mgau, n_feat, n_density, featlen);
+        return B200_ERR_ARG;
+    }
+    if (n_density > 32) { fclose(fp); set_error("Gaussian selector: more than 32 densities (the reference keeps one 32-bit word per map)"); return B200_ERR_UNSUP; }
+    if (n_code & 1) { fclose(fp); set_error("Gaussian selector: odd codeword count (gc_compute_closest_cw walks the codewords in pairs)"); return B200_ERR_UNSUP; }
+    const size_t words = (size_t)(n_density + 31) / 32;
+    std::vector<float> cw((size_t)n_code * featlen);
+    std::vector<uint32_t> map((size_t)n_mgau * n_code), row((size_t)n_mgau * words);
+    for (int k = 0; k < n_code; ++k) {
+        if (fread(&cw[(size_t)k * featlen], 4, featlen, fp) != (size_t)featlen || fread(row.data(), 4, row.size(), fp) != row.size()) {
+            fclose(fp); set_error("%s: truncated", file); return B200_ERR_IO;
+        }
+        for (int s = 0; s < n_mgau; ++s) map[(size_t)s * n_code + k] = row[(size_t)s * words];
+    }
+    fclose(fp);
+    if (cudaMalloc((void **)&m->d_gs_cw, cw.size() * 4) != cudaSuccess || cudaMalloc((void **)&m->d_gs_map, map.size() * 4) != cudaSuccess ||
+        cudaMemcpy(m->d_gs_cw, cw.data(), cw.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(m->d_gs_map, map.data(), map.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("Gaussian selector upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return B200_ERR_CUDA;
+    }
+    m->gs_n_code = n_code; m->gs_featlen = featlen;
     return B200_OK;
 }
 

@@ -687,6 +687,10 @@ class S3Mgau:
         check(lib.b200_s3_set_subvq(self.h, None if path is None else path.encode(), varfloor, max_sv, vqeval, subvqbeam),
               "s3_set_subvq")
 
+    def set_gs(self, path):
+        """-gs (S3/libam/gs.c); path None removes the layer."""
+        check(lib.b200_s3_set_gs(self.h, None if path is None else path.encode()), "s3_set_gs")
+
     def utt_reset(self):
         check(lib.b200_s3_utt_reset(self.h), "s3_utt_reset")
 

@@ -439,10 +439,17 @@ int  b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_rati
  * linearisation), subvq_gautbl_eval_logs3 :488-506, subvq_mgau_shortlist :383-468 and approx_mgau_eval's use of
  * the shortlist incl. its full re-evaluation below S3_LOGPROB_ZERO + 100000 (approx_cont_mgau.c:187-284).  On the
  * device the shortlist is a mask over the dense component scores.  -svq4svq (quantised scores AS the Gaussian
- * scores) and the Gaussian selector (-gs, gs.c: no map file in the tree to pin it against) are not implemented.
+ * scores) is not implemented.
  * file == NULL removes the layer.  The model must have been created with the same component layout the file
  * was made for (the reference's own check: #valid components per mixture). */
 int  b200_s3_set_subvq(b200_s3mgau_t *m, const char *file, double varfloor, int max_sv, int vqeval, double subvqbeam);
+/* -gs FILE: the Gaussian selector -- gs_read (S3/libam/gs.c:156-218), gc_compute_closest_cw (:221-259: the frame's
+ * nearest codeword) and gs_mgau_shortlist (:263-300: the bit map of (mixture, codeword), every component when it
+ * is empty), used by approx_mgau_eval ahead of the sub-VQ shortlist (approx_cont_mgau.c:207-212).  Refused: more
+ * than 32 densities (the reference keeps one 32-bit word) and an odd codeword count (its pairwise loop reads past
+ * the table).  The reference asserts best_cid > 0 (:209), i.e. aborts a debug build when codeword 0 is nearest;
+ * this implementation -- like a release build -- goes on.  file == NULL removes the layer. */
+int  b200_s3_set_gs(b200_s3mgau_t *m, const char *file);
 /* per-utterance reset of bstidx / updatetime (S3/libsearch/srch_time_switch_tree.c:484-490) */
 int  b200_s3_utt_reset(b200_s3mgau_t *m);
 /* Host copies of the precomputed parameters in the reference's order, padded

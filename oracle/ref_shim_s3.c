@@ -22,6 +22,7 @@
 #include "mdef.h"
 #include "logs3.h"
 #include "subvq.h"
+#include "gs.h"
 #include <sphinxbase/cmd_ln.h>
 
 typedef struct {
@@ -35,6 +36,7 @@ typedef struct {
     subvq_t *svq;       /* -subvq: sub-vector quantised shortlists (S3/libam/subvq.c), or NULL */
     double svqbeam;     /* -subvqbeam (probability) */
     cmd_ln_t *config;   /* carries -vqeval for subvq_init */
+    gs_t *gs;           /* -gs: Gaussian selector map (S3/libam/gs.c), or NULL */
 } s3h_t;
 
 void *
@@ -91,6 +93,24 @@ ref_s3_open_svq(void *vh, const char *file, double varfloor, int max_sv, int vqe
     h->svq = subvq_init(file, varfloor, max_sv, h->g, h->config, h->lmath);
     h->svqbeam = subvqbeam;
     return h->svq ? 0 : -1;
+}
+
+/* -gs FILE: the reference's own gs_read (gs.c:156-218).  0 on success. */
+int
+ref_s3_open_gs(void *vh, const char *file)
+{
+    s3h_t *h = vh;
+    h->gs = gs_read(file, h->lmath);
+    return h->gs ? 0 : -1;
+}
+
+/* gc_compute_closest_cw (gs.c:221-259) for T frames */
+void
+ref_s3_gs_closest(void *vh, const float *feat, int T, int32 *out)
+{
+    s3h_t *h = vh;
+    int t, L = h->g->veclen;
+    for (t = 0; t < T; ++t) out[t] = gc_compute_closest_cw(h->gs, (float32 *)feat + (size_t)t * L);
 }
 
 /* d[0..4] = n_sv, vqsize, origsize.r, origsize.c, VQ_EVAL; d[5] = logs3(subvqbeam) as fast_gmm_init stores it */
@@ -243,8 +263,8 @@ ref_s3_eval_utt(void *vh, const float *feat, int T, int frame0, uint8 *sen_activ
         float32 *x = (float32 *)feat + (size_t)t * L;
         if (sen_active) memcpy(h->a.sen_active, sen_active + (size_t)t * S, S);
         else memset(h->a.sen_active, 1, S);
-        approx_cont_mgau_ci_eval(h->svq, NULL, h->g, h->fg, h->mdef, x, ci, &cib, frame0 + t, h->lmath);
-        best[t] = approx_cont_mgau_frame_eval(h->mdef, h->svq, NULL, h->g, h->fg, &h->a, x, frame0 + t,
+        approx_cont_mgau_ci_eval(h->svq, h->gs, h->g, h->fg, h->mdef, x, ci, &cib, frame0 + t, h->lmath);
+        best[t] = approx_cont_mgau_frame_eval(h->mdef, h->svq, h->gs, h->g, h->fg, &h->a, x, frame0 + t,
                                               ci, &h->tm, h->lmath);
         memcpy(out + (size_t)t * S, h->a.senscr, S * sizeof(int32));
         if (sen_active) memcpy(sen_active + (size_t)t * S, h->a.sen_active, S);

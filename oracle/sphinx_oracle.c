@@ -943,6 +943,10 @@ struct orc_s3_model {
     int32_t *svq_dist;                       /* [n_sv * size] scores of the current frame */
     int32_t svq_beam;
     int32_t *svq_sl;                         /* [max_comp + 1] */
+    /* Gaussian selector (S3/libam/gs.c), optional */
+    int gs_n_code, gs_featlen, gs_best;      /* gs_best: closest codeword of the current frame */
+    float *gs_codeword;                      /* [n_code][featlen] */
+    uint32_t *gs_map;                        /* [n_sen][n_code] bit c = component c is in the shortlist */
 };
 
 /* S3/libcommon/vector.c:181-204 */
@@ -1027,6 +1031,7 @@ orc_s3_new(int n_sen, int n_comp, int veclen, const float *mean, const float *va
 void
 orc_s3_free(orc_s3_model_t *m)
 {
+    if (m && m->gs_n_code) { free(m->gs_codeword); free(m->gs_map); if (!m->svq_n_sv) free(m->svq_sl); }
     if (m && m->svq_n_sv) {
         int k;
         for (k = 0; k < m->svq_n_sv; ++k) { free(m->svq_featdim[k]); free(m->svq_mean[k]); free(m->svq_var[k]); free(m->svq_lrd[k]); }
@@ -1254,13 +1259,53 @@ orc_s3_svq_shortlist(orc_s3_model_t *m, int s)
     return nc;
 }
 
-/* approx_mgau_eval (approx_cont_mgau.c:187-284) without a Gaussian selector and with svq4svq off */
+/* gs_read's result (gs.c:156-218) from arrays: codewords [n_code][featlen] and, per (senone, codeword), the
+ * first 32-bit word of the file's bit vector */
+void
+orc_s3_set_gs(orc_s3_model_t *m, int n_code, int featlen, const float *codeword, const uint32_t *map)
+{
+    m->gs_n_code = n_code; m->gs_featlen = featlen;
+    m->gs_codeword = malloc(sizeof(float) * n_code * featlen);
+    memcpy(m->gs_codeword, codeword, sizeof(float) * n_code * featlen);
+    m->gs_map = malloc(sizeof(uint32_t) * m->n_sen * n_code);
+    memcpy(m->gs_map, map, sizeof(uint32_t) * m->n_sen * n_code);
+    if (!m->svq_sl) m->svq_sl = malloc(sizeof(int32_t) * (m->max_comp + 1));
+}
+
+/* gc_compute_closest_cw (gs.c:221-259): squared Euclidean distance, float32 differences summed in float64,
+ * the first minimum wins (the reference walks the codewords in pairs: an even count is assumed) */
+int
+orc_s3_gs_closest(const orc_s3_model_t *m, const float *x)
+{
+    int c, i, best = 0;
+    double min = 1.7976931348623157e308, tmp, diff;
+    for (c = 0; c < m->gs_n_code; ++c) {
+        for (tmp = 0, i = 0; i < m->gs_featlen; ++i) {
+            diff = x[i] - m->gs_codeword[(size_t)c * m->gs_featlen + i];
+            tmp += diff * diff;
+        }
+        if (tmp < min) { min = tmp; best = c; }
+    }
+    return best;
+}
+
+/* approx_mgau_eval (approx_cont_mgau.c:187-284): Gaussian selector first (gs4gs), else sub-VQ; svq4svq off.
+ * (The reference asserts best_cid > 0 before gs_mgau_shortlist, :209: a frame whose nearest codeword is number 0
+ * aborts its debug build; the port -- like a release build -- goes on.) */
 static int
 s3_approx_mgau_eval(orc_s3_model_t *m, int s, int32_t *senscr, const float *x, int fr)
 {
     const int32_t *sl = NULL;
     int ng = m->n_comp[s];
-    if (m->svq_n_sv) {
+    if (m->gs_n_code) {                                  /* gs_mgau_shortlist, gs.c:263-300 */
+        const uint32_t map = m->gs_map[(size_t)s * m->gs_n_code + m->gs_best];
+        int b, n = m->n_comp[s];
+        for (ng = 0, b = 0; b < n; ++b) if (map & (1u << b)) m->svq_sl[ng++] = b;
+        if (ng == 0) for (b = 0; b < n; ++b) m->svq_sl[ng++] = b;
+        m->svq_sl[ng] = -1;
+        sl = m->svq_sl;
+        if (ng == 0) { sl = NULL; ng = n; }
+    } else if (m->svq_n_sv) {
         ng = orc_s3_svq_shortlist(m, s);
         sl = m->svq_sl;
         if (ng == 0) { sl = NULL; ng = m->n_comp[s]; }
@@ -1278,6 +1323,7 @@ void
 orc_s3_ci_eval(orc_s3_model_t *m, const float *x, int32_t *ci_senscr, int32_t *best, int fr)
 {
     int s;
+    if (m->gs_n_code) m->gs_best = orc_s3_gs_closest(m, x);
     if (m->svq_n_sv) orc_s3_svq_eval(m, x);
     for (s = 0; s < m->n_ci_sen; ++s) s3_approx_mgau_eval(m, s, ci_senscr, x, fr);
     *best = INT_MIN;
@@ -1319,6 +1365,7 @@ orc_s3_frame_eval(orc_s3_model_t *m, const float *x, int frame, const int32_t *c
     int32_t best = INT_MIN, pbest = INT_MIN, dyn, single[2] = { -1, -1 };
     int s, is_skip;
     int64_t ns = 0, ng = 0;
+    if (m->gs_n_code) m->gs_best = orc_s3_gs_closest(m, x);
     if (m->svq_n_sv) orc_s3_svq_eval(m, x);
     if (m->max_cd < m->n_sen - m->n_ci_sen) dyn = s3_dyn_beam(m, sen_active, cache_ci_senscr);
     else dyn = m->ci_pbeam;

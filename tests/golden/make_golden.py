@@ -245,6 +245,19 @@ def s3_svq_case(name="s3_svq.npz", T=30):
             bi, ut = r.state()
             out.update({f"vq{i}": vq, f"scr{i}": o, f"best{i}": best, f"act{i}": a, f"bstidx{i}": bi, f"upd{i}": ut})
             r.free()
+        # Gaussian selector (gs.c) on the same model
+        cw, bits = orc.synthetic_gs(mean, 32)
+        path = os.path.join(d, "m.gs")
+        orc.write_gs(path, cw, bits, mean.shape[1])
+        r = orc.RefS3(mf, vf, wf, None, cd2ci, n_ci)
+        orc.ref_set_gs(r, path)
+        r.set_fast(ci_pbeam=1e-40, max_cd=60); r.utt_reset()
+        closest = np.zeros(T, np.int32)
+        orc.ref_s3().ref_s3_gs_closest(r.h, orc._p(feat, orc.C.c_float), T, orc._p(closest, orc.C.c_int32))
+        o, best, a = r.eval_utt(feat, act, 1)
+        bi, ut = r.state()
+        out.update(gs_closest=closest, gs_scr=o, gs_best=best, gs_act=a, gs_bstidx=bi, gs_upd=ut)
+        r.free()
     save(name, n_sen=160, n_ci=n_ci, feat=feat, act=act, frame0=1, **out)
 
 

@@ -589,6 +589,57 @@ def ref_set_svq(r3, path, varfloor=1e-4, max_sv=-1, vqeval=3, subvqbeam=1e-3):
     r3.svq_dims = [int(v) for v in d]       # n_sv, vqsize, r, c, VQ_EVAL, (beam valid after set_fast)
 
 
+# ------------------------------------------------------- sphinx3 Gaussian selector (S3/libam/gs.c)
+port.orc_s3_set_gs.argtypes = [vp, C.c_int, C.c_int, f32p, C.POINTER(C.c_uint32)]
+port.orc_s3_gs_closest.restype = C.c_int
+port.orc_s3_gs_closest.argtypes = [vp, f32p]
+
+
+def write_gs(path, codeword, bits, n_density):
+    """The binary map gs_read parses (gs.c:156-218): five int32 (n_mgau, n_feat = 1, n_density, n_code, featlen),
+    then per codeword its featlen float32 followed by one bit vector (bitvec_size(n_density) uint32 words, native
+    byte order) per mixture.  bits [n_mgau][n_code] uint32 = the first word (the only one the reference keeps)."""
+    codeword = _c(codeword, np.float32); bits = _c(bits, np.uint32)
+    n_code, featlen = codeword.shape
+    n_mgau = bits.shape[0]
+    words = (n_density + 31) // 32
+    with open(path, "wb") as f:
+        f.write(np.array([n_mgau, 1, n_density, n_code, featlen], np.int32).tobytes())
+        for k in range(n_code):
+            f.write(codeword[k].tobytes())
+            row = np.zeros((n_mgau, words), np.uint32); row[:, 0] = bits[:, k]
+            f.write(row.tobytes())
+
+
+def synthetic_gs(mean, n_code, seed=9):
+    """Codewords = means of randomly picked Gaussians (codeword 0 far away from everything: the reference asserts
+    best_cid > 0, approx_cont_mgau.c:209); map bit c of (senone, codeword) set when component c's mean is among the
+    senone's nearest half to the codeword -- so shortlists really drop components; a few maps are left empty to
+    exercise the all-components fall-back of gs_mgau_shortlist."""
+    rng = np.random.default_rng(seed)
+    S, M, D = mean.shape
+    cw = mean.reshape(S * M, D)[rng.choice(S * M, n_code, replace=False)].copy()
+    cw[0] = 1e4
+    d2 = ((mean[:, None, :, :] - cw[None, :, None, :]) ** 2).sum(-1)            # [S][n_code][M]
+    keep = d2 <= np.median(d2, axis=2, keepdims=True)
+    bits = (keep * (np.uint64(1) << np.arange(M, dtype=np.uint64))[None, None, :]).sum(-1).astype(np.uint32)
+    bits[rng.random(bits.shape) < 0.02] = 0
+    return cw.astype(np.float32), bits
+
+
+def port_set_gs(p3, codeword, bits):
+    codeword = _c(codeword, np.float32); bits = _c(bits, np.uint32)
+    port.orc_s3_set_gs(p3.h, codeword.shape[0], codeword.shape[1], _p(codeword, C.c_float), bits.ctypes.data_as(C.POINTER(C.c_uint32)))
+
+
+def ref_set_gs(r3, path):
+    L = ref_s3()
+    L.ref_s3_open_gs.restype = C.c_int
+    L.ref_s3_open_gs.argtypes = [vp, C.c_char_p]
+    L.ref_s3_gs_closest.argtypes = [vp, f32p, C.c_int, i32p]
+    assert L.ref_s3_open_gs(r3.h, path.encode()) == 0
+
+
 # ------------------------------------------------------- sphinx3 hmm_vit_eval
 port.orc_s3hmm_eval_batch.restype = C.c_int32
 port.orc_s3hmm_eval_batch.argtypes = [C.c_int, C.c_int, i32p, C.c_int, i16p, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p,

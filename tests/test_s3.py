@@ -334,3 +334,77 @@ def test_s3_subvq_gpu_real_model_and_per_frame_binding():
         small = b.S3Mgau.from_arrays(*synth.s3_model(n_sen=97, n_ci_sen=7, n_density=1, dim=39, seed=5))
         small.set_subvq(sv)
     p.free(); m.free()
+
+
+# ---------------------------------------------------------------- Gaussian selector (S3/libam/gs.c)
+def _gs_golden_model(tmp_path):
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(n_sen=160, n_ci_sen=16)
+    cw, bits = orc.synthetic_gs(mean, 32)
+    path = str(tmp_path / "m.gs")
+    orc.write_gs(path, cw, bits, mean.shape[1])
+    return mean, var, mixw, cd2ci, n_ci, cw, bits, path
+
+
+def _check_gs_golden(model, g):
+    model.set_fast(ci_pbeam=1e-40, max_cd=60); model.utt_reset()
+    o, best, a = model.eval_utt(g["feat"], g["act"], int(g["frame0"]))
+    np.testing.assert_array_equal(best, g["gs_best"]); np.testing.assert_array_equal(o, g["gs_scr"])
+    np.testing.assert_array_equal(a, g["gs_act"])
+    bi, ut = model.state()
+    np.testing.assert_array_equal(bi, g["gs_bstidx"]); np.testing.assert_array_equal(ut, g["gs_upd"])
+
+
+def test_s3_gs_port_matches_golden(tmp_path):
+    g = cases.load("s3_svq.npz")
+    mean, var, mixw, cd2ci, n_ci, cw, bits, path = _gs_golden_model(tmp_path)
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci)
+    orc.port_set_gs(p, cw, bits)
+    got = [orc.port.orc_s3_gs_closest(p.h, orc._p(np.ascontiguousarray(g["feat"][t]), orc.C.c_float)) for t in range(g["feat"].shape[0])]
+    np.testing.assert_array_equal(got, g["gs_closest"])
+    _check_gs_golden(p, g)
+    p.free()
+
+
+@pytest.mark.gpu
+def test_s3_gs_gpu_matches_golden(tmp_path):
+    g = cases.load("s3_svq.npz")
+    mean, var, mixw, cd2ci, n_ci, cw, bits, path = _gs_golden_model(tmp_path)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci)
+    m.set_gs(path)
+    _check_gs_golden(m, g)
+    m.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_code", [
+    (dict(n_sen=600, n_ci_sen=30, n_density=8, dim=39, seed=1), 64),
+    (dict(n_sen=300, n_ci_sen=21, n_density=5, dim=13, seed=2), 16),
+    (dict(n_sen=200, n_ci_sen=12, n_density=32, dim=39, seed=3), 256),      # 32 densities: every map bit in use
+    (dict(n_sen=97, n_ci_sen=7, n_density=1, dim=39, seed=5), 8),
+])
+def test_s3_gs_gpu_matches_oracle(tmp_path, shape, n_code):
+    mean, var, mixw, cd2ci, n_ci = synth.s3_model(**shape)
+    cw, bits = orc.synthetic_gs(mean, n_code, seed=shape["seed"])
+    path = str(tmp_path / "m.gs")
+    orc.write_gs(path, cw, bits, mean.shape[1])
+    p = orc.PortS3(mean, var, mixw, cd2ci, n_ci); orc.port_set_gs(p, cw, bits)
+    m = b.S3Mgau.from_arrays(mean, var, mixw, cd2ci, n_ci); m.set_gs(path)
+    T = 70
+    feat = synth.s3_features(mean, var, T, seed=shape["seed"] + 100)
+    act = synth.s3_active(mean.shape[0], n_ci, T, seed=shape["seed"] + 200)
+    for cfg in (dict(), dict(ci_pbeam=1e-40, max_cd=max(4, mean.shape[0] // 12)), dict(ci_pbeam=1e-30, ds_ratio=3)):
+        for active in (act, None):
+            p.set_fast(**cfg); m.set_fast(**cfg); p.utt_reset(); m.utt_reset()
+            a, c = p.eval_utt(feat, active, 2), m.eval_utt(feat, active, 2)
+            np.testing.assert_array_equal(c[1], a[1], err_msg=str(cfg))
+            np.testing.assert_array_equal(c[0], a[0], err_msg=str(cfg))
+            np.testing.assert_array_equal(np.stack(m.state()), np.stack(p.state()))
+    # with both layers the selector wins (approx_mgau_eval: gs4gs first)
+    q = orc.synthetic_subvq(mean, var, ~np.all(var == 0, axis=2), 1, 8, seed=3)
+    sv = str(tmp_path / "m.subvq"); orc.write_subvq(sv, q)
+    orc.port_set_svq(p, orc.read_subvq(sv)); m.set_subvq(sv)
+    p.set_fast(); m.set_fast(); p.utt_reset(); m.utt_reset()
+    np.testing.assert_array_equal(m.eval_utt(feat, act, 0)[0], p.eval_utt(feat, act, 0)[0])
+    with pytest.raises(b.B200Error, match="odd codeword count"):
+        orc.write_gs(path, cw[:7], bits[:, :7], mean.shape[1]); m.set_gs(path)
+    p.free(); m.free()

@@ -205,3 +205,33 @@ def test_subvq_real_model_matches_reference():
         a, b = p.eval_utt(feat, act), r.eval_utt(feat, act)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     p.free(); r.free()
+
+
+# ---------------------------------------------------------------- Gaussian selector (S3/libam/gs.c)
+@needs_ref
+@pytest.mark.parametrize("cfg", [dict(), dict(ci_pbeam=1e-40, max_cd=60), dict(ci_pbeam=1e-30, ds_ratio=3)])
+def test_gaussian_selector_matches_reference(tmp_path, cfg):
+    """gs_read / gc_compute_closest_cw / gs_mgau_shortlist inside approx_cont_mgau_ci_eval + _frame_eval."""
+    mean, var, p, r, cd2ci, n_ci = _synthetic(tmp_path)
+    cw, bits = orc.synthetic_gs(mean, 32)
+    path = str(tmp_path / "synthetic.gs")
+    orc.write_gs(path, cw, bits, mean.shape[1])
+    orc.port_set_gs(p, cw, bits); orc.ref_set_gs(r, path)
+    T = 50
+    feat = synth.s3_features(mean, var, T)
+    act = synth.s3_active(mean.shape[0], n_ci, T)
+    want = np.zeros(T, np.int32)
+    orc.ref_s3().ref_s3_gs_closest(r.h, orc._p(feat, orc.C.c_float), T, orc._p(want, orc.C.c_int32))
+    got = np.array([orc.port.orc_s3_gs_closest(p.h, orc._p(np.ascontiguousarray(feat[t]), orc.C.c_float)) for t in range(T)])
+    assert np.array_equal(got, want) and want.min() > 0 and len(set(want.tolist())) > 3
+    for m in (p, r):
+        m.set_fast(**cfg)
+    plain = orc.PortS3(mean, var, synth.s3_model()[2], cd2ci, n_ci); plain.set_fast(**cfg)
+    for active, f0 in [(act, 0), (None, 3)]:
+        p.utt_reset(); r.utt_reset(); plain.utt_reset()
+        a, b = p.eval_utt(feat, active, f0), r.eval_utt(feat, active, f0)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+        sa, sb = p.state(), r.state()
+        assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+        assert not np.array_equal(a[0], plain.eval_utt(feat, active, f0)[0])
+    p.free(); r.free(); plain.free()
