@@ -164,6 +164,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--replicas", type=int, default=16, help="copies of the 7 WSJ utterances in the batch arm (0 = skip)")
     ap.add_argument("--procs", type=int, default=os.cpu_count() or 8)
+    ap.add_argument("--mps", action="store_true",
+                    help="run under a CUDA MPS daemon (started and stopped here): the decoder processes of the plug-in arm "
+                         "then share the GPU concurrently instead of being time-sliced")
     args = ap.parse_args()
     out = {"metric": "batch_decode_xRT", "unit": "xRT (lower is better)", "higher_is_better": False, "data": "bundled WSJ .mfc x7",
            "runs": []}
@@ -178,8 +181,22 @@ def main():
                                     "identical_words": [l.rsplit("(", 1)[0] for l in cpu["hyp"].splitlines()] ==
                                                        [l.rsplit("(", 1)[0] for l in gpu["hyp"].splitlines()],
                                     "identical_path_scores": cpu["hyp"] == gpu["hyp"]})
-    if args.replicas > 0:
-        out["batch"] = batch_pipeline(args.replicas, args.procs)
+    mps = None
+    if args.mps:
+        import shutil
+        if shutil.which("nvidia-cuda-mps-control"):
+            os.environ["CUDA_MPS_PIPE_DIRECTORY"] = "/tmp/b200_mps_pipe"
+            os.environ["CUDA_MPS_LOG_DIRECTORY"] = "/tmp/b200_mps_log"
+            for d in (os.environ["CUDA_MPS_PIPE_DIRECTORY"], os.environ["CUDA_MPS_LOG_DIRECTORY"]):
+                os.makedirs(d, exist_ok=True)
+            mps = subprocess.run(["nvidia-cuda-mps-control", "-d"], timeout=60).returncode == 0
+        out["mps"] = bool(mps)
+    try:
+        if args.replicas > 0:
+            out["batch"] = batch_pipeline(args.replicas, args.procs)
+    finally:
+        if mps:
+            subprocess.run(["nvidia-cuda-mps-control"], input=b"quit\n", timeout=60)
     print(json.dumps(out))
 
 
