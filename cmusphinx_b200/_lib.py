@@ -118,6 +118,7 @@ _sig("b200_s3_dims", C.c_int, vp, c_i32p)
 _sig("b200_s3_set_fast", C.c_int, vp, C.c_double, C.c_int, C.c_int, C.c_float)
 _sig("b200_s3_set_subvq", C.c_int, vp, C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double)
 _sig("b200_s3_set_gs", C.c_int, vp, C.c_char_p)
+_sig("b200_s3_set_fast_log", C.c_int, vp, C.c_int32, C.c_int, C.c_int, C.c_float, C.c_int32)
 _sig("b200_s3_utt_reset", C.c_int, vp)
 _sig("b200_s3_params", C.c_int, vp, c_i32p, c_f32p, c_f32p, c_f32p, c_i32p, C.POINTER(C.c_double))
 _sig("b200_s3_state", C.c_int, vp, c_i32p, c_i32p)

@@ -771,6 +771,16 @@ int b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio
     return B200_OK;
 }
 
+// The same from the values fast_gmm_t already holds (fast_algo_struct.h:204-262: the beams are stored as
+// logs3 integers) -- what a binding inside the decoder has at hand.  svq_beam_log <= 0 is kept as is.
+int b200_s3_set_fast_log(b200_s3mgau_t *m, int32_t ci_pbeam_log, int max_cd, int ds_ratio, float tighten_factor,
+                         int32_t subvqbeam_log) {
+    if (!m || ds_ratio < 1) { set_error("b200_s3_set_fast_log: bad argument"); return B200_ERR_ARG; }
+    m->ci_pbeam = ci_pbeam_log; m->max_cd = max_cd; m->ds_ratio = ds_ratio; m->tighten = tighten_factor;
+    m->svq_beam = subvqbeam_log;
+    return B200_OK;
+}
+
 // -subvq FILE, -svmax, -vqeval, -subvqbeam: subvq_init (S3/libam/subvq.c:206-373) -- the text file gausubvq
 // writes -- then subvq_maha_precomp (:106-123: variance floor, vector_maha_precomp), subvq_map_compact
 // (:127-181) and subvq_map_linearize (:191-203); the beam goes through logs3 as fast_gmm_init does

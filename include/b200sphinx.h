@@ -434,6 +434,11 @@ int  b200_s3_dims(const b200_s3mgau_t *m, int32_t dims[5]);
  * probability), -maxcdsenpf, -ds, -tighten_factor. */
 int  b200_s3_set_fast(b200_s3mgau_t *m, double ci_pbeam, int max_cd, int ds_ratio,
                       float tighten_factor);
+/* The same with the beams as the logs3 integers fast_gmm_t holds (S3 include/fast_algo_struct.h:204-262:
+ * fg->gmms->ci_pbeam, ->max_cd, ->tighten_factor, fg->downs->ds_ratio, fg->gaus->subvqbeam) -- what a binding
+ * inside the decoder (plugin/b200_s3_mgau.c) has at hand. */
+int  b200_s3_set_fast_log(b200_s3mgau_t *m, int32_t ci_pbeam_log, int max_cd, int ds_ratio, float tighten_factor,
+                          int32_t subvqbeam_log);
 /* -subvq FILE -svmax N -vqeval N -subvqbeam P: sub-vector quantised Gaussian selection for the approx path --
  * subvq_init, S3/libam/subvq.c:206-373 (file format, variance floor, vector_maha_precomp, map compaction and
  * linearisation), subvq_gautbl_eval_logs3 :488-506, subvq_mgau_shortlist :383-468 and approx_mgau_eval's use of

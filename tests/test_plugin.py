@@ -372,3 +372,59 @@ def test_hmm_boundary_evaluate_channels_on_the_gpu(tmp_path, inp):
         assert rep, "the HMM binding did not run"
         frames, evals, fell = (int(x) for x in __import__("re").findall(r"(\d+) frames, (\d+) HMM evaluations on the GPU, (\d+) calls", rep[-1])[0])
         assert frames > 100 and evals > 20 * frames and fell == 0, rep[-1]
+
+
+# ---------------------------------------------------------------- sphinx3 boundary (last row)
+S3_PLUGIN = os.path.join(orc.ROOT, "cmusphinx_b200", "_plugin", "libb200_s3_plugin.so")
+S3_DECODE = os.path.join(orc.REF_DIR, "sphinx3_decode")
+needs_s3 = pytest.mark.skipif(not (os.path.exists(S3_PLUGIN) and os.path.exists(S3_DECODE)),
+                              reason="sphinx3_decode (oracle/_ref) or the sphinx3 plug-in not built")
+
+
+def _s3_decode(tmp_path, tag, extra, env_extra):
+    """The reference's own regression decode (sphinx3/src/tests/regression/test-decode-s3cont.sh): hub4_cd_continuous
+    + the an4 unigram LM on pittsburgh.littleendian.mfc through the UNMODIFIED sphinx3_decode."""
+    am, lm = os.path.join(D, "hmm", "cont"), os.path.join(D, "lm", "an4")
+    cep = tmp_path / "cep"
+    cep.mkdir(exist_ok=True)
+    dst = cep / "pittsburgh.littleendian.mfc"
+    if not dst.exists():
+        os.symlink(os.path.join(D, "test", "pittsburgh.littleendian.mfc"), dst)
+    cmd = [S3_DECODE, "-mdef", os.path.join(am, "mdef"), "-fdict", os.path.join(lm, "filler.dict"), "-dict", os.path.join(lm, "an4.dict"),
+           "-mean", os.path.join(am, "means"), "-var", os.path.join(am, "variances"), "-mixw", os.path.join(am, "mixture_weights"),
+           "-tmat", os.path.join(am, "transition_matrices"), "-ctl", os.path.join(lm, "an4.ctl"), "-cepdir", str(cep),
+           "-agc", "none", "-varnorm", "no", "-cmn", "current", "-maxwpf", "1", "-beam", "1e-40", "-pbeam", "1e-30",
+           "-wbeam", "1e-20", "-maxhmmpf", "1500", "-wend_beam", "1e-1", "-feat", "1s_c_d_dd",
+           "-lm", os.path.join(lm, "an4.ug.lm.DMP")] + extra
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = orc.REF_DIR + ":" + env.get("LD_LIBRARY_PATH", "")
+    env.update(env_extra)
+    p = subprocess.run(cmd, env=env, timeout=900, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace")
+    assert p.returncode == 0, p.stdout[-3000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("FWDVIT:") or l.startswith("FWDXCT:")]
+    return lines, p.stdout
+
+
+@needs_s3
+def test_sphinx3_reference_build_reproduces_its_regression_result(tmp_path):
+    lines, _ = _s3_decode(tmp_path, "ref", ["-senmgau", ".s3cont."], {})      # the regression's own setting (ms_mgau path)
+    assert lines and all("P I T G S B U R G H" in l for l in lines if l.startswith("FWDVIT:"))     # test-decode-s3cont.sh
+
+
+@needs_s3
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["-ci_pbeam", "1e-5", "-maxcdsenpf", "1000"], ["-ds", "2", "-ci_pbeam", "1e-8"],
+                                   ["-subvq", os.path.join(D, "hmm", "cont", "test.subvq"), "-subvqbeam", "1e-2"]],
+                         ids=["default", "ci_beam_dyn", "ds2", "subvq"])
+def test_sphinx3_boundary_frame_eval_on_the_gpu(tmp_path, extra):
+    """approx_cont_mgau_frame_eval of the unmodified sphinx3 decoder served by b200_s3_frame_eval
+    (plugin/b200_s3_mgau.c): the hypothesis AND the per-word acoustic / LM scores of the FWDXCT line
+    must be identical, with the fast-GMM layers switched on as well.  (-senmgau .cont. selects the
+    mgau_init / approx_cont_mgau path, kbcore.c:296-310; the regression script's .s3cont. is the ms_mgau one.)"""
+    extra = ["-senmgau", ".cont."] + extra
+    ref, _ = _s3_decode(tmp_path, "ref", extra, {})
+    gpu, log = _s3_decode(tmp_path, "gpu", extra, {"LD_PRELOAD": S3_PLUGIN})
+    assert "approx_cont_mgau_frame_eval is served by libb200sphinx" in log
+    assert ref and gpu == ref
+    off, log2 = _s3_decode(tmp_path, "off", extra, {"LD_PRELOAD": S3_PLUGIN, "B200_S3_PLUGIN_DISABLE": "1"})
+    assert off == ref and "served by libb200sphinx" not in log2
