@@ -109,6 +109,18 @@ _sig("b200_hmm_normalize_dev", C.c_int, vp, vp, vp)
 _sig("b200_hmm_clear_pruned_dev", C.c_int, vp, vp)
 _sig("b200_hmm_enter_dev", C.c_int, vp, vp, vp, vp, C.c_int, vp)
 _sig("b200_hmm_enter_host", C.c_int, vp, c_i32p, c_i32p, c_i32p, C.c_int)
+class PruneDev(C.Structure):
+    _fields_ = [("score", vp), ("history", vp), ("out_score", vp), ("out_history", vp), ("bestscore", vp), ("frame", vp),
+                ("state_stride", C.c_long), ("par", vp), ("pls_pen", vp), ("acl", vp), ("n_act", vp), ("list_cap", C.c_int32),
+                ("nacl", vp), ("n_nacl", vp), ("cand", vp), ("n_cand", vp), ("cand_cap", C.c_int32)]
+
+
+_sig("b200_chantree_create", vp, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int, C.c_int)
+_sig("b200_chantree_free", None, vp)
+_sig("b200_chantree_cand_cap", C.c_int, vp)
+_sig("b200_fwdtree_prune_dev", C.c_int, vp, C.c_int, C.POINTER(PruneDev), vp)
+_sig("b200_fwdtree_prune_host", C.c_int, vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p,
+     c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int)
 _sig("b200_s3_create", vp, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, C.c_double, C.c_double, C.c_double,
      c_i32p, C.c_int, C.c_int)
 _sig("b200_s3_load", vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_double, c_i32p, C.c_int,

@@ -427,6 +427,59 @@ class HmmPopulation:
         return s
 
 
+class ChanTree:
+    """The lexical tree of the forward tree search (root_chan_t / chan_t, ngram_search.h:64-104) on the
+    GPU, and its prune / phone-transition stage: prune_root_chan + prune_nonroot_chan
+    (ngram_search_fwdtree.c:714-869).  Arrays as include/b200sphinx.h describes them."""
+
+    PAR = ("frame", "best_score", "beam", "pbeam", "lpbeam", "pip", "nwpen", "has_pls")
+
+    def __init__(self, n_root, n_chan, child_off, child, ciphone, pw_off, pw_wid, pw_lastphone, n_ci, n_emit=3, device=0):
+        a = [_c(x, np.int32) for x in (child_off, child, ciphone, pw_off, pw_wid, pw_lastphone)]
+        h = lib.b200_chantree_create(int(n_root), int(n_chan), *[_p(x, C.c_int32) for x in a], int(n_ci), int(n_emit), device)
+        if not h:
+            raise B200Error(f"b200_chantree_create failed: {_lib.last_error()}")
+        self._h = C.c_void_p(h)
+        self.n_root, self.n_chan, self.n_ci, self.n_emit = int(n_root), int(n_chan), int(n_ci), int(n_emit)
+        self.cand_cap = lib.b200_chantree_cand_cap(self._h)
+
+    def free(self):
+        if self._h:
+            lib.b200_chantree_free(self._h)
+            self._h = None
+
+    def prune(self, par, pls_pen, acl_lists, score, history, out_score, out_history, bestscore, frame, list_cap=None):
+        """One frame for n_utt utterances.  par: [n_utt][8] (ChanTree.PAR order); pls_pen [n_utt][n_ci] or
+        None; acl_lists: one int array per utterance; state arrays state-major over n_utt * n_chan channels,
+        updated in place.  Returns (next active lists, candidate arrays [n][3]) per utterance."""
+        par = _c(par, np.int32).reshape(-1, 8)
+        n_utt = par.shape[0]
+        cap = max(1, self.n_chan - self.n_root) if list_cap is None else int(list_cap)
+        acl = np.zeros((n_utt, cap), np.int32)
+        n_act = np.zeros(n_utt, np.int32)
+        for u, l in enumerate(acl_lists):
+            l = np.asarray(l, np.int32)
+            if len(l) > cap:
+                raise B200Error("active list longer than list_cap")
+            acl[u, :len(l)] = l
+            n_act[u] = len(l)
+        pen = None if pls_pen is None else _c(pls_pen, np.int32).reshape(n_utt, self.n_ci)
+        for a in (score, history, out_score, out_history, bestscore, frame):
+            assert a.dtype == np.int32 and a.flags.c_contiguous
+        assert score.size == self.n_emit * n_utt * self.n_chan and frame.size == n_utt * self.n_chan
+        ccap = max(1, self.cand_cap)
+        nacl = np.zeros((n_utt, cap), np.int32)
+        cand = np.zeros((n_utt, ccap, 3), np.int32)
+        n_nacl, n_cand = np.zeros(n_utt, np.int32), np.zeros(n_utt, np.int32)
+        check(lib.b200_fwdtree_prune_host(self._h, n_utt, _p(par, C.c_int32), None if pen is None else _p(pen, C.c_int32),
+                                          _p(acl, C.c_int32), _p(n_act, C.c_int32), cap, _p(score, C.c_int32),
+                                          _p(history, C.c_int32), _p(out_score, C.c_int32), _p(out_history, C.c_int32),
+                                          _p(bestscore, C.c_int32), _p(frame, C.c_int32), _p(nacl, C.c_int32),
+                                          _p(n_nacl, C.c_int32), _p(cand, C.c_int32), _p(n_cand, C.c_int32), ccap),
+              "fwdtree_prune_host")
+        return [nacl[u, :n_nacl[u]].copy() for u in range(n_utt)], [cand[u, :n_cand[u]].copy() for u in range(n_utt)]
+
+
 def s3hmm_vit_eval(n_emit: int, tp, sseq, n_sen: int, senscr, score, history, out_score, out_history, ssid, tmatid, mpx,
                    bestscore, device: int = 0):
     """sphinx3's hmm_vit_eval (libs3decoder/libam/hmm.c:852-873) for every HMM, once per row of

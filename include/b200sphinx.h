@@ -396,6 +396,62 @@ int  b200_hmm_enter_dev(b200_hmmctx_t *c, const int32_t *d_idx, const int32_t *d
 int  b200_hmm_enter_host(b200_hmmctx_t *c, const int32_t *idx, const int32_t *score,
                          const int32_t *hist, int n);
 
+/* ----------------------------------------------------------------------------
+ * Prune / phone-transition stage of the forward tree search:
+ * prune_root_chan followed by prune_nonroot_chan, PS/ngram_search_fwdtree.c:714-790 and
+ * :792-869 (they are `static`; their only caller is prune_channels, :1125-1160), with
+ * hmm_enter (PS/hmm.c:197-203) and hmm_clear_scores (PS/hmm.c:169-181), for a batch of
+ * utterances that share one lexical tree.  Results -- channel states, the ORDER of the next
+ * frame's active list and the order of the last-phone candidates -- are identical to the
+ * reference's sequential walk (csrc/fwdtree_prune.cu explains how).
+ *
+ * The tree (root_chan_t / chan_t, PS/ngram_search.h:64-104) as arrays: channels
+ * 0..n_root-1 are ngs->root_chan[]; the children of channel c -- its `next` channel and
+ * that channel's `alt` chain, in chain order -- are child[child_off[c] .. child_off[c+1]);
+ * ciphone[c] is chan_t.ciphone (the phone-loop look-ahead is indexed with it, :748, :827);
+ * the words whose last phone follows c -- penult_phn_wid and its homophone_set chain
+ * (:765-766, :847-848) -- are pw_wid[pw_off[c] .. pw_off[c+1]) with
+ * pw_lastphone = dict_last_phone(w).  Every non-root channel must have exactly one
+ * parent (else NULL + b200_last_error).  n_emit = hmm_n_emit_state. */
+typedef struct b200_chantree b200_chantree_t;
+b200_chantree_t *b200_chantree_create(int n_root, int n_chan, const int32_t *child_off, const int32_t *child,
+                                      const int32_t *ciphone, const int32_t *pw_off, const int32_t *pw_wid,
+                                      const int32_t *pw_lastphone, int n_ci, int n_emit, int device);
+void b200_chantree_free(b200_chantree_t *t);
+int  b200_chantree_cand_cap(const b200_chantree_t *t);   /* the most candidates one frame can produce (= n_pw) */
+
+/* Per utterance and frame: par[8] = {frame_idx, ngs->best_score, ngs->dynamic_beam, ngs->pbeam,
+ * ngs->lpbeam, ngs->pip, ngs->nwpen, pls != NULL} (:725-730), pls_pen[n_ci] =
+ * phone_loop_search_score(pls, ci) (PS/phone_loop_search.h:104; may be NULL when no utterance
+ * has a look-ahead), acl = ngs->active_chan_list[frame_idx & 1] as channel ids, n_act its length.
+ * State: the hmm_t fields of every channel, state-major like b200_hmm_soa_t
+ * (score / history [n_emit][n_utt * n_chan], the others [n_utt * n_chan]) plus hmm_frame.
+ * Out: nacl / n_nacl = active_chan_list[(frame_idx + 1) & 1] in the reference's order,
+ * cand = ngs->lastphn_cand {wid, score, bp} in the reference's order (last_phone_transition,
+ * :876, consumes it on the host), the states updated in place.
+ * list_cap >= the longest list in or out (n_chan - n_root always suffices); cand_cap >=
+ * b200_chantree_cand_cap().  The device form takes device pointers and a stream
+ * (state_stride = the distance between two states' rows, >= n_utt * n_chan: the arrays may be
+ * the resident population of a b200_hmmctx_t). */
+typedef struct {
+    int32_t *score, *history, *out_score, *out_history, *bestscore, *frame;
+    long state_stride;
+    const int32_t *par;        /* [n_utt][8] */
+    const int32_t *pls_pen;    /* [n_utt][n_ci] or NULL */
+    const int32_t *acl;        /* [n_utt][list_cap] */
+    const int32_t *n_act;      /* [n_utt] */
+    int32_t list_cap;
+    int32_t *nacl, *n_nacl;    /* [n_utt][list_cap], [n_utt] */
+    int32_t *cand, *n_cand;    /* [n_utt][cand_cap][3], [n_utt] */
+    int32_t cand_cap;
+} b200_prune_dev_t;
+int  b200_fwdtree_prune_dev(b200_chantree_t *t, int n_utt, const b200_prune_dev_t *d, void *stream);
+int  b200_fwdtree_prune_host(b200_chantree_t *t, int n_utt, const int32_t *par, const int32_t *pls_pen,
+                             const int32_t *acl, const int32_t *n_act, int list_cap, int32_t *score,
+                             int32_t *history, int32_t *out_score, int32_t *out_history, int32_t *bestscore,
+                             int32_t *frame, int32_t *nacl, int32_t *n_nacl, int32_t *cand, int32_t *n_cand,
+                             int cand_cap);
+
 /* acmod_flags2list (PS/acmod.c:1219-1271): bitmask -> uint8 delta list with
  * the reference's lossy >255 bridging.  Host utility; returns n written. */
 int  b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_out);

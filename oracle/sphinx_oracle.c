@@ -1847,3 +1847,85 @@ int32_t orc_s3hmm_eval_batch(int ne, int n_hmm, const int32_t *tp, int n_tmat, c
     }
     return best;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * prune_root_chan + prune_nonroot_chan (ngram_search_fwdtree.c:714-869), sequential restatement on
+ * arrays (see sphinx_oracle.h).  WORST_SCORE = 0xE0000000 (hmm.h:74), BETTER_THAN is > (hmm.h:85).
+ * hmm_enter (hmm.c:197-203) sets score[0], history[0] and frame; hmm_clear_scores (hmm.c:169-181)
+ * sets every state score, the exit score and bestscore to WORST_SCORE and leaves histories and
+ * frame alone. */
+static void orc_prune_exits(int c, int32_t nps, int n_chan, const int32_t *pw_off, const int32_t *pw_wid,
+                            const int32_t *pw_lastphone, const int32_t *par, const int32_t *pls_pen,
+                            const int32_t *out_history, int32_t lastphn_thresh, int32_t *cand, int32_t *n_cand)
+{
+    int k;
+    (void)n_chan;
+    if (!(par[7] || nps > lastphn_thresh)) return;                 /* :763, :845 */
+    for (k = pw_off[c]; k < pw_off[c + 1]; ++k) {
+        const int32_t pl = nps + (par[7] ? pls_pen[pw_lastphone[k]] : 0);
+        if (pl > lastphn_thresh) {                                 /* :771, :853 */
+            int32_t *e = cand + 3 * (*n_cand)++;
+            e[0] = pw_wid[k]; e[1] = pl - par[6]; e[2] = out_history[c];
+        }
+    }
+}
+
+void orc_fwdtree_prune(int n_root, int n_chan, int ne, const int32_t *child_off, const int32_t *child,
+                       const int32_t *ciphone, const int32_t *pw_off, const int32_t *pw_wid,
+                       const int32_t *pw_lastphone, const int32_t *par, const int32_t *pls_pen,
+                       const int32_t *acl, int n_act, int32_t *score, int32_t *history, int32_t *out_score,
+                       int32_t *out_history, int32_t *bestscore, int32_t *frame, int32_t *nacl, int32_t *n_nacl,
+                       int32_t *cand, int32_t *n_cand)
+{
+    const int32_t WORST = (int32_t)0xE0000000;
+    const int32_t fi = par[0], nf = fi + 1;
+    const int32_t thresh = par[1] + par[2], newphone_thresh = par[1] + par[3], lastphn_thresh = par[1] + par[4];
+    const int has_pls = par[7];
+    int i, k, s, nn = 0;
+    *n_cand = 0;
+    /* prune_root_chan :733-789 */
+    for (i = 0; i < n_root; ++i) {
+        int32_t nps;
+        if (frame[i] < fi) continue;                                   /* :737 */
+        if (!(bestscore[i] > thresh)) continue;                        /* :740 */
+        frame[i] = nf;
+        nps = out_score[i] + par[5];
+        if (has_pls || nps > newphone_thresh) {                        /* :746 */
+            for (k = child_off[i]; k < child_off[i + 1]; ++k) {
+                const int c = child[k];
+                const int32_t pl = nps + (has_pls ? pls_pen[ciphone[c]] : 0);
+                if (pl > newphone_thresh && (frame[c] < fi || pl > score[c])) {   /* :750-752 */
+                    score[c] = pl; history[c] = out_history[i]; frame[c] = nf;
+                    nacl[nn++] = c;
+                }
+            }
+        }
+        orc_prune_exits(i, nps, n_chan, pw_off, pw_wid, pw_lastphone, par, pls_pen, out_history, lastphn_thresh, cand, n_cand);
+    }
+    /* prune_nonroot_chan :811-868 */
+    for (i = 0; i < n_act; ++i) {
+        const int h = acl[i];
+        if (bestscore[h] > thresh) {                                   /* :815 */
+            int32_t nps;
+            if (frame[h] != nf) { frame[h] = nf; nacl[nn++] = h; }     /* :817-820 */
+            nps = out_score[h] + par[5];
+            if (has_pls || nps > newphone_thresh) {                    /* :824 */
+                for (k = child_off[h]; k < child_off[h + 1]; ++k) {
+                    const int c = child[k];
+                    const int32_t pl = nps + (has_pls ? pls_pen[ciphone[c]] : 0);
+                    if (pl > newphone_thresh && (frame[c] < fi || pl > score[c])) {   /* :828-832 */
+                        if (frame[c] != nf) nacl[nn++] = c;            /* :833-836 */
+                        score[c] = pl; history[c] = out_history[h]; frame[c] = nf;
+                    }
+                }
+            }
+            orc_prune_exits(h, nps, n_chan, pw_off, pw_wid, pw_lastphone, par, pls_pen, out_history, lastphn_thresh, cand, n_cand);
+        }
+        else if (frame[h] != nf) {                                     /* :863-865 */
+            for (s = 0; s < ne; ++s) score[(size_t)s * n_chan + h] = WORST;
+            out_score[h] = WORST;
+            bestscore[h] = WORST;
+        }
+    }
+    *n_nacl = nn;
+}

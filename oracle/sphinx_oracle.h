@@ -170,6 +170,23 @@ int orc_feat_compute(int type, int cepsize, int cmn, int varnorm, int agc,
                      const float *lda, int lda_dim, const int *subvec, int n_subvec,
                      const float *cep, int T, float *out);
 
+/* ---- prune / phone-transition stage of the forward tree search: prune_root_chan then
+ * prune_nonroot_chan (ngram_search_fwdtree.c:714-790, 792-869), sequential, on the lexical tree as
+ * arrays.  Channels 0..n_root-1 are the roots; children of channel c (its `next` channel and that
+ * channel's `alt` chain, in chain order) are child[child_off[c] .. child_off[c+1]); the words whose
+ * last phone follows c (penult_phn_wid and its homophone_set chain, :765, :847) are
+ * pw_wid[pw_off[c]..], with dict_last_phone in pw_lastphone.  State arrays are state-major
+ * ([ne][n_chan]); frame[] is hmm_frame.  par = {frame_idx, best_score, dynamic_beam, pbeam, lpbeam,
+ * pip, nwpen, has_pls}; pls_pen[ciphone] = phone_loop_search_score (phone_loop_search.h:104).
+ * acl = the current frame's active non-root channels in list order.  Out: nacl (next frame's list,
+ * in the order the reference appends), cand = lastphn_cand {wid, score, bp} in append order. */
+void orc_fwdtree_prune(int n_root, int n_chan, int ne, const int32_t *child_off, const int32_t *child,
+                       const int32_t *ciphone, const int32_t *pw_off, const int32_t *pw_wid,
+                       const int32_t *pw_lastphone, const int32_t *par, const int32_t *pls_pen,
+                       const int32_t *acl, int n_act, int32_t *score, int32_t *history, int32_t *out_score,
+                       int32_t *out_history, int32_t *bestscore, int32_t *frame, int32_t *nacl, int32_t *n_nacl,
+                       int32_t *cand, int32_t *n_cand);
+
 #ifdef __cplusplus
 }
 #endif

@@ -740,3 +740,42 @@ def ref_feat_compute(cep, ftype="1s_c_d_dd", cmn=True, varnorm=False, agc=False,
         raise ValueError("reference rejected the feature configuration")
     rows = out.reshape(-1)[:n * row[0]].reshape(n, row[0])
     return rows[:, :od[0]].copy()
+
+
+# ---- prune / phone-transition stage (ngram_search_fwdtree.c:714-869)
+PRUNE_PAR = ("frame", "best_score", "beam", "pbeam", "lpbeam", "pip", "nwpen", "has_pls")
+
+
+def prune_rows_to_soa(rows):
+    """Trace / golden rows [n_chan][10] (score 0..2, history 0..2, out_score, out_history, bestscore, frame)
+    -> state-major arrays."""
+    rows = np.asarray(rows, np.int32)
+    return dict(score=_c(rows[:, 0:3].T, np.int32), history=_c(rows[:, 3:6].T, np.int32), out_score=_c(rows[:, 6], np.int32),
+                out_history=_c(rows[:, 7], np.int32), bestscore=_c(rows[:, 8], np.int32), frame=_c(rows[:, 9], np.int32))
+
+
+def prune_soa_to_rows(s):
+    return np.concatenate([s["score"].T, s["history"].T, s["out_score"][:, None], s["out_history"][:, None],
+                           s["bestscore"][:, None], s["frame"][:, None]], axis=1).astype(np.int32)
+
+
+def port_fwdtree_prune(topo, par, pls_pen, acl, soa):
+    """oracle/sphinx_oracle.c orc_fwdtree_prune on copies; -> (soa_after, nacl, cand[n][3])."""
+    L = _load_port()
+    s = {k: _c(v, np.int32).copy() for k, v in soa.items()}
+    n_chan, ne = int(topo["n_chan"]), s["score"].shape[0]
+    t = {k: _c(topo[k], np.int32) for k in ("child_off", "child", "ciphone", "pw_off", "pw_wid", "pw_lastphone")}
+    parv = _c([int(par[k]) for k in PRUNE_PAR], np.int32)
+    pen = _c(pls_pen, np.int32)
+    acl = _c(acl, np.int32)
+    nacl = np.zeros(max(1, n_chan), np.int32)
+    cand = np.zeros((max(1, len(t["pw_wid"])), 3), np.int32)
+    n1, n2 = C.c_int32(0), C.c_int32(0)
+    L.orc_fwdtree_prune.restype = None
+    L.orc_fwdtree_prune(C.c_int(int(topo["n_root"])), C.c_int(n_chan), C.c_int(ne), _p(t["child_off"], C.c_int32),
+                        _p(t["child"], C.c_int32), _p(t["ciphone"], C.c_int32), _p(t["pw_off"], C.c_int32),
+                        _p(t["pw_wid"], C.c_int32), _p(t["pw_lastphone"], C.c_int32), _p(parv, C.c_int32), _p(pen, C.c_int32),
+                        _p(acl, C.c_int32), C.c_int(len(acl)), _p(s["score"], C.c_int32), _p(s["history"], C.c_int32),
+                        _p(s["out_score"], C.c_int32), _p(s["out_history"], C.c_int32), _p(s["bestscore"], C.c_int32),
+                        _p(s["frame"], C.c_int32), _p(nacl, C.c_int32), C.byref(n1), _p(cand, C.c_int32), C.byref(n2))
+    return s, nacl[:n1.value].copy(), cand[:n2.value].copy()
