@@ -115,6 +115,7 @@ class PruneDev(C.Structure):
                 ("nacl", vp), ("n_nacl", vp), ("cand", vp), ("n_cand", vp), ("cand_cap", C.c_int32)]
 
 
+_sig("b200_hmm_pop_device", C.c_int, vp, C.POINTER(HmmSoa), C.POINTER(vp))
 _sig("b200_chantree_create", vp, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int, C.c_int)
 _sig("b200_chantree_free", None, vp)
 _sig("b200_chantree_cand_cap", C.c_int, vp)

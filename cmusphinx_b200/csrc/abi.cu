@@ -891,6 +891,18 @@ int b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h) {
     return B200_OK;
 }
 
+// Device addresses of the resident population (for callers that chain their own device-side
+// stages behind the step kernels, e.g. b200_fwdtree_prune_dev) and the stream its kernels run on.
+int b200_hmm_pop_device(b200_hmmctx_t *c, b200_hmm_soa_t *dev, void **stream) {
+    if (!c || !dev) { set_error("null argument"); return B200_ERR_ARG; }
+    if (c->p.n_hmm <= 0) { set_error("b200_hmm_pop_device: no resident population"); return B200_ERR_ARG; }
+    dev->n_hmm = c->p.n_hmm;
+    dev->score = c->p.score; dev->history = c->p.history; dev->out_score = c->p.out_score; dev->out_history = c->p.out_history;
+    dev->senid = c->p.senid; dev->tmatid = c->p.tmatid; dev->mpx = c->p.mpx; dev->bestscore = c->p.bestscore;
+    if (stream) *stream = (void *)c->st;
+    return B200_OK;
+}
+
 // One launch of the persistent step kernel: n_frames frames, frame f on the scores at
 // d_senscr + ((frame0 + f) % n_cycle) * frame_stride.
 static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, int n_cycle, int n_frames, int32_t beam,

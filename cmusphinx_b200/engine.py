@@ -479,6 +479,47 @@ class ChanTree:
               "fwdtree_prune_host")
         return [nacl[u, :n_nacl[u]].copy() for u in range(n_utt)], [cand[u, :n_cand[u]].copy() for u in range(n_utt)]
 
+    def prune_resident(self, ctx, frame, par, pls_pen, acl_lists):
+        """The same stage on the RESIDENT population of an HmmContext (the tree's channels of n_utt utterances,
+        as left by ctx.step / run_dev): b200_fwdtree_prune_dev on the context's stream, the channel states never
+        leave HBM.  frame: host int32 [n_utt * n_chan] (hmm_frame; updated in place).  Only the lists come back."""
+        par = _c(par, np.int32).reshape(-1, 8)
+        n_utt, nc = par.shape[0], self.n_chan
+        soa, st = ctx.device_arrays()
+        assert soa.n_hmm == n_utt * nc and frame.dtype == np.int32 and frame.size == n_utt * nc
+        cap, ccap = max(1, nc - self.n_root), max(1, self.cand_cap)
+        acl = np.zeros((n_utt, cap), np.int32)
+        n_act = np.array([len(l) for l in acl_lists], np.int32)
+        for u, l in enumerate(acl_lists):
+            acl[u, :len(l)] = l
+        pen = np.zeros((n_utt, self.n_ci), np.int32) if pls_pen is None else _c(pls_pen, np.int32).reshape(n_utt, self.n_ci)
+        host = [frame, par, pen, acl, n_act]
+        sizes = [a.nbytes for a in host] + [n_utt * cap * 4, n_utt * 4, n_utt * ccap * 12, n_utt * 4]
+        dev = [lib.b200_dev_alloc(max(1, n), 0) for n in sizes]
+        try:
+            if not all(dev):
+                raise B200Error("device allocation failed")
+            for a, d in zip(host, dev):
+                check(lib.b200_dev_upload(d, a.ctypes.data, a.nbytes), "upload")
+            p = _lib.PruneDev()
+            as_vp = lambda x: C.cast(x, C.c_void_p)
+            p.score, p.history, p.out_score = as_vp(soa.score), as_vp(soa.history), as_vp(soa.out_score)
+            p.out_history, p.bestscore = as_vp(soa.out_history), as_vp(soa.bestscore)
+            p.frame, p.state_stride = dev[0], soa.n_hmm
+            p.par, p.pls_pen, p.acl, p.n_act, p.list_cap = dev[1], dev[2], dev[3], dev[4], cap
+            p.nacl, p.n_nacl, p.cand, p.n_cand, p.cand_cap = dev[5], dev[6], dev[7], dev[8], ccap
+            check(lib.b200_fwdtree_prune_dev(self._h, n_utt, C.byref(p), st), "fwdtree_prune_dev")
+            check(lib.b200_dev_sync(0), "sync")
+            nacl, cand = np.zeros((n_utt, cap), np.int32), np.zeros((n_utt, ccap, 3), np.int32)
+            n_nacl, n_cand = np.zeros(n_utt, np.int32), np.zeros(n_utt, np.int32)
+            for a, d in ((frame, dev[0]), (nacl, dev[5]), (n_nacl, dev[6]), (cand, dev[7]), (n_cand, dev[8])):
+                check(lib.b200_dev_download(a.ctypes.data, d, a.nbytes), "download")
+        finally:
+            for d in dev:
+                if d:
+                    lib.b200_dev_free(d)
+        return [nacl[u, :n_nacl[u]].copy() for u in range(n_utt)], [cand[u, :n_cand[u]].copy() for u in range(n_utt)]
+
 
 def s3hmm_vit_eval(n_emit: int, tp, sseq, n_sen: int, senscr, score, history, out_score, out_history, ssid, tmatid, mpx,
                    bestscore, device: int = 0):
@@ -547,6 +588,12 @@ class HmmContext:
     def download(self, pop: HmmPopulation):
         soa = pop.to_c()
         check(lib.b200_hmm_pop_download(self._h, C.byref(soa)), "pop_download")
+
+    def device_arrays(self):
+        """(HmmSoa of DEVICE pointers, stream) of the resident population (b200_hmm_pop_device)."""
+        soa, st = HmmSoa(), C.c_void_p()
+        check(lib.b200_hmm_pop_device(self._h, C.byref(soa), C.byref(st)), "pop_device")
+        return soa, st
 
     def set_utts(self, utt_off):
         """Split the resident population into utterances (see b200_hmm_pop_set_utts)."""

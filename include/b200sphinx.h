@@ -345,6 +345,9 @@ int  b200_hmm_eval_host(b200_hmmctx_t *c, b200_hmm_soa_t *h,
 /* Device-resident population for benchmarking / resident search state. */
 int  b200_hmm_pop_upload(b200_hmmctx_t *c, const b200_hmm_soa_t *h);
 int  b200_hmm_pop_download(b200_hmmctx_t *c, b200_hmm_soa_t *h);
+/* Device addresses of the resident population (state stride = n_hmm) and the stream its kernels
+ * run on: for device-side stages chained behind the step kernels (b200_fwdtree_prune_dev). */
+int  b200_hmm_pop_device(b200_hmmctx_t *c, b200_hmm_soa_t *dev, void **stream);
 /* Batched search state: split the resident population into n_utt utterances,
  * utterance u owning HMMs [utt_off[u], utt_off[u+1]) (utt_off[0] = 0,
  * utt_off[n_utt] = n_hmm).  Afterwards b200_hmm_step_* take n_utt rows of

@@ -355,3 +355,66 @@ def test_gpu_prune_matches_port_on_synthetic_trees(ne, n_root, n_chan, has_pls):
     for u, (g, w) in enumerate(zip(_gpu_prune(tree, items[::-1], ne), want[::-1])):
         _same(g, w, f"second call utt {u}")
     tree.free()
+
+
+@pytest.mark.gpu
+def test_eval_then_prune_without_leaving_the_device():
+    """hmm_vit_eval for every channel of the tree (the resident population of an HmmContext, three utterances) and
+    the prune / transition stage chained behind it on the context's stream (b200_hmm_pop_device +
+    b200_fwdtree_prune_dev): the channel states stay in HBM between the two stages; only the frame stamps and the
+    lists travel.  Against the oracle's hmm_vit_eval followed by its sequential prune walk."""
+    import cmusphinx_b200 as b
+    from cmusphinx_b200 import synth
+    ne, n_sen, n_tmat, n_sseq, n_root, n_chan, n_utt = 3, 800, 12, 900, 40, 5000, 3
+    rng = np.random.default_rng(11)
+    topo, _ = random_tree(rng, n_root, n_chan)
+    tree = b.ChanTree(n_root, n_chan, *[topo[k] for k in TOPO_KEYS], topo["n_ci"], n_emit=ne)
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n_utt * n_chan, ne, n_sen, n_tmat, n_sseq, seed=4, mpx_fraction=0.0)
+    frames, acls, pens = [], [], []
+    for u in range(n_utt):
+        rows, acl, par, pen = random_frame(rng, topo, ne, frame=20, p_active=0.4, has_pls=(u == 1))
+        sl = slice(u * n_chan, (u + 1) * n_chan)
+        d["score"][sl], d["history"][sl] = rows[:, 0:ne], rows[:, ne:2 * ne]
+        d["out_score"][sl], d["out_history"][sl], d["bestscore"][sl] = rows[:, 2 * ne], rows[:, 2 * ne + 1], rows[:, 2 * ne + 2]
+        d["mpx"][u * n_chan:u * n_chan + n_root] = 1                     # the roots are multiplex HMMs (ngram_search_fwdtree.c:239)
+        d["senid"][u * n_chan:u * n_chan + n_root] = rng.integers(0, n_sseq, (n_root, ne))
+        frames.append(rows[:, 2 * ne + 3].copy()); acls.append(acl); pens.append(pen)
+    sen = np.stack([synth.senscr_frames(1, n_sen, 30 + u)[0] for u in range(n_utt)])
+    # oracle: evaluate, then walk
+    o = {k: v.copy() for k, v in d.items()}
+    want = []
+    for u in range(n_utt):
+        sl = slice(u * n_chan, (u + 1) * n_chan)
+        v = {k: np.ascontiguousarray(o[k][sl]) for k in ("score", "history", "out_score", "out_history", "senid", "tmatid", "mpx", "bestscore")}
+        orc.hmm_eval(orc.port.orc_hmm_eval_batch, ne, tp, d["sseq"], sen[u], v["score"], v["history"], v["out_score"],
+                     v["out_history"], v["senid"], v["tmatid"], v["mpx"], v["bestscore"])
+        act = np.concatenate([np.nonzero(frames[u][:n_root] >= 20)[0], acls[u]])
+        best = int(v["bestscore"][act].max())
+        par = dict(frame=20, best_score=best, beam=-600, pbeam=-500, lpbeam=-450, pip=-5, nwpen=-3, has_pls=int(u == 1))
+        soa = dict(score=np.ascontiguousarray(v["score"].T), history=np.ascontiguousarray(v["history"].T), out_score=v["out_score"],
+                   out_history=v["out_history"], bestscore=v["bestscore"], frame=frames[u])
+        want.append((par,) + orc.port_fwdtree_prune(topo, par, pens[u], acls[u], soa))
+    # device: one resident population, evaluate, prune on the same stream
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    pop = b.HmmPopulation(n_utt * n_chan, ne)
+    pop.score[:], pop.history[:], pop.senid[:] = d["score"].T, d["history"].T, d["senid"].T
+    pop.out_score[:], pop.out_history[:], pop.tmatid[:], pop.mpx[:] = d["out_score"], d["out_history"], d["tmatid"], d["mpx"]
+    pop.bestscore[:] = d["bestscore"]
+    ctx.upload(pop)
+    ctx.set_utts(np.arange(n_utt + 1) * n_chan)
+    ctx.step(sen, -600, n_utt * n_chan)
+    frame = np.concatenate(frames).astype(np.int32)
+    nacl, cand = tree.prune_resident(ctx, frame, [[w[0][k] for k in orc.PRUNE_PAR] for w in want], np.stack(pens),
+                                     acls)
+    ctx.download(pop)
+    for u in range(n_utt):
+        sl = slice(u * n_chan, (u + 1) * n_chan)
+        _, ws, wn, wc = want[u]
+        assert np.array_equal(pop.score[:, sl], ws["score"]) and np.array_equal(pop.history[:, sl], ws["history"])
+        assert np.array_equal(pop.out_score[sl], ws["out_score"]) and np.array_equal(pop.bestscore[sl], ws["bestscore"])
+        assert np.array_equal(frame[sl], ws["frame"])
+        assert np.array_equal(nacl[u], wn) and np.array_equal(cand[u], wc)
+        assert len(wn) > 100 and len(wc) > 10
+    ctx.free()
+    tree.free()
