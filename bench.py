@@ -274,6 +274,7 @@ def device_pipeline(b, m, h_feat, d_out, T, dev, world):
 
 def run_secondary(args):
     """BASELINE configs[2] (ptm), configs[3] (hmm: the literal 1 x 50 000 and the batched 64 x 50 000)
+    the prune / phone-transition stage (recorded decoder states)
     and sphinx3's float64 flavour, each with its roofline and the reference's own CPU code beside it.
     N = 1 only; bounded to about a minute."""
     import types
@@ -282,6 +283,7 @@ def run_secondary(args):
     jobs = [("ptm", lambda: __import__("bench_ptm").run(frames=100_000, steps=2, cpu=True, cpu_budget_s=8.0)),
             ("hmm", lambda: __import__("bench_hmm").run(utts=64, frames=200, warmup=80, cpu=True, cpu_frames=100)),
             ("hmm_single", lambda: __import__("bench_hmm").run(utts=1, frames=2000, warmup=200, cpu=False)),
+            ("prune", lambda: __import__("bench_prune").run(utts=128, steps=30, warmup=5, cpu=True)),
             ("s3", lambda: __import__("bench_s3").run(types.SimpleNamespace(frames=16384, steps=5, warmup=3, cpu_frames=400)))]
     for name, fn in jobs:
         if time.time() - t0 > 150:
@@ -499,14 +501,14 @@ def main():
     ap.add_argument("--path", type=int, default=None, help="force kernel family: 0 exact, 1 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2]/[3]/sphinx3 secondary benches (N = 1)")
-    ap.add_argument("--workload", default="ms_cont", choices=["ms_cont", "ptm", "hmm", "s3", "e2e_decode"],
+    ap.add_argument("--workload", default="ms_cont", choices=["ms_cont", "ptm", "hmm", "s3", "prune", "e2e_decode"],
                     help="ms_cont = the headline (BASELINE configs[1]); the others run the secondary benches "
                          "(bench_ptm.py configs[2], bench_hmm.py configs[3], bench_s3.py sphinx3 flavour, "
                          "bench_e2e_decode.py configs[4]: sharded batch decode, runs under torchrun too) on one GPU")
     args, rest = ap.parse_known_args()
     if args.workload != "ms_cont":
         import runpy
-        script = {"ptm": "bench_ptm.py", "hmm": "bench_hmm.py", "s3": "bench_s3.py", "e2e_decode": "bench_e2e_decode.py"}[args.workload]
+        script = {"ptm": "bench_ptm.py", "hmm": "bench_hmm.py", "s3": "bench_s3.py", "prune": "bench_prune.py", "e2e_decode": "bench_e2e_decode.py"}[args.workload]
         if args.workload == "e2e_decode":
             rest = rest + ["--gpus", str(args.gpus)]
         sys.argv = [script] + rest
