@@ -116,6 +116,7 @@ class PruneDev(C.Structure):
 
 
 _sig("b200_hmm_pop_device", C.c_int, vp, C.POINTER(HmmSoa), C.POINTER(vp))
+_sig("b200_hmm_eval_list_dev", C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp)
 _sig("b200_chantree_create", vp, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int, C.c_int)
 _sig("b200_chantree_free", None, vp)
 _sig("b200_chantree_cand_cap", C.c_int, vp)

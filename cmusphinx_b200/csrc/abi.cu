@@ -903,6 +903,20 @@ int b200_hmm_pop_device(b200_hmmctx_t *c, b200_hmm_soa_t *dev, void **stream) {
     return B200_OK;
 }
 
+// eval_root_chan + eval_nonroot_chan (PS/ngram_search_fwdtree.c:598-634) on the resident population.
+int b200_hmm_eval_list_dev(b200_hmmctx_t *c, int n_root, int n_chan, const int32_t *d_frame, const int32_t *d_par,
+                           const int32_t *d_acl, const int32_t *d_n_act, int list_cap, const int16_t *d_senscr,
+                           int32_t *d_best, void *stream) {
+    if (!c || n_root < 0 || n_chan < 1 || n_root > n_chan || !d_frame || !d_par || !d_n_act || list_cap < 0 ||
+        (list_cap && !d_acl) || !d_senscr || !d_best) { set_error("b200_hmm_eval_list_dev: bad argument"); return B200_ERR_ARG; }
+    if (c->p.n_hmm <= 0 || c->p.n_hmm % n_chan) { set_error("b200_hmm_eval_list_dev: the resident population (%d HMMs) is not a whole number of %d-channel trees", c->p.n_hmm, n_chan); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(c->device));
+    HmmList l{};
+    l.n_root = n_root; l.n_chan = n_chan; l.list_cap = list_cap; l.frame = d_frame; l.par = d_par; l.acl = d_acl; l.n_act = d_n_act;
+    l.senscr = d_senscr; l.best = d_best;
+    return hmm_launch_eval_list(c->c, c->p, l, c->p.n_hmm / n_chan, stream ? (cudaStream_t)stream : c->st);
+}
+
 // One launch of the persistent step kernel: n_frames frames, frame f on the scores at
 // d_senscr + ((frame0 + f) % n_cycle) * frame_stride.
 static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, int n_cycle, int n_frames, int32_t beam,

@@ -40,6 +40,17 @@ struct HmmRun {
 };
 int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run, cudaStream_t st);
 
+// eval_root_chan + eval_nonroot_chan over per-utterance channel lists (see hmm_eval_list_kernel)
+struct HmmList {
+    int n_root, n_chan, list_cap;
+    const int32_t *frame;      // [n_utt * n_chan] hmm_frame
+    const int32_t *par;        // [n_utt][8], par[0] = frame_idx (the b200_fwdtree_prune_* parameter rows)
+    const int32_t *acl, *n_act;
+    const int16_t *senscr;     // [n_utt][n_sen]
+    int32_t *best;             // [n_utt] out
+};
+int hmm_launch_eval_list(const HmmDev &c, const HmmPop &p, const HmmList &l, int n_utt, cudaStream_t st);
+
 int hmm_launch_normalize(const HmmPop &p, int n_emit, const int32_t *d_best_per_utt, const HmmFrame *fr, cudaStream_t st);
 int hmm_launch_clear_pruned(const HmmPop &p, int n_emit, const HmmFrame *fr, cudaStream_t st);
 int hmm_launch_enter(const HmmPop &p, const int32_t *d_idx, const int32_t *d_score, const int32_t *d_hist, int n,

@@ -746,6 +746,88 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
 #undef B200_HMM_NE
 
 
+// ------------------------------------------------------------ evaluation of a LIST of channels
+// eval_root_chan + eval_nonroot_chan (PS/ngram_search_fwdtree.c:598-634): hmm_vit_eval for the root
+// channels whose frame stamp is the current frame and for every entry of the frame's active list, the
+// best of their scores per utterance.  The population is n_utt copies of one lexical tree's channels
+// (channel c of utterance u = HMM u * n_chan + c), the lists are those fwdtree_prune_kernel writes
+// (csrc/fwdtree_prune.cu): evaluate and prune alternate on the device without a host copy of any
+// state.  Gathers by index: the senone scores and the transition table are read through L1 / L2.
+template <int NE>
+__global__ void __launch_bounds__(kHmmBlock)
+hmm_eval_list_kernel(HmmDev c, HmmPop p, HmmList l) {
+    __shared__ int32_t s_best[kHmmBlock / 32];
+    const int u = blockIdx.y, tid = threadIdx.x;
+    const int n_act = l.n_act[u];
+    const int e = blockIdx.x * kHmmBlock + tid;
+    if (blockIdx.x * kHmmBlock >= l.n_root + n_act) return;          // uniform
+    const int32_t fi = l.par[(size_t)u * 8];
+    const size_t base = (size_t)u * l.n_chan;
+    int32_t best = kWorstScore;
+    int ch = -1;
+    if (e < l.n_root) { if (l.frame[base + e] == fi) ch = e; }       // :604
+    else if (e < l.n_root + n_act) ch = l.acl[(size_t)u * l.list_cap + (e - l.n_root)];
+    if (ch >= 0) {
+        const size_t i = base + ch;
+        const int n = p.n_hmm;
+        const int16_t *sen = l.senscr + (size_t)u * c.n_sen;
+        HmmRegs h;
+#pragma unroll
+        for (int s = 0; s < NE; ++s) {
+            h.sc[s] = p.score[(size_t)s * n + i];
+            h.hi[s] = p.history[(size_t)s * n + i];
+            h.sid[s] = p.senid[(size_t)s * n + i];
+        }
+        h.out_sc = p.out_score[i];
+        h.out_hi = p.out_history[i];
+        const uint8_t *tp = c.tp + (int)p.tmatid[i] * NE * (NE + 1);
+        const bool mpx = p.mpx[i] != 0;
+        if (NE == 3) { if (mpx) eval3_mpx(h, tp, sen, c.sseq); else eval3(h, tp, sen); }
+        else if (NE == 5) { if (mpx) eval5_mpx(h, tp, sen, c.sseq); else eval5(h, tp, sen); }
+        else eval_any<NE>(h, tp, sen, c.sseq, mpx);
+#pragma unroll
+        for (int s = 0; s < NE; ++s) {
+            p.score[(size_t)s * n + i] = h.sc[s];
+            p.history[(size_t)s * n + i] = h.hi[s];
+        }
+        if (mpx) {
+#pragma unroll
+            for (int s = 1; s < NE; ++s) p.senid[(size_t)s * n + i] = h.sid[s];
+        }
+        p.out_score[i] = h.out_sc;
+        p.out_history[i] = h.out_hi;
+        p.bestscore[i] = h.best;
+        best = h.best;
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) s_best[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < kHmmBlock / 32; ++k) best = max(best, s_best[k]);
+        if (best > kWorstScore) atomicMax(&l.best[u], best);
+    }
+}
+
+__global__ void hmm_fill_kernel(int32_t *dst, int n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+int hmm_launch_eval_list(const HmmDev &c, const HmmPop &p, const HmmList &l, int n_utt, cudaStream_t st) {
+    hmm_fill_kernel<<<(n_utt + 255) / 256, 256, 0, st>>>(l.best, n_utt, kWorstScore);
+    B200_LAUNCH_CHECK();
+    const dim3 grid((l.n_root + l.list_cap + kHmmBlock - 1) / kHmmBlock, n_utt);
+    switch (c.n_emit) {
+        case 1: hmm_eval_list_kernel<1><<<grid, kHmmBlock, 0, st>>>(c, p, l); break;
+        case 2: hmm_eval_list_kernel<2><<<grid, kHmmBlock, 0, st>>>(c, p, l); break;
+        case 3: hmm_eval_list_kernel<3><<<grid, kHmmBlock, 0, st>>>(c, p, l); break;
+        case 4: hmm_eval_list_kernel<4><<<grid, kHmmBlock, 0, st>>>(c, p, l); break;
+        default: hmm_eval_list_kernel<5><<<grid, kHmmBlock, 0, st>>>(c, p, l); break;
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 // ------------------------------------------------------------ maintenance
 // hmm_normalize (PS/hmm.c:207-218) for the whole population: every state score
 // and exit score that is BETTER_THAN WORST_SCORE loses its utterance's value.

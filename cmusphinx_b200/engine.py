@@ -521,6 +521,97 @@ class ChanTree:
         return [nacl[u, :n_nacl[u]].copy() for u in range(n_utt)], [cand[u, :n_cand[u]].copy() for u in range(n_utt)]
 
 
+class FwdtreeDevice:
+    """The tree-internal part of one forward-tree frame, resident on the device for a batch of utterances:
+    evaluate_channels' eval_root_chan + eval_nonroot_chan (b200_hmm_eval_list_dev) and prune_channels'
+    prune_root_chan + prune_nonroot_chan (b200_fwdtree_prune_dev) alternate on the channel states of an
+    HmmContext's resident population; the active list one stage writes is the list the next one reads.  What
+    crosses the host link per frame: senone scores in, per-utterance best / list lengths / last-phone
+    candidates out (the LM-dependent last_phone_transition and word_transition stay on the host)."""
+
+    def __init__(self, tree: "ChanTree", ctx: "HmmContext", n_utt: int, frame: np.ndarray):
+        self.tree, self.ctx, self.n_utt = tree, ctx, n_utt
+        nc = tree.n_chan
+        self.cap, self.ccap = max(1, nc - tree.n_root), max(1, tree.cand_cap)
+        sizes = dict(frame=n_utt * nc * 4, par=n_utt * 32, pen=n_utt * tree.n_ci * 4, acl0=n_utt * self.cap * 4,
+                     acl1=n_utt * self.cap * 4, n0=n_utt * 4, n1=n_utt * 4, cand=n_utt * self.ccap * 12, n_cand=n_utt * 4,
+                     best=n_utt * 4, senscr=n_utt * ctx.n_sen * 2)
+        self.d = {k: lib.b200_dev_alloc(v, 0) for k, v in sizes.items()}
+        if not all(self.d.values()):
+            raise B200Error("device allocation failed")
+        self.cur = 0
+        frame = _c(frame, np.int32)
+        assert frame.size == n_utt * nc
+        check(lib.b200_dev_upload(self.d["frame"], frame.ctypes.data, frame.nbytes), "upload")
+        self.set_lists([np.zeros(0, np.int32)] * n_utt)
+
+    def free(self):
+        for v in self.d.values():
+            lib.b200_dev_free(v)
+        self.d = {}
+
+    def _up(self, key, a):
+        check(lib.b200_dev_upload(self.d[key], a.ctypes.data, a.nbytes), "upload")
+
+    def _down(self, key, a):
+        check(lib.b200_dev_download(a.ctypes.data, self.d[key], a.nbytes), "download")
+        return a
+
+    def set_lists(self, lists):
+        acl = np.zeros((self.n_utt, self.cap), np.int32)
+        n = np.array([len(l) for l in lists], np.int32)
+        for u, l in enumerate(lists):
+            acl[u, :len(l)] = l
+        self._up(f"acl{self.cur}", acl)
+        self._up(f"n{self.cur}", n)
+
+    def lists(self):
+        acl = self._down(f"acl{self.cur}", np.zeros((self.n_utt, self.cap), np.int32))
+        n = self._down(f"n{self.cur}", np.zeros(self.n_utt, np.int32))
+        return [acl[u, :n[u]].copy() for u in range(self.n_utt)]
+
+    def frame_stamps(self):
+        return self._down("frame", np.zeros(self.n_utt * self.tree.n_chan, np.int32))
+
+    def set_frame_stamps(self, frame):
+        self._up("frame", _c(frame, np.int32))
+
+    def evaluate(self, senscr, frame_idx):
+        """-> best[n_utt] over the evaluated tree channels (the caller folds in its word channels)."""
+        par = np.zeros((self.n_utt, 8), np.int32)
+        par[:, 0] = frame_idx
+        self._up("par", par)
+        self._up("senscr", _c(senscr, np.int16).reshape(self.n_utt, self.ctx.n_sen))
+        t = self.tree
+        check(lib.b200_hmm_eval_list_dev(self.ctx._h, t.n_root, t.n_chan, self.d["frame"], self.d["par"], self.d[f"acl{self.cur}"],
+                                         self.d[f"n{self.cur}"], self.cap, self.d["senscr"], self.d["best"], None), "hmm_eval_list_dev")
+        check(lib.b200_dev_sync(0), "sync")
+        return self._down("best", np.zeros(self.n_utt, np.int32))
+
+    def prune(self, par, pls_pen=None):
+        """par [n_utt][8] (ChanTree.PAR order).  -> list of candidate arrays; the next list stays on the device."""
+        par = _c(par, np.int32).reshape(self.n_utt, 8)
+        self._up("par", par)
+        if pls_pen is not None:
+            self._up("pen", _c(pls_pen, np.int32).reshape(self.n_utt, self.tree.n_ci))
+        soa, st = self.ctx.device_arrays()
+        p = _lib.PruneDev()
+        as_vp = lambda x: C.cast(x, C.c_void_p)
+        p.score, p.history, p.out_score = as_vp(soa.score), as_vp(soa.history), as_vp(soa.out_score)
+        p.out_history, p.bestscore = as_vp(soa.out_history), as_vp(soa.bestscore)
+        p.frame, p.state_stride = self.d["frame"], soa.n_hmm
+        nxt = 1 - self.cur
+        p.par, p.pls_pen = self.d["par"], (self.d["pen"] if pls_pen is not None else None)
+        p.acl, p.n_act, p.list_cap = self.d[f"acl{self.cur}"], self.d[f"n{self.cur}"], self.cap
+        p.nacl, p.n_nacl, p.cand, p.n_cand, p.cand_cap = self.d[f"acl{nxt}"], self.d[f"n{nxt}"], self.d["cand"], self.d["n_cand"], self.ccap
+        check(lib.b200_fwdtree_prune_dev(self.tree._h, self.n_utt, C.byref(p), st), "fwdtree_prune_dev")
+        check(lib.b200_dev_sync(0), "sync")
+        self.cur = nxt
+        n_cand = self._down("n_cand", np.zeros(self.n_utt, np.int32))
+        cand = self._down("cand", np.zeros((self.n_utt, self.ccap, 3), np.int32))
+        return [cand[u, :n_cand[u]].copy() for u in range(self.n_utt)]
+
+
 def s3hmm_vit_eval(n_emit: int, tp, sseq, n_sen: int, senscr, score, history, out_score, out_history, ssid, tmatid, mpx,
                    bestscore, device: int = 0):
     """sphinx3's hmm_vit_eval (libs3decoder/libam/hmm.c:852-873) for every HMM, once per row of

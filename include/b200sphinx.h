@@ -448,6 +448,16 @@ typedef struct {
     int32_t *cand, *n_cand;    /* [n_utt][cand_cap][3], [n_utt] */
     int32_t cand_cap;
 } b200_prune_dev_t;
+/* The stage in front of it, on the same lists: eval_root_chan + eval_nonroot_chan
+ * (PS/ngram_search_fwdtree.c:598-634) -- hmm_vit_eval for the root channels whose hmm_frame is
+ * the current frame (d_par[u][0]) and for every entry of the active list, on the RESIDENT
+ * population of `c` (n_utt copies of the tree's n_chan channels: b200_hmm_pop_upload), senone
+ * scores d_senscr [n_utt][n_sen]; d_best[u] = the best hmm_vit_eval result of utterance u
+ * (WORST_SCORE when nothing is active).  All pointers are device pointers.  Evaluate and prune
+ * alternate on the device: the list b200_fwdtree_prune_dev writes is the next frame's d_acl. */
+int  b200_hmm_eval_list_dev(b200_hmmctx_t *c, int n_root, int n_chan, const int32_t *d_frame, const int32_t *d_par,
+                            const int32_t *d_acl, const int32_t *d_n_act, int list_cap, const int16_t *d_senscr,
+                            int32_t *d_best, void *stream);
 int  b200_fwdtree_prune_dev(b200_chantree_t *t, int n_utt, const b200_prune_dev_t *d, void *stream);
 int  b200_fwdtree_prune_host(b200_chantree_t *t, int n_utt, const int32_t *par, const int32_t *pls_pen,
                              const int32_t *acl, const int32_t *n_act, int list_cap, int32_t *score,

@@ -418,3 +418,102 @@ def test_eval_then_prune_without_leaving_the_device():
         assert len(wn) > 100 and len(wc) > 10
     ctx.free()
     tree.free()
+
+
+@pytest.mark.gpu
+def test_frames_of_evaluate_and_prune_resident_on_the_device():
+    """Eight frames of the tree-internal part of the forward tree search for three utterances, device resident
+    (FwdtreeDevice: b200_hmm_eval_list_dev -> b200_fwdtree_prune_dev, the list one stage writes is the list the
+    next one reads), against the oracle doing the same with hmm_vit_eval on the listed channels
+    (eval_root_chan + eval_nonroot_chan, ngram_search_fwdtree.c:598-634) and the sequential prune walk.  The host
+    plays word_transition: it re-enters a few root channels every frame."""
+    import cmusphinx_b200 as b
+    from cmusphinx_b200 import synth
+    ne, n_sen, n_tmat, n_sseq, n_root, n_chan, n_utt, T = 3, 600, 10, 700, 30, 3000, 3, 8
+    rng = np.random.default_rng(21)
+    topo, _ = random_tree(rng, n_root, n_chan)
+    tree = b.ChanTree(n_root, n_chan, *[topo[k] for k in TOPO_KEYS], topo["n_ci"], n_emit=ne)
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n_utt * n_chan, ne, n_sen, n_tmat, n_sseq, seed=5, mpx_fraction=0.0)
+    frame = np.zeros(n_utt * n_chan, np.int32)
+    lists = []
+    for u in range(n_utt):
+        rows, acl, _, _ = random_frame(rng, topo, ne, frame=0, p_active=0.3)
+        sl = slice(u * n_chan, (u + 1) * n_chan)
+        d["score"][sl], d["history"][sl] = rows[:, 0:ne], rows[:, ne:2 * ne]
+        d["out_score"][sl], d["out_history"][sl], d["bestscore"][sl] = rows[:, 2 * ne], rows[:, 2 * ne + 1], rows[:, 2 * ne + 2]
+        d["mpx"][u * n_chan:u * n_chan + n_root] = 1
+        d["senid"][u * n_chan:u * n_chan + n_root] = rng.integers(0, n_sseq, (n_root, ne))
+        frame[sl] = rows[:, 2 * ne + 3]
+        lists.append(acl)
+    sen = np.stack([synth.senscr_frames(n_utt, n_sen, 50 + f) for f in range(T)])          # [T][n_utt][n_sen]
+    entries = [[(rng.choice(n_root, 4, replace=False), -rng.integers(0, 200, 4).astype(np.int32), rng.integers(0, 99, 4).astype(np.int32))
+                for _ in range(n_utt)] for _ in range(T)]
+    # ---- device
+    ctx = b.HmmContext(ne, tp, d["sseq"], n_sen)
+    pop = b.HmmPopulation(n_utt * n_chan, ne)
+    pop.score[:], pop.history[:], pop.senid[:] = d["score"].T, d["history"].T, d["senid"].T
+    pop.out_score[:], pop.out_history[:], pop.tmatid[:], pop.mpx[:] = d["out_score"], d["out_history"], d["tmatid"], d["mpx"]
+    pop.bestscore[:] = d["bestscore"]
+    ctx.upload(pop)
+    ctx.set_utts(np.arange(n_utt + 1) * n_chan)
+    dev = b.FwdtreeDevice(tree, ctx, n_utt, frame)
+    dev.set_lists(lists)
+    got_best, got_cand, got_lists = [], [], []
+    for f in range(T):
+        best = dev.evaluate(sen[f], f)
+        got_best.append(best.copy())
+        par = [[f, int(best[u]), -700, -600, -500, -5, -3, 0] for u in range(n_utt)]
+        got_cand.append(dev.prune(par))
+        got_lists.append(dev.lists())
+        # word_transition stand-in: hmm_enter of a few roots for the next frame (only if better, PS/ngram_search_fwdtree.c:1383)
+        fr = dev.frame_stamps()
+        idx = np.concatenate([u * n_chan + e[0] for u, e in enumerate(entries[f])]).astype(np.int32)
+        ctx.enter(idx, np.concatenate([e[1] for e in entries[f]]), np.concatenate([e[2] for e in entries[f]]))
+        for u, e in enumerate(entries[f]):
+            fr[u * n_chan + e[0]] = f + 1
+        dev.set_frame_stamps(fr)
+    ctx.download(pop)
+    frame_dev = dev.frame_stamps()
+    # ---- oracle
+    o = {k: v.copy() for k, v in d.items()}
+    fr_o = frame.copy()
+    cur = [l.copy() for l in lists]
+    n_eval = 0
+    for f in range(T):
+        for u in range(n_utt):
+            base = u * n_chan
+            roots = np.nonzero(fr_o[base:base + n_root] == f)[0]
+            ids = base + np.concatenate([roots, cur[u]]).astype(np.int64)
+            best = int(WORST)
+            if ids.size:
+                v = {k: np.ascontiguousarray(o[k][ids]) for k in ("score", "history", "out_score", "out_history", "senid", "tmatid", "mpx", "bestscore")}
+                orc.hmm_eval(orc.port.orc_hmm_eval_batch, ne, tp, d["sseq"], sen[f][u], v["score"], v["history"], v["out_score"],
+                             v["out_history"], v["senid"], v["tmatid"], v["mpx"], v["bestscore"])
+                for k in ("score", "history", "out_score", "out_history", "senid", "bestscore"):
+                    o[k][ids] = v[k]
+                best = int(v["bestscore"].max())
+                n_eval += ids.size
+            assert best == got_best[f][u], (f, u)
+            par = dict(frame=f, best_score=best, beam=-700, pbeam=-600, lpbeam=-500, pip=-5, nwpen=-3, has_pls=0)
+            sl = slice(base, base + n_chan)
+            soa = dict(score=np.ascontiguousarray(o["score"][sl].T), history=np.ascontiguousarray(o["history"][sl].T),
+                       out_score=o["out_score"][sl].copy(), out_history=o["out_history"][sl].copy(), bestscore=o["bestscore"][sl].copy(),
+                       frame=fr_o[sl].copy())
+            s2, nacl, cand = orc.port_fwdtree_prune(topo, par, np.zeros(topo["n_ci"], np.int32), cur[u], soa)
+            o["score"][sl], o["history"][sl] = s2["score"].T, s2["history"].T
+            o["out_score"][sl], o["bestscore"][sl], fr_o[sl] = s2["out_score"], s2["bestscore"], s2["frame"]
+            assert np.array_equal(nacl, got_lists[f][u]), (f, u, "list")
+            assert np.array_equal(cand, got_cand[f][u]), (f, u, "candidates")
+            cur[u] = nacl
+            r, sc, hi = entries[f][u]
+            for k in range(len(r)):                              # hmm_enter if better, list order
+                i = base + r[k]
+                if sc[k] > o["score"][i, 0]:
+                    o["score"][i, 0], o["history"][i, 0] = sc[k], hi[k]
+                fr_o[i] = f + 1
+    assert n_eval > 2000
+    assert np.array_equal(pop.score.T, o["score"]) and np.array_equal(pop.history.T, o["history"])
+    assert np.array_equal(pop.out_score, o["out_score"]) and np.array_equal(pop.bestscore, o["bestscore"])
+    assert np.array_equal(frame_dev, fr_o)
+    dev.free(); ctx.free(); tree.free()
