@@ -135,6 +135,50 @@ def run(utts=128, steps=30, warmup=5, cpu=True):
                         "frac": bytes_model / t / 1e9 / peak, "traffic": None,
                         "bytes_model": "70 B per walk element + 22 B per child of a surviving element (bench_prune.py docstring)",
                         "note": "one CTA per utterance: latency bound by the three dependent phases, not by HBM"}}
+    # ---- the stage in front of it on the same lists: eval_root_chan + eval_nonroot_chan (b200_hmm_eval_list_dev) on the
+    # resident population of an HmmContext (synthetic senone ids / transition matrices for the tree's channels)
+    try:
+        from cmusphinx_b200 import synth
+        from cmusphinx_b200.engine import LOGBASE
+        n_sen, n_tmat, n_sseq = 5000, 50, 27000
+        tp = b.tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, LOGBASE)
+        dd = synth.hmm_population(B * nc, ne, n_sen, n_tmat, n_sseq, seed=42, mpx_fraction=0.0)
+        pop = b.HmmPopulation(B * nc, ne)
+        pop.score[:] = rows[:, :, 0:3].transpose(2, 0, 1).reshape(3, B * nc)
+        pop.history[:] = rows[:, :, 3:6].transpose(2, 0, 1).reshape(3, B * nc)
+        pop.out_score[:], pop.out_history[:], pop.bestscore[:] = rows[:, :, 6].reshape(-1), rows[:, :, 7].reshape(-1), rows[:, :, 8].reshape(-1)
+        pop.senid[:], pop.tmatid[:] = dd["senid"].T, dd["tmatid"]
+        mp = np.zeros((B, nc), np.uint8); mp[:, :nr] = 1                    # the roots are multiplex HMMs
+        pop.mpx[:] = mp.reshape(-1)
+        sid = pop.senid.reshape(ne, B, nc); sid[:, :, :nr] = np.random.default_rng(3).integers(0, n_sseq, (ne, B, nr))
+        ctx = b.HmmContext(ne, tp, dd["sseq"], n_sen)
+        d_sen = T(synth.senscr_frames(B, n_sen, 99))
+        d_best = torch.zeros(B, dtype=torch.int32, device=dev)
+        ems = []
+        n_eval = sum(len(c["acl"]) + int((c["state"][:nr, 9] == int(c["par"][0])).sum()) for c in pick)
+        for it in range(3 + 10):
+            ctx.upload(pop)
+            ctx.set_utts(np.arange(B + 1, dtype=np.int32) * nc)
+            with torch.cuda.stream(side):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                _lib.check(b.lib.b200_hmm_eval_list_dev(ctx._h, nr, nc, pristine["frame"].data_ptr(), d_par.data_ptr(), d_acl.data_ptr(),
+                                                         d_nact.data_ptr(), cap, d_sen.data_ptr(), d_best.data_ptr(), side.cuda_stream), "eval_list")
+                e1.record(side)
+                side.synchronize()
+            if it >= 3:
+                ems.append(e0.elapsed_time(e1))
+        te = float(np.mean(ems)) * 1e-3
+        out["eval_list"] = {"what": "eval_root_chan + eval_nonroot_chan on the same lists (b200_hmm_eval_list_dev), resident population of "
+                                    f"{B} x {nc} channels", "hmms_per_step": n_eval, "ms_per_step": te * 1e3,
+                            "value": n_eval / te, "unit": "HMM*frames/s",
+                            "roofline": {"bound": "hbm", "achieved": 72 * n_eval / te / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": 72 * n_eval / te / 1e9 / peak,
+                                         "bytes_model": "72 B per evaluated HMM (68 B of hmm_t fields + the list id), gathered by index"}}
+        out["tree_frame_us_per_utterance"] = (t + te) * 1e6 / B
+        ctx.free()
+    except Exception as ex:
+        out["eval_list"] = {"value": None, "note": f"failed: {ex!r}"}
     if cpu:
         try:
             out["cpu_baseline"] = cpu_port(topo, cases)
