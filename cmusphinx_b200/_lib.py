@@ -121,6 +121,8 @@ _sig("b200_chantree_create", vp, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i32
 _sig("b200_chantree_free", None, vp)
 _sig("b200_chantree_cand_cap", C.c_int, vp)
 _sig("b200_fwdtree_prune_dev", C.c_int, vp, C.c_int, C.POINTER(PruneDev), vp)
+_sig("b200_fwdtree_renorm_dev", C.c_int, vp, C.c_int, C.POINTER(PruneDev), vp, vp)
+_sig("b200_fwdtree_deactivate_dev", C.c_int, vp, C.c_int, C.POINTER(PruneDev), vp)
 _sig("b200_fwdtree_prune_host", C.c_int, vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p,
      c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int)
 _sig("b200_s3_create", vp, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, C.c_double, C.c_double, C.c_double,

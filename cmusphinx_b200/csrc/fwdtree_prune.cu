@@ -231,6 +231,37 @@ __global__ void __launch_bounds__(kPruneThreads) fwdtree_prune_kernel(PruneTree 
     }
 }
 
+// The two other places where ngram_fwdtree_search touches the tree's channels:
+//   mode 0  renormalize_scores (ngram_search_fwdtree.c:557-576, the tree part): hmm_normalize (hmm.c:205-216) of
+//           the roots stamped with the current frame and of every active-list entry, norm[u] = the
+//           utterance's best score;
+//   mode 1  deactivate_channels (:1418-1431): hmm_clear_scores of the roots still stamped with the
+//           current frame after word_transition (the ones prune_root_chan did not keep).
+__global__ void __launch_bounds__(256) fwdtree_maint_kernel(PruneTree tr, PruneArgs a, const int32_t *norm, int mode) {
+    const int u = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int n_act = mode == 0 ? a.n_act[u] : 0;
+    if (e >= tr.n_root + n_act) return;
+    const size_t base = (size_t)u * tr.n_chan;
+    const int32_t fi = a.par[(size_t)u * 8];
+    int c;
+    if (e < tr.n_root) { if (a.frame[base + e] != fi) return; c = e; }
+    else c = a.acl[(size_t)u * a.list_cap + (e - tr.n_root)];
+    if (mode == 0) {
+        const int32_t b = norm[u];
+        for (int s = 0; s < a.ne; ++s) {
+            const int32_t v = a.score[(size_t)s * a.stride + base + c];
+            if (v > kWorst) a.score[(size_t)s * a.stride + base + c] = v - b;
+        }
+        const int32_t o = a.out_score[base + c];
+        if (o > kWorst) a.out_score[base + c] = o - b;
+    } else {
+        for (int s = 0; s < a.ne; ++s) a.score[(size_t)s * a.stride + base + c] = kWorst;
+        a.out_score[base + c] = kWorst;
+        a.bestscore[base + c] = kWorst;
+    }
+}
+
 }  // namespace
 
 }  // namespace b200
@@ -421,4 +452,27 @@ extern "C" int b200_fwdtree_prune_host(b200_chantree_t *h, int n_utt, const int3
             return B200_ERR_ARG;
         }
     return B200_OK;
+}
+
+static int fwdtree_maint(b200_chantree_t *h, int n_utt, const b200_prune_dev_t *d, const int32_t *d_norm, int mode, void *stream) {
+    if (!h || !d || n_utt < 1 || !d->score || !d->out_score || !d->bestscore || !d->frame || !d->par ||
+        (mode == 0 && (!d_norm || !d->n_act || d->list_cap < 0 || (d->list_cap && !d->acl))) ||
+        d->state_stride < (long)n_utt * h->t.n_chan) { set_error("b200_fwdtree_renorm_dev / _deactivate_dev: bad argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    PruneArgs a{};
+    a.ne = h->n_emit; a.stride = d->state_stride;
+    a.score = d->score; a.history = d->history; a.out_score = d->out_score; a.out_history = d->out_history;
+    a.bestscore = d->bestscore; a.frame = d->frame; a.par = d->par; a.acl = d->acl; a.n_act = d->n_act; a.list_cap = d->list_cap;
+    const int elems = h->t.n_root + (mode == 0 ? d->list_cap : 0);
+    fwdtree_maint_kernel<<<dim3((elems + 255) / 256, n_utt), 256, 0, (cudaStream_t)stream>>>(h->t, a, d_norm, mode);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_fwdtree_renorm_dev(b200_chantree_t *h, int n_utt, const b200_prune_dev_t *d, const int32_t *d_norm, void *stream) {
+    return fwdtree_maint(h, n_utt, d, d_norm, 0, stream);
+}
+
+extern "C" int b200_fwdtree_deactivate_dev(b200_chantree_t *h, int n_utt, const b200_prune_dev_t *d, void *stream) {
+    return fwdtree_maint(h, n_utt, d, nullptr, 1, stream);
 }

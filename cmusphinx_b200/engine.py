@@ -588,21 +588,44 @@ class FwdtreeDevice:
         check(lib.b200_dev_sync(0), "sync")
         return self._down("best", np.zeros(self.n_utt, np.int32))
 
-    def prune(self, par, pls_pen=None):
-        """par [n_utt][8] (ChanTree.PAR order).  -> list of candidate arrays; the next list stays on the device."""
-        par = _c(par, np.int32).reshape(self.n_utt, 8)
-        self._up("par", par)
-        if pls_pen is not None:
-            self._up("pen", _c(pls_pen, np.int32).reshape(self.n_utt, self.tree.n_ci))
+    def _args(self, with_pen=False):
         soa, st = self.ctx.device_arrays()
         p = _lib.PruneDev()
         as_vp = lambda x: C.cast(x, C.c_void_p)
         p.score, p.history, p.out_score = as_vp(soa.score), as_vp(soa.history), as_vp(soa.out_score)
         p.out_history, p.bestscore = as_vp(soa.out_history), as_vp(soa.bestscore)
         p.frame, p.state_stride = self.d["frame"], soa.n_hmm
-        nxt = 1 - self.cur
-        p.par, p.pls_pen = self.d["par"], (self.d["pen"] if pls_pen is not None else None)
+        p.par, p.pls_pen = self.d["par"], (self.d["pen"] if with_pen else None)
         p.acl, p.n_act, p.list_cap = self.d[f"acl{self.cur}"], self.d[f"n{self.cur}"], self.cap
+        return p, st
+
+    def renormalize(self, frame_idx, norm):
+        """renormalize_scores' tree part (ngram_search_fwdtree.c:557-576) by norm[n_utt]."""
+        par = np.zeros((self.n_utt, 8), np.int32)
+        par[:, 0] = frame_idx
+        self._up("par", par)
+        self._up("best", _c(norm, np.int32))
+        p, st = self._args()
+        check(lib.b200_fwdtree_renorm_dev(self.tree._h, self.n_utt, C.byref(p), self.d["best"], st), "fwdtree_renorm_dev")
+        check(lib.b200_dev_sync(0), "sync")
+
+    def deactivate(self, frame_idx):
+        """deactivate_channels' root loop (ngram_search_fwdtree.c:1418-1431)."""
+        par = np.zeros((self.n_utt, 8), np.int32)
+        par[:, 0] = frame_idx
+        self._up("par", par)
+        p, st = self._args()
+        check(lib.b200_fwdtree_deactivate_dev(self.tree._h, self.n_utt, C.byref(p), st), "fwdtree_deactivate_dev")
+        check(lib.b200_dev_sync(0), "sync")
+
+    def prune(self, par, pls_pen=None):
+        """par [n_utt][8] (ChanTree.PAR order).  -> list of candidate arrays; the next list stays on the device."""
+        par = _c(par, np.int32).reshape(self.n_utt, 8)
+        self._up("par", par)
+        if pls_pen is not None:
+            self._up("pen", _c(pls_pen, np.int32).reshape(self.n_utt, self.tree.n_ci))
+        p, st = self._args(pls_pen is not None)
+        nxt = 1 - self.cur
         p.nacl, p.n_nacl, p.cand, p.n_cand, p.cand_cap = self.d[f"acl{nxt}"], self.d[f"n{nxt}"], self.d["cand"], self.d["n_cand"], self.ccap
         check(lib.b200_fwdtree_prune_dev(self.tree._h, self.n_utt, C.byref(p), st), "fwdtree_prune_dev")
         check(lib.b200_dev_sync(0), "sync")

@@ -459,6 +459,13 @@ int  b200_hmm_eval_list_dev(b200_hmmctx_t *c, int n_root, int n_chan, const int3
                             const int32_t *d_acl, const int32_t *d_n_act, int list_cap, const int16_t *d_senscr,
                             int32_t *d_best, void *stream);
 int  b200_fwdtree_prune_dev(b200_chantree_t *t, int n_utt, const b200_prune_dev_t *d, void *stream);
+/* The two other places where ngram_fwdtree_search touches the tree's channels, on the same arrays
+ * (only score / out_score / bestscore / frame / par / acl / n_act / list_cap of `d` are read):
+ * renormalize_scores' tree part (PS/ngram_search_fwdtree.c:557-576: hmm_normalize of the roots stamped
+ * with the current frame and of the active list, by d_norm[u]) and deactivate_channels' root loop
+ * (:1418-1431: hmm_clear_scores of the roots still stamped with the current frame). */
+int  b200_fwdtree_renorm_dev(b200_chantree_t *t, int n_utt, const b200_prune_dev_t *d, const int32_t *d_norm, void *stream);
+int  b200_fwdtree_deactivate_dev(b200_chantree_t *t, int n_utt, const b200_prune_dev_t *d, void *stream);
 int  b200_fwdtree_prune_host(b200_chantree_t *t, int n_utt, const int32_t *par, const int32_t *pls_pen,
                              const int32_t *acl, const int32_t *n_act, int list_cap, int32_t *score,
                              int32_t *history, int32_t *out_score, int32_t *out_history, int32_t *bestscore,

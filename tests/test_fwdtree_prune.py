@@ -517,3 +517,60 @@ def test_frames_of_evaluate_and_prune_resident_on_the_device():
     assert np.array_equal(pop.out_score, o["out_score"]) and np.array_equal(pop.bestscore, o["bestscore"])
     assert np.array_equal(frame_dev, fr_o)
     dev.free(); ctx.free(); tree.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+def test_renormalize_and_deactivate_on_the_device():
+    """renormalize_scores' tree part (ngram_search_fwdtree.c:557-576) and deactivate_channels' root loop
+    (:1418-1431) on the resident population, against the reference's OWN hmm_normalize / hmm_clear_scores
+    (oracle/ref_shim.c ref_hmm_maint) applied to the channels those loops visit."""
+    import cmusphinx_b200 as b
+    from cmusphinx_b200 import synth
+    ne, n_sen, n_root, n_chan, n_utt, f = 3, 300, 25, 2000, 2, 9
+    rng = np.random.default_rng(31)
+    topo, _ = random_tree(rng, n_root, n_chan)
+    tree = b.ChanTree(n_root, n_chan, *[topo[k] for k in TOPO_KEYS], topo["n_ci"], n_emit=ne)
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(4, ne, 7), 1e-4, orc.LOGBASE)
+    pop = b.HmmPopulation(n_utt * n_chan, ne)
+    frame = np.zeros(n_utt * n_chan, np.int32)
+    lists = []
+    for u in range(n_utt):
+        rows, acl, _, _ = random_frame(rng, topo, ne, frame=f, p_active=0.5)
+        sl = slice(u * n_chan, (u + 1) * n_chan)
+        pop.score[:, sl], pop.history[:, sl] = rows[:, 0:ne].T, rows[:, ne:2 * ne].T
+        pop.out_score[sl], pop.out_history[sl], pop.bestscore[sl], frame[sl] = rows[:, 2 * ne], rows[:, 2 * ne + 1], rows[:, 2 * ne + 2], rows[:, 2 * ne + 3]
+        lists.append(acl)
+    before = {k: getattr(pop, k).copy() for k in ("score", "history", "out_score", "out_history", "bestscore")}
+    ctx = b.HmmContext(ne, tp, None, n_sen)
+    ctx.upload(pop)
+    ctx.set_utts(np.arange(n_utt + 1) * n_chan)
+    dev = b.FwdtreeDevice(tree, ctx, n_utt, frame)
+    dev.set_lists(lists)
+    norm = np.array([-777, -31], np.int32)
+
+    def reference(op, visited, arg):
+        sel = np.zeros(n_utt * n_chan, np.uint8)
+        sel[visited] = 1
+        a = np.zeros(n_utt * n_chan, np.int32)
+        a[visited] = arg[visited // n_chan]                      # hmm_normalize by 0 leaves the others alone
+        return orc.ref_hmm_maint(op, np.ascontiguousarray(cur["score"].T), np.ascontiguousarray(cur["history"].T), cur["out_score"],
+                                 cur["out_history"], cur["bestscore"], sel=sel, arg=a)
+
+    cur = before
+    roots = np.concatenate([u * n_chan + np.nonzero(frame[u * n_chan:u * n_chan + n_root] == f)[0] for u in range(n_utt)])
+    listed = np.concatenate([u * n_chan + lists[u] for u in range(n_utt)])
+    assert roots.size > 5 and listed.size > 500
+    dev.renormalize(f, norm)
+    sc, hi, os_, oh, bs = reference(1, np.concatenate([roots, listed]), norm)
+    ctx.download(pop)
+    assert np.array_equal(pop.score.T, sc) and np.array_equal(pop.out_score, os_) and np.array_equal(pop.bestscore, bs)
+    assert not np.array_equal(pop.score, before["score"])
+    cur = dict(score=pop.score.copy(), history=pop.history.copy(), out_score=pop.out_score.copy(), out_history=pop.out_history.copy(),
+               bestscore=pop.bestscore.copy())
+    dev.deactivate(f)
+    sc, hi, os_, oh, bs = reference(0, roots, norm)
+    ctx.download(pop)
+    assert np.array_equal(pop.score.T, sc) and np.array_equal(pop.out_score, os_) and np.array_equal(pop.bestscore, bs)
+    assert np.array_equal(pop.history.T, hi) and (pop.score[:, roots] == WORST).all()
+    dev.free(); ctx.free(); tree.free()
