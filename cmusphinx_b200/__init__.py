@@ -13,7 +13,7 @@ from .engine import (  # noqa: F401
     semi_from_arrays, tied_from_model_dir, HmmContext, HmmPopulation,
     logadd_table, gauden_precompute, mixw_quantize_ms, mixw_quantize_tied,
     tmat_quantize, flags2list, read_gauden, read_mixw, read_tmat, read_sendump,
-    device_count, launch_count, S3Mgau, s3hmm_vit_eval, read_s3_cont_arrays, feat_1s_c_d_dd, feat_compute, FEAT_TYPES, sen_write, sen_read, mdef_maps, ChanTree, FwdtreeDevice,
+    device_count, launch_count, S3Mgau, s3hmm_vit_eval, read_s3_cont_arrays, feat_1s_c_d_dd, feat_compute, FEAT_TYPES, sen_write, sen_read, mdef_maps, ChanTree, FwdtreeDevice, PhoneLoop,
 )
 from . import s3io, synth, shard  # noqa: F401
 

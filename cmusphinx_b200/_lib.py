@@ -117,6 +117,13 @@ class PruneDev(C.Structure):
 
 _sig("b200_hmm_pop_device", C.c_int, vp, C.POINTER(HmmSoa), C.POINTER(vp))
 _sig("b200_hmm_eval_list_dev", C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp)
+_sig("b200_phone_loop_create", vp, C.c_int, C.c_int, c_u8p, C.c_int, c_u16p, c_i16p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int)
+_sig("b200_phone_loop_free", None, vp)
+_sig("b200_phone_loop_start", C.c_int, vp)
+_sig("b200_phone_loop_set_state", C.c_int, vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p)
+_sig("b200_phone_loop_get_state", C.c_int, vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p)
+_sig("b200_phone_loop_step_dev", C.c_int, vp, vp, C.c_int, vp, vp)
+_sig("b200_phone_loop_step_host", C.c_int, vp, c_i16p, C.c_int, c_i32p, c_i32p)
 _sig("b200_chantree_create", vp, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int, C.c_int)
 _sig("b200_chantree_free", None, vp)
 _sig("b200_chantree_cand_cap", C.c_int, vp)

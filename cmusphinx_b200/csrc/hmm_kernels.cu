@@ -936,4 +936,246 @@ int hmm_launch_enter(const HmmPop &p, const int32_t *d_idx, const int32_t *d_sco
     return B200_OK;
 }
 
+// ------------------------------------------------------------ phone-loop look-ahead search
+// phone_loop_search_step (PS/phone_loop_search.c:253-291) minus its acmod calls, for a batch of utterances
+// in lock step: renormalize_hmms (:171-184) when best + 2 beam underflows, evaluate_hmms (:186-210),
+// prune_hmms (:212-233), phone_transition (:235-268), and the look-ahead penalties the forward tree
+// search reads through phone_loop_search_score (PS/phone_loop_search.h:104).  One CTA per utterance, one
+// thread per CI phone.  phone_transition is a double loop whose inner test reads what earlier sources
+// wrote: it is kept sequential over the SOURCE phone (a block-uniform loop of n_phones steps) and parallel
+// over the target, which reproduces the reference for any input.
+struct PhoneLoop {
+    int n_phones, n_emit, n_sen, n_utt;
+    const uint8_t *tp; const uint16_t *senid;     // [n_emit][n_phones], shared by the utterances
+    const int16_t *tmatid;
+    int32_t *score, *history;                     // [n_emit][n_utt * n_phones]
+    int32_t *out_score, *out_history, *bestscore, *frame;
+    int32_t *best;                                // [n_utt] pls->best_score
+    int32_t *renorm;                              // [n_utt] norm applied this frame, or 0
+    int32_t beam, pbeam, pip;
+};
+
+template <int NE>
+__global__ void __launch_bounds__(1024)
+phone_loop_step_kernel(PhoneLoop q, const int16_t *__restrict__ senscr_all, int frame_idx, int32_t *__restrict__ pls_pen) {
+    extern __shared__ int32_t sm_pl[];
+    int32_t *s_frame = sm_pl, *s_out = sm_pl + q.n_phones, *s_outh = sm_pl + 2 * q.n_phones;
+    __shared__ int32_t s_red[32];
+    __shared__ int32_t s_best;
+    const int u = blockIdx.x, i = threadIdx.x, n = q.n_phones;
+    const size_t N = (size_t)q.n_utt * n, at = (size_t)u * n + i;
+    const bool on = i < n;
+    const int16_t *sen = senscr_all + (size_t)u * q.n_sen;
+    const int32_t nf = frame_idx + 1;
+    HmmRegs h; int32_t fr = -1;
+    if (on) {
+#pragma unroll
+        for (int s = 0; s < NE; ++s) { h.sc[s] = q.score[(size_t)s * N + at]; h.hi[s] = q.history[(size_t)s * N + at]; h.sid[s] = q.senid[(size_t)s * n + i]; }
+        h.out_sc = q.out_score[at]; h.out_hi = q.out_history[at]; h.best = q.bestscore[at];
+        fr = q.frame[at];
+    }
+    // renormalize_hmms
+    const int32_t prev_best = q.best[u];
+    int32_t norm = 0;
+    if (WT(prev_best + 2 * q.beam, kWorstScore)) {                       // :273
+        norm = prev_best;
+        if (on) {
+#pragma unroll
+            for (int s = 0; s < NE; ++s) if (BT(h.sc[s], kWorstScore)) h.sc[s] -= norm;
+            if (BT(h.out_sc, kWorstScore)) h.out_sc -= norm;
+        }
+    }
+    // evaluate_hmms
+    int32_t b = kWorstScore;
+    if (on && fr >= frame_idx) {                                         // :199
+        const uint8_t *tp = q.tp + (int)q.tmatid[i] * NE * (NE + 1);
+        if (NE == 3) eval3(h, tp, sen);
+        else if (NE == 5) eval5(h, tp, sen);
+        else eval_any<NE>(h, tp, sen, nullptr, false);
+        b = h.best;
+    }
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((i & 31) == 0) s_red[i >> 5] = b;
+    __syncthreads();
+    if (i == 0) {
+        int32_t m = s_red[0];
+        for (int k = 1; k < (int)((blockDim.x + 31) >> 5); ++k) m = max(m, s_red[k]);
+        s_best = m;
+    }
+    __syncthreads();
+    const int32_t bs = s_best;
+    // prune_hmms
+    if (on && fr >= frame_idx) {
+        if (BT(h.best, bs + q.beam)) fr = nf;
+        else {
+#pragma unroll
+            for (int s = 0; s < NE; ++s) h.sc[s] = kWorstScore;
+            h.out_sc = kWorstScore; h.best = kWorstScore;
+        }
+    }
+    if (on) { s_frame[i] = fr; s_out[i] = h.out_sc; s_outh[i] = h.out_hi; }
+    __syncthreads();
+    // phone_transition: sequential over the source, parallel over the target
+    const int32_t thresh = bs + q.pbeam;
+    for (int k = 0; k < n; ++k) {
+        const bool src = s_frame[k] == nf;                               // :248 (as the walk finds it)
+        const int32_t nps = s_out[k] + q.pip;
+        __syncthreads();
+        if (src && BT(nps, thresh) && on && (fr < frame_idx || BT(nps, h.sc[0]))) {   // :258-259
+            h.sc[0] = nps; h.hi[0] = s_outh[k]; fr = nf;
+            s_frame[i] = nf;
+        }
+        __syncthreads();
+    }
+    if (on) {
+#pragma unroll
+        for (int s = 0; s < NE; ++s) { q.score[(size_t)s * N + at] = h.sc[s]; q.history[(size_t)s * N + at] = h.hi[s]; }
+        q.out_score[at] = h.out_sc; q.out_history[at] = h.out_hi; q.bestscore[at] = h.best; q.frame[at] = fr;
+        if (pls_pen) pls_pen[at] = h.best - bs;                          // phone_loop_search_score
+    }
+    if (i == 0) { q.best[u] = bs; q.renorm[u] = norm; }
+}
+
 }  // namespace b200
+
+using namespace b200;
+
+struct b200_phoneloop {
+    PhoneLoop q{};
+    int device = 0;
+    std::vector<void *> owned;
+    int16_t *d_senscr = nullptr;      // host-form staging
+    int32_t *d_pen = nullptr;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+template <typename T>
+int pl_alloc(b200_phoneloop *h, T **dst, size_t n, const T *src) {
+    void *p = nullptr;
+    B200_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    h->owned.push_back(p);
+    if (src && n) B200_CUDA_OK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (T *)p;
+    return B200_OK;
+}
+}  // namespace
+
+extern "C" b200_phoneloop_t *b200_phone_loop_create(int n_phones, int n_emit, const uint8_t *tp, int n_tmat, const uint16_t *senid,
+                                                    const int16_t *tmatid, int n_sen, int32_t beam, int32_t pbeam, int32_t pip,
+                                                    int n_utt, int device) {
+    if (n_phones < 1 || n_phones > 1024 || n_emit < 1 || n_emit > 5 || !tp || n_tmat < 1 || !senid || !tmatid || n_sen < 1 || n_utt < 1) {
+        set_error("b200_phone_loop_create: bad argument"); return nullptr;
+    }
+    for (int i = 0; i < n_phones; ++i) {
+        if (tmatid[i] < 0 || tmatid[i] >= n_tmat) { set_error("b200_phone_loop_create: tmatid[%d] = %d", i, tmatid[i]); return nullptr; }
+        for (int s = 0; s < n_emit; ++s)
+            if (senid[(size_t)s * n_phones + i] >= n_sen) { set_error("b200_phone_loop_create: senid[%d][%d] out of range", s, i); return nullptr; }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libb200sphinx has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { set_error("bad device %d", device); return nullptr; }
+    auto *h = new b200_phoneloop;
+    h->device = device;
+    PhoneLoop &q = h->q;
+    q.n_phones = n_phones; q.n_emit = n_emit; q.n_sen = n_sen; q.n_utt = n_utt; q.beam = beam; q.pbeam = pbeam; q.pip = pip;
+    const size_t N = (size_t)n_utt * n_phones;
+    uint8_t *d_tp = nullptr; uint16_t *d_sid = nullptr; int16_t *d_tm = nullptr;
+    if (pl_alloc(h, &d_tp, (size_t)n_tmat * n_emit * (n_emit + 1), tp) || pl_alloc(h, &d_sid, (size_t)n_emit * n_phones, senid) ||
+        pl_alloc(h, &d_tm, (size_t)n_phones, tmatid) || pl_alloc<int32_t>(h, &q.score, N * n_emit, nullptr) ||
+        pl_alloc<int32_t>(h, &q.history, N * n_emit, nullptr) || pl_alloc<int32_t>(h, &q.out_score, N, nullptr) ||
+        pl_alloc<int32_t>(h, &q.out_history, N, nullptr) || pl_alloc<int32_t>(h, &q.bestscore, N, nullptr) ||
+        pl_alloc<int32_t>(h, &q.frame, N, nullptr) || pl_alloc<int32_t>(h, &q.best, (size_t)n_utt, nullptr) ||
+        pl_alloc<int32_t>(h, &q.renorm, (size_t)n_utt, nullptr) || pl_alloc<int16_t>(h, &h->d_senscr, (size_t)n_utt * n_sen, nullptr) ||
+        pl_alloc<int32_t>(h, &h->d_pen, N, nullptr) || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+        b200_phone_loop_free(h);
+        return nullptr;
+    }
+    q.tp = d_tp; q.senid = d_sid; q.tmatid = d_tm;
+    if (b200_phone_loop_start(h) != B200_OK) { b200_phone_loop_free(h); return nullptr; }
+    return h;
+}
+
+extern "C" void b200_phone_loop_free(b200_phoneloop_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void *p : h->owned) cudaFree(p);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+// phone_loop_search_start (:153-169): hmm_clear + hmm_enter(hmm, 0, -1, 0) for every phone, best_score = 0
+extern "C" int b200_phone_loop_start(b200_phoneloop_t *h) {
+    if (!h) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    const PhoneLoop &q = h->q;
+    const size_t N = (size_t)q.n_utt * q.n_phones;
+    std::vector<int32_t> sc(N * q.n_emit, kWorstScore), hi(N * q.n_emit, -1), w(N, kWorstScore), m1(N, -1), z(N, 0), zb(q.n_utt, 0);
+    std::fill(sc.begin(), sc.begin() + N, 0);                         // state 0 of every phone entered with score 0
+    return b200_phone_loop_set_state(h, sc.data(), hi.data(), w.data(), m1.data(), w.data(), z.data(), zb.data());
+}
+
+extern "C" int b200_phone_loop_set_state(b200_phoneloop_t *h, const int32_t *score, const int32_t *history, const int32_t *out_score,
+                                         const int32_t *out_history, const int32_t *bestscore, const int32_t *frame, const int32_t *best) {
+    if (!h || !score || !history || !out_score || !out_history || !bestscore || !frame || !best) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    const PhoneLoop &q = h->q;
+    const size_t N = (size_t)q.n_utt * q.n_phones;
+    B200_CUDA_OK(cudaStreamSynchronize(h->st));
+    B200_CUDA_OK(cudaMemcpy(q.score, score, N * q.n_emit * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.history, history, N * q.n_emit * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.out_score, out_score, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.out_history, out_history, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.bestscore, bestscore, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.frame, frame, N * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(q.best, best, (size_t)q.n_utt * 4, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+extern "C" int b200_phone_loop_get_state(b200_phoneloop_t *h, int32_t *score, int32_t *history, int32_t *out_score, int32_t *out_history,
+                                         int32_t *bestscore, int32_t *frame, int32_t *best, int32_t *renorm) {
+    if (!h) { set_error("null argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    const PhoneLoop &q = h->q;
+    const size_t N = (size_t)q.n_utt * q.n_phones;
+    B200_CUDA_OK(cudaStreamSynchronize(h->st));
+    if (score) B200_CUDA_OK(cudaMemcpy(score, q.score, N * q.n_emit * 4, cudaMemcpyDeviceToHost));
+    if (history) B200_CUDA_OK(cudaMemcpy(history, q.history, N * q.n_emit * 4, cudaMemcpyDeviceToHost));
+    if (out_score) B200_CUDA_OK(cudaMemcpy(out_score, q.out_score, N * 4, cudaMemcpyDeviceToHost));
+    if (out_history) B200_CUDA_OK(cudaMemcpy(out_history, q.out_history, N * 4, cudaMemcpyDeviceToHost));
+    if (bestscore) B200_CUDA_OK(cudaMemcpy(bestscore, q.bestscore, N * 4, cudaMemcpyDeviceToHost));
+    if (frame) B200_CUDA_OK(cudaMemcpy(frame, q.frame, N * 4, cudaMemcpyDeviceToHost));
+    if (best) B200_CUDA_OK(cudaMemcpy(best, q.best, (size_t)q.n_utt * 4, cudaMemcpyDeviceToHost));
+    if (renorm) B200_CUDA_OK(cudaMemcpy(renorm, q.renorm, (size_t)q.n_utt * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_phone_loop_step_dev(b200_phoneloop_t *h, const int16_t *d_senscr, int frame_idx, int32_t *d_pls_pen, void *stream) {
+    if (!h || !d_senscr || frame_idx < 0) { set_error("b200_phone_loop_step_dev: bad argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    const PhoneLoop &q = h->q;
+    const int threads = ((q.n_phones + 31) / 32) * 32;
+    const size_t sh = (size_t)3 * q.n_phones * 4;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->st;
+    switch (q.n_emit) {
+        case 1: phone_loop_step_kernel<1><<<q.n_utt, threads, sh, st>>>(q, d_senscr, frame_idx, d_pls_pen); break;
+        case 2: phone_loop_step_kernel<2><<<q.n_utt, threads, sh, st>>>(q, d_senscr, frame_idx, d_pls_pen); break;
+        case 3: phone_loop_step_kernel<3><<<q.n_utt, threads, sh, st>>>(q, d_senscr, frame_idx, d_pls_pen); break;
+        case 4: phone_loop_step_kernel<4><<<q.n_utt, threads, sh, st>>>(q, d_senscr, frame_idx, d_pls_pen); break;
+        default: phone_loop_step_kernel<5><<<q.n_utt, threads, sh, st>>>(q, d_senscr, frame_idx, d_pls_pen); break;
+    }
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_phone_loop_step_host(b200_phoneloop_t *h, const int16_t *senscr, int frame_idx, int32_t *pls_pen, int32_t *best) {
+    if (!h || !senscr) { set_error("b200_phone_loop_step_host: bad argument"); return B200_ERR_ARG; }
+    B200_CUDA_OK(cudaSetDevice(h->device));
+    const PhoneLoop &q = h->q;
+    B200_CUDA_OK(cudaMemcpyAsync(h->d_senscr, senscr, (size_t)q.n_utt * q.n_sen * 2, cudaMemcpyHostToDevice, h->st));
+    if (int rc = b200_phone_loop_step_dev(h, h->d_senscr, frame_idx, h->d_pen, h->st)) return rc;
+    B200_CUDA_OK(cudaStreamSynchronize(h->st));
+    if (pls_pen) B200_CUDA_OK(cudaMemcpy(pls_pen, h->d_pen, (size_t)q.n_utt * q.n_phones * 4, cudaMemcpyDeviceToHost));
+    if (best) B200_CUDA_OK(cudaMemcpy(best, q.best, (size_t)q.n_utt * 4, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}

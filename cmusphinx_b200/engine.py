@@ -635,6 +635,55 @@ class FwdtreeDevice:
         return [cand[u, :n_cand[u]].copy() for u in range(self.n_utt)]
 
 
+class PhoneLoop:
+    """The phone-loop look-ahead search (phone_loop_search.c) for n_utt utterances in lock step, its phone HMMs
+    resident on the device: start() = phone_loop_search_start, step() = phone_loop_search_step minus the acmod
+    calls; step returns (best_score [n_utt], pls_pen [n_utt][n_phones]) -- the penalties
+    phone_loop_search_score hands to prune_root_chan / prune_nonroot_chan."""
+
+    def __init__(self, tp, senid, tmatid, n_sen, beam, pbeam, pip, n_utt=1, device=0):
+        tp, senid, tmatid = _c(tp, np.uint8), _c(senid, np.uint16), _c(tmatid, np.int16)
+        self.n_emit, self.n_phones = senid.shape
+        assert tp.shape[1] == self.n_emit and tp.shape[2] == self.n_emit + 1
+        h = lib.b200_phone_loop_create(self.n_phones, self.n_emit, _p(tp, C.c_uint8), tp.shape[0], _p(senid, C.c_uint16),
+                                       _p(tmatid, C.c_int16), int(n_sen), int(beam), int(pbeam), int(pip), int(n_utt), device)
+        if not h:
+            raise B200Error(f"b200_phone_loop_create failed: {_lib.last_error()}")
+        self._h, self.n_utt, self.n_sen = C.c_void_p(h), int(n_utt), int(n_sen)
+
+    def free(self):
+        if self._h:
+            lib.b200_phone_loop_free(self._h)
+            self._h = None
+
+    def start(self):
+        check(lib.b200_phone_loop_start(self._h), "phone_loop_start")
+
+    def set_state(self, score, history, out_score, out_history, bestscore, frame, best):
+        a = [_c(x, np.int32) for x in (score, history, out_score, out_history, bestscore, frame, best)]
+        N = self.n_utt * self.n_phones
+        assert a[0].size == self.n_emit * N and a[2].size == N and a[6].size == self.n_utt
+        check(lib.b200_phone_loop_set_state(self._h, *[_p(x, C.c_int32) for x in a]), "phone_loop_set_state")
+
+    def state(self):
+        N = self.n_utt * self.n_phones
+        out = dict(score=np.zeros((self.n_emit, N), np.int32), history=np.zeros((self.n_emit, N), np.int32),
+                   out_score=np.zeros(N, np.int32), out_history=np.zeros(N, np.int32), bestscore=np.zeros(N, np.int32),
+                   frame=np.zeros(N, np.int32), best=np.zeros(self.n_utt, np.int32), renorm=np.zeros(self.n_utt, np.int32))
+        check(lib.b200_phone_loop_get_state(self._h, *[_p(out[k], C.c_int32) for k in
+                                                       ("score", "history", "out_score", "out_history", "bestscore", "frame", "best", "renorm")]),
+              "phone_loop_get_state")
+        return out
+
+    def step(self, senscr, frame_idx):
+        s = _c(senscr, np.int16).reshape(self.n_utt, self.n_sen)
+        pen = np.zeros((self.n_utt, self.n_phones), np.int32)
+        best = np.zeros(self.n_utt, np.int32)
+        check(lib.b200_phone_loop_step_host(self._h, _p(s, C.c_int16), int(frame_idx), _p(pen, C.c_int32), _p(best, C.c_int32)),
+              "phone_loop_step_host")
+        return best, pen
+
+
 def s3hmm_vit_eval(n_emit: int, tp, sseq, n_sen: int, senscr, score, history, out_score, out_history, ssid, tmatid, mpx,
                    bestscore, device: int = 0):
     """sphinx3's hmm_vit_eval (libs3decoder/libam/hmm.c:852-873) for every HMM, once per row of

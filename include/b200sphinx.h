@@ -472,6 +472,34 @@ int  b200_fwdtree_prune_host(b200_chantree_t *t, int n_utt, const int32_t *par, 
                              int32_t *frame, int32_t *nacl, int32_t *n_nacl, int32_t *cand, int32_t *n_cand,
                              int cand_cap);
 
+/* ----------------------------------------------------------------------------
+ * The phone-loop look-ahead search (-pl_window > 0; another caller of hmm_vit_eval,
+ * PS/phone_loop_search.c:201): phone_loop_search_step (:253-291) minus its acmod calls --
+ * renormalize_hmms (:171-184), evaluate_hmms (:186-210), prune_hmms (:212-233),
+ * phone_transition (:235-268) -- for n_utt utterances in lock step, the phone HMMs resident on
+ * the device; its product is what the forward tree search reads through
+ * phone_loop_search_score (PS/phone_loop_search.h:104): pls_pen[u][ci] =
+ * hmm_bestscore(phone ci) - best_score, the pls_pen input of b200_fwdtree_prune_*.
+ * create = phone_loop_search_reinit (:66-106): n_phones = bin_mdef_n_ciphone, non-mpx HMMs,
+ * senid [n_emit][n_phones] = sseq[pid2ssid(ci)], tmatid = pid2tmatid(ci), beam / pbeam / pip =
+ * logmath_log of -pl_beam / -pl_pbeam / -pip; start = phone_loop_search_start (:153-169).
+ * State arrays are state-major: score / history [n_emit][n_utt * n_phones], the rest
+ * [n_utt * n_phones]; best [n_utt] = pls->best_score; renorm [n_utt] = the norm the last step
+ * applied (0: none; the reference keeps them in pls->renorm). */
+typedef struct b200_phoneloop b200_phoneloop_t;
+b200_phoneloop_t *b200_phone_loop_create(int n_phones, int n_emit, const uint8_t *tp, int n_tmat, const uint16_t *senid,
+                                         const int16_t *tmatid, int n_sen, int32_t beam, int32_t pbeam, int32_t pip,
+                                         int n_utt, int device);
+void b200_phone_loop_free(b200_phoneloop_t *h);
+int  b200_phone_loop_start(b200_phoneloop_t *h);
+int  b200_phone_loop_set_state(b200_phoneloop_t *h, const int32_t *score, const int32_t *history, const int32_t *out_score,
+                               const int32_t *out_history, const int32_t *bestscore, const int32_t *frame, const int32_t *best);
+int  b200_phone_loop_get_state(b200_phoneloop_t *h, int32_t *score, int32_t *history, int32_t *out_score, int32_t *out_history,
+                               int32_t *bestscore, int32_t *frame, int32_t *best, int32_t *renorm);
+/* One frame.  senscr [n_utt][n_sen] int16 (device pointer for _dev); pls_pen [n_utt][n_phones] or NULL. */
+int  b200_phone_loop_step_dev(b200_phoneloop_t *h, const int16_t *d_senscr, int frame_idx, int32_t *d_pls_pen, void *stream);
+int  b200_phone_loop_step_host(b200_phoneloop_t *h, const int16_t *senscr, int frame_idx, int32_t *pls_pen, int32_t *best);
+
 /* acmod_flags2list (PS/acmod.c:1219-1271): bitmask -> uint8 delta list with
  * the reference's lossy >255 bridging.  Host utility; returns n written. */
 int  b200_flags2list(const uint32_t *mask, int n_sen, uint8_t *deltas, int max_out);

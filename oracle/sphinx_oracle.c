@@ -1929,3 +1929,56 @@ void orc_fwdtree_prune(int n_root, int n_chan, int ne, const int32_t *child_off,
     }
     *n_nacl = nn;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * phone_loop_search_step (phone_loop_search.c:253-291), see sphinx_oracle.h. */
+int32_t orc_phone_loop_step(int n_phones, int ne, const uint8_t *tp, const int16_t *senscr, int32_t *par,
+                            int32_t *score, int32_t *history, int32_t *out_score, int32_t *out_history,
+                            int32_t *bestscore, int32_t *frame, uint16_t *senid, const int16_t *tmatid,
+                            int32_t *renorm)
+{
+    const int32_t fi = par[0], nf = fi + 1, beam = par[2], pbeam = par[3], pip = par[4];
+    int32_t bs, thresh;
+    int i, j, s;
+    *renorm = 0;
+    if (par[1] + 2 * beam < W) {                                   /* :273: WORSE_THAN WORST_SCORE */
+        const int32_t norm = par[1];
+        *renorm = 1;
+        for (i = 0; i < n_phones; ++i) {                           /* hmm_normalize, hmm.c:205-216 */
+            for (s = 0; s < ne; ++s)
+                if (score[i * ne + s] > W) score[i * ne + s] -= norm;
+            if (out_score[i] > W) out_score[i] -= norm;
+        }
+    }
+    bs = W;                                                        /* evaluate_hmms :186-210 */
+    for (i = 0; i < n_phones; ++i) {
+        int32_t b;
+        if (frame[i] < fi) continue;
+        b = hmm_eval_one(ne, tp + (long)tmatid[i] * ne * (ne + 1), NULL, senscr, score + (long)i * ne,
+                         history + (long)i * ne, &out_score[i], &out_history[i], senid + (long)i * ne, 0);
+        bestscore[i] = b;
+        if (b > bs) bs = b;
+    }
+    par[1] = bs;
+    thresh = bs + beam;                                            /* prune_hmms :212-233 */
+    for (i = 0; i < n_phones; ++i) {
+        if (frame[i] < fi) continue;
+        if (bestscore[i] > thresh) frame[i] = nf;
+        else {
+            for (s = 0; s < ne; ++s) score[i * ne + s] = W;
+            out_score[i] = W; bestscore[i] = W;
+        }
+    }
+    thresh = bs + pbeam;                                           /* phone_transition :235-268 */
+    for (i = 0; i < n_phones; ++i) {
+        int32_t nps;
+        if (frame[i] != nf) continue;
+        nps = out_score[i] + pip;
+        if (nps > thresh)
+            for (j = 0; j < n_phones; ++j)
+                if (frame[j] < fi || nps > score[j * ne]) {
+                    score[j * ne] = nps; history[j * ne] = out_history[i]; frame[j] = nf;
+                }
+    }
+    return bs;
+}

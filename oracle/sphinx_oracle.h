@@ -187,6 +187,17 @@ void orc_fwdtree_prune(int n_root, int n_chan, int ne, const int32_t *child_off,
                        int32_t *out_history, int32_t *bestscore, int32_t *frame, int32_t *nacl, int32_t *n_nacl,
                        int32_t *cand, int32_t *n_cand);
 
+/* ---- the phone-loop look-ahead search, one frame: phone_loop_search_step (phone_loop_search.c:253-291)
+ * minus its acmod calls = renormalize_hmms (:171-184) if best + 2 beam underflows, evaluate_hmms
+ * (:186-210), prune_hmms (:212-233), phone_transition (:235-268).  HMM-major arrays ([n_phones][ne]),
+ * non-mpx HMMs, senid = senone ids into senscr.  par = {frame_idx, best_score, beam, pbeam, pip}:
+ * best_score is the previous frame's on entry and this frame's on return (also the return value);
+ * *renorm = 1 when the frame renormalised (by the previous best). */
+int32_t orc_phone_loop_step(int n_phones, int ne, const uint8_t *tp, const int16_t *senscr, int32_t *par,
+                            int32_t *score, int32_t *history, int32_t *out_score, int32_t *out_history,
+                            int32_t *bestscore, int32_t *frame, uint16_t *senid, const int16_t *tmatid,
+                            int32_t *renorm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,3 +37,26 @@ def read_trace(path):
         else:
             raise ValueError(f"bad record tag {tag!r} at {pos}")
     return out
+
+
+def read_pls_trace(path):
+    """Records of oracle/ref_pls_trace.c -> (tp [n_tmat][ne][ne+1] uint8, list of frame dicts).  The state in
+    record f+1 of an utterance is the reference's result for frame f."""
+    a = np.fromfile(path, dtype=np.int32)
+    pos, tp, out = 0, None, []
+    while pos < a.size:
+        tag = chr(int(a[pos])); pos += 1
+        if tag == "M":
+            n_tmat, ne = int(a[pos]), int(a[pos + 1]); pos += 2
+            tp = a[pos:pos + n_tmat * ne * (ne + 1)].reshape(n_tmat, ne, ne + 1).astype(np.uint8); pos += n_tmat * ne * (ne + 1)
+        elif tag == "P":
+            frame, best, beam, pbeam, pip, n, ne = (int(x) for x in a[pos:pos + 7]); pos += 7
+            w = 3 * ne + 5
+            rows = a[pos:pos + n * w].reshape(n, w).copy(); pos += n * w
+            sen = a[pos:pos + n * ne].reshape(n, ne).copy(); pos += n * ne
+            out.append(dict(frame=frame, best_score=best, beam=beam, pbeam=pbeam, pip=pip, ne=ne, score=rows[:, 0:ne], history=rows[:, ne:2 * ne],
+                            out_score=rows[:, 2 * ne], out_history=rows[:, 2 * ne + 1], bestscore=rows[:, 2 * ne + 2], frame_of=rows[:, 2 * ne + 3],
+                            senid=rows[:, 2 * ne + 4:3 * ne + 4], tmatid=rows[:, 3 * ne + 4], senscr=sen))
+        else:
+            raise ValueError(f"bad record tag {tag!r}")
+    return tp, out

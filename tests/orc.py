@@ -779,3 +779,25 @@ def port_fwdtree_prune(topo, par, pls_pen, acl, soa):
                         _p(s["out_score"], C.c_int32), _p(s["out_history"], C.c_int32), _p(s["bestscore"], C.c_int32),
                         _p(s["frame"], C.c_int32), _p(nacl, C.c_int32), C.byref(n1), _p(cand, C.c_int32), C.byref(n2))
     return s, nacl[:n1.value].copy(), cand[:n2.value].copy()
+
+
+# ---- phone-loop look-ahead search (phone_loop_search.c:253-291)
+def port_phone_loop_step(tp, rec):
+    """One frame through oracle/sphinx_oracle.c orc_phone_loop_step.  rec: a frame dict of
+    fwdtree_trace.read_pls_trace (state before the step, senscr [n_phones][ne] = the frame's score of every
+    state's senone).  -> dict of the state after the step (+ best_score, renorm)."""
+    L = _load_port()
+    n, ne = rec["score"].shape
+    tp = _c(tp, np.uint8)
+    sc, hi = _c(rec["score"], np.int32).copy(), _c(rec["history"], np.int32).copy()
+    os_, oh, bs, fr = (_c(rec[k], np.int32).copy() for k in ("out_score", "out_history", "bestscore", "frame_of"))
+    senscr = _c(rec["senscr"], np.int16).reshape(-1)                 # compact: senone of (phone i, state s) = i * ne + s
+    senid = np.arange(n * ne, dtype=np.uint16)
+    tm = _c(rec["tmatid"], np.int16)
+    par = np.array([rec["frame"], rec["best_score"], rec["beam"], rec["pbeam"], rec["pip"]], np.int32)
+    rn = C.c_int32(0)
+    L.orc_phone_loop_step.restype = C.c_int32
+    best = L.orc_phone_loop_step(C.c_int(n), C.c_int(ne), _p(tp, C.c_uint8), _p(senscr, C.c_int16), _p(par, C.c_int32), _p(sc, C.c_int32),
+                                 _p(hi, C.c_int32), _p(os_, C.c_int32), _p(oh, C.c_int32), _p(bs, C.c_int32), _p(fr, C.c_int32),
+                                 _p(senid, C.c_uint16), _p(tm, C.c_int16), C.byref(rn))
+    return dict(score=sc, history=hi, out_score=os_, out_history=oh, bestscore=bs, frame_of=fr, best_score=int(best), renorm=rn.value)
