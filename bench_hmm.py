@@ -47,15 +47,11 @@ def cpu_reference(d, tp, cpu_frames):
             "sample": f"{cpu_frames} frames x {N_HMM} HMMs ({dt:.1f} s), hmm_vit_eval only (no beam / gather), one core"}
 
 
-def run(utts=64, frames=200, warmup=80, single_steps=False, cpu=True, cpu_frames=200):
-    import torch
-    import cmusphinx_b200 as b
-    from cmusphinx_b200 import synth
-    from cmusphinx_b200.engine import LOGBASE
-    assert b.device_count() > 0
-    B = utts
-    tp = b.tmat_quantize(synth.bakis_tmat(N_TMAT, NE, 7), 1e-4, LOGBASE)
-    d = synth.hmm_population(N_HMM * B, NE, N_SEN, N_TMAT, N_SSEQ, seed=42, mpx_fraction=0.1)
+def _measure(b, torch, synth, d, tp, B, frames, warmup, single_steps, roots_first):
+    """One timed run of `frames` frames on the population d (roots_first: every utterance's multiplex HMMs first)."""
+    if roots_first:
+        order = np.concatenate([u * N_HMM + np.argsort(d["mpx"][u * N_HMM:(u + 1) * N_HMM] == 0, kind="stable") for u in range(B)])
+        d = {k: (np.ascontiguousarray(v[order]) if k != "sseq" else v) for k, v in d.items()}
     pop = b.HmmPopulation(N_HMM * B, NE)
     pop.score[:], pop.history[:], pop.senid[:] = d["score"].T, d["history"].T, d["senid"].T
     pop.out_score[:], pop.out_history[:], pop.tmatid[:], pop.mpx[:] = d["out_score"], d["out_history"], d["tmatid"], d["mpx"]
@@ -86,27 +82,49 @@ def run(utts=64, frames=200, warmup=80, single_steps=False, cpu=True, cpu_frames
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / frames
     launches = b.launch_count() - l0
+    _, nk1, _ = ctx.step_results(N_HMM * B, want_idx=False)
+    ctx.free()
+    del sen
+    torch.cuda.empty_cache()
+    return ms, launches, float(np.sum(nk0)) / (N_HMM * B), float(np.sum(nk1)) / (N_HMM * B)
+
+
+def run(utts=64, frames=200, warmup=80, single_steps=False, cpu=True, cpu_frames=200, both_layouts=True):
+    import torch
+    import cmusphinx_b200 as b
+    from cmusphinx_b200 import synth
+    from cmusphinx_b200.engine import LOGBASE
+    assert b.device_count() > 0
+    B = utts
+    tp = b.tmat_quantize(synth.bakis_tmat(N_TMAT, NE, 7), 1e-4, LOGBASE)
+    d = synth.hmm_population(N_HMM * B, NE, N_SEN, N_TMAT, N_SSEQ, seed=42, mpx_fraction=0.1)
+    # The headline layout keeps every utterance's multiplex HMMs (the 10 % "roots") ahead of the others, as the reference does:
+    # root channels live in their own array (ngram_search.h root_chan) and eval_root_chan / eval_nonroot_chan
+    # (ngram_search_fwdtree.c:598-634) are separate loops.  The same population with the two kinds interleaved at random
+    # (every warp then runs both hmm_vit_eval flavours) is timed beside it.
+    ms, launches, s0, s1 = _measure(b, torch, synth, d, tp, B, frames, warmup, single_steps, True)
     units = N_HMM * B
     value = units / (ms / 1e3)
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
     achieved = units * BYTES_PER_UNIT / (ms / 1e3) / 1e9
-    _, nk1, _ = ctx.step_results(N_HMM * B, want_idx=False)
     res = {
         "metric": "hmm_frames_evaluated_per_sec", "value": value, "unit": "HMM*frames/s", "n_gpus": 1,
         "steps": frames, "ms_per_step": ms, "us_per_frame": ms * 1e3, "higher_is_better": True, "dtype": "int32",
         "data": "synthetic",
         "config": {"workload": f"hmm_vit_eval_3st + beam + compaction + active-senone gather, {B} utterance(s) x {N_HMM} "
-                               "HMMs per frame (BASELINE configs[3])", "n_sen": N_SEN, "mpx_fraction": 0.1, "beam": BEAM},
+                               "HMMs per frame (BASELINE configs[3])", "n_sen": N_SEN, "mpx_fraction": 0.1, "beam": BEAM,
+                   "mpx_layout": "roots first within each utterance (the reference's root_chan array)"},
         "gpu_launches": int(launches),
         "issue": "b200_hmm_step_dev per frame" if single_steps else "b200_hmm_run_dev",
-        "survivor_fraction": {"first_timed_frame": float(np.sum(nk0)) / units, "last_timed_frame": float(np.sum(nk1)) / units},
+        "survivor_fraction": {"first_timed_frame": s0, "last_timed_frame": s1},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(pk) else "fallback"}}
-    ctx.free()
-    del sen
-    torch.cuda.empty_cache()
+    if both_layouts:
+        ms2, _, _, _ = _measure(b, torch, synth, d, tp, B, max(20, frames // 4), max(10, warmup // 4), single_steps, False)
+        res["interleaved_layout"] = {"us_per_frame": ms2 * 1e3, "frac": units * BYTES_PER_UNIT / (ms2 / 1e3) / 1e9 / peak,
+                                     "note": "multiplex and plain HMMs interleaved at random: every warp runs both flavours"}
     if cpu:
         try:
             res["cpu_baseline"] = cpu_reference(d, tp, cpu_frames)

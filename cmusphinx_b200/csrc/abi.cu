@@ -831,7 +831,7 @@ b200_hmmctx_t *b200_hmm_ctx_create(int n_emit, const uint8_t *tp, int n_tmat, co
     const int n_words = (n_sen + 31) / 32;
     if (dev_alloc_copy(&c->d_tp, tp, (size_t)n_tmat * n_emit * (n_emit + 1)) ||
         dev_alloc_copy(&c->d_sseq, sseq, (size_t)std::max(n_sseq, 1) * n_emit * (n_sseq > 0 ? 1 : 0)) ||
-        cudaMalloc((void **)&c->d_total, 4) != cudaSuccess || cudaMalloc((void **)&c->d_bar, 4) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_total, 4) != cudaSuccess || cudaMalloc((void **)&c->d_bar, (size_t)kHmmBarRows * 32 * sizeof(unsigned)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev[0]) != cudaSuccess || cudaEventCreate(&c->ev[1]) != cudaSuccess) {
         set_error("hmm context allocation failed"); b200_hmm_ctx_free(c); return nullptr;
@@ -932,7 +932,7 @@ static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, i
     r.mask_part = c->d_mask_part; r.mask_part_words = c->mask_part_cap;
     r.total = c->d_total; r.bar = c->d_bar;
     static long long *d_probe = nullptr;
-    if (getenv("B200_HMM_PROBE") && !d_probe) cudaMalloc((void **)&d_probe, 64);
+    if (getenv("B200_HMM_PROBE") && !d_probe) cudaMalloc((void **)&d_probe, 128);
     r.probe = d_probe;
     const int rc = hmm_launch_run(c->c, c->p, r, st);
     if (rc) return rc;
@@ -941,10 +941,11 @@ static int hmm_run(b200_hmmctx *c, const int16_t *d_senscr, long frame_stride, i
     c->mask_par = (r.mask0 + n_frames - 1) & 1;
     c->stepped = do_beam != 0;
     if (d_probe) {
-        long long h[6];
+        long long h[11];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_probe, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "hmm probe (cycles): A %lld  bar1 %lld  B %lld  bar2 %lld  C %lld\n", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+        fprintf(stderr, "hmm probe (cycles): A %lld  bar1 %lld  B %lld (mask merge %lld, beam votes %lld, counts %lld)  bar2 %lld  C %lld (counts in %lld, scan %lld, scatter %lld, mask out %lld)\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[6] - h[2], h[7] - h[6], h[3] - h[7], h[4] - h[3], h[5] - h[4], h[8] - h[4], h[9] - h[8], h[10] - h[9], h[5] - h[10]);
     }
     return B200_OK;
 }

@@ -24,6 +24,7 @@ struct HmmPop {               // SoA mirror of hmm_t (PS/hmm.h:156-173), state-m
 struct HmmFrame { int32_t best; int32_t n_keep; int32_t thresh; int32_t pad; };
 
 // one launch = a run of frames (see hmm_run_kernel)
+constexpr int kHmmBarRows = 4096;
 struct HmmRun {
     const int16_t *sen_base; long frame_stride; int n_cycle, frame0, n_frames;   // frame f scores: sen_base + ((frame0 + f) % n_cycle) * frame_stride + utt * n_sen
     int32_t beam; int do_beam;
@@ -35,7 +36,9 @@ struct HmmRun {
     uint32_t *mask2; int mask0;          // [2][n_utt][n_words], frame f uses (mask0 + f) & 1
     uint32_t *mask_part; size_t mask_part_words;   // [2][n_utt][gx][n_words] per-CTA partial masks
     int32_t *total;
-    unsigned *bar;                       // grid barrier counter
+    unsigned *bar;                       // barrier counters: [0] for the grid, [row * 32] per grid row (kHmmBarRows rows)
+    int pre_off;                         // set by the launcher: byte offset of phase A's prefetch slots in dynamic shared memory
+    int row_sync;                        // set by the launcher: barriers per grid row (see hmm_run_kernel)
     long long *probe;                    // development: phase time stamps of CTA 0 on the last frame (or null)
 };
 int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run, cudaStream_t st);

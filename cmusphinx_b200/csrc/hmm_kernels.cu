@@ -30,8 +30,28 @@ struct HmmRegs {
 // tp row-major [from][to] with n+1 columns, stored negated (uint8).
 template <int NE>
 __device__ __forceinline__ int32_t tpv(const uint8_t *tp, int i, int j) { return -(int32_t)tp[i * (NE + 1) + j]; }
+// The same matrix held in registers: hmm_run_kernel reads an HMM's whole matrix from shared memory with one or
+// two 16-byte loads (rows padded to kTpStride) instead of a byte load per use -- with a different matrix per lane
+// every byte load was a bank-conflicted wavefront of its own, ~18 per HMM and warp against 4 now, and the LSU
+// data pipe is what bounds phase A.
+template <int NE> struct TpRow { uint32_t w[(NE * (NE + 1) + 15) / 16 * 4]; };
+template <int NE> constexpr int kTpStride = (NE * (NE + 1) + 15) / 16 * 16;
+template <int NE>
+__device__ __forceinline__ int32_t tpv(const TpRow<NE> &tp, int i, int j) {
+    const int k = i * (NE + 1) + j;
+    return -(int32_t)((tp.w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+}
+template <int NE>
+__device__ __forceinline__ TpRow<NE> tp_row(const uint8_t *s_tp, int tm) {
+    TpRow<NE> t;
+    const uint4 *q = reinterpret_cast<const uint4 *>(s_tp + tm * kTpStride<NE>);
+#pragma unroll
+    for (int k = 0; k < kTpStride<NE> / 16; ++k) { const uint4 v = q[k]; t.w[4 * k] = v.x; t.w[4 * k + 1] = v.y; t.w[4 * k + 2] = v.z; t.w[4 * k + 3] = v.w; }
+    return t;
+}
 
-__device__ __forceinline__ void eval3(HmmRegs &h, const uint8_t *tp, const int16_t *sen) {
+template <class TP>
+__device__ __forceinline__ void eval3(HmmRegs &h, const TP &tp, const int16_t *sen) {
     int32_t s3, s2, s1, s0, t2, t1, t0, best;
     s2 = h.sc[2] - sen[h.sid[2]];
     s1 = h.sc[1] - sen[h.sid[1]];
@@ -73,7 +93,8 @@ __device__ __forceinline__ void eval3(HmmRegs &h, const uint8_t *tp, const int16
 
 #define MPX_SEN(st) sen[sseq[(size_t)h.sid[st] * NE + (st)]]
 
-__device__ __forceinline__ void eval3_mpx(HmmRegs &h, const uint8_t *tp, const int16_t *sen,
+template <class TP>
+__device__ __forceinline__ void eval3_mpx(HmmRegs &h, const TP &tp, const int16_t *sen,
                                           const uint16_t *__restrict__ sseq) {
     constexpr int NE = 3;
     int32_t s3, s2, s1, s0, t2, t1, t0, best;
@@ -127,7 +148,8 @@ __device__ __forceinline__ void eval3_mpx(HmmRegs &h, const uint8_t *tp, const i
     if (BT(S_TO, best)) best = S_TO;                                                 \
     h.sc[TO] = S_TO;
 
-__device__ __forceinline__ void eval5(HmmRegs &h, const uint8_t *tp, const int16_t *sen) {
+template <class TP>
+__device__ __forceinline__ void eval5(HmmRegs &h, const TP &tp, const int16_t *sen) {
     int32_t s5, s4, s3, s2, s1, s0, t2, t1, t0, best;
     best = kWorstScore;
     s4 = h.sc[4] - sen[h.sid[4]];
@@ -175,7 +197,8 @@ __device__ __forceinline__ void eval5(HmmRegs &h, const uint8_t *tp, const int16
     if (BT(S_TO, best)) best = S_TO;                                                  \
     h.sc[TO] = S_TO;
 
-__device__ __forceinline__ void eval5_mpx(HmmRegs &h, const uint8_t *tp, const int16_t *sen,
+template <class TP>
+__device__ __forceinline__ void eval5_mpx(HmmRegs &h, const TP &tp, const int16_t *sen,
                                           const uint16_t *__restrict__ sseq) {
     constexpr int NE = 5;
     int32_t s5, s4, s3, s2, s1, s0, t2, t1, t0, best;
@@ -241,8 +264,8 @@ constexpr int kHmmBlock = 256;
 // keep the earlier candidate (self loop, then from = to-1, to-2, ...).  As in the
 // reference, state 0's sum is not clamped, new scores are stored unclamped, and
 // a missing senone scores WORST_SCORE (hmm_senscr, hmm.h:198-200).
-template <int NE>
-__device__ __forceinline__ void eval_any(HmmRegs &h, const uint8_t *tp, const int16_t *sen, const uint16_t *sseq,
+template <int NE, class TP>
+__device__ __forceinline__ void eval_any(HmmRegs &h, const TP &tp, const int16_t *sen, const uint16_t *sseq,
                                          bool mpx) {
     int32_t st[NE];
 #pragma unroll
@@ -317,6 +340,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned n_cta, unsi
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// `ctr` / `n_cta`: the whole grid's counter, or -- in the row form -- the counter of this grid row and gridDim.x
 template <bool CL>
 __device__ __forceinline__ void sync_ctas(unsigned *ctr, unsigned n_cta, unsigned &epoch) {
     if (CL) cluster_barrier();
@@ -339,24 +363,49 @@ __device__ __forceinline__ int2 block_sum2(int a, int b, int32_t *s_red /* [2 * 
 // The active-senone mask of one utterance and frame: the OR of the partial masks its gx CTAs
 // stored with plain stores (merging them with atomicOr made every CTA of an utterance hammer
 // the same n_words addresses: 17 us per frame on 196 CTAs).  One thread per mask word.
+struct MergePlan { int L, per_pass, sub, slot, n_mine; };
+template <int BLK>
+__device__ __forceinline__ MergePlan merge_plan(int gx, int n_words, int w0, int wstep) {
+    // L lanes share a word (each ORs every L-th partial), BLK / L words per pass; this CTA owns the words
+    // w0, w0 + wstep, ...; L shrinks until one pass covers them (then every load of the merge is issued at once)
+    MergePlan m;
+    m.n_mine = w0 < n_words ? (n_words - w0 + wstep - 1) / wstep : 0;
+    int L = 1;
+    while (L < 32 && L < gx) L <<= 1;
+    while (L > 1 && BLK / L < m.n_mine) L >>= 1;
+    m.L = L; m.per_pass = BLK / L; m.sub = threadIdx.x % L; m.slot = threadIdx.x / L;
+    return m;
+}
+// first trip of pass j0: eight independent loads per lane (a plain loop waits for every partial in turn)
+__device__ __forceinline__ void merge_load(const MergePlan &m, const uint32_t *part_u, int gx, int n_words, int w0, int wstep,
+                                           int j0, int b0, uint32_t (&t)[8]) {
+    const int j = j0 + m.slot, kk = w0 + j * wstep;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int b = b0 + q * m.L; t[q] = (j < m.n_mine && b < gx) ? __ldcg(part_u + (size_t)b * n_words + kk) : 0u; }
+}
+// the rest of the merge; t holds the loads of (pass 0, first trip) issued earlier by merge_load
+template <int BLK>
+__device__ __forceinline__ void merge_finish(const MergePlan &m, const uint32_t *part_u, int gx, int n_words, uint32_t *mask_u,
+                                             int w0, int wstep, uint32_t (&t)[8]) {
+    for (int j0 = 0; j0 < m.n_mine; j0 += m.per_pass) {
+        const int j = j0 + m.slot, kk = w0 + j * wstep;
+        uint32_t v = 0;
+        for (int b0 = m.sub; b0 < gx; b0 += 8 * m.L) {
+            if (j0 != 0 || b0 != m.sub) merge_load(m, part_u, gx, n_words, w0, wstep, j0, b0, t);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v |= t[q];
+        }
+        for (int o = m.L >> 1; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if (j < m.n_mine && m.sub == 0) mask_u[kk] = v;
+    }
+}
 template <int BLK>
 __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_words] */, int gx, int n_words, uint32_t *mask_u,
                                            int w0, int wstep) {
-    // L lanes share a word (each ORs every L-th partial), 256 / L words per pass; this CTA owns
-    // the words w0, w0 + wstep, ...
-    int L = 1;
-    while (L < 32 && L < gx) L <<= 1;
-    const int per_pass = BLK / L, sub = threadIdx.x % L, slot = threadIdx.x / L;
-    const int n_mine = w0 < n_words ? (n_words - w0 + wstep - 1) / wstep : 0;
-    for (int j0 = 0; j0 < n_mine; j0 += per_pass) {
-        const int j = j0 + slot;
-        const int kk = w0 + j * wstep;
-        uint32_t v = 0;
-        if (j < n_mine)
-            for (int b = sub; b < gx; b += L) v |= part_u[(size_t)b * n_words + kk];
-        for (int o = L >> 1; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-        if (j < n_mine && sub == 0) mask_u[kk] = v;
-    }
+    const MergePlan m = merge_plan<BLK>(gx, n_words, w0, wstep);
+    uint32_t t[8];
+    merge_load(m, part_u, gx, n_words, w0, wstep, 0, m.sub, t);
+    merge_finish<BLK>(m, part_u, gx, n_words, mask_u, w0, wstep, t);
 }
 
 // BLK threads per CTA.  CL = false: cooperative launch, one resident wave of 256-thread CTAs, grid
@@ -367,39 +416,49 @@ __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_word
 // of streaming from HBM.  Only the last frame's survivor list has to be ordered across
 // utterances: the cluster form writes per-utterance lists (r.keep_tmp) and
 // hmm_compact_last_kernel packs them.
+constexpr int kPre = 3;             // HMMs per thread whose state loads phase A keeps in flight
+constexpr int kBeamBatch = 8;       // tiles whose bestscore loads phase B issues before its first vote
 template <int NE, int BLK, bool CL>
 __global__ void __launch_bounds__(BLK, BLK == 256 ? 4 : 1)
 hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
     const size_t sen_bytes = ((size_t)c.n_sen * 2 + 15) & ~(size_t)15;
-    const size_t tp_bytes = ((size_t)c.n_tmat * NE * (NE + 1) + 15) & ~(size_t)15;
+    const size_t tp_bytes = (size_t)c.n_tmat * kTpStride<NE>;      // one padded row per matrix
     uint8_t *s_tp = sm_raw + sen_bytes;
     uint32_t *s_flag_w = reinterpret_cast<uint32_t *>(sm_raw + sen_bytes + tp_bytes);   // one flag byte per senone
     uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
     // tile counts of one utterance | offsets of my tiles | keep ballots of my tiles (all my utterances)
-    const int rows = (r.tpu + (int)gridDim.x - 1) / (int)gridDim.x + 3;                 // my tiles per utterance (+ the 4-tile batch overrun)
+    const int rows = (r.tpu + (int)gridDim.x - 1) / (int)gridDim.x + kBeamBatch - 1;   // my tiles per utterance (+ the batch overrun)
     int32_t *s_tc = reinterpret_cast<int32_t *>(s_flag + (size_t)((c.n_sen + 31) / 32) * 32);
     int32_t *s_off = s_tc + r.tpu;
     uint32_t *s_bal = reinterpret_cast<uint32_t *>(s_off + rows);
+    int32_t *s_pre = reinterpret_cast<int32_t *>(sm_raw + r.pre_off);           // [kPre][2 NE + 2][BLK] phase A's prefetch slots
     __shared__ int32_t s_red[2 * (BLK / 32)];
     __shared__ int32_t s_wcnt[BLK / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gx = gridDim.x, gy = gridDim.y, bx = blockIdx.x, by = blockIdx.y;
-    const unsigned n_cta = (unsigned)gx * gy;
+    // Row form (r.row_sync, cooperative launch): utterances are independent, so only the gx CTAs of a grid ROW -- the
+    // ones that share utterances -- meet at a barrier; the rows drift apart and one row's latency-bound phases B / C
+    // overlap the others' streaming phase A.  Like the cluster form it leaves per-utterance survivor lists
+    // (hmm_compact_last_kernel packs the last frame's).
+    const bool row = !CL && r.row_sync != 0;
+    const bool own_list = CL || row;
+    const unsigned n_cta = row ? (unsigned)gx : (unsigned)gx * gy;
+    unsigned *const bar = row ? r.bar + (size_t)by * 32 : r.bar;
     const int n = p.n_hmm, n_utt = p.n_utt;
     const int n_words = (c.n_sen + 31) / 32;
     unsigned epoch = 0;
 
     {   // transition table once; frame records and the first mask
         const int ntp = c.n_tmat * NE * (NE + 1);
-        for (int i = tid; i < ntp; i += BLK) s_tp[i] = c.tp[i];
+        for (int i = tid; i < ntp; i += BLK) s_tp[(i / (NE * (NE + 1))) * kTpStride<NE> + i % (NE * (NE + 1))] = c.tp[i];
         if (bx == 0)
             for (int u = by; u < n_utt; u += gy) {
                 if (tid < 3) { HmmFrame f; f.best = kWorstScore; f.n_keep = 0; f.thresh = kWorstScore; f.pad = 0; r.fr3[(size_t)tid * n_utt + u] = f; }
             }
     }
-    sync_ctas<CL>(r.bar, n_cta, epoch);
+    sync_ctas<CL>(bar, n_cta, epoch);
 
     for (int u0 = by; u0 < (CL ? n_utt : by + 1); u0 += gy) {       // CL: one utterance at a time, all its frames
     const int u_lo = CL ? u0 : by, u_hi = CL ? u0 + 1 : n_utt;
@@ -423,31 +482,53 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             }
             __syncthreads();
             int32_t blockbest = kWorstScore;
-            // Software pipeline: the 13 loads of the NEXT HMM of this thread are issued before the current one is
-            // evaluated and stored, so every warp keeps loads in flight through its compute / store half as well
-            // (without it a warp's loads and stores alternate and phase A ran at 0.6 of the HBM rate).
-            auto load_hmm = [&](int i, HmmRegs &h, int &tm, bool &mpx) {
+            // Software pipeline through shared memory: a thread's 2 NE + 2 int32 values of its next kPre HMMs are in flight
+            // as 4-byte cp.async copies into slots only this thread touches (no barrier: cp.async.wait_group orders a thread's
+            // own copies), the five small fields of the next HMM as plain loads.  Against holding the whole next HMM in
+            // registers (13 loads, one deep) this keeps 2.5x the bytes in flight per thread with 6 fewer registers.
+            constexpr int NA = 2 * NE + 2;
+            uint32_t pre_base = (uint32_t)__cvta_generic_to_shared(s_pre) + tid * 4;
+            auto pre_issue = [&](int i, int slot) {
+                if (i < hi) {
+                    const uint32_t d = pre_base + slot * (NA * BLK * 4);
 #pragma unroll
-                for (int s = 0; s < NE; ++s) {
-                    h.sc[s] = p.score[(size_t)s * n + i];
-                    h.hi[s] = p.history[(size_t)s * n + i];
-                    h.sid[s] = p.senid[(size_t)s * n + i];
+                    for (int s = 0; s < NE; ++s) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + s * BLK * 4), "l"(p.score + (size_t)s * n + i) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + (NE + s) * BLK * 4), "l"(p.history + (size_t)s * n + i) : "memory");
+                    }
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 2 * NE * BLK * 4), "l"(p.out_score + i) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + (2 * NE + 1) * BLK * 4), "l"(p.out_history + i) : "memory");
                 }
-                h.out_sc = p.out_score[i];
-                h.out_hi = p.out_history[i];
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            auto load_small = [&](int i, HmmRegs &h, int &tm, bool &mpx) {
+#pragma unroll
+                for (int s = 0; s < NE; ++s) h.sid[s] = p.senid[(size_t)s * n + i];
                 tm = (int)p.tmatid[i];
                 mpx = p.mpx[i] != 0;
             };
+            const int step = gx * BLK;
             int i = lo + bx * BLK + tid;
+#pragma unroll
+            for (int d = 0; d < kPre; ++d) pre_issue(i + d * step, d);
             HmmRegs h; int tm = 0; bool mpx = false;
-            if (i < hi) load_hmm(i, h, tm, mpx);
+            if (i < hi) load_small(i, h, tm, mpx);
+            int slot = 0;
             while (i < hi) {
-                const int i_next = i + gx * BLK;
                 HmmRegs hn; int tm_n = 0; bool mpx_n = false;
-                if (i_next < hi) load_hmm(i_next, hn, tm_n, mpx_n);
-                const uint8_t *tp = s_tp + tm * NE * (NE + 1);
-                if (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
-                else if (NE == 5) { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
+                if (i + step < hi) load_small(i + step, hn, tm_n, mpx_n);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kPre - 1) : "memory");
+                {
+                    const int32_t *q = s_pre + (size_t)slot * NA * BLK + tid;
+#pragma unroll
+                    for (int s = 0; s < NE; ++s) { h.sc[s] = q[s * BLK]; h.hi[s] = q[(NE + s) * BLK]; }
+                    h.out_sc = q[2 * NE * BLK]; h.out_hi = q[(2 * NE + 1) * BLK];
+                }
+                pre_issue(i + kPre * step, slot);               // (the slot's values are in registers)
+                slot = slot + 1 == kPre ? 0 : slot + 1;
+                const TpRow<NE> tp = tp_row<NE>(s_tp, tm);
+                if constexpr (NE == 3) { if (mpx) eval3_mpx(h, tp, s_sen, c.sseq); else eval3(h, tp, s_sen); }
+                else if constexpr (NE == 5) { if (mpx) eval5_mpx(h, tp, s_sen, c.sseq); else eval5(h, tp, s_sen); }
                 else eval_any<NE>(h, tp, s_sen, c.sseq, mpx);
 #pragma unroll
                 for (int s = 0; s < NE; ++s) {
@@ -462,8 +543,11 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 p.out_history[i] = h.out_hi;
                 p.bestscore[i] = h.best;
                 blockbest = max(blockbest, h.best);
-                h = hn; tm = tm_n; mpx = mpx_n; i = i_next;
+#pragma unroll
+                for (int s = 0; s < NE; ++s) h.sid[s] = hn.sid[s];
+                tm = tm_n; mpx = mpx_n; i += step;
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             for (int o = 16; o > 0; o >>= 1) blockbest = max(blockbest, __shfl_xor_sync(0xffffffffu, blockbest, o));
             if (lane == 0) s_wcnt[w] = blockbest;
             __syncthreads();
@@ -475,7 +559,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
         }
         if (!r.do_beam) continue;                               // (eval only: one frame per launch)
         if (probe) r.probe[1] = clock64();
-        sync_ctas<CL>(r.bar, n_cta, epoch);
+        sync_ctas<CL>(bar, n_cta, epoch);
         if (probe) r.probe[2] = clock64();
 
         // ------------------------------------------------ B: beam test, counts
@@ -483,27 +567,32 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
         // ballots stay in shared memory for phase C (no keep-byte array, no second read).
         for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
-            if (f > 0)                                          // the previous frame's partial masks are complete (barrier 1)
-                merge_mask<BLK>(r.mask_part + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx * n_words, gx, n_words,
-                           r.mask2 + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * n_words, bx, gx);
+            // the previous frame's partial masks are complete (barrier 1): their loads are issued here and merged after the
+            // beam test -- nothing in this frame waits for that mask
+            const MergePlan mp_ = merge_plan<BLK>(gx, n_words, bx, gx);
+            const uint32_t *mpart = r.mask_part + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx * n_words;
+            uint32_t mt[8];
+            if (f > 0) merge_load(mp_, mpart, gx, n_words, bx, gx, 0, mp_.sub, mt);
             const int32_t thresh = fr[u].best + r.beam;
+            if (probe) r.probe[6] = clock64();
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
             uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
             int row = 0;
-            for (int t0 = bx; t0 < n_tiles; t0 += 4 * gx, row += 4) {
-                int32_t bs[4];
+            for (int t0 = bx; t0 < n_tiles; t0 += kBeamBatch * gx, row += kBeamBatch) {
+                int32_t bs[kBeamBatch];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kBeamBatch; ++j) {
                     const int i = lo + (t0 + j * gx) * BLK + tid;
                     bs[j] = (t0 + j * gx < n_tiles && i < hi) ? p.bestscore[i] : (int32_t)0x80000000;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < kBeamBatch; ++j) {
                     const unsigned bal = __ballot_sync(0xffffffffu, BT(bs[j], thresh));
                     if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * (BLK / 32) + w] = bal;
                 }
             }
             __syncthreads();
+            if (probe) r.probe[7] = clock64();
             int cta_cnt = 0;
             for (int rr = tid; bx + rr * gx < n_tiles; rr += BLK) {
                 int cnt = 0;
@@ -517,9 +606,10 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 if (cta_cnt) atomicAdd(&fr[u].n_keep, cta_cnt);
                 if (bx == 0) fr[u].thresh = thresh;
             }
+            if (f > 0) merge_finish<BLK>(mp_, mpart, gx, n_words, r.mask2 + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * n_words, bx, gx, mt);
         }
         if (probe) r.probe[3] = clock64();
-        sync_ctas<CL>(r.bar, n_cta, epoch);
+        sync_ctas<CL>(bar, n_cta, epoch);
         if (probe) r.probe[4] = clock64();
 
         // ------------------------------------------------ C: scatter + active senones
@@ -531,13 +621,14 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             const uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
             // survivors of the utterances before this one; the utterance's tile counts
             int part = 0;
-            if (!CL) for (int k = tid; k < u; k += BLK) part += fr[k].n_keep;
+            if (!own_list) for (int k = tid; k < u; k += BLK) part += fr[k].n_keep;
             for (int k = tid; k < n_tiles; k += BLK) s_tc[k] = r.tile_count[(size_t)u * r.tpu + k];
             const int base_all = block_sum2<BLK>(part, 0, s_red).x;  // (its barriers also publish s_tc)
-            const int base = CL ? lo : base_all;                     // CL: a list per utterance, packed after the run
-            int32_t *keep_dst = CL ? r.keep_tmp : r.keep_idx;
+            if (probe) r.probe[8] = clock64();
+            const int base = own_list ? lo : base_all;               // a list per utterance, packed after the run
+            int32_t *keep_dst = own_list ? r.keep_tmp : r.keep_idx;
             if (bx == 0 && tid == 0) {
-                if (!CL && u == n_utt - 1) *r.total = base + fr[u].n_keep;
+                if (!own_list && u == n_utt - 1) *r.total = base + fr[u].n_keep;
                 HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
                 fr_n2[u] = z;                                   // the record of the frame after next
             }
@@ -565,6 +656,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 for (int k = k0; k < k1; ++k) { const int v = s_tc[k]; s_tc[k] = run; run += v; }
             }
             __syncthreads();
+            if (probe) r.probe[9] = clock64();
             // four of my tiles at a time: every load of the batch is issued (unconditionally, on a
             // clamped index) before the first use
             for (int row0 = 0; bx + row0 * gx < n_tiles; row0 += 4) {
@@ -599,16 +691,19 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 }
             }
             __syncthreads();
-            for (int kk = w; kk < n_words; kk += BLK / 32) {      // warp-uniform loop
-                const unsigned word = __ballot_sync(0xffffffffu, s_flag[kk * 32 + lane] != 0);
-                if (lane == 0) part_u[kk] = word;
+            if (probe) r.probe[10] = clock64();
+            // 32 flag bytes (0 / 1) -> one mask word per thread: two 16-byte reads, a multiply packs four bytes into a nibble
+            for (int kk = tid; kk < n_words; kk += BLK) {
+                const uint4 a = reinterpret_cast<const uint4 *>(s_flag)[2 * kk], b = reinterpret_cast<const uint4 *>(s_flag)[2 * kk + 1];
+                auto nib = [](uint32_t x) { return (x * 0x01020408u) >> 24 & 0xfu; };
+                part_u[kk] = nib(a.x) | nib(a.y) << 4 | nib(a.z) << 8 | nib(a.w) << 12 | nib(b.x) << 16 | nib(b.y) << 20 | nib(b.z) << 24 | nib(b.w) << 28;
             }
             __syncthreads();
         }
         if (probe) r.probe[5] = clock64();
     }
     if (r.do_beam && r.n_frames > 0) {                          // the last frame's mask
-        sync_ctas<CL>(r.bar, n_cta, epoch);
+        sync_ctas<CL>(bar, n_cta, epoch);
         const int f = r.n_frames - 1;
         for (int u = u_lo; u < u_hi; u += gy)
             merge_mask<BLK>(r.mask_part + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx * n_words, gx, n_words,
@@ -636,9 +731,15 @@ hmm_compact_last_kernel(HmmPop p, const HmmFrame *__restrict__ fr, const int32_t
 }
 
 // ------------------------------------------------------------ host launcher
-static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
-    const int rows = (tpu + gx - 1) / gx + 3;
-    return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (((size_t)c.n_tmat * c.n_emit * (c.n_emit + 1) + 15) & ~(size_t)15) +
+static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk);
+static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk, int *pre_off = nullptr) {
+    const size_t base = (run_smem_base(c, tpu, gx, utts_per_cta, blk) + 15) & ~(size_t)15;
+    if (pre_off) *pre_off = (int)base;
+    return base + (size_t)kPre * (2 * c.n_emit + 2) * blk * 4;
+}
+static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
+    const int rows = (tpu + gx - 1) / gx + kBeamBatch - 1;
+    return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * ((c.n_emit * (c.n_emit + 1) + 15) / 16 * 16) +
            (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (blk / 32)) * 4 + 16;
 }
 
@@ -678,7 +779,7 @@ static int hmm_launch_run_cluster(const HmmDev &c, const HmmPop &p, const HmmRun
 #undef B200_SET
     }
     for (int cs = 16; cs >= 8; cs >>= 1) {
-        const size_t sh = run_smem(c, r.tpu, cs, 1, kClusterBlock);
+        const size_t sh = run_smem(c, r.tpu, cs, 1, kClusterBlock, &r.pre_off);
         if (sh > 200 * 1024) continue;
         if ((size_t)2 * p.n_utt * cs * ((c.n_sen + 31) / 32) > run_in.mask_part_words) continue;
         cudaLaunchConfig_t cfg{};
@@ -727,13 +828,13 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
     int n_sm = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    int gx = 1, gy = 1;
+    int gx = 1, gy = 1, pre_off = 0;
     size_t sh = 0;
     for (int per_sm_try = (c.n_emit == 3 ? 5 : 4); per_sm_try >= 1; --per_sm_try) {
         const int wave = per_sm_try * n_sm;
         gy = std::max(1, std::min(p.n_utt, wave));
         gx = std::max(1, std::min(bpu, wave / gy));
-        sh = run_smem(c, bpu, gx, (p.n_utt + gy - 1) / gy, kHmmBlock);
+        sh = run_smem(c, bpu, gx, (p.n_utt + gy - 1) / gy, kHmmBlock, &pre_off);
         if (sh > 200 * 1024) continue;
         int per_sm = 0;
         B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_run_kernel<NE, kHmmBlock, false>, kHmmBlock, sh));
@@ -742,17 +843,28 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
     }
     if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
     HmmRun r = run_in;
+    r.pre_off = pre_off;
     if ((size_t)2 * p.n_utt * gx * ((c.n_sen + 31) / 32) > run_in.mask_part_words) {
         set_error("hmm step: partial-mask buffer too small (%zu words)", run_in.mask_part_words);
         return B200_ERR_ARG;
     }
     HmmDev cc = c; HmmPop pp = p;
-    B200_CUDA_OK(cudaMemsetAsync(r.bar, 0, sizeof(unsigned), st));
+    // row barriers when there is more than one row and a run of frames to drift over (B200_HMM_ROWSYNC=0: grid barriers)
+    static int row_ok = -1;
+    if (row_ok < 0) { const char *e = getenv("B200_HMM_ROWSYNC"); row_ok = (e && atoi(e) == 0) ? 0 : 1; }
+    r.row_sync = (row_ok && r.do_beam && gy > 1 && r.n_frames > 1 && gy <= kHmmBarRows) ? 1 : 0;
+    B200_CUDA_OK(cudaMemsetAsync(r.bar, 0, r.row_sync ? (size_t)gy * 32 * sizeof(unsigned) : sizeof(unsigned), st));
     void *args[] = {(void *)&cc, (void *)&pp, (void *)&r};
     cudaError_t e = cudaSuccess;
     B200_HMM_NE(e = cudaLaunchCooperativeKernel((const void *)hmm_run_kernel<NE, kHmmBlock, false>, dim3(gx, gy), dim3(kHmmBlock), args, sh, st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     B200_CUDA_OK(e);
+    if (r.row_sync) {
+        const HmmFrame *fr_last = r.fr3 + (size_t)((r.slot0 + r.n_frames - 1) % 3) * p.n_utt;
+        hmm_compact_last_kernel<<<p.n_utt, 256, 0, st>>>(pp, fr_last, r.keep_tmp, r.keep_idx, r.total);
+        B200_LAUNCH_CHECK();
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return B200_OK;
 }
 #undef B200_HMM_NE
