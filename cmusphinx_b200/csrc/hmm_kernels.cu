@@ -433,6 +433,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     int32_t *s_tc = reinterpret_cast<int32_t *>(s_flag + (size_t)((c.n_sen + 31) / 32) * 32);
     int32_t *s_off = s_tc + r.tpu;
     uint32_t *s_bal = reinterpret_cast<uint32_t *>(s_off + rows);
+    constexpr int BS = BLK / 32 + BLK / 64;     // words per tile row: the warps' keep ballots, then their uint16 survivor prefixes
     int32_t *s_pre = reinterpret_cast<int32_t *>(sm_raw + r.pre_off);           // [kPre][2 NE + 2][BLK] phase A's prefetch slots
     __shared__ int32_t s_red[2 * (BLK / 32)];
     __shared__ int32_t s_wcnt[BLK / 32];
@@ -576,7 +577,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             const int32_t thresh = fr[u].best + r.beam;
             if (probe) r.probe[6] = clock64();
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
-            uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
+            uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * BS;
             int row = 0;
             for (int t0 = bx; t0 < n_tiles; t0 += kBeamBatch * gx, row += kBeamBatch) {
                 int32_t bs[kBeamBatch];
@@ -588,7 +589,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
 #pragma unroll
                 for (int j = 0; j < kBeamBatch; ++j) {
                     const unsigned bal = __ballot_sync(0xffffffffu, BT(bs[j], thresh));
-                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * (BLK / 32) + w] = bal;
+                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * BS + w] = bal;
                 }
             }
             __syncthreads();
@@ -596,8 +597,9 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             int cta_cnt = 0;
             for (int rr = tid; bx + rr * gx < n_tiles; rr += BLK) {
                 int cnt = 0;
+                uint16_t *pre = reinterpret_cast<uint16_t *>(bal_u + rr * BS + BLK / 32);     // survivors in the warps before warp k
 #pragma unroll
-                for (int k = 0; k < BLK / 32; ++k) cnt += __popc(bal_u[rr * (BLK / 32) + k]);
+                for (int k = 0; k < BLK / 32; ++k) { pre[k] = (uint16_t)cnt; cnt += __popc(bal_u[rr * BS + k]); }
                 r.tile_count[(size_t)u * r.tpu + bx + rr * gx] = cnt;
                 cta_cnt += cnt;
             }
@@ -618,7 +620,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
         for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
-            const uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * (BLK / 32);
+            const uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * BS;
             // survivors of the utterances before this one; the utterance's tile counts
             int part = 0;
             if (!own_list) for (int k = tid; k < u; k += BLK) part += fr[k].n_keep;
@@ -665,25 +667,26 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 for (int j = 0; j < 4; ++j) {
                     const int t = bx + (row0 + j) * gx;
                     idx[j] = lo + t * BLK + tid;
-                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * (BLK / 32) + w] >> lane) & 1u);
+                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * BS + w] >> lane) & 1u);
                     const int ii = min(idx[j], hi - 1);
                     mp[j] = p.mpx[ii] != 0;
 #pragma unroll
                     for (int s = 0; s < NE; ++s) sid[j][s] = p.senid[(size_t)s * n + ii];
                 }
+                if (__any_sync(0xffffffffu, mp[0] | mp[1] | mp[2] | mp[3])) {      // (most warps hold no multiplex HMM)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                    for (int s = 0; s < NE; ++s)
-                        if (mp[j]) sid[j][s] = (act[j] && sid[j][s] != B200_BAD_SSID) ? c.sseq[(size_t)sid[j][s] * NE + s] : 0xffffffffu;
+                        for (int s = 0; s < NE; ++s)
+                            if (mp[j]) sid[j][s] = (act[j] && sid[j][s] != B200_BAD_SSID) ? c.sseq[(size_t)sid[j][s] * NE + s] : 0xffffffffu;
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (!act[j]) continue;
                     const int row = row0 + j;
-                    const unsigned bal = bal_u[row * (BLK / 32) + w];
-                    int woff = 0;
-                    for (int k = 0; k < w; ++k) woff += __popc(bal_u[row * (BLK / 32) + k]);
+                    const unsigned bal = bal_u[row * BS + w];
+                    const int woff = reinterpret_cast<const uint16_t *>(bal_u + row * BS + BLK / 32)[w];   // (phase B's prefix)
                     keep_dst[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = idx[j];
 #pragma unroll
                     for (int s = 0; s < NE; ++s)
@@ -740,7 +743,7 @@ static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int b
 static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
     const int rows = (tpu + gx - 1) / gx + kBeamBatch - 1;
     return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * ((c.n_emit * (c.n_emit + 1) + 15) / 16 * 16) +
-           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (blk / 32)) * 4 + 16;
+           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (blk / 32 + blk / 64)) * 4 + 16;
 }
 
 #define B200_HMM_NE(...)                                   \
