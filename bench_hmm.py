@@ -121,6 +121,10 @@ def run(utts=64, frames=200, warmup=80, single_steps=False, cpu=True, cpu_frames
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_unit": BYTES_PER_UNIT, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(pk) else "fallback"}}
+    prof = os.path.join(ROOT, "profiles", "r2_ncu_hmm_run.json")
+    if B == 64 and os.path.exists(prof):       # the profiled shape: DRAM bytes per frame of one ncu --set full capture
+        res["roofline"]["traffic"] = json.load(open(prof))["per_frame"]["dram_bytes"]
+        res["roofline"]["traffic_source"] = "static: profiles/r2_ncu_hmm_run.json (dram__bytes_read + write of one 8-frame launch / 8)"
     if both_layouts:
         ms2, _, _, _ = _measure(b, torch, synth, d, tp, B, max(20, frames // 4), max(10, warmup // 4), single_steps, False)
         res["interleaved_layout"] = {"us_per_frame": ms2 * 1e3, "frac": units * BYTES_PER_UNIT / (ms2 / 1e3) / 1e9 / peak,
