@@ -780,7 +780,7 @@ int set_utts(b200_hmmctx *c, int n_utt, const int32_t *off) {
             c->mask_part_cap = need;
         }
     }
-    const size_t nb = (size_t)((mx + 255) / 256) * n_utt + 1;
+    const size_t nb = (size_t)2 * ((mx + 255) / 256) * n_utt + 1;     // (the resident kernel alternates between two sets of tile counts)
     if (nb > c->bc_cap) {
         cudaFree(c->d_block_count); c->d_block_count = nullptr; c->bc_cap = 0;
         B200_CUDA_OK(cudaMalloc((void **)&c->d_block_count, nb * 4));

@@ -733,6 +733,183 @@ hmm_compact_last_kernel(HmmPop p, const HmmFrame *__restrict__ fr, const int32_t
     for (int i = threadIdx.x; i < n; i += 256) keep_idx[base + i] = keep_tmp[lo + i];
 }
 
+// ------------------------------------------------------------ the resident form
+// When the whole population fits one HMM per thread of one resident wave (tiles of all utterances <= CTAs the device
+// keeps resident: the literal config 4, one utterance x 50 000 HMMs = 196 CTAs), a run of frames never re-reads the state:
+// every thread loads its HMM once, keeps it in registers through all frames of the run and stores it after the last one.
+// Per frame only the senone row (prefetched one frame ahead with cp.async into a second buffer), the frame records, the
+// tile counts, the survivor list and the partial masks move; phases, barriers (per utterance), records, masks and lists
+// are those of hmm_run_kernel's row form, which the same tests compare it with.
+template <int NE>
+__global__ void __launch_bounds__(kHmmBlock, 4)
+hmm_resident_kernel(HmmDev c, HmmPop p, HmmRun r) {
+    constexpr int BLK = kHmmBlock;
+    extern __shared__ uint8_t sm_raw[];
+    const size_t sen_bytes = ((size_t)c.n_sen * 2 + 15) & ~(size_t)15;
+    int16_t *s_sen2 = reinterpret_cast<int16_t *>(sm_raw);                       // two rows
+    uint8_t *s_tp = sm_raw + 2 * sen_bytes;
+    uint32_t *s_flag_w = reinterpret_cast<uint32_t *>(s_tp + (size_t)c.n_tmat * kTpStride<NE>);
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_flag_w);
+    __shared__ int32_t s_red[2 * (BLK / 32)];
+    __shared__ int32_t s_wcnt[BLK / 32];
+    __shared__ uint32_t s_bal[BLK / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gx = gridDim.x, bx = blockIdx.x, u = blockIdx.y;
+    const int n = p.n_hmm, n_utt = p.n_utt, n_words = (c.n_sen + 31) / 32;
+    unsigned *const bar = r.bar + (size_t)u * 32;
+    unsigned epoch = 0;
+    const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
+    const int n_tiles = (hi - lo + BLK - 1) / BLK;
+    const bool has = bx < n_tiles;                          // (a shorter utterance leaves some CTAs of its row without a tile)
+    const int i = lo + bx * BLK + tid;
+    const bool on = has && i < hi;
+    {
+        const int ntp = c.n_tmat * NE * (NE + 1);
+        for (int k = tid; k < ntp; k += BLK) s_tp[(k / (NE * (NE + 1))) * kTpStride<NE> + k % (NE * (NE + 1))] = c.tp[k];
+        if (bx == 0 && tid < 3) { HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0; r.fr3[(size_t)tid * n_utt + u] = z; }
+    }
+    HmmRegs h; int tm = 0; bool mpx = false;
+    h.best = kWorstScore;
+    if (on) {
+#pragma unroll
+        for (int s = 0; s < NE; ++s) { h.sc[s] = p.score[(size_t)s * n + i]; h.hi[s] = p.history[(size_t)s * n + i]; h.sid[s] = p.senid[(size_t)s * n + i]; }
+        h.out_sc = p.out_score[i]; h.out_hi = p.out_history[i];
+        tm = (int)p.tmatid[i]; mpx = p.mpx[i] != 0;
+    }
+    // the senone row of a frame -> buffer (frame & 1); 16-byte cp.async when the row allows it
+    auto row_of = [&](int f) { return r.sen_base + (size_t)((r.frame0 + f) % r.n_cycle) * r.frame_stride + (size_t)u * c.n_sen; };
+    auto stage_row = [&](int f) {
+        const int16_t *src = row_of(f);
+        int16_t *dst = s_sen2 + (size_t)(f & 1) * (sen_bytes / 2);
+        const int n16 = ((reinterpret_cast<size_t>(src) & 15) == 0) ? (c.n_sen * 2) / 16 : 0;
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+        for (int k = tid; k < n16; k += BLK)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + k * 16), "l"(reinterpret_cast<const int4 *>(src) + k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int k = n16 * 8 + tid; k < c.n_sen; k += BLK) dst[k] = src[k];
+    };
+    if (has) stage_row(0);
+    grid_barrier(bar, gx, epoch);
+
+    // ONE barrier per frame: the frame's best needs one (every HMM evaluated before the beam test), and the survivor
+    // list needs the tile counts of the whole utterance -- but nothing in frame f + 1 waits for the list or the mask of
+    // frame f, so phase C of frame f runs behind the barrier of frame f + 1, next to that frame's beam test, on what
+    // the thread kept of frame f in registers (its ballot, prefix and senone ids).  Iteration f: A(f) | barrier |
+    // B(f), C(f - 1), merge of the partial masks of f - 2.  Tile counts alternate between two buffers.
+    const int F = r.n_frames;
+    unsigned bal_p = 0; int woff_p = 0; uint32_t rid_p[NE];
+#pragma unroll
+    for (int s = 0; s < NE; ++s) rid_p[s] = 0xffffffffu;
+    for (int f = 0; f <= F; ++f) {
+        HmmFrame *fr = r.fr3 + (size_t)((r.slot0 + f) % 3) * n_utt;
+        uint32_t rid[NE];
+#pragma unroll
+        for (int s = 0; s < NE; ++s) rid[s] = 0xffffffffu;
+        // ------------------------------------------------ A(f)
+        if (has && f < F) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                // the row of frame f is complete; the other buffer's readers are done
+            if (f + 1 < F) stage_row(f + 1);
+            const int16_t *sen = s_sen2 + (size_t)(f & 1) * (sen_bytes / 2);
+            int32_t blockbest = kWorstScore;
+            if (on) {
+                const TpRow<NE> tp = tp_row<NE>(s_tp, tm);
+                if constexpr (NE == 3) { if (mpx) eval3_mpx(h, tp, sen, c.sseq); else eval3(h, tp, sen); }
+                else if constexpr (NE == 5) { if (mpx) eval5_mpx(h, tp, sen, c.sseq); else eval5(h, tp, sen); }
+                else eval_any<NE>(h, tp, sen, c.sseq, mpx);
+                blockbest = h.best;
+#pragma unroll
+                for (int s = 0; s < NE; ++s) {              // the senones this HMM activates if it survives the frame
+                    uint32_t id = h.sid[s];
+                    if (mpx) id = id != B200_BAD_SSID ? (uint32_t)c.sseq[(size_t)id * NE + s] : 0xffffffffu;
+                    rid[s] = id;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) blockbest = max(blockbest, __shfl_xor_sync(0xffffffffu, blockbest, o));
+            if (lane == 0) s_wcnt[w] = blockbest;
+            __syncthreads();
+            if (tid == 0) {
+                int32_t b = s_wcnt[0];
+                for (int k = 1; k < BLK / 32; ++k) b = max(b, s_wcnt[k]);
+                atomicMax(&fr[u].best, b);
+            }
+        }
+        grid_barrier(bar, gx, epoch);
+
+        // the partial masks of frame f - 2 are complete: loads now, merge at the end of the iteration
+        const MergePlan mp_ = merge_plan<BLK>(gx, n_words, bx, gx);
+        const uint32_t *mpart = r.mask_part + ((size_t)((r.mask0 + f - 2) & 1) * n_utt + u) * gx * n_words;
+        uint32_t mt[8];
+        if (f >= 2) merge_load(mp_, mpart, gx, n_words, bx, gx, 0, mp_.sub, mt);
+        // ------------------------------------------------ B(f)
+        unsigned bal = 0; int woff = 0;
+        if (f < F) {
+            if (bx == 0 && tid == 0) {
+                HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
+                (r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt)[u] = z;      // the record of the frame after next (its A follows the next barrier)
+            }
+            const int32_t thresh = __ldcg(&fr[u].best) + r.beam;
+            const bool keep = on && BT(h.best, thresh);
+            bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_bal[w] = bal;
+            __syncthreads();
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < BLK / 32; ++k) { const int pc = __popc(s_bal[k]); if (k < w) woff += pc; cnt += pc; }
+            if (tid == 0) {
+                if (has) r.tile_count[((size_t)(f & 1) * n_utt + u) * r.tpu + bx] = cnt;
+                if (cnt) atomicAdd(&fr[u].n_keep, cnt);
+                if (bx == 0) fr[u].thresh = thresh;
+            }
+        }
+        // ------------------------------------------------ C(f - 1)
+        if (f > 0) {
+            uint32_t *part_u = r.mask_part + (((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * gx + bx) * n_words;
+            if (!has) {
+                for (int k = tid; k < n_words; k += BLK) part_u[k] = 0u;
+            } else {
+                int before = 0;
+                for (int k = tid; k < bx; k += BLK) before += __ldcg(r.tile_count + ((size_t)((f - 1) & 1) * n_utt + u) * r.tpu + k);
+                for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
+                const int base = lo + block_sum2<BLK>(before, 0, s_red).x;      // (its barriers also publish the cleared flags and free s_bal)
+                if ((bal_p >> lane) & 1u) {
+                    r.keep_tmp[base + woff_p + __popc(bal_p & ((1u << lane) - 1u))] = i;
+#pragma unroll
+                    for (int s = 0; s < NE; ++s)
+                        if (rid_p[s] != 0xffffffffu) s_flag[rid_p[s]] = 1;
+                }
+                __syncthreads();
+                for (int kk = tid; kk < n_words; kk += BLK) {
+                    const uint4 a = reinterpret_cast<const uint4 *>(s_flag)[2 * kk], b = reinterpret_cast<const uint4 *>(s_flag)[2 * kk + 1];
+                    auto nib = [](uint32_t x) { return (x * 0x01020408u) >> 24 & 0xfu; };
+                    part_u[kk] = nib(a.x) | nib(a.y) << 4 | nib(a.z) << 8 | nib(a.w) << 12 | nib(b.x) << 16 | nib(b.y) << 20 | nib(b.z) << 24 | nib(b.w) << 28;
+                }
+            }
+        }
+        if (f >= 2) merge_finish<BLK>(mp_, mpart, gx, n_words, r.mask2 + ((size_t)((r.mask0 + f - 2) & 1) * n_utt + u) * n_words, bx, gx, mt);
+        bal_p = bal;                                        // the warp's keep ballot of frame f
+        woff_p = woff;
+#pragma unroll
+        for (int s = 0; s < NE; ++s) rid_p[s] = rid[s];
+    }
+    if (on) {                                               // the state goes back once
+#pragma unroll
+        for (int s = 0; s < NE; ++s) { p.score[(size_t)s * n + i] = h.sc[s]; p.history[(size_t)s * n + i] = h.hi[s]; }
+        if (mpx) {
+#pragma unroll
+            for (int s = 1; s < NE; ++s) p.senid[(size_t)s * n + i] = h.sid[s];
+        }
+        p.out_score[i] = h.out_sc; p.out_history[i] = h.out_hi; p.bestscore[i] = h.best;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    grid_barrier(bar, gx, epoch);
+    {
+        const int f = r.n_frames - 1;
+        merge_mask<BLK>(r.mask_part + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx * n_words, gx, n_words,
+                        r.mask2 + ((size_t)((r.mask0 + f) & 1) * n_utt + u) * n_words, bx, gx);
+    }
+}
+
 // ------------------------------------------------------------ host launcher
 static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk);
 static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk, int *pre_off = nullptr) {
@@ -809,11 +986,51 @@ static int hmm_launch_run_cluster(const HmmDev &c, const HmmPop &p, const HmmRun
     return 1;
 }
 
+// The resident form (see hmm_resident_kernel).  Returns 1 when it does not apply.
+static int hmm_launch_run_resident(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("B200_HMM_RESIDENT"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled || !run_in.do_beam || run_in.n_frames < 2 || p.n_utt > kHmmBarRows) return 1;
+    const int gx = (p.max_per_utt + kHmmBlock - 1) / kHmmBlock, gy = p.n_utt;
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if ((long)gx * gy > 8L * n_sm) return 1;
+    const size_t sh = 2 * (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * ((c.n_emit * (c.n_emit + 1) + 15) / 16 * 16) +
+                      (size_t)((c.n_sen + 31) / 32) * 32 + 16;
+    if (sh > 200 * 1024) return 1;
+    if ((size_t)2 * p.n_utt * gx * ((c.n_sen + 31) / 32) > run_in.mask_part_words) return 1;
+    static AttrOnce attr;
+    if (attr.need()) {
+        cudaError_t e = cudaSuccess;
+        B200_HMM_NE(e = cudaFuncSetAttribute(hmm_resident_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); B200_CUDA_OK(e);
+    }
+    int per_sm = 0;
+    B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_resident_kernel<NE>, kHmmBlock, sh));
+    if ((long)per_sm * n_sm < (long)gx * gy) return 1;
+    HmmRun r = run_in;
+    HmmDev cc = c; HmmPop pp = p;
+    B200_CUDA_OK(cudaMemsetAsync(r.bar, 0, (size_t)gy * 32 * sizeof(unsigned), st));
+    void *args[] = {(void *)&cc, (void *)&pp, (void *)&r};
+    cudaError_t e = cudaSuccess;
+    B200_HMM_NE(e = cudaLaunchCooperativeKernel((const void *)hmm_resident_kernel<NE>, dim3(gx, gy), dim3(kHmmBlock), args, sh, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    B200_CUDA_OK(e);
+    const HmmFrame *fr_last = r.fr3 + (size_t)((r.slot0 + r.n_frames - 1) % 3) * p.n_utt;
+    hmm_compact_last_kernel<<<p.n_utt, 256, 0, st>>>(pp, fr_last, r.keep_tmp, r.keep_idx, r.total);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
 int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaStream_t st) {
     if (p.n_hmm <= 0 || p.n_utt <= 0 || run_in.n_frames <= 0) return B200_OK;
     if (c.n_emit < 1 || c.n_emit > 5) { set_error("n_emit_state %d outside 1..5 (HMM_MAX_NSTATE)", c.n_emit); return B200_ERR_UNSUP; }
     {
         const int rc = hmm_launch_run_cluster(c, p, run_in, st);
+        if (rc != 1) return rc;
+    }
+    {
+        const int rc = hmm_launch_run_resident(c, p, run_in, st);
         if (rc != 1) return rc;
     }
     static AttrOnce attr;
