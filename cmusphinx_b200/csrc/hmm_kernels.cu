@@ -323,14 +323,17 @@ __device__ __forceinline__ void eval_any(HmmRegs &h, const TP &tp, const int16_t
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned n_cta, unsigned &epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        // release / acquire at gpu scope instead of two sequentially consistent fences around a relaxed atomic
         ++epoch;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         const unsigned target = epoch * n_cta;
         const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned *>(ctr) < target)
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v >= target) break;
             if (clock64() - t0 > 4000000000LL) __trap();        // a protocol bug must trap, not hang the box
-        __threadfence();
+        }
     }
     __syncthreads();
 }
@@ -841,6 +844,9 @@ hmm_resident_kernel(HmmDev c, HmmPop p, HmmRun r) {
         const uint32_t *mpart = r.mask_part + ((size_t)((r.mask0 + f - 2) & 1) * n_utt + u) * gx * n_words;
         uint32_t mt[8];
         if (f >= 2) merge_load(mp_, mpart, gx, n_words, bx, gx, 0, mp_.sub, mt);
+        int before = 0;                                     // survivors of frame f - 1 in the tiles ahead of mine (loads issued with the others)
+        if (f > 0 && has)
+            for (int k = tid; k < bx; k += BLK) before += __ldcg(r.tile_count + ((size_t)((f - 1) & 1) * n_utt + u) * r.tpu + k);
         // ------------------------------------------------ B(f)
         unsigned bal = 0; int woff = 0;
         if (f < F) {
@@ -868,8 +874,6 @@ hmm_resident_kernel(HmmDev c, HmmPop p, HmmRun r) {
             if (!has) {
                 for (int k = tid; k < n_words; k += BLK) part_u[k] = 0u;
             } else {
-                int before = 0;
-                for (int k = tid; k < bx; k += BLK) before += __ldcg(r.tile_count + ((size_t)((f - 1) & 1) * n_utt + u) * r.tpu + k);
                 for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
                 const int base = lo + block_sum2<BLK>(before, 0, s_red).x;      // (its barriers also publish the cleared flags and free s_bal)
                 if ((bal_p >> lane) & 1u) {
