@@ -818,7 +818,7 @@ class HmmContext:
 
     def run_dev(self, d_senscr: int, frame_stride: int, n_cycle: int, n_frames: int, beam: int, stream=None):
         """n_frames steps on device-resident senone scores (frame f at d_senscr + (f % n_cycle) * frame_stride
-        int16 elements); long runs replay a CUDA graph.  Read the last frame with step_results()."""
+        int16 elements) in one persistent launch.  Read the last frame with step_results()."""
         check(lib.b200_hmm_run_dev(self._h, d_senscr, int(frame_stride), int(n_cycle), int(n_frames), int(beam), stream),
               "hmm_run_dev")
 

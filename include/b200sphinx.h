@@ -364,10 +364,11 @@ int  b200_hmm_pop_set_utts(b200_hmmctx_t *c, int n_utt, const int32_t *utt_off);
  * b200_hmm_step_results. */
 /* n_frames consecutive b200_hmm_step_dev calls; frame f reads the senone scores at
  * d_senscr + (f % n_cycle) * frame_stride (int16 elements).  Same results as the
- * single steps; long runs are issued as replays of one instantiated CUDA graph of
- * >= 32 frames (a single-utterance population is launch-latency bound: 5 small
- * kernels per frame).  The results of the LAST frame are read with
- * b200_hmm_step_results. */
+ * single steps, issued as ONE persistent cooperative launch for the whole run
+ * (phases separated by barriers among the CTAs of an utterance; a population of at
+ * most one HMM per resident thread -- e.g. one utterance x 50 000 HMMs -- keeps its
+ * state in registers from the first frame to the last).  The results of the LAST
+ * frame are read with b200_hmm_step_results. */
 int  b200_hmm_run_dev(b200_hmmctx_t *c, const int16_t *d_senscr, long frame_stride,
                       int n_cycle, int n_frames, int32_t beam, void *stream);
 /* (n_emit_state may be 1..5 = HMM_MAX_NSTATE: 3 and 5 run the reference's unrolled

@@ -237,9 +237,9 @@ def test_hmm_maintenance_ops_match_sequential_reference():
 
 @pytest.mark.parametrize("n_utt", [1, 3])
 def test_run_of_frames_as_graph_replays_equals_single_steps(n_utt):
-    """b200_hmm_run_dev (a CUDA graph of >= 32 frames replayed, plus directly launched head and
-    tail frames) leaves exactly the population and the last-frame results of the same number of
-    b200_hmm_step_dev calls; a second run reuses the instantiated graph."""
+    """b200_hmm_run_dev (one persistent launch per run: hmm_resident_kernel for these populations, state in
+    registers and one barrier per frame; the single steps go through hmm_run_kernel) leaves exactly the
+    population and the last-frame results of the same number of b200_hmm_step_dev calls."""
     ne, n_sen, n_tmat, n_sseq, n, cyc, beam = 3, 800, 10, 2000, 4000, 8, -60000
     tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 7), 1e-4, orc.LOGBASE)
     d = synth.hmm_population(n, ne, n_sen, n_tmat, n_sseq, seed=21, mpx_fraction=0.15)
@@ -257,7 +257,7 @@ def test_run_of_frames_as_graph_replays_equals_single_steps(n_utt):
         ctxs.append(c)
     a, g = ctxs
     done = 0
-    for n_frames in (100, 75, 3):           # graph built, graph reused (with a tail), too short for a graph
+    for n_frames in (100, 75, 3, 2):
         for f in range(n_frames):
             a.step_dev_async(d_sen + ((f % cyc) * stride) * 2, beam)
         g.run_dev(d_sen, stride, cyc, n_frames, beam)
