@@ -419,10 +419,14 @@ __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_word
 // of streaming from HBM.  Only the last frame's survivor list has to be ordered across
 // utterances: the cluster form writes per-utterance lists (r.keep_tmp) and
 // hmm_compact_last_kernel packs them.
+#ifndef B200_RUN_CTAS
+#define B200_RUN_CTAS 4
+#endif
+constexpr int kRunCtasPerSm = B200_RUN_CTAS;
 constexpr int kPre = 3;             // HMMs per thread whose state loads phase A keeps in flight
 constexpr int kBeamBatch = 8;       // tiles whose bestscore loads phase B issues before its first vote
 template <int NE, int BLK, bool CL>
-__global__ void __launch_bounds__(BLK, BLK == 256 ? 4 : 1)
+__global__ void __launch_bounds__(BLK, BLK == 256 ? kRunCtasPerSm : 1)
 hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     extern __shared__ uint8_t sm_raw[];
     int16_t *s_sen = reinterpret_cast<int16_t *>(sm_raw);
