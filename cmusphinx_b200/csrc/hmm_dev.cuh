@@ -38,6 +38,7 @@ struct HmmRun {
     int32_t *total;
     unsigned *bar;                       // barrier counters: [0] for the grid, [row * 32] per grid row (kHmmBarRows rows)
     int pre_off;                         // set by the launcher: byte offset of phase A's prefetch slots in dynamic shared memory
+    int pair;                            // set by the launcher: phase A may take two adjacent HMMs per thread (see hmm_run_kernel)
     int row_sync;                        // set by the launcher: barriers per grid row (see hmm_run_kernel)
     long long *probe;                    // development: phase time stamps of CTA 0 on the last frame (or null)
 };

@@ -423,7 +423,7 @@ __device__ __forceinline__ void merge_mask(const uint32_t *part_u /* [gx][n_word
 #define B200_RUN_CTAS 4
 #endif
 constexpr int kRunCtasPerSm = B200_RUN_CTAS;
-constexpr int kPre = 3;             // HMMs per thread whose state loads phase A keeps in flight
+constexpr int kPre = 2;             // HMMs per thread whose state loads phase A keeps in flight
 constexpr int kBeamBatch = 8;       // tiles whose bestscore loads phase B issues before its first vote
 template <int NE, int BLK, bool CL>
 __global__ void __launch_bounds__(BLK, BLK == 256 ? kRunCtasPerSm : 1)
@@ -516,7 +516,97 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 mpx = p.mpx[i] != 0;
             };
             const int step = gx * BLK;
-            int i = lo + bx * BLK + tid;
+            // Pair form (NE <= 3, 256-thread CTAs, even n_hmm and utterance start): two of the CTA's FULL tiles per trip, half
+            // of the threads each, a thread taking two ADJACENT HMMs with 8-byte copies, loads and stores -- the same 13 + 9
+            // memory instructions (and their address arithmetic) now serve two HMMs, and the two evaluations are independent
+            // chains for the scheduler.  Left-over and ragged tiles go through the single loop below.
+            int k_done = 0;                                     // my tiles already evaluated
+            if constexpr (NE <= 3 && BLK == 256 && !CL) {
+                const int n_tiles_a = (hi - lo + BLK - 1) / BLK;
+                const int k_mine = (n_tiles_a - bx + gx - 1) / gx;
+                int k_full = k_mine;                            // my tiles that are complete
+                if (k_mine > 0 && bx + (k_mine - 1) * gx == n_tiles_a - 1 && ((hi - lo) % BLK) != 0) --k_full;
+                const int n_trips = (r.pair && ((n | lo) & 1) == 0) ? k_full / 2 : 0;
+                if (n_trips > 0) {
+                    constexpr int H = BLK / 2;
+                    const int q = tid / H, pi = tid % H;
+                    const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(s_pre) + tid * 8;
+                    auto i_of = [&](int trip) { return lo + (bx + (2 * trip + q) * gx) * BLK + 2 * pi; };
+                    auto issue2 = [&](int trip) {                  // ONE stage: the copies of trip t + 1 fly during trip t's evaluation
+                        if (trip < n_trips) {
+                            const int i2 = i_of(trip);
+                            const uint32_t d = pbase;
+#pragma unroll
+                            for (int s = 0; s < NE; ++s) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + s * BLK * 8), "l"(p.score + (size_t)s * n + i2) : "memory");
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + (NE + s) * BLK * 8), "l"(p.history + (size_t)s * n + i2) : "memory");
+                            }
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 2 * NE * BLK * 8), "l"(p.out_score + i2) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + (2 * NE + 1) * BLK * 8), "l"(p.out_history + i2) : "memory");
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    };
+                    uint32_t sidw[NE], tmw; uint32_t mpw;       // the small fields of both HMMs, packed as loaded
+                    auto small2 = [&](int trip) {
+                        const int i2 = i_of(trip);
+#pragma unroll
+                        for (int s = 0; s < NE; ++s) sidw[s] = *reinterpret_cast<const uint32_t *>(p.senid + (size_t)s * n + i2);
+                        tmw = *reinterpret_cast<const uint32_t *>(p.tmatid + i2);
+                        mpw = *reinterpret_cast<const uint16_t *>(p.mpx + i2);
+                    };
+                    issue2(0);
+                    small2(0);
+                    for (int trip = 0; trip < n_trips; ++trip) {
+                        const int i2 = i_of(trip);
+                        HmmRegs ha, hb;
+#pragma unroll
+                        for (int s = 0; s < NE; ++s) { ha.sid[s] = (uint16_t)(sidw[s] & 0xffffu); hb.sid[s] = (uint16_t)(sidw[s] >> 16); }
+                        const int tma = (int)(int16_t)(tmw & 0xffffu), tmb = (int)(int16_t)(tmw >> 16);
+                        const bool mpa = (mpw & 0xffu) != 0, mpb = (mpw >> 8) != 0;
+                        if (trip + 1 < n_trips) small2(trip + 1);
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        {
+                            const int2 *qq = reinterpret_cast<const int2 *>(s_pre) + tid;
+#pragma unroll
+                            for (int s = 0; s < NE; ++s) {
+                                const int2 a = qq[s * BLK], b = qq[(NE + s) * BLK];
+                                ha.sc[s] = a.x; hb.sc[s] = a.y; ha.hi[s] = b.x; hb.hi[s] = b.y;
+                            }
+                            const int2 a = qq[2 * NE * BLK], b = qq[(2 * NE + 1) * BLK];
+                            ha.out_sc = a.x; hb.out_sc = a.y; ha.out_hi = b.x; hb.out_hi = b.y;
+                        }
+                        issue2(trip + 1);                       // (the slot's values are in registers)
+                        {
+                            const TpRow<NE> tp = tp_row<NE>(s_tp, tma);
+                            if constexpr (NE == 3) { if (mpa) eval3_mpx(ha, tp, s_sen, c.sseq); else eval3(ha, tp, s_sen); }
+                            else eval_any<NE>(ha, tp, s_sen, c.sseq, mpa);
+                        }
+                        {
+                            const TpRow<NE> tp = tp_row<NE>(s_tp, tmb);
+                            if constexpr (NE == 3) { if (mpb) eval3_mpx(hb, tp, s_sen, c.sseq); else eval3(hb, tp, s_sen); }
+                            else eval_any<NE>(hb, tp, s_sen, c.sseq, mpb);
+                        }
+#pragma unroll
+                        for (int s = 0; s < NE; ++s) {
+                            *reinterpret_cast<int2 *>(p.score + (size_t)s * n + i2) = make_int2(ha.sc[s], hb.sc[s]);
+                            *reinterpret_cast<int2 *>(p.history + (size_t)s * n + i2) = make_int2(ha.hi[s], hb.hi[s]);
+                        }
+                        if (mpa | mpb) {                        // (a plain HMM's ids are unchanged: writing them back is harmless)
+#pragma unroll
+                            for (int s = 1; s < NE; ++s)
+                                *reinterpret_cast<uint32_t *>(p.senid + (size_t)s * n + i2) = (uint32_t)ha.sid[s] | ((uint32_t)hb.sid[s] << 16);
+                        }
+                        *reinterpret_cast<int2 *>(p.out_score + i2) = make_int2(ha.out_sc, hb.out_sc);
+                        *reinterpret_cast<int2 *>(p.out_history + i2) = make_int2(ha.out_hi, hb.out_hi);
+                        *reinterpret_cast<int2 *>(p.bestscore + i2) = make_int2(ha.best, hb.best);
+                        blockbest = max(blockbest, max(ha.best, hb.best));
+                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();                            // the single loop lays its 4-byte slots over other threads' 8-byte ones
+                    k_done = 2 * n_trips;
+                }
+            }
+            int i = lo + (bx + k_done * gx) * BLK + tid;
 #pragma unroll
             for (int d = 0; d < kPre; ++d) pre_issue(i + d * step, d);
             HmmRegs h; int tm = 0; bool mpx = false;
@@ -923,7 +1013,9 @@ static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, 
 static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk, int *pre_off = nullptr) {
     const size_t base = (run_smem_base(c, tpu, gx, utts_per_cta, blk) + 15) & ~(size_t)15;
     if (pre_off) *pre_off = (int)base;
-    return base + (size_t)kPre * (2 * c.n_emit + 2) * blk * 4;
+    // the single loop's kPre stages of 4-byte slots, or (NE <= 3) the pair loop's one stage of 8-byte slots (16 kB either way for NE = 3:
+    // four CTAs then fit the 164 kB shared-memory carve-out and the L1 keeps 92 kB -- with 32 kB of slots it drops to 28 kB and phase A runs 50 % slower)
+    return base + std::max((size_t)kPre * (2 * c.n_emit + 2) * blk * 4, c.n_emit <= 3 ? (size_t)(2 * c.n_emit + 2) * blk * 8 : (size_t)0);
 }
 static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
     const int rows = (tpu + gx - 1) / gx + kBeamBatch - 1;
@@ -1072,6 +1164,11 @@ int hmm_launch_run(const HmmDev &c, const HmmPop &p, const HmmRun &run_in, cudaS
     if (sh > 200 * 1024) { set_error("hmm step needs %zu B shared memory", sh); return B200_ERR_UNSUP; }
     HmmRun r = run_in;
     r.pre_off = pre_off;
+    {
+        static int pair_on = -1;
+        if (pair_on < 0) { const char *e = getenv("B200_HMM_PAIR"); pair_on = (e && atoi(e) == 0) ? 0 : 1; }
+        r.pair = pair_on;
+    }
     if ((size_t)2 * p.n_utt * gx * ((c.n_sen + 31) / 32) > run_in.mask_part_words) {
         set_error("hmm step: partial-mask buffer too small (%zu words)", run_in.mask_part_words);
         return B200_ERR_ARG;
