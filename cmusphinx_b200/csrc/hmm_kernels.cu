@@ -1103,7 +1103,12 @@ static int hmm_launch_run_resident(const HmmDev &c, const HmmPop &p, const HmmRu
     static AttrOnce attr;
     if (attr.need()) {
         cudaError_t e = cudaSuccess;
-        B200_HMM_NE(e = cudaFuncSetAttribute(hmm_resident_kernel<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); B200_CUDA_OK(e);
+        // (every instantiation: the once-flag is per device, not per NE)
+        e = cudaFuncSetAttribute(hmm_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_resident_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_resident_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_resident_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
+        e = cudaFuncSetAttribute(hmm_resident_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); B200_CUDA_OK(e);
     }
     int per_sm = 0;
     B200_HMM_NE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hmm_resident_kernel<NE>, kHmmBlock, sh));

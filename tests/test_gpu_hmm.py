@@ -290,3 +290,35 @@ def test_cluster_form_of_the_run_kernel_gives_the_same_results():
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+@pytest.mark.parametrize("ne", [1, 2, 4, 5])
+def test_run_of_frames_resident_kernel_every_topology(ne):
+    """hmm_resident_kernel<NE> for the other numbers of emitting states (eval_any / eval5): a run of frames against
+    the same number of single steps, two utterances with a ragged last tile each."""
+    n_sen, n_tmat, n_sseq, n, cyc, beam, n_frames = 700, 9, 1500, 3001, 3, -50000, 7
+    tp = orc.port_tmat_quantize(synth.bakis_tmat(n_tmat, ne, 5), 1e-4, orc.LOGBASE)
+    d = synth.hmm_population(n, ne, n_sen, n_tmat, n_sseq, seed=40 + ne, mpx_fraction=0.2)
+    off = np.array([0, 1301, n], np.int32)
+    sen = np.ascontiguousarray(synth.senscr_frames(cyc * 2, n_sen, 33).reshape(cyc, 2, n_sen))
+    d_sen = b.lib.b200_dev_alloc(sen.nbytes, 0)
+    assert d_sen
+    b.engine.check(b.lib.b200_dev_upload(d_sen, sen.ctypes.data, sen.nbytes), "upload")
+    ctxs = []
+    for _ in range(2):
+        c = b.HmmContext(ne, tp, d["sseq"], n_sen)
+        c.upload(_to_pop(d, ne))
+        c.set_utts(off)
+        ctxs.append(c)
+    a, g = ctxs
+    for f in range(n_frames):
+        a.step_dev_async(d_sen + ((f % cyc) * 2 * n_sen) * 2, beam)
+    g.run_dev(d_sen, 2 * n_sen, cyc, n_frames, beam)
+    for x, y in zip(a.step_results(n), g.step_results(n)):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+    pa, pg = b.HmmPopulation(n, ne), b.HmmPopulation(n, ne)
+    a.download(pa); g.download(pg)
+    for k in ("score", "history", "out_score", "out_history", "bestscore", "senid"):
+        np.testing.assert_array_equal(getattr(pa, k), getattr(pg, k), err_msg=k)
+    a.free(); g.free()
+    b.lib.b200_dev_free(d_sen)
