@@ -675,18 +675,45 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             if (probe) r.probe[6] = clock64();
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
             uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * BS;
-            int row = 0;
-            for (int t0 = bx; t0 < n_tiles; t0 += kBeamBatch * gx, row += kBeamBatch) {
-                int32_t bs[kBeamBatch];
+            uint32_t *part_u = r.mask_part + (((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx + bx) * n_words;
+            for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
+            __syncthreads();                                    // (the flags are clear before the first survivor sets one)
+            // Four of my tiles at a time: bestscore, mpx and the senone ids of every HMM are loaded together (unconditionally,
+            // on a clamped index), then the beam vote, and the survivors flag their senones -- acmod_activate_hmm needs only
+            // the keep bits, not the survivors' positions in the list, so it runs here and not behind the second barrier
+            // with the scatter: its loads share the round trip of the beam test's.
+            for (int row0 = 0; bx + row0 * gx < n_tiles; row0 += 4) {
+                int32_t bs[4]; uint32_t sid[4][NE]; bool mp[4], act[4];
 #pragma unroll
-                for (int j = 0; j < kBeamBatch; ++j) {
-                    const int i = lo + (t0 + j * gx) * BLK + tid;
-                    bs[j] = (t0 + j * gx < n_tiles && i < hi) ? p.bestscore[i] : (int32_t)0x80000000;
+                for (int j = 0; j < 4; ++j) {
+                    const int t = bx + (row0 + j) * gx;
+                    const int i = lo + t * BLK + tid;
+                    const int ii = min(i, hi - 1);
+                    bs[j] = (t < n_tiles && i < hi) ? p.bestscore[ii] : (int32_t)0x80000000;
+                    mp[j] = p.mpx[ii] != 0;
+#pragma unroll
+                    for (int s = 0; s < NE; ++s) sid[j][s] = p.senid[(size_t)s * n + ii];
                 }
 #pragma unroll
-                for (int j = 0; j < kBeamBatch; ++j) {
-                    const unsigned bal = __ballot_sync(0xffffffffu, BT(bs[j], thresh));
-                    if (lane == 0 && t0 + j * gx < n_tiles) bal_u[(row + j) * BS + w] = bal;
+                for (int j = 0; j < 4; ++j) {
+                    act[j] = BT(bs[j], thresh);
+                    const unsigned bal = __ballot_sync(0xffffffffu, act[j]);
+                    if (lane == 0 && bx + (row0 + j) * gx < n_tiles) bal_u[(row0 + j) * BS + w] = bal;
+                }
+                if (__any_sync(0xffffffffu, mp[0] | mp[1] | mp[2] | mp[3])) {      // (most warps hold no multiplex HMM)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int s = 0; s < NE; ++s)
+                            if (mp[j]) sid[j][s] = (act[j] && sid[j][s] != B200_BAD_SSID) ? c.sseq[(size_t)sid[j][s] * NE + s] : 0xffffffffu;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!act[j]) continue;
+#pragma unroll
+                    for (int s = 0; s < NE; ++s)
+                        if (sid[j][s] != 0xffffffffu) s_flag[sid[j][s]] = 1;
                 }
             }
             __syncthreads();
@@ -705,14 +732,21 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 if (cta_cnt) atomicAdd(&fr[u].n_keep, cta_cnt);
                 if (bx == 0) fr[u].thresh = thresh;
             }
+            // this CTA's partial mask of the frame (the block_sum2 barriers above publish the flags): 32 flag bytes (0 / 1) -> one
+            // mask word per thread, two 16-byte reads and a multiply that packs four bytes into a nibble
+            for (int kk = tid; kk < n_words; kk += BLK) {
+                const uint4 a = reinterpret_cast<const uint4 *>(s_flag)[2 * kk], b = reinterpret_cast<const uint4 *>(s_flag)[2 * kk + 1];
+                auto nib = [](uint32_t x) { return (x * 0x01020408u) >> 24 & 0xfu; };
+                part_u[kk] = nib(a.x) | nib(a.y) << 4 | nib(a.z) << 8 | nib(a.w) << 12 | nib(b.x) << 16 | nib(b.y) << 20 | nib(b.z) << 24 | nib(b.w) << 28;
+            }
             if (f > 0) merge_finish<BLK>(mp_, mpart, gx, n_words, r.mask2 + ((size_t)((r.mask0 + f - 1) & 1) * n_utt + u) * n_words, bx, gx, mt);
+            __syncthreads();                                    // (the next utterance of this CTA clears the flags)
         }
         if (probe) r.probe[3] = clock64();
         sync_ctas<CL>(bar, n_cta, epoch);
         if (probe) r.probe[4] = clock64();
 
-        // ------------------------------------------------ C: scatter + active senones
-        uint32_t *part_f = r.mask_part + (size_t)((r.mask0 + f) & 1) * n_utt * gx * n_words;
+        // ------------------------------------------------ C: scatter
         HmmFrame *fr_n2 = r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt;
         for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
@@ -731,15 +765,9 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
                 fr_n2[u] = z;                                   // the record of the frame after next
             }
-            uint32_t *part_u = part_f + ((size_t)u * gx + bx) * n_words;
-            if (bx >= n_tiles) {                                // (uniform) no tile of this utterance: an empty partial mask
-                for (int k = tid; k < n_words; k += BLK) part_u[k] = 0u;
-                continue;
-            }
-            for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
+            if (bx >= n_tiles) continue;                        // (uniform) no tile of this utterance
             // exclusive scan of the utterance's tile counts, in place (one pass: a chunk per thread,
             // then a scan of the 256 chunk sums)
-            __syncthreads();
             {
                 const int per = (n_tiles + BLK - 1) / BLK;
                 const int k0 = min(n_tiles, tid * per), k1 = min(n_tiles, k0 + per);
@@ -755,50 +783,16 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 for (int k = k0; k < k1; ++k) { const int v = s_tc[k]; s_tc[k] = run; run += v; }
             }
             __syncthreads();
-            if (probe) r.probe[9] = clock64();
-            // four of my tiles at a time: every load of the batch is issued (unconditionally, on a
-            // clamped index) before the first use
-            for (int row0 = 0; bx + row0 * gx < n_tiles; row0 += 4) {
-                bool act[4]; int idx[4]; uint32_t sid[4][NE]; bool mp[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int t = bx + (row0 + j) * gx;
-                    idx[j] = lo + t * BLK + tid;
-                    act[j] = t < n_tiles && ((bal_u[(row0 + j) * BS + w] >> lane) & 1u);
-                    const int ii = min(idx[j], hi - 1);
-                    mp[j] = p.mpx[ii] != 0;
-#pragma unroll
-                    for (int s = 0; s < NE; ++s) sid[j][s] = p.senid[(size_t)s * n + ii];
-                }
-                if (__any_sync(0xffffffffu, mp[0] | mp[1] | mp[2] | mp[3])) {      // (most warps hold no multiplex HMM)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                        for (int s = 0; s < NE; ++s)
-                            if (mp[j]) sid[j][s] = (act[j] && sid[j][s] != B200_BAD_SSID) ? c.sseq[(size_t)sid[j][s] * NE + s] : 0xffffffffu;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!act[j]) continue;
-                    const int row = row0 + j;
-                    const unsigned bal = bal_u[row * BS + w];
-                    const int woff = reinterpret_cast<const uint16_t *>(bal_u + row * BS + BLK / 32)[w];   // (phase B's prefix)
-                    keep_dst[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = idx[j];
-#pragma unroll
-                    for (int s = 0; s < NE; ++s)
-                        if (sid[j][s] != 0xffffffffu) s_flag[sid[j][s]] = 1;
+            if (probe) { r.probe[9] = clock64(); r.probe[10] = r.probe[9]; }
+            // the survivors' indices, in order: tile offset + the warp's prefix (phase B) + the lane's rank in its ballot
+            for (int row = 0; bx + row * gx < n_tiles; ++row) {
+                const unsigned bal = bal_u[row * BS + w];
+                if ((bal >> lane) & 1u) {
+                    const int woff = reinterpret_cast<const uint16_t *>(bal_u + row * BS + BLK / 32)[w];
+                    keep_dst[s_tc[bx + row * gx] + woff + __popc(bal & ((1u << lane) - 1u))] = lo + (bx + row * gx) * BLK + tid;
                 }
             }
-            __syncthreads();
-            if (probe) r.probe[10] = clock64();
-            // 32 flag bytes (0 / 1) -> one mask word per thread: two 16-byte reads, a multiply packs four bytes into a nibble
-            for (int kk = tid; kk < n_words; kk += BLK) {
-                const uint4 a = reinterpret_cast<const uint4 *>(s_flag)[2 * kk], b = reinterpret_cast<const uint4 *>(s_flag)[2 * kk + 1];
-                auto nib = [](uint32_t x) { return (x * 0x01020408u) >> 24 & 0xfu; };
-                part_u[kk] = nib(a.x) | nib(a.y) << 4 | nib(a.z) << 8 | nib(a.w) << 12 | nib(b.x) << 16 | nib(b.y) << 20 | nib(b.z) << 24 | nib(b.w) << 28;
-            }
-            __syncthreads();
+            __syncthreads();                                    // (s_tc is rewritten for the next utterance of this CTA)
         }
         if (probe) r.probe[5] = clock64();
     }
