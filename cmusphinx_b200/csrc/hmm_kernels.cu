@@ -452,6 +452,11 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
     // (hmm_compact_last_kernel packs the last frame's).
     const bool row = !CL && r.row_sync != 0;
     const bool own_list = CL || row;
+    // Row form over a run of frames: ONE barrier per frame.  The frame's best needs one (every HMM evaluated before the beam
+    // test) and the survivor list needs the tile counts of the whole utterance -- but nothing in frame f + 1 waits for the list
+    // of frame f, and phase C reads shared memory and the tile counts only: it runs behind the barrier of frame f + 1, after
+    // that frame's phase B, on the ballots / tile counts of the other parity.
+    const bool defer = row && r.n_frames >= 2;
     const unsigned n_cta = row ? (unsigned)gx : (unsigned)gx * gy;
     unsigned *const bar = row ? r.bar + (size_t)by * 32 : r.bar;
     const int n = p.n_hmm, n_utt = p.n_utt;
@@ -470,13 +475,14 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
 
     for (int u0 = by; u0 < (CL ? n_utt : by + 1); u0 += gy) {       // CL: one utterance at a time, all its frames
     const int u_lo = CL ? u0 : by, u_hi = CL ? u0 + 1 : n_utt;
-    for (int f = 0; f < r.n_frames; ++f) {
+    for (int f = 0; f < r.n_frames + (defer ? 1 : 0); ++f) {    // (deferred: one more turn for the last frame's phase C)
+        const bool live = f < r.n_frames;
         const bool probe = r.probe && f == r.n_frames - 1 && bx == 0 && by == 0 && tid == 0;
         if (probe) r.probe[0] = clock64();
         HmmFrame *fr = r.fr3 + (size_t)((r.slot0 + f) % 3) * n_utt;
         const int16_t *sen_frame = r.sen_base + (size_t)((r.frame0 + f) % r.n_cycle) * r.frame_stride;
         // ------------------------------------------------ A: hmm_vit_eval
-        for (int u = u_lo; u < u_hi; u += gy) {
+        for (int u = u_lo; live && u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
             if (lo + bx * BLK >= hi) continue;            // uniform per block
             const int16_t *senscr = sen_frame + (size_t)u * c.n_sen;
@@ -663,7 +669,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
         // ------------------------------------------------ B: beam test, counts
         // All loads of the CTA's tiles of an utterance are issued before the first vote; the keep
         // ballots stay in shared memory for phase C (no keep-byte array, no second read).
-        for (int u = u_lo; u < u_hi; u += gy) {
+        for (int u = u_lo; live && u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
             // the previous frame's partial masks are complete (barrier 1): their loads are issued here and merged after the
             // beam test -- nothing in this frame waits for that mask
@@ -674,7 +680,7 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             const int32_t thresh = fr[u].best + r.beam;
             if (probe) r.probe[6] = clock64();
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
-            uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * BS;
+            uint32_t *bal_u = s_bal + ((size_t)(defer ? (f & 1) * ((n_utt + gy - 1) / gy) : 0) + (CL ? 0 : (u - by) / gy)) * rows * BS;
             uint32_t *part_u = r.mask_part + (((size_t)((r.mask0 + f) & 1) * n_utt + u) * gx + bx) * n_words;
             for (int k = tid; k < n_words * 8; k += BLK) s_flag_w[k] = 0u;
             __syncthreads();                                    // (the flags are clear before the first survivor sets one)
@@ -724,13 +730,17 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 uint16_t *pre = reinterpret_cast<uint16_t *>(bal_u + rr * BS + BLK / 32);     // survivors in the warps before warp k
 #pragma unroll
                 for (int k = 0; k < BLK / 32; ++k) { pre[k] = (uint16_t)cnt; cnt += __popc(bal_u[rr * BS + k]); }
-                r.tile_count[(size_t)u * r.tpu + bx + rr * gx] = cnt;
+                r.tile_count[((size_t)(defer ? (f & 1) : 0) * n_utt + u) * r.tpu + bx + rr * gx] = cnt;
                 cta_cnt += cnt;
             }
             cta_cnt = block_sum2<BLK>(cta_cnt, 0, s_red).x;
             if (tid == 0) {
                 if (cta_cnt) atomicAdd(&fr[u].n_keep, cta_cnt);
                 if (bx == 0) fr[u].thresh = thresh;
+                if (defer && bx == 0) {                         // the record of the frame after next (its phase A follows the next barrier)
+                    HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
+                    (r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt)[u] = z;
+                }
             }
             // this CTA's partial mask of the frame (the block_sum2 barriers above publish the flags): 32 flag bytes (0 / 1) -> one
             // mask word per thread, two 16-byte reads and a multiply that packs four bytes into a nibble
@@ -743,27 +753,28 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
             __syncthreads();                                    // (the next utterance of this CTA clears the flags)
         }
         if (probe) r.probe[3] = clock64();
-        sync_ctas<CL>(bar, n_cta, epoch);
-        if (probe) r.probe[4] = clock64();
-
-        // ------------------------------------------------ C: scatter
-        HmmFrame *fr_n2 = r.fr3 + (size_t)((r.slot0 + f + 2) % 3) * n_utt;
+        // ------------------------------------------------ C: scatter (of frame g)
+        auto phase_c = [&](int g) {
+        HmmFrame *fr_n2 = r.fr3 + (size_t)((r.slot0 + g + 2) % 3) * n_utt;
+        HmmFrame *fr = r.fr3 + (size_t)((r.slot0 + g) % 3) * n_utt;
         for (int u = u_lo; u < u_hi; u += gy) {
             const int lo = p.utt_off[u], hi = p.utt_off[u + 1];
             const int n_tiles = (hi - lo + BLK - 1) / BLK;
-            const uint32_t *bal_u = s_bal + (size_t)(CL ? 0 : (u - by) / gy) * rows * BS;
+            const uint32_t *bal_u = s_bal + ((size_t)(defer ? (g & 1) * ((n_utt + gy - 1) / gy) : 0) + (CL ? 0 : (u - by) / gy)) * rows * BS;
             // survivors of the utterances before this one; the utterance's tile counts
             int part = 0;
             if (!own_list) for (int k = tid; k < u; k += BLK) part += fr[k].n_keep;
-            for (int k = tid; k < n_tiles; k += BLK) s_tc[k] = r.tile_count[(size_t)u * r.tpu + k];
+            for (int k = tid; k < n_tiles; k += BLK) s_tc[k] = __ldcg(r.tile_count + ((size_t)(defer ? (g & 1) : 0) * n_utt + u) * r.tpu + k);
             const int base_all = block_sum2<BLK>(part, 0, s_red).x;  // (its barriers also publish s_tc)
             if (probe) r.probe[8] = clock64();
             const int base = own_list ? lo : base_all;               // a list per utterance, packed after the run
             int32_t *keep_dst = own_list ? r.keep_tmp : r.keep_idx;
             if (bx == 0 && tid == 0) {
                 if (!own_list && u == n_utt - 1) *r.total = base + fr[u].n_keep;
-                HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
-                fr_n2[u] = z;                                   // the record of the frame after next
+                if (!defer) {
+                    HmmFrame z; z.best = kWorstScore; z.n_keep = 0; z.thresh = kWorstScore; z.pad = 0;
+                    fr_n2[u] = z;                               // the record of the frame after next
+                }
             }
             if (bx >= n_tiles) continue;                        // (uniform) no tile of this utterance
             // exclusive scan of the utterance's tile counts, in place (one pass: a chunk per thread,
@@ -793,6 +804,15 @@ hmm_run_kernel(HmmDev c, HmmPop p, HmmRun r) {
                 }
             }
             __syncthreads();                                    // (s_tc is rewritten for the next utterance of this CTA)
+        }
+        };
+        if (!defer) {
+            sync_ctas<CL>(bar, n_cta, epoch);
+            if (probe) r.probe[4] = clock64();
+            phase_c(f);
+        } else {
+            if (probe) r.probe[4] = clock64();
+            if (f > 0) phase_c(f - 1);
         }
         if (probe) r.probe[5] = clock64();
     }
@@ -1014,7 +1034,7 @@ static size_t run_smem(const HmmDev &c, int tpu, int gx, int utts_per_cta, int b
 static size_t run_smem_base(const HmmDev &c, int tpu, int gx, int utts_per_cta, int blk) {
     const int rows = (tpu + gx - 1) / gx + kBeamBatch - 1;
     return (((size_t)c.n_sen * 2 + 15) & ~(size_t)15) + (size_t)c.n_tmat * ((c.n_emit * (c.n_emit + 1) + 15) / 16 * 16) +
-           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)utts_per_cta * rows * (blk / 32 + blk / 64)) * 4 + 16;
+           (size_t)((c.n_sen + 31) / 32) * 32 + ((size_t)tpu + rows + (size_t)2 * utts_per_cta * rows * (blk / 32 + blk / 64)) * 4 + 16;      // (ballots of two frames: see `defer`)
 }
 
 #define B200_HMM_NE(...)                                   \
